@@ -1,0 +1,141 @@
+/* lhm.h -- C ABI of liblhm.so: B200 (sm_100a) implementation of LeHaMoC's leptonic per-timestep
+ * kinetic update, batched over independent parameter sets ("walkers").
+ *
+ * The reference (mariapetro/LeHaMoC) is pure Python and has no FFI; its boundary is the Python
+ * surface  `python LeMoC.py <Parameters.txt> <suffix>`  (LeMoC/LeMoC.py:45-58,290-296),
+ * `Code.LeMoC(params, fileName) -> (nu_tot, nuLnu)`  (Fit_emcee/Code.py:51,277) and the function
+ * library LeHaMoC_f.py.  This header is what a ctypes binding of that surface loads; each entry
+ * point cites the reference code it replaces.  `lehamoc_b200/_lib.py` is that binding.
+ *
+ * Conventions
+ *  - all arithmetic is float64; `double*` arguments are DEVICE pointers unless the name ends in
+ *    `_host`; 2-D arrays are row-major [W, n];
+ *  - the caller owns every input/output buffer; the handle owns only its per-batch table workspace;
+ *  - every call is asynchronous on the `stream` given to lhm_create (no hidden synchronisation),
+ *    except the *_host convenience calls, which copy and synchronise;
+ *  - one handle per GPU, not thread-safe per handle; errors are negative lhm_status codes, never exit().
+ */
+#ifndef LHM_H
+#define LHM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LHM_VERSION 100
+
+typedef enum {
+    LHM_OK = 0,
+    LHM_ERR_ARG = -1,          /* bad argument / size */
+    LHM_ERR_CUDA = -2,         /* CUDA runtime error (see lhm_last_cuda_error) */
+    LHM_ERR_NO_DEVICE = -3,    /* no sm_100 device: there is NO CPU fallback */
+    LHM_ERR_STATE = -4,        /* call order (e.g. run before setup) */
+    LHM_ERR_CAPACITY = -5      /* W larger than the handle's capacity / shared memory exceeded */
+} lhm_status;
+
+/* IC emissivity formulation */
+#define LHM_IC_PATH_R 0        /* triple sum nu_out x gamma x nu_in, kernel recomputed in registers */
+#define LHM_IC_PATH_S 1        /* exact suffix-sum collapse of the nu_in sum */
+
+/* Static description of a batch: grid sizes, process flags, driver variant.
+ * Flags are the reference's float flags compared with ==1. / ==0. (LeMoC/LeMoC.py:206-279). */
+typedef struct {
+    int Ng;                 /* len(g_el)                 = int(grid_g_el)          LeMoC.py:115 */
+    int Ns;                 /* len(nu_syn) AFTER the appended point = Ng/2+1        LeMoC.py:131,185 */
+    int Ni;                 /* len(nu_ic)                = Ng/2                     LeMoC.py:132 */
+    int Nt;                 /* len(nu_tot)               = int(grid_nu)             LeMoC.py:133 */
+    int inj_flag, Ad_l_flag, Syn_l_flag, Syn_emis_flag, IC_l_flag, IC_emis_flag, SSA_l_flag,
+        gg_flag, esc_flag;
+    int loss_minus_one;     /* 1: (gamma^2-1) loss shape LeMoC.py:224-234; 0: gamma^2 Code.py:210-220 */
+    int qee_from_ic;        /* 0: Q_ee_f(nu_tot,n,nu_tot,n) LeMoC.py:283; 1: (...,nu_ic,photons_IC/V) Code.py:269 */
+    int gg_npts;            /* resample points of a_gg / Q_ee_f: 50 in LeMoC/LeHaMoC_f.py:132,144 */
+    int ic_path;            /* LHM_IC_PATH_R or LHM_IC_PATH_S */
+    int max_walkers;        /* capacity W of the handle's workspace */
+} lhm_config;
+
+/* per-walker scalar block, [W, LHM_NCONST] doubles, host-packed by lehamoc_b200/setup_host.py */
+enum {
+    LHM_C_R0 = 0,           /* cm                                        LeMoC.py:79  */
+    LHM_C_B0,               /* G                                         LeMoC.py:80  */
+    LHM_C_M,                /* B = B0 (R0/R)^m                           LeMoC.py:81  */
+    LHM_C_VEXP,             /* cm/s (already multiplied by c)            LeMoC.py:78  */
+    LHM_C_DT,               /* s, = step_alg*R0/c                        LeMoC.py:108 */
+    LHM_C_TINIT,            /* time_init exactly as the driver uses it   LeMoC.py:107 */
+    LHM_C_NSTEPS,           /* number of timesteps of this walker        LeMoC.py:196 / Code.py:183 */
+    LHM_C_COR_P,            /* p_el passed to cor_factor_syn_el          LeMoC.py:251 */
+    LHM_C_COR_Q0,           /* Q_el_Lum(L, p, g[1], g[-2])               LeHaMoC_f.py:202 */
+    LHM_C_COR_B,            /* 1e4 G                                     LeMoC.py:251 */
+    LHM_NCONST = 12
+};
+
+typedef struct lhm_handle lhm_handle;
+
+int lhm_version(void);
+const char* lhm_strerror(int status);
+const char* lhm_last_cuda_error(void);
+/* number of kernels launched by this library since load (bench.py's gpu_launches) */
+long long lhm_launch_count(void);
+
+int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle** out);
+void lhm_destroy(lhm_handle*);
+/* bytes of dynamic shared memory per CTA the fused step kernel uses for this config */
+int lhm_step_smem_bytes(const lhm_handle*);
+
+/* Build every state-independent table of W walkers (interpolation stencils, trapezoid weights,
+ * gamma-gamma sample kernels ...).  Replaces the per-call grid work of LeMoC.py:113-191 that does not
+ * depend on N(gamma), n(nu).  consts [W,LHM_NCONST]; g_el [W,Ng]; nu_syn [W,Ns]; nu_ic [W,Ni];
+ * nu_tot [W,Nt]; el_inj [W,Ng] (LeMoC.py:174-175); ext [W,Nt] = BB+PL+user photon densities already
+ * interpolated on nu_tot (LeMoC.py:140-169 through LeHaMoC_f.py:154-156). */
+int lhm_setup_batch(lhm_handle*, int W, const double* consts, const double* g_el, const double* nu_syn,
+                    const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext);
+
+/* A5: cor_factor_syn_el (LeHaMoC_f.py:175-237) for every walker of the current batch -> out[W].
+ * One warp per walker; the 200-step inner simulation is advanced with a warp-level affine scan. */
+int lhm_cor_factor_batch(lhm_handle*, double* out);
+
+/* A0: the whole time integration (LeMoC.py:196-296 / Code.py:183-277), one CTA per walker, state
+ * resident in shared memory for all steps.  snapshots=0: only the state after the last step is
+ * written (N_el_out [W,Ng] = N_el/Volume, nuLnu_out [W,Nt]); snapshots=S>0: one row per step for the
+ * first S steps ([W,S,Ng], [W,S,Nt]).  Either output may be NULL.  lhm_cor_factor_batch is run
+ * internally when Syn_emis_flag is set. */
+int lhm_run_batch(lhm_handle*, double* N_el_out, double* nuLnu_out, int snapshots);
+
+/* Device time (ms, CUDA events on the handle's stream) of the most recent set-up, cor-factor and fused-step
+ * kernels; -1 if never launched.  Synchronises on those events only.  bench.py's roofline uses run_ms. */
+int lhm_last_timings(lhm_handle*, float* setup_ms, float* cor_ms, float* run_ms);
+
+/* Host-buffer convenience used by Code.LeMoC / LeMoC_batch: H2D of the packed inputs, setup, run,
+ * D2H of the outputs, stream synchronise.  All pointers are HOST pointers (pinned or pageable). */
+int lhm_run_batch_host(lhm_handle*, int W, const double* consts_host, const double* g_el_host,
+                       const double* nu_syn_host, const double* nu_ic_host, const double* nu_tot_host,
+                       const double* el_inj_host, const double* ext_host,
+                       double* N_el_out_host, double* nuLnu_out_host, int snapshots);
+
+/* ---- function-level entry points (unit-test twins of LeHaMoC_f.py; same device code as the fused
+ *      kernel).  All act on the walkers of the current batch (after lhm_setup_batch). ---- */
+/* A1 photons_tot LeHaMoC_f.py:154-156 incl. the /Volume of LeMoC.py:204: n[W,Nt] */
+int lhm_photons_tot_batch(lhm_handle*, const double* photons_syn, const double* photons_IC,
+                          const double* radius /*[W]*/, double* n_out);
+/* A2 U_ph_f LeHaMoC_f.py:160-172: U_ph[W,Ng] */
+int lhm_uph_batch(lhm_handle*, const double* n, const double* radius, double* U_out);
+/* A4+A6 Q_syn_space (raw, before the cor-factor division) LeHaMoC_f.py:86-92 -> Q[W,Ns-1];
+ * aSSA LeHaMoC_f.py:101-102 on nu_syn -> aS[W,Ns] and on nu_ic -> aI[W,Ni] (signed, as the function returns) */
+int lhm_syn_ssa_batch(lhm_handle*, const double* n_e /*[W,Ng] = N_el/V*/, const double* Bfield /*[W]*/,
+                      double* Q_syn_out, double* aS_out, double* aI_out);
+/* A7 Q_IC_space_optimized LeHaMoC_f.py:113-124 for nu_ic[0..Ni-2]: Q[W,Ni-1]; ic_path overrides cfg */
+int lhm_ic_emissivity_batch(lhm_handle*, const double* n_e, const double* n, double* Q_out, int ic_path);
+/* A8 a_gg LeHaMoC_f.py:127-137 -> a_gg[W,Ni];  A9 Q_ee_f LeHaMoC_f.py:140-151 -> Q_ee[W,Ng-1].
+ * photons_IC_dens [W,Ni] is read only when cfg.qee_from_ic (Code.py:269); may be NULL otherwise. */
+int lhm_gg_batch(lhm_handle*, const double* n, const double* photons_IC_dens, double* a_gg_out,
+                 double* Q_ee_out);
+/* A3 thomas() with a == 0 (every call site: LeMoC.py:239,267,273): x = upper-bidiagonal solve, [W,n] */
+int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const double* d, double* x,
+                           void* cuda_stream);
+
+/* measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator */
+int lhm_fp64_peak_probe(int device, void* cuda_stream, double* tflops_out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LHM_H */

@@ -1,0 +1,48 @@
+"""Drop-in for Fit_emcee/Code.py: `LeMoC(params, fileName) -> (nu_tot, nuLnu)` plus a batched twin.
+
+Same call, same meaning of `params = [log R0, log B0, log gamma_min, log gamma_max, log l_e, p]`
+(Fit_emcee/Code.py:51-61), same frozen parameter file (Code.py:63-94), same return value (Code.py:277):
+the comoving-frame spectrum after the last timestep.  The time integration runs on the GPU
+(lhm_run_batch_host); there is no CPU path.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+from .engine import Engine
+from .setup_host import pack_code, read_parameter_file
+
+_engines = {}
+
+
+def _engine_for(batch, ic_path, capacity):
+    key = (tuple(sorted(batch.cfg.items())), ic_path)
+    eng = _engines.get(key)
+    if eng is None or eng.max_walkers < capacity:
+        if eng is not None:
+            eng.close()
+        eng = Engine(batch.cfg, max(capacity, 64), ic_path=ic_path)
+        _engines[key] = eng
+    return eng
+
+
+def LeMoC_batch(params, fileName, ic_path="R", return_particles=False):
+    """`params` [W,6]; returns (nu_tot [W,Nt], nuLnu [W,Nt]) (and n_e = N_el/V [W,Ng] if asked)."""
+    frozen = fileName if isinstance(fileName, dict) else read_parameter_file(fileName)
+    batch = pack_code(params, frozen)
+    eng = _engine_for(batch, ic_path, batch.W)
+    N, sed = eng.run_host(batch, snapshots=0)
+    if return_particles:
+        return batch.nu_tot, sed, N
+    return batch.nu_tot, sed
+
+
+def LeMoC(params, fileName):
+    """Fit_emcee/Code.py:51: one model evaluation."""
+    nu_tot, sed = LeMoC_batch(np.asarray(params, dtype=np.float64)[None, :], fileName)
+    return (nu_tot[0], sed[0])
+
+
+def LeHaMoC(params, fileName):
+    """Fit_emcee/Code.py:280 (proton-synchrotron variant): hadronic stage, SURVEY.md section 8 rows A11-A15."""
+    raise NotImplementedError("the leptohadronic driver is scheduled after the leptonic path (SURVEY.md 8f-2)")

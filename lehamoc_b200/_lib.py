@@ -1,0 +1,80 @@
+"""ctypes binding of liblhm.so (include/lhm.h).  There is no CPU fallback: if the library or a B200 is
+missing, calls raise."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "liblhm.so")
+
+LHM_OK = 0
+LHM_IC_PATH_R = 0
+LHM_IC_PATH_S = 1
+LHM_NCONST = 12
+# indices of the per-walker scalar block (include/lhm.h)
+C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B = range(10)
+
+
+class LhmError(RuntimeError):
+    pass
+
+
+class lhm_config(C.Structure):
+    _fields_ = [(n, C.c_int) for n in (
+        "Ng", "Ns", "Ni", "Nt",
+        "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag", "SSA_l_flag",
+        "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "max_walkers")]
+
+
+# every symbol include/lhm.h declares: (restype, argtypes)
+_P = C.c_void_p
+SIGNATURES = {
+    "lhm_version": (C.c_int, []),
+    "lhm_strerror": (C.c_char_p, [C.c_int]),
+    "lhm_last_cuda_error": (C.c_char_p, []),
+    "lhm_launch_count": (C.c_longlong, []),
+    "lhm_create": (C.c_int, [C.POINTER(lhm_config), C.c_int, _P, C.POINTER(_P)]),
+    "lhm_destroy": (None, [_P]),
+    "lhm_step_smem_bytes": (C.c_int, [_P]),
+    "lhm_setup_batch": (C.c_int, [_P, C.c_int] + [_P] * 7),
+    "lhm_cor_factor_batch": (C.c_int, [_P, _P]),
+    "lhm_run_batch": (C.c_int, [_P, _P, _P, C.c_int]),
+    "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),
+    "lhm_photons_tot_batch": (C.c_int, [_P] * 5),
+    "lhm_uph_batch": (C.c_int, [_P] * 4),
+    "lhm_syn_ssa_batch": (C.c_int, [_P] * 6),
+    "lhm_ic_emissivity_batch": (C.c_int, [_P] * 4 + [C.c_int]),
+    "lhm_gg_batch": (C.c_int, [_P] * 5),
+    "lhm_bidiag_solve_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "lhm_fp64_peak_probe": (C.c_int, [C.c_int, _P, C.POINTER(C.c_double)]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen liblhm.so and attach the prototypes.  Raises LhmError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise LhmError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(or `python -m lehamoc_b200.build`).  There is no CPU fallback.")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)            # AttributeError if the symbol is not exported
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != LHM_OK:
+        lib = load()
+        msg = lib.lhm_strerror(rc).decode()
+        if rc == -2:
+            msg += ": " + lib.lhm_last_cuda_error().decode()
+        raise LhmError(f"{what or 'liblhm'} failed ({rc}): {msg}")

@@ -1,0 +1,43 @@
+"""Compile liblhm.so for sm_100a in-tree (nvcc cross-compiles without a GPU)."""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(HERE, "csrc", "lhm.cu")
+OUT = os.path.join(HERE, "liblhm.so")
+DEPS = [os.path.join(HERE, "csrc", f) for f in ("lhm.cu", "lhm_device.cuh", "lhm_setup.cuh", "lhm_step.cuh", "lhm_cor.cuh")]
+DEPS.append(os.path.join(os.path.dirname(HERE), "include", "lhm.h"))
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-shared", "-Xcompiler", "-fPIC"]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(OUT):
+        return True
+    t = os.path.getmtime(OUT)
+    return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return OUT
+    nvcc = os.environ.get("NVCC", "nvcc")
+    cmd = [nvcc, *NVCC_FLAGS, SRC, "-o", OUT]
+    if verbose:
+        cmd.insert(1, "-Xptxas")
+        cmd.insert(2, "-v")
+        print(" ".join(cmd))
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv, verbose=True)
+    print("built", OUT)

@@ -1,0 +1,552 @@
+// lhm.cu -- liblhm.so: kernels + C ABI (include/lhm.h).  Build: see lehamoc_b200/build.py
+//   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC lhm.cu -o liblhm.so
+#include <cuda_runtime.h>
+#include <atomic>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "../../include/lhm.h"
+#include "lhm_device.cuh"
+#include "lhm_setup.cuh"
+#include "lhm_step.cuh"
+#include "lhm_cor.cuh"
+
+namespace lhm {
+
+constexpr int NT = 256;             // threads per walker CTA
+constexpr int NW = NT / 32;
+
+// =================================================================================================
+// fused time integration: one CTA per walker, all steps inside one launch
+// =================================================================================================
+struct RunArgs {
+    Layout L;
+    StepFlags F;
+    int W, snapshots;
+    const double* consts;
+    const double* tabd;
+    const int* tabi;
+    const double* cor;      // [W] cor_factor_syn_el
+    double* N_out;          // [W,(S),Ng] or null
+    double* sed_out;        // [W,(S),Nt] or null
+};
+
+__device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlags& F, const double* consts,
+                                         const double* tabd, const int* tabi, int w) {
+    C.L = L; C.F = F;
+    C.T = tabd + (size_t)w * L.n_doubles;
+    C.TI = tabi + (size_t)w * L.n_ints;
+    const double* c = consts + (size_t)w * LHM_NCONST;
+    C.R0 = c[LHM_C_R0]; C.B0 = c[LHM_C_B0]; C.m = c[LHM_C_M]; C.Vexp = c[LHM_C_VEXP];
+    C.dt = c[LHM_C_DT]; C.tinit = c[LHM_C_TINIT];
+    C.Rad = C.R0; C.B = C.B0; C.V = volume_of(C.R0);
+}
+
+__global__ void __launch_bounds__(NT, 2) run_kernel(RunArgs A) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+
+    // initial state (LeMoC.py:172-183)
+    for (int j = tid; j < Ng; j += NT) {
+        S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];
+        S.qee[j] = 0.0;
+    }
+    for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; }
+    for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    ic_prepare<NT>(C, S);
+
+    double t = C.tinit;
+    for (int step = 0; step < nsteps; ++step) {
+        t += C.dt;                                               // LeMoC.py:198-201
+        C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.V = volume_of(C.Rad);
+
+        phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        phase_electrons<NT>(C, S);
+        phase_vectors<NT>(C, S);
+        phase_syn_rows<NT>(C, S, false);
+        if (C.F.ic_e) {
+            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
+        }
+        __syncthreads();
+        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        phase_photon_solves<NT>(C, S, cor);
+        if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
+            const double* Lng = S.Ln;
+            if (C.F.qee_from_ic) {
+                for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
+                __syncthreads();
+                Lng = S.Lic;
+            }
+            phase_gg<NT>(C, S, Lng, S.agg, S.qee);
+            __syncthreads();
+        }
+        // output (LeMoC.py:286-291): every step when snapshots are requested, else after the last step
+        const bool last = (step == nsteps - 1);
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && last)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT)
+                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =================================================================================================
+// function-level kernels: same device code, one phase each (unit-test twins of LeHaMoC_f.py)
+// =================================================================================================
+struct UnitArgs {
+    Layout L;
+    StepFlags F;
+    int W;
+    const double* consts;
+    const double* tabd;
+    const int* tabi;
+    const double *in0, *in1, *in2;
+    double *out0, *out1, *out2;
+    int mode;
+};
+
+enum { U_PHOTONS = 0, U_UPH, U_SYN, U_IC, U_GG };
+
+__global__ void __launch_bounds__(NT, 2) unit_kernel(UnitArgs A) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    ic_prepare<NT>(C, S);
+    switch (A.mode) {
+    case U_PHOTONS: {       // in0 photons_syn [W,Ns], in1 photons_IC [W,Ni], in2 radius [W] -> out0 n [W,Nt]
+        C.Rad = A.in2[w]; C.V = volume_of(C.Rad);
+        for (int k = tid; k < Ns; k += NT) S.psyn[k] = A.in0[(size_t)w * Ns + k];
+        for (int k = tid; k < Ni; k += NT) S.pic[k] = A.in1[(size_t)w * Ni + k];
+        __syncthreads();
+        phase_photons<NT>(C, S, false);
+        for (int k = tid; k < Nt; k += NT) A.out0[(size_t)w * Nt + k] = S.n[k];
+    } break;
+    case U_UPH: {           // in0 n [W,Nt], in2 radius [W] -> out0 U_ph [W,Ng]
+        C.Rad = A.in2[w]; C.V = volume_of(C.Rad);
+        const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;
+        for (int k = tid; k < Nt; k += NT) {
+            double nk = A.in0[(size_t)w * Nt + k];
+            S.n[k] = nk; S.Ln[k] = log10(nk); S.y[k] = C.T[L.xt + k] * nk * K;
+        }
+        __syncthreads();
+        phase_uph<NT>(C, S, S.ne);
+        for (int j = tid; j < Ng; j += NT) A.out0[(size_t)w * Ng + j] = S.ne[j];
+    } break;
+    case U_SYN: {           // in0 n_e [W,Ng], in2 B [W] -> out0 Q_syn [W,Ns-1], out1 aS [W,Ns], out2 aI [W,Ni]
+        C.B = A.in2[w]; C.V = 1.0;
+        C.F.syn_e = 1; C.F.ssa = 1;
+        for (int j = tid; j < Ng; j += NT) S.N[j] = A.in0[(size_t)w * Ng + j];
+        __syncthreads();
+        phase_vectors<NT>(C, S);
+        phase_syn_rows<NT>(C, S, true);
+        __syncthreads();
+        for (int k = tid; k < Ns - 1; k += NT) A.out0[(size_t)w * (Ns - 1) + k] = S.Qsyn[k];
+        for (int k = tid; k < Ns; k += NT) A.out1[(size_t)w * Ns + k] = S.aS[k];
+        for (int k = tid; k < Ni; k += NT) A.out2[(size_t)w * Ni + k] = S.aI[k];
+    } break;
+    case U_IC: {            // in0 n_e [W,Ng], in1 n [W,Nt] -> out0 Q_IC [W,Ni-1]
+        C.V = 1.0;
+        for (int j = tid; j < Ng; j += NT) S.N[j] = A.in0[(size_t)w * Ng + j];
+        for (int k = tid; k < Nt; k += NT) {
+            double nk = A.in1[(size_t)w * Nt + k];
+            S.n[k] = nk; S.tri[4 * k + 2] = C.T[L.wt + k] * nk;
+        }
+        __syncthreads();
+        phase_vectors<NT>(C, S);
+        if (C.F.ic_path == LHM_IC_PATH_R) {
+            phase_ic_R<NT>(C, S);
+            __syncthreads();
+            phase_ic_finish_R<NT>(C, S);
+        } else {
+            phase_ic_S<NT>(C, S);
+        }
+        __syncthreads();
+        for (int k = tid; k < Ni - 1; k += NT) A.out0[(size_t)w * (Ni - 1) + k] = S.QIC[k];
+    } break;
+    case U_GG: {            // in0 n [W,Nt], in1 photons_IC density [W,Ni] (qee_from_ic) -> out0 a_gg [W,Ni], out1 Q_ee [W,Ng-1]
+        for (int k = tid; k < Nt; k += NT) {
+            double nk = A.in0[(size_t)w * Nt + k];
+            S.Ln[k] = log10(nk); S.Lm[k] = log10(nk * kPC.mc2_h);
+        }
+        const double* Lng = S.Ln;
+        if (C.F.qee_from_ic) {
+            for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(A.in1[(size_t)w * Ni + k]);
+            Lng = S.Lic;
+        }
+        __syncthreads();
+        phase_gg<NT>(C, S, Lng, S.agg, S.qee);
+        __syncthreads();
+        for (int k = tid; k < Ni; k += NT) A.out0[(size_t)w * Ni + k] = S.agg[k];
+        for (int j = tid; j < Ng - 1; j += NT) A.out1[(size_t)w * (Ng - 1) + j] = S.qee[j];
+    } break;
+    }
+}
+
+// generic batched upper-bidiagonal solve (thomas() with a == 0), one CTA per system
+__global__ void __launch_bounds__(128) bidiag_kernel(int n, const double* b, const double* c, const double* d, double* x) {
+    extern __shared__ __align__(16) double sb[];
+    double* cp = sb; double* dp = sb + n;
+    const size_t off = (size_t)blockIdx.x * n;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        cp[i] = c[off + i] / b[off + i];
+        dp[i] = d[off + i] / b[off + i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) backsub(cp, dp, x + off, n);
+}
+
+// FP64 FMA throughput probe: 8 independent chains per thread
+__global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
+    double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
+    const double m = 0.999999, b = 1e-9 * threadIdx.x;
+    for (int i = 0; i < iters; ++i) {
+        a0 = fma(a0, m, b); a1 = fma(a1, m, b); a2 = fma(a2, m, b); a3 = fma(a3, m, b);
+        a4 = fma(a4, m, b); a5 = fma(a5, m, b); a6 = fma(a6, m, b); a7 = fma(a7, m, b);
+    }
+    out[blockIdx.x * blockDim.x + threadIdx.x] = a0 + a1 + a2 + a3 + a4 + a5 + a6 + a7;
+}
+
+}  // namespace lhm
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+using namespace lhm;
+
+static thread_local std::string g_cuda_err;
+static std::atomic<long long> g_launches{0};
+
+#define CUDA_TRY(expr)                                                                 \
+    do {                                                                               \
+        cudaError_t _e = (expr);                                                       \
+        if (_e != cudaSuccess) {                                                       \
+            g_cuda_err = std::string(#expr) + ": " + cudaGetErrorString(_e);           \
+            return LHM_ERR_CUDA;                                                       \
+        }                                                                              \
+    } while (0)
+
+struct lhm_handle {
+    lhm_config cfg;
+    Layout L;
+    StepFlags F;
+    int device;
+    cudaStream_t stream;
+    int W;                    // walkers of the current batch (0 = none)
+    size_t smem;
+    double* d_tabd;
+    int* d_tabi;
+    double* d_cor;
+    const double* consts;     // device pointers of the current batch (caller- or staging-owned)
+    const double* g_el;
+    // staging for the *_host entry points
+    double* d_in;
+    double* d_Nout;
+    double* d_sed;
+    size_t Nout_cap, sed_cap;
+    // device-side timing of the last setup / cor / run launches (lhm_last_timings)
+    cudaEvent_t ev[6];
+    bool ev_set[3];
+};
+
+static PhysConst make_consts() {
+    PhysConst p;
+    p.c = 2.99792458e10; p.h = 6.62607015e-27; p.q = 4.803204712570263e-10;
+    p.sigmaT = 6.6524587321e-25; p.m_el = 9.1093837015e-28;
+    const double pi = M_PI;
+    p.mc2 = p.m_el * std::pow(p.c, 2.0);
+    p.C_syn = p.sigmaT * p.c / (p.h * 24. * std::pow(pi, 2.) * 0.8975) * std::pow(4. * pi * p.m_el * p.c / (3. * p.q), 4. / 3.);
+    p.ssa_pref = std::pow(p.q, 3.) / (2. * std::pow(p.m_el, 2.) * std::pow(p.c, 2.) * 0.8975);
+    p.bsyn_pref = (4. / 3.) * p.sigmaT / (8. * pi * p.m_el * p.c);
+    p.acr_pref = 3. * p.q / (4. * pi * p.m_el * p.c);
+    p.nuc_pref = 3. / (4. * pi) * p.q / (p.m_el * p.c);
+    p.ic_pref = p.sigmaT * p.c * 0.75;
+    p.gg_pref = 0.652 * p.sigmaT;
+    p.qee_pref = p.c * p.sigmaT * p.m_el * std::pow(p.c, 2.) / p.h;
+    p.mc2_h = p.m_el * std::pow(p.c, 2.) / p.h;
+    p.nuT_num = 3. * p.m_el * std::pow(p.c, 2.);
+    return p;
+}
+
+extern "C" {
+
+int lhm_version(void) { return LHM_VERSION; }
+
+const char* lhm_strerror(int s) {
+    switch (s) {
+    case LHM_OK: return "ok";
+    case LHM_ERR_ARG: return "invalid argument";
+    case LHM_ERR_CUDA: return "CUDA runtime error (see lhm_last_cuda_error)";
+    case LHM_ERR_NO_DEVICE: return "no CUDA device with compute capability 10.x (there is no CPU fallback)";
+    case LHM_ERR_STATE: return "call order: lhm_setup_batch must precede this call";
+    case LHM_ERR_CAPACITY: return "batch larger than the handle capacity, or shared memory exceeded";
+    default: return "unknown lhm_status";
+    }
+}
+
+const char* lhm_last_cuda_error(void) { return g_cuda_err.c_str(); }
+long long lhm_launch_count(void) { return g_launches.load(); }
+
+int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle** out) {
+    if (!cfg || !out) return LHM_ERR_ARG;
+    if (cfg->Ng < 4 || cfg->Ns < 3 || cfg->Ni < 3 || cfg->Nt < 4 || cfg->gg_npts < 3 || cfg->max_walkers < 1) return LHM_ERR_ARG;
+    if (cfg->Ni > 2040 || cfg->Ng > 4080) return LHM_ERR_ARG;             // IC task encoding (8+8 bits)
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return LHM_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return LHM_ERR_NO_DEVICE;
+    CUDA_TRY(cudaSetDevice(device));
+    lhm_handle* h = new (std::nothrow) lhm_handle();
+    if (!h) return LHM_ERR_ARG;
+    std::memset(h, 0, sizeof(*h));
+    h->cfg = *cfg;
+    h->device = device;
+    h->stream = (cudaStream_t)cuda_stream;
+    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts);
+    StepFlags& F = h->F;
+    F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
+    F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
+    F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
+    h->smem = smem_bytes(h->L, NW);
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
+    PhysConst pc = make_consts();
+    CUDA_TRY(cudaMemcpyToSymbol(kPC, &pc, sizeof(pc)));
+    CUDA_TRY(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CUDA_TRY(cudaFuncSetAttribute(unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CUDA_TRY(cudaFuncSetAttribute(cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cor_smem_bytes(cfg->Ng)));
+    const size_t W = cfg->max_walkers;
+    CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
+    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    *out = h;
+    return LHM_OK;
+}
+
+void lhm_destroy(lhm_handle* h) {
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor);
+    cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
+    for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    delete h;
+}
+
+int lhm_step_smem_bytes(const lhm_handle* h) { return h ? (int)h->smem : LHM_ERR_ARG; }
+
+int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_el, const double* nu_syn,
+                    const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext) {
+    if (!h || !consts || !g_el || !nu_syn || !nu_ic || !nu_tot || !el_inj || !ext) return LHM_ERR_ARG;
+    if (W < 1) return LHM_ERR_ARG;
+    if (W > h->cfg.max_walkers) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaSetDevice(h->device));
+    SetupArgs A;
+    A.L = h->L; A.W = W; A.loss_minus_one = h->cfg.loss_minus_one; A.qee_from_ic = h->cfg.qee_from_ic;
+    A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
+    A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi;
+    CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
+    setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
+    h->ev_set[0] = true;
+    h->W = W; h->consts = consts; h->g_el = g_el;
+    return LHM_OK;
+}
+
+int lhm_cor_factor_batch(lhm_handle* h, double* out) {
+    if (!h || !out) return LHM_ERR_ARG;
+    if (h->W < 1) return LHM_ERR_STATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
+    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    cor_kernel<<<(h->W + COR_WARPS - 1) / COR_WARPS, COR_WARPS * 32, cor_smem_bytes(h->cfg.Ng), h->stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
+    h->ev_set[1] = true;
+    return LHM_OK;
+}
+
+int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapshots) {
+    if (!h || snapshots < 0) return LHM_ERR_ARG;
+    if (h->W < 1) return LHM_ERR_STATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const double* cor = nullptr;
+    if (h->cfg.Syn_emis_flag) {
+        int rc = lhm_cor_factor_batch(h, h->d_cor);
+        if (rc != LHM_OK) return rc;
+        cor = h->d_cor;
+    }
+    RunArgs A;
+    A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
+    A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
+    CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
+    run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
+    h->ev_set[2] = true;
+    return LHM_OK;
+}
+
+int lhm_last_timings(lhm_handle* h, float* setup_ms, float* cor_ms, float* run_ms) {
+    if (!h) return LHM_ERR_ARG;
+    float* outs[3] = {setup_ms, cor_ms, run_ms};
+    for (int i = 0; i < 3; ++i) {
+        if (!outs[i]) continue;
+        *outs[i] = -1.f;
+        if (!h->ev_set[i]) continue;
+        CUDA_TRY(cudaEventSynchronize(h->ev[2 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(outs[i], h->ev[2 * i], h->ev[2 * i + 1]));
+    }
+    return LHM_OK;
+}
+
+int lhm_run_batch_host(lhm_handle* h, int W, const double* consts, const double* g_el, const double* nu_syn,
+                       const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext,
+                       double* N_out, double* sed_out, int snapshots) {
+    if (!h || W < 1 || snapshots < 0) return LHM_ERR_ARG;
+    if (W > h->cfg.max_walkers) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const lhm_config& c = h->cfg;
+    const size_t Wm = c.max_walkers;
+    const size_t per = (size_t)LHM_NCONST + 2 * c.Ng + c.Ns + c.Ni + 2 * c.Nt;
+    if (!h->d_in) CUDA_TRY(cudaMalloc(&h->d_in, Wm * per * sizeof(double)));
+    double* p = h->d_in;
+    double* d_consts = p; p += Wm * LHM_NCONST;
+    double* d_g = p; p += Wm * c.Ng;
+    double* d_ns = p; p += Wm * c.Ns;
+    double* d_ni = p; p += Wm * c.Ni;
+    double* d_nt = p; p += Wm * c.Nt;
+    double* d_inj = p; p += Wm * c.Ng;
+    double* d_ext = p;
+    cudaStream_t s = h->stream;
+    CUDA_TRY(cudaMemcpyAsync(d_consts, consts, (size_t)W * LHM_NCONST * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_g, g_el, (size_t)W * c.Ng * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ns, nu_syn, (size_t)W * c.Ns * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ni, nu_ic, (size_t)W * c.Ni * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_nt, nu_tot, (size_t)W * c.Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_inj, el_inj, (size_t)W * c.Ng * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaMemcpyAsync(d_ext, ext, (size_t)W * c.Nt * sizeof(double), cudaMemcpyHostToDevice, s));
+    int rc = lhm_setup_batch(h, W, d_consts, d_g, d_ns, d_ni, d_nt, d_inj, d_ext);
+    if (rc != LHM_OK) return rc;
+    const size_t S_ = snapshots > 0 ? snapshots : 1;
+    const size_t nN = (size_t)W * S_ * c.Ng, nS = (size_t)W * S_ * c.Nt;
+    if (N_out && nN > h->Nout_cap) { cudaFree(h->d_Nout); h->d_Nout = nullptr; CUDA_TRY(cudaMalloc(&h->d_Nout, nN * sizeof(double))); h->Nout_cap = nN; }
+    if (sed_out && nS > h->sed_cap) { cudaFree(h->d_sed); h->d_sed = nullptr; CUDA_TRY(cudaMalloc(&h->d_sed, nS * sizeof(double))); h->sed_cap = nS; }
+    rc = lhm_run_batch(h, N_out ? h->d_Nout : nullptr, sed_out ? h->d_sed : nullptr, snapshots);
+    if (rc != LHM_OK) return rc;
+    if (N_out) CUDA_TRY(cudaMemcpyAsync(N_out, h->d_Nout, nN * sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (sed_out) CUDA_TRY(cudaMemcpyAsync(sed_out, h->d_sed, nS * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    return LHM_OK;
+}
+
+static int launch_unit(lhm_handle* h, int mode, const double* in0, const double* in1, const double* in2,
+                       double* out0, double* out1, double* out2, int ic_path) {
+    if (!h) return LHM_ERR_ARG;
+    if (h->W < 1) return LHM_ERR_STATE;
+    CUDA_TRY(cudaSetDevice(h->device));
+    UnitArgs A;
+    A.L = h->L; A.F = h->F; A.W = h->W; A.consts = h->consts; A.tabd = h->d_tabd; A.tabi = h->d_tabi;
+    if (ic_path >= 0) A.F.ic_path = ic_path;
+    A.in0 = in0; A.in1 = in1; A.in2 = in2; A.out0 = out0; A.out1 = out1; A.out2 = out2; A.mode = mode;
+    unit_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_photons_tot_batch(lhm_handle* h, const double* photons_syn, const double* photons_IC, const double* radius, double* n_out) {
+    if (!photons_syn || !photons_IC || !radius || !n_out) return LHM_ERR_ARG;
+    return launch_unit(h, U_PHOTONS, photons_syn, photons_IC, radius, n_out, nullptr, nullptr, -1);
+}
+int lhm_uph_batch(lhm_handle* h, const double* n, const double* radius, double* U_out) {
+    if (!n || !radius || !U_out) return LHM_ERR_ARG;
+    return launch_unit(h, U_UPH, n, nullptr, radius, U_out, nullptr, nullptr, -1);
+}
+int lhm_syn_ssa_batch(lhm_handle* h, const double* n_e, const double* Bfield, double* Q, double* aS, double* aI) {
+    if (!n_e || !Bfield || !Q || !aS || !aI) return LHM_ERR_ARG;
+    return launch_unit(h, U_SYN, n_e, nullptr, Bfield, Q, aS, aI, -1);
+}
+int lhm_ic_emissivity_batch(lhm_handle* h, const double* n_e, const double* n, double* Q, int ic_path) {
+    if (!n_e || !n || !Q || (ic_path != LHM_IC_PATH_R && ic_path != LHM_IC_PATH_S)) return LHM_ERR_ARG;
+    return launch_unit(h, U_IC, n_e, n, nullptr, Q, nullptr, nullptr, ic_path);
+}
+int lhm_gg_batch(lhm_handle* h, const double* n, const double* photons_IC_dens, double* a_gg, double* Q_ee) {
+    if (!n || !a_gg || !Q_ee) return LHM_ERR_ARG;
+    if (h && h->cfg.qee_from_ic && !photons_IC_dens) return LHM_ERR_ARG;
+    return launch_unit(h, U_GG, n, photons_IC_dens, nullptr, a_gg, Q_ee, nullptr, -1);
+}
+
+int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const double* d, double* x, void* stream) {
+    if (W < 1 || n < 1 || !b || !c || !d || !x) return LHM_ERR_ARG;
+    if ((size_t)n * 2 * sizeof(double) > 48 * 1024) return LHM_ERR_CAPACITY;
+    bidiag_kernel<<<W, 128, (size_t)n * 2 * sizeof(double), (cudaStream_t)stream>>>(n, b, c, d, x);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_fp64_peak_probe(int device, void* stream, double* tflops_out) {
+    if (!tflops_out) return LHM_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return LHM_ERR_NO_DEVICE;
+    CUDA_TRY(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CUDA_TRY(cudaGetDeviceProperties(&prop, device));
+    const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 1 << 16;
+    double* buf = nullptr;
+    CUDA_TRY(cudaMalloc(&buf, (size_t)blocks * threads * sizeof(double)));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    cudaStream_t s = (cudaStream_t)stream;
+    double best = 0.0;
+    for (int rep = 0; rep < 4; ++rep) {
+        CUDA_TRY(cudaEventRecord(e0, s));
+        fp64_probe_kernel<<<blocks, threads, 0, s>>>(buf, iters, 1.0 + rep);
+        g_launches++;
+        CUDA_TRY(cudaEventRecord(e1, s));
+        CUDA_TRY(cudaEventSynchronize(e1));
+        float ms = 0.f;
+        CUDA_TRY(cudaEventElapsedTime(&ms, e0, e1));
+        double tf = 2.0 * 8.0 * (double)iters * blocks * threads / (ms * 1e-3) / 1e12;
+        if (rep > 0 && tf > best) best = tf;
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(buf);
+    *tflops_out = best;
+    return LHM_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,140 @@
+// lhm_device.cuh -- layout of the per-walker tables and small device helpers.
+// sm_100a only; float64 everywhere (values span 1e-306 .. 1e+60).
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+namespace lhm {
+
+// ---- physical constants: astropy 5.0.4 CGS values the reference pins (LeHaMoC_f.py:17-31) -------
+struct PhysConst {
+    double c, h, q, sigmaT, m_el, mc2;  // mc2 = m_el*c**2.
+    double C_syn;       // LeHaMoC_f.py:87
+    double ssa_pref;    // q**3./(2.*m_el**2.*c**2.*0.8975)            LeHaMoC_f.py:102
+    double bsyn_pref;   // (4./3.)*sigmaT/(8.*pi*m_el*c)               LeMoC.py:223
+    double acr_pref;    // 3.*q/(4.*pi*m_el*c)                          LeMoC.py:201
+    double nuc_pref;    // 3./(4.*pi)*q/(m_el*c)                        LeHaMoC_f.py:79
+    double ic_pref;     // sigmaT*c*0.75                                LeHaMoC_f.py:123
+    double gg_pref;     // 0.652*sigmaT                                 LeHaMoC_f.py:135
+    double qee_pref;    // c*sigmaT*m_el*c**2./h                        LeHaMoC_f.py:151
+    double mc2_h;       // m_el*c**2./h
+    double nuT_num;     // 3.*m_el*c**2.                                LeHaMoC_f.py:164
+};
+
+// single translation unit (lhm.cu): the constant block lives here
+__constant__ PhysConst kPC;
+
+#define LHM_SENT 1e-260   // 10**(-260.)  LeMoC.py:174-183
+
+// ---- per-walker table layout (offsets in doubles / ints from the walker's base) ------------------
+struct Layout {
+    int Ng, Ns, Ni, Nt, NP;
+    // double tables
+    int g, lg, wg, wgi, g13, inv4g, sm, sp, am, ap, elinj, u_xT, u_dx, u_Dx, q_dx, q_Dx;   // Ng each
+    int nsyn, lsyn, nm23s, nm53s, asm_, asp_;                                              // Ns each
+    int nic, lic, nm53i, aim, aip, eps, lnu4;                                              // Ni each
+    int nt, lt, lxt, xt, wt, invnt, l2nt, hnu2, ext, ps_dx, ps_Dx, pi_dx, pi_Dx;           // Nt each
+    int aggK, aggT, qeeK, qeeT;                                                            // Ni*NP, Ng*NP
+    int n_doubles;
+    // int tables
+    int ps_j, pi_j;                 // Nt
+    int u_idx, u_j, q_j;            // Ng
+    int jm_syn;                     // Ns
+    int aggJ, qeeJ;                 // Ni*NP, Ng*NP
+    int n_ints;
+};
+
+inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
+    Layout L;
+    L.Ng = Ng; L.Ns = Ns; L.Ni = Ni; L.Nt = Nt; L.NP = NP;
+    int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };   // keep 16-byte alignment
+    L.g = take(Ng); L.lg = take(Ng); L.wg = take(Ng); L.wgi = take(Ng); L.g13 = take(Ng);
+    L.inv4g = take(Ng); L.sm = take(Ng); L.sp = take(Ng); L.am = take(Ng); L.ap = take(Ng);
+    L.elinj = take(Ng); L.u_xT = take(Ng); L.u_dx = take(Ng); L.u_Dx = take(Ng); L.q_dx = take(Ng);
+    L.q_Dx = take(Ng);
+    L.nsyn = take(Ns); L.lsyn = take(Ns); L.nm23s = take(Ns); L.nm53s = take(Ns); L.asm_ = take(Ns);
+    L.asp_ = take(Ns);
+    L.nic = take(Ni); L.lic = take(Ni); L.nm53i = take(Ni); L.aim = take(Ni); L.aip = take(Ni);
+    L.eps = take(Ni); L.lnu4 = take(Ni);
+    L.nt = take(Nt); L.lt = take(Nt); L.lxt = take(Nt); L.xt = take(Nt); L.wt = take(Nt);
+    L.invnt = take(Nt); L.l2nt = take(Nt); L.hnu2 = take(Nt); L.ext = take(Nt); L.ps_dx = take(Nt);
+    L.ps_Dx = take(Nt); L.pi_dx = take(Nt); L.pi_Dx = take(Nt);
+    L.aggK = take(Ni * NP); L.aggT = take(Ni * NP); L.qeeK = take(Ng * NP); L.qeeT = take(Ng * NP);
+    L.n_doubles = o;
+    o = 0;
+    L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
+    L.jm_syn = take(Ns); L.aggJ = take(Ni * NP); L.qeeJ = take(Ng * NP);
+    L.n_ints = o;
+    return L;
+}
+
+// ---- np.interp semantics (NumPy C `arr_interp`) ---------------------------------
+// A stencil is (code, dx, Dx): code = (j << 1) | exact.  exact -> result fp[j] (clamped ends or
+// x == xp[j]); otherwise slope form with NumPy's NaN fall-backs, which decide what happens to the
+// -inf ordinates log10(0) produces.
+__device__ __forceinline__ void interp_stencil(double x, const double* __restrict__ xp, int n,
+                                               int& code, double& dx, double& Dx) {
+    dx = 0.0; Dx = 1.0;
+    if (x > xp[n - 1]) { code = ((n - 1) << 1) | 1; return; }
+    if (x < xp[0])     { code = 1; return; }
+    if (x == xp[n - 1]) { code = ((n - 1) << 1) | 1; return; }
+    int lo = 0, hi = n - 1;                      // invariant xp[lo] <= x < xp[hi]
+    while (hi - lo > 1) {
+        int mid = (lo + hi) >> 1;
+        if (xp[mid] <= x) lo = mid; else hi = mid;
+    }
+    if (xp[lo] == x) { code = (lo << 1) | 1; return; }
+    code = lo << 1;
+    dx = x - xp[lo];
+    Dx = xp[lo + 1] - xp[lo];
+}
+
+__device__ __forceinline__ double interp_eval(const double* __restrict__ fp, int code, double dx, double Dx) {
+    int j = code >> 1;
+    double f0 = fp[j];
+    if (code & 1) return f0;
+    double f1 = fp[j + 1];
+    double slope = (f1 - f0) / Dx;
+    double r = slope * dx + f0;
+    if (isnan(r)) {
+        r = slope * (dx - Dx) + f1;
+        if (isnan(r) && f0 == f1) r = f0;
+    }
+    return r;
+}
+
+// lerp form used for the (many) gamma-gamma samples: fp[j] + t*(fp[j+1]-fp[j]); a NaN can only come
+// from -inf ordinates, for which np.interp yields -inf (see DESIGN.md "np.interp corner cases").
+__device__ __forceinline__ double lerp_log(const double* __restrict__ fp, int j, double t) {
+    double f0 = fp[j], f1 = fp[j + 1];
+    double r = fma(t, f1 - f0, f0);
+    return isnan(r) ? -INFINITY : r;
+}
+
+// max(F, 0) for finite F without touching the FP64 pipe: clear all bits when the sign bit is set
+__device__ __forceinline__ double clamp_neg_to_zero(double F) {
+    int hi = __double2hiint(F), lo = __double2loint(F);
+    int mask = ~(hi >> 31);
+    return __hiloint2double(hi & mask, lo & mask);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+    return v;
+}
+
+// trapezoid weight of node j on abscissae x[0..n-1] (np.trapz(y, x) == sum_j w_j y_j)
+__device__ __forceinline__ double trapz_w(const double* __restrict__ x, int j, int n) {
+    double a = (j > 0) ? (x[j] - x[j - 1]) : 0.0;
+    double b = (j < n - 1) ? (x[j + 1] - x[j]) : 0.0;
+    return (a + b) * 0.5;
+}
+
+__device__ __forceinline__ double volume_of(double R) {      // LeHaMoC_f.py:47-48
+    return 4.0 * M_PI / 3.0 * (R * R * R);
+}
+
+}  // namespace lhm

@@ -1,0 +1,527 @@
+// lhm_step.cuh -- the per-timestep kinetic update of one walker, executed by one CTA with the whole
+// state resident in shared memory (LeMoC/LeMoC.py:196-296, Fit_emcee/Code.py:183-277).
+//
+// Phases of a step (Appendix A of SURVEY.md gives the index-exact statement):
+//   A  log10 of the photon state                      -> Lsyn, Lic
+//   B  photons_tot (np.interp merge)                  -> n, log tables           LeHaMoC_f.py:154
+//   C  U_ph_f prefix integral -> Compton loss rate    -> bcom                    LeHaMoC_f.py:160
+//   D  electron coefficients + bidiagonal solve       -> N                       LeMoC.py:239-247
+//   E  per-gamma vectors for the contractions         -> ne, av, u, v, inuc
+//   F  synchrotron/SSA rows + IC pairs                -> Qsyn, aS, aI, QIC       LeHaMoC_f.py:86,101,113
+//   G  photon solves                                  -> psyn, pic               LeMoC.py:267-277
+//   H  gamma-gamma opacity + pair injection           -> agg, qee                LeHaMoC_f.py:127,140
+#pragma once
+#include "lhm_device.cuh"
+
+namespace lhm {
+
+
+struct StepFlags {
+    int inj, ad, syn_l, syn_e, ic_l, ic_e, ssa, gg, esc, qee_from_ic, ic_path;
+};
+
+// shared-memory carve-up; all pointers are into dynamic shared memory
+struct Smem {
+    double *N, *psyn, *pic, *agg, *qee;          // state
+    double *Lsyn, *Lic;                          // log10 of photon state
+    double *n, *Ln, *Lm, *y, *cum;               // total photon field + derived
+    double *bcom;                                // Compton loss coefficient per gamma
+    double *cp, *dp;                             // solver scratch (size Nmax)
+    double *ne, *av, *u, *v, *inuc;              // per-gamma vectors of phase E
+    double *Qsyn, *aS, *aI, *QIC;                // contraction results
+    double *tri;                                 // [Nt][4] = {1/nu_i, 2 ln nu_i, w_i n_i, 0}
+    double *gS, *lgS, *inv4gS, *epsS, *lnu4S, *nuoS;   // IC pair-constant inputs
+    double *sfx;                                 // [4][Nt] suffix sums of IC path S
+    double *partial;                             // [NW][NiPad] IC partial sums
+    unsigned short* tasks;                       // IC (o-group, gamma-block) task list
+    int* ntasks;                                 // (shared) number of active tasks
+};
+
+__host__ __device__ inline int imax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
+__host__ __device__ inline int pad2(int n) { return (n + 1) & ~1; }
+
+// IC tiling: a warp task covers OG outgoing frequencies x GB gammas; a thread owns 1 frequency x PT gammas
+constexpr int IC_OG = 8;      // lanes>>2
+constexpr int IC_GL = 4;      // gamma lanes (lane & 3)
+constexpr int IC_PT = 4;      // pairs per thread
+constexpr int IC_GB = IC_GL * IC_PT;   // 16 gammas per task
+
+__host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
+    int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    int Nmax = imax3(Ng, Ns, Ni);
+    size_t d = 0;
+    d += pad2(Ng) * 2 + pad2(Ns) + pad2(Ni) * 2;            // state
+    d += pad2(Ns) + pad2(Ni);                               // logs
+    d += pad2(Nt) * 5;                                      // n Ln Lm y cum
+    d += pad2(Ng);                                          // bcom
+    d += pad2(Nmax) * 2;                                    // cp dp
+    d += pad2(Ng) * 5;                                      // ne av u v inuc
+    d += pad2(Ns) * 2 + pad2(Ni) * 2;                       // Qsyn aS aI QIC
+    d += (size_t)Nt * 4;                                    // tri
+    d += pad2(Ng) * 3 + pad2(Ni) * 3;                       // gS lgS inv4gS epsS lnu4S nuoS
+    d += (size_t)4 * pad2(Nt);                              // sfx
+    int NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    d += (size_t)NW * NiPad;                                // partial
+    return d;
+}
+__host__ __device__ inline int ic_max_tasks(const Layout& L) {
+    return ((L.Ni + IC_OG - 1) / IC_OG) * ((L.Ng + IC_GB - 1) / IC_GB);
+}
+__host__ __device__ inline size_t smem_bytes(const Layout& L, int NW) {
+    return smem_doubles(L, NW) * sizeof(double) + (size_t)pad2(ic_max_tasks(L)) * sizeof(unsigned short) * 1 + 16;
+}
+
+__device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
+    int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    int Nmax = imax3(Ng, Ns, Ni);
+    double* p = base;
+    auto take = [&](int n) { double* r = p; p += n; return r; };
+    S.N = take(pad2(Ng)); S.qee = take(pad2(Ng)); S.psyn = take(pad2(Ns)); S.pic = take(pad2(Ni)); S.agg = take(pad2(Ni));
+    S.Lsyn = take(pad2(Ns)); S.Lic = take(pad2(Ni));
+    S.n = take(pad2(Nt)); S.Ln = take(pad2(Nt)); S.Lm = take(pad2(Nt)); S.y = take(pad2(Nt)); S.cum = take(pad2(Nt));
+    S.bcom = take(pad2(Ng));
+    S.cp = take(pad2(Nmax)); S.dp = take(pad2(Nmax));
+    S.ne = take(pad2(Ng)); S.av = take(pad2(Ng)); S.u = take(pad2(Ng)); S.v = take(pad2(Ng)); S.inuc = take(pad2(Ng));
+    S.Qsyn = take(pad2(Ns)); S.aS = take(pad2(Ns)); S.aI = take(pad2(Ni)); S.QIC = take(pad2(Ni));
+    S.tri = take(Nt * 4);
+    S.gS = take(pad2(Ng)); S.lgS = take(pad2(Ng)); S.inv4gS = take(pad2(Ng));
+    S.epsS = take(pad2(Ni)); S.lnu4S = take(pad2(Ni)); S.nuoS = take(pad2(Ni));
+    S.sfx = take(4 * pad2(Nt));
+    int NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    S.partial = take(NW * NiPad);
+    S.tasks = reinterpret_cast<unsigned short*>(p);
+    S.ntasks = reinterpret_cast<int*>(S.tasks + pad2(ic_max_tasks(L)));
+}
+
+// Per-walker context: table pointers + scalars of the current step
+struct Ctx {
+    Layout L;
+    const double* T;      // double tables of this walker
+    const int* TI;        // int tables of this walker
+    StepFlags F;
+    double R0, B0, m, Vexp, dt, tinit;
+    double Rad, B, V;     // current step
+};
+
+// ---------------------------------------------------------------------------------------------
+// load the static IC inputs and build the IC task list (once per walker)
+template <int NT>
+__device__ void ic_prepare(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < L.Ng; j += NT) {
+        S.gS[j] = C.T[L.g + j]; S.lgS[j] = C.T[L.lg + j]; S.inv4gS[j] = C.T[L.inv4g + j];
+    }
+    for (int o = tid; o < L.Ni; o += NT) {
+        S.epsS[o] = C.T[L.eps + o]; S.lnu4S[o] = C.T[L.lnu4 + o]; S.nuoS[o] = C.T[L.nic + o];
+    }
+    for (int i = tid; i < L.Nt; i += NT) {
+        S.tri[4 * i + 0] = C.T[L.invnt + i];
+        S.tri[4 * i + 1] = C.T[L.l2nt + i];
+        S.tri[4 * i + 2] = 0.0;
+        S.tri[4 * i + 3] = 0.0;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // active tasks in (o-group major, gamma-block minor) order.  A pair is active iff gamma > eps_o
+        // (the reference's `q_IC[0] > 0.` test, LeHaMoC_f.py:117); eps grows with o, gamma with j.
+        const int No = L.Ni - 1;                                   // outgoing frequencies nu_ic[0..Ni-2]
+        const int nog = (No + IC_OG - 1) / IC_OG, ngb = (L.Ng + IC_GB - 1) / IC_GB;
+        int nt = 0;
+        for (int og = 0; og < nog; ++og) {
+            double emin = S.epsS[og * IC_OG];
+            for (int gb = 0; gb < ngb; ++gb) {
+                int jhi = min(gb * IC_GB + IC_GB - 1, L.Ng - 1);
+                if (S.gS[jhi] > emin) S.tasks[nt++] = (unsigned short)((og << 8) | gb);
+            }
+        }
+        *S.ntasks = nt;
+    }
+    __syncthreads();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Phase B: photons_tot (LeHaMoC_f.py:154-156) with the /Volume of LeMoC.py:204.  The external
+// fields enter as densities already interpolated on nu_tot (host), because
+// 10**interp(log10(bb*V))/V == 10**interp(log10(bb)) up to rounding.
+template <int NT>
+__device__ void phase_photons(const Ctx& C, Smem& S, bool aux) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    for (int k = tid; k < L.Ns; k += NT) S.Lsyn[k] = log10(S.psyn[k]);
+    for (int k = tid; k < L.Ni; k += NT) S.Lic[k] = log10(S.pic[k]);
+    __syncthreads();
+    const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;          // sigmaT*R*m_el*c**2./h  LeHaMoC_f.py:170
+    for (int k = tid; k < L.Nt; k += NT) {
+        double a = interp_eval(S.Lsyn, C.TI[L.ps_j + k], C.T[L.ps_dx + k], C.T[L.ps_Dx + k]);
+        double b = interp_eval(S.Lic, C.TI[L.pi_j + k], C.T[L.pi_dx + k], C.T[L.pi_Dx + k]);
+        double nk = (exp10(a) + exp10(b)) / C.V + C.T[L.ext + k];
+        S.n[k] = nk;
+        if (aux) {
+            S.Ln[k] = log10(nk);
+            S.Lm[k] = log10(nk * kPC.mc2_h);
+            S.y[k] = C.T[L.xt + k] * nk * K;
+            S.tri[4 * k + 2] = C.T[L.wt + k] * nk;               // p_i = trapz weight x photons
+        }
+    }
+    __syncthreads();
+}
+
+// Phase C: U_ph_f (LeHaMoC_f.py:160-172) -> b_Com (LeMoC.py:232)
+template <int NT>
+__device__ void phase_uph(const Ctx& C, Smem& S, double* U_out /*smem or null*/) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    const int Nt = L.Nt;
+    // exclusive prefix of the trapezoids of np.trapz(y, x): cum[m] = sum_{i<m} (x[i+1]-x[i])*(y[i+1]+y[i])/2
+    for (int m = tid; m < Nt; m += NT) {
+        double s = 0.0;
+        for (int i = 0; i < m; ++i)
+            s += (C.T[L.xt + i + 1] - C.T[L.xt + i]) * (S.y[i + 1] + S.y[i]) / 2.0;
+        S.cum[m] = s;
+    }
+    __syncthreads();
+    const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;
+    const double pre = kPC.mc2 / (kPC.sigmaT * C.Rad);
+    // the `else` branch value U_ph_tot integrates nu*n*K over nu (not x) on nu[:-1]  LeHaMoC_f.py:162
+    for (int j = tid; j < L.Ng; j += NT) {
+        int idx = C.TI[L.u_idx + j];
+        double U;
+        if (idx >= 1) {
+            double v = interp_eval(S.Ln, C.TI[L.u_j + j], C.T[L.u_dx + j], C.T[L.u_Dx + j]);
+            double xT = C.T[L.u_xT + j];
+            double yT = xT * exp10(v) * K;
+            double xm = C.T[L.xt + idx - 1];
+            U = pre * (S.cum[idx - 1] + (xT - xm) * (yT + S.y[idx - 1]) / 2.0);
+        } else if (idx == 0) {
+            U = 0.0;       // nu_T below the grid: the reference would raise (max of empty); unreachable
+        } else {
+            double s = 0.0;
+            for (int i = 0; i < Nt - 2; ++i) {
+                double y0 = C.T[L.nt + i] * S.n[i] * K, y1 = C.T[L.nt + i + 1] * S.n[i + 1] * K;
+                s += (C.T[L.nt + i + 1] - C.T[L.nt + i]) * (y1 + y0) / 2.0;
+            }
+            U = pre * s;
+        }
+        if (U_out) U_out[j] = U;
+        S.bcom[j] = 4.0 / 3.0 * kPC.sigmaT * (kPC.c * U) / kPC.mc2;   // LeMoC.py:232
+    }
+    __syncthreads();
+}
+
+// serial upper-bidiagonal back-substitution, exactly thomas() with a == 0 (LeHaMoC_f.py:250-262)
+__device__ __forceinline__ void backsub(const double* __restrict__ cp, const double* __restrict__ dp,
+                                        double* __restrict__ x, int n) {
+    double xv = dp[n - 1];
+    x[n - 1] = xv;
+    for (int i = n - 2; i >= 0; --i) {
+        xv = dp[i] - cp[i] * xv;
+        x[i] = xv;
+    }
+}
+
+// Phase D: electron equation (LeMoC.py:206-247)
+template <int NT>
+__device__ void phase_electrons(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    const int n = L.Ng - 2;
+    const double dt = C.dt;
+    const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
+    const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (C.B * C.B) : 0.0;
+    const double esc = kPC.c / C.Rad * (double)C.F.esc;
+    for (int j = tid; j < n; j += NT) {
+        double smj = C.T[L.sm + j], spj = C.T[L.sp + j];
+        double syn_m = b_syn * smj, syn_p = b_syn * spj;
+        double ic_m = 0.0, ic_p = 0.0;
+        if (C.F.ic_l) { ic_m = S.bcom[j + 1] * smj; ic_p = S.bcom[j + 2] * spj; }
+        double ad_m = b_ad * C.T[L.am + j], ad_p = b_ad * C.T[L.ap + j];
+        double V2 = 1.0 + dt * (esc + syn_m + ic_m + ad_m);
+        double V3 = -dt * (syn_p + ic_p + ad_p);
+        double d = S.N[j + 1];
+        if (C.F.inj) d += C.T[L.elinj + j + 1] * dt;
+        d += (S.qee[j + 1] * dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (tid == 0) backsub(S.cp, S.dp, S.N + 1, n);
+    __syncthreads();
+}
+
+// Phase E: per-gamma vectors consumed by the contractions
+template <int NT>
+__device__ void phase_vectors(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    const int Ng = L.Ng;
+    const double dgl = C.T[L.lg + 1] - C.T[L.lg + 0];            // dg_l_el  LeMoC.py:118
+    for (int j = tid; j < Ng; j += NT) S.ne[j] = S.N[j] / C.V;
+    __syncthreads();
+    for (int j = tid; j < Ng; j += NT) {
+        double gj = S.gS[j];
+        double nej = S.ne[j];
+        double nuc = kPC.nuc_pref * C.B * (gj * gj);                // nu_c(g, B)  LeHaMoC_f.py:78-79
+        S.inuc[j] = 1.0 / nuc;
+        S.av[j] = C.T[L.wg + j] * (nej * (1.0 / gj));                 // trapz weight x Np*g**(-1.)
+        S.u[j] = C.T[L.wg + j] * (nej * C.T[L.g13 + j]);
+        double vj = 0.0;
+        if (j >= 1 && j <= Ng - 2) {
+            double D = (S.ne[j + 1] - nej) / dgl - 2.0 * nej;        // np.diff(N_el[1:])/dg_l_el-2.*N_el[1:-1]
+            vj = C.T[L.wgi + j] * (pow(2.0 * nuc, -1.0 / 3.0) * D);
+        }
+        S.v[j] = vj;
+    }
+    __syncthreads();
+}
+
+// Phase F1: synchrotron emissivity + SSA rows; one warp per frequency, lanes over gamma.
+// exp(-nu/nu_c) is shared between Q_syn_space (nu/(a_cr g^2)) and aSSA (nu/nu_c(g,B)) on the nu_syn grid.
+template <int NT>
+__device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
+    const Layout& L = C.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni;
+    const bool need_q = C.F.syn_e, need_a = C.F.ssa;
+    if (!need_q && !need_a) return;
+    const int nrows = Ns + (need_a ? Ni : 0);
+    const double qpref = kPC.C_syn * pow(C.B, 2.0 / 3.0);
+    const double apref = kPC.ssa_pref * C.B;
+    for (int row = warp; row < nrows; row += NW) {
+        const bool is_syn = row < Ns;
+        const int k = is_syn ? row : row - Ns;
+        if (!all_rows) {        // the drivers only consume [1:] / [1:-1]  (LeMoC.py:268-276)
+            if (k == 0) continue;
+            if (is_syn ? (k > Ns - 2) : (k > Ni - 2)) continue;
+        }
+        const double nu = is_syn ? C.T[L.nsyn + k] : C.T[L.nic + k];
+        const int jm = is_syn ? C.TI[L.jm_syn + k] : 0;
+        const bool do_q = is_syn && need_q && (k < Ns - 1);
+        double sq = 0.0, sa = 0.0;
+        for (int j = lane; j < Ng; j += 32) {
+            double x = nu * S.inuc[j];
+            double E = (x > 745.2) ? 0.0 : exp(-x);
+            if (do_q && j >= jm) sq = fma(E, S.u[j], sq);
+            sa = fma(E, S.v[j], sa);
+        }
+        sq = warp_sum(sq);
+        sa = warp_sum(sa);
+        if (lane == 0) {
+            if (is_syn) {
+                if (k < Ns - 1) S.Qsyn[k] = do_q ? qpref * C.T[L.nm23s + k] * sq : 0.0;
+                S.aS[k] = need_a ? apref * C.T[L.nm53s + k] * sa : 0.0;
+            } else {
+                S.aI[k] = apref * C.T[L.nm53i + k] * sa;
+            }
+        }
+    }
+}
+
+// Phase F2, path R: Blumenthal-Gould/Jones triple sum with the kernel recomputed in registers.
+//   F = 2q ln q + (1+2q)(1-q) + G(1-q),  q = A/nu_i,  A = nu_o/(4 g (g-eps)),  G = w^2/(2(1+w)), w = eps/(g-eps)
+//     = G1 + q*(c1 - 2 ln nu_i - 2q),    G1 = 1+G,    c1 = 1 - G + 2 ln A          (exact regrouping)
+// per (o, gamma) pair: one reciprocal + one log; per (o, gamma, nu_i) element: 1 DMUL, 1 DADD, 3 DFMA on the
+// FP64 pipe; the clamp max(F,0) is a sign-mask on the integer pipe (fmax() would add a DSETP + 5 ALU ops).
+template <int NT>
+__device__ void phase_ic_R(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
+    const int Ng = L.Ng, No = L.Ni - 1, Ntar = L.Nt - 1;
+    const int NiPad = ((L.Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    double* part = S.partial + warp * NiPad;
+    for (int o = lane; o < NiPad; o += 32) part[o] = 0.0;
+    __syncwarp();
+    const int nt = *S.ntasks;
+    const int t0 = (int)(((long long)nt * warp) / NW), t1 = (int)(((long long)nt * (warp + 1)) / NW);
+    const int osub = lane >> 2, gsub = lane & 3;
+    int cur_og = -1;
+    double run = 0.0;
+    const double2* tri2 = reinterpret_cast<const double2*>(S.tri);
+    for (int t = t0; t < t1; ++t) {
+        const int og = S.tasks[t] >> 8, gb = S.tasks[t] & 255;
+        if (og != cur_og) {
+            if (cur_og >= 0) {
+                run += __shfl_xor_sync(0xffffffffu, run, 1);
+                run += __shfl_xor_sync(0xffffffffu, run, 2);
+                if (gsub == 0) part[cur_og * IC_OG + osub] = run;
+            }
+            cur_og = og; run = 0.0;
+        }
+        const int o = og * IC_OG + osub;
+        const bool ovalid = o < No;
+        const double eps = ovalid ? S.epsS[o] : 0.0;
+        const double nuo = ovalid ? S.nuoS[o] : 0.0;
+        const double lnu4 = ovalid ? S.lnu4S[o] : 0.0;
+        double A[IC_PT], c1[IC_PT], G1[IC_PT], acc[IC_PT], wa[IC_PT];
+#pragma unroll
+        for (int r = 0; r < IC_PT; ++r) {
+            const int j = gb * IC_GB + r * IC_GL + gsub;
+            const bool act = ovalid && (j < Ng) && (S.gS[min(j, Ng - 1)] > eps);
+            const int jj = act ? j : 0;
+            const double d = act ? (S.gS[jj] - eps) : 1.0;
+            const double rr = 1.0 / d;
+            const double i4 = S.inv4gS[jj];
+            const double Gv = 2.0 * eps * eps * rr * i4;
+            A[r] = act ? nuo * rr * i4 : 0.0;
+            G1[r] = act ? 1.0 + Gv : 0.0;
+            c1[r] = act ? (1.0 - Gv) + 2.0 * (lnu4 - S.lgS[jj] - log(d)) : 0.0;
+            wa[r] = act ? S.av[jj] : 0.0;
+            acc[r] = 0.0;
+        }
+#pragma unroll 2
+        for (int i = 0; i < Ntar; ++i) {
+            const double2 t01 = tri2[2 * i];         // {1/nu_i, 2 ln nu_i}
+            const double pi = S.tri[4 * i + 2];      // w_i n_i
+#pragma unroll
+            for (int r = 0; r < IC_PT; ++r) {
+                double qv = A[r] * t01.x;
+                double s = c1[r] - t01.y;
+                s = fma(-2.0, qv, s);
+                double Fv = fma(qv, s, G1[r]);
+                Fv = clamp_neg_to_zero(Fv);          // function_IC[function_IC < 0.] = 0.
+                acc[r] = fma(pi, Fv, acc[r]);
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < IC_PT; ++r) run = fma(wa[r], acc[r], run);
+    }
+    if (cur_og >= 0) {
+        run += __shfl_xor_sync(0xffffffffu, run, 1);
+        run += __shfl_xor_sync(0xffffffffu, run, 2);
+        if (gsub == 0) part[cur_og * IC_OG + osub] = run;
+    }
+}
+
+// Phase F2, path S: the nu_i sum collapses to four suffix sums because max(F,0) only cuts the sum at the
+// first nu_i > A (F > 0 <=> q < 1) and F is rank-4 separable in (o,gamma) x (i)  (SURVEY.md 7.1b-1).
+template <int NT>
+__device__ void phase_ic_S(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT / 32;
+    const int Ng = L.Ng, No = L.Ni - 1, Ntar = L.Nt - 1;
+    const int NtP = pad2(L.Nt);
+    // suffix sums P_k[j] = sum_{i>=j} p_i * {1, 1/nu_i, (1/nu_i)*2ln nu_i, 1/nu_i^2};  P_k[Ntar] = 0
+    if (tid < 4) {
+        double s = 0.0;
+        double* P = S.sfx + tid * NtP;
+        P[Ntar] = 0.0;
+        for (int i = Ntar - 1; i >= 0; --i) {
+            double inv = S.tri[4 * i], l2 = S.tri[4 * i + 1], p = S.tri[4 * i + 2];
+            double f = (tid == 0) ? 1.0 : (tid == 1) ? inv : (tid == 2) ? inv * l2 : inv * inv;
+            s = fma(p, f, s);
+            P[i] = s;
+        }
+    }
+    __syncthreads();
+    const double* P0 = S.sfx, *P1 = S.sfx + NtP, *P2 = S.sfx + 2 * NtP, *P3 = S.sfx + 3 * NtP;
+    const double lnu0 = 0.5 * S.tri[1];                                 // ln nu_0
+    const double inv_dl = (double)(Ntar - 1) / (0.5 * S.tri[4 * (Ntar - 1) + 1] - lnu0);
+    for (int o = warp; o < No; o += NW) {
+        const double eps = S.epsS[o], nuo = S.nuoS[o], lnu4 = S.lnu4S[o];
+        double sum = 0.0;
+        for (int j = lane; j < Ng; j += 32) {
+            const double gj = S.gS[j];
+            if (!(gj > eps)) continue;
+            const double d = gj - eps, rr = 1.0 / d, i4 = S.inv4gS[j];
+            const double Gv = 2.0 * eps * eps * rr * i4;
+            const double Av = nuo * rr * i4;
+            const double lnA = lnu4 - S.lgS[j] - log(d);
+            // first i with nu_i > A (q < 1): arithmetic guess on the log-uniform grid, then exact fix-up
+            int is = (int)floor((lnA - lnu0) * inv_dl) + 1;
+            is = max(0, min(is, Ntar));
+            while (is > 0 && !(Av * S.tri[4 * (is - 1)] >= 1.0)) --is;       // nu_{is-1} > A  -> move left
+            while (is < Ntar && (Av * S.tri[4 * is] >= 1.0)) ++is;           // nu_is <= A      -> move right
+            const double G1 = 1.0 + Gv, c1 = (1.0 - Gv) + 2.0 * lnA;
+            // sum_i p_i [G1 + q(c1 - 2 ln nu_i - 2 q)],  q = A/nu_i
+            double inner = G1 * P0[is] + Av * (c1 * P1[is] - P2[is] - 2.0 * Av * P3[is]);
+            sum = fma(S.av[j], inner, sum);
+        }
+        sum = warp_sum(sum);
+        if (lane == 0) S.QIC[o] = kPC.ic_pref * sum;
+    }
+}
+
+template <int NT>
+__device__ void phase_ic_finish_R(const Ctx& C, Smem& S) {
+    const int NW = NT / 32;
+    const int No = C.L.Ni - 1;
+    const int NiPad = ((C.L.Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    for (int o = threadIdx.x; o < No; o += NT) {
+        double s = 0.0;
+        for (int w = 0; w < NW; ++w) s += S.partial[w * NiPad + o];
+        S.QIC[o] = kPC.ic_pref * s;                                         // sigmaT*c*0.75*trapz(...)
+    }
+}
+
+// Phase G: photon equations (LeMoC.py:267-277)
+template <int NT>
+__device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    const double dt = C.dt, cc = kPC.c;
+    const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
+    const double esc = cc / C.Rad;
+    const int ns = L.Ns - 2, ni = L.Ni - 2;
+    // synchrotron photons -> cp/dp[0..ns)
+    for (int j = tid; j < ns; j += NT) {
+        double aS = C.F.ssa ? -fabs(S.aS[j + 1]) : 0.0;                  // -np.absolute(aSSA)  LeMoC.py:261
+        double V2 = 1.0 + dt * (esc + b_ad * C.T[L.asm_ + j] - aS * cc);
+        double V3 = -dt * (b_ad * C.T[L.asp_ + j]);
+        double Q = C.F.syn_e ? S.Qsyn[j + 1] / cor : 0.0;                // np.divide(Q_syn, cor_factor)
+        double d = S.psyn[j + 1] + 4.0 * M_PI * (Q * dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (C.F.ad) { if (tid == 0) backsub(S.cp, S.dp, S.psyn + 1, ns); }
+    else { for (int j = tid; j < ns; j += NT) S.psyn[j + 1] = S.dp[j]; }   // V3 == 0: diagonal system
+    __syncthreads();
+    for (int j = tid; j < ni; j += NT) {
+        double aI = C.F.ssa ? -fabs(S.aI[j + 1]) : 0.0;
+        double V2 = 1.0 + dt * (esc + b_ad * C.T[L.aim + j] + S.agg[j + 1] * cc - aI * cc);
+        double V3 = -dt * (b_ad * C.T[L.aip + j]);
+        double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
+        double d = S.pic[j + 1] + (Q * dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (C.F.ad) { if (tid == 0) backsub(S.cp, S.dp, S.pic + 1, ni); }
+    else { for (int j = tid; j < ni; j += NT) S.pic[j + 1] = S.dp[j]; }
+    __syncthreads();
+}
+
+// Phase H: a_gg (LeHaMoC_f.py:127-137) and Q_ee_f (LeHaMoC_f.py:140-151); warp per row, lanes over samples.
+// `Lng`/(stencil) give n_g: log10 of the field Q_ee_f's n_g is interpolated from.
+template <int NT>
+__device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_out, double* qee_out) {
+    const Layout& L = C.L;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
+    const int NP = L.NP, Ni = L.Ni, Ng = L.Ng;
+    const int nrows = Ni + (Ng - 1);
+    for (int row = warp; row < nrows; row += NW) {
+        const bool is_a = row < Ni;
+        const int r = is_a ? row : row - Ni;
+        const double* K = C.T + (is_a ? L.aggK : L.qeeK) + (size_t)r * NP;
+        const double* Tt = C.T + (is_a ? L.aggT : L.qeeT) + (size_t)r * NP;
+        const int* J = C.TI + (is_a ? L.aggJ : L.qeeJ) + (size_t)r * NP;
+        double s = 0.0;
+        for (int e = lane; e < NP; e += 32) {
+            double Kv = K[e];
+            double ph = exp10(lerp_log(S.Lm, J[e], Tt[e]));
+            s = fma(Kv, ph, s);
+        }
+        s = warp_sum(s);
+        if (lane == 0) {
+            if (is_a) agg_out[r] = s;
+            else {
+                double ng = 0.0;
+                if (2.0 * S.gS[r] > 1.0)
+                    ng = exp10(interp_eval(Lng, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
+                qee_out[r] = kPC.qee_pref * (ng * s);
+            }
+        }
+    }
+}
+
+}  // namespace lhm

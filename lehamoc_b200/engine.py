@@ -1,0 +1,196 @@
+"""Thin Python owner of one lhm_handle: PyTorch supplies device memory and the CUDA stream, liblhm.so does
+the work.  One Engine per (grid sizes, flags, variant) per GPU; not thread-safe (one process per GPU)."""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LhmError, lhm_config, check
+from .setup_host import Batch
+
+IC_PATHS = {"R": _lib.LHM_IC_PATH_R, "S": _lib.LHM_IC_PATH_S}
+
+
+def _require_cuda():
+    if not torch.cuda.is_available():
+        raise LhmError("no CUDA device: lehamoc_b200 has no CPU fallback (the CPU oracle lives in oracle/ "
+                       "and is test infrastructure only)")
+
+
+def _ptr(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+class Engine:
+    def __init__(self, cfg: dict, max_walkers: int, ic_path: str = "R", device: int | None = None):
+        _require_cuda()
+        self.lib = _lib.load()
+        self.device = torch.cuda.current_device() if device is None else int(device)
+        self.cfg = dict(cfg)
+        self.ic_path = ic_path
+        c = lhm_config()
+        for k, v in cfg.items():
+            setattr(c, k, int(v))
+        c.ic_path = IC_PATHS[ic_path]
+        c.max_walkers = int(max_walkers)
+        self._c = c
+        self.max_walkers = int(max_walkers)
+        self.stream = torch.cuda.current_stream(self.device)
+        h = C.c_void_p()
+        check(self.lib.lhm_create(C.byref(c), self.device, C.c_void_p(self.stream.cuda_stream), C.byref(h)), "lhm_create")
+        self.h = h
+        self.W = 0
+        self._keep = None           # device inputs of the current batch (the library reads them again)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.lhm_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- sizes ------------------------------------------------------------------------------------
+    @property
+    def Ng(self): return self.cfg["Ng"]
+    @property
+    def Ns(self): return self.cfg["Ns"]
+    @property
+    def Ni(self): return self.cfg["Ni"]
+    @property
+    def Nt(self): return self.cfg["Nt"]
+
+    def smem_bytes(self):
+        return self.lib.lhm_step_smem_bytes(self.h)
+
+    def _dev(self, a):
+        if isinstance(a, torch.Tensor):
+            return a.to(device=f"cuda:{self.device}", dtype=torch.float64).contiguous()
+        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(f"cuda:{self.device}", non_blocking=True)
+
+    def _new(self, *shape):
+        return torch.empty(shape, dtype=torch.float64, device=f"cuda:{self.device}")
+
+    # -- batch set-up -----------------------------------------------------------------------------
+    def setup(self, batch: Batch):
+        """Copy the packed inputs to the device and build the per-walker tables (lhm_setup_batch)."""
+        for k in ("Ng", "Ns", "Ni", "Nt"):
+            if batch.cfg[k] != self.cfg[k]:
+                raise LhmError(f"batch {k}={batch.cfg[k]} does not match the engine ({self.cfg[k]})")
+        W = batch.W
+        dev = [self._dev(a) for a in batch.arrays()]
+        self.setup_device(W, *dev)
+
+    def setup_device(self, W, consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext):
+        self._keep = (consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext)
+        check(self.lib.lhm_setup_batch(self.h, int(W), *[_ptr(t) for t in self._keep]), "lhm_setup_batch")
+        self.W = int(W)
+
+    # -- the whole time integration ---------------------------------------------------------------
+    def run(self, snapshots: int = 0, want_N: bool = True, want_sed: bool = True):
+        S = snapshots if snapshots > 0 else 1
+        N = self._new(self.W, S, self.Ng) if want_N else None
+        sed = self._new(self.W, S, self.Nt) if want_sed else None
+        check(self.lib.lhm_run_batch(self.h, _ptr(N), _ptr(sed), int(snapshots)), "lhm_run_batch")
+        if snapshots == 0:
+            N = N[:, 0] if N is not None else None
+            sed = sed[:, 0] if sed is not None else None
+        return N, sed
+
+    def run_into(self, N, sed, snapshots: int = 0):
+        check(self.lib.lhm_run_batch(self.h, _ptr(N), _ptr(sed), int(snapshots)), "lhm_run_batch")
+
+    def run_host(self, batch: Batch, snapshots: int = 0, N_out=None, sed_out=None):
+        """lhm_run_batch_host: host buffers in, host buffers out (H2D + set-up + run + D2H + sync)."""
+        W = batch.W
+        S = snapshots if snapshots > 0 else 1
+        if N_out is None:
+            N_out = np.empty((W, S, self.Ng))
+        if sed_out is None:
+            sed_out = np.empty((W, S, self.Nt))
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        check(self.lib.lhm_run_batch_host(self.h, W, *[hp(a) for a in batch.arrays()], hp(N_out), hp(sed_out),
+                                          int(snapshots)), "lhm_run_batch_host")
+        self.W = W
+        self._keep = None
+        if snapshots == 0:
+            return N_out.reshape(W, S, self.Ng)[:, 0], sed_out.reshape(W, S, self.Nt)[:, 0]
+        return N_out, sed_out
+
+    def last_timings(self):
+        """(setup_ms, cor_ms, run_ms) of the most recent launches, measured with CUDA events on the stream."""
+        a, b, c = C.c_float(), C.c_float(), C.c_float()
+        check(self.lib.lhm_last_timings(self.h, C.byref(a), C.byref(b), C.byref(c)), "lhm_last_timings")
+        return a.value, b.value, c.value
+
+    # -- function-level entry points (unit-test twins of LeHaMoC_f.py) ------------------------------
+    def cor_factor(self):
+        out = self._new(self.W)
+        check(self.lib.lhm_cor_factor_batch(self.h, _ptr(out)), "lhm_cor_factor_batch")
+        return out
+
+    def photons_tot(self, photons_syn, photons_IC, radius):
+        out = self._new(self.W, self.Nt)
+        a, b, r = self._dev(photons_syn), self._dev(photons_IC), self._dev(radius)   # keep alive across the launch
+        check(self.lib.lhm_photons_tot_batch(self.h, _ptr(a), _ptr(b), _ptr(r), _ptr(out)), "lhm_photons_tot_batch")
+        return out
+
+    def U_ph(self, n, radius):
+        out = self._new(self.W, self.Ng)
+        a, r = self._dev(n), self._dev(radius)
+        check(self.lib.lhm_uph_batch(self.h, _ptr(a), _ptr(r), _ptr(out)), "lhm_uph_batch")
+        return out
+
+    def syn_ssa(self, n_e, Bfield):
+        Q = self._new(self.W, self.Ns - 1)
+        aS = self._new(self.W, self.Ns)
+        aI = self._new(self.W, self.Ni)
+        a, b = self._dev(n_e), self._dev(Bfield)
+        check(self.lib.lhm_syn_ssa_batch(self.h, _ptr(a), _ptr(b), _ptr(Q), _ptr(aS), _ptr(aI)), "lhm_syn_ssa_batch")
+        return Q, aS, aI
+
+    def ic_emissivity(self, n_e, n, ic_path: str | None = None, out=None):
+        Q = self._new(self.W, self.Ni - 1) if out is None else out
+        path = IC_PATHS[ic_path or self.ic_path]
+        a, b = self._dev(n_e), self._dev(n)
+        check(self.lib.lhm_ic_emissivity_batch(self.h, _ptr(a), _ptr(b), _ptr(Q), path), "lhm_ic_emissivity_batch")
+        return Q
+
+    def gg(self, n, photons_IC_dens=None):
+        a = self._new(self.W, self.Ni)
+        Q = self._new(self.W, self.Ng - 1)
+        nn = self._dev(n)
+        pic = self._dev(photons_IC_dens) if photons_IC_dens is not None else None
+        check(self.lib.lhm_gg_batch(self.h, _ptr(nn), _ptr(pic), _ptr(a), _ptr(Q)), "lhm_gg_batch")
+        return a, Q
+
+
+def bidiag_solve(b, c, d, device=None):
+    """thomas() with a == 0 for a batch of systems [W, n] (lhm_bidiag_solve_batch)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = f"cuda:{torch.cuda.current_device() if device is None else device}"
+    tb, tc, td = (torch.as_tensor(np.atleast_2d(x), dtype=torch.float64).to(dev).contiguous() for x in (b, c, d))
+    x = torch.empty_like(td)
+    W, n = td.shape
+    check(lib.lhm_bidiag_solve_batch(W, n, _ptr(tb), _ptr(tc), _ptr(td), _ptr(x),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lhm_bidiag_solve_batch")
+    return x
+
+
+def fp64_peak_tflops(device: int = 0) -> float:
+    _require_cuda()
+    lib = _lib.load()
+    out = C.c_double()
+    check(lib.lhm_fp64_peak_probe(device, C.c_void_p(torch.cuda.current_stream(device).cuda_stream), C.byref(out)),
+          "lhm_fp64_peak_probe")
+    return out.value

@@ -1,0 +1,234 @@
+"""Host side of a batch: parameter files, grids and initial conditions for W walkers at once.
+
+Mirrors the set-up part of the reference drivers with the reference's own NumPy expressions, so
+grid doubles and integer indices are identical by construction:
+  * LeMoC/LeMoC.py:60-191   (variant "script": every parameter comes from the parameter file),
+  * Fit_emcee/Code.py:51-180 (variant "code": six free parameters + frozen parameter file).
+Everything state-dependent happens on the GPU; nothing here depends on N(gamma) or n(nu).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from .constants import c, h, kb, m_el, q, sigmaT, SENTINEL
+
+if not hasattr(np, "trapz"):                       # numpy >= 2.4
+    np.trapz = np.trapezoid                        # type: ignore[attr-defined]
+
+FLAG_KEYS = ("inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag",
+             "SSA_l_flag", "gg_flag", "esc_flag")
+# keys of LeMoC/Parameters*.txt that may differ between the walkers of one batch
+WALKER_KEYS = ("g_min_el", "g_max_el", "g_PL_min", "g_PL_max", "p_el", "L_el", "R0", "B0")
+SCRIPT_KEYS = ("time_init", "time_end", "step_alg", "g_min_el", "g_max_el", "g_PL_min", "g_PL_max", "grid_g_el",
+               "grid_nu", "p_el", "L_el", "Vexp", "R0", "B0", "m", "delta") + FLAG_KEYS + (
+               "BB_flag", "BB_temperature", "GB_ext", "PL_flag", "dE_dV_ph", "nu_min_ph", "nu_max_ph", "s_ph", "User_ph")
+CODE_KEYS = tuple(k for k in SCRIPT_KEYS if k not in WALKER_KEYS + ("delta",))
+
+
+def read_parameter_file(fileName) -> dict:
+    """`key = value` per line, every value a float (LeMoC.py:60-65, Code.py:63-68)."""
+    params = {}
+    with open(fileName) as fileObj:
+        for line in fileObj:
+            line = line.strip()
+            if not line:
+                continue
+            key_value = line.split("=")
+            params[key_value[0].strip()] = float(key_value[1].strip())
+    return params
+
+
+def _flag01(P, key):
+    v = float(P[key])
+    if v not in (0.0, 1.0):
+        raise ValueError(f"{key} = {v}: the drivers compare flags with ==1./==0.; only 0 or 1 is supported")
+    return int(v)
+
+
+@dataclass
+class Batch:
+    """Packed inputs of lhm_setup_batch for W walkers (all float64, C-contiguous)."""
+    variant: str
+    cfg: dict                      # fields of lhm_config except ic_path/max_walkers
+    consts: np.ndarray             # [W, LHM_NCONST]
+    g_el: np.ndarray               # [W, Ng]
+    nu_syn: np.ndarray             # [W, Ns]  (appended point included)
+    nu_ic: np.ndarray              # [W, Ni]
+    nu_tot: np.ndarray             # [W, Nt]
+    el_inj: np.ndarray             # [W, Ng]
+    ext: np.ndarray                # [W, Nt]
+    nsteps: np.ndarray             # [W] int
+    index_PL_min: np.ndarray = field(default=None)
+    index_PL_max: np.ndarray = field(default=None)
+
+    @property
+    def W(self):
+        return self.consts.shape[0]
+
+    def arrays(self):
+        return (self.consts, self.g_el, self.nu_syn, self.nu_ic, self.nu_tot, self.el_inj, self.ext)
+
+
+def _nu_c(gamma, B):                               # LeHaMoC_f.py:78-79
+    return 3. / (4. * np.pi) * q * B / (m_el * c) * gamma ** 2.
+
+
+def _Q_el_Lum(L_el, p_el, g_min_el, g_max_el):     # LeHaMoC_f.py:52-56
+    if p_el == 2.:
+        return L_el / (m_el * c ** 2. * np.log(g_max_el / g_min_el))
+    return L_el * (-p_el + 2.) / (m_el * c ** 2. * (g_max_el ** (-p_el + 2.) - g_min_el ** (-p_el + 2.)))
+
+
+def _Lum_e_inj(comp, R):                           # LeHaMoC_f.py:66-67
+    return 4. * np.pi * R * m_el * c ** 3. * comp / sigmaT
+
+
+def external_fields(F: dict, nu_tot: np.ndarray) -> np.ndarray:
+    """BB + PL + user photon densities on nu_tot as they come out of photons_tot (LeMoC.py:140-169 through
+    LeHaMoC_f.py:154-156), for one nu_tot grid.  With BB_flag = 0 the BB term is log10(0) = -inf everywhere
+    (np.interp's NaN fall-backs give 0) except the last bin, which hits the appended 1e-260 point."""
+    Nt = len(nu_tot)
+    if F["BB_flag"] == 0.:
+        bb = np.zeros(Nt)
+        bb[-1] = SENTINEL
+    else:
+        T = 10 ** float(F["BB_temperature"])
+        nu_bb = np.logspace(np.log10(5.879 * 10 ** 10 * T) - 6., np.log10(5.879 * 10 ** 10 * T) + 1.5, 60)
+        with np.errstate(over="ignore"):
+            Bnu = 2.0 * h * nu_bb ** 3 / c ** 2 / np.expm1(h * nu_bb / (kb * T))    # astropy BlackBody(T)(nu)
+        photons_bb = 4. * np.pi / c * Bnu / (h * nu_bb)
+        GB_norm = np.trapz(photons_bb * h * nu_bb ** 2., np.log(nu_bb)) / float(F["GB_ext"])
+        dN = np.append(photons_bb / GB_norm, SENTINEL)
+        nu_bb = np.append(nu_bb, nu_tot[-1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            bb = 10 ** np.interp(np.log10(nu_tot), np.log10(nu_bb), np.log10(dN))
+    if F["PL_flag"] == 0.:
+        pl = np.zeros(Nt)
+    else:                                          # literal LeMoC.py:155-158 (known to yield inf)
+        sp = np.logspace(float(F["nu_min_ph"]), float(F["nu_max_ph"]), 100)
+        k_ph = (np.trapz(float(F["dE_dV_ph"]) * sp ** (-float(F["s_ph"]) + 1.))) ** (-1.)
+        sp[-1] = 0.
+        with np.errstate(divide="ignore", invalid="ignore"):
+            pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(k_ph * sp ** (-float(F["s_ph"]))))
+    if F["User_ph"] != 0.:
+        raise NotImplementedError("User_ph: Photons_spec_user.txt input (LeMoC.py:165) is not supported yet")
+    return bb + pl
+
+
+def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> Batch:
+    from ._lib import LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B
+    W = len(R0)
+    Ng = int(float(F["grid_g_el"]))
+    Nh = int(float(F["grid_g_el"]) / 2)
+    Nt = int(float(F["grid_nu"]))
+    time_init, time_end, step_alg = float(F["time_init"]), float(F["time_end"]), float(F["step_alg"])
+    Vexp = float(F["Vexp"]) * c
+    dt = step_alg * R0 / c                                                    # LeMoC.py:108
+
+    g_el = np.logspace(g_min_el, g_max_el, Ng, axis=-1)                       # LeMoC.py:115  [W,Ng]
+    # PL window (LeMoC.py:120-128); thresholds with Python float pow like the reference's `10**g_PL_max`
+    thr_max = np.array([10 ** float(x) for x in g_PL_max])
+    thr_min = np.array([10 ** float(x) for x in g_PL_min])
+    gt = g_el > thr_max[:, None]
+    lt = g_el < thr_min[:, None]
+    same = g_PL_max == g_max_el
+    if np.any(~same & ~gt.any(axis=1)) or np.any((g_PL_min != 0.) & ~lt.any(axis=1)):
+        raise ValueError("power-law window outside the gamma grid (the reference raises here too)")
+    index_PL_max = np.where(same, -1, gt.argmax(axis=1))
+    index_PL_min = np.where(g_PL_min == 0., 1, lt.sum(axis=1) - 1)
+
+    nu_syn = np.logspace(7.5, np.log10(7. * _nu_c(g_el[:, -1], B0)) + 1.4, Nh, axis=-1)   # LeMoC.py:131
+    nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
+    nu_tot = np.logspace(np.log10(nu_syn[:, 0]), np.log10(nu_ic[-1]), Nt, axis=-1)         # LeMoC.py:133
+    nu_syn = np.concatenate([nu_syn, nu_tot[:, -1:]], axis=1)                              # LeMoC.py:185
+    nu_ic = np.broadcast_to(nu_ic, (W, Nh)).copy()
+
+    # injection (LeMoC.py:174-175): scalar pieces per walker with NumPy scalars, as the reference evaluates them
+    el_inj = np.full((W, Ng), SENTINEL)
+    cor_Q0 = np.empty(W)
+    for w in range(W):
+        a, b = int(index_PL_min[w]), int(index_PL_max[w])
+        gw = g_el[w]
+        Q0 = _Q_el_Lum(_Lum_e_inj(comp_inj[w], R0[w]), p_el[w], gw[a], gw[b])
+        el_inj[w, a:b] = Q0 * gw[a:b] ** (-p_el[w])
+        cor_Q0[w] = _Q_el_Lum(_Lum_e_inj(comp_cor[w], R0[w]), p_el[w], gw[1], gw[-2])      # LeHaMoC_f.py:202
+
+    # number of steps: range(int(time_end)) (LeMoC.py:196) / while time_real < time_end*R0/c (Code.py:183)
+    if variant == "script":
+        nsteps = np.full(W, int(time_end), dtype=np.int64)
+    else:
+        nsteps = np.zeros(W, dtype=np.int64)
+        t = np.full(W, time_init)
+        lim = time_end * R0 / c
+        live = t < lim
+        while live.any():
+            t = np.where(live, t + dt, t)
+            nsteps += live
+            live = t < lim
+
+    # external fields: identical for walkers that share nu_tot (nu_syn[0] = 10**7.5 and nu_ic[-1] = 1e30 always)
+    ext1 = external_fields(F, nu_tot[0])
+    ext = np.broadcast_to(ext1, (W, Nt)).copy()
+    if not np.all(nu_tot == nu_tot[0]):
+        for w in range(1, W):
+            ext[w] = external_fields(F, nu_tot[w])
+
+    consts = np.zeros((W, LHM_NCONST))
+    consts[:, C_R0] = R0
+    consts[:, C_B0] = B0
+    consts[:, C_M] = float(F["m"])
+    consts[:, C_VEXP] = Vexp
+    consts[:, C_DT] = dt
+    consts[:, C_TINIT] = time_init
+    consts[:, C_NSTEPS] = nsteps
+    consts[:, C_COR_P] = p_el
+    consts[:, C_COR_Q0] = cor_Q0
+    consts[:, C_COR_B] = 10 ** 4.
+    cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=50,
+               loss_minus_one=1 if variant == "script" else 0,       # LeMoC.py:224 vs Code.py:210
+               qee_from_ic=0 if variant == "script" else 1)          # LeMoC.py:283 vs Code.py:269
+    for k in FLAG_KEYS:
+        cfg[k] = _flag01(F, k)
+    # gg_flag is tested with `== 0.` (LeMoC.py:279): anything else switches it on; inj_flag is tested both ways
+    cont = np.ascontiguousarray
+    return Batch(variant, cfg, cont(consts), cont(g_el), cont(nu_syn), cont(nu_ic), cont(nu_tot), cont(el_inj),
+                 cont(ext), nsteps, index_PL_min, index_PL_max)
+
+
+def pack_script(param_sets) -> Batch:
+    """Batch for the LeMoC.py driver.  `param_sets`: one dict (or a list of dicts) with the keys of
+    LeMoC/Parameters*.txt; all walkers must agree on everything except WALKER_KEYS."""
+    if isinstance(param_sets, dict):
+        param_sets = [param_sets]
+    F = param_sets[0]
+    missing = [k for k in SCRIPT_KEYS if k not in F]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")           # the reference raises KeyError likewise
+    for P in param_sets[1:]:
+        for k in SCRIPT_KEYS:
+            if k not in WALKER_KEYS and float(P[k]) != float(F[k]):
+                raise ValueError(f"walkers of one batch must share '{k}'")
+    col = lambda k: np.array([float(P[k]) for P in param_sets])
+    R0 = np.array([10 ** float(P["R0"]) for P in param_sets])                 # LeMoC.py:79
+    B0 = col("B0")
+    comp_el = np.array([sigmaT * 10 ** float(P["L_el"]) / (4. * np.pi * r * m_el * c ** 3)
+                        for P, r in zip(param_sets, R0)])                      # LeMoC.py:110
+    return _pack("script", F, R0, B0, col("g_min_el"), col("g_max_el"), col("g_PL_min"), col("g_PL_max"),
+                 col("p_el"), comp_el, comp_el)
+
+
+def pack_code(thetas, frozen: dict) -> Batch:
+    """Batch for Fit_emcee/Code.py::LeMoC.  thetas [W,6] = [log R0, log B0, log g_min, log g_max, log l_e, p]."""
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    missing = [k for k in CODE_KEYS if k not in frozen]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    R0 = np.array([10 ** float(x) for x in thetas[:, 0]])                      # Code.py:53
+    B0 = np.array([10 ** float(x) for x in thetas[:, 1]])                      # Code.py:54
+    g_PL_min, g_PL_max = thetas[:, 2].copy(), thetas[:, 3].copy()
+    comp_inj = np.array([10 ** float(x) for x in thetas[:, 4]])                # Code.py:163
+    comp_cor = thetas[:, 4].copy()                                             # Code.py:237 passes the log value
+    return _pack("code", frozen, R0, B0, g_PL_min - 1., g_PL_max + 1., g_PL_min, g_PL_max, thetas[:, 5].copy(),
+                 comp_inj, comp_cor)

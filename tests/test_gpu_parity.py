@@ -1,0 +1,296 @@
+"""GPU parity tests (run on a B200: `pytest -m gpu`).  Every comparison goes through the C ABI of liblhm.so;
+the checker is the NumPy oracle and the golden vectors captured from the unmodified reference."""
+import numpy as np
+import pytest
+
+from util import (TOL_LOG10, assert_signed_close, assert_spectra_close, load_golden, quiet)
+
+pytestmark = pytest.mark.gpu
+quiet()
+
+
+@pytest.fixture(scope="module")
+def orc():
+    import lehamoc_oracle
+    return lehamoc_oracle
+
+
+def _run_script(P, ic_path="R", snapshots=True):
+    from lehamoc_b200 import LeMoC
+    return LeMoC.run(P, ic_path=ic_path, snapshots=snapshots)
+
+
+# ---------------------------------------------------------------------------------------------------
+# function-level parity on the captured Test-1 state (every step of the reference run)
+# ---------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def test1_engine():
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    z, P = load_golden("test1")
+    b = pack_script(P)
+    eng = Engine(b.cfg, 1, ic_path="R")
+    eng.setup(b)
+    return eng, z, P, b
+
+
+def _V(R):
+    return 4. * np.pi / 3. * R ** 3.
+
+
+def test_photons_tot_steps(test1_engine):
+    eng, z, P, b = test1_engine
+    R0 = 10 ** P["R0"]
+    sent = 10 ** (-260.)
+    for s in range(1, 10):
+        ps = np.concatenate([[sent], z["step_photons_syn_int"][s - 1], [sent]])
+        pi = np.concatenate([[sent], z["step_photons_IC_int"][s - 1], [sent]])
+        Rad = R0 + P["Vexp"] * 2.99792458e10 * ((s + 1) * float(z["dt"]))
+        n = eng.photons_tot(ps[None], pi[None], np.array([Rad])).cpu().numpy()[0]
+        ref = z["step_photons_top_raw"][s] / _V(Rad)
+        assert_spectra_close(n, ref, f"photons_tot step {s + 1}")
+
+
+def test_U_ph_steps(test1_engine):
+    eng, z, P, b = test1_engine
+    R0 = 10 ** P["R0"]
+    for s in (0, 1, 4, 9):
+        Rad = R0 + P["Vexp"] * 2.99792458e10 * ((s + 1) * float(z["dt"]))
+        n = z["step_photons_top_raw"][s] / _V(Rad)
+        U = eng.U_ph(n[None], np.array([Rad])).cpu().numpy()[0]
+        assert_spectra_close(U, z["step_U_ph"][s], f"U_ph step {s + 1}")
+
+
+def test_syn_ssa_steps(test1_engine):
+    eng, z, P, b = test1_engine
+    R0 = 10 ** P["R0"]
+    sent = 10 ** (-260.)
+    for s in (0, 1, 4, 9):
+        Rad = R0 + P["Vexp"] * 2.99792458e10 * ((s + 1) * float(z["dt"]))
+        N = np.concatenate([[sent], z["step_N_el_int"][s], [sent]])
+        Q, aS, aI = [t.cpu().numpy()[0] for t in eng.syn_ssa((N / _V(Rad))[None], np.array([P["B0"]]))]
+        assert_spectra_close(Q, z["step_Q_syn_raw"][s], f"Q_syn step {s + 1}")
+        assert_signed_close(-np.abs(aS), z["step_aSSA_syn"][s], f"aSSA(nu_syn) step {s + 1}")
+        assert_signed_close(-np.abs(aI), z["step_aSSA_ic"][s], f"aSSA(nu_ic) step {s + 1}")
+
+
+@pytest.mark.parametrize("path", ["R", "S"])
+def test_ic_emissivity_steps(test1_engine, path):
+    eng, z, P, b = test1_engine
+    R0 = 10 ** P["R0"]
+    sent = 10 ** (-260.)
+    for s in range(0, 10):
+        Rad = R0 + P["Vexp"] * 2.99792458e10 * ((s + 1) * float(z["dt"]))
+        N = np.concatenate([[sent], z["step_N_el_int"][s], [sent]])
+        n = z["step_photons_top_raw"][s] / _V(Rad)
+        Q = eng.ic_emissivity((N / _V(Rad))[None], n[None], path).cpu().numpy()[0]
+        ref = z["step_Q_IC"][s]
+        # step 1 has only sentinel photons: values ~1e-320 are denormal noise in both codes
+        if s == 0:
+            assert np.all(np.isfinite(Q)) and np.all(Q[ref == 0] == 0)
+            continue
+        assert_spectra_close(Q, ref, f"Q_IC path {path} step {s + 1}", tol=1e-10)
+
+
+def test_gg_steps(test1_engine):
+    eng, z, P, b = test1_engine
+    R0 = 10 ** P["R0"]
+    for s in (1, 4, 9):
+        Rad = R0 + P["Vexp"] * 2.99792458e10 * ((s + 1) * float(z["dt"]))
+        n = z["step_photons_top_raw"][s] / _V(Rad)
+        a, Qee = [t.cpu().numpy()[0] for t in eng.gg(n[None])]
+        assert_spectra_close(a, z["step_a_gg"][s], f"a_gg step {s + 1}", tol=1e-10)
+        assert_spectra_close(Qee, z["step_Q_ee"][s], f"Q_ee step {s + 1}", tol=1e-10)
+
+
+def test_cor_factor(test1_engine, golden_dir):
+    eng, z, P, b = test1_engine
+    cor = float(eng.cor_factor()[0].item())
+    assert abs(cor / float(z["cor_factor"]) - 1.) < 1e-11
+
+
+def test_function_twins(orc):
+    """lehamoc_b200.LeHaMoC_f mirrors the reference's function library call for call."""
+    from lehamoc_b200 import LeHaMoC_f as f
+    fz = np.load(__import__("os").path.join(__import__("util").GOLD, "functions.npz"))
+    z, P = load_golden("test1")
+    g = z["g_el"]
+    got = f.cor_factor_syn_el(g, 1e15, 1e4, 1.9, f.Lum_e_inj(1e-3, 1e15))
+    assert abs(got / float(fz["cor_factor_test1"]) - 1.) < 1e-11
+    gfit = np.logspace(2., 7.081445, 160)
+    got = f.cor_factor_syn_el(gfit, 10 ** 15.25808, 1e4, 2.0, f.Lum_e_inj(-4., 10 ** 15.25808))
+    assert abs(got / float(fz["cor_factor_fitgrid"]) - 1.) < 1e-11
+    x = f.thomas(np.zeros(17), fz["thomas_in_b"], fz["thomas_in_c"], fz["thomas_in_d"])
+    np.testing.assert_allclose(x, fz["thomas_out_bidiag"], rtol=1e-14)
+    with pytest.raises(NotImplementedError):
+        f.thomas(fz["thomas_in_a"], fz["thomas_in_b"], fz["thomas_in_c"], fz["thomas_in_d"])
+    # per-frequency functions against the oracle's literal restatement on a synthetic state
+    rng = np.random.default_rng(3)
+    gs = np.logspace(0., 5., 40)
+    Np = 1e3 * gs ** -2.2 * np.exp(rng.normal(0, 0.1, 40))
+    Bf = 0.7
+    a_cr = 3. * f.q * Bf / (4. * np.pi * f.m_el * f.c)
+    for nu in (1e9, 3e12, 1e16):
+        assert abs(f.Q_syn_space(Np, Bf, nu, a_cr, gs) / orc.Q_syn_space(Np.copy(), Bf, nu, a_cr, gs) - 1.) < 1e-11
+        dgl = np.log(gs[1]) - np.log(gs[0])
+        assert abs(f.aSSA(Np, Bf, nu, gs, dgl) / orc.aSSA(Np, Bf, nu, gs, dgl) - 1.) < 1e-10
+    nu_t = np.logspace(8., 22., 30)
+    ph = 1e5 * (nu_t / 1e12) ** -1.5
+    for nu in (1e15, 1e20, 3e23):
+        ref = orc.Q_IC_space_optimized(Np, gs, nu, ph, nu_t, len(nu_t) - 1)
+        for path in ("R", "S"):
+            got = f.Q_IC_space_optimized(Np, gs, nu, ph, nu_t, len(nu_t) - 1, ic_path=path)
+            assert abs(got / ref - 1.) < 1e-11, (nu, path)
+    nu_ic = np.logspace(18., 26., 12)
+    np.testing.assert_allclose(f.a_gg(nu_ic, nu_t, ph), orc.a_gg(nu_ic, nu_t, ph), rtol=1e-10)
+    pic = 1e-3 * (nu_ic / 1e20) ** -2.
+    np.testing.assert_allclose(f.Q_ee_f(nu_t, ph, nu_ic, pic, gs, 1e15), orc.Q_ee_f(nu_t, ph, nu_ic, pic, gs, 1e15),
+                               rtol=1e-10)
+    np.testing.assert_allclose(f.U_ph_f(gs, nu_t, ph, 1e15), orc.U_ph_f(gs, nu_t, ph, 1e15), rtol=1e-11)
+
+
+# ---------------------------------------------------------------------------------------------------
+# whole time integrations against the golden vectors of the unmodified reference
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly"])
+@pytest.mark.parametrize("path", ["R", "S"])
+def test_script_runs_match_reference(name, path):
+    z, P = load_golden(name)
+    batch, N, sed = _run_script(P, ic_path=path)
+    ns = int(z["nsteps"])
+    assert N.shape == (1, ns, len(z["g_el"])) and sed.shape == (1, ns, len(z["nu_tot"]))
+    for s in range(ns):
+        assert_spectra_close(N[0, s], 10 ** z["out_log_ne"][s], f"{name}/{path} n_e step {s + 1}", tol=TOL_LOG10)
+        assert_spectra_close(sed[0, s], 10 ** z["out_log_nuLnu"][s], f"{name}/{path} nuLnu step {s + 1}", tol=TOL_LOG10)
+    # the text files only carry ~16 digits of log10: compare the raw state of the final step tightly
+    sent = 10 ** (-260.)
+
+
+def test_test1_final_state_tight():
+    """Test 1 (BASELINE config 1) final state vs the reference's in-memory arrays at <= 1e-8 relative."""
+    z, P = load_golden("test1")
+    for path in ("R", "S"):
+        batch, N, sed = _run_script(P, ic_path=path, snapshots=False)
+        V = 4. * np.pi / 3. * (10 ** P["R0"] + P["Vexp"] * 2.99792458e10 * 10 * float(z["dt"])) ** 3
+        assert_spectra_close(N[0, 0], z["final_N_el"] / V, f"Test1 n_e path {path}", tol=TOL_LOG10)
+        assert_spectra_close(sed[0, 0], 10 ** z["out_log_nuLnu"][-1], f"Test1 nuLnu path {path}", tol=TOL_LOG10)
+
+
+@pytest.mark.parametrize("name", ["test3_synadi", "test3_adiabatic"])
+def test_long_runs_match_reference(name):
+    """LeMoC/Parameters.txt (100 steps, syn+SSA+adiabatic: the run behind the shipped *_Test3_LeMoC.txt) and
+    Parameters_Test3.txt (600 steps, adiabatic only)."""
+    z, P = load_golden(name)
+    batch, N, sed = _run_script(P)
+    keep = z["kept_steps"]
+    for row, s in enumerate(keep):
+        assert_spectra_close(N[0, s], 10 ** z["out_log_ne"][row], f"{name} n_e step {s + 1}", tol=TOL_LOG10)
+        ref = 10 ** z["out_log_nuLnu"][row]
+        if np.all(ref < 1e-150):
+            # adiabatic-only run: the photon field is the 1e-260 sentinels decaying through the denormal
+            # range to exact zeros (the reference prints -inf there).  Normal-range bins must agree to 1e-6
+            # in log10; bins the reference has below 1e-300 (few or no significant bits) must be as negligible
+            lref = z["out_log_nuLnu"][row]
+            normal = lref > -300.
+            got = sed[0, s]
+            assert np.all(got >= 0.) and np.all(np.isfinite(got))
+            np.testing.assert_allclose(np.log10(got[normal]), lref[normal], atol=1e-6)
+            assert np.all(got[~normal] < 1e-295)
+        else:
+            assert_spectra_close(sed[0, s], ref, f"{name} nuLnu step {s + 1}", tol=TOL_LOG10)
+
+
+def test_code_lemoc_matches_reference():
+    """Fit_emcee/Code.py::LeMoC at the fit start point and 7 perturbed walkers (BASELINE config 4)."""
+    from lehamoc_b200 import Code
+    z, P = load_golden("code_fit")
+    nu, sed = Code.LeMoC_batch(z["thetas"], P)
+    for i in range(len(z["thetas"])):
+        np.testing.assert_array_equal(nu[i], z["nu_tot"][i])
+        assert_spectra_close(sed[i], z["nuLnu"][i], f"Code.LeMoC walker {i}")
+    nu1, sed1 = Code.LeMoC(list(z["thetas"][0]), P)
+    np.testing.assert_array_equal(sed1, sed[0])              # batch == single evaluation, bit for bit
+    nuS, sedS = Code.LeMoC_batch(z["thetas"], P, ic_path="S")
+    for i in range(len(z["thetas"])):
+        assert_spectra_close(sedS[i], z["nuLnu"][i], f"Code.LeMoC walker {i} path S")
+
+
+def test_batch_of_walkers_vs_oracle(orc):
+    """Heterogeneous walkers in one launch: each must equal its own single-model oracle run."""
+    from lehamoc_b200 import LeMoC
+    _, P = load_golden("test1")
+    P.update(grid_g_el=80., grid_nu=50., time_end=4.)
+    rng = np.random.default_rng(20231)
+    sets = []
+    for i in range(12):
+        Q = dict(P)
+        Q.update(R0=rng.uniform(14.5, 16), B0=10 ** rng.uniform(-1, 1), L_el=40.4857 + rng.uniform(-1, 1),
+                 p_el=rng.uniform(1.6, 2.6), g_PL_min=rng.uniform(0.5, 3), g_PL_max=rng.uniform(5, 6.0))
+        sets.append(Q)
+    batch, N, sed = LeMoC.run(sets, snapshots=False)
+    for i, Q in enumerate(sets):
+        _, ne_ref, sed_ref = orc.run_script(Q)
+        assert_spectra_close(N[i, 0], ne_ref[-1], f"walker {i} n_e")
+        assert_spectra_close(sed[i, 0], sed_ref[-1], f"walker {i} nuLnu")
+
+
+def test_full_size_properties():
+    """BASELINE-size batch (Test-1 grid, 296 walkers): independence of walkers and determinism --
+    identical walkers give bit-identical spectra wherever they sit in the batch, and a repeat run is
+    bit-identical."""
+    from lehamoc_b200 import LeMoC
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    _, P = load_golden("test1")
+    sets = []
+    for i in range(296):
+        Q = dict(P)
+        if i % 4:
+            Q.update(B0=1.0 + 0.01 * (i % 7), p_el=1.9 + 0.001 * (i % 5))
+        sets.append(Q)
+    b = pack_script(sets)
+    eng = Engine(b.cfg, b.W)
+    N1, s1 = eng.run_host(b)
+    N1, s1 = N1.copy(), s1.copy()
+    N2, s2 = eng.run_host(b)
+    np.testing.assert_array_equal(s1, s2)
+    np.testing.assert_array_equal(N1, N2)
+    base = s1[0]
+    for i in range(0, 296, 4):
+        np.testing.assert_array_equal(s1[i], base)
+    z, _ = load_golden("test1")
+    assert_spectra_close(base, 10 ** z["out_log_nuLnu"][-1], "walker 0 of the big batch", tol=TOL_LOG10)
+
+
+def test_cli_text_format(tmp_path, monkeypatch):
+    """python -m lehamoc_b200.LeMoC writes the reference's text format (LeMoC.py:290-296)."""
+    from lehamoc_b200 import LeMoC
+    z, P = load_golden("test1")
+    pf = tmp_path / "Parameters_Test1.txt"
+    pf.write_text("\n".join(f"{k} = {v!r}" for k, v in P.items()))
+    monkeypatch.chdir(tmp_path)
+    assert LeMoC.main(["LeMoC.py", str(pf), "t1"]) == 0
+    part = np.loadtxt(tmp_path / "Particles_Distribution_t1.txt")
+    phot = np.loadtxt(tmp_path / "Photons_Distribution_t1.txt")
+    assert part.shape == (10 * 260, 2) and phot.shape == (10 * 100, 2)
+    ref1 = np.array([[float(t) for t in ln.split()] for ln in str(z["photons_txt_step1"]).strip().split("\n")])
+    np.testing.assert_array_equal(phot[:100, 0], ref1[:, 0])
+    np.testing.assert_allclose(phot[:100, 1], ref1[:, 1], atol=1e-7)
+    assert LeMoC.main(["LeMoC.py"]) == 1
+
+
+def test_error_paths():
+    from lehamoc_b200 import _lib
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    _, P = load_golden("test1")
+    P.update(grid_g_el=40., grid_nu=30.)
+    b = pack_script(P)
+    eng = Engine(b.cfg, 1)
+    with pytest.raises(_lib.LhmError):
+        eng.run()                                   # run before setup -> LHM_ERR_STATE
+    b2 = pack_script([P, P])
+    with pytest.raises(_lib.LhmError):
+        eng.setup(b2)                               # over capacity
+    with pytest.raises(_lib.LhmError):
+        Engine(dict(b.cfg, Ng=2), 1)                # invalid size

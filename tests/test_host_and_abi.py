@@ -1,0 +1,106 @@
+"""CPU: host-side logic (parameter files, batched grid construction) and the C-ABI library surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+import lehamoc_oracle as orc
+from lehamoc_b200 import _lib, setup_host
+from util import ROOT, load_golden, quiet
+
+quiet()
+
+
+def test_parameter_file_roundtrip(tmp_path):
+    _, P = load_golden("test1")
+    pf = tmp_path / "Parameters.txt"
+    pf.write_text("\n".join(f"{k} = {v!r}" for k, v in P.items()))      # no trailing newline, like the shipped files
+    assert setup_host.read_parameter_file(pf) == P == orc.read_parameter_file(pf)
+    with pytest.raises(KeyError):
+        bad = dict(P); bad.pop("gg_flag")
+        setup_host.pack_script(bad)
+    with pytest.raises(ValueError):
+        setup_host.pack_script(dict(P, SSA_l_flag=0.5))
+
+
+@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "test3_synadi"])
+def test_pack_script_is_bit_identical_to_reference_setup(name):
+    z, P = load_golden(name)
+    b = setup_host.pack_script(P)
+    for k, a in (("g_el", b.g_el), ("nu_syn", b.nu_syn), ("nu_ic", b.nu_ic), ("nu_tot", b.nu_tot), ("el_inj", b.el_inj)):
+        np.testing.assert_array_equal(a[0], z[k], err_msg=k)          # vectors captured from the live reference
+    assert int(b.index_PL_min[0]) == int(z["index_PL_min"]) and int(b.index_PL_max[0]) == int(z["index_PL_max"])
+    assert int(b.nsteps[0]) == int(z["nsteps"]) and b.consts[0, _lib.C_DT] == float(z["dt"])
+    # external fields as they come out of photons_tot
+    r = orc.LeptonicRun(P, "script")
+    V = orc.Volume(r.R0)
+    with np.errstate(all="ignore"):
+        ext = 10 ** np.interp(np.log10(r.nu_tot), np.log10(r.nu_bb), np.log10(r.bb * V)) / V + r.pl
+    np.testing.assert_allclose(b.ext[0], ext, rtol=1e-12)
+
+
+def test_pack_code_matches_oracle_and_batches():
+    z, P = load_golden("code_fit")
+    b = setup_host.pack_code(z["thetas"], P)
+    assert b.cfg["loss_minus_one"] == 0 and b.cfg["qee_from_ic"] == 1
+    for i, th in enumerate(z["thetas"]):
+        r = orc.LeptonicRun(P, "code", theta=list(th))
+        np.testing.assert_array_equal(b.g_el[i], r.g_el)
+        np.testing.assert_array_equal(b.nu_syn[i], r.nu_syn)
+        np.testing.assert_array_equal(b.nu_tot[i], z["nu_tot"][i])
+        np.testing.assert_array_equal(b.el_inj[i], r.el_inj)
+        assert int(b.nsteps[i]) == r.n_steps() == 4
+    one = setup_host.pack_code(z["thetas"][3], P)
+    np.testing.assert_array_equal(one.g_el[0], b.g_el[3])
+
+
+def test_heterogeneous_script_batch_rules():
+    _, P = load_golden("test1")
+    b = setup_host.pack_script([P, dict(P, B0=3.0, p_el=2.0, g_PL_min=2.0, g_PL_max=5.0)])
+    assert b.W == 2 and b.index_PL_max[0] == -1 and b.index_PL_max[1] > 0
+    assert b.el_inj[1, 0] == 10 ** (-260.) and b.el_inj[1, b.index_PL_min[1]] > 1.
+    with pytest.raises(ValueError):
+        setup_host.pack_script([P, dict(P, grid_nu=50.)])            # grid sizes are shared by a batch
+    with pytest.raises(ValueError):
+        setup_host.pack_script(dict(P, g_PL_max=7.5))                # window outside the grid
+
+
+def test_library_exports_every_declared_symbol():
+    """liblhm.so loads on a GPU-less host and exports exactly what include/lhm.h declares."""
+    header = open(os.path.join(ROOT, "include", "lhm.h")).read()
+    declared = set(re.findall(r"\b(lhm_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    lib = _lib.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.lhm_version() == 100
+    assert b"no CPU fallback" in lib.lhm_strerror(-3)
+    # struct layout agreed between header and binding
+    n_int_fields = len(re.search(r"typedef struct \{(.*?)\} lhm_config;", header, re.S).group(1)
+                       .replace("\n", " ").split(";")) - 1
+    assert ctypes.sizeof(_lib.lhm_config) == 4 * len(_lib.lhm_config._fields_)
+    assert len(_lib.lhm_config._fields_) == 18 and n_int_fields >= 8
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from lehamoc_b200 import Code
+    z, P = load_golden("code_fit")
+    with pytest.raises(_lib.LhmError):
+        Code.LeMoC(list(z["thetas"][0]), P)
+    cfg = _lib.lhm_config(Ng=16, Ns=9, Ni=8, Nt=10, gg_npts=50, max_walkers=1)
+    h = ctypes.c_void_p()
+    rc = _lib.load().lhm_create(ctypes.byref(cfg), 0, None, ctypes.byref(h))
+    assert rc == -3                                                   # LHM_ERR_NO_DEVICE, never a silent CPU path
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "lehamoc_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert "lehamoc_oracle" not in src and "run_reference" not in src, fn

@@ -1,0 +1,108 @@
+"""CPU: the NumPy oracle against (a) vectors captured from the unmodified reference (tests/golden/*.npz, made
+by oracle/make_golden.py) and (b) the reference's own shipped output files where present."""
+import os
+
+import numpy as np
+import pytest
+
+import lehamoc_oracle as orc
+from util import load_golden, quiet
+
+quiet()
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, float), np.asarray(b, float)
+    m = (b != 0) & np.isfinite(b)
+    assert np.array_equal(a[~m], b[~m])
+    return float(np.max(np.abs(a[m] / b[m] - 1.))) if m.any() else 0.0
+
+
+@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly"])
+def test_oracle_reproduces_reference_every_step(name):
+    z, P = load_golden(name)
+    run, ne, sed = orc.run_script(P, record=True)
+    with np.errstate(divide="ignore"):
+        assert np.nanmax(np.abs(np.log10(ne) - z["out_log_ne"])) < 1e-13
+        d = np.abs(np.log10(sed) - z["out_log_nuLnu"])
+        assert np.nanmax(d[np.isfinite(d)]) < 1e-13
+    tr = run.trace
+    pairs = [("N_el", "step_N_el_int", True), ("photons_syn", "step_photons_syn_int", True),
+             ("photons_IC", "step_photons_IC_int", True), ("U_ph", "step_U_ph", False),
+             ("Q_syn_raw", "step_Q_syn_raw", False), ("Q_IC", "step_Q_IC", False),
+             ("a_gg", "step_a_gg", False), ("Q_ee", "step_Q_ee", False)]
+    for k, gk, interior in pairs:
+        if gk in z.files and k in tr:
+            a = np.array(tr[k])
+            if interior:
+                a = a[:, 1:-1]
+            assert _rel(a, z[gk]) < 1e-13, k
+    if "cor_factor" in z.files:
+        assert abs(run.cor_factor() / float(z["cor_factor"]) - 1.) < 1e-14
+
+
+def test_oracle_long_runs():
+    for name in ("test3_synadi", "test3_adiabatic"):
+        z, P = load_golden(name)
+        _, ne, sed = orc.run_script(P)
+        keep = z["kept_steps"]
+        with np.errstate(divide="ignore"):
+            assert np.nanmax(np.abs(np.log10(ne[keep]) - z["out_log_ne"])) < 1e-12
+            d = np.abs(np.log10(sed[keep]) - z["out_log_nuLnu"])
+            assert np.nanmax(d[np.isfinite(d)]) < 1e-12
+
+
+def test_oracle_code_lemoc():
+    z, P = load_golden("code_fit")
+    for i in (0, 1, 5):
+        nu, sed = orc.code_LeMoC(z["thetas"][i], P)
+        np.testing.assert_array_equal(nu, z["nu_tot"][i])
+        assert _rel(sed, z["nuLnu"][i]) < 1e-12
+
+
+def test_literal_and_broadcast_forms_agree():
+    """The loop-structured port that bench.py times equals the broadcast form the tests use."""
+    _, P = load_golden("test1")
+    P.update(grid_g_el=60., grid_nu=40., time_end=2.)
+    _, ne1, sed1 = orc.run_script(P, literal=True, hoist_cor=False)
+    _, ne2, sed2 = orc.run_script(P, literal=False)
+    assert _rel(ne1, ne2) < 1e-13 and _rel(sed1, sed2) < 1e-13
+
+
+def test_function_vectors():
+    f = np.load(os.path.join(os.path.dirname(__file__), "golden", "functions.npz"))
+    z, _ = load_golden("test1")
+    got = orc.cor_factor_syn_el(z["g_el"], 1e15, 1e4, 1.9, orc.Lum_e_inj(1e-3, 1e15))
+    assert abs(got / float(f["cor_factor_test1"]) - 1.) < 1e-14
+    x = orc.thomas(f["thomas_in_a"], f["thomas_in_b"], f["thomas_in_c"], f["thomas_in_d"])
+    np.testing.assert_allclose(x, f["thomas_out_tridiag"], rtol=0, atol=0)
+    x = orc.bidiag_solve(f["thomas_in_b"], f["thomas_in_c"], f["thomas_in_d"])
+    np.testing.assert_allclose(x, f["thomas_out_bidiag"], rtol=1e-15)
+
+
+REF = "/root/reference/LeMoC"
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference tree only exists in the build container")
+def test_against_shipped_reference_outputs():
+    """The reference's own golden files pin Test 1 only to ~1e-3 in log10."""
+    _, ne, sed = orc.run_script(os.path.join(REF, "Parameters_Test1.txt"))
+    g = np.loadtxt(os.path.join(REF, "Photons_Distribution_Test1_LeMoC.txt"))[:, 1].reshape(10, 100)
+    d = np.abs(np.log10(sed) - g)
+    assert np.max(d[g > -100]) < 3e-3
+    g = np.loadtxt(os.path.join(REF, "Particles_Distribution_Test1_LeMoC.txt"))[:, 1].reshape(10, 260)
+    d = np.abs(np.log10(ne) - g)
+    assert np.max(d[g > -100]) < 3e-3
+
+
+def test_likelihood_restatement_self_consistency():
+    """fit_emcee.py:121-145 has no reference-owned fixture (parity unpinned): check its structural properties."""
+    x = np.linspace(10, 25, 31)
+    flags = np.zeros(31); flags[[26, 27, 29]] = 1
+    y = -12 + 0.1 * np.sin(x)
+    err = np.full(31, 0.1)
+    ll0 = orc.log_likelihood_from_model(y.copy(), -2., y, err, err * 2, flags)
+    ll1 = orc.log_likelihood_from_model(y + 0.3, -2., y, err, err * 2, flags)
+    assert ll0 > ll1
+    assert orc.log_prior_LeMoC([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2]) == 0.0
+    assert orc.log_prior_LeMoC([13.0, 0.038818, 3., 6.081445, -4., 2., 1.3, -2]) == -np.inf
