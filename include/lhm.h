@@ -80,6 +80,8 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
 void lhm_destroy(lhm_handle*);
 /* bytes of dynamic shared memory per CTA the fused step kernel uses for this config */
 int lhm_step_smem_bytes(const lhm_handle*);
+/* bytes of table workspace (HBM) per walker */
+long long lhm_table_bytes_per_walker(const lhm_handle*);
 
 /* Build every state-independent table of W walkers (interpolation stencils, trapezoid weights,
  * gamma-gamma sample kernels ...).  Replaces the per-call grid work of LeMoC.py:113-191 that does not

@@ -16,13 +16,13 @@ from .engine import Engine
 from .setup_host import pack_script, read_parameter_file
 
 
-def run(param_sets, ic_path="R", snapshots=True, engine=None):
+def run(param_sets, ic_path="R", snapshots=True, engine=None, pinned=False):
     """Evolve one or more LeMoC.py parameter sets.  Returns (batch, n_e [W,S,Ng], nuLnu [W,S,Nt]); S = number
     of timesteps when `snapshots` (the reference writes every step), else 1."""
     batch = pack_script(param_sets)
     eng = engine or Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
     S = int(batch.nsteps.max()) if snapshots else 0
-    N, sed = eng.run_host(batch, snapshots=S)
+    N, sed = eng.run_host(batch, snapshots=S, pinned=pinned)
     if not snapshots:
         N, sed = N[:, None], sed[:, None]
     return batch, N, sed

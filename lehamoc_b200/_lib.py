@@ -37,6 +37,7 @@ SIGNATURES = {
     "lhm_create": (C.c_int, [C.POINTER(lhm_config), C.c_int, _P, C.POINTER(_P)]),
     "lhm_destroy": (None, [_P]),
     "lhm_step_smem_bytes": (C.c_int, [_P]),
+    "lhm_table_bytes_per_walker": (C.c_longlong, [_P]),
     "lhm_setup_batch": (C.c_int, [_P, C.c_int] + [_P] * 7),
     "lhm_cor_factor_batch": (C.c_int, [_P, _P]),
     "lhm_run_batch": (C.c_int, [_P, _P, _P, C.c_int]),

@@ -363,6 +363,9 @@ void lhm_destroy(lhm_handle* h) {
 }
 
 int lhm_step_smem_bytes(const lhm_handle* h) { return h ? (int)h->smem : LHM_ERR_ARG; }
+long long lhm_table_bytes_per_walker(const lhm_handle* h) {
+    return h ? (long long)h->L.n_doubles * 8 + (long long)h->L.n_ints * 4 : LHM_ERR_ARG;
+}
 
 int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_el, const double* nu_syn,
                     const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext) {

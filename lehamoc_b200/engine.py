@@ -72,6 +72,9 @@ class Engine:
     def smem_bytes(self):
         return self.lib.lhm_step_smem_bytes(self.h)
 
+    def table_bytes_per_walker(self):
+        return int(self.lib.lhm_table_bytes_per_walker(self.h))
+
     def _dev(self, a):
         if isinstance(a, torch.Tensor):
             return a.to(device=f"cuda:{self.device}", dtype=torch.float64).contiguous()
@@ -109,16 +112,37 @@ class Engine:
     def run_into(self, N, sed, snapshots: int = 0):
         check(self.lib.lhm_run_batch(self.h, _ptr(N), _ptr(sed), int(snapshots)), "lhm_run_batch")
 
-    def run_host(self, batch: Batch, snapshots: int = 0, N_out=None, sed_out=None):
-        """lhm_run_batch_host: host buffers in, host buffers out (H2D + set-up + run + D2H + sync)."""
+    def _pinned(self, key, shape):
+        """NumPy view of a cached page-locked buffer (grown on demand)."""
+        n = int(np.prod(shape))
+        pool = self.__dict__.setdefault("_pin", {})
+        t = pool.get(key)
+        if t is None or t.numel() < n:
+            t = torch.empty(max(n, 1), dtype=torch.float64, pin_memory=True)
+            pool[key] = t
+        return t.numpy()[:n].reshape(shape)
+
+    def run_host(self, batch: Batch, snapshots: int = 0, N_out=None, sed_out=None, pinned: bool = False):
+        """lhm_run_batch_host: host buffers in, host buffers out (H2D + set-up + run + D2H + sync).
+        With pinned=True the returned arrays are views of reusable page-locked buffers."""
         W = batch.W
         S = snapshots if snapshots > 0 else 1
+        hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        ins = batch.arrays()
+        if pinned:
+            # stage through page-locked buffers so the copies run at full PCIe/NVLink-C2C rate
+            ins = [self._pinned(f"in{i}", a.shape) for i, a in enumerate(batch.arrays())]
+            for dst, src in zip(ins, batch.arrays()):
+                np.copyto(dst, src)
+            if N_out is None:
+                N_out = self._pinned("N", (W, S, self.Ng))
+            if sed_out is None:
+                sed_out = self._pinned("sed", (W, S, self.Nt))
         if N_out is None:
             N_out = np.empty((W, S, self.Ng))
         if sed_out is None:
             sed_out = np.empty((W, S, self.Nt))
-        hp = lambda a: a.ctypes.data_as(C.c_void_p)
-        check(self.lib.lhm_run_batch_host(self.h, W, *[hp(a) for a in batch.arrays()], hp(N_out), hp(sed_out),
+        check(self.lib.lhm_run_batch_host(self.h, W, *[hp(a) for a in ins], hp(N_out), hp(sed_out),
                                           int(snapshots)), "lhm_run_batch_host")
         self.W = W
         self._keep = None

@@ -1,0 +1,25 @@
+"""Small driver for ncu captures: one set-up + fused-step launch of a Test-1 batch.
+    python tools/prof_run.py [--walkers 296] [--ic-path R|S] [--reps 2]"""
+import argparse
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from lehamoc_b200.engine import Engine  # noqa: E402
+from lehamoc_b200.presets import test1_walkers  # noqa: E402
+from lehamoc_b200.setup_host import pack_script  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--walkers", type=int, default=296)
+ap.add_argument("--ic-path", default="R")
+ap.add_argument("--reps", type=int, default=2)
+a = ap.parse_args()
+b = pack_script(test1_walkers(a.walkers))
+eng = Engine(b.cfg, a.walkers, ic_path=a.ic_path)
+eng.setup(b)
+for _ in range(a.reps):
+    N, sed = eng.run()
+torch.cuda.synchronize()
+print("timings (setup, cor, run) ms:", eng.last_timings(), "sum sed[0]:", float(sed[0].sum()))
