@@ -106,6 +106,10 @@ int lhm_run_batch(lhm_handle*, double* N_el_out, double* nuLnu_out, int snapshot
  * kernels; -1 if never launched.  Synchronises on those events only.  bench.py's roofline uses run_ms. */
 int lhm_last_timings(lhm_handle*, float* setup_ms, float* cor_ms, float* run_ms);
 
+/* Diagnostics: when set (device pointer to 16 zeroed uint64), thread 0 of every walker CTA adds the clock64
+ * cycles it spent in each phase of the timestep loop; NULL (default) switches it off. */
+int lhm_set_phase_profile(lhm_handle*, unsigned long long* dev_counters16);
+
 /* Host-buffer convenience used by Code.LeMoC / LeMoC_batch: H2D of the packed inputs, setup, run,
  * D2H of the outputs, stream synchronise.  All pointers are HOST pointers (pinned or pageable). */
 int lhm_run_batch_host(lhm_handle*, int W, const double* consts_host, const double* g_el_host,

@@ -6,7 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "liblhm.so")
+LIB_PATH = os.environ.get("LHM_LIB", os.path.join(HERE, "liblhm.so"))     # LHM_LIB: experimental builds
 
 LHM_OK = 0
 LHM_IC_PATH_R = 0
@@ -42,6 +42,7 @@ SIGNATURES = {
     "lhm_cor_factor_batch": (C.c_int, [_P, _P]),
     "lhm_run_batch": (C.c_int, [_P, _P, _P, C.c_int]),
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
+    "lhm_set_phase_profile": (C.c_int, [_P, _P]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),
     "lhm_photons_tot_batch": (C.c_int, [_P] * 5),
     "lhm_uph_batch": (C.c_int, [_P] * 4),

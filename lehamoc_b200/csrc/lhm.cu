@@ -32,6 +32,7 @@ struct RunArgs {
     const double* cor;      // [W] cor_factor_syn_el
     double* N_out;          // [W,(S),Ng] or null
     double* sed_out;        // [W,(S),Nt] or null
+    unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
 
 __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlags& F, const double* consts,
@@ -45,7 +46,10 @@ __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlag
     C.Rad = C.R0; C.B = C.B0; C.V = volume_of(C.R0);
 }
 
-__global__ void __launch_bounds__(NT, 2) run_kernel(RunArgs A) {
+#ifndef LHM_MIN_CTAS
+#define LHM_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
     extern __shared__ __align__(16) double smem_raw[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x;
@@ -67,6 +71,8 @@ __global__ void __launch_bounds__(NT, 2) run_kernel(RunArgs A) {
     for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
     ic_prepare<NT>(C, S);
 
+    long long tprev = clock64();
+#define LHM_TICK(i) do { if (A.prof && tid == 0) { long long now_ = clock64(); atomicAdd(A.prof + (i), (unsigned long long)(now_ - tprev)); tprev = now_; } } while (0)
     double t = C.tinit;
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeMoC.py:198-201
@@ -74,17 +80,26 @@ __global__ void __launch_bounds__(NT, 2) run_kernel(RunArgs A) {
         C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
         C.V = volume_of(C.Rad);
 
+        LHM_TICK(0);
         phase_photons<NT>(C, S, true);
+        LHM_TICK(1);
         if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        LHM_TICK(2);
         phase_electrons<NT>(C, S);
+        LHM_TICK(3);
         phase_vectors<NT>(C, S);
+        LHM_TICK(4);
         phase_syn_rows<NT>(C, S, false);
+        LHM_TICK(5);
         if (C.F.ic_e) {
             if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
         }
+        LHM_TICK(6);
         __syncthreads();
+        LHM_TICK(7);
         if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
         phase_photon_solves<NT>(C, S, cor);
+        LHM_TICK(8);
         if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
             const double* Lng = S.Ln;
             if (C.F.qee_from_ic) {
@@ -95,6 +110,7 @@ __global__ void __launch_bounds__(NT, 2) run_kernel(RunArgs A) {
             phase_gg<NT>(C, S, Lng, S.agg, S.qee);
             __syncthreads();
         }
+        LHM_TICK(9);
         // output (LeMoC.py:286-291): every step when snapshots are requested, else after the last step
         const bool last = (step == nsteps - 1);
         const int slot = A.snapshots > 0 ? step : 0;
@@ -273,6 +289,7 @@ struct lhm_handle {
     double* d_Nout;
     double* d_sed;
     size_t Nout_cap, sed_cap;
+    unsigned long long* d_prof;   // optional per-phase cycle counters (lhm_set_phase_profile)
     // device-side timing of the last setup / cor / run launches (lhm_last_timings)
     cudaEvent_t ev[6];
     bool ev_set[3];
@@ -414,12 +431,19 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     RunArgs A;
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
+    A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
     h->ev_set[2] = true;
+    return LHM_OK;
+}
+
+int lhm_set_phase_profile(lhm_handle* h, unsigned long long* dev_counters16) {
+    if (!h) return LHM_ERR_ARG;
+    h->d_prof = dev_counters16;
     return LHM_OK;
 }
 

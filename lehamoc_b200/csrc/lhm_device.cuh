@@ -35,13 +35,15 @@ struct Layout {
     int nsyn, lsyn, nm23s, nm53s, asm_, asp_;                                              // Ns each
     int nic, lic, nm53i, aim, aip, eps, lnu4;                                              // Ni each
     int nt, lt, lxt, xt, wt, invnt, l2nt, hnu2, ext, ps_dx, ps_Dx, pi_dx, pi_Dx;           // Nt each
-    int aggK, aggT, qeeK, qeeT;                                                            // Ni*NP, Ng*NP
+    int agg_a, agg_d;               // Ni: first abscissa / step (log10) of the a_gg resample grid
+    int qee_a, qee_d;               // Ng: same for Q_ee_f
+    int aggK, qeeK;                 // Ni*NP, Ng*NP static kernel factors
     int n_doubles;
     // int tables
     int ps_j, pi_j;                 // Nt
     int u_idx, u_j, q_j;            // Ng
     int jm_syn;                     // Ns
-    int aggJ, qeeJ;                 // Ni*NP, Ng*NP
+
     int n_ints;
 };
 
@@ -61,11 +63,12 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
     L.nt = take(Nt); L.lt = take(Nt); L.lxt = take(Nt); L.xt = take(Nt); L.wt = take(Nt);
     L.invnt = take(Nt); L.l2nt = take(Nt); L.hnu2 = take(Nt); L.ext = take(Nt); L.ps_dx = take(Nt);
     L.ps_Dx = take(Nt); L.pi_dx = take(Nt); L.pi_Dx = take(Nt);
-    L.aggK = take(Ni * NP); L.aggT = take(Ni * NP); L.qeeK = take(Ng * NP); L.qeeT = take(Ng * NP);
+    L.agg_a = take(Ni); L.agg_d = take(Ni); L.qee_a = take(Ng); L.qee_d = take(Ng);
+    L.aggK = take(Ni * NP); L.qeeK = take(Ng * NP);
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
-    L.jm_syn = take(Ns); L.aggJ = take(Ni * NP); L.qeeJ = take(Ng * NP);
+    L.jm_syn = take(Ns);
     L.n_ints = o;
     return L;
 }

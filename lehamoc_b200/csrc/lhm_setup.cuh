@@ -166,12 +166,12 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
     // ---- gamma-gamma sample tables ---------------------------------------------------------------
     const double* lxt = T + L.lxt;
     const double xmax_l = lxt[Nt - 1];                           // log10(max(x)) / log10(h nu_tot[-1]/mc2)
-    // a_gg: NP samples per nu_ic (LeHaMoC_f.py:130-136)
+    // a_gg: NP samples per nu_ic (LeHaMoC_f.py:130-136).  K = trapz weight x 0.652 sigmaT (s^2-1)/s^3 ln s x'
     for (int e = tid; e < Ni * NP; e += NT) {
         int o = e / NP, s = e - o * NP;
         double xIC = T[L.eps + o];
         double a = log10(1.3 / xIC);
-        double K = 0.0, tt = 0.0; int jj = 0;
+        double K = 0.0;
         double x0 = logspace_pt(a, xmax_l, 0, NP), x1 = logspace_pt(a, xmax_l, 1, NP);
         if (x0 < x1) {
             double xs = logspace_pt(a, xmax_l, s, NP);
@@ -181,21 +181,17 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             double wtr = (((s > 0) ? (lc - lm) : 0.0) + ((s < NP - 1) ? (lp - lc) : 0.0)) * 0.5;
             double sv = xs * xIC;
             K = wtr * (pc.gg_pref * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
-            int code; double dx, Dx;
-            interp_stencil(log10(xs), lxt, Nt, code, dx, Dx);
-            jj = code >> 1;
-            tt = (code & 1) ? 0.0 : dx / Dx;
-            if (jj >= Nt - 1) { jj = Nt - 2; tt = 1.0; }
         }
-        T[L.aggK + e] = K; T[L.aggT + e] = tt; TI[L.aggJ + e] = jj;
+        T[L.aggK + e] = K;
+        if (s == 0) { T[L.agg_a + o] = a; T[L.agg_d + o] = (xmax_l - a) / (double)(NP - 1); }
     }
     // Q_ee_f: NP samples per gamma (LeHaMoC_f.py:143-149); the 2.61 R_gg kernel and trapz weight folded in K
     for (int e = tid; e < Ng * NP; e += NT) {
         int j = e / NP, s = e - j * NP;
         double gj = g[j];
-        double K = 0.0, tt = 0.0; int jj = 0;
+        double K = 0.0;
+        double a = log10(1.0 / (2.0 * gj));
         if (2.0 * gj > 1.0) {
-            double a = log10(1.0 / (2.0 * gj));
             double xs = logspace_pt(a, xmax_l, s, NP);
             double lm = (s > 0) ? log(logspace_pt(a, xmax_l, s - 1, NP)) : 0.0;
             double lc = log(xs);
@@ -203,13 +199,9 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             double wtr = (((s > 0) ? (lc - lm) : 0.0) + ((s < NP - 1) ? (lp - lc) : 0.0)) * 0.5;
             double sv = 2.0 * gj * xs;
             K = wtr * (2.61 * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
-            int code; double dx, Dx;
-            interp_stencil(log10(xs), lxt, Nt, code, dx, Dx);
-            jj = code >> 1;
-            tt = (code & 1) ? 0.0 : dx / Dx;
-            if (jj >= Nt - 1) { jj = Nt - 2; tt = 1.0; }
         }
-        T[L.qeeK + e] = K; T[L.qeeT + e] = tt; TI[L.qeeJ + e] = jj;
+        T[L.qeeK + e] = K;
+        if (s == 0) { T[L.qee_a + j] = a; T[L.qee_d + j] = (xmax_l - a) / (double)(NP - 1); }
     }
 }
 

@@ -31,6 +31,7 @@ struct Smem {
     double *Qsyn, *aS, *aI, *QIC;                // contraction results
     double *tri;                                 // [Nt][4] = {1/nu_i, 2 ln nu_i, w_i n_i, 0}
     double *gS, *lgS, *inv4gS, *epsS, *lnu4S, *nuoS;   // IC pair-constant inputs
+    double *lxtS;                                // log10(h nu_tot/mc2): abscissae of the gamma-gamma interpolation
     double *sfx;                                 // [4][Nt] suffix sums of IC path S
     double *partial;                             // [NW][NiPad] IC partial sums
     unsigned short* tasks;                       // IC (o-group, gamma-block) task list
@@ -59,9 +60,14 @@ __host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
     d += pad2(Ns) * 2 + pad2(Ni) * 2;                       // Qsyn aS aI QIC
     d += (size_t)Nt * 4;                                    // tri
     d += pad2(Ng) * 3 + pad2(Ni) * 3;                       // gS lgS inv4gS epsS lnu4S nuoS
-    d += (size_t)4 * pad2(Nt);                              // sfx
+    d += pad2(Nt);                                          // lxtS
+    // `partial` (IC path R) and `sfx` (IC path S) alias the scratch block {Lsyn Lic y cum bcom cp dp}, which
+    // is dead while the IC phase runs; pad if that block is too small for them
+    size_t scratch = pad2(Ns) + pad2(Ni) + 2 * pad2(Nt) + pad2(Ng) + 2 * pad2(Nmax);
     int NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
-    d += (size_t)NW * NiPad;                                // partial
+    size_t need = (size_t)NW * NiPad;
+    if ((size_t)4 * pad2(Nt) > need) need = (size_t)4 * pad2(Nt);
+    if (need > scratch) d += need - scratch;
     return d;
 }
 __host__ __device__ inline int ic_max_tasks(const Layout& L) {
@@ -77,18 +83,22 @@ __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     double* p = base;
     auto take = [&](int n) { double* r = p; p += n; return r; };
     S.N = take(pad2(Ng)); S.qee = take(pad2(Ng)); S.psyn = take(pad2(Ns)); S.pic = take(pad2(Ni)); S.agg = take(pad2(Ni));
-    S.Lsyn = take(pad2(Ns)); S.Lic = take(pad2(Ni));
-    S.n = take(pad2(Nt)); S.Ln = take(pad2(Nt)); S.Lm = take(pad2(Nt)); S.y = take(pad2(Nt)); S.cum = take(pad2(Nt));
-    S.bcom = take(pad2(Ng));
-    S.cp = take(pad2(Nmax)); S.dp = take(pad2(Nmax));
+    S.n = take(pad2(Nt)); S.Ln = take(pad2(Nt)); S.Lm = take(pad2(Nt));
     S.ne = take(pad2(Ng)); S.av = take(pad2(Ng)); S.u = take(pad2(Ng)); S.v = take(pad2(Ng)); S.inuc = take(pad2(Ng));
     S.Qsyn = take(pad2(Ns)); S.aS = take(pad2(Ns)); S.aI = take(pad2(Ni)); S.QIC = take(pad2(Ni));
     S.tri = take(Nt * 4);
     S.gS = take(pad2(Ng)); S.lgS = take(pad2(Ng)); S.inv4gS = take(pad2(Ng));
     S.epsS = take(pad2(Ni)); S.lnu4S = take(pad2(Ni)); S.nuoS = take(pad2(Ni));
-    S.sfx = take(4 * pad2(Nt));
-    int NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
-    S.partial = take(NW * NiPad);
+    S.lxtS = take(pad2(Nt));
+    // scratch block, last: dead during the IC phase, so the IC partial sums / suffix sums live on top of it
+    double* scratch0 = p;
+    S.Lsyn = take(pad2(Ns)); S.Lic = take(pad2(Ni));
+    S.y = take(pad2(Nt)); S.cum = take(pad2(Nt));
+    S.bcom = take(pad2(Ng));
+    S.cp = take(pad2(Nmax)); S.dp = take(pad2(Nmax));
+    S.partial = scratch0;
+    S.sfx = scratch0;
+    p = base + smem_doubles(L, NW);
     S.tasks = reinterpret_cast<unsigned short*>(p);
     S.ntasks = reinterpret_cast<int*>(S.tasks + pad2(ic_max_tasks(L)));
 }
@@ -116,6 +126,7 @@ __device__ void ic_prepare(const Ctx& C, Smem& S) {
         S.epsS[o] = C.T[L.eps + o]; S.lnu4S[o] = C.T[L.lnu4 + o]; S.nuoS[o] = C.T[L.nic + o];
     }
     for (int i = tid; i < L.Nt; i += NT) {
+        S.lxtS[i] = C.T[L.lxt + i];
         S.tri[4 * i + 0] = C.T[L.invnt + i];
         S.tri[4 * i + 1] = C.T[L.l2nt + i];
         S.tri[4 * i + 2] = 0.0;
@@ -298,12 +309,24 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
         const int jm = is_syn ? C.TI[L.jm_syn + k] : 0;
         const bool do_q = is_syn && need_q && (k < Ns - 1);
         double sq = 0.0, sa = 0.0;
-        for (int j = lane; j < Ng; j += 32) {
-            double x = nu * S.inuc[j];
-            double E = (x > 745.2) ? 0.0 : exp(-x);
-            if (do_q && j >= jm) sq = fma(E, S.u[j], sq);
-            sa = fma(E, S.v[j], sa);
+        // two gammas per lane and iteration: two independent exp() chains in flight
+        double sq1 = 0.0, sa1 = 0.0;
+        for (int j = lane; j < Ng; j += 64) {
+            const int j1 = j + 32;
+            const bool has1 = j1 < Ng;
+            const double x0 = nu * S.inuc[j];
+            const double x1 = has1 ? nu * S.inuc[j1] : 1e300;
+            // exp(-x) underflows to exactly 0 beyond 745.14 in IEEE double, as in the reference
+            const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
+            const double E1 = (x1 > 745.2) ? 0.0 : exp(-x1);
+            if (do_q && j >= jm) sq = fma(E0, S.u[j], sq);
+            sa = fma(E0, S.v[j], sa);
+            if (has1) {
+                if (do_q && j1 >= jm) sq1 = fma(E1, S.u[j1], sq1);
+                sa1 = fma(E1, S.v[j1], sa1);
+            }
         }
+        sq += sq1; sa += sa1;
         sq = warp_sum(sq);
         sa = warp_sum(sa);
         if (lane == 0) {
@@ -499,17 +522,51 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
     const int NP = L.NP, Ni = L.Ni, Ng = L.Ng;
     const int nrows = Ni + (Ng - 1);
+    // The resample abscissae of a row are log10-uniform, y_s = a + s*step (np.logspace), and so is the
+    // nu_tot grid they are interpolated on: the np.interp bracket is found arithmetically and then
+    // verified against the actual grid doubles, so only the static kernel factor K[row][s] is tabulated.
+    const int Nt = L.Nt;
+    const double* lxt = S.lxtS;
+    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
+    const double invD = (double)(Nt - 1) / (lxN - lx0);
+    constexpr int KPRE = 4;                         // samples per lane held in registers (NP <= 128)
+    double Kn[KPRE];
+    auto load_row = [&](int row_, double* Kr) {
+        const bool a_ = row_ < Ni;
+        const int r_ = a_ ? row_ : row_ - Ni;
+        const double* K = C.T + (a_ ? L.aggK : L.qeeK) + (size_t)r_ * NP;
+#pragma unroll
+        for (int q = 0; q < KPRE; ++q) { int e = lane + 32 * q; Kr[q] = (e < NP) ? __ldg(K + e) : 0.0; }
+    };
+    if (warp < nrows) load_row(warp, Kn);
     for (int row = warp; row < nrows; row += NW) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
-        const double* K = C.T + (is_a ? L.aggK : L.qeeK) + (size_t)r * NP;
-        const double* Tt = C.T + (is_a ? L.aggT : L.qeeT) + (size_t)r * NP;
-        const int* J = C.TI + (is_a ? L.aggJ : L.qeeJ) + (size_t)r * NP;
+        double Kc[KPRE];
+#pragma unroll
+        for (int q = 0; q < KPRE; ++q) Kc[q] = Kn[q];
+        if (row + NW < nrows) load_row(row + NW, Kn);           // prefetch the next row of this warp
+        const double a = __ldg(C.T + (is_a ? L.agg_a : L.qee_a) + r);
+        const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
         double s = 0.0;
-        for (int e = lane; e < NP; e += 32) {
-            double Kv = K[e];
-            double ph = exp10(lerp_log(S.Lm, J[e], Tt[e]));
-            s = fma(Kv, ph, s);
+#pragma unroll
+        for (int q = 0; q < KPRE; ++q) {
+            const int e = lane + 32 * q;
+            if (e < NP) {
+                const double y = (e == NP - 1) ? lxN : fma((double)e, step, a);
+                double Lv;
+                if (y >= lxN) Lv = S.Lm[Nt - 1];
+                else if (y <= lx0) Lv = S.Lm[0];
+                else {
+                    int j = (int)((y - lx0) * invD);
+                    j = max(0, min(j, Nt - 2));
+                    while (y < lxt[j]) --j;
+                    while (y >= lxt[j + 1]) ++j;
+                    const double dx = y - lxt[j];
+                    Lv = (dx == 0.0) ? S.Lm[j] : lerp_log(S.Lm, j, dx / (lxt[j + 1] - lxt[j]));
+                }
+                s = fma(Kc[q], exp10(Lv), s);
+            }
         }
         s = warp_sum(s);
         if (lane == 0) {

@@ -23,3 +23,17 @@ for _ in range(a.reps):
     N, sed = eng.run()
 torch.cuda.synchronize()
 print("timings (setup, cor, run) ms:", eng.last_timings(), "sum sed[0]:", float(sed[0].sum()))
+
+# per-phase cycle breakdown of thread 0 (diagnostic counters inside run_kernel)
+import ctypes as C  # noqa: E402
+prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+eng.lib.lhm_set_phase_profile(eng.h, C.c_void_p(prof.data_ptr()))
+eng.run()
+torch.cuda.synchronize()
+eng.lib.lhm_set_phase_profile(eng.h, None)
+p = prof.cpu().numpy().astype(float)
+names = ["loop/out", "photons", "uph", "electrons", "vectors", "syn_rows(w0)", "ic(w0)", "wait_ic", "ic_fin+ph_solves", "gg"]
+tot = p.sum()
+print("phase cycles per walker-step (thread 0), total %.0f:" % (tot / a.walkers / 10))
+for n_, v in zip(names, p):
+    print(f"  {n_:18s} {v / a.walkers / 10:10.0f}  {100 * v / tot:5.1f}%")
