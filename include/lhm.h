@@ -50,6 +50,8 @@ typedef struct {
     int qee_from_ic;        /* 0: Q_ee_f(nu_tot,n,nu_tot,n) LeMoC.py:283; 1: (...,nu_ic,photons_IC/V) Code.py:269 */
     int gg_npts;            /* resample points of a_gg / Q_ee_f: 50 in LeMoC/LeHaMoC_f.py:132,144 */
     int ic_path;            /* LHM_IC_PATH_R or LHM_IC_PATH_S */
+    int const_B;            /* 1: B(t) == B0 for every walker (m == 0 or Vexp == 0, LeMoC.py:200): the synchrotron
+                               exponentials are tabulated once per walker instead of every step */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 

@@ -30,16 +30,18 @@ struct RunArgs {
     const double* tabd;
     const int* tabi;
     const double* cor;      // [W] cor_factor_syn_el
+    const double* Ecache;   // [W,(Ns+Ni)*Ng] or null
     double* N_out;          // [W,(S),Ng] or null
     double* sed_out;        // [W,(S),Nt] or null
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
 
 __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlags& F, const double* consts,
-                                         const double* tabd, const int* tabi, int w) {
+                                         const double* tabd, const int* tabi, const double* Ecache, int w) {
     C.L = L; C.F = F;
     C.T = tabd + (size_t)w * L.n_doubles;
     C.TI = tabi + (size_t)w * L.n_ints;
+    C.E = Ecache ? Ecache + (size_t)w * (L.Ns + L.Ni) * L.Ng : nullptr;
     const double* c = consts + (size_t)w * LHM_NCONST;
     C.R0 = c[LHM_C_R0]; C.B0 = c[LHM_C_B0]; C.m = c[LHM_C_M]; C.Vexp = c[LHM_C_VEXP];
     C.dt = c[LHM_C_DT]; C.tinit = c[LHM_C_TINIT];
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
     Smem S;
     carve(S, smem_raw, A.L, NW);
     Ctx C;
-    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, w);
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, w);
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -141,6 +143,7 @@ struct UnitArgs {
     const double* consts;
     const double* tabd;
     const int* tabi;
+    const double* Ecache;
     const double *in0, *in1, *in2;
     double *out0, *out1, *out2;
     int mode;
@@ -154,7 +157,7 @@ __global__ void __launch_bounds__(NT, 2) unit_kernel(UnitArgs A) {
     Smem S;
     carve(S, smem_raw, A.L, NW);
     Ctx C;
-    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, w);
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, w);
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     ic_prepare<NT>(C, S);
@@ -282,6 +285,7 @@ struct lhm_handle {
     double* d_tabd;
     int* d_tabi;
     double* d_cor;
+    double* d_E;              // const-B exponential cache (cfg.const_B)
     const double* consts;     // device pointers of the current batch (caller- or staging-owned)
     const double* g_el;
     // staging for the *_host entry points
@@ -365,6 +369,8 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
+    if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
+        CUDA_TRY(cudaMalloc(&h->d_E, W * (size_t)(cfg->Ns + cfg->Ni) * cfg->Ng * sizeof(double)));
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     *out = h;
     return LHM_OK;
@@ -373,7 +379,7 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
 void lhm_destroy(lhm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor);
+    cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -393,7 +399,7 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     SetupArgs A;
     A.L = h->L; A.W = W; A.loss_minus_one = h->cfg.loss_minus_one; A.qee_from_ic = h->cfg.qee_from_ic;
     A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
-    A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi;
+    A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
@@ -431,6 +437,7 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     RunArgs A;
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
+    A.Ecache = h->d_E;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
@@ -507,6 +514,7 @@ static int launch_unit(lhm_handle* h, int mode, const double* in0, const double*
     CUDA_TRY(cudaSetDevice(h->device));
     UnitArgs A;
     A.L = h->L; A.F = h->F; A.W = h->W; A.consts = h->consts; A.tabd = h->d_tabd; A.tabi = h->d_tabi;
+    A.Ecache = nullptr;   // function-level calls take B as an argument: always recompute
     if (ic_path >= 0) A.F.ic_path = ic_path;
     A.in0 = in0; A.in1 = in1; A.in2 = in2; A.out0 = out0; A.out1 = out1; A.out2 = out2; A.mode = mode;
     unit_kernel<<<h->W, NT, h->smem, h->stream>>>(A);

@@ -43,6 +43,7 @@ struct Layout {
     int ps_j, pi_j;                 // Nt
     int u_idx, u_j, q_j;            // Ng
     int jm_syn;                     // Ns
+    int jz;                         // Ns+Ni: first gamma index whose exp(-nu/nu_c) is non-zero (const-B cache)
 
     int n_ints;
 };
@@ -68,7 +69,7 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
-    L.jm_syn = take(Ns);
+    L.jm_syn = take(Ns); L.jz = take(Ns + Ni);
     L.n_ints = o;
     return L;
 }

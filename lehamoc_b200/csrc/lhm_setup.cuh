@@ -20,6 +20,7 @@ struct SetupArgs {
     const double* el_inj;   // [W, Ng]
     const double* ext;      // [W, Nt]
     double* tabd;           // [W, L.n_doubles]
+    double* Ecache;         // [W, (Ns+Ni)*Ng] or null: exp(-nu/nu_c) table for time-constant B
     int* tabi;              // [W, L.n_ints]
 };
 
@@ -163,6 +164,28 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             TI[L.pi_j + k] = code; T[L.pi_dx + k] = dx; T[L.pi_Dx + k] = Dx;
         }
     }
+    // ---- synchrotron exponentials when B(t) == B0 (m == 0 or Vexp == 0): same expressions as phase_vectors /
+    //      phase_syn_rows evaluate per step, tabulated once ------------------------------------------------------
+    if (A.Ecache) {
+        double* E = A.Ecache + (size_t)w * (Ns + Ni) * Ng;
+        const double B0 = A.consts[(size_t)w * LHM_NCONST + LHM_C_B0];
+        for (int row = tid; row < Ns + Ni; row += NT) {
+            const double nu = (row < Ns) ? ns[row] : ni[row - Ns];
+            int lo = 0, hi = Ng;                                 // first j with nu/nu_c(g_j) <= 745.2 (x falls with j)
+            while (lo < hi) {
+                int mid = (lo + hi) >> 1;
+                double x = nu * (1.0 / (pc.nuc_pref * B0 * (g[mid] * g[mid])));
+                if (x > 745.2) lo = mid + 1; else hi = mid;
+            }
+            TI[L.jz + row] = lo;
+        }
+        for (int e = tid; e < (Ns + Ni) * Ng; e += NT) {
+            const int row = e / Ng, j = e - row * Ng;
+            const double nu = (row < Ns) ? ns[row] : ni[row - Ns];
+            const double x = nu * (1.0 / (pc.nuc_pref * B0 * (g[j] * g[j])));
+            E[(size_t)j * (Ns + Ni) + row] = (x > 745.2) ? 0.0 : exp(-x);   // transposed: [gamma][row]
+        }
+    }
     // ---- gamma-gamma sample tables ---------------------------------------------------------------
     const double* lxt = T + L.lxt;
     const double xmax_l = lxt[Nt - 1];                           // log10(max(x)) / log10(h nu_tot[-1]/mc2)
@@ -182,7 +205,7 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             double sv = xs * xIC;
             K = wtr * (pc.gg_pref * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
         }
-        T[L.aggK + e] = K;
+        T[L.aggK + (size_t)s * Ni + o] = K;                   // transposed: [sample][row]
         if (s == 0) { T[L.agg_a + o] = a; T[L.agg_d + o] = (xmax_l - a) / (double)(NP - 1); }
     }
     // Q_ee_f: NP samples per gamma (LeHaMoC_f.py:143-149); the 2.61 R_gg kernel and trapz weight folded in K
@@ -200,7 +223,7 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             double sv = 2.0 * gj * xs;
             K = wtr * (2.61 * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
         }
-        T[L.qeeK + e] = K;
+        T[L.qeeK + (size_t)s * Ng + j] = K;
         if (s == 0) { T[L.qee_a + j] = a; T[L.qee_d + j] = (xmax_l - a) / (double)(NP - 1); }
     }
 }

@@ -108,6 +108,7 @@ struct Ctx {
     Layout L;
     const double* T;      // double tables of this walker
     const int* TI;        // int tables of this walker
+    const double* E;      // [(Ns+Ni), Ng] exp(-nu/nu_c(gamma,B)) of this walker when B is constant in time, else null
     StepFlags F;
     double R0, B0, m, Vexp, dt, tinit;
     double Rad, B, V;     // current step
@@ -286,19 +287,22 @@ __device__ void phase_vectors(const Ctx& C, Smem& S) {
     __syncthreads();
 }
 
-// Phase F1: synchrotron emissivity + SSA rows; one warp per frequency, lanes over gamma.
-// exp(-nu/nu_c) is shared between Q_syn_space (nu/(a_cr g^2)) and aSSA (nu/nu_c(g,B)) on the nu_syn grid.
+// Phase F1: synchrotron emissivity + SSA, one THREAD per frequency row, serial over gamma with two independent
+// accumulator chains.  exp(-nu/nu_c) is shared between Q_syn_space (nu/(a_cr g^2)) and aSSA (nu/nu_c(g,B)) on the
+// nu_syn grid.  When B is constant in time the exponentials come from the per-walker table built at set-up
+// (transposed [gamma][row] so that the 32 rows of a warp read one coalesced line per gamma); leading gammas
+// whose exponential underflowed to exactly 0 are skipped.  Both modes use the same expressions and summation order.
 template <int NT>
 __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
     const Layout& L = C.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni;
     const bool need_q = C.F.syn_e, need_a = C.F.ssa;
     if (!need_q && !need_a) return;
+    const int NR = Ns + Ni;                                  // row stride of the transposed table
     const int nrows = Ns + (need_a ? Ni : 0);
     const double qpref = kPC.C_syn * pow(C.B, 2.0 / 3.0);
     const double apref = kPC.ssa_pref * C.B;
-    for (int row = warp; row < nrows; row += NW) {
+    for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_syn = row < Ns;
         const int k = is_syn ? row : row - Ns;
         if (!all_rows) {        // the drivers only consume [1:] / [1:-1]  (LeMoC.py:268-276)
@@ -306,36 +310,50 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
             if (is_syn ? (k > Ns - 2) : (k > Ni - 2)) continue;
         }
         const double nu = is_syn ? C.T[L.nsyn + k] : C.T[L.nic + k];
-        const int jm = is_syn ? C.TI[L.jm_syn + k] : 0;
         const bool do_q = is_syn && need_q && (k < Ns - 1);
-        double sq = 0.0, sa = 0.0;
-        // two gammas per lane and iteration: two independent exp() chains in flight
-        double sq1 = 0.0, sa1 = 0.0;
-        for (int j = lane; j < Ng; j += 64) {
-            const int j1 = j + 32;
-            const bool has1 = j1 < Ng;
-            const double x0 = nu * S.inuc[j];
-            const double x1 = has1 ? nu * S.inuc[j1] : 1e300;
-            // exp(-x) underflows to exactly 0 beyond 745.14 in IEEE double, as in the reference
-            const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
-            const double E1 = (x1 > 745.2) ? 0.0 : exp(-x1);
-            if (do_q && j >= jm) sq = fma(E0, S.u[j], sq);
-            sa = fma(E0, S.v[j], sa);
-            if (has1) {
-                if (do_q && j1 >= jm) sq1 = fma(E1, S.u[j1], sq1);
-                sa1 = fma(E1, S.v[j1], sa1);
+        const int jm = do_q ? C.TI[L.jm_syn + k] : Ng;       // Q_syn_space mask: gammas below jm emit nothing
+        double sq0 = 0.0, sq1 = 0.0, sa0 = 0.0, sa1 = 0.0;
+        if (C.E) {
+            const double* __restrict__ Et = C.E + row;
+            int j = C.TI[L.jz + row] & ~1;
+#pragma unroll 4
+            for (; j + 1 < Ng; j += 2) {
+                const double E0 = __ldg(Et + (size_t)j * NR), E1 = __ldg(Et + (size_t)(j + 1) * NR);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                sa0 = fma(E0, S.v[j], sa0);
+                sa1 = fma(E1, S.v[j + 1], sa1);
+            }
+            if (j < Ng) {
+                const double E0 = __ldg(Et + (size_t)j * NR);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                sa0 = fma(E0, S.v[j], sa0);
+            }
+        } else {
+            int j = 0;
+            for (; j + 1 < Ng; j += 2) {
+                const double x0 = nu * S.inuc[j], x1 = nu * S.inuc[j + 1];
+                // exp(-x) underflows to exactly 0 beyond 745.14 in IEEE double, as in the reference
+                const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
+                const double E1 = (x1 > 745.2) ? 0.0 : exp(-x1);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                sa0 = fma(E0, S.v[j], sa0);
+                sa1 = fma(E1, S.v[j + 1], sa1);
+            }
+            if (j < Ng) {
+                const double x0 = nu * S.inuc[j];
+                const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                sa0 = fma(E0, S.v[j], sa0);
             }
         }
-        sq += sq1; sa += sa1;
-        sq = warp_sum(sq);
-        sa = warp_sum(sa);
-        if (lane == 0) {
-            if (is_syn) {
-                if (k < Ns - 1) S.Qsyn[k] = do_q ? qpref * C.T[L.nm23s + k] * sq : 0.0;
-                S.aS[k] = need_a ? apref * C.T[L.nm53s + k] * sa : 0.0;
-            } else {
-                S.aI[k] = apref * C.T[L.nm53i + k] * sa;
-            }
+        const double sq = sq0 + sq1, sa = sa0 + sa1;
+        if (is_syn) {
+            if (k < Ns - 1) S.Qsyn[k] = do_q ? qpref * C.T[L.nm23s + k] * sq : 0.0;
+            S.aS[k] = need_a ? apref * C.T[L.nm53s + k] * sa : 0.0;
+        } else {
+            S.aI[k] = apref * C.T[L.nm53i + k] * sa;
         }
     }
 }
@@ -514,69 +532,61 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
     __syncthreads();
 }
 
-// Phase H: a_gg (LeHaMoC_f.py:127-137) and Q_ee_f (LeHaMoC_f.py:140-151); warp per row, lanes over samples.
-// `Lng`/(stencil) give n_g: log10 of the field Q_ee_f's n_g is interpolated from.
+// Phase H: a_gg (LeHaMoC_f.py:127-137) and Q_ee_f (LeHaMoC_f.py:140-151), one THREAD per row.
+// The NP resample abscissae of a row are log10-uniform, y_s = a + s*step (np.logspace), and increase with s, so
+// the np.interp bracket on the nu_tot grid only moves forward: it is advanced incrementally against the actual
+// grid doubles (no search, no stencil table).  Only the static factor K[s][row] (trapezoid weight x pair-production
+// kernel x x') is tabulated, transposed so that a warp reads one coalesced line per sample.  Two samples are in
+// flight per thread.  `Lng` gives n_g: log10 of the field Q_ee_f's n_g is interpolated from.
+__device__ __forceinline__ double gg_sample(const double* __restrict__ lxt, const double* __restrict__ Lm, int Nt,
+                                            double y, int& j) {
+    // returns log10 of the interpolated photon density at abscissa y; j is the running bracket (lxt[j] <= y)
+    if (y >= lxt[Nt - 1]) return Lm[Nt - 1];
+    if (y <= lxt[0]) return Lm[0];
+    while (y >= lxt[j + 1]) ++j;
+    const double dx = y - lxt[j];
+    return (dx == 0.0) ? Lm[j] : lerp_log(Lm, j, dx / (lxt[j + 1] - lxt[j]));
+}
+
 template <int NT>
 __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_out, double* qee_out) {
     const Layout& L = C.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
-    const int NP = L.NP, Ni = L.Ni, Ng = L.Ng;
+    const int NP = L.NP, Ni = L.Ni, Ng = L.Ng, Nt = L.Nt;
     const int nrows = Ni + (Ng - 1);
-    // The resample abscissae of a row are log10-uniform, y_s = a + s*step (np.logspace), and so is the
-    // nu_tot grid they are interpolated on: the np.interp bracket is found arithmetically and then
-    // verified against the actual grid doubles, so only the static kernel factor K[row][s] is tabulated.
-    const int Nt = L.Nt;
     const double* lxt = S.lxtS;
-    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
-    const double invD = (double)(Nt - 1) / (lxN - lx0);
-    constexpr int KPRE = 4;                         // samples per lane held in registers (NP <= 128)
-    double Kn[KPRE];
-    auto load_row = [&](int row_, double* Kr) {
-        const bool a_ = row_ < Ni;
-        const int r_ = a_ ? row_ : row_ - Ni;
-        const double* K = C.T + (a_ ? L.aggK : L.qeeK) + (size_t)r_ * NP;
-#pragma unroll
-        for (int q = 0; q < KPRE; ++q) { int e = lane + 32 * q; Kr[q] = (e < NP) ? __ldg(K + e) : 0.0; }
-    };
-    if (warp < nrows) load_row(warp, Kn);
-    for (int row = warp; row < nrows; row += NW) {
+    const double lxN = lxt[Nt - 1];
+    for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
-        double Kc[KPRE];
-#pragma unroll
-        for (int q = 0; q < KPRE; ++q) Kc[q] = Kn[q];
-        if (row + NW < nrows) load_row(row + NW, Kn);           // prefetch the next row of this warp
+        const int stride = is_a ? Ni : Ng;
+        const double* __restrict__ K = C.T + (is_a ? L.aggK : L.qeeK) + r;      // K[s*stride + r]
         const double a = __ldg(C.T + (is_a ? L.agg_a : L.qee_a) + r);
         const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
-        double s = 0.0;
-#pragma unroll
-        for (int q = 0; q < KPRE; ++q) {
-            const int e = lane + 32 * q;
+        double s0 = 0.0, s1 = 0.0;
+        if (step > 0.0) {                       // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
+            int j = 0;
+            int e = 0;
+            for (; e + 1 < NP; e += 2) {
+                const double y0 = fma((double)e, step, a);
+                const double y1 = (e + 1 == NP - 1) ? lxN : fma((double)(e + 1), step, a);
+                const double K0 = __ldg(K + (size_t)e * stride), K1 = __ldg(K + (size_t)(e + 1) * stride);
+                const double L0 = gg_sample(lxt, S.Lm, Nt, y0, j);
+                const double L1 = gg_sample(lxt, S.Lm, Nt, y1, j);
+                s0 = fma(K0, exp10(L0), s0);
+                s1 = fma(K1, exp10(L1), s1);
+            }
             if (e < NP) {
-                const double y = (e == NP - 1) ? lxN : fma((double)e, step, a);
-                double Lv;
-                if (y >= lxN) Lv = S.Lm[Nt - 1];
-                else if (y <= lx0) Lv = S.Lm[0];
-                else {
-                    int j = (int)((y - lx0) * invD);
-                    j = max(0, min(j, Nt - 2));
-                    while (y < lxt[j]) --j;
-                    while (y >= lxt[j + 1]) ++j;
-                    const double dx = y - lxt[j];
-                    Lv = (dx == 0.0) ? S.Lm[j] : lerp_log(S.Lm, j, dx / (lxt[j + 1] - lxt[j]));
-                }
-                s = fma(Kc[q], exp10(Lv), s);
+                const double y0 = (e == NP - 1) ? lxN : fma((double)e, step, a);
+                s0 = fma(__ldg(K + (size_t)e * stride), exp10(gg_sample(lxt, S.Lm, Nt, y0, j)), s0);
             }
         }
-        s = warp_sum(s);
-        if (lane == 0) {
-            if (is_a) agg_out[r] = s;
-            else {
-                double ng = 0.0;
-                if (2.0 * S.gS[r] > 1.0)
-                    ng = exp10(interp_eval(Lng, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
-                qee_out[r] = kPC.qee_pref * (ng * s);
-            }
+        const double s = s0 + s1;
+        if (is_a) agg_out[r] = s;
+        else {
+            double ng = 0.0;
+            if (2.0 * S.gS[r] > 1.0)
+                ng = exp10(interp_eval(Lng, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
+            qee_out[r] = kPC.qee_pref * (ng * s);
         }
     }
 }
