@@ -29,13 +29,16 @@ struct Smem {
     double *cp, *dp;                             // solver scratch (size Nmax)
     double *ne, *av, *u, *v, *inuc;              // per-gamma vectors of phase E
     double *Qsyn, *aS, *aI, *QIC;                // contraction results
-    double *tri;                                 // [Nt][4] = {1/nu_i, 2 ln nu_i, w_i n_i, 0}
+    double *tri;                                 // [Nt][4] = {1/nu_i, (1/nu_i) 2 ln nu_i, w_i n_i, 1/nu_i^2}
     double *gS, *lgS, *inv4gS, *epsS, *lnu4S, *nuoS;   // IC pair-constant inputs
     double *lxtS;                                // log10(h nu_tot/mc2): abscissae of the gamma-gamma interpolation
     double *sfx;                                 // [4][Nt] suffix sums of IC path S
     double *partial;                             // [NW][NiPad] IC partial sums
-    unsigned short* tasks;                       // IC (o-group, gamma-block) task list
-    int* ntasks;                                 // (shared) number of active tasks
+    unsigned short* tasks;                       // IC (o-group, gamma-block) task list, active tasks only
+    unsigned short* ti0;                         // first target-frequency index a task has to visit
+    unsigned short* ti1;                         // first target-frequency index from which no pair of the task clamps
+    unsigned short* cand;                        // scratch of ic_prepare: i0 per candidate task (0xFFFF = inactive)
+    int* tbound;                                 // [NW+1] task range of every warp (cost-balanced, static)
 };
 
 __host__ __device__ inline int imax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
@@ -74,7 +77,8 @@ __host__ __device__ inline int ic_max_tasks(const Layout& L) {
     return ((L.Ni + IC_OG - 1) / IC_OG) * ((L.Ng + IC_GB - 1) / IC_GB);
 }
 __host__ __device__ inline size_t smem_bytes(const Layout& L, int NW) {
-    return smem_doubles(L, NW) * sizeof(double) + (size_t)pad2(ic_max_tasks(L)) * sizeof(unsigned short) * 1 + 16;
+    return smem_doubles(L, NW) * sizeof(double) + (size_t)pad2(ic_max_tasks(L)) * sizeof(unsigned short) * 5
+           + (size_t)(NW + 1 + 3) / 4 * 4 * sizeof(int);
 }
 
 __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
@@ -99,8 +103,12 @@ __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     S.partial = scratch0;
     S.sfx = scratch0;
     p = base + smem_doubles(L, NW);
-    S.tasks = reinterpret_cast<unsigned short*>(p);
-    S.ntasks = reinterpret_cast<int*>(S.tasks + pad2(ic_max_tasks(L)));
+    const int mt = pad2(ic_max_tasks(L));
+    S.tbound = reinterpret_cast<int*>(p);
+    S.tasks = reinterpret_cast<unsigned short*>(S.tbound + (NW + 1 + 3) / 4 * 4);
+    S.ti0 = S.tasks + mt;
+    S.ti1 = S.ti0 + mt;
+    S.cand = S.ti1 + mt;                                   // 2 entries per candidate
 }
 
 // Per-walker context: table pointers + scalars of the current step
@@ -115,11 +123,19 @@ struct Ctx {
 };
 
 // ---------------------------------------------------------------------------------------------
-// load the static IC inputs and build the IC task list (once per walker)
+// load the static IC inputs and build the IC task list (once per walker).
+//
+// A task is a tile of IC_OG outgoing frequencies x IC_GB gammas.  Everything that decides which tiles matter is a
+// function of the grids only: a pair is active iff gamma > eps_o (the reference's `q_IC[0] > 0.` test,
+// LeHaMoC_f.py:117), and within a pair F <= 0 (clamped to 0 by LeHaMoC_f.py:121) for every target frequency
+// nu_i <= A = nu_o/(4 gamma (gamma-eps_o)), because F > 0 <=> q = A/nu_i < 1.  So per tile the smallest A over its
+// active pairs gives the first target index i0 the tile has to visit (one guard element kept), the largest A the
+// index i1 from which no pair clamps any more, and the tile costs (Ntar - i0) inner iterations.  Tiles are dealt to the warps as contiguous, cost-balanced ranges -- a static
+// schedule, so the summation order (and the result bits) do not depend on timing.
 template <int NT>
 __device__ void ic_prepare(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, NW = NT / 32;
     for (int j = tid; j < L.Ng; j += NT) {
         S.gS[j] = C.T[L.g + j]; S.lgS[j] = C.T[L.lg + j]; S.inv4gS[j] = C.T[L.inv4g + j];
     }
@@ -127,27 +143,71 @@ __device__ void ic_prepare(const Ctx& C, Smem& S) {
         S.epsS[o] = C.T[L.eps + o]; S.lnu4S[o] = C.T[L.lnu4 + o]; S.nuoS[o] = C.T[L.nic + o];
     }
     for (int i = tid; i < L.Nt; i += NT) {
+        const double x = C.T[L.invnt + i];
         S.lxtS[i] = C.T[L.lxt + i];
-        S.tri[4 * i + 0] = C.T[L.invnt + i];
-        S.tri[4 * i + 1] = C.T[L.l2nt + i];
-        S.tri[4 * i + 2] = 0.0;
-        S.tri[4 * i + 3] = 0.0;
+        S.tri[4 * i + 0] = x;                            // 1/nu_i
+        S.tri[4 * i + 1] = x * C.T[L.l2nt + i];          // (1/nu_i) 2 ln nu_i
+        S.tri[4 * i + 2] = 0.0;                          // p_i = trapz weight x photons (every step)
+        S.tri[4 * i + 3] = x * x;                        // 1/nu_i^2
+    }
+    __syncthreads();
+    const int No = L.Ni - 1, Ntar = L.Nt - 1;             // outgoing nu_ic[0..Ni-2], targets nu_tot[0..Nt-2]
+    const int nog = (No + IC_OG - 1) / IC_OG, ngb = (L.Ng + IC_GB - 1) / IC_GB;
+    for (int c = tid; c < nog * ngb; c += NT) {
+        const int og = c / ngb, gb = c - og * ngb;
+        double Amax = -1.0, Amin = 1e308;
+        for (int oo = 0; oo < IC_OG; ++oo) {
+            const int o = og * IC_OG + oo;
+            if (o >= No) break;
+            const double eps = S.epsS[o], nuo = S.nuoS[o];
+            for (int jj = 0; jj < IC_GB; ++jj) {
+                const int j = gb * IC_GB + jj;
+                if (j >= L.Ng) break;
+                if (S.gS[j] > eps) {
+                    const double rr = 1.0 / (S.gS[j] - eps);
+                    const double Av = nuo * rr * S.inv4gS[j];
+                    Amax = fmax(Amax, Av);
+                    Amin = fmin(Amin, Av);
+                }
+            }
+        }
+        unsigned short i0 = 0xFFFF, i1 = 0xFFFF;
+        if (Amax >= 0.0) {
+            int is = 0;
+            while (is < Ntar && Amin * S.tri[4 * is] >= 1.0) ++is;     // nu_i <= Amin: q >= 1, F <= 0 for EVERY pair
+            i0 = (unsigned short)max(is - 1, 0);                       // (one guard element kept)
+            while (is < Ntar && Amax * S.tri[4 * is] >= 1.0) ++is;     // first i with q < 1 for every pair of the tile
+            i1 = (unsigned short)min(is + 1, Ntar);                    // one guard element: beyond, q <= nu_i/nu_{i+1} < 1
+        }
+        S.cand[2 * c] = i0;
+        S.cand[2 * c + 1] = i1;
     }
     __syncthreads();
     if (tid == 0) {
-        // active tasks in (o-group major, gamma-block minor) order.  A pair is active iff gamma > eps_o
-        // (the reference's `q_IC[0] > 0.` test, LeHaMoC_f.py:117); eps grows with o, gamma with j.
-        const int No = L.Ni - 1;                                   // outgoing frequencies nu_ic[0..Ni-2]
-        const int nog = (No + IC_OG - 1) / IC_OG, ngb = (L.Ng + IC_GB - 1) / IC_GB;
         int nt = 0;
-        for (int og = 0; og < nog; ++og) {
-            double emin = S.epsS[og * IC_OG];
-            for (int gb = 0; gb < ngb; ++gb) {
-                int jhi = min(gb * IC_GB + IC_GB - 1, L.Ng - 1);
-                if (S.gS[jhi] > emin) S.tasks[nt++] = (unsigned short)((og << 8) | gb);
-            }
+        long long tot = 0;
+        constexpr int FIXED = 12;                          // per-tile preamble (reciprocal + log per pair) in iterations
+        for (int c = 0; c < nog * ngb; ++c) {
+            const unsigned short i0 = S.cand[2 * c];
+            if (i0 == 0xFFFF) continue;
+            const int og = c / ngb, gb = c - og * ngb;
+            S.tasks[nt] = (unsigned short)((og << 8) | gb);
+            S.ti0[nt] = i0;
+            S.ti1[nt] = S.cand[2 * c + 1];
+            tot += (Ntar - i0) + FIXED;
+            ++nt;
         }
-        *S.ntasks = nt;
+        // warp w takes the tiles whose cumulative-cost midpoint lies in [w, w+1) * tot / NW
+        int wcur = 0;
+        long long cum = 0;
+        S.tbound[0] = 0;
+        for (int t = 0; t < nt; ++t) {
+            const long long cst = (Ntar - S.ti0[t]) + FIXED;
+            const long long mid2 = 2 * cum + cst;           // 2 x midpoint
+            while (wcur < NW - 1 && mid2 * NW >= 2 * tot * (wcur + 1)) S.tbound[++wcur] = t;
+            cum += cst;
+        }
+        while (wcur < NW) S.tbound[++wcur] = nt;
     }
     __syncthreads();
 }
@@ -360,26 +420,33 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
 
 // Phase F2, path R: Blumenthal-Gould/Jones triple sum with the kernel recomputed in registers.
 //   F = 2q ln q + (1+2q)(1-q) + G(1-q),  q = A/nu_i,  A = nu_o/(4 g (g-eps)),  G = w^2/(2(1+w)), w = eps/(g-eps)
-//     = G1 + q*(c1 - 2 ln nu_i - 2q),    G1 = 1+G,    c1 = 1 - G + 2 ln A          (exact regrouping)
-// per (o, gamma) pair: one reciprocal + one log; per (o, gamma, nu_i) element: 1 DMUL, 1 DADD, 3 DFMA on the
-// FP64 pipe; the clamp max(F,0) is a sign-mask on the integer pipe (fmax() would add a DSETP + 5 ALU ops).
+//     = G1 + q*(c1 - 2 ln nu_i - 2q),    G1 = 1+G,    c1 = 1 - G + 2 ln A                    (exact regrouping)
+//     = G1 + a1*x_i + a2*(x_i 2 ln nu_i) + a3*x_i^2,   x_i = 1/nu_i,  a1 = A c1, a2 = -A, a3 = -2 A^2
+// per (o, gamma) pair: one reciprocal + one log; per (o, gamma, nu_i) element: 3 DFMA for F and one DFMA for the
+// accumulation, the latter predicated on the sign bit of F (that is `function_IC[function_IC < 0.] = 0.`,
+// LeHaMoC_f.py:121: an integer compare on the high word instead of a DSETP/DMNMX on the FP64 pipe).
+__device__ __forceinline__ void ic_acc_if_nonneg(double& acc, double p, double F) {
+    asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, 0;\n\t@q fma.rn.f64 %0, %2, %3, %0;\n\t}"
+        : "+d"(acc) : "r"(__double2hiint(F)), "d"(p), "d"(F));
+}
+
 template <int NT>
 __device__ void phase_ic_R(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, NW = NT / 32;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ng = L.Ng, No = L.Ni - 1, Ntar = L.Nt - 1;
     const int NiPad = ((L.Ni + IC_OG - 1) / IC_OG) * IC_OG;
     double* part = S.partial + warp * NiPad;
     for (int o = lane; o < NiPad; o += 32) part[o] = 0.0;
     __syncwarp();
-    const int nt = *S.ntasks;
-    const int t0 = (int)(((long long)nt * warp) / NW), t1 = (int)(((long long)nt * (warp + 1)) / NW);
+    const int t0 = S.tbound[warp], t1 = S.tbound[warp + 1];
     const int osub = lane >> 2, gsub = lane & 3;
     int cur_og = -1;
     double run = 0.0;
     const double2* tri2 = reinterpret_cast<const double2*>(S.tri);
     for (int t = t0; t < t1; ++t) {
         const int og = S.tasks[t] >> 8, gb = S.tasks[t] & 255;
+        const int i0 = S.ti0[t], i1 = S.ti1[t];
         if (og != cur_og) {
             if (cur_og >= 0) {
                 run += __shfl_xor_sync(0xffffffffu, run, 1);
@@ -393,7 +460,7 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
         const double eps = ovalid ? S.epsS[o] : 0.0;
         const double nuo = ovalid ? S.nuoS[o] : 0.0;
         const double lnu4 = ovalid ? S.lnu4S[o] : 0.0;
-        double A[IC_PT], c1[IC_PT], G1[IC_PT], acc[IC_PT], wa[IC_PT];
+        double a1[IC_PT], a2[IC_PT], a3[IC_PT], G1[IC_PT], acc[IC_PT], wa[IC_PT];
 #pragma unroll
         for (int r = 0; r < IC_PT; ++r) {
             const int j = gb * IC_GB + r * IC_GL + gsub;
@@ -403,24 +470,38 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             const double rr = 1.0 / d;
             const double i4 = S.inv4gS[jj];
             const double Gv = 2.0 * eps * eps * rr * i4;
-            A[r] = act ? nuo * rr * i4 : 0.0;
+            const double Av = nuo * rr * i4;
+            const double c1 = (1.0 - Gv) + 2.0 * (lnu4 - S.lgS[jj] - log(d));
+            a1[r] = act ? Av * c1 : 0.0;
+            a2[r] = act ? -Av : 0.0;
+            a3[r] = act ? -2.0 * Av * Av : 0.0;
             G1[r] = act ? 1.0 + Gv : 0.0;
-            c1[r] = act ? (1.0 - Gv) + 2.0 * (lnu4 - S.lgS[jj] - log(d)) : 0.0;
             wa[r] = act ? S.av[jj] : 0.0;
             acc[r] = 0.0;
         }
-#pragma unroll 2
-        for (int i = 0; i < Ntar; ++i) {
-            const double2 t01 = tri2[2 * i];         // {1/nu_i, 2 ln nu_i}
-            const double pi = S.tri[4 * i + 2];      // w_i n_i
+        // [i0, i1): some pair of the tile may still have q >= 1, i.e. F <= 0 -> clamp
+        for (int i = i0; i < i1; ++i) {
+            const double2 u = tri2[2 * i];           // {1/nu_i, (1/nu_i) 2 ln nu_i}
+            const double2 v = tri2[2 * i + 1];       // {w_i n_i, 1/nu_i^2}
 #pragma unroll
             for (int r = 0; r < IC_PT; ++r) {
-                double qv = A[r] * t01.x;
-                double s = c1[r] - t01.y;
-                s = fma(-2.0, qv, s);
-                double Fv = fma(qv, s, G1[r]);
-                Fv = clamp_neg_to_zero(Fv);          // function_IC[function_IC < 0.] = 0.
-                acc[r] = fma(pi, Fv, acc[r]);
+                double Fv = fma(a1[r], u.x, G1[r]);
+                Fv = fma(a2[r], u.y, Fv);
+                Fv = fma(a3[r], v.y, Fv);
+                ic_acc_if_nonneg(acc[r], v.x, Fv);   // function_IC[function_IC < 0.] = 0.
+            }
+        }
+        // [i1, Ntar): q < 1 for every active pair of the tile, so F > 0 and the clamp is the identity
+#pragma unroll 2
+        for (int i = i1; i < Ntar; ++i) {
+            const double2 u = tri2[2 * i];
+            const double2 v = tri2[2 * i + 1];
+#pragma unroll
+            for (int r = 0; r < IC_PT; ++r) {
+                double Fv = fma(a1[r], u.x, G1[r]);
+                Fv = fma(a2[r], u.y, Fv);
+                Fv = fma(a3[r], v.y, Fv);
+                acc[r] = fma(v.x, Fv, acc[r]);
             }
         }
 #pragma unroll
@@ -447,16 +528,16 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
         double* P = S.sfx + tid * NtP;
         P[Ntar] = 0.0;
         for (int i = Ntar - 1; i >= 0; --i) {
-            double inv = S.tri[4 * i], l2 = S.tri[4 * i + 1], p = S.tri[4 * i + 2];
-            double f = (tid == 0) ? 1.0 : (tid == 1) ? inv : (tid == 2) ? inv * l2 : inv * inv;
+            const double p = S.tri[4 * i + 2];
+            const double f = (tid == 0) ? 1.0 : (tid == 1) ? S.tri[4 * i] : (tid == 2) ? S.tri[4 * i + 1] : S.tri[4 * i + 3];
             s = fma(p, f, s);
             P[i] = s;
         }
     }
     __syncthreads();
     const double* P0 = S.sfx, *P1 = S.sfx + NtP, *P2 = S.sfx + 2 * NtP, *P3 = S.sfx + 3 * NtP;
-    const double lnu0 = 0.5 * S.tri[1];                                 // ln nu_0
-    const double inv_dl = (double)(Ntar - 1) / (0.5 * S.tri[4 * (Ntar - 1) + 1] - lnu0);
+    const double lnu0 = 0.5 * C.T[L.l2nt];                              // ln nu_0
+    const double inv_dl = (double)(Ntar - 1) / (0.5 * C.T[L.l2nt + Ntar - 1] - lnu0);
     for (int o = warp; o < No; o += NW) {
         const double eps = S.epsS[o], nuo = S.nuoS[o], lnu4 = S.lnu4S[o];
         double sum = 0.0;
