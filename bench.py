@@ -49,6 +49,34 @@ def algorithmic_flops_per_model(batch, ic_path: str):
     return run, cor, active
 
 
+def ic_tile_schedule(batch, w=0, OG=8, GB=16):
+    """Replays ic_prepare (lhm_step.cuh) for walker w: returns (tiles, inner iterations, clamped iterations) of one
+    timestep.  Every tile iteration executes OG*GB (o,gamma) elements, inactive lanes included."""
+    h, m_el, c = 6.62607015e-27, 9.1093837015e-28, 2.99792458e10
+    g = batch.g_el[w]
+    no = batch.nu_ic[w, :-1]
+    x = 1.0 / batch.nu_tot[w, :-1]
+    Ntar = len(x)
+    eps = h * no / (m_el * c ** 2.)
+    act = g[None, :] > eps[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = no[:, None] * (1.0 / (g[None, :] - eps[:, None])) * (1.0 / (4.0 * g))[None, :]
+    tiles = iters = clamped = 0
+    for o0 in range(0, len(no), OG):
+        for j0 in range(0, len(g), GB):
+            a = act[o0:o0 + OG, j0:j0 + GB]
+            if not a.any():
+                continue
+            Av = A[o0:o0 + OG, j0:j0 + GB][a]
+            is0 = int(np.argmax(Av.min() * x < 1.0)) if (Av.min() * x < 1.0).any() else Ntar
+            is1 = int(np.argmax(Av.max() * x < 1.0)) if (Av.max() * x < 1.0).any() else Ntar
+            i0, i1 = max(is0 - 1, 0), min(is1 + 1, Ntar)
+            tiles += 1
+            iters += Ntar - i0
+            clamped += max(i1 - i0, 0)
+    return tiles, iters, clamped
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
@@ -330,8 +358,25 @@ def main():
     except Exception:
         pass
     alg_bytes = float(h2d + d2h)
+    # executed FP64-pipe instructions of the IC phase (path R): 4 per tile element (3 DFMA for F + 1 accumulate)
+    # plus ~45 per (o,gamma) pair for the reciprocal + log preamble; 2 flops per instruction at the FMA peak
+    pipe = None
+    if args.ic_path == "R":
+        shared = bool(np.all(batch.g_el == batch.g_el[0]) and np.all(batch.nu_tot == batch.nu_tot[0])
+                      and np.all(batch.nu_ic == batch.nu_ic[0]))
+        ws = [0] if shared else list(range(0, W, max(1, W // 8)))
+        sched = np.array([ic_tile_schedule(batch, w) for w in ws], dtype=np.float64).mean(axis=0)
+        inst_step = sched[1] * 128 * 4 + sched[0] * 128 * 45
+        inst_launch = inst_step * float(batch.nsteps.sum())
+        pipe = {"ic_tiles_per_step": sched[0], "ic_tile_iterations_per_step": sched[1],
+                "ic_clamped_iterations_per_step": sched[2],
+                "executed_fp64_inst_per_launch": inst_launch,
+                "fp64_pipe_frac": 2.0 * inst_launch / (run_ms * 1e-3) / 1e12 / peak_tf,
+                "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element + ~45 per pair "
+                        "preamble, inactive lanes of a tile included; compare with ncu sm__pipe_fp64_cycles_active"}
     roofline = {"bound": "fp64", "kernel": "lhm::run_kernel (fused timestep loop, one CTA per walker)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "executed": pipe,
                 "peak_source": "measured live by lhm_fp64_peak_probe (DFMA, 8 independent chains/thread); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
                 "flops_per_launch": flops_launch, "flops_per_model": float(run_flops.mean()),

@@ -140,6 +140,19 @@ int lhm_gg_batch(lhm_handle*, const double* n, const double* photons_IC_dens, do
 int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const double* d, double* x,
                            void* cuda_stream);
 
+/* A10 fit epilogue for W walkers, one warp per walker (handle-free, like lhm_bidiag_solve_batch):
+ *   Model.__call__ (Fit_emcee/fit_emcee.py:103-115): xp = log10(nu_tot) + doppler - log10(1+z),
+ *     yp = log10(nuLnu) - distance_norm + 4*doppler, y_model = np.interp(x, xp, yp);
+ *   log_likelihood_LeMoC (fit_emcee.py:121-145): Gaussian chi^2 on the detections (flags == 0) with jitter
+ *     exp(2 log_f), the lower error bar on the last two detections when the model lies below them, and the
+ *     erf upper-limit term (flags == 1, rms = 0.05).
+ * nu_tot, nuLnu [W,Nt]; doppler, log_f [W]; x, y, yerr_hi, yerr_lo, flags [nd] (flags as the reference's floats);
+ * logl_out [W]; ymodel_out [W,nd] or NULL. */
+int lhm_loglike_batch(int W, int Nt, const double* nu_tot, const double* nuLnu, const double* doppler,
+                      const double* log_f, double log10_1pz, double distance_norm, int nd, const double* x,
+                      const double* y, const double* yerr_hi, const double* yerr_lo, const double* flags,
+                      double* logl_out, double* ymodel_out, void* cuda_stream);
+
 /* measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator */
 int lhm_fp64_peak_probe(int device, void* cuda_stream, double* tflops_out);
 

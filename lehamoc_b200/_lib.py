@@ -50,6 +50,7 @@ SIGNATURES = {
     "lhm_ic_emissivity_batch": (C.c_int, [_P] * 4 + [C.c_int]),
     "lhm_gg_batch": (C.c_int, [_P] * 5),
     "lhm_bidiag_solve_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P]),
+    "lhm_loglike_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int] + [_P] * 8),
     "lhm_fp64_peak_probe": (C.c_int, [C.c_int, _P, C.POINTER(C.c_double)]),
 }
 

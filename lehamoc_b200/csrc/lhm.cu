@@ -244,6 +244,59 @@ __global__ void __launch_bounds__(128) bidiag_kernel(int n, const double* b, con
     if (threadIdx.x == 0) backsub(cp, dp, x + off, n);
 }
 
+// A10 fit epilogue: observation transform + log-likelihood (Fit_emcee/fit_emcee.py:103-115,121-145), warp per walker
+constexpr int LL_WARPS = 4;
+struct LoglikeArgs {
+    int W, Nt, nd;
+    const double *nu_tot, *sed, *doppler, *log_f;
+    double log1pz, dist_norm;
+    const double *x, *y, *yerr, *yerr1, *flags;
+    double *logl, *ymodel;
+};
+
+__global__ void __launch_bounds__(LL_WARPS * 32) loglike_kernel(LoglikeArgs A) {
+    extern __shared__ __align__(16) double sll[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * LL_WARPS + warp;
+    if (w >= A.W) return;                                        // whole warp exits together
+    const int Nt = A.Nt, nd = A.nd;
+    double* xp = sll + (size_t)warp * 2 * Nt;
+    double* yp = xp + Nt;
+    const double dop = A.doppler[w], lf = A.log_f[w];
+    const double flux_norm = -A.dist_norm + 4 * dop;            // fit_emcee.py:105-107
+    for (int k = lane; k < Nt; k += 32) {
+        xp[k] = log10(A.nu_tot[(size_t)w * Nt + k]) + dop - A.log1pz;        // fit_emcee.py:109
+        yp[k] = log10(A.sed[(size_t)w * Nt + k]) + flux_norm;               // fit_emcee.py:110
+    }
+    __syncwarp();
+    // the last two detections (y_det[-1], y_det[-2]) take the lower error bar when the model is below them
+    int m1 = -1, m2 = -1;
+    for (int i = nd - 1; i >= 0; --i)
+        if (A.flags[i] == 0.0) { if (m1 < 0) m1 = i; else { m2 = i; break; } }
+    const double rms = 0.05;
+    const double jit = exp(2 * lf);
+    double det = 0.0, lim = 0.0;
+    for (int i = lane; i < nd; i += 32) {
+        int code; double dx, Dx;
+        interp_stencil(A.x[i], xp, Nt, code, dx, Dx);
+        const double ym = interp_eval(yp, code, dx, Dx);         // np.interp(x, xp, y_pred_d)  fit_emcee.py:115
+        if (A.ymodel) A.ymodel[(size_t)w * nd + i] = ym;
+        const double fl = A.flags[i], yi = A.y[i];
+        if (fl == 0.0) {
+            double e = A.yerr[i];
+            if ((i == m1 || i == m2) && ym < yi) e = A.yerr1[i];                 // fit_emcee.py:132-135
+            const double sigma2 = e * e + jit;
+            det += (yi - ym) * (yi - ym) / sigma2 + log(sigma2);
+        } else if (fl == 1.0) {
+            const double temp = erf((yi - ym) / (sqrt(2.0) * rms));
+            lim += log(sqrt(M_PI / 2.) * rms * (1. + temp));
+        }
+    }
+    det = warp_sum(det);
+    lim = warp_sum(lim);
+    if (lane == 0) A.logl[w] = -0.5 * det + 1. * lim;
+}
+
 // FP64 FMA throughput probe: 8 independent chains per thread
 __global__ void __launch_bounds__(256) fp64_probe_kernel(double* out, int iters, double seed) {
     double a0 = seed, a1 = seed + 1, a2 = seed + 2, a3 = seed + 3, a4 = seed + 4, a5 = seed + 5, a6 = seed + 6, a7 = seed + 7;
@@ -549,6 +602,24 @@ int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const
     if (W < 1 || n < 1 || !b || !c || !d || !x) return LHM_ERR_ARG;
     if ((size_t)n * 2 * sizeof(double) > 48 * 1024) return LHM_ERR_CAPACITY;
     bidiag_kernel<<<W, 128, (size_t)n * 2 * sizeof(double), (cudaStream_t)stream>>>(n, b, c, d, x);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_loglike_batch(int W, int Nt, const double* nu_tot, const double* nuLnu, const double* doppler,
+                      const double* log_f, double log10_1pz, double distance_norm, int nd, const double* x,
+                      const double* y, const double* yerr_hi, const double* yerr_lo, const double* flags,
+                      double* logl_out, double* ymodel_out, void* stream) {
+    if (W < 1 || Nt < 2 || nd < 1 || !nu_tot || !nuLnu || !doppler || !log_f || !x || !y || !yerr_hi || !yerr_lo ||
+        !flags || !logl_out) return LHM_ERR_ARG;
+    const size_t smem = (size_t)LL_WARPS * 2 * Nt * sizeof(double);
+    if (smem > 48 * 1024) return LHM_ERR_CAPACITY;
+    LoglikeArgs A;
+    A.W = W; A.Nt = Nt; A.nd = nd; A.nu_tot = nu_tot; A.sed = nuLnu; A.doppler = doppler; A.log_f = log_f;
+    A.log1pz = log10_1pz; A.dist_norm = distance_norm; A.x = x; A.y = y; A.yerr = yerr_hi; A.yerr1 = yerr_lo;
+    A.flags = flags; A.logl = logl_out; A.ymodel = ymodel_out;
+    loglike_kernel<<<(W + LL_WARPS - 1) / LL_WARPS, LL_WARPS * 32, smem, (cudaStream_t)stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return LHM_OK;

@@ -16,8 +16,11 @@ Parity pinning: `oracle/make_golden.py` runs the unmodified reference from /root
 container only) and stores its per-step state in `tests/golden/*.npz`;
 `tests/test_oracle_vs_golden.py` checks this restatement against those vectors and against the
 reference's own shipped outputs (`LeMoC/*_Distribution_Test1_LeMoC.txt`, which pin only ~1e-3).
-The likelihood has no reference-owned fixture: **parity unpinned** for `log_likelihood` beyond
-our own restatement.
+The reference ships no fixture or test for the likelihood; it is pinned with the reference's OWN
+definitions instead: `oracle/make_golden_fit.py` exec's `read_data`, `Model`, `log_likelihood_LeMoC`,
+`log_prior_LeMoC`, `log_probability` unmodified out of `Fit_emcee/fit_emcee.py` (the module itself
+cannot be imported: it runs the MCMC at import) on the reference's data files and stores the results
+in `tests/golden/fit_loglike.npz`; `tests/test_fit.py` checks this restatement against them.
 
 Two evaluation styles are provided for the two expensive functions:
   * `literal=True`  -- the same Python-loop structure as the reference (one call per frequency,

@@ -1,0 +1,139 @@
+"""Fit layer: observation transform, likelihood, priors, sampler.
+
+The golden vectors in tests/golden/fit_loglike.npz were produced by the reference's OWN definitions of
+read_data / Model / log_likelihood_LeMoC / log_prior_LeMoC / log_probability (oracle/make_golden_fit.py exec's
+them unmodified from Fit_emcee/fit_emcee.py) on the reference's data files and the reference's Code.LeMoC spectra.
+"""
+import os
+
+import numpy as np
+import pytest
+
+import lehamoc_oracle as orc
+from util import GOLD, load_golden
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(GOLD, "fit_loglike.npz"))
+
+
+# ---- CPU: the oracle restatement against the reference's own functions ---------------------------------------
+def test_oracle_likelihood_matches_reference(gold):
+    cf, P = load_golden("code_fit")
+    m = orc.Model(lambda th, f: None, D=float(gold["D_Mpc"]), z=float(gold["z"]))
+    assert m.distance_norm == float(gold["distance_norm"])
+    for k, th in enumerate(gold["theta8"]):
+        ym = m.transform(gold["xd"], cf["nu_tot"][k], cf["nuLnu"][k], th[6])
+        np.testing.assert_allclose(ym, gold["ymodel"][k], rtol=1e-14, atol=0)
+        ll = orc.log_likelihood_from_model(ym, th[7], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"])
+        assert abs(ll - gold["loglike"][k]) <= 1e-12 * abs(gold["loglike"][k])
+        assert orc.log_prior_LeMoC(th) == gold["logprior"][k]
+
+
+def test_host_prior_and_reader(gold, tmp_path):
+    from lehamoc_b200 import fit
+    np.testing.assert_array_equal(fit.log_prior_batch(gold["theta8"]), gold["logprior"])
+    bad = gold["theta8"].copy()
+    bad[0, 0] = 13.0; bad[1, 7] = 1.5; bad[2, 5] = 3.0          # outside / on the open boundary
+    assert np.all(np.isneginf(fit.log_prior_batch(bad)[:3]))
+    assert fit.log_prior_LeMoC(list(gold["theta8"][0])) == 0.0
+    # reader: same file format as the reference's two data files (4 columns each)
+    f1, f2 = tmp_path / "mw.txt", tmp_path / "fermi.txt"
+    f1.write_text("10.5 0.1 -12.3 0.05\n14.2 0.1 -11.9 0.07\n")
+    f2.write_text("1e23 2.0e-6 5.0e-7 0\n1e24 1.0e-6 9.9e-7 1\n")
+    x, y, hi, lo, fl = fit.read_data(str(f1), str(f2))
+    xo, yo, hio, loo, flo = orc.read_data(str(f1), str(f2))
+    for a, b in zip((x, y, hi, lo, fl), (xo, yo, hio, loo, flo)):
+        np.testing.assert_array_equal(a, b)
+    assert list(fl) == [0., 0., 0., 1.]
+
+
+def test_sampler_recovers_gaussian():
+    """Stretch move on a 3-d Gaussian with a NumPy log-prob: mean and variance come out right, calls are batched."""
+    from lehamoc_b200 import fit
+    mu, sig = np.array([1.0, -2.0, 0.5]), np.array([0.5, 2.0, 1.0])
+    calls = []
+
+    def logp(th):
+        calls.append(th.shape)
+        return -0.5 * np.sum(((th - mu) / sig) ** 2, axis=1)
+    rng = np.random.default_rng(1)
+    pos = mu + 0.1 * rng.standard_normal((32, 3))
+    res = fit.run_mcmc(logp, pos, 1500, seed=3)
+    flat = res["chain"][500:].reshape(-1, 3)
+    assert np.all(np.abs(flat.mean(axis=0) - mu) < 0.15 * sig)
+    assert np.all(np.abs(flat.std(axis=0) / sig - 1.0) < 0.15)
+    assert calls[0] == (32, 3) and all(c == (16, 3) for c in calls[1:])
+    assert 0.2 < res["acceptance_fraction"].mean() < 0.9
+    res2 = fit.run_mcmc(logp, pos, 50, seed=3)
+    np.testing.assert_array_equal(res2["chain"], res["chain"][:50])      # reproducible from the seed
+    with pytest.raises(ValueError):
+        fit.run_mcmc(logp, pos[:5], 10)
+
+
+# ---- GPU: the CUDA epilogue against the reference's numbers --------------------------------------------------
+@pytest.mark.gpu
+def test_gpu_loglike_matches_reference(gold):
+    from lehamoc_b200 import fit
+    _, P = load_golden("code_fit")
+    ev = fit.FitEvaluator(gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"], param_file=P,
+                          D=float(gold["D_Mpc"]), z=float(gold["z"]))
+    logl, ym = ev.model_and_loglike(gold["theta8"], want_model=True)
+    logl, ym = logl.cpu().numpy(), ym.cpu().numpy()
+    # y_model is log10 of the spectrum: 1e-8 relative on the spectrum <=> 4.3e-9 absolute here
+    assert np.max(np.abs(ym - gold["ymodel"])) <= 4.3e-9
+    # chi^2 amplifies a model shift dy by (y-ym)/sigma^2 ~ up to 1e5 here: compare at the propagated tolerance
+    np.testing.assert_allclose(logl, gold["loglike"], rtol=1e-6)
+    lp = ev.log_probability(gold["theta8"])
+    np.testing.assert_allclose(lp, gold["logprob"], rtol=1e-6)
+    bad = gold["theta8"].copy()
+    bad[3, 0] = 17.5
+    lpb = ev.log_probability(bad)
+    assert lpb[3] == -np.inf and np.allclose(np.delete(lpb, 3), np.delete(lp, 3), rtol=0, atol=0)
+    # single-call surface of the reference
+    m = fit.Model(float(gold["D_Mpc"]), float(gold["z"]), param_file=P)
+    y1 = m(gold["xd"], list(gold["theta8"][0, :7]))
+    np.testing.assert_array_equal(y1, ym[0])
+    ll0 = fit.log_likelihood_LeMoC(list(gold["theta8"][0]), gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"],
+                                   gold["flags"], param_file=P)
+    assert ll0 == logl[0]
+
+
+@pytest.mark.gpu
+def test_gpu_loglike_epilogue_alone(gold):
+    """lhm_loglike_batch on the REFERENCE's spectra (isolates the epilogue from the time integration)."""
+    import ctypes as C
+    import torch
+    from lehamoc_b200 import _lib
+    from lehamoc_b200._lib import check
+    cf, _ = load_golden("code_fit")
+    lib = _lib.load()
+    dev = "cuda:0"
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
+    W, Nt, nd = len(gold["theta8"]), cf["nu_tot"].shape[1], len(gold["xd"])
+    args = [t(cf["nu_tot"]), t(cf["nuLnu"]), t(gold["theta8"][:, 6]), t(gold["theta8"][:, 7])]
+    data = [t(gold[k]) for k in ("xd", "yd", "yerr_hi", "yerr_lo", "flags")]
+    logl = torch.empty(W, dtype=torch.float64, device=dev)
+    ym = torch.empty((W, nd), dtype=torch.float64, device=dev)
+    p = lambda x: C.c_void_p(x.data_ptr())
+    check(lib.lhm_loglike_batch(W, Nt, *[p(a) for a in args], float(np.log10(1. + gold["z"])),
+                                float(gold["distance_norm"]), nd, *[p(a) for a in data], p(logl), p(ym),
+                                C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lhm_loglike_batch")
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(ym.cpu().numpy(), gold["ymodel"], rtol=1e-14, atol=1e-13)
+    np.testing.assert_allclose(logl.cpu().numpy(), gold["loglike"], rtol=1e-11)
+
+
+@pytest.mark.gpu
+def test_gpu_mcmc_smoke(gold):
+    """A short ensemble run end to end on the GPU: 16 walkers x 8 dims, 3 iterations, finite log-probs."""
+    from lehamoc_b200 import fit
+    _, P = load_golden("code_fit")
+    rng = np.random.default_rng(0)
+    init = np.array([*gold["theta8"][0, :7], -2.0])
+    pos = init + 1e-2 * rng.standard_normal((16, 8))
+    fn = lambda th: fit.log_probability_batch(th, gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"],
+                                              gold["flags"], "LeMoC", param_file=P)
+    res = fit.run_mcmc(fn, pos, 3, seed=1)
+    assert res["chain"].shape == (3, 16, 8) and np.all(np.isfinite(res["log_prob"]))
