@@ -460,7 +460,8 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
         const double eps = ovalid ? S.epsS[o] : 0.0;
         const double nuo = ovalid ? S.nuoS[o] : 0.0;
         const double lnu4 = ovalid ? S.lnu4S[o] : 0.0;
-        double a1[IC_PT], a2[IC_PT], a3[IC_PT], G1[IC_PT], acc[IC_PT], wa[IC_PT];
+        double a1[IC_PT], a2[IC_PT], a3[IC_PT], G1[IC_PT], acc[IC_PT];
+        int jw[IC_PT];                                   // gamma index whose weight multiplies acc (-1: inactive pair)
 #pragma unroll
         for (int r = 0; r < IC_PT; ++r) {
             const int j = gb * IC_GB + r * IC_GL + gsub;
@@ -476,7 +477,7 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             a2[r] = act ? -Av : 0.0;
             a3[r] = act ? -2.0 * Av * Av : 0.0;
             G1[r] = act ? 1.0 + Gv : 0.0;
-            wa[r] = act ? S.av[jj] : 0.0;
+            jw[r] = act ? jj : -1;
             acc[r] = 0.0;
         }
         // [i0, i1): some pair of the tile may still have q >= 1, i.e. F <= 0 -> clamp
@@ -492,7 +493,7 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             }
         }
         // [i1, Ntar): q < 1 for every active pair of the tile, so F > 0 and the clamp is the identity
-#pragma unroll 2
+#pragma unroll 4
         for (int i = i1; i < Ntar; ++i) {
             const double2 u = tri2[2 * i];
             const double2 v = tri2[2 * i + 1];
@@ -505,7 +506,7 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < IC_PT; ++r) run = fma(wa[r], acc[r], run);
+        for (int r = 0; r < IC_PT; ++r) run = fma((jw[r] >= 0) ? S.av[jw[r]] : 0.0, acc[r], run);
     }
     if (cur_og >= 0) {
         run += __shfl_xor_sync(0xffffffffu, run, 1);
