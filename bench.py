@@ -366,14 +366,16 @@ def main():
                       and np.all(batch.nu_ic == batch.nu_ic[0]))
         ws = [0] if shared else list(range(0, W, max(1, W // 8)))
         sched = np.array([ic_tile_schedule(batch, w) for w in ws], dtype=np.float64).mean(axis=0)
-        inst_step = sched[1] * 128 * 4 + sched[0] * 128 * 45
+        pre = 0 if batch.cfg.get("ic_pair_table") else 45      # reciprocal + log per pair unless tabulated at set-up
+        inst_step = sched[1] * 128 * 4 + sched[0] * 128 * pre
         inst_launch = inst_step * float(batch.nsteps.sum())
         pipe = {"ic_tiles_per_step": sched[0], "ic_tile_iterations_per_step": sched[1],
                 "ic_clamped_iterations_per_step": sched[2],
                 "executed_fp64_inst_per_launch": inst_launch,
                 "fp64_pipe_frac": 2.0 * inst_launch / (run_ms * 1e-3) / 1e12 / peak_tf,
-                "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element + ~45 per pair "
-                        "preamble, inactive lanes of a tile included; compare with ncu sm__pipe_fp64_cycles_active"}
+                "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element (+ ~45 per pair when "
+                        "the pair constants are not tabulated), inactive lanes of a tile included; compare with "
+                        "ncu sm__pipe_fp64_cycles_active"}
     roofline = {"bound": "fp64", "kernel": "lhm::run_kernel (fused timestep loop, one CTA per walker)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
                 "executed": pipe,

@@ -52,6 +52,11 @@ typedef struct {
     int ic_path;            /* LHM_IC_PATH_R or LHM_IC_PATH_S */
     int const_B;            /* 1: B(t) == B0 for every walker (m == 0 or Vexp == 0, LeMoC.py:200): the synchrotron
                                exponentials are tabulated once per walker instead of every step */
+    int ic_pair_table;      /* 1: the four per-(nu_out, gamma) constants of the IC kernel are tabulated at set-up (32 B per
+                               pair, read once per timestep) instead of recomputed (a reciprocal and a log per pair) */
+    int shared_ic_grids;    /* 1: the caller guarantees that all walkers of every batch have identical g_el, nu_ic and
+                               nu_tot rows (fixed-grid parameter sweeps): one pair table for the whole batch.  Checked
+                               by the *_host entry points; needs ic_pair_table */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 

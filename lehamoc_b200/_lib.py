@@ -24,7 +24,8 @@ class lhm_config(C.Structure):
     _fields_ = [(n, C.c_int) for n in (
         "Ng", "Ns", "Ni", "Nt",
         "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag", "SSA_l_flag",
-        "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "max_walkers")]
+        "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "ic_pair_table",
+        "shared_ic_grids", "max_walkers")]
 
 
 # every symbol include/lhm.h declares: (restype, argtypes)

@@ -10,8 +10,8 @@
 
 #include "../../include/lhm.h"
 #include "lhm_device.cuh"
-#include "lhm_setup.cuh"
 #include "lhm_step.cuh"
+#include "lhm_setup.cuh"
 #include "lhm_cor.cuh"
 
 namespace lhm {
@@ -31,17 +31,21 @@ struct RunArgs {
     const int* tabi;
     const double* cor;      // [W] cor_factor_syn_el
     const double* Ecache;   // [W,(Ns+Ni)*Ng] or null
+    const double2* ptab;    // IC pair table or null
+    int ptab_shared;
     double* N_out;          // [W,(S),Ng] or null
     double* sed_out;        // [W,(S),Nt] or null
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
 
 __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlags& F, const double* consts,
-                                         const double* tabd, const int* tabi, const double* Ecache, int w) {
+                                         const double* tabd, const int* tabi, const double* Ecache,
+                                         const double2* ptab, int ptab_shared, int w) {
     C.L = L; C.F = F;
     C.T = tabd + (size_t)w * L.n_doubles;
     C.TI = tabi + (size_t)w * L.n_ints;
     C.E = Ecache ? Ecache + (size_t)w * (L.Ns + L.Ni) * L.Ng : nullptr;
+    C.P = ptab ? ptab + (ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)) : nullptr;
     const double* c = consts + (size_t)w * LHM_NCONST;
     C.R0 = c[LHM_C_R0]; C.B0 = c[LHM_C_B0]; C.m = c[LHM_C_M]; C.Vexp = c[LHM_C_VEXP];
     C.dt = c[LHM_C_DT]; C.tinit = c[LHM_C_TINIT];
@@ -58,7 +62,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
     Smem S;
     carve(S, smem_raw, A.L, NW);
     Ctx C;
-    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, w);
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -144,6 +148,8 @@ struct UnitArgs {
     const double* tabd;
     const int* tabi;
     const double* Ecache;
+    const double2* ptab;
+    int ptab_shared;
     const double *in0, *in1, *in2;
     double *out0, *out1, *out2;
     int mode;
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(NT, 2) unit_kernel(UnitArgs A) {
     Smem S;
     carve(S, smem_raw, A.L, NW);
     Ctx C;
-    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, w);
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     ic_prepare<NT>(C, S);
@@ -215,7 +221,7 @@ __global__ void __launch_bounds__(NT, 2) unit_kernel(UnitArgs A) {
     case U_GG: {            // in0 n [W,Nt], in1 photons_IC density [W,Ni] (qee_from_ic) -> out0 a_gg [W,Ni], out1 Q_ee [W,Ng-1]
         for (int k = tid; k < Nt; k += NT) {
             double nk = A.in0[(size_t)w * Nt + k];
-            S.Ln[k] = log10(nk); S.Lm[k] = log10(nk * kPC.mc2_h);
+            S.Ln[k] = log10(nk); S.Lm[k] = log2(nk * kPC.mc2_h);
         }
         const double* Lng = S.Ln;
         if (C.F.qee_from_ic) {
@@ -339,6 +345,7 @@ struct lhm_handle {
     int* d_tabi;
     double* d_cor;
     double* d_E;              // const-B exponential cache (cfg.const_B)
+    double2* d_ptab;          // IC pair table (cfg.ic_pair_table)
     const double* consts;     // device pointers of the current batch (caller- or staging-owned)
     const double* g_el;
     // staging for the *_host entry points
@@ -394,6 +401,7 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     if (!cfg || !out) return LHM_ERR_ARG;
     if (cfg->Ng < 4 || cfg->Ns < 3 || cfg->Ni < 3 || cfg->Nt < 4 || cfg->gg_npts < 3 || cfg->max_walkers < 1) return LHM_ERR_ARG;
     if (cfg->Ni > 2040 || cfg->Ng > 4080) return LHM_ERR_ARG;             // IC task encoding (8+8 bits)
+    if (cfg->shared_ic_grids && !cfg->ic_pair_table) return LHM_ERR_ARG;
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0 || device >= ndev) return LHM_ERR_NO_DEVICE;
     cudaDeviceProp prop;
@@ -424,6 +432,10 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
     if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
         CUDA_TRY(cudaMalloc(&h->d_E, W * (size_t)(cfg->Ns + cfg->Ni) * cfg->Ng * sizeof(double)));
+    if (cfg->ic_pair_table && cfg->IC_emis_flag) {
+        const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);
+        CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));
+    }
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     *out = h;
     return LHM_OK;
@@ -432,7 +444,7 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
 void lhm_destroy(lhm_handle* h) {
     if (!h) return;
     cudaSetDevice(h->device);
-    cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E);
+    cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E); cudaFree(h->d_ptab);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     delete h;
@@ -453,6 +465,7 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     A.L = h->L; A.W = W; A.loss_minus_one = h->cfg.loss_minus_one; A.qee_from_ic = h->cfg.qee_from_ic;
     A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
     A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
+    A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
@@ -491,6 +504,7 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
     A.Ecache = h->d_E;
+    A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
@@ -527,6 +541,12 @@ int lhm_run_batch_host(lhm_handle* h, int W, const double* consts, const double*
     if (W > h->cfg.max_walkers) return LHM_ERR_CAPACITY;
     CUDA_TRY(cudaSetDevice(h->device));
     const lhm_config& c = h->cfg;
+    if (c.shared_ic_grids) {                                   // the contract of lhm_config::shared_ic_grids
+        for (int w = 1; w < W; ++w)
+            if (std::memcmp(g_el, g_el + (size_t)w * c.Ng, c.Ng * sizeof(double)) ||
+                std::memcmp(nu_ic, nu_ic + (size_t)w * c.Ni, c.Ni * sizeof(double)) ||
+                std::memcmp(nu_tot, nu_tot + (size_t)w * c.Nt, c.Nt * sizeof(double))) return LHM_ERR_ARG;
+    }
     const size_t Wm = c.max_walkers;
     const size_t per = (size_t)LHM_NCONST + 2 * c.Ng + c.Ns + c.Ni + 2 * c.Nt;
     if (!h->d_in) CUDA_TRY(cudaMalloc(&h->d_in, Wm * per * sizeof(double)));
@@ -568,6 +588,7 @@ static int launch_unit(lhm_handle* h, int mode, const double* in0, const double*
     UnitArgs A;
     A.L = h->L; A.F = h->F; A.W = h->W; A.consts = h->consts; A.tabd = h->d_tabd; A.tabi = h->d_tabi;
     A.Ecache = nullptr;   // function-level calls take B as an argument: always recompute
+    A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     if (ic_path >= 0) A.F.ic_path = ic_path;
     A.in0 = in0; A.in1 = in1; A.in2 = in2; A.out0 = out0; A.out1 = out1; A.out2 = out2; A.mode = mode;
     unit_kernel<<<h->W, NT, h->smem, h->stream>>>(A);

@@ -27,6 +27,14 @@ __constant__ PhysConst kPC;
 
 #define LHM_SENT 1e-260   // 10**(-260.)  LeMoC.py:174-183
 
+// ---- IC tiling: a warp task covers IC_OG outgoing frequencies x IC_GB gammas; a thread owns 1 frequency x IC_PT
+//      gammas (lane>>2 = frequency, lane&3 = gamma lane) -------------------------------------------------------
+constexpr int IC_OG = 8;
+constexpr int IC_GL = 4;
+constexpr int IC_PT = 4;
+constexpr int IC_GB = IC_GL * IC_PT;   // 16 gammas per task
+constexpr int IC_NW = 8;               // warps of the walker CTA the static tile schedule is built for
+
 // ---- per-walker table layout (offsets in doubles / ints from the walker's base) ------------------
 struct Layout {
     int Ng, Ns, Ni, Nt, NP;
@@ -37,13 +45,20 @@ struct Layout {
     int nt, lt, lxt, xt, wt, invnt, l2nt, hnu2, ext, ps_dx, ps_Dx, pi_dx, pi_Dx;           // Nt each
     int agg_a, agg_d;               // Ni: first abscissa / step (log10) of the a_gg resample grid
     int qee_a, qee_d;               // Ng: same for Q_ee_f
-    int aggK, qeeK;                 // Ni*NP, Ng*NP static kernel factors
+    int agg_c, agg_r2;              // Ni: 0.652 sigmaT/x_IC and 10**(-2 step): the sample kernel is rebuilt from these
+    int qee_c, qee_r2;              // Ng: 2.61/(2 gamma) and 10**(-2 step)
     int n_doubles;
     // int tables
     int ps_j, pi_j;                 // Nt
     int u_idx, u_j, q_j;            // Ng
     int jm_syn;                     // Ns
     int jz;                         // Ns+Ni: first gamma index whose exp(-nu/nu_c) is non-zero (const-B cache)
+    // IC tile schedule (lhm_setup.cuh: ic_build_schedule)
+    int ic_maxT;                    // number of candidate tiles = ceil((Ni-1)/IC_OG) * ceil(Ng/IC_GB)
+    int ic_nt;                      // 1: number of active tiles
+    int ic_task, ic_i0, ic_i1;      // ic_maxT each: (og << 16) | gb, first visited / first unclamped target index
+    int ic_tb;                      // IC_NW+1: tile range of every warp
+    int ic_cand;                    // 2*ic_maxT scratch
 
     int n_ints;
 };
@@ -65,11 +80,14 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
     L.invnt = take(Nt); L.l2nt = take(Nt); L.hnu2 = take(Nt); L.ext = take(Nt); L.ps_dx = take(Nt);
     L.ps_Dx = take(Nt); L.pi_dx = take(Nt); L.pi_Dx = take(Nt);
     L.agg_a = take(Ni); L.agg_d = take(Ni); L.qee_a = take(Ng); L.qee_d = take(Ng);
-    L.aggK = take(Ni * NP); L.qeeK = take(Ng * NP);
+    L.agg_c = take(Ni); L.agg_r2 = take(Ni); L.qee_c = take(Ng); L.qee_r2 = take(Ng);
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
     L.jm_syn = take(Ns); L.jz = take(Ns + Ni);
+    L.ic_maxT = ((Ni - 1 + IC_OG - 1) / IC_OG) * ((Ng + IC_GB - 1) / IC_GB);
+    L.ic_nt = take(2); L.ic_task = take(L.ic_maxT); L.ic_i0 = take(L.ic_maxT); L.ic_i1 = take(L.ic_maxT);
+    L.ic_tb = take(IC_NW + 1); L.ic_cand = take(2 * L.ic_maxT);
     L.n_ints = o;
     return L;
 }

@@ -3,6 +3,7 @@
 // stencils, the gamma-gamma sample kernels.  Built once per batch, read by every timestep.
 #pragma once
 #include "lhm_device.cuh"
+#include "lhm_step.cuh"
 #include "../../include/lhm.h"
 
 namespace lhm {
@@ -22,6 +23,8 @@ struct SetupArgs {
     double* tabd;           // [W, L.n_doubles]
     double* Ecache;         // [W, (Ns+Ni)*Ng] or null: exp(-nu/nu_c) table for time-constant B
     int* tabi;              // [W, L.n_ints]
+    double2* ptab;          // IC pair table [W or 1, ic_maxT*IC_PT*2*32] or null
+    int ptab_shared;        // 1: every walker has the same g_el / nu_ic / nu_tot, one table (walker 0 builds it)
 };
 
 // log-spaced resample grid of a_gg / Q_ee_f: np.logspace(a, b, NP)[s] = 10**(a + s*step), last = 10**b
@@ -186,45 +189,124 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             E[(size_t)j * (Ns + Ni) + row] = (x > 745.2) ? 0.0 : exp(-x);   // transposed: [gamma][row]
         }
     }
-    // ---- gamma-gamma sample tables ---------------------------------------------------------------
+    // ---- IC tile schedule (LeHaMoC_f.py:113-124; see phase_ic_R) ----------------------------------------
+    // A task is a tile of IC_OG outgoing frequencies x IC_GB gammas.  Everything that decides which tiles matter is a
+    // function of the grids only: a pair is active iff gamma > eps_o (the reference's `q_IC[0] > 0.` test,
+    // LeHaMoC_f.py:117), and within a pair F <= 0 (clamped to 0 by LeHaMoC_f.py:121) for every target frequency
+    // nu_i <= A = nu_o/(4 gamma (gamma-eps_o)), because F > 0 <=> q = A/nu_i < 1.  So per tile the smallest A over
+    // its active pairs gives the first target index i0 the tile has to visit (one guard element kept), the largest A
+    // the index i1 from which no pair clamps any more, and the tile costs (Ntar - i0) inner iterations.  Tiles are
+    // dealt to the warps as contiguous, cost-balanced ranges -- a static schedule, so the summation order (and the
+    // result bits) do not depend on timing.
+    {
+        const int No = Ni - 1, Ntar = Nt - 1;             // outgoing nu_ic[0..Ni-2], targets nu_tot[0..Nt-2]
+        const int nog = (No + IC_OG - 1) / IC_OG, ngb = (Ng + IC_GB - 1) / IC_GB;
+        const double* xi = T + L.invnt;
+        for (int c = tid; c < nog * ngb; c += NT) {
+            const int og = c / ngb, gb = c - og * ngb;
+            double Amax = -1.0, Amin = 1e308;
+            for (int oo = 0; oo < IC_OG; ++oo) {
+                const int o = og * IC_OG + oo;
+                if (o >= No) break;
+                const double eps = T[L.eps + o], nuo = ni[o];
+                for (int jj = 0; jj < IC_GB; ++jj) {
+                    const int j = gb * IC_GB + jj;
+                    if (j >= Ng) break;
+                    if (g[j] > eps) {
+                        const double rr = 1.0 / (g[j] - eps);
+                        const double Av = nuo * rr * T[L.inv4g + j];
+                        Amax = fmax(Amax, Av);
+                        Amin = fmin(Amin, Av);
+                    }
+                }
+            }
+            int i0 = -1, i1 = -1;
+            if (Amax >= 0.0) {
+                int is = 0;
+                while (is < Ntar && Amin * xi[is] >= 1.0) ++is;     // nu_i <= Amin: q >= 1, F <= 0 for EVERY pair
+                i0 = max(is - 1, 0);                                // (one guard element kept)
+                while (is < Ntar && Amax * xi[is] >= 1.0) ++is;     // first i with q < 1 for every pair of the tile
+                i1 = min(is + 1, Ntar);                             // one guard element: beyond, q <= nu_i/nu_{i+1} < 1
+            }
+            TI[L.ic_cand + 2 * c] = i0;
+            TI[L.ic_cand + 2 * c + 1] = i1;
+        }
+        __syncthreads();
+        if (tid == 0) {
+            int nt = 0;
+            long long tot = 0;
+            const int FIXED = A.ptab ? 2 : 12;                 // per-tile preamble in units of inner iterations
+            for (int c = 0; c < nog * ngb; ++c) {
+                const int i0 = TI[L.ic_cand + 2 * c];
+                if (i0 < 0) continue;
+                const int og = c / ngb, gb = c - og * ngb;
+                TI[L.ic_task + nt] = (og << 16) | gb;
+                TI[L.ic_i0 + nt] = i0;
+                TI[L.ic_i1 + nt] = TI[L.ic_cand + 2 * c + 1];
+                tot += (Ntar - i0) + FIXED;
+                ++nt;
+            }
+            TI[L.ic_nt] = nt;
+            // warp w takes the tiles whose cumulative-cost midpoint lies in [w, w+1) * tot / IC_NW
+            int wcur = 0;
+            long long cum = 0;
+            TI[L.ic_tb] = 0;
+            for (int t = 0; t < nt; ++t) {
+                const long long cst = (Ntar - TI[L.ic_i0 + t]) + FIXED;
+                const long long mid2 = 2 * cum + cst;           // 2 x midpoint
+                while (wcur < IC_NW - 1 && mid2 * IC_NW >= 2 * tot * (wcur + 1)) TI[L.ic_tb + (++wcur)] = t;
+                cum += cst;
+            }
+            while (wcur < IC_NW) TI[L.ic_tb + (++wcur)] = nt;
+        }
+        __syncthreads();
+        // per-pair constants {G1, a1}, {a2, a3} in tile order: [tile][pair r][half][lane]
+        if (A.ptab && (!A.ptab_shared || w == 0)) {
+            double2* P = A.ptab + (A.ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32));
+            const int nt = TI[L.ic_nt];
+            for (int e = tid; e < nt * IC_PT * 32; e += NT) {
+                const int t = e / (IC_PT * 32), r = (e >> 5) % IC_PT, lane = e & 31;
+                const int tk = TI[L.ic_task + t];
+                const int o = (tk >> 16) * IC_OG + (lane >> 2);
+                const int j = (tk & 0xffff) * IC_GB + r * IC_GL + (lane & 3);
+                const int oc = min(o, No - 1), jc = min(j, Ng - 1);
+                double G1, a1, a2, a3;
+                ic_pair_constants(o < No && j < Ng, T[L.eps + oc], ni[oc], T[L.lnu4 + oc], g[jc], T[L.inv4g + jc],
+                                  T[L.lg + jc], G1, a1, a2, a3);
+                P[((size_t)t * IC_PT + r) * 64 + lane] = make_double2(G1, a1);
+                P[((size_t)t * IC_PT + r) * 64 + 32 + lane] = make_double2(a2, a3);
+            }
+        }
+    }
+    // ---- gamma-gamma sample grids -----------------------------------------------------------------
+    // a_gg (LeHaMoC_f.py:130-136) resamples the photon field on x' = np.logspace(log10(1.3/x_IC), log10(max(x)), NP)
+    // and integrates 0.652 sigmaT (s^2-1)/s^3 ln(s) x' n(x') over ln x', s = x' x_IC.  With x'_k = 10^(a + k step):
+    //   s_k = 1.3 * 10^(k step),  ln s_k = ln 1.3 + k step ln 10,  (s^2-1)/s^3 * x' = (1 - s^-2)/x_IC,
+    // and the trapezoid weights in ln x' are step*ln10 (half at the ends), so the whole static factor of sample k is
+    //   w_k * (0.652 sigmaT / x_IC) * (1 - s_k^-2) * ln s_k,    s_k^-2 = s_0^-2 * (10^(-2 step))^k
+    // which phase_gg rebuilds in registers from (a, step, c, r2); nothing per sample is tabulated.
+    // Q_ee_f (LeHaMoC_f.py:143-149) is the same with s = 2 gamma x', s_0 = 1 and prefactor 2.61/(2 gamma).
     const double* lxt = T + L.lxt;
     const double xmax_l = lxt[Nt - 1];                           // log10(max(x)) / log10(h nu_tot[-1]/mc2)
-    // a_gg: NP samples per nu_ic (LeHaMoC_f.py:130-136).  K = trapz weight x 0.652 sigmaT (s^2-1)/s^3 ln s x'
-    for (int e = tid; e < Ni * NP; e += NT) {
-        int o = e / NP, s = e - o * NP;
-        double xIC = T[L.eps + o];
-        double a = log10(1.3 / xIC);
-        double K = 0.0;
-        double x0 = logspace_pt(a, xmax_l, 0, NP), x1 = logspace_pt(a, xmax_l, 1, NP);
-        if (x0 < x1) {
-            double xs = logspace_pt(a, xmax_l, s, NP);
-            double lm = (s > 0) ? log(logspace_pt(a, xmax_l, s - 1, NP)) : 0.0;
-            double lc = log(xs);
-            double lp = (s < NP - 1) ? log(logspace_pt(a, xmax_l, s + 1, NP)) : 0.0;
-            double wtr = (((s > 0) ? (lc - lm) : 0.0) + ((s < NP - 1) ? (lp - lc) : 0.0)) * 0.5;
-            double sv = xs * xIC;
-            K = wtr * (pc.gg_pref * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
-        }
-        T[L.aggK + (size_t)s * Ni + o] = K;                   // transposed: [sample][row]
-        if (s == 0) { T[L.agg_a + o] = a; T[L.agg_d + o] = (xmax_l - a) / (double)(NP - 1); }
+    for (int o = tid; o < Ni; o += NT) {
+        const double xIC = T[L.eps + o];
+        const double a = log10(1.3 / xIC);
+        const double step = (xmax_l - a) / (double)(NP - 1);
+        // the reference's guard `x_space[0] < x_space[1]`
+        const bool on = logspace_pt(a, xmax_l, 0, NP) < logspace_pt(a, xmax_l, 1, NP);
+        T[L.agg_a + o] = a;
+        T[L.agg_d + o] = on ? step : 0.0;
+        T[L.agg_c + o] = pc.gg_pref / xIC;
+        T[L.agg_r2 + o] = exp10(-2.0 * step);
     }
-    // Q_ee_f: NP samples per gamma (LeHaMoC_f.py:143-149); the 2.61 R_gg kernel and trapz weight folded in K
-    for (int e = tid; e < Ng * NP; e += NT) {
-        int j = e / NP, s = e - j * NP;
-        double gj = g[j];
-        double K = 0.0;
-        double a = log10(1.0 / (2.0 * gj));
-        if (2.0 * gj > 1.0) {
-            double xs = logspace_pt(a, xmax_l, s, NP);
-            double lm = (s > 0) ? log(logspace_pt(a, xmax_l, s - 1, NP)) : 0.0;
-            double lc = log(xs);
-            double lp = (s < NP - 1) ? log(logspace_pt(a, xmax_l, s + 1, NP)) : 0.0;
-            double wtr = (((s > 0) ? (lc - lm) : 0.0) + ((s < NP - 1) ? (lp - lc) : 0.0)) * 0.5;
-            double sv = 2.0 * gj * xs;
-            K = wtr * (2.61 * (sv * sv - 1.0) / (sv * sv * sv) * log(sv) * xs);
-        }
-        T[L.qeeK + (size_t)s * Ng + j] = K;
-        if (s == 0) { T[L.qee_a + j] = a; T[L.qee_d + j] = (xmax_l - a) / (double)(NP - 1); }
+    for (int j = tid; j < Ng; j += NT) {
+        const double gj = g[j];
+        const double a = log10(1.0 / (2.0 * gj));
+        const double step = (xmax_l - a) / (double)(NP - 1);
+        T[L.qee_a + j] = a;
+        T[L.qee_d + j] = (2.0 * gj > 1.0) ? step : 0.0;         // `if (2.*g_e) > 1.` else 0
+        T[L.qee_c + j] = 2.61 / (2.0 * gj);
+        T[L.qee_r2 + j] = exp10(-2.0 * step);
     }
 }
 

@@ -32,23 +32,18 @@ struct Smem {
     double *tri;                                 // [Nt][4] = {1/nu_i, (1/nu_i) 2 ln nu_i, w_i n_i, 1/nu_i^2}
     double *gS, *lgS, *inv4gS, *epsS, *lnu4S, *nuoS;   // IC pair-constant inputs
     double *lxtS;                                // log10(h nu_tot/mc2): abscissae of the gamma-gamma interpolation
+    double *ilxS;                                // 1/(lxtS[j+1]-lxtS[j])
+    double *e2tab;                               // [64] 2^(i/64): table of fast_exp2
     double *sfx;                                 // [4][Nt] suffix sums of IC path S
     double *partial;                             // [NW][NiPad] IC partial sums
     unsigned short* tasks;                       // IC (o-group, gamma-block) task list, active tasks only
     unsigned short* ti0;                         // first target-frequency index a task has to visit
     unsigned short* ti1;                         // first target-frequency index from which no pair of the task clamps
-    unsigned short* cand;                        // scratch of ic_prepare: i0 per candidate task (0xFFFF = inactive)
     int* tbound;                                 // [NW+1] task range of every warp (cost-balanced, static)
 };
 
 __host__ __device__ inline int imax3(int a, int b, int c) { return a > b ? (a > c ? a : c) : (b > c ? b : c); }
 __host__ __device__ inline int pad2(int n) { return (n + 1) & ~1; }
-
-// IC tiling: a warp task covers OG outgoing frequencies x GB gammas; a thread owns 1 frequency x PT gammas
-constexpr int IC_OG = 8;      // lanes>>2
-constexpr int IC_GL = 4;      // gamma lanes (lane & 3)
-constexpr int IC_PT = 4;      // pairs per thread
-constexpr int IC_GB = IC_GL * IC_PT;   // 16 gammas per task
 
 __host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
     int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
@@ -63,7 +58,7 @@ __host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
     d += pad2(Ns) * 2 + pad2(Ni) * 2;                       // Qsyn aS aI QIC
     d += (size_t)Nt * 4;                                    // tri
     d += pad2(Ng) * 3 + pad2(Ni) * 3;                       // gS lgS inv4gS epsS lnu4S nuoS
-    d += pad2(Nt);                                          // lxtS
+    d += pad2(Nt) * 2 + 64;                                 // lxtS ilxS e2tab
     // `partial` (IC path R) and `sfx` (IC path S) alias the scratch block {Lsyn Lic y cum bcom cp dp}, which
     // is dead while the IC phase runs; pad if that block is too small for them
     size_t scratch = pad2(Ns) + pad2(Ni) + 2 * pad2(Nt) + pad2(Ng) + 2 * pad2(Nmax);
@@ -77,7 +72,7 @@ __host__ __device__ inline int ic_max_tasks(const Layout& L) {
     return ((L.Ni + IC_OG - 1) / IC_OG) * ((L.Ng + IC_GB - 1) / IC_GB);
 }
 __host__ __device__ inline size_t smem_bytes(const Layout& L, int NW) {
-    return smem_doubles(L, NW) * sizeof(double) + (size_t)pad2(ic_max_tasks(L)) * sizeof(unsigned short) * 5
+    return smem_doubles(L, NW) * sizeof(double) + (size_t)pad2(ic_max_tasks(L)) * sizeof(unsigned short) * 3
            + (size_t)(NW + 1 + 3) / 4 * 4 * sizeof(int);
 }
 
@@ -93,7 +88,7 @@ __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     S.tri = take(Nt * 4);
     S.gS = take(pad2(Ng)); S.lgS = take(pad2(Ng)); S.inv4gS = take(pad2(Ng));
     S.epsS = take(pad2(Ni)); S.lnu4S = take(pad2(Ni)); S.nuoS = take(pad2(Ni));
-    S.lxtS = take(pad2(Nt));
+    S.lxtS = take(pad2(Nt)); S.ilxS = take(pad2(Nt)); S.e2tab = take(64);
     // scratch block, last: dead during the IC phase, so the IC partial sums / suffix sums live on top of it
     double* scratch0 = p;
     S.Lsyn = take(pad2(Ns)); S.Lic = take(pad2(Ni));
@@ -108,7 +103,6 @@ __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     S.tasks = reinterpret_cast<unsigned short*>(S.tbound + (NW + 1 + 3) / 4 * 4);
     S.ti0 = S.tasks + mt;
     S.ti1 = S.ti0 + mt;
-    S.cand = S.ti1 + mt;                                   // 2 entries per candidate
 }
 
 // Per-walker context: table pointers + scalars of the current step
@@ -117,98 +111,43 @@ struct Ctx {
     const double* T;      // double tables of this walker
     const int* TI;        // int tables of this walker
     const double* E;      // [(Ns+Ni), Ng] exp(-nu/nu_c(gamma,B)) of this walker when B is constant in time, else null
+    const double2* P;     // IC pair table of this walker (ic_fill_pair_table), or null: recompute per step
     StepFlags F;
     double R0, B0, m, Vexp, dt, tinit;
     double Rad, B, V;     // current step
 };
 
 // ---------------------------------------------------------------------------------------------
-// load the static IC inputs and build the IC task list (once per walker).
-//
-// A task is a tile of IC_OG outgoing frequencies x IC_GB gammas.  Everything that decides which tiles matter is a
-// function of the grids only: a pair is active iff gamma > eps_o (the reference's `q_IC[0] > 0.` test,
-// LeHaMoC_f.py:117), and within a pair F <= 0 (clamped to 0 by LeHaMoC_f.py:121) for every target frequency
-// nu_i <= A = nu_o/(4 gamma (gamma-eps_o)), because F > 0 <=> q = A/nu_i < 1.  So per tile the smallest A over its
-// active pairs gives the first target index i0 the tile has to visit (one guard element kept), the largest A the
-// index i1 from which no pair clamps any more, and the tile costs (Ntar - i0) inner iterations.  Tiles are dealt to the warps as contiguous, cost-balanced ranges -- a static
-// schedule, so the summation order (and the result bits) do not depend on timing.
+// load the static IC inputs and the IC tile schedule built at set-up (once per walker)
 template <int NT>
 __device__ void ic_prepare(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
-    const int tid = threadIdx.x, NW = NT / 32;
+    const int tid = threadIdx.x;
+    static_assert(NT / 32 == IC_NW, "the tile schedule is built for IC_NW warps");
     for (int j = tid; j < L.Ng; j += NT) {
         S.gS[j] = C.T[L.g + j]; S.lgS[j] = C.T[L.lg + j]; S.inv4gS[j] = C.T[L.inv4g + j];
     }
     for (int o = tid; o < L.Ni; o += NT) {
         S.epsS[o] = C.T[L.eps + o]; S.lnu4S[o] = C.T[L.lnu4 + o]; S.nuoS[o] = C.T[L.nic + o];
     }
+    for (int i = tid; i < 64; i += NT) S.e2tab[i] = exp2((double)i / 64.0);
     for (int i = tid; i < L.Nt; i += NT) {
         const double x = C.T[L.invnt + i];
         S.lxtS[i] = C.T[L.lxt + i];
+        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.T[L.lxt + i + 1] - C.T[L.lxt + i]) : 0.0;
         S.tri[4 * i + 0] = x;                            // 1/nu_i
         S.tri[4 * i + 1] = x * C.T[L.l2nt + i];          // (1/nu_i) 2 ln nu_i
         S.tri[4 * i + 2] = 0.0;                          // p_i = trapz weight x photons (every step)
         S.tri[4 * i + 3] = x * x;                        // 1/nu_i^2
     }
-    __syncthreads();
-    const int No = L.Ni - 1, Ntar = L.Nt - 1;             // outgoing nu_ic[0..Ni-2], targets nu_tot[0..Nt-2]
-    const int nog = (No + IC_OG - 1) / IC_OG, ngb = (L.Ng + IC_GB - 1) / IC_GB;
-    for (int c = tid; c < nog * ngb; c += NT) {
-        const int og = c / ngb, gb = c - og * ngb;
-        double Amax = -1.0, Amin = 1e308;
-        for (int oo = 0; oo < IC_OG; ++oo) {
-            const int o = og * IC_OG + oo;
-            if (o >= No) break;
-            const double eps = S.epsS[o], nuo = S.nuoS[o];
-            for (int jj = 0; jj < IC_GB; ++jj) {
-                const int j = gb * IC_GB + jj;
-                if (j >= L.Ng) break;
-                if (S.gS[j] > eps) {
-                    const double rr = 1.0 / (S.gS[j] - eps);
-                    const double Av = nuo * rr * S.inv4gS[j];
-                    Amax = fmax(Amax, Av);
-                    Amin = fmin(Amin, Av);
-                }
-            }
-        }
-        unsigned short i0 = 0xFFFF, i1 = 0xFFFF;
-        if (Amax >= 0.0) {
-            int is = 0;
-            while (is < Ntar && Amin * S.tri[4 * is] >= 1.0) ++is;     // nu_i <= Amin: q >= 1, F <= 0 for EVERY pair
-            i0 = (unsigned short)max(is - 1, 0);                       // (one guard element kept)
-            while (is < Ntar && Amax * S.tri[4 * is] >= 1.0) ++is;     // first i with q < 1 for every pair of the tile
-            i1 = (unsigned short)min(is + 1, Ntar);                    // one guard element: beyond, q <= nu_i/nu_{i+1} < 1
-        }
-        S.cand[2 * c] = i0;
-        S.cand[2 * c + 1] = i1;
+    const int nt = C.TI[L.ic_nt];
+    for (int t = tid; t < nt; t += NT) {
+        const int tk = C.TI[L.ic_task + t];
+        S.tasks[t] = (unsigned short)(((tk >> 16) << 8) | (tk & 255));
+        S.ti0[t] = (unsigned short)C.TI[L.ic_i0 + t];
+        S.ti1[t] = (unsigned short)C.TI[L.ic_i1 + t];
     }
-    __syncthreads();
-    if (tid == 0) {
-        int nt = 0;
-        long long tot = 0;
-        constexpr int FIXED = 12;                          // per-tile preamble (reciprocal + log per pair) in iterations
-        for (int c = 0; c < nog * ngb; ++c) {
-            const unsigned short i0 = S.cand[2 * c];
-            if (i0 == 0xFFFF) continue;
-            const int og = c / ngb, gb = c - og * ngb;
-            S.tasks[nt] = (unsigned short)((og << 8) | gb);
-            S.ti0[nt] = i0;
-            S.ti1[nt] = S.cand[2 * c + 1];
-            tot += (Ntar - i0) + FIXED;
-            ++nt;
-        }
-        // warp w takes the tiles whose cumulative-cost midpoint lies in [w, w+1) * tot / NW
-        int wcur = 0;
-        long long cum = 0;
-        S.tbound[0] = 0;
-        for (int t = 0; t < nt; ++t) {
-            const long long cst = (Ntar - S.ti0[t]) + FIXED;
-            const long long mid2 = 2 * cum + cst;           // 2 x midpoint
-            while (wcur < NW - 1 && mid2 * NW >= 2 * tot * (wcur + 1)) S.tbound[++wcur] = t;
-            cum += cst;
-        }
-        while (wcur < NW) S.tbound[++wcur] = nt;
-    }
+    for (int k = tid; k <= IC_NW; k += NT) S.tbound[k] = C.TI[L.ic_tb + k];
     __syncthreads();
 }
 
@@ -231,7 +170,7 @@ __device__ void phase_photons(const Ctx& C, Smem& S, bool aux) {
         S.n[k] = nk;
         if (aux) {
             S.Ln[k] = log10(nk);
-            S.Lm[k] = log10(nk * kPC.mc2_h);
+            S.Lm[k] = log2(nk * kPC.mc2_h);                      // gamma-gamma phases interpolate in log2 (fast_exp2)
             S.y[k] = C.T[L.xt + k] * nk * K;
             S.tri[4 * k + 2] = C.T[L.wt + k] * nk;               // p_i = trapz weight x photons
         }
@@ -425,6 +364,22 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
 // per (o, gamma) pair: one reciprocal + one log; per (o, gamma, nu_i) element: 3 DFMA for F and one DFMA for the
 // accumulation, the latter predicated on the sign bit of F (that is `function_IC[function_IC < 0.] = 0.`,
 // LeHaMoC_f.py:121: an integer compare on the high word instead of a DSETP/DMNMX on the FP64 pipe).
+// the four per-(nu_o, gamma) constants of F; an inactive pair (gamma <= eps_o, LeHaMoC_f.py:117, or padding) gets
+// zeros, i.e. F == 0 for every nu_i
+__device__ __forceinline__ void ic_pair_constants(bool valid, double eps, double nuo, double lnu4, double g, double inv4g,
+                                                  double lg, double& G1, double& a1, double& a2, double& a3) {
+    const bool act = valid && (g > eps);
+    const double d = act ? (g - eps) : 1.0;
+    const double rr = 1.0 / d;
+    const double Gv = 2.0 * eps * eps * rr * inv4g;
+    const double Av = nuo * rr * inv4g;
+    const double c1 = (1.0 - Gv) + 2.0 * (lnu4 - lg - log(d));
+    G1 = act ? 1.0 + Gv : 0.0;
+    a1 = act ? Av * c1 : 0.0;
+    a2 = act ? -Av : 0.0;
+    a3 = act ? -2.0 * Av * Av : 0.0;
+}
+
 __device__ __forceinline__ void ic_acc_if_nonneg(double& acc, double p, double F) {
     asm("{\n\t.reg .pred q;\n\tsetp.ge.s32 q, %1, 0;\n\t@q fma.rn.f64 %0, %2, %3, %0;\n\t}"
         : "+d"(acc) : "r"(__double2hiint(F)), "d"(p), "d"(F));
@@ -455,30 +410,29 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             }
             cur_og = og; run = 0.0;
         }
-        const int o = og * IC_OG + osub;
-        const bool ovalid = o < No;
-        const double eps = ovalid ? S.epsS[o] : 0.0;
-        const double nuo = ovalid ? S.nuoS[o] : 0.0;
-        const double lnu4 = ovalid ? S.lnu4S[o] : 0.0;
         double a1[IC_PT], a2[IC_PT], a3[IC_PT], G1[IC_PT], acc[IC_PT];
-        int jw[IC_PT];                                   // gamma index whose weight multiplies acc (-1: inactive pair)
+        if (C.P) {
+            // per-pair constants from the table built at set-up (tile-major, one coalesced 512-byte line per load)
+            const double2* __restrict__ Pt = C.P + (size_t)t * (IC_PT * 2 * 32) + lane;
 #pragma unroll
-        for (int r = 0; r < IC_PT; ++r) {
-            const int j = gb * IC_GB + r * IC_GL + gsub;
-            const bool act = ovalid && (j < Ng) && (S.gS[min(j, Ng - 1)] > eps);
-            const int jj = act ? j : 0;
-            const double d = act ? (S.gS[jj] - eps) : 1.0;
-            const double rr = 1.0 / d;
-            const double i4 = S.inv4gS[jj];
-            const double Gv = 2.0 * eps * eps * rr * i4;
-            const double Av = nuo * rr * i4;
-            const double c1 = (1.0 - Gv) + 2.0 * (lnu4 - S.lgS[jj] - log(d));
-            a1[r] = act ? Av * c1 : 0.0;
-            a2[r] = act ? -Av : 0.0;
-            a3[r] = act ? -2.0 * Av * Av : 0.0;
-            G1[r] = act ? 1.0 + Gv : 0.0;
-            jw[r] = act ? jj : -1;
-            acc[r] = 0.0;
+            for (int r = 0; r < IC_PT; ++r) {
+                const double2 q01 = __ldg(Pt + (r * 2) * 32), q23 = __ldg(Pt + (r * 2 + 1) * 32);
+                G1[r] = q01.x; a1[r] = q01.y; a2[r] = q23.x; a3[r] = q23.y;
+                acc[r] = 0.0;
+            }
+        } else {
+            const int o = og * IC_OG + osub;
+            const bool ovalid = o < No;
+            const double eps = ovalid ? S.epsS[o] : 0.0;
+            const double nuo = ovalid ? S.nuoS[o] : 0.0;
+            const double lnu4 = ovalid ? S.lnu4S[o] : 0.0;
+#pragma unroll
+            for (int r = 0; r < IC_PT; ++r) {
+                const int j = gb * IC_GB + r * IC_GL + gsub;
+                ic_pair_constants(ovalid && (j < Ng), eps, nuo, lnu4, S.gS[min(j, Ng - 1)], S.inv4gS[min(j, Ng - 1)],
+                                  S.lgS[min(j, Ng - 1)], G1[r], a1[r], a2[r], a3[r]);
+                acc[r] = 0.0;
+            }
         }
         // [i0, i1): some pair of the tile may still have q >= 1, i.e. F <= 0 -> clamp
         for (int i = i0; i < i1; ++i) {
@@ -506,7 +460,8 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
             }
         }
 #pragma unroll
-        for (int r = 0; r < IC_PT; ++r) run = fma((jw[r] >= 0) ? S.av[jw[r]] : 0.0, acc[r], run);
+        for (int r = 0; r < IC_PT; ++r)      // an inactive pair has F == 0 throughout, so acc == 0 whatever the weight
+            run = fma(S.av[min(gb * IC_GB + r * IC_GL + gsub, Ng - 1)], acc[r], run);
     }
     if (cur_og >= 0) {
         run += __shfl_xor_sync(0xffffffffu, run, 1);
@@ -614,55 +569,109 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
     __syncthreads();
 }
 
-// Phase H: a_gg (LeHaMoC_f.py:127-137) and Q_ee_f (LeHaMoC_f.py:140-151), one THREAD per row.
-// The NP resample abscissae of a row are log10-uniform, y_s = a + s*step (np.logspace), and increase with s, so
-// the np.interp bracket on the nu_tot grid only moves forward: it is advanced incrementally against the actual
-// grid doubles (no search, no stencil table).  Only the static factor K[s][row] (trapezoid weight x pair-production
-// kernel x x') is tabulated, transposed so that a warp reads one coalesced line per sample.  Two samples are in
-// flight per thread.  `Lng` gives n_g: log10 of the field Q_ee_f's n_g is interpolated from.
-__device__ __forceinline__ double gg_sample(const double* __restrict__ lxt, const double* __restrict__ Lm, int Nt,
-                                            double y, int& j) {
-    // returns log10 of the interpolated photon density at abscissa y; j is the running bracket (lxt[j] <= y)
-    if (y >= lxt[Nt - 1]) return Lm[Nt - 1];
-    if (y <= lxt[0]) return Lm[0];
-    while (y >= lxt[j + 1]) ++j;
-    const double dx = y - lxt[j];
-    return (dx == 0.0) ? Lm[j] : lerp_log(Lm, j, dx / (lxt[j + 1] - lxt[j]));
+// 2^x for x finite, -inf or NaN (the latter two give 0, which is what 10**np.interp yields for the -inf ordinates
+// of an empty photon bin); x <= ~1000.  x = n/64 + f, |f| <= 1/128: 2^f by a degree-5 polynomial (truncation 4e-17),
+// 2^(n mod 64 / 64) from a 64-entry table, 2^(n div 64) by two exponent-field multiplies (gradual underflow kept).
+__device__ __forceinline__ double fast_exp2(double x, const double* __restrict__ tab) {
+    if (!(x > -1100.0)) x = -1100.0;
+    const double MAGIC = 6755399441055744.0;                      // 2^52 + 2^51: round-to-nearest-integer by addition
+    const double zm = fma(x, 64.0, MAGIC);
+    const int n = __double2loint(zm);
+    const double f = fma(zm - MAGIC, -1.0 / 64.0, x);             // exact
+    const double r = f * 0.693147180559945309417;
+    double p = 1.0 / 120.0;
+    p = fma(p, r, 1.0 / 24.0);
+    p = fma(p, r, 1.0 / 6.0);
+    p = fma(p, r, 0.5);
+    p = fma(p, r, 1.0);
+    p = fma(p, r, 1.0);
+    p *= tab[n & 63];
+    const int k = n >> 6, k1 = k >> 1, k2 = k - k1;
+    p *= __hiloint2double((k1 + 1023) << 20, 0);
+    p *= __hiloint2double((k2 + 1023) << 20, 0);
+    return p;
 }
+
+// Phase H: a_gg (LeHaMoC_f.py:127-137) and Q_ee_f (LeHaMoC_f.py:140-151), one THREAD per row, GG_U samples of the
+// row evaluated side by side and written stage by stage so that GG_U independent dependency chains interleave (a
+// single chain of FP64 operations advances one instruction per ~10 cycles on this pipe).
+// The NP resample abscissae of a row are log10-uniform, y_s = a + s*step (np.logspace), and so is the nu_tot grid
+// they are interpolated on: the np.interp bracket is found arithmetically and then verified against the actual
+// grid doubles.  The static factor of a sample (trapezoid weight x pair-production kernel x x') is rebuilt in
+// registers from four per-row numbers (see lhm_setup.cuh): no table is streamed at all.  S.Lm holds log2 of the
+// photon field (x mc^2/h), so 10**np.interp(log10 ...) becomes fast_exp2 of the same linear interpolant.
+// `Lng` gives n_g: log10 of the field Q_ee_f's n_g is interpolated from.
+constexpr int GG_U = 4;
 
 template <int NT>
 __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_out, double* qee_out) {
     const Layout& L = C.L;
     const int NP = L.NP, Ni = L.Ni, Ng = L.Ng, Nt = L.Nt;
     const int nrows = Ni + (Ng - 1);
-    const double* lxt = S.lxtS;
-    const double lxN = lxt[Nt - 1];
+    const double* __restrict__ lxt = S.lxtS;
+    const double* __restrict__ ilx = S.ilxS;
+    const double* __restrict__ Lm = S.Lm;
+    const double* __restrict__ tab = S.e2tab;
+    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
+    const double invD = (double)(Nt - 1) / (lxN - lx0);
+    const double LN10 = 2.302585092994045684, LN13 = 0.262364264467491052;     // ln 10, ln 1.3
     for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
-        const int stride = is_a ? Ni : Ng;
-        const double* __restrict__ K = C.T + (is_a ? L.aggK : L.qeeK) + r;      // K[s*stride + r]
         const double a = __ldg(C.T + (is_a ? L.agg_a : L.qee_a) + r);
         const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
-        double s0 = 0.0, s1 = 0.0;
+        const double cf = __ldg(C.T + (is_a ? L.agg_c : L.qee_c) + r);
+        const double r2 = __ldg(C.T + (is_a ? L.agg_r2 : L.qee_r2) + r);
+        double acc[GG_U];
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
         if (step > 0.0) {                       // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
-            int j = 0;
-            int e = 0;
-            for (; e + 1 < NP; e += 2) {
-                const double y0 = fma((double)e, step, a);
-                const double y1 = (e + 1 == NP - 1) ? lxN : fma((double)(e + 1), step, a);
-                const double K0 = __ldg(K + (size_t)e * stride), K1 = __ldg(K + (size_t)(e + 1) * stride);
-                const double L0 = gg_sample(lxt, S.Lm, Nt, y0, j);
-                const double L1 = gg_sample(lxt, S.Lm, Nt, y1, j);
-                s0 = fma(K0, exp10(L0), s0);
-                s1 = fma(K1, exp10(L1), s1);
-            }
-            if (e < NP) {
-                const double y0 = (e == NP - 1) ? lxN : fma((double)e, step, a);
-                s0 = fma(__ldg(K + (size_t)e * stride), exp10(gg_sample(lxt, S.Lm, Nt, y0, j)), s0);
+            const double dl = step * LN10;                      // spacing of ln x' = trapezoid weight of inner samples
+            const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
+            double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
+            inv[0] = is_a ? (1.0 / 1.69) : 1.0;
+#pragma unroll
+            for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
+            double rU = r2;
+#pragma unroll
+            for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
+            for (int e0 = 0; e0 < NP; e0 += GG_U) {
+                double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
+                int j[GG_U];
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    const int e = e0 + u;
+                    const double ed = (double)e;
+                    y[u] = (e >= NP - 1) ? lxN : fma(ed, step, a);
+                    const double wgt = (e == 0 || e == NP - 1) ? 0.5 * dl : ((e < NP) ? dl : 0.0);
+                    Kv[u] = wgt * cf * (1.0 - inv[u]) * fma(ed, dl, lns0);
+                    inv[u] *= rU;
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    int jj = (int)((y[u] - lx0) * invD);
+                    jj = max(0, min(jj, Nt - 2));
+                    while (jj > 0 && y[u] < lxt[jj]) --jj;
+                    while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                    j[u] = jj;
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    t[u] = (y[u] - lxt[j[u]]) * ilx[j[u]];
+                    if (y[u] <= lx0) t[u] = 0.0;                // np.interp clamps below the grid
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    const double f0 = Lm[j[u]], f1 = Lm[j[u] + 1];
+                    Lv[u] = fma(t[u], f1 - f0, f0);             // NaN (from -inf ordinates) -> 0 inside fast_exp2
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) acc[u] = fma(Kv[u], fast_exp2(Lv[u], tab), acc[u]);
             }
         }
-        const double s = s0 + s1;
+        double s = acc[0];
+#pragma unroll
+        for (int u = 1; u < GG_U; ++u) s += acc[u];
         if (is_a) agg_out[r] = s;
         else {
             double ng = 0.0;

@@ -90,10 +90,20 @@ class Engine:
             if batch.cfg[k] != self.cfg[k]:
                 raise LhmError(f"batch {k}={batch.cfg[k]} does not match the engine ({self.cfg[k]})")
         W = batch.W
+        self._check_shared(batch)
         dev = [self._dev(a) for a in batch.arrays()]
         self.setup_device(W, *dev)
 
+    def _check_shared(self, batch):
+        if self.cfg.get("shared_ic_grids") and not (np.all(batch.g_el == batch.g_el[0])
+                                                    and np.all(batch.nu_ic == batch.nu_ic[0])
+                                                    and np.all(batch.nu_tot == batch.nu_tot[0])):
+            raise LhmError("this engine was created for batches whose walkers share g_el/nu_ic/nu_tot "
+                           "(cfg.shared_ic_grids); the batch does not")
+
     def setup_device(self, W, consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext):
+        """Device tensors in, tables built on the stream.  With cfg.shared_ic_grids the caller guarantees that every
+        walker has the same g_el / nu_ic / nu_tot rows (not re-checked here: that would need a synchronisation)."""
         self._keep = (consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext)
         check(self.lib.lhm_setup_batch(self.h, int(W), *[_ptr(t) for t in self._keep]), "lhm_setup_batch")
         self.W = int(W)

@@ -189,7 +189,10 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
     cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=50,
                loss_minus_one=1 if variant == "script" else 0,       # LeMoC.py:224 vs Code.py:210
                qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
-               const_B=int(float(F["m"]) == 0. or Vexp == 0.))      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
+               const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
+               ic_pair_table=1,
+               # fixed-grid sweeps (every walker has the same g_el / nu_ic / nu_tot): one IC pair table per batch
+               shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))))
     for k in FLAG_KEYS:
         cfg[k] = _flag01(F, k)
     # gg_flag is tested with `== 0.` (LeMoC.py:279): anything else switches it on; inj_flag is tested both ways

@@ -294,3 +294,32 @@ def test_error_paths():
         eng.setup(b2)                               # over capacity
     with pytest.raises(_lib.LhmError):
         Engine(dict(b.cfg, Ng=2), 1)                # invalid size
+
+
+def test_ic_pair_table_modes_are_bit_identical():
+    """The IC pair table (per walker, or one per batch when the grids are shared) holds exactly what the kernel
+    would recompute: all three modes must give the same bits.  A shared-grid engine refuses a ragged batch."""
+    from lehamoc_b200 import _lib
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    _, P = load_golden("test1")
+    P.update(grid_g_el=90., grid_nu=60., time_end=3.)
+    sets = [dict(P, B0=1.0 + 0.1 * i, p_el=1.8 + 0.02 * i) for i in range(5)]
+    b = pack_script(sets)
+    assert b.cfg["shared_ic_grids"] == 1 and b.cfg["ic_pair_table"] == 1
+    outs = []
+    for cfg in (b.cfg, dict(b.cfg, shared_ic_grids=0), dict(b.cfg, shared_ic_grids=0, ic_pair_table=0)):
+        eng = Engine(cfg, b.W)
+        N, sed = eng.run_host(b)
+        outs.append((N.copy(), sed.copy()))
+        eng.close()
+    for N, sed in outs[1:]:
+        np.testing.assert_array_equal(sed, outs[0][1])
+        np.testing.assert_array_equal(N, outs[0][0])
+    ragged = pack_script([dict(P), dict(P, g_max_el=5.9, g_PL_max=5.5)])
+    assert ragged.cfg["shared_ic_grids"] == 0
+    eng = Engine(dict(ragged.cfg, shared_ic_grids=1), 2)
+    with pytest.raises(_lib.LhmError):
+        eng.run_host(ragged)
+    with pytest.raises(_lib.LhmError):
+        eng.setup(ragged)
