@@ -28,6 +28,45 @@ def run(param_sets, ic_path="R", snapshots=True, engine=None, pinned=False):
     return batch, N, sed
 
 
+def run_many(batches, ic_path="R", engines=None, depth=2):
+    """Evolve a stream of walker batches (an iterable of lists of parameter dicts) and yield
+    (batch, n_e [W,Ng], nuLnu [W,Nt]) per batch in order, final state only.
+
+    This is the throughput path for sweeps and samplers: `depth` worker threads each own an engine on its own CUDA
+    stream and do packing (NumPy) -> pinned H2D -> set-up + cor-factor + fused kernel -> D2H for their batch, so the
+    host work and the copies of one batch overlap the kernels of the other (NumPy and the ctypes call release the
+    GIL).  The yielded spectra are views of that engine's page-locked buffers: they stay valid until `depth` more
+    batches have been drawn; copy them if they must live longer."""
+    from concurrent.futures import ThreadPoolExecutor
+    import torch
+    depth = max(1, int(depth))
+    engines = engines if engines is not None else []        # a caller-owned list is filled in place and can be reused
+    while len(engines) < depth:
+        engines.append(None)
+    streams = [torch.cuda.Stream() for _ in range(depth)]
+
+    def work(slot, sets):
+        batch = pack_script(sets)
+        with torch.cuda.stream(streams[slot]):
+            eng = engines[slot]
+            if eng is None or eng.max_walkers < batch.W or any(eng.cfg.get(k) != v for k, v in batch.cfg.items()):
+                eng = engines[slot] = Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
+            N, sed = eng.run_host(batch, snapshots=0, pinned=True)
+        return batch, N, sed
+
+    it = iter(batches)
+    with ThreadPoolExecutor(max_workers=depth) as pool:
+        window = []
+        k = 0
+        for sets in it:
+            window.append(pool.submit(work, k % depth, sets))
+            k += 1
+            if len(window) == depth:
+                yield window.pop(0).result()
+        while window:
+            yield window.pop(0).result()
+
+
 def write_outputs(batch, N, sed, out_s, w=0):
     """LeMoC.py:290-296: str(float) of log10 values, space separated."""
     out1 = "Particles_Distribution_" + out_s + ".txt"

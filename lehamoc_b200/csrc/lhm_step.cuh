@@ -47,7 +47,7 @@ __host__ __device__ inline int pad2(int n) { return (n + 1) & ~1; }
 
 __host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
     int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
-    int Nmax = imax3(Ng, Ns, Ni);
+    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, 0);
     size_t d = 0;
     d += pad2(Ng) * 2 + pad2(Ns) + pad2(Ni) * 2;            // state
     d += pad2(Ns) + pad2(Ni);                               // logs
@@ -78,7 +78,7 @@ __host__ __device__ inline size_t smem_bytes(const Layout& L, int NW) {
 
 __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
-    int Nmax = imax3(Ng, Ns, Ni);
+    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, 0);
     double* p = base;
     auto take = [&](int n) { double* r = p; p += n; return r; };
     S.N = take(pad2(Ng)); S.qee = take(pad2(Ng)); S.psyn = take(pad2(Ns)); S.pic = take(pad2(Ni)); S.agg = take(pad2(Ni));
@@ -178,6 +178,51 @@ __device__ void phase_photons(const Ctx& C, Smem& S, bool aux) {
     __syncthreads();
 }
 
+// The same back-substitution by one warp: the recurrence x_i = dp_i - cp_i x_{i+1} is an affine map per row, so each
+// lane composes the maps of a contiguous chunk, a 5-level shuffle scan composes the chunks, and each lane then replays
+// its chunk with the reference's own recurrence from the incoming value (rounding differs from the serial order by a
+// few ulp only through that incoming value).  All 32 lanes of the calling warp must take part.
+__device__ __forceinline__ void backsub_warp(const double* __restrict__ cp, const double* __restrict__ dp,
+                                             double* __restrict__ x, int n) {
+    const int lane = threadIdx.x & 31;
+    const int Cn = (n + 31) >> 5;
+    const int s = min(lane * Cn, n), e = min(s + Cn, n);
+    double D = 0.0, M = 1.0;                                   // x_s = D + M * x_e
+    for (int i = e - 1; i >= s; --i) {
+        const double c = (i == n - 1) ? 0.0 : cp[i];           // the last row's c never enters (LeHaMoC_f.py:258)
+        D = fma(-c, D, dp[i]);
+        M = -c * M;
+    }
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double Dn = __shfl_down_sync(0xffffffffu, D, d), Mn = __shfl_down_sync(0xffffffffu, M, d);
+        if (lane + d < 32) { D = fma(M, Dn, D); M *= Mn; }
+    }
+    double xv = __shfl_down_sync(0xffffffffu, D, 1);           // x at the start of the next chunk
+    if (lane == 31) xv = 0.0;
+    for (int i = e - 1; i >= s; --i) {
+        xv = (i == n - 1) ? dp[i] : dp[i] - cp[i] * xv;
+        x[i] = xv;
+    }
+}
+
+// exclusive prefix sum out[m] = sum_{i<m} v[i] by one warp (chunk per lane + shuffle scan); out may not alias v
+__device__ __forceinline__ void exclusive_prefix_warp(const double* __restrict__ v, double* __restrict__ out, int n) {
+    const int lane = threadIdx.x & 31;
+    const int Cn = (n + 31) >> 5;
+    const int s = min(lane * Cn, n), e = min(s + Cn, n);
+    double tot = 0.0;
+    for (int i = s; i < e; ++i) tot += v[i];
+    double incl = tot;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const double t = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += t;
+    }
+    double run = incl - tot;
+    for (int i = s; i < e; ++i) { out[i] = run; run += v[i]; }
+}
+
 // Phase C: U_ph_f (LeHaMoC_f.py:160-172) -> b_Com (LeMoC.py:232)
 template <int NT>
 __device__ void phase_uph(const Ctx& C, Smem& S, double* U_out /*smem or null*/) {
@@ -185,12 +230,10 @@ __device__ void phase_uph(const Ctx& C, Smem& S, double* U_out /*smem or null*/)
     const int tid = threadIdx.x;
     const int Nt = L.Nt;
     // exclusive prefix of the trapezoids of np.trapz(y, x): cum[m] = sum_{i<m} (x[i+1]-x[i])*(y[i+1]+y[i])/2
-    for (int m = tid; m < Nt; m += NT) {
-        double s = 0.0;
-        for (int i = 0; i < m; ++i)
-            s += (C.T[L.xt + i + 1] - C.T[L.xt + i]) * (S.y[i + 1] + S.y[i]) / 2.0;
-        S.cum[m] = s;
-    }
+    for (int m = tid; m < Nt; m += NT)
+        S.dp[m] = (m < Nt - 1) ? (C.T[L.xt + m + 1] - C.T[L.xt + m]) * (S.y[m + 1] + S.y[m]) / 2.0 : 0.0;
+    __syncthreads();
+    if (tid < 32) exclusive_prefix_warp(S.dp, S.cum, Nt);
     __syncthreads();
     const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;
     const double pre = kPC.mc2 / (kPC.sigmaT * C.Rad);
@@ -256,7 +299,7 @@ __device__ void phase_electrons(const Ctx& C, Smem& S) {
         S.dp[j] = d / V2;
     }
     __syncthreads();
-    if (tid == 0) backsub(S.cp, S.dp, S.N + 1, n);
+    if (tid < 32) backsub_warp(S.cp, S.dp, S.N + 1, n);
     __syncthreads();
 }
 
@@ -284,6 +327,46 @@ __device__ void phase_vectors(const Ctx& C, Smem& S) {
         S.v[j] = vj;
     }
     __syncthreads();
+}
+
+// exp(-x) for U values x >= 0 at once, written stage by stage so that the U dependency chains interleave.
+// -x = n ln2/64 + r, |r| <= ln2/128 (two-term Cody-Waite reduction), exp(r) by a degree-5 polynomial, 2^(n mod 64 / 64)
+// from the 64-entry table, 2^(n div 64) by two exponent-field multiplies (gradual underflow kept); ~1e-15 relative.
+// x > 745.2 gives exactly 0, like np.exp(-x) in IEEE double.
+template <int U>
+__device__ __forceinline__ void fast_exp_neg(const double (&x)[U], double (&out)[U], const double* __restrict__ tab) {
+    const double MAGIC = 6755399441055744.0;                      // 2^52 + 2^51
+    const double L2E64 = -92.332482616893658071;                  // -64/ln 2
+    const double LN2_64_HI = 0.01083042469326756, LN2_64_LO = 2.9815858269852933e-12;   // ln2/64 = HI + LO, HI has 21 trailing zero bits (n*HI exact)
+    double zm[U], r[U], p[U];
+    int n[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) zm[u] = fma(x[u], L2E64, MAGIC);
+#pragma unroll
+    for (int u = 0; u < U; ++u) { n[u] = __double2loint(zm[u]); zm[u] -= MAGIC; }
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(zm[u], -LN2_64_HI, -x[u]);      // -x - n ln2/64
+#pragma unroll
+    for (int u = 0; u < U; ++u) r[u] = fma(zm[u], -LN2_64_LO, r[u]);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(1.0 / 120.0, r[u], 1.0 / 24.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0 / 6.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 0.5);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] = fma(p[u], r[u], 1.0);
+#pragma unroll
+    for (int u = 0; u < U; ++u) p[u] *= tab[n[u] & 63];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int k = n[u] >> 6, k1 = k >> 1, k2 = k - k1;
+        p[u] *= __hiloint2double((k1 + 1023) << 20, 0);
+        p[u] *= __hiloint2double((k2 + 1023) << 20, 0);
+        out[u] = (x[u] > 745.2) ? 0.0 : p[u];
+    }
 }
 
 // Phase F1: synchrotron emissivity + SSA, one THREAD per frequency row, serial over gamma with two independent
@@ -329,22 +412,26 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
                 sa0 = fma(E0, S.v[j], sa0);
             }
         } else {
-            int j = 0;
-            for (; j + 1 < Ng; j += 2) {
-                const double x0 = nu * S.inuc[j], x1 = nu * S.inuc[j + 1];
-                // exp(-x) underflows to exactly 0 beyond 745.14 in IEEE double, as in the reference
-                const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
-                const double E1 = (x1 > 745.2) ? 0.0 : exp(-x1);
-                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
-                if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
-                sa0 = fma(E0, S.v[j], sa0);
-                sa1 = fma(E1, S.v[j + 1], sa1);
-            }
-            if (j < Ng) {
-                const double x0 = nu * S.inuc[j];
-                const double E0 = (x0 > 745.2) ? 0.0 : exp(-x0);
-                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
-                sa0 = fma(E0, S.v[j], sa0);
+            // recompute the exponentials: SYN_U gammas side by side, stage by stage (independent chains interleave)
+            constexpr int SYN_U = 4;
+            for (int j0 = 0; j0 < Ng; j0 += SYN_U) {
+                double x[SYN_U], Ev[SYN_U];
+#pragma unroll
+                for (int u = 0; u < SYN_U; ++u) x[u] = nu * S.inuc[min(j0 + u, Ng - 1)];
+                fast_exp_neg<SYN_U>(x, Ev, S.e2tab);
+#pragma unroll
+                for (int u = 0; u < SYN_U; ++u) {
+                    const int j = j0 + u;
+                    if (j < Ng) {
+                        if (u & 1) {
+                            if (j >= jm) sq1 = fma(Ev[u], S.u[j], sq1);
+                            sa1 = fma(Ev[u], S.v[j], sa1);
+                        } else {
+                            if (j >= jm) sq0 = fma(Ev[u], S.u[j], sq0);
+                            sa0 = fma(Ev[u], S.v[j], sa0);
+                        }
+                    }
+                }
             }
         }
         const double sq = sq0 + sq1, sa = sa0 + sa1;
@@ -551,7 +638,7 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
         S.dp[j] = d / V2;
     }
     __syncthreads();
-    if (C.F.ad) { if (tid == 0) backsub(S.cp, S.dp, S.psyn + 1, ns); }
+    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.psyn + 1, ns); }
     else { for (int j = tid; j < ns; j += NT) S.psyn[j + 1] = S.dp[j]; }   // V3 == 0: diagonal system
     __syncthreads();
     for (int j = tid; j < ni; j += NT) {
@@ -564,7 +651,7 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
         S.dp[j] = d / V2;
     }
     __syncthreads();
-    if (C.F.ad) { if (tid == 0) backsub(S.cp, S.dp, S.pic + 1, ni); }
+    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.pic + 1, ni); }
     else { for (int j = tid; j < ni; j += NT) S.pic[j + 1] = S.dp[j]; }
     __syncthreads();
 }

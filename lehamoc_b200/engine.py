@@ -3,6 +3,7 @@ the work.  One Engine per (grid sizes, flags, variant) per GPU; not thread-safe 
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import numpy as np
 import torch
@@ -33,6 +34,9 @@ class Engine:
         self.lib = _lib.load()
         self.device = torch.cuda.current_device() if device is None else int(device)
         self.cfg = dict(cfg)
+        if "LHM_CONST_B" in os.environ:                      # experiments: force the exponential cache on/off
+            self.cfg["const_B"] = int(os.environ["LHM_CONST_B"])
+        cfg = self.cfg
         self.ic_path = ic_path
         c = lhm_config()
         for k, v in cfg.items():

@@ -9,6 +9,7 @@ Everything state-dependent happens on the GPU; nothing here depends on N(gamma) 
 from __future__ import annotations
 
 from dataclasses import dataclass, field
+from operator import itemgetter
 
 import numpy as np
 
@@ -127,10 +128,17 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
     Vexp = float(F["Vexp"]) * c
     dt = step_alg * R0 / c                                                    # LeMoC.py:108
 
-    g_el = np.logspace(g_min_el, g_max_el, Ng, axis=-1)                       # LeMoC.py:115  [W,Ng]
+    def rows_logspace(lo, hi, n):
+        """np.logspace(lo[w], hi[w], n) per walker; one evaluation broadcast when all walkers agree (same doubles)."""
+        lo, hi = np.broadcast_to(np.asarray(lo, dtype=np.float64), (W,)), np.broadcast_to(np.asarray(hi, dtype=np.float64), (W,))
+        if W > 1 and np.all(lo == lo[0]) and np.all(hi == hi[0]):
+            return np.broadcast_to(np.logspace(lo[0], hi[0], n), (W, n))
+        return np.logspace(lo, hi, n, axis=-1)
+
+    g_el = rows_logspace(g_min_el, g_max_el, Ng)                              # LeMoC.py:115  [W,Ng]
     # PL window (LeMoC.py:120-128); thresholds with Python float pow like the reference's `10**g_PL_max`
-    thr_max = np.array([10 ** float(x) for x in g_PL_max])
-    thr_min = np.array([10 ** float(x) for x in g_PL_min])
+    thr_max = np.array([10 ** x for x in g_PL_max.tolist()])
+    thr_min = np.array([10 ** x for x in g_PL_min.tolist()])
     gt = g_el > thr_max[:, None]
     lt = g_el < thr_min[:, None]
     same = g_PL_max == g_max_el
@@ -139,21 +147,34 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
     index_PL_max = np.where(same, -1, gt.argmax(axis=1))
     index_PL_min = np.where(g_PL_min == 0., 1, lt.sum(axis=1) - 1)
 
-    nu_syn = np.logspace(7.5, np.log10(7. * _nu_c(g_el[:, -1], B0)) + 1.4, Nh, axis=-1)   # LeMoC.py:131
+    nu_syn = rows_logspace(7.5, np.log10(7. * _nu_c(g_el[:, -1], B0)) + 1.4, Nh)         # LeMoC.py:131
     nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
-    nu_tot = np.logspace(np.log10(nu_syn[:, 0]), np.log10(nu_ic[-1]), Nt, axis=-1)         # LeMoC.py:133
+    nu_tot = rows_logspace(np.log10(nu_syn[:, 0]), np.log10(nu_ic[-1]), Nt)                # LeMoC.py:133
     nu_syn = np.concatenate([nu_syn, nu_tot[:, -1:]], axis=1)                              # LeMoC.py:185
-    nu_ic = np.broadcast_to(nu_ic, (W, Nh)).copy()
+    nu_ic = np.broadcast_to(nu_ic, (W, Nh))
 
-    # injection (LeMoC.py:174-175): scalar pieces per walker with NumPy scalars, as the reference evaluates them
-    el_inj = np.full((W, Ng), SENTINEL)
-    cor_Q0 = np.empty(W)
-    for w in range(W):
-        a, b = int(index_PL_min[w]), int(index_PL_max[w])
-        gw = g_el[w]
-        Q0 = _Q_el_Lum(_Lum_e_inj(comp_inj[w], R0[w]), p_el[w], gw[a], gw[b])
-        el_inj[w, a:b] = Q0 * gw[a:b] ** (-p_el[w])
-        cor_Q0[w] = _Q_el_Lum(_Lum_e_inj(comp_cor[w], R0[w]), p_el[w], gw[1], gw[-2])      # LeHaMoC_f.py:202
+    # injection (LeMoC.py:174-175).  The reference evaluates the normalisation with scalars: the two scalar powers
+    # and the log go through Python floats (libm), everything else is elementwise IEEE arithmetic in the same order.
+    rows = np.arange(W)
+    col = np.arange(Ng)[None, :]
+    g_lo = g_el[rows, index_PL_min]
+    g_hi = g_el[rows, index_PL_max]                                  # -1 -> last point, as g_el[index_PL_max]
+
+    def Q_el_Lum_rows(L_el, g_min, g_max):                           # LeHaMoC_f.py:52-56
+        e = -p_el + 2.
+        pw_hi = np.array([x ** y for x, y in zip(g_max.tolist(), e.tolist())])
+        pw_lo = np.array([x ** y for x, y in zip(g_min.tolist(), e.tolist())])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = L_el * e / (m_el * c ** 2. * (pw_hi - pw_lo))
+        for w in np.flatnonzero(p_el == 2.):
+            out[w] = L_el[w] / (m_el * c ** 2. * np.log(g_max[w] / g_min[w]))
+        return out
+
+    Q0 = Q_el_Lum_rows(_Lum_e_inj(comp_inj, R0), g_lo, g_hi)
+    stop = np.where(index_PL_max < 0, Ng + index_PL_max, index_PL_max)
+    inside = (col >= index_PL_min[:, None]) & (col < stop[:, None])
+    el_inj = np.where(inside, Q0[:, None] * g_el ** (-p_el[:, None]), SENTINEL)
+    cor_Q0 = Q_el_Lum_rows(_Lum_e_inj(comp_cor, R0), g_el[:, 1], g_el[:, -2])              # LeHaMoC_f.py:202
 
     # number of steps: range(int(time_end)) (LeMoC.py:196) / while time_real < time_end*R0/c (Code.py:183)
     if variant == "script":
@@ -170,8 +191,9 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
 
     # external fields: identical for walkers that share nu_tot (nu_syn[0] = 10**7.5 and nu_ic[-1] = 1e30 always)
     ext1 = external_fields(F, nu_tot[0])
-    ext = np.broadcast_to(ext1, (W, Nt)).copy()
+    ext = np.broadcast_to(ext1, (W, Nt))
     if not np.all(nu_tot == nu_tot[0]):
+        ext = ext.copy()
         for w in range(1, W):
             ext[w] = external_fields(F, nu_tot[w])
 
@@ -210,15 +232,19 @@ def pack_script(param_sets) -> Batch:
     missing = [k for k in SCRIPT_KEYS if k not in F]
     if missing:
         raise KeyError(f"parameter file lacks {missing}")           # the reference raises KeyError likewise
+    shared_keys = [k for k in SCRIPT_KEYS if k not in WALKER_KEYS]
+    get_shared, get_walker = itemgetter(*shared_keys), itemgetter(*WALKER_KEYS)
+    ref = tuple(float(v) for v in get_shared(F))
     for P in param_sets[1:]:
-        for k in SCRIPT_KEYS:
-            if k not in WALKER_KEYS and float(P[k]) != float(F[k]):
-                raise ValueError(f"walkers of one batch must share '{k}'")
-    col = lambda k: np.array([float(P[k]) for P in param_sets])
-    R0 = np.array([10 ** float(P["R0"]) for P in param_sets])                 # LeMoC.py:79
+        if get_shared(P) != ref and tuple(float(v) for v in get_shared(P)) != ref:
+            bad = [k for k in shared_keys if float(P[k]) != float(F[k])]
+            raise ValueError(f"walkers of one batch must share '{bad[0]}'")
+    table = np.array([get_walker(P) for P in param_sets], dtype=np.float64)           # [W, len(WALKER_KEYS)]
+    col = lambda k: np.ascontiguousarray(table[:, WALKER_KEYS.index(k)])
+    R0 = np.array([10 ** x for x in col("R0").tolist()])                      # LeMoC.py:79
     B0 = col("B0")
-    comp_el = np.array([sigmaT * 10 ** float(P["L_el"]) / (4. * np.pi * r * m_el * c ** 3)
-                        for P, r in zip(param_sets, R0)])                      # LeMoC.py:110
+    L_el = np.array([10 ** x for x in col("L_el").tolist()])                  # LeMoC.py:76
+    comp_el = sigmaT * L_el / (4. * np.pi * R0 * m_el * c ** 3)               # LeMoC.py:110
     return _pack("script", F, R0, B0, col("g_min_el"), col("g_max_el"), col("g_PL_min"), col("g_PL_max"),
                  col("p_el"), comp_el, comp_el)
 
@@ -229,10 +255,10 @@ def pack_code(thetas, frozen: dict) -> Batch:
     missing = [k for k in CODE_KEYS if k not in frozen]
     if missing:
         raise KeyError(f"parameter file lacks {missing}")
-    R0 = np.array([10 ** float(x) for x in thetas[:, 0]])                      # Code.py:53
-    B0 = np.array([10 ** float(x) for x in thetas[:, 1]])                      # Code.py:54
+    R0 = np.array([10 ** x for x in thetas[:, 0].tolist()])                    # Code.py:53
+    B0 = np.array([10 ** x for x in thetas[:, 1].tolist()])                    # Code.py:54
     g_PL_min, g_PL_max = thetas[:, 2].copy(), thetas[:, 3].copy()
-    comp_inj = np.array([10 ** float(x) for x in thetas[:, 4]])                # Code.py:163
+    comp_inj = np.array([10 ** x for x in thetas[:, 4].tolist()])              # Code.py:163
     comp_cor = thetas[:, 4].copy()                                             # Code.py:237 passes the log value
     return _pack("code", frozen, R0, B0, g_PL_min - 1., g_PL_max + 1., g_PL_min, g_PL_max, thetas[:, 5].copy(),
                  comp_inj, comp_cor)

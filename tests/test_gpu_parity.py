@@ -323,3 +323,17 @@ def test_ic_pair_table_modes_are_bit_identical():
         eng.run_host(ragged)
     with pytest.raises(_lib.LhmError):
         eng.setup(ragged)
+
+
+def test_run_many_matches_run():
+    """The pipelined throughput API gives, batch by batch and in order, exactly what the synchronous call gives."""
+    from lehamoc_b200 import LeMoC
+    _, P = load_golden("test1")
+    P.update(grid_g_el=70., grid_nu=40., time_end=3.)
+    batches = [[dict(P, B0=0.5 + 0.1 * (i + 3 * k), p_el=1.7 + 0.05 * i) for i in range(3 + k)] for k in range(5)]
+    ref = [LeMoC.run(b, snapshots=False) for b in batches]
+    got = [(b.W, N.copy(), sed.copy()) for b, N, sed in LeMoC.run_many(iter(batches))]
+    assert [g[0] for g in got] == [len(b) for b in batches]
+    for (_, N, sed), (_, Nr, sedr) in zip(got, ref):
+        np.testing.assert_array_equal(sed, sedr[:, 0])
+        np.testing.assert_array_equal(N, Nr[:, 0])
