@@ -193,7 +193,7 @@ def run_reference_arm(args):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def workload_name(args):
@@ -202,12 +202,36 @@ def workload_name(args):
 
 
 # ------------------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _guard_stdout():
+    """Anything libraries print to fd 1 (NCCL's version banner, for one) goes to stderr; the JSON line alone goes to
+    the real stdout through emit()."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line: dict):
+    data = (json.dumps(line) + "\n").encode()
+    sys.stdout.flush()
+    if _REAL_STDOUT is None:
+        os.write(1, data)
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    _guard_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--walkers", type=int, default=1024, help="walkers per GPU")
+    ap.add_argument("--walkers", type=int, default=1184,
+                    help="walkers per GPU (default 1184 = 4 full waves of 148 SMs x 2 resident walker CTAs)")
     ap.add_argument("--ic-path", default="R", choices=["R", "S"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -452,7 +476,7 @@ def main():
                                 "hoisted_vectorised_port_value": vh,
                                 "hoisted_note": f"same models with cor_factor hoisted and the gamma loop broadcast "
                                                 f"(bit-identical results); {wallh:.1f} s wall"}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
