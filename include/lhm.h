@@ -158,6 +158,32 @@ int lhm_loglike_batch(int W, int Nt, const double* nu_tot, const double* nuLnu, 
                       const double* y, const double* yerr_hi, const double* yerr_lo, const double* flags,
                       double* logl_out, double* ymodel_out, void* cuda_stream);
 
+/* ---- hadronic stage, function-level entry points (handle-free) -------------------------
+ * The six tables the reference reads at import (`LeHaMoC Code and Tests/LeHaMoC_f.py`:14-19), as DEVICE pointers to
+ * row-major copies of the files. */
+typedef struct {
+    const double* phi_g;   int n_phi_g;     /* Phi_g_K&A.txt          [n,4]  eta/eta0, s, d, B                       */
+    const double* phi_el;  int n_phi_el;    /* Phi_g_leptons_K&A.txt  [n,13] eta/eta0, (s,d,B) x e+, anti-nu_mu, nu_mu, nu_e */
+    const double* phi_el1; int n_phi_el1;   /* Phi_e-nu_e_K&A.txt     [n,7]  eta/eta0, (s,d,B) x e-, anti-nu_e       */
+    const double* fk;      int n_fk;        /* f(xi).csv              [n,2]  log10 kappa, log10 f                    */
+    const double* cs;      int n_cs;        /* cross_section.csv      [n,2]  photon energy (GeV), sigma (microbarn)  */
+    const double* kp;      int n_kp;        /* kp_pg.txt              [n,2]  photon energy (GeV), inelasticity       */
+} lhm_had_tables;
+
+/* A11 proton loss rates for W walkers at Ne proton Lorentz factors each: which = 0 dg_dt_pg (LeHaMoC_f.py:201-220,
+ * photopion), which = 1 dg_dt_BH (LeHaMoC_f.py:185-196, Bethe-Heitler).  g_eval [W,Ne]; nu, photons [W,Nt];
+ * out [W,Ne]. */
+int lhm_had_loss_batch(int W, int Ne, int Nt, int which, const double* g_eval, const double* nu, const double* photons,
+                       const lhm_had_tables* tables, double* out, void* cuda_stream);
+
+/* A12 photopion secondaries Qp_g_opt (LeHaMoC_f.py:358-464, Phi_g :466-563).  species: 0 "2_g" (out [W,Ni] on h nu_ic),
+ * 1 "e+", 2 "e-" (out [W,Ng] on g_el m_e c^2), 3 "nu_mu", 4 anti-nu_mu, 5 "nu_e", 6 anti-nu_e (out [W,Nnu] on E_nu).
+ * g_el [W,Ng]; nu_ic [W,Ni]; E_nu [Nnu] (erg, shared); N_pr, g_pr [W,Np]; photons, nu_target [W,Nt]. */
+int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int Nnu, const double* g_el,
+                        const double* nu_ic, const double* E_nu, const double* N_pr, const double* g_pr,
+                        const double* photons, const double* nu_target, const lhm_had_tables* tables, double* out,
+                        void* cuda_stream);
+
 /* measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator */
 int lhm_fp64_peak_probe(int device, void* cuda_stream, double* tflops_out);
 

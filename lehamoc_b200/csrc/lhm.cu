@@ -13,6 +13,7 @@
 #include "lhm_step.cuh"
 #include "lhm_setup.cuh"
 #include "lhm_cor.cuh"
+#include "lhm_had.cuh"
 
 namespace lhm {
 
@@ -641,6 +642,71 @@ int lhm_loglike_batch(int W, int Nt, const double* nu_tot, const double* nuLnu, 
     A.log1pz = log10_1pz; A.dist_norm = distance_norm; A.x = x; A.y = y; A.yerr = yerr_hi; A.yerr1 = yerr_lo;
     A.flags = flags; A.logl = logl_out; A.ymodel = ymodel_out;
     loglike_kernel<<<(W + LL_WARPS - 1) / LL_WARPS, LL_WARPS * 32, smem, (cudaStream_t)stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+static int had_init() {
+    static bool done = false;       // per process and device context; constants never change
+    HadConst hc;
+    hc.c = 2.99792458e10; hc.h = 6.62607015e-27; hc.m_el = 9.1093837015e-28; hc.m_pr = 1.67262192369e-24;
+    hc.sigmaT = 6.6524587321e-25; hc.eV = 1.602176634e-12;
+    (void)done;
+    CUDA_TRY(cudaMemcpyToSymbol(kHC, &hc, sizeof(hc)));
+    return LHM_OK;
+}
+
+static HadTables to_dev_tables(const lhm_had_tables* t) {
+    HadTables T;
+    T.phi_g = t->phi_g; T.n_phi_g = t->n_phi_g; T.phi_el = t->phi_el; T.n_phi_el = t->n_phi_el;
+    T.phi_el1 = t->phi_el1; T.n_phi_el1 = t->n_phi_el1; T.fk = t->fk; T.n_fk = t->n_fk; T.cs = t->cs; T.n_cs = t->n_cs;
+    T.kp = t->kp; T.n_kp = t->n_kp;
+    return T;
+}
+
+int lhm_had_loss_batch(int W, int Ne, int Nt, int which, const double* g_eval, const double* nu, const double* photons,
+                       const lhm_had_tables* tables, double* out, void* stream) {
+    if (W < 1 || Ne < 1 || Nt < 2 || (which != 0 && which != 1) || !g_eval || !nu || !photons || !tables || !out)
+        return LHM_ERR_ARG;
+    if (which == 0 && (!tables->cs || !tables->kp || tables->n_cs < 3 || tables->n_kp < 2)) return LHM_ERR_ARG;
+    if (which == 1 && (!tables->fk || tables->n_fk < 2)) return LHM_ERR_ARG;
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    LossArgs A;
+    A.W = W; A.Ne = Ne; A.Nt = Nt; A.which = which; A.g_eval = g_eval; A.nu = nu; A.photons = photons;
+    A.T = to_dev_tables(tables); A.out = out;
+    const int nt = tables->n_cs > tables->n_fk ? tables->n_cs : tables->n_fk;
+    const size_t smem = ((size_t)2 * Nt + 2 * nt + 2 * tables->n_kp) * sizeof(double);
+    if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaFuncSetAttribute(had_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    had_loss_kernel<<<W, HAD_NT, smem, (cudaStream_t)stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int Nnu, const double* g_el,
+                        const double* nu_ic, const double* E_nu, const double* N_pr, const double* g_pr,
+                        const double* photons, const double* nu_target, const lhm_had_tables* tables, double* out,
+                        void* stream) {
+    if (W < 1 || species < 0 || species >= SP_COUNT || Ng < 1 || Ni < 1 || Np < 2 || Nt < 2 || Nnu < 1 || !g_el || !nu_ic ||
+        !E_nu || !N_pr || !g_pr || !photons || !nu_target || !tables || !out) return LHM_ERR_ARG;
+    if (!tables->phi_g || !tables->phi_el || !tables->phi_el1) return LHM_ERR_ARG;
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    PionArgs A;
+    A.W = W; A.species = species; A.Ng = Ng; A.Ni = Ni; A.Np = Np; A.Nt = Nt; A.Nnu = Nnu;
+    A.Nout = (species == SP_2G) ? Ni : (species == SP_EP || species == SP_EM) ? Ng : Nnu;
+    A.g_el = g_el; A.nu_ic = nu_ic; A.E_nu = E_nu; A.N_pr = N_pr; A.g_pr = g_pr; A.photons = photons; A.nu_t = nu_target;
+    A.T = to_dev_tables(tables); A.out = out;
+    int ntab = tables->n_phi_g;
+    if (tables->n_phi_el > ntab) ntab = tables->n_phi_el;
+    if (tables->n_phi_el1 > ntab) ntab = tables->n_phi_el1;
+    const size_t smem = pion_smem_doubles(Nt, Np, ntab) * sizeof(double);
+    if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaFuncSetAttribute(had_pion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    had_pion_kernel<<<W, HAD_NT, smem, (cudaStream_t)stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return LHM_OK;

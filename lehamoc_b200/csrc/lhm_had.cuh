@@ -1,0 +1,311 @@
+// lhm_had.cuh -- hadronic stage, function-level kernels, batched over walkers.
+//   A11  dg_dt_BH  `LeHaMoC Code and Tests/LeHaMoC_f.py`:185-196   Bethe-Heitler proton loss rate (table f(xi).csv)
+//        dg_dt_pg  LeHaMoC_f.py:201-220                            photopion proton loss rate (cross_section.csv, kp_pg.txt)
+//   A12  Qp_g_opt  LeHaMoC_f.py:358-464 with Phi_g :466-563        photopion secondaries (Kelner & Aharonian 2008 eq. 30)
+// The six tables are tiny (< 4 KB each); they are staged in shared memory per CTA.  float64 throughout.
+#pragma once
+#include "lhm_device.cuh"
+#include "../../include/lhm.h"
+
+namespace lhm {
+
+struct HadTables {            // device pointers, row-major
+    const double* phi_g;   int n_phi_g;      // [n,4]  eta/eta0, s, d, B                         Phi_g_K&A.txt
+    const double* phi_el;  int n_phi_el;     // [n,13] eta/eta0, (s,d,B) x {e+, anti-nu_mu, nu_mu, nu_e}   Phi_g_leptons_K&A.txt
+    const double* phi_el1; int n_phi_el1;    // [n,7]  eta/eta0, (s,d,B) x {e-, anti-nu_e}       Phi_e-nu_e_K&A.txt
+    const double* fk;      int n_fk;         // [n,2]  log10 kappa, log10 f                       f(xi).csv
+    const double* cs;      int n_cs;         // [n,2]  photon energy (GeV), cross section (microbarn)  cross_section.csv
+    const double* kp;      int n_kp;         // [n,2]  photon energy (GeV), inelasticity          kp_pg.txt
+};
+
+struct HadConst {
+    double c, h, m_el, m_pr, sigmaT, eV;
+};
+__constant__ HadConst kHC;
+
+// np.interp(x, xp, fp) with end clamping (finite ordinates)
+__device__ __forceinline__ double interp_clamped(double x, const double* __restrict__ xp, const double* __restrict__ fp,
+                                                 int n, int fstride = 1) {
+    int code; double dx, Dx;
+    interp_stencil(x, xp, n, code, dx, Dx);
+    const int j = code >> 1;
+    const double f0 = fp[(size_t)j * fstride];
+    if (code & 1) return f0;
+    const double f1 = fp[(size_t)(j + 1) * fstride];
+    const double slope = (f1 - f0) / Dx;
+    double r = slope * dx + f0;
+    if (isnan(r)) {
+        r = slope * (dx - Dx) + f1;
+        if (isnan(r) && f0 == f1) r = f0;
+    }
+    return r;
+}
+
+// np.logspace(a, b, n)[i] = 10**(a + i*step), the last point exactly 10**b (np.linspace semantics)
+__device__ __forceinline__ double logspace_exp(double a, double b, int i, int n) {
+    const double step = (b - a) / (double)(n - 1);
+    return (i == n - 1) ? b : fma((double)i, step, a);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A11: proton loss rates.  One CTA per walker, one warp per proton Lorentz factor, lanes over the outer samples.
+// ---------------------------------------------------------------------------------------------------------------
+struct LossArgs {
+    int W, Ne, Nt, which;          // which: 0 = photopion (dg_dt_pg), 1 = Bethe-Heitler (dg_dt_BH)
+    const double *g_eval, *nu, *photons;      // [W,Ne], [W,Nt], [W,Nt]
+    HadTables T;
+    double* out;                   // [W,Ne]
+};
+
+constexpr int HAD_NT = 256;
+
+__global__ void __launch_bounds__(HAD_NT) had_loss_kernel(LossArgs A) {
+    extern __shared__ __align__(16) double sh[];
+    const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
+    const int Nt = A.Nt;
+    const HadConst& K = kHC;
+    double* lx = sh;                 // abscissae of the photon interpolation
+    double* lp = lx + Nt;            // ordinates
+    double* tx = lp + Nt;            // table abscissae (log10)
+    double* ty = tx + max(A.T.n_cs, A.T.n_fk);
+    double* ux = ty + max(A.T.n_cs, A.T.n_fk);      // second table (kp) abscissae / ordinates
+    double* uy = ux + A.T.n_kp;
+    const double* nu = A.nu + (size_t)w * Nt;
+    const double* ph = A.photons + (size_t)w * Nt;
+    const double mc2 = K.m_el * K.c * K.c;
+    int ncs = 0;
+    if (A.which == 0) {
+        for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k]); lp[k] = log10(ph[k] / K.h); }
+        ncs = A.T.n_cs - 1;                                     // the reference drops the first row ([1:])
+        for (int k = tid; k < ncs; k += HAD_NT) {
+            tx[k] = log10(A.T.cs[2 * (k + 1)] * 1e9 * K.eV);
+            ty[k] = A.T.cs[2 * (k + 1) + 1];
+        }
+        for (int k = tid; k < A.T.n_kp; k += HAD_NT) { ux[k] = log10(A.T.kp[2 * k] * 1e9 * K.eV); uy[k] = A.T.kp[2 * k + 1]; }
+    } else {
+        for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k] / mc2); lp[k] = log10(ph[k]); }
+        for (int k = tid; k < A.T.n_fk; k += HAD_NT) { tx[k] = A.T.fk[2 * k]; ty[k] = A.T.fk[2 * k + 1]; }
+    }
+    __syncthreads();
+    const double hnu_max = K.h * nu[Nt - 1];
+    for (int e = warp; e < A.Ne; e += NW) {
+        const double g_p = A.g_eval[(size_t)w * A.Ne + e];
+        double res = 0.0;
+        if (A.which == 0) {
+            const double E_th = 145. * 1e6 * K.eV;
+            if (g_p * hnu_max > E_th) {
+                const double a = log10(E_th), b = log10(2. * g_p * hnu_max) + 3;
+                const double dle = (b - a) / 99.0 * 2.302585092994046;           // spacing of ln(eps_bar)
+                double s = 0.0;
+                for (int i = lane; i < 100; i += 32) {
+                    const double leb = logspace_exp(a, b, i, 100);
+                    const double eb = exp10(leb);
+                    double inner = 0.0;
+                    if (eb / (2. * g_p) < hnu_max / 2.) {
+                        // trapz(dN/eps', ln eps') over eps' = logspace(log10(eb/(2 g_p)), log10(h nu_max), 30)
+                        const double a2 = log10(eb / (2. * g_p)), b2 = log10(hnu_max);
+                        double prev_l = 0.0, prev_y = 0.0;
+                        for (int q = 0; q < 30; ++q) {
+                            const double le = logspace_exp(a2, b2, q, 30);
+                            const double ep = exp10(le);
+                            const double y = exp10(interp_clamped(log10(ep), lx, lp, Nt)) / ep;
+                            const double ln_e = log(ep);
+                            if (q > 0) inner += (ln_e - prev_l) * (y + prev_y) / 2.0;
+                            prev_l = ln_e; prev_y = y;
+                        }
+                    }
+                    const double CS = interp_clamped(log10(eb), tx, ty, ncs);
+                    const double KP = interp_clamped(log10(eb), ux, uy, A.T.n_kp);
+                    // trapezoid weights on the uniform ln(eps_bar) grid: reproduce np.trapz on the actual logs
+                    const double lm = (i > 0) ? log(exp10(logspace_exp(a, b, i - 1, 100))) : 0.0;
+                    const double lc = log(eb);
+                    const double lq = (i < 99) ? log(exp10(logspace_exp(a, b, i + 1, 100))) : 0.0;
+                    const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 99) ? (lq - lc) : 0.0)) * 0.5;
+                    (void)dle;
+                    s += wgt * (CS * KP * inner * (eb * eb));
+                }
+                s = warp_sum(s);
+                res = 1. / g_p * s * (5e-31 * K.c);
+            }
+        } else {
+            if (g_p * hnu_max > 2.1 * mc2) {
+                const double C_BH = 3. * K.sigmaT * K.c * K.m_el / (8 * M_PI * 137. * K.m_pr);
+                const double a = log10(2.), b = log10(g_p * hnu_max / mc2);
+                double s = 0.0;
+                for (int i = lane; i < 50; i += 32) {
+                    const double lk = logspace_exp(a, b, i, 50);
+                    const double kap = exp10(lk);
+                    const double phb = mc2 / K.h * exp10(interp_clamped(log10(kap / (2. * g_p)), lx, lp, Nt));
+                    const double fk = interp_clamped(log10(kap), tx, ty, A.T.n_fk);
+                    // np.trapz(..., np.log10(kappa))
+                    const double lm = (i > 0) ? log10(exp10(logspace_exp(a, b, i - 1, 50))) : 0.0;
+                    const double lc = log10(kap);
+                    const double lq = (i < 49) ? log10(exp10(logspace_exp(a, b, i + 1, 50))) : 0.0;
+                    const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 49) ? (lq - lc) : 0.0)) * 0.5;
+                    s += wgt * (exp10(fk) * phb * kap);
+                }
+                s = warp_sum(s);
+                res = s * C_BH;
+            }
+        }
+        if (lane == 0) A.out[(size_t)w * A.Ne + e] = res;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// A12: photopion secondaries.  One CTA per (walker, species); per proton energy the eta grid, the interpolated target
+// photons and the integration measure are independent of the outgoing energy and are staged in shared memory; a warp
+// then owns one outgoing energy and runs its lanes over the 50 x 25 (gamma_p, eta) points.
+// ---------------------------------------------------------------------------------------------------------------
+enum { SP_2G = 0, SP_EP, SP_EM, SP_NUMU, SP_ANUMU, SP_NUE, SP_ANUE, SP_COUNT };
+constexpr int PG_NG = 50, PG_NE = 25, PG_N = PG_NG * PG_NE;
+
+struct PionArgs {
+    int W, species, Ng, Ni, Np, Nt, Nnu, Nout;
+    const double *g_el, *nu_ic, *E_nu;        // [W,Ng], [W,Ni], [Nnu] (erg)
+    const double *N_pr, *g_pr;                // [W,Np]
+    const double *photons, *nu_t;             // [W,Nt]
+    HadTables T;
+    double* out;                              // [W,Nout]
+};
+
+__host__ __device__ inline size_t pion_smem_doubles(int Nt, int Np, int ntab) {
+    return (size_t)2 * Nt + 2 * Np + 4 * ntab + 3 * PG_NG + 8 * PG_N;
+}
+
+__device__ __forceinline__ double ka_x_plus(double eta, double r) {
+    return 1. / (2. * (1. + eta)) * (eta + r * r + sqrt((eta - r * r - 2. * r) * (eta - r * r + 2. * r)));
+}
+__device__ __forceinline__ double ka_x_minus(double eta, double r) {
+    return 1. / (2. * (1. + eta)) * (eta + r * r - sqrt((eta - r * r - 2. * r) * (eta - r * r + 2. * r)));
+}
+__device__ __forceinline__ double ka_x_plus_e(double eta, double r) {
+    return 1. / (2. * (1. + eta)) * (eta - 2 * r + sqrt(eta * (eta - 4. * r * (1. + r))));
+}
+__device__ __forceinline__ double ka_x_minus_e(double eta, double r) {
+    return 1. / (2. * (1. + eta)) * (eta - 2 * r - sqrt(eta * (eta - 4. * r * (1. + r))));
+}
+
+__global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
+    extern __shared__ __align__(16) double sh[];
+    const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
+    const HadConst& K = kHC;
+    const int Nt = A.Nt, Np = A.Np, sp = A.species;
+    const double h_0 = 0.313, r = 0.1458;
+    const double mpc2 = K.m_pr * K.c * K.c, mec2 = K.m_el * K.c * K.c;
+    // species-dependent pieces (LeHaMoC_f.py:359-461, 466-563)
+    const bool is_em = (sp == SP_EM || sp == SP_ANUE);
+    const double thr = is_em ? 2.14 * h_0 : h_0;
+    const double* tab; int ntab, ncol, c_s;
+    if (sp == SP_2G) { tab = A.T.phi_g; ntab = A.T.n_phi_g; ncol = 4; c_s = 1; }
+    else if (is_em) { tab = A.T.phi_el1; ntab = A.T.n_phi_el1; ncol = 7; c_s = (sp == SP_EM) ? 1 : 4; }
+    else { tab = A.T.phi_el; ntab = A.T.n_phi_el; ncol = 13;
+           c_s = (sp == SP_EP) ? 1 : (sp == SP_ANUMU) ? 4 : (sp == SP_NUMU) ? 7 : 10; }
+    const double* g_el = A.g_el + (size_t)w * A.Ng;
+    const double* nu_ic = A.nu_ic + (size_t)w * A.Ni;
+    const double* nu_t = A.nu_t + (size_t)w * Nt;
+    const double* g_pr = A.g_pr + (size_t)w * Np;
+    double g_min_int, pref;
+    if (sp == SP_2G) { g_min_int = h_0 * mpc2 / (4. * K.h * nu_t[Nt - 1]); pref = K.h; }
+    else if (sp == SP_EP || sp == SP_EM) { g_min_int = thr * mpc2 / (4. * g_el[A.Ng - 1] * mec2); pref = mec2; }
+    else { g_min_int = thr * mpc2 / (4. * A.E_nu[A.Nnu - 1]); pref = K.h; }
+
+    double* lnt = sh;                  double* lpt = lnt + Nt;
+    double* lgp = lpt + Nt;            double* lNp = lgp + Np;
+    double* tx = lNp + Np;             double* ts = tx + ntab; double* td = ts + ntab; double* tB = td + ntab;
+    double* g_t = tB + ntab;           double* coef = g_t + PG_NG;  double* act = coef + PG_NG;   // per gamma_p
+    double* Wt = act + PG_NG;          // [PG_N] trapezoid weight x photons x nu
+    double* Es = Wt + PG_N;            double* Ed = Es + PG_N;    double* EB = Ed + PG_N;
+    double* Epsi = EB + PG_N;          double* Exm = Epsi + PG_N; double* Exp = Exm + PG_N; double* Elow = Exp + PG_N;
+
+    for (int k = tid; k < Nt; k += HAD_NT) {
+        lnt[k] = log10(nu_t[k]);
+        lpt[k] = log10(A.photons[(size_t)w * Nt + k]);
+    }
+    for (int k = tid; k < Np; k += HAD_NT) { lgp[k] = log10(g_pr[k]); lNp[k] = log10(A.N_pr[(size_t)w * Np + k]); }
+    for (int k = tid; k < ntab; k += HAD_NT) {
+        tx[k] = tab[k * ncol]; ts[k] = tab[k * ncol + c_s]; td[k] = tab[k * ncol + c_s + 1]; tB[k] = tab[k * ncol + c_s + 2];
+    }
+    __syncthreads();
+    const double ga = log10(fmax(g_min_int, g_pr[0])), gb = log10(g_pr[Np - 1]);
+    for (int gi = tid; gi < PG_NG; gi += HAD_NT) {
+        const double lg = logspace_exp(ga, gb, gi, PG_NG);
+        const double gp = exp10(lg);
+        g_t[gi] = gp;
+        const double Nt_ = exp10(interp_clamped(log10(gp), lgp, lNp, Np));
+        // np.trapz(., np.log(g_pr_temp)) weights
+        const double lm = (gi > 0) ? log(exp10(logspace_exp(ga, gb, gi - 1, PG_NG))) : 0.0;
+        const double lc = log(gp);
+        const double lq = (gi < PG_NG - 1) ? log(exp10(logspace_exp(ga, gb, gi + 1, PG_NG))) : 0.0;
+        const double wg = (((gi > 0) ? (lc - lm) : 0.0) + ((gi < PG_NG - 1) ? (lq - lc) : 0.0)) * 0.5;
+        coef[gi] = wg * (pref * Nt_ / mpc2);
+        const double c_t = mpc2 / (4. * gp);
+        act[gi] = (log10(thr * c_t / K.h) < log10(nu_t[Nt - 1])) ? 1.0 : 0.0;
+    }
+    __syncthreads();
+    for (int e = tid; e < PG_N; e += HAD_NT) {
+        const int gi = e / PG_NE, ei = e - gi * PG_NE;
+        const double gp = g_t[gi];
+        const double c_t = mpc2 / (4. * gp);
+        const double eta_max = 4. * K.h * nu_t[Nt - 1] * gp / mpc2;
+        const double ea = log10(thr), eb = log10(eta_max);
+        auto eta_at = [&](int i) { return exp10(logspace_exp(ea, eb, i, PG_NE)); };
+        const double eta = eta_at(ei);
+        const double nut = eta * c_t / K.h;
+        const double phv = exp10(interp_clamped(log10(nut), lnt, lpt, Nt));
+        // np.trapz(., np.log(h*nu_target_temp))
+        const double lc = log(K.h * nut);
+        const double lm = (ei > 0) ? log(K.h * (eta_at(ei - 1) * c_t / K.h)) : 0.0;
+        const double lq = (ei < PG_NE - 1) ? log(K.h * (eta_at(ei + 1) * c_t / K.h)) : 0.0;
+        const double wgt = (((ei > 0) ? (lc - lm) : 0.0) + ((ei < PG_NE - 1) ? (lq - lc) : 0.0)) * 0.5;
+        Wt[e] = (act[gi] != 0.0) ? wgt * (phv * nut) : 0.0;
+        const double hh = eta / h_0;
+        const double s = interp_clamped(hh, tx, ts, ntab), d = interp_clamped(hh, tx, td, ntab), B = interp_clamped(hh, tx, tB, ntab);
+        double xp, xm, psi;
+        if (sp == SP_2G) { xp = ka_x_plus(eta, r); xm = ka_x_minus(eta, r); psi = 2.5 + 0.4 * log(hh); }
+        else if (sp == SP_EP || sp == SP_ANUMU || sp == SP_NUE) { xp = ka_x_plus(eta, r); xm = ka_x_minus(eta, r) / 4.; psi = 2.5 + 1.4 * log(hh); }
+        else if (sp == SP_NUMU) {
+            if (hh < 2.17) xp = 0.427 * ka_x_plus(eta, r);
+            else if (hh > 2.17 && hh < 10) xp = (0.427 + 0.0729 * (hh - 2.14)) * ka_x_plus(eta, r);
+            else xp = ka_x_plus(eta, r);
+            xm = 0.427 * ka_x_minus(eta, r);
+            psi = 2.5 + 1.4 * log(hh);
+        } else {
+            xp = ka_x_plus_e(eta, r); xm = ka_x_minus_e(eta, r) / 2.;
+            psi = (hh > 4.) ? 6. * (1 - exp(1.5 * (4. - hh))) : 0.;
+        }
+        Es[e] = s; Ed[e] = d; EB[e] = B; Epsi[e] = psi; Exm[e] = xm; Exp[e] = xp;
+        Elow[e] = B * pow(log(2.), psi);
+    }
+    __syncthreads();
+    const bool nan_to_num = (sp != SP_2G);
+    for (int k = warp; k < A.Nout; k += NW) {
+        double Eo;
+        if (sp == SP_2G) Eo = K.h * nu_ic[k];
+        else if (sp == SP_EP || sp == SP_EM) Eo = g_el[k] * mec2;
+        else Eo = A.E_nu[k];
+        double acc = 0.0;
+        for (int e = lane; e < PG_N; e += 32) {
+            const int gi = e / PG_NE;
+            const double wv = Wt[e];
+            if (act[gi] == 0.0) continue;
+            const double x = Eo / (g_t[gi] * mpc2);
+            const double xm = Exm[e], xp = Exp[e];
+            double Phi;
+            if (x < xm) Phi = Elow[e];
+            else if (xp > x && x > xm) {
+                const double y = (x - xm) / (xp - xm);
+                Phi = EB[e] * exp(-Es[e] * pow(log(x / xm), Ed[e])) * pow(log(2. / (1 + y * y)), Epsi[e]);
+            } else Phi = 0.0;
+            if (nan_to_num) {                                   // np.nan_to_num: nan -> 0, +-inf -> +-max double
+                if (isnan(Phi)) Phi = 0.0;
+                else if (isinf(Phi)) Phi = copysign(1.7976931348623157e308, Phi);
+            }
+            acc += coef[gi] * (wv * Phi);
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) A.out[(size_t)w * A.Nout + k] = acc;
+    }
+}
+
+}  // namespace lhm

@@ -55,3 +55,47 @@ def test_oracle_photopion_secondaries(gold, sp):
 
 def test_neutrino_grid(gold):
     np.testing.assert_array_equal(oh.E_NU_SPACE, gold["E_nu_space"])
+
+
+# ---- GPU: the CUDA kernels against the live reference ---------------------------------------------------------
+def _load(gold):
+    from lehamoc_b200 import hadronic
+    T = tables_of(gold)
+    hadronic.set_tables({"phi_g": T["Phi_g"], "phi_el": T["Phi_el"], "phi_el1": T["Phi_el_1"], "fk": T["f_k_i"],
+                         "cs": T["cross_section"], "kp": T["kp_pg"]})
+    return hadronic
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1])
+def test_gpu_loss_rates(gold, case):
+    had = _load(gold)
+    p = f"c{case}_"
+    rel_close(had.dg_dt_BH(gold[p + "g_pr"], gold[p + "nu"], gold[p + "photons"]), gold[p + "dg_dt_BH"], 1e-8, "dg_dt_BH")
+    rel_close(had.dg_dt_pg(gold[p + "g_pr"], gold[p + "nu"], gold[p + "photons"]), gold[p + "dg_dt_pg"], 1e-8, "dg_dt_pg")
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("sp", oh.SPECIES)
+def test_gpu_photopion_secondaries(gold, sp):
+    had = _load(gold)
+    for case in (0, 1):
+        p = f"c{case}_"
+        got = had.Qp_g_opt(gold[p + "g_el"], gold[p + "nu_ic"], gold[p + "N_pr"], gold[p + "g_pr"], gold[p + "photons"],
+                           gold[p + "nu"], sp)
+        rel_close(got, gold[p + "Q_" + sp.replace("\b", "b")], 1e-8, f"Qp_g_opt {sp!r} case {case}")
+
+
+@pytest.mark.gpu
+def test_gpu_hadronic_batch_equals_single(gold):
+    """Two different walkers in one launch give what each gives alone."""
+    had = _load(gold)
+    keys = ("g_el", "nu_ic", "N_pr", "g_pr", "photons", "nu")
+    both = [np.stack([gold[f"c{c}_" + k] for c in (0, 1)]) for k in keys]
+    got = had.Qp_g_opt(*both, "e+")
+    for c in (0, 1):
+        one = had.Qp_g_opt(*[gold[f"c{c}_" + k] for k in keys], "e+")
+        np.testing.assert_array_equal(got[c], one)
+    lb = had.dg_dt_pg(np.stack([gold["c0_g_pr"], gold["c1_g_pr"]]), np.stack([gold["c0_nu"], gold["c1_nu"]]),
+                      np.stack([gold["c0_photons"], gold["c1_photons"]]))
+    np.testing.assert_array_equal(lb[1], had.dg_dt_pg(gold["c1_g_pr"], gold["c1_nu"], gold["c1_photons"]))
