@@ -57,6 +57,11 @@ typedef struct {
     int shared_ic_grids;    /* 1: the caller guarantees that all walkers of every batch have identical g_el, nu_ic and
                                nu_tot rows (fixed-grid parameter sweeps): one pair table for the whole batch.  Checked
                                by the *_host entry points; needs ic_pair_table */
+    int driver;             /* 0: LeMoC/LeMoC.py and Fit_emcee/Code.py (leptonic); 1: `LeHaMoC Code and Tests/LeHaMoC.py`
+                               (electron + proton equations, proton synchrotron, f_had variants of U_ph_f / a_gg /
+                               Q_ee_f with gg_npts = 100, gamma-gamma pre-attenuation of the first two steps) */
+    int Np;                 /* len(g_pr) = int(grid_g_pr), driver 1 only                   LeHaMoC.py:147 */
+    int esc_flag_pr;        /* proton escape flag, driver 1 only                            LeHaMoC.py:331 */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 
@@ -108,6 +113,12 @@ int lhm_cor_factor_batch(lhm_handle*, double* out);
  * first S steps ([W,S,Ng], [W,S,Nt]).  Either output may be NULL.  lhm_cor_factor_batch is run
  * internally when Syn_emis_flag is set. */
 int lhm_run_batch(lhm_handle*, double* N_el_out, double* nuLnu_out, int snapshots);
+
+/* Driver 1 (LeHaMoC.py): proton grid and injection rate per volume of the next batch, g_pr [W,Np], pr_inj [W,Np]
+ * (LeHaMoC.py:147,258); call before lhm_setup_batch.  el_inj of lhm_setup_batch is per volume too (LeHaMoC.py:257). */
+int lhm_set_protons(lhm_handle*, const double* g_pr, const double* pr_inj);
+/* Driver 1: the whole time integration LeHaMoC.py:266-434; as lhm_run_batch plus N_pr/Volume [W,(S),Np]. */
+int lhm_run_batch_lh(lhm_handle*, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots);
 
 /* Device time (ms, CUDA events on the handle's stream) of the most recent set-up, cor-factor and fused-step
  * kernels; -1 if never launched.  Synchronises on those events only.  bench.py's roofline uses run_ms. */

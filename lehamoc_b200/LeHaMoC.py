@@ -1,0 +1,69 @@
+"""Drop-in for `python LeHaMoC.py <Parameters.txt> <_suffix>` (`LeHaMoC Code and Tests/LeHaMoC.py`:56-71,436-453):
+
+    python -m lehamoc_b200.LeHaMoC Parameters.txt _out
+
+writes Pairs_Distribution<suffix>.txt, Photons_Distribution<suffix>.txt, Protons_Distribution<suffix>.txt and
+Neutrinos_Distribution<suffix>.txt in the reference's text format (one block per timestep).  `run()` is the importable
+form and takes several parameter sets at once.  Runs with the photo-hadronic / pp flags set raise NotImplementedError
+(their source and loss terms exist as function-level kernels, lehamoc_b200.hadronic, but are not wired into the
+timestep yet); the neutrino distribution of a run without them is identically zero, as in the reference.
+"""
+from __future__ import annotations
+
+import sys
+import time
+
+import numpy as np
+
+from .constants import eV, h
+from .engine import Engine
+from .setup_host import pack_lehamoc, read_parameter_file
+
+
+def run(param_sets, ic_path="R", snapshots=True, engine=None):
+    """Returns (batch, n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np]) as NumPy arrays; S = number of timesteps when
+    `snapshots` (the reference writes every step), else 1 (final state)."""
+    batch = pack_lehamoc(param_sets)
+    eng = engine or Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
+    eng.setup(batch)
+    S = int(batch.nsteps.max()) if snapshots else 0
+    N, sed, Npr = eng.run_lh(snapshots=S)
+    return batch, N.cpu().numpy(), sed.cpu().numpy(), Npr.cpu().numpy()
+
+
+def write_outputs(batch, N, sed, Npr, out_s, w=0):
+    """LeHaMoC.py:440-453: str(float) of log10 values, space separated, four files."""
+    nu_nu = np.logspace(10., 22., 50) * eV / h                                   # LeHaMoC.py:173
+    names = ["Pairs_Distribution" + out_s + ".txt", "Photons_Distribution" + out_s + ".txt",
+             "Protons_Distribution" + out_s + ".txt", "Neutrinos_Distribution" + out_s + ".txt"]
+    with np.errstate(divide="ignore"):
+        xs = [np.log10(batch.g_el[w]), np.log10(batch.nu_tot[w]), np.log10(batch.g_pr[w]), np.log10(nu_nu)]
+        files = [open(n, "w") for n in names]
+        try:
+            for s in range(int(batch.nsteps[w])):
+                ys = [np.log10(N[w, s]), np.log10(sed[w, s]), np.log10(Npr[w, s]), np.log10(np.zeros(50))]
+                for f, x, y in zip(files, xs, ys):
+                    for a, b in zip(x, y):
+                        f.write(str(a) + " " + str(b) + "\n")
+        finally:
+            for f in files:
+                f.close()
+    return names
+
+
+def main(argv=None):
+    argv = sys.argv if argv is None else argv
+    if len(argv) != 3:
+        print('incorrect parameters passed')
+        print('try something like this')
+        print('python -m lehamoc_b200.LeHaMoC Parameters.txt _fileName')
+        return 1
+    start_time = time.time()
+    batch, N, sed, Npr = run(read_parameter_file(argv[1]))
+    write_outputs(batch, N, sed, Npr, argv[2])
+    print("--- %s seconds ---" % "{:.2f}".format((time.time() - start_time)))
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -12,6 +12,7 @@
 #include "lhm_device.cuh"
 #include "lhm_step.cuh"
 #include "lhm_setup.cuh"
+#include "lhm_lh.cuh"
 #include "lhm_cor.cuh"
 #include "lhm_had.cuh"
 
@@ -35,6 +36,8 @@ struct RunArgs {
     const double2* ptab;    // IC pair table or null
     int ptab_shared;
     double* N_out;          // [W,(S),Ng] or null
+    double* Np_out;         // [W,(S),Np] or null (LeHaMoC.py driver)
+    int esc_pr;
     double* sed_out;        // [W,(S),Nt] or null
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
@@ -132,6 +135,75 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
                 for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// =================================================================================================
+// the LeHaMoC.py driver (leptonic processes + proton equation + proton synchrotron), lhm_lh.cuh
+// =================================================================================================
+__global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    SmemLh H;
+    carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+    // initial state (LeHaMoC.py:222-259): N_el = el_inj * Volume(R0), N_pr = 0, photons 1e-260
+    const double V0 = volume_of(C.R0);
+    for (int j = tid; j < Ng; j += NT) {
+        S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j] * V0;
+        S.qee[j] = 0.0;
+    }
+    for (int j = tid; j < Np; j += NT) H.Npr[j] = 0.0;
+    for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.aggS[k] = 0.0; H.QsynP[k] = 0.0; }
+    for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    ic_prepare<NT>(C, S);
+    double t = C.tinit;
+    for (int step = 0; step < nsteps; ++step) {
+        t += C.dt;                                               // LeHaMoC.py:268-272
+        C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.V = volume_of(C.Rad);
+        phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph_lh<NT>(C, S);
+        phase_protons<NT>(C, S, H, A.esc_pr);
+        phase_electrons_lh<NT>(C, S);
+        phase_vectors<NT>(C, S);
+        phase_syn_rows<NT>(C, S, false);
+        phase_syn_protons<NT>(C, S, H);
+        if (C.F.ic_e) {
+            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
+        }
+        __syncthreads();
+        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        phase_photon_solves_lh<NT>(C, S, H, cor);
+        if (C.F.gg) phase_gg_lh<NT>(C, S, H, step);
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && step == nsteps - 1)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT)
+                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            if (A.Np_out) {
+                double* o = A.Np_out + ((size_t)w * S_ + slot) * Np;
+                for (int j = tid; j < Np; j += NT) o[j] = H.Npr[j] / C.V;
             }
             __syncthreads();
         }
@@ -347,6 +419,8 @@ struct lhm_handle {
     double* d_cor;
     double* d_E;              // const-B exponential cache (cfg.const_B)
     double2* d_ptab;          // IC pair table (cfg.ic_pair_table)
+    const double* g_pr;       // driver 1: proton grid / injection of the next batch (caller-owned)
+    const double* pr_inj;
     const double* consts;     // device pointers of the current batch (caller- or staging-owned)
     const double* g_el;
     // staging for the *_host entry points
@@ -415,17 +489,21 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     h->cfg = *cfg;
     h->device = device;
     h->stream = (cudaStream_t)cuda_stream;
-    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts);
+    if (cfg->driver != 0 && cfg->driver != 1) return LHM_ERR_ARG;
+    if (cfg->driver == 1 && cfg->Np < 4) return LHM_ERR_ARG;
+    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts, cfg->driver == 1 ? cfg->Np : 0);
     StepFlags& F = h->F;
     F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
     F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
     F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
     h->smem = smem_bytes(h->L, NW);
+    if (cfg->driver == 1) h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
     PhysConst pc = make_consts();
     CUDA_TRY(cudaMemcpyToSymbol(kPC, &pc, sizeof(pc)));
     CUDA_TRY(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CUDA_TRY(cudaFuncSetAttribute(unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CUDA_TRY(cudaFuncSetAttribute(run_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CUDA_TRY(cudaFuncSetAttribute(cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cor_smem_bytes(cfg->Ng)));
     const size_t W = cfg->max_walkers;
     CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
@@ -467,6 +545,11 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
     A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
+    A.g_pr = nullptr; A.pr_inj = nullptr;
+    if (h->cfg.driver == 1) {
+        if (!h->g_pr || !h->pr_inj) return LHM_ERR_STATE;
+        A.g_pr = h->g_pr; A.pr_inj = h->pr_inj;
+    }
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
@@ -491,8 +574,28 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
     return LHM_OK;
 }
 
+static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots, bool lh);
+
+int lhm_set_protons(lhm_handle* h, const double* g_pr, const double* pr_inj) {
+    if (!h || !g_pr || !pr_inj) return LHM_ERR_ARG;
+    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    h->g_pr = g_pr; h->pr_inj = pr_inj;
+    return LHM_OK;
+}
+
+int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots) {
+    if (!h || snapshots < 0) return LHM_ERR_ARG;
+    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    return run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
+}
+
 int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
+    if (h->cfg.driver != 0) return LHM_ERR_STATE;
+    return run_common(h, N_el_out, nuLnu_out, nullptr, snapshots, false);
+}
+
+static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots, bool lh) {
     if (h->W < 1) return LHM_ERR_STATE;
     CUDA_TRY(cudaSetDevice(h->device));
     const double* cor = nullptr;
@@ -504,11 +607,13 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     RunArgs A;
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
+    A.Np_out = N_pr_out; A.esc_pr = h->cfg.esc_flag_pr;
     A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-    run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    if (lh) run_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    else run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));

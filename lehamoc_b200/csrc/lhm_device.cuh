@@ -38,6 +38,7 @@ constexpr int IC_NW = 8;               // warps of the walker CTA the static til
 // ---- per-walker table layout (offsets in doubles / ints from the walker's base) ------------------
 struct Layout {
     int Ng, Ns, Ni, Nt, NP;
+    int Np;                         // proton grid of the LeHaMoC.py driver (0: leptonic drivers)
     // double tables
     int g, lg, wg, wgi, g13, inv4g, sm, sp, am, ap, elinj, u_xT, u_dx, u_Dx, q_dx, q_Dx;   // Ng each
     int nsyn, lsyn, nm23s, nm53s, asm_, asp_;                                              // Ns each
@@ -47,6 +48,11 @@ struct Layout {
     int qee_a, qee_d;               // Ng: same for Q_ee_f
     int agg_c, agg_r2;              // Ni: 0.652 sigmaT/x_IC and 10**(-2 step): the sample kernel is rebuilt from these
     int qee_c, qee_r2;              // Ng: 2.61/(2 gamma) and 10**(-2 step)
+    // LeHaMoC.py driver only (Np > 0)
+    int gp, lgp, wgp, g13p, spm, spp, prinj;        // Np: proton grid, ln, trapz weights, g^(1/3), loss stencils, injection
+    int ags_a, ags_d, ags_c, ags_r2;                // Ns: a_gg resample grid on nu_syn (LeHaMoC.py:415)
+    int agt_a, agt_d, agt_c, agt_r2;                // Nt: a_gg resample grid on nu_tot (LeHaMoC.py:416)
+    int uv_d;                                       // Ng: step (log10) of U_ph_f's 50-point resample (LeHaMoC_f.py:177)
     int n_doubles;
     // int tables
     int ps_j, pi_j;                 // Nt
@@ -60,12 +66,14 @@ struct Layout {
     int ic_tb;                      // IC_NW+1: tile range of every warp
     int ic_cand;                    // 2*ic_maxT scratch
 
+    int jm_p;                       // Ns: first proton index that may emit at nu_syn[k] (Q_syn_space mask, m = m_pr)
+    int uv_on;                      // Ng: 1 if nu_T < nu_target[-1] (LeHaMoC_f.py:176)
     int n_ints;
 };
 
-inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
+inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP, int Np = 0) {
     Layout L;
-    L.Ng = Ng; L.Ns = Ns; L.Ni = Ni; L.Nt = Nt; L.NP = NP;
+    L.Ng = Ng; L.Ns = Ns; L.Ni = Ni; L.Nt = Nt; L.NP = NP; L.Np = Np;
     int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };   // keep 16-byte alignment
     L.g = take(Ng); L.lg = take(Ng); L.wg = take(Ng); L.wgi = take(Ng); L.g13 = take(Ng);
@@ -81,6 +89,12 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
     L.ps_Dx = take(Nt); L.pi_dx = take(Nt); L.pi_Dx = take(Nt);
     L.agg_a = take(Ni); L.agg_d = take(Ni); L.qee_a = take(Ng); L.qee_d = take(Ng);
     L.agg_c = take(Ni); L.agg_r2 = take(Ni); L.qee_c = take(Ng); L.qee_r2 = take(Ng);
+    const int np_ = Np > 0 ? Np : 0, nsl = Np > 0 ? Ns : 0, ntl = Np > 0 ? Nt : 0, ngl = Np > 0 ? Ng : 0;
+    L.gp = take(np_); L.lgp = take(np_); L.wgp = take(np_); L.g13p = take(np_); L.spm = take(np_); L.spp = take(np_);
+    L.prinj = take(np_);
+    L.ags_a = take(nsl); L.ags_d = take(nsl); L.ags_c = take(nsl); L.ags_r2 = take(nsl);
+    L.agt_a = take(ntl); L.agt_d = take(ntl); L.agt_c = take(ntl); L.agt_r2 = take(ntl);
+    L.uv_d = take(ngl);
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
@@ -88,6 +102,7 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP) {
     L.ic_maxT = ((Ni - 1 + IC_OG - 1) / IC_OG) * ((Ng + IC_GB - 1) / IC_GB);
     L.ic_nt = take(2); L.ic_task = take(L.ic_maxT); L.ic_i0 = take(L.ic_maxT); L.ic_i1 = take(L.ic_maxT);
     L.ic_tb = take(IC_NW + 1); L.ic_cand = take(2 * L.ic_maxT);
+    L.jm_p = take(Np > 0 ? Ns : 0); L.uv_on = take(Np > 0 ? Ng : 0);
     L.n_ints = o;
     return L;
 }

@@ -1,0 +1,328 @@
+// lhm_lh.cuh -- the `LeHaMoC Code and Tests/LeHaMoC.py` driver (BASELINE configs 3 and 5) on top of the leptonic phases:
+// electron AND proton equations, proton synchrotron, the f_had variants of U_ph_f (50-point resample, LeHaMoC_f.py:171-182),
+// a_gg on the nu_ic, nu_syn and nu_tot grids (100 samples, :145-155; LeHaMoC.py:414-416), the gamma-gamma pre-attenuation
+// of the first two steps (LeHaMoC.py:418-426) and Q_ee_f (100 samples, full length, :158-168).  One CTA per walker, all
+// timesteps in one launch, state in shared memory.  The photo-hadronic source and loss terms (lhm_had.cuh) are not wired
+// in yet: this kernel covers runs with the hadronic flags off (leptonic processes + proton synchrotron).
+#pragma once
+#include "lhm_step.cuh"
+
+namespace lhm {
+
+// ---- set-up additions (called from setup_kernel when the layout has a proton grid) ------------------------------------
+struct LhSetup {
+    const double* g_pr;     // [W, Np]
+    const double* pr_inj;   // [W, Np]  dN/(dV dgamma dt)
+};
+
+template <int NT>
+__device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const double* gp, const double* prinj,
+                                const double* ns, const double* nt) {
+    const int tid = threadIdx.x, Np = L.Np, Ns = L.Ns, Nt = L.Nt, Ng = L.Ng, NP = L.NP;
+    const PhysConst& pc = kPC;
+    const double m_pr = 1.67262192369e-24;
+    for (int j = tid; j < Np; j += NT) {
+        const double g = gp[j];
+        T[L.gp + j] = g;
+        T[L.lgp + j] = log(g);
+        T[L.g13p + j] = pow(g, 1.0 / 3.0);
+        T[L.prinj + j] = prinj[j];
+        if (j < Np - 2) {                                   // g_pr_mp / dg_pr, LeHaMoC.py:149-150 (negative-index wrap at 0)
+            const double mp0 = (gp[j + 1] + gp[(j == 0) ? (Np - 1) : (j - 1)]) / 2.0;
+            const double mp1 = (gp[j + 2] + gp[j]) / 2.0;
+            const double dg = (gp[j + 2] - gp[j]) / 2.0;
+            T[L.spm + j] = (mp0 * mp0 - 1.0) / dg;          // LeHaMoC.py:296-297
+            T[L.spp + j] = (mp1 * mp1 - 1.0) / dg;
+        } else {
+            T[L.spm + j] = T[L.spp + j] = 0.0;
+        }
+    }
+    __syncthreads();
+    for (int j = tid; j < Np; j += NT) T[L.wgp + j] = trapz_w(T + L.lgp, j, Np);
+    for (int k = tid; k < Ns; k += NT) {                    // Q_syn_space mask m_pr*c**2*g < h*nu: a prefix in gamma
+        int lo = 0, hi = Np;
+        const double hn = pc.h * ns[k];
+        const double mpc2 = m_pr * pc.c * pc.c;
+        while (lo < hi) { int mid = (lo + hi) >> 1; if (mpc2 * gp[mid] < hn) lo = mid + 1; else hi = mid; }
+        TI[L.jm_p + k] = lo;
+    }
+    // a_gg resample grids on nu_syn and nu_tot (same four numbers per row as for nu_ic, see setup_kernel)
+    const double xmax_l = T[L.lxt + Nt - 1];
+    for (int e = tid; e < Ns + Nt; e += NT) {
+        const bool on_syn = e < Ns;
+        const int k = on_syn ? e : e - Ns;
+        const double x = pc.h * (on_syn ? ns[k] : nt[k]) / pc.mc2;
+        const double a = log10(1.3 / x);
+        const double step = (xmax_l - a) / (double)(NP - 1);
+        const bool on = logspace_pt(a, xmax_l, 0, NP) < logspace_pt(a, xmax_l, 1, NP);
+        const int oa = on_syn ? L.ags_a : L.agt_a, od = on_syn ? L.ags_d : L.agt_d, oc = on_syn ? L.ags_c : L.agt_c,
+                  orr = on_syn ? L.ags_r2 : L.agt_r2;
+        T[oa + k] = a; T[od + k] = on ? step : 0.0; T[oc + k] = pc.gg_pref / x; T[orr + k] = exp10(-2.0 * step);
+    }
+    // U_ph_f: nu_temp = np.logspace(log10(nu_target[0]), log10(nu_T), 50)  (LeHaMoC_f.py:175-177)
+    for (int j = tid; j < Ng; j += NT) {
+        const double nuT = pc.nuT_num / (4.0 * pc.h * T[L.g + j]);
+        const bool on = nuT < nt[Nt - 1];
+        TI[L.uv_on + j] = on ? 1 : 0;
+        T[L.uv_d + j] = (log10(nuT) - log10(nt[0])) / 49.0;
+    }
+}
+
+// ---- shared memory of the LH kernel: the leptonic carve-up + proton state and the extra gamma-gamma vectors -------------
+struct SmemLh {
+    double *Npr, *up, *inucp;          // [Np] proton number, weight x n_p x g^(1/3), 1/(a_cr_pr g^2)
+    double *QsynP;                     // [Ns] proton synchrotron emissivity
+    double *aggS, *aggSN;              // [Ns] a_gg on nu_syn: used by the current solve / computed for the next
+    double *atmp;                      // [Nt] a_gg on nu_tot
+    double *Lm2, *Ln2;                 // [Nt] log2 / log10 of the field Q_ee_f integrates (attenuated in the first two steps)
+};
+__host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
+    return (size_t)3 * pad2(L.Np) + 3 * pad2(L.Ns) + 3 * pad2(L.Nt);
+}
+__device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L) {
+    auto take = [&](int n) { double* r = p; p += n; return r; };
+    H.Npr = take(pad2(L.Np)); H.up = take(pad2(L.Np)); H.inucp = take(pad2(L.Np));
+    H.QsynP = take(pad2(L.Ns)); H.aggS = take(pad2(L.Ns)); H.aggSN = take(pad2(L.Ns));
+    H.atmp = take(pad2(L.Nt)); H.Lm2 = take(pad2(L.Nt)); H.Ln2 = take(pad2(L.Nt));
+}
+
+// U_ph_f, LeHaMoC_f.py:171-182: per gamma a 50-point log resample of the photon field up to nu_T, linear-x trapezoid.
+// pre*K = (mc^2)^2/h, so with x = h nu/mc^2:  U = mc^2 * trapz(x * (n mc^2/h), x);  n mc^2/h = 2^Lm.
+template <int NT>
+__device__ void phase_uph_lh(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int Nt = L.Nt, Ng = L.Ng;
+    const double* __restrict__ lxt = S.lxtS;
+    const double* __restrict__ ilx = S.ilxS;
+    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
+    const double invD = (double)(Nt - 1) / (lxN - lx0);
+    const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;
+    const double pre = kPC.mc2 / (kPC.sigmaT * C.Rad);
+    for (int j = threadIdx.x; j < Ng; j += NT) {
+        double U;
+        if (C.TI[L.uv_on + j]) {
+            const double step = __ldg(C.T + L.uv_d + j);
+            const double rr = exp10(step);                          // ratio of consecutive abscissae
+            double acc[GG_U];
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
+            double xs[GG_U];                                        // x of sample e0+u
+            const double x0 = exp10(lx0);
+            xs[0] = x0;
+#pragma unroll
+            for (int u = 1; u < GG_U; ++u) xs[u] = xs[u - 1] * rr;
+            double rU = rr;
+#pragma unroll
+            for (int u = 1; u < GG_U; ++u) rU *= rr;
+            const double irr = 1.0 / rr;
+            for (int e0 = 0; e0 < 50; e0 += GG_U) {
+                double y[GG_U], wv[GG_U], t[GG_U], Lv[GG_U];
+                int jb[GG_U];
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    const int e = e0 + u;
+                    y[u] = fma((double)min(e, 49), step, lx0);
+                    // np.trapz(f, x): weight of node e = (x_{e+1} - x_{e-1})/2 (one-sided at the ends)
+                    const double xm = (e > 0) ? xs[u] * irr : xs[u], xp = (e < 49) ? xs[u] * rr : xs[u];
+                    wv[u] = (e < 50) ? 0.5 * (xp - xm) * xs[u] : 0.0;
+                    xs[u] *= rU;
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    int jj = (int)((y[u] - lx0) * invD);
+                    jj = max(0, min(jj, Nt - 2));
+                    while (jj > 0 && y[u] < lxt[jj]) --jj;
+                    while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                    jb[u] = jj;
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    t[u] = (y[u] - lxt[jb[u]]) * ilx[jb[u]];
+                    if (y[u] <= lx0) t[u] = 0.0;
+                    if (y[u] >= lxN) t[u] = 1.0;
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    const double f0 = S.Lm[jb[u]], f1 = S.Lm[jb[u] + 1];
+                    Lv[u] = fma(t[u], f1 - f0, f0);
+                }
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) acc[u] = fma(wv[u], fast_exp2(Lv[u], S.e2tab), acc[u]);
+            }
+            double s = acc[0];
+#pragma unroll
+            for (int u = 1; u < GG_U; ++u) s += acc[u];
+            U = kPC.mc2 * s;
+        } else {                                                    // U_ph_tot, LeHaMoC_f.py:173
+            double s = 0.0;
+            for (int i = 0; i < Nt - 2; ++i) {
+                const double y0 = C.T[L.nt + i] * S.n[i] * K, y1 = C.T[L.nt + i + 1] * S.n[i + 1] * K;
+                s += (C.T[L.nt + i + 1] - C.T[L.nt + i]) * (y1 + y0) / 2.0;
+            }
+            U = pre * s;
+        }
+        S.bcom[j] = 4.0 / 3.0 * kPC.sigmaT * (kPC.c * U) / kPC.mc2;      // LeHaMoC.py:304
+    }
+    __syncthreads();
+}
+
+// proton equation (LeHaMoC.py:330-335 with the hadronic loss terms off): synchrotron cooling + escape + injection
+template <int NT>
+__device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, n = L.Np - 2;
+    const double m_el = 9.1093837015e-28, m_pr = 1.67262192369e-24;
+    const double rm = m_el / m_pr;
+    const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (rm * rm * rm) * (C.B * C.B) : 0.0;      // const_pr * M_F**2
+    const double esc = kPC.c / C.Rad * (double)esc_pr;
+    for (int j = tid; j < n; j += NT) {
+        const double V2 = 1.0 + C.dt * (esc + b_syn * C.T[L.spm + j]);
+        const double V3 = -C.dt * (b_syn * C.T[L.spp + j]);
+        const double d = H.Npr[j + 1] + (C.T[L.prinj + j + 1] * C.dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (tid < 32) backsub_warp(S.cp, S.dp, H.Npr + 1, n);
+    __syncthreads();
+}
+
+// electron equation, LeHaMoC.py:359-367 (injection per volume; Q_ee aligned with the interior points)
+template <int NT>
+__device__ void phase_electrons_lh(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, n = L.Ng - 2;
+    const double dt = C.dt;
+    const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
+    const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (C.B * C.B) : 0.0;
+    const double esc = kPC.c / C.Rad * (double)C.F.esc;
+    for (int j = tid; j < n; j += NT) {
+        const double smj = C.T[L.sm + j], spj = C.T[L.sp + j];
+        double ic_m = 0.0, ic_p = 0.0;
+        if (C.F.ic_l) { ic_m = S.bcom[j + 1] * smj; ic_p = S.bcom[j + 2] * spj; }
+        const double V2 = 1.0 + dt * (esc + b_syn * smj + ic_m + b_ad * C.T[L.am + j]);
+        const double V3 = -dt * (b_syn * spj + ic_p + b_ad * C.T[L.ap + j]);
+        double src = S.qee[j + 1];
+        if (C.F.inj) src += C.T[L.elinj + j + 1];
+        const double d = S.N[j + 1] + (src * dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (tid < 32) backsub_warp(S.cp, S.dp, S.N + 1, n);
+    __syncthreads();
+}
+
+// proton synchrotron emissivity Q_syn_space(dN_pr, M_F, nu, a_cr_pr, C_syn_pr, g_pr, m_pr), LeHaMoC.py:372
+template <int NT>
+__device__ void phase_syn_protons(const Ctx& C, Smem& S, SmemLh& H) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, Np = L.Np, Ns = L.Ns;
+    const double m_el = 9.1093837015e-28, m_pr = 1.67262192369e-24;
+    const double a_cr_pr = kPC.acr_pref * (m_el / m_pr) * C.B;                 // 3 q B/(4 pi m_pr c)
+    for (int j = tid; j < Np; j += NT) {
+        const double g = C.T[L.gp + j];
+        H.inucp[j] = 1.0 / (a_cr_pr * (g * g));
+        H.up[j] = C.T[L.wgp + j] * ((H.Npr[j] / C.V) * C.T[L.g13p + j]);
+    }
+    __syncthreads();
+    const double C_syn_pr = kPC.C_syn * pow(m_pr / m_el, 4.0 / 3.0) * ((m_el / m_pr) * (m_el / m_pr));
+    const double qpref = C_syn_pr * pow(C.B, 2.0 / 3.0);
+    for (int k = tid; k < Ns; k += NT) {
+        double s0 = 0.0, s1 = 0.0;
+        if (C.F.syn_e && k >= 1 && k <= Ns - 2) {
+            const double nu = C.T[L.nsyn + k];
+            const int jm = C.TI[L.jm_p + k];
+            for (int j0 = 0; j0 < Np; j0 += 4) {
+                double x[4], Ev[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) x[u] = nu * H.inucp[min(j0 + u, Np - 1)];
+                fast_exp_neg<4>(x, Ev, S.e2tab);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int j = j0 + u;
+                    if (j < Np && j >= jm) { if (u & 1) s1 = fma(Ev[u], H.up[j], s1); else s0 = fma(Ev[u], H.up[j], s0); }
+                }
+            }
+        }
+        H.QsynP[k] = qpref * C.T[L.nm23s + k] * (s0 + s1);
+    }
+    __syncthreads();
+}
+
+// photon equations, LeHaMoC.py:397-407: as the leptonic ones plus gamma-gamma absorption on the synchrotron grid and
+// the proton synchrotron source
+template <int NT>
+__device__ void phase_photon_solves_lh(const Ctx& C, Smem& S, SmemLh& H, double cor) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    const double dt = C.dt, cc = kPC.c;
+    const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
+    const double esc = cc / C.Rad;
+    const int ns = L.Ns - 2, ni = L.Ni - 2;
+    for (int j = tid; j < ns; j += NT) {
+        const double aS = C.F.ssa ? -fabs(S.aS[j + 1]) : 0.0;
+        const double V2 = 1.0 + dt * (esc + b_ad * C.T[L.asm_ + j] - aS * cc + H.aggS[j + 1] * cc);
+        const double V3 = -dt * (b_ad * C.T[L.asp_ + j]);
+        const double Q = C.F.syn_e ? (S.Qsyn[j + 1] / cor + H.QsynP[j + 1]) : 0.0;
+        const double d = S.psyn[j + 1] + 4.0 * M_PI * Q * dt * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.psyn + 1, ns); }
+    else { for (int j = tid; j < ns; j += NT) S.psyn[j + 1] = S.dp[j]; }
+    __syncthreads();
+    for (int j = tid; j < ni; j += NT) {
+        const double aI = C.F.ssa ? -fabs(S.aI[j + 1]) : 0.0;
+        const double V2 = 1.0 + dt * (esc + b_ad * C.T[L.aim + j] - aI * cc + S.agg[j + 1] * cc);
+        const double V3 = -dt * (b_ad * C.T[L.aip + j]);
+        const double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
+        const double d = S.pic[j + 1] + (Q * dt) * C.V;
+        S.cp[j] = V3 / V2;
+        S.dp[j] = d / V2;
+    }
+    __syncthreads();
+    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.pic + 1, ni); }
+    else { for (int j = tid; j < ni; j += NT) S.pic[j + 1] = S.dp[j]; }
+    __syncthreads();
+}
+
+// gamma-gamma block, LeHaMoC.py:409-428: a_gg on three grids from the photon field of the top of the step; in the first
+// two steps the field Q_ee_f integrates is attenuated by one implicit absorption step first.
+template <int NT>
+__device__ void phase_gg_lh(const Ctx& C, Smem& S, SmemLh& H, int interv) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, NP = L.NP, Ni = L.Ni, Ns = L.Ns, Nt = L.Nt, Ng = L.Ng;
+    const int nrows = Ni + Ns + Nt;
+    for (int row = tid; row < nrows; row += NT) {
+        int r, oa, od, oc, orr; double* out;
+        if (row < Ni) { r = row; oa = L.agg_a; od = L.agg_d; oc = L.agg_c; orr = L.agg_r2; out = S.agg; }
+        else if (row < Ni + Ns) { r = row - Ni; oa = L.ags_a; od = L.ags_d; oc = L.ags_c; orr = L.ags_r2; out = H.aggS; }
+        else { r = row - Ni - Ns; oa = L.agt_a; od = L.agt_d; oc = L.agt_c; orr = L.agt_r2; out = H.atmp; }
+        out[r] = gg_row_sum(S, S.Lm, Nt, NP, __ldg(C.T + oa + r), __ldg(C.T + od + r), __ldg(C.T + oc + r),
+                            __ldg(C.T + orr + r), true);
+    }
+    __syncthreads();
+    for (int k = tid; k < Nt; k += NT) {
+        double nk = S.n[k];
+        if (interv < 2 && k >= 1 && k <= Nt - 2) {              // thomas() of the diagonal system LeHaMoC.py:419-425
+            const double pt = nk * C.V;
+            nk = (pt / (1.0 + C.dt * (H.atmp[k] * kPC.c))) / C.V;
+        }
+        H.Lm2[k] = log2(nk * kPC.mc2_h);
+        H.Ln2[k] = log10(nk);
+    }
+    __syncthreads();
+    for (int r = tid; r < Ng; r += NT) {                            // Q_ee_f, full length; the driver uses [1:-1]
+        const double s = gg_row_sum(S, H.Lm2, Nt, NP, __ldg(C.T + L.qee_a + r), __ldg(C.T + L.qee_d + r),
+                                    __ldg(C.T + L.qee_c + r), __ldg(C.T + L.qee_r2 + r), false);
+        double ng = 0.0;
+        if (2.0 * S.gS[r] > 1.0)
+            ng = exp10(interp_eval(H.Ln2, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
+        S.qee[r] = kPC.qee_pref * (ng * s);
+    }
+    __syncthreads();
+}
+
+}  // namespace lhm

@@ -25,6 +25,8 @@ struct SetupArgs {
     int* tabi;              // [W, L.n_ints]
     double2* ptab;          // IC pair table [W or 1, ic_maxT*IC_PT*2*32] or null
     int ptab_shared;        // 1: every walker has the same g_el / nu_ic / nu_tot, one table (walker 0 builds it)
+    const double* g_pr;     // [W, Np] or null: proton grid / injection of the LeHaMoC.py driver
+    const double* pr_inj;   // [W, Np]
 };
 
 // log-spaced resample grid of a_gg / Q_ee_f: np.logspace(a, b, NP)[s] = 10**(a + s*step), last = 10**b
@@ -33,6 +35,10 @@ __device__ __forceinline__ double logspace_pt(double a, double b, int s, int NP)
     double y = (s == NP - 1) ? b : (a + (double)s * step);
     return exp10(y);
 }
+
+template <int NT>
+__device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const double* gp, const double* prinj,
+                                const double* ns, const double* nt);
 
 template <int NT>
 __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
@@ -307,6 +313,10 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
         T[L.qee_d + j] = (2.0 * gj > 1.0) ? step : 0.0;         // `if (2.*g_e) > 1.` else 0
         T[L.qee_c + j] = 2.61 / (2.0 * gj);
         T[L.qee_r2 + j] = exp10(-2.0 * step);
+    }
+    if (L.Np > 0 && A.g_pr) {
+        __syncthreads();
+        setup_lh_tables<NT>(L, T, TI, A.g_pr + (size_t)w * L.Np, A.pr_inj + (size_t)w * L.Np, ns, nt);
     }
 }
 

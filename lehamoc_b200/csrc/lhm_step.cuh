@@ -690,18 +690,73 @@ __device__ __forceinline__ double fast_exp2(double x, const double* __restrict__
 // `Lng` gives n_g: log10 of the field Q_ee_f's n_g is interpolated from.
 constexpr int GG_U = 4;
 
+// one row: sum_k w_k * cf * (1 - s_k^-2) * ln s_k * 2^(interp of Lm at y_k),  y_k = a + k*step, k = 0..NP-1
+__device__ __forceinline__ double gg_row_sum(const Smem& S, const double* __restrict__ Lm, int Nt, int NP, double a,
+                                             double step, double cf, double r2, bool is_a) {
+    const double* __restrict__ lxt = S.lxtS;
+    const double* __restrict__ ilx = S.ilxS;
+    const double* __restrict__ tab = S.e2tab;
+    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
+    const double invD = (double)(Nt - 1) / (lxN - lx0);
+    const double LN10 = 2.302585092994045684, LN13 = 0.262364264467491052;     // ln 10, ln 1.3
+    double acc[GG_U];
+#pragma unroll
+    for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
+    if (step > 0.0) {                       // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
+        const double dl = step * LN10;                      // spacing of ln x' = trapezoid weight of inner samples
+        const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
+        double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
+        inv[0] = is_a ? (1.0 / 1.69) : 1.0;
+#pragma unroll
+        for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
+        double rU = r2;
+#pragma unroll
+        for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
+        for (int e0 = 0; e0 < NP; e0 += GG_U) {
+            double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
+            int j[GG_U];
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) {
+                const int e = e0 + u;
+                const double ed = (double)e;
+                y[u] = (e >= NP - 1) ? lxN : fma(ed, step, a);
+                const double wgt = (e == 0 || e == NP - 1) ? 0.5 * dl : ((e < NP) ? dl : 0.0);
+                Kv[u] = wgt * cf * (1.0 - inv[u]) * fma(ed, dl, lns0);
+                inv[u] *= rU;
+            }
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) {
+                int jj = (int)((y[u] - lx0) * invD);
+                jj = max(0, min(jj, Nt - 2));
+                while (jj > 0 && y[u] < lxt[jj]) --jj;
+                while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                j[u] = jj;
+            }
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) {
+                t[u] = (y[u] - lxt[j[u]]) * ilx[j[u]];
+                if (y[u] <= lx0) t[u] = 0.0;                // np.interp clamps below the grid
+            }
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) {
+                const double f0 = Lm[j[u]], f1 = Lm[j[u] + 1];
+                Lv[u] = fma(t[u], f1 - f0, f0);             // NaN (from -inf ordinates) -> 0 inside fast_exp2
+            }
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) acc[u] = fma(Kv[u], fast_exp2(Lv[u], tab), acc[u]);
+        }
+    }
+    double s = acc[0];
+#pragma unroll
+    for (int u = 1; u < GG_U; ++u) s += acc[u];
+    return s;
+}
+
 template <int NT>
 __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_out, double* qee_out) {
     const Layout& L = C.L;
     const int NP = L.NP, Ni = L.Ni, Ng = L.Ng, Nt = L.Nt;
     const int nrows = Ni + (Ng - 1);
-    const double* __restrict__ lxt = S.lxtS;
-    const double* __restrict__ ilx = S.ilxS;
-    const double* __restrict__ Lm = S.Lm;
-    const double* __restrict__ tab = S.e2tab;
-    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
-    const double invD = (double)(Nt - 1) / (lxN - lx0);
-    const double LN10 = 2.302585092994045684, LN13 = 0.262364264467491052;     // ln 10, ln 1.3
     for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
@@ -709,56 +764,7 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
         const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
         const double cf = __ldg(C.T + (is_a ? L.agg_c : L.qee_c) + r);
         const double r2 = __ldg(C.T + (is_a ? L.agg_r2 : L.qee_r2) + r);
-        double acc[GG_U];
-#pragma unroll
-        for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
-        if (step > 0.0) {                       // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
-            const double dl = step * LN10;                      // spacing of ln x' = trapezoid weight of inner samples
-            const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
-            double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
-            inv[0] = is_a ? (1.0 / 1.69) : 1.0;
-#pragma unroll
-            for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
-            double rU = r2;
-#pragma unroll
-            for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
-            for (int e0 = 0; e0 < NP; e0 += GG_U) {
-                double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
-                int j[GG_U];
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) {
-                    const int e = e0 + u;
-                    const double ed = (double)e;
-                    y[u] = (e >= NP - 1) ? lxN : fma(ed, step, a);
-                    const double wgt = (e == 0 || e == NP - 1) ? 0.5 * dl : ((e < NP) ? dl : 0.0);
-                    Kv[u] = wgt * cf * (1.0 - inv[u]) * fma(ed, dl, lns0);
-                    inv[u] *= rU;
-                }
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) {
-                    int jj = (int)((y[u] - lx0) * invD);
-                    jj = max(0, min(jj, Nt - 2));
-                    while (jj > 0 && y[u] < lxt[jj]) --jj;
-                    while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
-                    j[u] = jj;
-                }
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) {
-                    t[u] = (y[u] - lxt[j[u]]) * ilx[j[u]];
-                    if (y[u] <= lx0) t[u] = 0.0;                // np.interp clamps below the grid
-                }
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) {
-                    const double f0 = Lm[j[u]], f1 = Lm[j[u] + 1];
-                    Lv[u] = fma(t[u], f1 - f0, f0);             // NaN (from -inf ordinates) -> 0 inside fast_exp2
-                }
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) acc[u] = fma(Kv[u], fast_exp2(Lv[u], tab), acc[u]);
-            }
-        }
-        double s = acc[0];
-#pragma unroll
-        for (int u = 1; u < GG_U; ++u) s += acc[u];
+        const double s = gg_row_sum(S, S.Lm, Nt, NP, a, step, cf, r2, is_a);
         if (is_a) agg_out[r] = s;
         else {
             double ng = 0.0;

@@ -96,6 +96,9 @@ class Engine:
         W = batch.W
         self._check_shared(batch)
         dev = [self._dev(a) for a in batch.arrays()]
+        if self.cfg.get("driver", 0) == 1:
+            self._keep_pr = (self._dev(batch.g_pr), self._dev(batch.pr_inj))
+            check(self.lib.lhm_set_protons(self.h, _ptr(self._keep_pr[0]), _ptr(self._keep_pr[1])), "lhm_set_protons")
         self.setup_device(W, *dev)
 
     def _check_shared(self, batch):
@@ -122,6 +125,15 @@ class Engine:
             N = N[:, 0] if N is not None else None
             sed = sed[:, 0] if sed is not None else None
         return N, sed
+
+    def run_lh(self, snapshots: int = 0):
+        """Driver 1 (LeHaMoC.py): returns (n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np]) device tensors."""
+        S = snapshots if snapshots > 0 else 1
+        N = self._new(self.W, S, self.Ng)
+        sed = self._new(self.W, S, self.Nt)
+        Npr = self._new(self.W, S, self.cfg["Np"])
+        check(self.lib.lhm_run_batch_lh(self.h, _ptr(N), _ptr(sed), _ptr(Npr), int(snapshots)), "lhm_run_batch_lh")
+        return N, sed, Npr
 
     def run_into(self, N, sed, snapshots: int = 0):
         check(self.lib.lhm_run_batch(self.h, _ptr(N), _ptr(sed), int(snapshots)), "lhm_run_batch")

@@ -63,6 +63,8 @@ class Batch:
     nsteps: np.ndarray             # [W] int
     index_PL_min: np.ndarray = field(default=None)
     index_PL_max: np.ndarray = field(default=None)
+    g_pr: np.ndarray = field(default=None)         # [W, Np]   LeHaMoC.py driver only
+    pr_inj: np.ndarray = field(default=None)       # [W, Np]
 
     @property
     def W(self):
@@ -212,7 +214,7 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
                loss_minus_one=1 if variant == "script" else 0,       # LeMoC.py:224 vs Code.py:210
                qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
                const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
-               ic_pair_table=1,
+               ic_pair_table=1, driver=0, Np=0, esc_flag_pr=0,
                # fixed-grid sweeps (every walker has the same g_el / nu_ic / nu_tot): one IC pair table per batch
                shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))))
     for k in FLAG_KEYS:
@@ -221,6 +223,135 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
     cont = np.ascontiguousarray
     return Batch(variant, cfg, cont(consts), cont(g_el), cont(nu_syn), cont(nu_ic), cont(nu_tot), cont(el_inj),
                  cont(ext), nsteps, index_PL_min, index_PL_max)
+
+
+LH_KEYS = ("time_init", "time_end", "step_alg", "PL_inj", "g_min_el", "g_max_el", "g_el_PL_min", "g_el_PL_max",
+           "grid_g_el", "g_min_pr", "g_max_pr", "g_pr_PL_min", "g_pr_PL_max", "grid_g_pr", "grid_nu", "p_el", "L_el",
+           "p_pr", "L_pr", "Vexp", "R0", "B0", "m", "delta", "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag",
+           "IC_l_flag", "IC_emis_flag", "SSA_l_flag", "gg_flag", "pg_pi_l_flag", "pg_pi_emis_flag", "pg_BH_l_flag",
+           "pg_BH_emis_flag", "n_H", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
+           "neutrino_flag", "esc_flag_el", "esc_flag_pr", "BB_flag", "temperature", "GB_ext", "PL_flag", "dE_dV_ph",
+           "nu_min_ph", "nu_max_ph", "s_ph", "User_ph")
+HADRONIC_FLAGS = ("pg_pi_l_flag", "pg_pi_emis_flag", "pg_BH_l_flag", "pg_BH_emis_flag", "pp_l_flag", "pp_ee_emis_flag",
+                  "pp_g_emis_flag", "pp_nu_emis_flag")
+m_pr_ = 1.67262192369e-24
+
+
+def _Q_norm_exp_c(R0, comp, g, g_max_ind, p_i):          # LeHaMoC_f.py:81-82
+    return 4. * np.pi * R0 * c * comp / (sigmaT * np.trapz(g[:g_max_ind] ** (-p_i + 2.) * np.exp(-g[:g_max_ind] / g[g_max_ind]),
+                                                            np.log(g[:g_max_ind])))
+
+
+def _Q_pr_Lum(L_pr, p_pr, g_min_pr, g_max_pr):           # LeHaMoC_f.py:75-79
+    if p_pr == 2.:
+        return L_pr / (m_pr_ * c ** 2. * np.log(g_max_pr / g_min_pr))
+    return L_pr * (-p_pr + 2.) / (m_pr_ * c ** 2. * (g_max_pr ** (-p_pr + 2.) - g_min_pr ** (-p_pr + 2.)))
+
+
+def pack_lehamoc(param_sets) -> Batch:
+    """Batch for the `LeHaMoC Code and Tests/LeHaMoC.py` driver (one dict or a list of dicts with the 53 keys of its
+    Parameters.txt).  Set-up with the reference's own expressions, LeHaMoC.py:132-259, one walker at a time (this
+    driver is not on the headline path; the loop costs ~50 us per walker).  Only runs with the hadronic flags off are
+    supported so far (leptonic processes + proton equation + proton synchrotron)."""
+    from ._lib import LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B
+    if isinstance(param_sets, dict):
+        param_sets = [param_sets]
+    F = param_sets[0]
+    missing = [k for k in LH_KEYS if k not in F]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    per_walker = ("g_min_el", "g_max_el", "g_el_PL_min", "g_el_PL_max", "g_min_pr", "g_max_pr", "g_pr_PL_min",
+                  "g_pr_PL_max", "p_el", "L_el", "p_pr", "L_pr", "R0", "B0")
+    for P in param_sets:
+        for k in HADRONIC_FLAGS:
+            if float(P[k]) != 0.:
+                raise NotImplementedError(f"{k} = {P[k]}: the photo-hadronic and pp terms are not wired into the "
+                                          "timestep driver yet (function-level kernels: lehamoc_b200.hadronic)")
+        if float(P["User_ph"]) != 0.:
+            raise NotImplementedError("User_ph: Photons_spec_user.txt input is not supported yet")
+        for k in LH_KEYS:
+            if k not in per_walker and float(P[k]) != float(F[k]):
+                raise ValueError(f"walkers of one batch must share '{k}'")
+    W = len(param_sets)
+    Ng, Nh, Np, Nt = int(float(F["grid_g_el"])), int(float(F["grid_g_el"]) / 2), int(float(F["grid_g_pr"])), int(float(F["grid_nu"]))
+    time_init, time_end, step_alg = float(F["time_init"]), float(F["time_end"]), float(F["step_alg"])
+    Vexp = float(F["Vexp"]) * c
+    g_el = np.empty((W, Ng)); g_prs = np.empty((W, Np)); nu_syn = np.empty((W, Nh + 1)); nu_ic = np.empty((W, Nh))
+    nu_tot = np.empty((W, Nt)); el_inj = np.empty((W, Ng)); pr_inj = np.empty((W, Np)); ext = np.empty((W, Nt))
+    consts = np.zeros((W, LHM_NCONST))
+    for w, P in enumerate(param_sets):
+        f = lambda k: float(P[k])
+        R0 = 10 ** f("R0")
+        B0 = f("B0")
+        comp_el = sigmaT * 10 ** f("L_el") / (4. * np.pi * R0 * m_el * c ** 3)                 # LeHaMoC.py:136
+        comp_pr = sigmaT * 10 ** f("L_pr") / (4. * np.pi * R0 * m_pr_ * c ** 3)
+        ge = np.logspace(f("g_min_el"), f("g_max_el"), Ng)
+        gp = np.logspace(f("g_min_pr"), f("g_max_pr"), Np)
+        ie_max = -1 if f("g_el_PL_max") == f("g_max_el") else int(np.min(np.where(ge > 10 ** f("g_el_PL_max"))[0]))
+        ie_min = 1 if f("g_el_PL_min") == 0. else int(np.max(np.where(ge < 10 ** f("g_el_PL_min"))[0]))
+        ip_max = -1 if f("g_pr_PL_max") == f("g_max_pr") else int(np.min(np.where(gp > 10 ** f("g_pr_PL_max"))[0]) + 1)
+        ip_min = 1 if f("g_pr_PL_min") == 0. else int(np.max(np.where(gp < 10 ** f("g_pr_PL_min"))[0]) + 1)
+        ns = np.logspace(7.5, np.log10(7. * _nu_c(ge[-1], B0)) + 1.4, Nh)                      # LeHaMoC.py:171
+        ni = np.logspace(15., 32., Nh)
+        nt = np.logspace(np.log10(ns[0]), np.log10(max(ni[-1], ns[-1])), Nt)
+        V0 = 4. * np.pi / 3. * R0 ** 3.
+        ei = np.ones(Ng) * SENTINEL
+        pi_ = np.ones(Np) * SENTINEL
+        if f("PL_inj") == 1.:                                                                  # LeHaMoC.py:256-261
+            ei[ie_min:ie_max] = _Q_el_Lum(_Lum_e_inj(comp_el, R0), f("p_el"), ge[ie_min], ge[ie_max]) \
+                * ge[ie_min:ie_max] ** (-f("p_el")) / V0
+            Lp = 4. * np.pi * R0 * m_pr_ * c ** 3. * comp_pr / sigmaT
+            pi_[ip_min:ip_max] = _Q_pr_Lum(Lp, f("p_pr"), gp[ip_min], gp[ip_max]) * gp[ip_min:ip_max] ** (-f("p_pr")) / V0
+        else:
+            pi_ = _Q_norm_exp_c(R0, comp_pr, gp, ip_max, f("p_pr")) * gp ** (-f("p_pr")) * np.exp(-gp / gp[ip_max]) / V0
+            ei = _Q_norm_exp_c(R0, comp_el, ge, ie_max, f("p_el")) * ge ** (-f("p_el")) * np.exp(-ge / ge[ie_max]) / V0
+        g_el[w], g_prs[w], nu_ic[w], nu_tot[w], el_inj[w], pr_inj[w] = ge, gp, ni, nt, ei, pi_
+        nu_syn[w] = np.append(ns, nt[-1])                                                     # LeHaMoC.py:234
+        ext[w] = external_fields_lh(P, nt)
+        dt = step_alg * R0 / c
+        consts[w, [C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS]] = [R0, B0, float(F["m"]), Vexp, dt, time_init,
+                                                                         int(time_end / step_alg)]
+        consts[w, C_COR_P] = f("p_el")
+        consts[w, C_COR_Q0] = _Q_el_Lum(_Lum_e_inj(comp_el, R0), f("p_el"), ge[1], ge[-2])     # LeHaMoC_f.py:646
+        consts[w, C_COR_B] = 10 ** 4.
+    cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=100, loss_minus_one=1, qee_from_ic=0,
+               const_B=int(float(F["m"]) == 0. or Vexp == 0.), ic_pair_table=1,
+               shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))),
+               driver=1, Np=Np, esc_flag_pr=_flag01(F, "esc_flag_pr"))
+    for k in FLAG_KEYS:
+        cfg[k] = _flag01(F, "esc_flag_el" if k == "esc_flag" else k)
+    nsteps = np.full(W, int(time_end / step_alg), dtype=np.int64)
+    b = Batch("lehamoc", cfg, consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext, nsteps)
+    b.g_pr, b.pr_inj = g_prs, pr_inj
+    return b
+
+
+def external_fields_lh(F: dict, nu_tot: np.ndarray) -> np.ndarray:
+    """BB + PL photon densities on nu_tot for the LeHaMoC.py driver (LeHaMoC.py:177-212 through photons_tot)."""
+    Nt = len(nu_tot)
+    if float(F["BB_flag"]) == 0.:
+        bb = np.zeros(Nt)
+        bb[-1] = SENTINEL
+    else:
+        T = 10 ** float(F["temperature"])
+        nu_bb = np.logspace(np.log10(5.879 * 10 ** 10 * T) - 6., np.log10(5.879 * 10 ** 10 * T) + 1.5, 60)
+        with np.errstate(over="ignore"):
+            Bnu = 2.0 * h * nu_bb ** 3 / c ** 2 / np.expm1(h * nu_bb / (kb * T))
+        photons_bb = 4. * np.pi / c * Bnu / (h * nu_bb)
+        GB_norm = np.trapz(photons_bb * h * nu_bb ** 2., np.log(nu_bb)) / float(F["GB_ext"])
+        dN = np.append(photons_bb / GB_norm, SENTINEL)
+        nu_bb = np.append(nu_bb, nu_tot[-1])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            bb = 10 ** np.interp(np.log10(nu_tot), np.log10(nu_bb), np.log10(dN))
+    if float(F["PL_flag"]) == 0.:
+        pl = np.zeros(Nt)
+    else:                                                    # LeHaMoC.py:195-199
+        sp = np.logspace(float(F["nu_min_ph"]), float(F["nu_max_ph"]), 100)
+        k_ph = float(F["dE_dV_ph"]) / np.trapz(sp ** (-float(F["s_ph"]) + 1.), sp) / h
+        tmp = k_ph * sp ** (-float(F["s_ph"]))
+        tmp[-1] = SENTINEL
+        pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(tmp))
+    return bb + pl
 
 
 def pack_script(param_sets) -> Batch:

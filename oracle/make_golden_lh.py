@@ -1,0 +1,58 @@
+"""Generate tests/golden/lh_*.npz by running the UNMODIFIED `LeHaMoC Code and Tests/LeHaMoC.py` (build container).
+
+TEST INFRASTRUCTURE ONLY.   python oracle/make_golden_lh.py [names...]
+Each fixture stores the parameter set and the four per-step output snapshots (log10, exactly as written)."""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import run_reference as rr  # noqa: E402
+import run_reference_lh as rl  # noqa: E402
+
+GOLD = os.path.join(os.path.dirname(HERE), "tests", "golden")
+SHIPPED = rr.read_params(os.path.join(rl.HAD_DIR, "Parameters.txt"))
+
+
+def variant(**kw):
+    p = dict(SHIPPED)
+    p.update(kw)
+    return p
+
+
+VARIANTS = {
+    # LeHaMoC Code and Tests/Parameters.txt as shipped (leptonic processes + proton synchrotron, hadronic flags 0)
+    "lh_shipped": dict(SHIPPED),
+    # BASELINE config 5: external black body + power-law photon fields (the sane PL form of LeHaMoC.py:195-199)
+    "lh_bbpl": variant(grid_g_el=100., grid_nu=100., time_end=6., BB_flag=1., temperature=4., GB_ext=1e-3, PL_flag=1.,
+                       dE_dV_ph=1e-3, nu_min_ph=12., nu_max_ph=16., s_ph=2.),
+    # expansion + decaying field + protons that matter (proton synchrotron), exponential cut-off injection
+    "lh_expand": variant(grid_g_el=120., grid_g_pr=60., g_max_pr=7., g_pr_PL_max=6., L_pr=46., time_end=8.,
+                         step_alg=2., Ad_l_flag=1., Vexp=0.1, m=1., PL_inj=0., g_el_PL_max=5., B0=10.),
+    # gamma-gamma off, injection off after the initial condition
+    "lh_nogg": variant(grid_g_el=80., time_end=5., gg_flag=0., inj_flag=0.),
+    # photohadronic loss terms + photopion emissivities + neutrinos on reduced grids
+    "lh_pg": variant(grid_g_el=40., grid_g_pr=30., g_max_pr=8., g_pr_PL_max=8., p_pr=2., L_pr=46.5, grid_nu=60.,
+                     time_end=3., pg_pi_l_flag=1., pg_BH_l_flag=1., pg_pi_emis_flag=1., neutrino_flag=1., B0=10.),
+}
+
+
+def main():
+    names = sys.argv[1:] or list(VARIANTS)
+    for name in names:
+        P = VARIANTS[name]
+        r = rl.run_lehamoc_script(P)
+        keys = sorted(P)
+        out = {"param_keys": np.array(keys), "param_vals": np.array([P[k] for k in keys], dtype=np.float64)}
+        out.update({k: v for k, v in r.items() if k != "wall_s"})
+        out["wall_s"] = np.float64(r["wall_s"])
+        np.savez_compressed(os.path.join(GOLD, name + ".npz"), **out)
+        print(f"{name}: {r['wall_s']:.1f} s, steps {r['nuLnu'].shape[0]}")
+
+
+if __name__ == "__main__":
+    main()

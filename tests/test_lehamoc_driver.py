@@ -1,0 +1,106 @@
+"""The leptohadronic driver `LeHaMoC Code and Tests/LeHaMoC.py` (BASELINE configs 3 and 5).
+tests/golden/lh_*.npz hold the per-step outputs of the UNMODIFIED script (oracle/make_golden_lh.py)."""
+import os
+
+import numpy as np
+import pytest
+
+import lehamoc_oracle_lh as olh
+from util import GOLD, load_golden
+
+
+def log_close(got, ref_log, what, tol=4.3e-9, floor_decades=200., tol_floor=1e-6):
+    """`got` linear, `ref_log` the log10 values the reference wrote; same rule as util.assert_spectra_close."""
+    with np.errstate(divide="ignore", invalid="ignore"):
+        lg = np.log10(np.asarray(got, dtype=np.float64))
+    ref_log = np.asarray(ref_log, dtype=np.float64)
+    assert lg.shape == ref_log.shape, what
+    ninf = np.isneginf(ref_log)
+    assert np.array_equal(np.isneginf(lg), ninf), f"{what}: zeros differ"
+    ok = ~ninf & ~np.isnan(ref_log)
+    assert np.all(np.isfinite(lg[ok])), what
+    peak = np.max(np.where(ok, ref_log, -np.inf), axis=-1, keepdims=True)
+    main = ok & (ref_log > peak - floor_decades)
+    d = np.abs(lg - ref_log)
+    worst = float(d[main].max()) if main.any() else 0.0
+    assert worst <= tol, f"{what}: max |dlog10| {worst:.3e} > {tol:.1e}"
+    fl = ok & ~main
+    if fl.any():
+        assert float(d[fl].max()) <= tol_floor, f"{what}: sentinel-level bins differ by {d[fl].max():.3e}"
+    return worst
+
+
+def tables():
+    g = np.load(os.path.join(GOLD, "had_functions.npz"))
+    return {k[len("table_"):]: g[k] for k in g.files if k.startswith("table_")}
+
+
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg"])
+def test_oracle_reproduces_lehamoc_script(name):
+    z, P = load_golden(name)
+    run = olh.LeptoHadronicRun(P)
+    ne, sed, n_p, N_nu = run.run()
+    np.testing.assert_array_equal(np.log10(run.g_el), z["g_el"])
+    np.testing.assert_array_equal(np.log10(run.nu_tot), z["nu_tot"])
+    np.testing.assert_array_equal(np.log10(run.g_pr), z["g_pr"])
+    log_close(ne, z["n_e"], f"{name} n_e", tol=1e-11)
+    log_close(sed, z["nuLnu"], f"{name} nuLnu", tol=1e-11)
+    log_close(n_p, z["n_p"], f"{name} n_p", tol=1e-11)
+
+
+def test_pack_lehamoc_matches_oracle_setup():
+    from lehamoc_b200.setup_host import pack_lehamoc
+    for name in ("lh_shipped", "lh_bbpl", "lh_expand"):
+        _, P = load_golden(name)
+        b = pack_lehamoc(P)
+        run = olh.LeptoHadronicRun(P)
+        np.testing.assert_array_equal(b.g_el[0], run.g_el)
+        np.testing.assert_array_equal(b.g_pr[0], run.g_pr)
+        np.testing.assert_array_equal(b.nu_syn[0], run.nu_syn)
+        np.testing.assert_array_equal(b.nu_ic[0], run.nu_ic)
+        np.testing.assert_array_equal(b.nu_tot[0], run.nu_tot)
+        np.testing.assert_array_equal(b.el_inj[0], run.el_inj)
+        np.testing.assert_array_equal(b.pr_inj[0], run.pr_inj)
+        assert b.cfg["driver"] == 1 and b.cfg["gg_npts"] == 100 and int(b.nsteps[0]) == run.n_steps()
+        # external fields as photons_tot delivers them on nu_tot
+        V = 1.0
+        with np.errstate(all="ignore"):
+            ext_ref = 10 ** np.interp(np.log10(run.nu_tot), np.log10(run.nu_bb), np.log10(run.bb * V)) + run.pl
+        np.testing.assert_allclose(b.ext[0], ext_ref, rtol=1e-14, atol=0)
+    _, P = load_golden("lh_shipped")
+    with pytest.raises(NotImplementedError):
+        pack_lehamoc(dict(P, pg_pi_l_flag=1.))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg"])
+@pytest.mark.parametrize("path", ["R", "S"])
+def test_gpu_lehamoc_driver_matches_reference(name, path):
+    """Every step's pairs, photons and protons against what the unmodified LeHaMoC.py wrote."""
+    from lehamoc_b200 import LeHaMoC
+    z, P = load_golden(name)
+    batch, N, sed, Npr = LeHaMoC.run(P, ic_path=path)
+    assert N.shape[1] == z["n_e"].shape[0]
+    log_close(N[0], z["n_e"], f"{name} n_e")
+    log_close(sed[0], z["nuLnu"], f"{name} nuLnu")
+    log_close(Npr[0], z["n_p"], f"{name} n_p")
+
+
+@pytest.mark.gpu
+def test_gpu_lehamoc_cli_and_batch(tmp_path, monkeypatch):
+    from lehamoc_b200 import LeHaMoC
+    z, P = load_golden("lh_nogg")
+    pf = tmp_path / "Parameters.txt"
+    pf.write_text("\n".join(f"{k} = {v!r}" for k, v in P.items()))
+    monkeypatch.chdir(tmp_path)
+    assert LeHaMoC.main(["LeHaMoC.py", str(pf), "_t"]) == 0
+    ph = np.loadtxt(tmp_path / "Photons_Distribution_t.txt")
+    assert ph.shape == (z["nuLnu"].size, 2)
+    np.testing.assert_array_equal(ph[:len(z["nu_tot"]), 0], z["nu_tot"])
+    # two different walkers in one launch == each alone
+    sets = [dict(P), dict(P, B0=3.0, p_el=2.2, L_pr=8.0)]
+    _, N2, sed2, Np2 = LeHaMoC.run(sets, snapshots=False)
+    for i, Q in enumerate(sets):
+        _, N1, sed1, Np1 = LeHaMoC.run(Q, snapshots=False)
+        np.testing.assert_array_equal(sed2[i], sed1[0])
+        np.testing.assert_array_equal(Np2[i], Np1[0])
