@@ -104,3 +104,16 @@ def test_gpu_lehamoc_cli_and_batch(tmp_path, monkeypatch):
         _, N1, sed1, Np1 = LeHaMoC.run(Q, snapshots=False)
         np.testing.assert_array_equal(sed2[i], sed1[0])
         np.testing.assert_array_equal(Np2[i], Np1[0])
+
+
+def test_oracle_with_photohadronic_terms():
+    """lh_pg: photopion + Bethe-Heitler loss terms, photopion pairs / photons / neutrinos switched on (reduced grids):
+    pins the wiring of lehamoc_oracle_had.py into the driver restatement against the unmodified script."""
+    z, P = load_golden("lh_pg")
+    run = olh.LeptoHadronicRun(P, tables=tables())
+    ne, sed, n_p, N_nu = run.run()
+    log_close(ne, z["n_e"], "lh_pg n_e", tol=1e-10)
+    log_close(sed, z["nuLnu"], "lh_pg nuLnu", tol=1e-10)
+    log_close(n_p, z["n_p"], "lh_pg n_p", tol=1e-10)
+    log_close(N_nu, z["N_nu"], "lh_pg N_nu", tol=1e-10)
+    assert np.any(N_nu[-1] > 0)
