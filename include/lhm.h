@@ -62,6 +62,8 @@ typedef struct {
                                Q_ee_f with gg_npts = 100, gamma-gamma pre-attenuation of the first two steps) */
     int Np;                 /* len(g_pr) = int(grid_g_pr), driver 1 only                   LeHaMoC.py:147 */
     int esc_flag_pr;        /* proton escape flag, driver 1 only                            LeHaMoC.py:331 */
+    int pg_pi_l_flag, pg_BH_l_flag;     /* driver 1: photopion / Bethe-Heitler proton loss terms   LeHaMoC.py:311-323 */
+    int pg_pi_emis_flag, neutrino_flag; /* driver 1: photopion pairs + photons, neutrinos           LeHaMoC.py:343-352 */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 
@@ -117,8 +119,13 @@ int lhm_run_batch(lhm_handle*, double* N_el_out, double* nuLnu_out, int snapshot
 /* Driver 1 (LeHaMoC.py): proton grid and injection rate per volume of the next batch, g_pr [W,Np], pr_inj [W,Np]
  * (LeHaMoC.py:147,258); call before lhm_setup_batch.  el_inj of lhm_setup_batch is per volume too (LeHaMoC.py:257). */
 int lhm_set_protons(lhm_handle*, const double* g_pr, const double* pr_inj);
-/* Driver 1: the whole time integration LeHaMoC.py:266-434; as lhm_run_batch plus N_pr/Volume [W,(S),Np]. */
-int lhm_run_batch_lh(lhm_handle*, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots);
+/* Driver 1: the whole time integration LeHaMoC.py:266-434; as lhm_run_batch plus N_pr/Volume [W,(S),Np] and the
+ * neutrino distribution N_nu [W,(S),50] on E_nu_space (either may be NULL).  With a photo-hadronic flag set the tables
+ * must have been given with lhm_set_had_tables (struct declared below). */
+struct lhm_had_tables_s;
+int lhm_set_had_tables(lhm_handle*, const struct lhm_had_tables_s* tables);
+int lhm_run_batch_lh(lhm_handle*, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
+                     int snapshots);
 
 /* Device time (ms, CUDA events on the handle's stream) of the most recent set-up, cor-factor and fused-step
  * kernels; -1 if never launched.  Synchronises on those events only.  bench.py's roofline uses run_ms. */
@@ -172,7 +179,7 @@ int lhm_loglike_batch(int W, int Nt, const double* nu_tot, const double* nuLnu, 
 /* ---- hadronic stage, function-level entry points (handle-free) -------------------------
  * The six tables the reference reads at import (`LeHaMoC Code and Tests/LeHaMoC_f.py`:14-19), as DEVICE pointers to
  * row-major copies of the files. */
-typedef struct {
+typedef struct lhm_had_tables_s {
     const double* phi_g;   int n_phi_g;     /* Phi_g_K&A.txt          [n,4]  eta/eta0, s, d, B                       */
     const double* phi_el;  int n_phi_el;    /* Phi_g_leptons_K&A.txt  [n,13] eta/eta0, (s,d,B) x e+, anti-nu_mu, nu_mu, nu_e */
     const double* phi_el1; int n_phi_el1;   /* Phi_e-nu_e_K&A.txt     [n,7]  eta/eta0, (s,d,B) x e-, anti-nu_e       */

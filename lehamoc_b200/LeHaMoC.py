@@ -4,9 +4,9 @@
 
 writes Pairs_Distribution<suffix>.txt, Photons_Distribution<suffix>.txt, Protons_Distribution<suffix>.txt and
 Neutrinos_Distribution<suffix>.txt in the reference's text format (one block per timestep).  `run()` is the importable
-form and takes several parameter sets at once.  Runs with the photo-hadronic / pp flags set raise NotImplementedError
-(their source and loss terms exist as function-level kernels, lehamoc_b200.hadronic, but are not wired into the
-timestep yet); the neutrino distribution of a run without them is identically zero, as in the reference.
+form and takes several parameter sets at once.  The photopion and Bethe-Heitler proton loss terms, the photopion pairs / photons and the neutrinos
+are part of the fused timestep; the Bethe-Heitler emissivity (pg_BH_emis_flag) and the pp channels raise
+NotImplementedError.
 """
 from __future__ import annotations
 
@@ -21,17 +21,22 @@ from .setup_host import pack_lehamoc, read_parameter_file
 
 
 def run(param_sets, ic_path="R", snapshots=True, engine=None):
-    """Returns (batch, n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np]) as NumPy arrays; S = number of timesteps when
-    `snapshots` (the reference writes every step), else 1 (final state)."""
+    """Returns (batch, n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np], N_nu [W,S,50]) as NumPy arrays; S = number of
+    timesteps when `snapshots` (the reference writes every step), else 1 (final state).  With a photo-hadronic flag
+    set the six tables are read from the working directory like the reference does (or set them beforehand with
+    lehamoc_b200.hadronic.load_tables / set_tables)."""
     batch = pack_lehamoc(param_sets)
     eng = engine or Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
+    if any(batch.cfg[k] for k in ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag")):
+        from . import hadronic
+        eng.set_had_tables(hadronic._need_tables())
     eng.setup(batch)
     S = int(batch.nsteps.max()) if snapshots else 0
-    N, sed, Npr = eng.run_lh(snapshots=S)
-    return batch, N.cpu().numpy(), sed.cpu().numpy(), Npr.cpu().numpy()
+    N, sed, Npr, Nnu = eng.run_lh(snapshots=S)
+    return batch, N.cpu().numpy(), sed.cpu().numpy(), Npr.cpu().numpy(), Nnu.cpu().numpy()
 
 
-def write_outputs(batch, N, sed, Npr, out_s, w=0):
+def write_outputs(batch, N, sed, Npr, Nnu, out_s, w=0):
     """LeHaMoC.py:440-453: str(float) of log10 values, space separated, four files."""
     nu_nu = np.logspace(10., 22., 50) * eV / h                                   # LeHaMoC.py:173
     names = ["Pairs_Distribution" + out_s + ".txt", "Photons_Distribution" + out_s + ".txt",
@@ -41,7 +46,7 @@ def write_outputs(batch, N, sed, Npr, out_s, w=0):
         files = [open(n, "w") for n in names]
         try:
             for s in range(int(batch.nsteps[w])):
-                ys = [np.log10(N[w, s]), np.log10(sed[w, s]), np.log10(Npr[w, s]), np.log10(np.zeros(50))]
+                ys = [np.log10(N[w, s]), np.log10(sed[w, s]), np.log10(Npr[w, s]), np.log10(Nnu[w, s])]
                 for f, x, y in zip(files, xs, ys):
                     for a, b in zip(x, y):
                         f.write(str(a) + " " + str(b) + "\n")
@@ -59,8 +64,8 @@ def main(argv=None):
         print('python -m lehamoc_b200.LeHaMoC Parameters.txt _fileName')
         return 1
     start_time = time.time()
-    batch, N, sed, Npr = run(read_parameter_file(argv[1]))
-    write_outputs(batch, N, sed, Npr, argv[2])
+    batch, N, sed, Npr, Nnu = run(read_parameter_file(argv[1]))
+    write_outputs(batch, N, sed, Npr, Nnu, argv[2])
     print("--- %s seconds ---" % "{:.2f}".format((time.time() - start_time)))
     return 0
 

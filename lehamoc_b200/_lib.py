@@ -25,7 +25,8 @@ class lhm_config(C.Structure):
         "Ng", "Ns", "Ni", "Nt",
         "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag", "SSA_l_flag",
         "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "ic_pair_table",
-        "shared_ic_grids", "driver", "Np", "esc_flag_pr", "max_walkers")]
+        "shared_ic_grids", "driver", "Np", "esc_flag_pr", "pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag",
+        "neutrino_flag", "max_walkers")]
 
 
 # every symbol include/lhm.h declares: (restype, argtypes)
@@ -43,7 +44,8 @@ SIGNATURES = {
     "lhm_cor_factor_batch": (C.c_int, [_P, _P]),
     "lhm_run_batch": (C.c_int, [_P, _P, _P, C.c_int]),
     "lhm_set_protons": (C.c_int, [_P, _P, _P]),
-    "lhm_run_batch_lh": (C.c_int, [_P, _P, _P, _P, C.c_int]),
+    "lhm_set_had_tables": (C.c_int, [_P, _P]),
+    "lhm_run_batch_lh": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),

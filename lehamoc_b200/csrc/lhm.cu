@@ -37,7 +37,9 @@ struct RunArgs {
     int ptab_shared;
     double* N_out;          // [W,(S),Ng] or null
     double* Np_out;         // [W,(S),Np] or null (LeHaMoC.py driver)
-    int esc_pr;
+    double* Nnu_out;        // [W,(S),50] or null
+    int esc_pr, had;        // had: photo-hadronic terms switched on (shared memory reserved for them)
+    HadTables HT;
     double* sed_out;        // [W,(S),Nt] or null
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
@@ -167,6 +169,16 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
     for (int j = tid; j < Np; j += NT) H.Npr[j] = 0.0;
     for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.aggS[k] = 0.0; H.QsynP[k] = 0.0; }
     for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    LossTab Tb;
+    if (A.had) {
+        loss_tab_stage(Tb, H.ltab, A.HT, NT);
+        for (int k = tid; k < 52; k += NT) {
+            H.Nnu[k] = 0.0; H.Qnu[k] = 0.0;
+            H.Enu[k] = (k < 50) ? exp10(logspace_exp(10., 22., k, 50)) * kHC.eV : 0.0;     // E_nu_space, LeHaMoC_f.py:41
+        }
+        for (int j = tid; j < Ng; j += NT) H.Qpi[j] = 0.0;
+        for (int k = tid; k < Ni; k += NT) H.Qpg[k] = 0.0;
+    }
     ic_prepare<NT>(C, S);
     double t = C.tinit;
     for (int step = 0; step < nsteps; ++step) {
@@ -176,8 +188,9 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
         C.V = volume_of(C.Rad);
         phase_photons<NT>(C, S, true);
         if (C.F.ic_l) phase_uph_lh<NT>(C, S);
-        phase_protons<NT>(C, S, H, A.esc_pr);
-        phase_electrons_lh<NT>(C, S);
+        phase_protons<NT>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr);
+        if (C.F.pg_e) phase_photopion<NT>(C, S, H, A.HT);
+        phase_electrons_lh<NT>(C, S, C.F.pg_e ? H.Qpi : nullptr);
         phase_vectors<NT>(C, S);
         phase_syn_rows<NT>(C, S, false);
         phase_syn_protons<NT>(C, S, H);
@@ -186,8 +199,12 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
         }
         __syncthreads();
         if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
-        phase_photon_solves_lh<NT>(C, S, H, cor);
+        phase_photon_solves_lh<NT>(C, S, H, cor, C.F.pg_e ? H.Qpg : nullptr);
         if (C.F.gg) phase_gg_lh<NT>(C, S, H, step);
+        if (A.had) {                                             // neutrino equation: escape only, LeHaMoC.py:430-434
+            const double V2 = 1.0 + C.dt * (kPC.c / C.Rad);
+            for (int k = tid + 1; k < 49; k += NT) H.Nnu[k] = (H.Nnu[k] + H.Qnu[k]) / V2;
+        }
         const int slot = A.snapshots > 0 ? step : 0;
         if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && step == nsteps - 1)) {
             const int S_ = A.snapshots > 0 ? A.snapshots : 1;
@@ -204,6 +221,10 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
             if (A.Np_out) {
                 double* o = A.Np_out + ((size_t)w * S_ + slot) * Np;
                 for (int j = tid; j < Np; j += NT) o[j] = H.Npr[j] / C.V;
+            }
+            if (A.Nnu_out) {
+                double* o = A.Nnu_out + ((size_t)w * S_ + slot) * 50;
+                for (int k = tid; k < 50; k += NT) o[k] = A.had ? H.Nnu[k] : 0.0;
             }
             __syncthreads();
         }
@@ -421,6 +442,8 @@ struct lhm_handle {
     double2* d_ptab;          // IC pair table (cfg.ic_pair_table)
     const double* g_pr;       // driver 1: proton grid / injection of the next batch (caller-owned)
     const double* pr_inj;
+    HadTables HT;             // driver 1 with photo-hadronic flags: device tables (lhm_set_had_tables)
+    bool have_HT;
     const double* consts;     // device pointers of the current batch (caller- or staging-owned)
     const double* g_el;
     // staging for the *_host entry points
@@ -496,8 +519,13 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
     F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
     F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
+    F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
+    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu)) { delete h; return LHM_ERR_ARG; }
     h->smem = smem_bytes(h->L, NW);
-    if (cfg->driver == 1) h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
+    if (cfg->driver == 1) {
+        h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
+        if (F.pg_l || F.bh_l || F.pg_e) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
+    }
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
     PhysConst pc = make_consts();
     CUDA_TRY(cudaMemcpyToSymbol(kPC, &pc, sizeof(pc)));
@@ -575,6 +603,8 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
 }
 
 static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots, bool lh);
+static int had_init();
+static HadTables to_dev_tables(const lhm_had_tables* t);
 
 int lhm_set_protons(lhm_handle* h, const double* g_pr, const double* pr_inj) {
     if (!h || !g_pr || !pr_inj) return LHM_ERR_ARG;
@@ -583,10 +613,30 @@ int lhm_set_protons(lhm_handle* h, const double* g_pr, const double* pr_inj) {
     return LHM_OK;
 }
 
-int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots) {
+int lhm_set_had_tables(lhm_handle* h, const lhm_had_tables* t) {
+    if (!h || !t) return LHM_ERR_ARG;
+    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    if (!t->phi_g || !t->phi_el || !t->phi_el1 || !t->fk || !t->cs || !t->kp) return LHM_ERR_ARG;
+    if (t->n_phi_g > HAD_MAXTAB || t->n_phi_el > HAD_MAXTAB || t->n_phi_el1 > HAD_MAXTAB || t->n_cs > 128 || t->n_kp > 64 ||
+        t->n_fk > 128) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    h->HT = to_dev_tables(t);
+    h->have_HT = true;
+    return LHM_OK;
+}
+
+static double* g_nnu_out = nullptr;     // per-call output slot of lhm_run_batch_lh (single-threaded per handle)
+
+int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
     if (h->cfg.driver != 1) return LHM_ERR_STATE;
-    return run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
+    if ((h->F.pg_l || h->F.bh_l || h->F.pg_e) && !h->have_HT) return LHM_ERR_STATE;
+    g_nnu_out = N_nu_out;
+    int rc = run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
+    g_nnu_out = nullptr;
+    return rc;
 }
 
 int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapshots) {
@@ -608,6 +658,9 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
     A.Np_out = N_pr_out; A.esc_pr = h->cfg.esc_flag_pr;
+    A.Nnu_out = lh ? g_nnu_out : nullptr;
+    A.had = lh && (h->F.pg_l || h->F.bh_l || h->F.pg_e);
+    if (A.had) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
     A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
@@ -774,15 +827,13 @@ int lhm_had_loss_batch(int W, int Ne, int Nt, int which, const double* g_eval, c
                        const lhm_had_tables* tables, double* out, void* stream) {
     if (W < 1 || Ne < 1 || Nt < 2 || (which != 0 && which != 1) || !g_eval || !nu || !photons || !tables || !out)
         return LHM_ERR_ARG;
-    if (which == 0 && (!tables->cs || !tables->kp || tables->n_cs < 3 || tables->n_kp < 2)) return LHM_ERR_ARG;
-    if (which == 1 && (!tables->fk || tables->n_fk < 2)) return LHM_ERR_ARG;
+    if (!tables->cs || !tables->kp || tables->n_cs < 3 || tables->n_kp < 2 || !tables->fk || tables->n_fk < 2) return LHM_ERR_ARG;
     int rc = had_init();
     if (rc != LHM_OK) return rc;
     LossArgs A;
     A.W = W; A.Ne = Ne; A.Nt = Nt; A.which = which; A.g_eval = g_eval; A.nu = nu; A.photons = photons;
     A.T = to_dev_tables(tables); A.out = out;
-    const int nt = tables->n_cs > tables->n_fk ? tables->n_cs : tables->n_fk;
-    const size_t smem = ((size_t)2 * Nt + 2 * nt + 2 * tables->n_kp) * sizeof(double);
+    const size_t smem = ((size_t)2 * Nt + loss_tab_doubles(A.T)) * sizeof(double);
     if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
     CUDA_TRY(cudaFuncSetAttribute(had_loss_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     had_loss_kernel<<<W, HAD_NT, smem, (cudaStream_t)stream>>>(A);

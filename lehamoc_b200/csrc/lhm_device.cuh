@@ -50,6 +50,7 @@ struct Layout {
     int qee_c, qee_r2;              // Ng: 2.61/(2 gamma) and 10**(-2 step)
     // LeHaMoC.py driver only (Np > 0)
     int gp, lgp, wgp, g13p, spm, spp, prinj;        // Np: proton grid, ln, trapz weights, g^(1/3), loss stencils, injection
+    int gpm, idgp, l10gp;                           // Np: g_pr_mp[k], 1/dg_pr[j], log10(g_pr)
     int ags_a, ags_d, ags_c, ags_r2;                // Ns: a_gg resample grid on nu_syn (LeHaMoC.py:415)
     int agt_a, agt_d, agt_c, agt_r2;                // Nt: a_gg resample grid on nu_tot (LeHaMoC.py:416)
     int uv_d;                                       // Ng: step (log10) of U_ph_f's 50-point resample (LeHaMoC_f.py:177)
@@ -91,7 +92,7 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP, int Np = 0) {
     L.agg_c = take(Ni); L.agg_r2 = take(Ni); L.qee_c = take(Ng); L.qee_r2 = take(Ng);
     const int np_ = Np > 0 ? Np : 0, nsl = Np > 0 ? Ns : 0, ntl = Np > 0 ? Nt : 0, ngl = Np > 0 ? Ng : 0;
     L.gp = take(np_); L.lgp = take(np_); L.wgp = take(np_); L.g13p = take(np_); L.spm = take(np_); L.spp = take(np_);
-    L.prinj = take(np_);
+    L.prinj = take(np_); L.gpm = take(np_); L.idgp = take(np_); L.l10gp = take(np_);
     L.ags_a = take(nsl); L.ags_d = take(nsl); L.ags_c = take(nsl); L.ags_r2 = take(nsl);
     L.agt_a = take(ntl); L.agt_d = take(ntl); L.agt_c = take(ntl); L.agt_r2 = take(ntl);
     L.uv_d = take(ngl);

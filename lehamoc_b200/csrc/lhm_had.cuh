@@ -59,6 +59,96 @@ struct LossArgs {
 
 constexpr int HAD_NT = 256;
 
+// tables of the loss rates staged in shared memory: (log10 energy, value) of cross_section.csv[1:] and kp_pg.txt for
+// the photopion rate, (log10 kappa, log10 f) of f(xi).csv for the Bethe-Heitler rate
+struct LossTab {
+    const double *tx, *ty; int ncs;
+    const double *ux, *uy; int nkp;
+    const double *fx, *fy; int nfk;
+};
+__host__ __device__ inline size_t loss_tab_doubles(const HadTables& T) { return (size_t)2 * (T.n_cs + T.n_kp + T.n_fk); }
+
+// stage the tables (all threads of the CTA; no barrier inside)
+__device__ inline void loss_tab_stage(LossTab& Tb, double* sm, const HadTables& T, int nthreads) {
+    const HadConst& K = kHC;
+    double* tx = sm; double* ty = tx + T.n_cs; double* ux = ty + T.n_cs; double* uy = ux + T.n_kp;
+    double* fx = uy + T.n_kp; double* fy = fx + T.n_fk;
+    const int ncs = T.cs ? T.n_cs - 1 : 0;                          // the reference drops the first row ([1:])
+    for (int k = threadIdx.x; k < ncs; k += nthreads) {
+        tx[k] = log10(T.cs[2 * (k + 1)] * 1e9 * K.eV);
+        ty[k] = T.cs[2 * (k + 1) + 1];
+    }
+    for (int k = threadIdx.x; k < (T.kp ? T.n_kp : 0); k += nthreads) { ux[k] = log10(T.kp[2 * k] * 1e9 * K.eV); uy[k] = T.kp[2 * k + 1]; }
+    for (int k = threadIdx.x; k < (T.fk ? T.n_fk : 0); k += nthreads) { fx[k] = T.fk[2 * k]; fy[k] = T.fk[2 * k + 1]; }
+    Tb.tx = tx; Tb.ty = ty; Tb.ncs = ncs; Tb.ux = ux; Tb.uy = uy; Tb.nkp = T.n_kp; Tb.fx = fx; Tb.fy = fy; Tb.nfk = T.n_fk;
+}
+
+// one proton Lorentz factor by one warp (all 32 lanes take part, all get the result).
+// which = 0: dg_dt_pg (lx = log10(h nu), lp = log10(photons/h)); 1: dg_dt_BH (lx = log10(h nu/mc2), lp = log10(photons))
+__device__ double had_loss_warp(int which, double g_p, int Nt, double hnu_max, const double* __restrict__ lx,
+                                const double* __restrict__ lp, const LossTab& Tb) {
+    const int lane = threadIdx.x & 31;
+    const HadConst& K = kHC;
+    const double mc2 = K.m_el * K.c * K.c;
+    double res = 0.0;
+    if (which == 0) {
+        const double E_th = 145. * 1e6 * K.eV;
+        if (g_p * hnu_max > E_th) {
+            const double a = log10(E_th), b = log10(2. * g_p * hnu_max) + 3;
+            double s = 0.0;
+            for (int i = lane; i < 100; i += 32) {
+                const double leb = logspace_exp(a, b, i, 100);
+                const double eb = exp10(leb);
+                double inner = 0.0;
+                if (eb / (2. * g_p) < hnu_max / 2.) {
+                    // trapz(dN/eps', ln eps') over eps' = logspace(log10(eb/(2 g_p)), log10(h nu_max), 30)
+                    const double a2 = log10(eb / (2. * g_p)), b2 = log10(hnu_max);
+                    double prev_l = 0.0, prev_y = 0.0;
+                    for (int q = 0; q < 30; ++q) {
+                        const double le = logspace_exp(a2, b2, q, 30);
+                        const double ep = exp10(le);
+                        const double y = exp10(interp_clamped(log10(ep), lx, lp, Nt)) / ep;
+                        const double ln_e = log(ep);
+                        if (q > 0) inner += (ln_e - prev_l) * (y + prev_y) / 2.0;
+                        prev_l = ln_e; prev_y = y;
+                    }
+                }
+                const double CS = interp_clamped(log10(eb), Tb.tx, Tb.ty, Tb.ncs);
+                const double KP = interp_clamped(log10(eb), Tb.ux, Tb.uy, Tb.nkp);
+                // np.trapz(., np.log(eps_bar)) weights from the actual logs
+                const double lm = (i > 0) ? log(exp10(logspace_exp(a, b, i - 1, 100))) : 0.0;
+                const double lc = log(eb);
+                const double lq = (i < 99) ? log(exp10(logspace_exp(a, b, i + 1, 100))) : 0.0;
+                const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 99) ? (lq - lc) : 0.0)) * 0.5;
+                s += wgt * (CS * KP * inner * (eb * eb));
+            }
+            s = warp_sum(s);
+            res = 1. / g_p * s * (5e-31 * K.c);
+        }
+    } else {
+        if (g_p * hnu_max > 2.1 * mc2) {
+            const double C_BH = 3. * K.sigmaT * K.c * K.m_el / (8 * M_PI * 137. * K.m_pr);
+            const double a = log10(2.), b = log10(g_p * hnu_max / mc2);
+            double s = 0.0;
+            for (int i = lane; i < 50; i += 32) {
+                const double lk = logspace_exp(a, b, i, 50);
+                const double kap = exp10(lk);
+                const double phb = mc2 / K.h * exp10(interp_clamped(log10(kap / (2. * g_p)), lx, lp, Nt));
+                const double fk = interp_clamped(log10(kap), Tb.fx, Tb.fy, Tb.nfk);
+                // np.trapz(..., np.log10(kappa))
+                const double lm = (i > 0) ? log10(exp10(logspace_exp(a, b, i - 1, 50))) : 0.0;
+                const double lc = log10(kap);
+                const double lq = (i < 49) ? log10(exp10(logspace_exp(a, b, i + 1, 50))) : 0.0;
+                const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 49) ? (lq - lc) : 0.0)) * 0.5;
+                s += wgt * (exp10(fk) * phb * kap);
+            }
+            s = warp_sum(s);
+            res = s * C_BH;
+        }
+    }
+    return res;
+}
+
 __global__ void __launch_bounds__(HAD_NT) had_loss_kernel(LossArgs A) {
     extern __shared__ __align__(16) double sh[];
     const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
@@ -66,88 +156,17 @@ __global__ void __launch_bounds__(HAD_NT) had_loss_kernel(LossArgs A) {
     const HadConst& K = kHC;
     double* lx = sh;                 // abscissae of the photon interpolation
     double* lp = lx + Nt;            // ordinates
-    double* tx = lp + Nt;            // table abscissae (log10)
-    double* ty = tx + max(A.T.n_cs, A.T.n_fk);
-    double* ux = ty + max(A.T.n_cs, A.T.n_fk);      // second table (kp) abscissae / ordinates
-    double* uy = ux + A.T.n_kp;
     const double* nu = A.nu + (size_t)w * Nt;
     const double* ph = A.photons + (size_t)w * Nt;
     const double mc2 = K.m_el * K.c * K.c;
-    int ncs = 0;
-    if (A.which == 0) {
-        for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k]); lp[k] = log10(ph[k] / K.h); }
-        ncs = A.T.n_cs - 1;                                     // the reference drops the first row ([1:])
-        for (int k = tid; k < ncs; k += HAD_NT) {
-            tx[k] = log10(A.T.cs[2 * (k + 1)] * 1e9 * K.eV);
-            ty[k] = A.T.cs[2 * (k + 1) + 1];
-        }
-        for (int k = tid; k < A.T.n_kp; k += HAD_NT) { ux[k] = log10(A.T.kp[2 * k] * 1e9 * K.eV); uy[k] = A.T.kp[2 * k + 1]; }
-    } else {
-        for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k] / mc2); lp[k] = log10(ph[k]); }
-        for (int k = tid; k < A.T.n_fk; k += HAD_NT) { tx[k] = A.T.fk[2 * k]; ty[k] = A.T.fk[2 * k + 1]; }
-    }
+    LossTab Tb;
+    loss_tab_stage(Tb, lp + Nt, A.T, HAD_NT);
+    if (A.which == 0) for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k]); lp[k] = log10(ph[k] / K.h); }
+    else for (int k = tid; k < Nt; k += HAD_NT) { lx[k] = log10(K.h * nu[k] / mc2); lp[k] = log10(ph[k]); }
     __syncthreads();
     const double hnu_max = K.h * nu[Nt - 1];
     for (int e = warp; e < A.Ne; e += NW) {
-        const double g_p = A.g_eval[(size_t)w * A.Ne + e];
-        double res = 0.0;
-        if (A.which == 0) {
-            const double E_th = 145. * 1e6 * K.eV;
-            if (g_p * hnu_max > E_th) {
-                const double a = log10(E_th), b = log10(2. * g_p * hnu_max) + 3;
-                const double dle = (b - a) / 99.0 * 2.302585092994046;           // spacing of ln(eps_bar)
-                double s = 0.0;
-                for (int i = lane; i < 100; i += 32) {
-                    const double leb = logspace_exp(a, b, i, 100);
-                    const double eb = exp10(leb);
-                    double inner = 0.0;
-                    if (eb / (2. * g_p) < hnu_max / 2.) {
-                        // trapz(dN/eps', ln eps') over eps' = logspace(log10(eb/(2 g_p)), log10(h nu_max), 30)
-                        const double a2 = log10(eb / (2. * g_p)), b2 = log10(hnu_max);
-                        double prev_l = 0.0, prev_y = 0.0;
-                        for (int q = 0; q < 30; ++q) {
-                            const double le = logspace_exp(a2, b2, q, 30);
-                            const double ep = exp10(le);
-                            const double y = exp10(interp_clamped(log10(ep), lx, lp, Nt)) / ep;
-                            const double ln_e = log(ep);
-                            if (q > 0) inner += (ln_e - prev_l) * (y + prev_y) / 2.0;
-                            prev_l = ln_e; prev_y = y;
-                        }
-                    }
-                    const double CS = interp_clamped(log10(eb), tx, ty, ncs);
-                    const double KP = interp_clamped(log10(eb), ux, uy, A.T.n_kp);
-                    // trapezoid weights on the uniform ln(eps_bar) grid: reproduce np.trapz on the actual logs
-                    const double lm = (i > 0) ? log(exp10(logspace_exp(a, b, i - 1, 100))) : 0.0;
-                    const double lc = log(eb);
-                    const double lq = (i < 99) ? log(exp10(logspace_exp(a, b, i + 1, 100))) : 0.0;
-                    const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 99) ? (lq - lc) : 0.0)) * 0.5;
-                    (void)dle;
-                    s += wgt * (CS * KP * inner * (eb * eb));
-                }
-                s = warp_sum(s);
-                res = 1. / g_p * s * (5e-31 * K.c);
-            }
-        } else {
-            if (g_p * hnu_max > 2.1 * mc2) {
-                const double C_BH = 3. * K.sigmaT * K.c * K.m_el / (8 * M_PI * 137. * K.m_pr);
-                const double a = log10(2.), b = log10(g_p * hnu_max / mc2);
-                double s = 0.0;
-                for (int i = lane; i < 50; i += 32) {
-                    const double lk = logspace_exp(a, b, i, 50);
-                    const double kap = exp10(lk);
-                    const double phb = mc2 / K.h * exp10(interp_clamped(log10(kap / (2. * g_p)), lx, lp, Nt));
-                    const double fk = interp_clamped(log10(kap), tx, ty, A.T.n_fk);
-                    // np.trapz(..., np.log10(kappa))
-                    const double lm = (i > 0) ? log10(exp10(logspace_exp(a, b, i - 1, 50))) : 0.0;
-                    const double lc = log10(kap);
-                    const double lq = (i < 49) ? log10(exp10(logspace_exp(a, b, i + 1, 50))) : 0.0;
-                    const double wgt = (((i > 0) ? (lc - lm) : 0.0) + ((i < 49) ? (lq - lc) : 0.0)) * 0.5;
-                    s += wgt * (exp10(fk) * phb * kap);
-                }
-                s = warp_sum(s);
-                res = s * C_BH;
-            }
-        }
+        const double res = had_loss_warp(A.which, A.g_eval[(size_t)w * A.Ne + e], Nt, hnu_max, lx, lp, Tb);
         if (lane == 0) A.out[(size_t)w * A.Ne + e] = res;
     }
 }
@@ -169,10 +188,6 @@ struct PionArgs {
     double* out;                              // [W,Nout]
 };
 
-__host__ __device__ inline size_t pion_smem_doubles(int Nt, int Np, int ntab) {
-    return (size_t)2 * Nt + 2 * Np + 4 * ntab + 3 * PG_NG + 8 * PG_N;
-}
-
 __device__ __forceinline__ double ka_x_plus(double eta, double r) {
     return 1. / (2. * (1. + eta)) * (eta + r * r + sqrt((eta - r * r - 2. * r) * (eta - r * r + 2. * r)));
 }
@@ -186,48 +201,53 @@ __device__ __forceinline__ double ka_x_minus_e(double eta, double r) {
     return 1. / (2. * (1. + eta)) * (eta - 2 * r - sqrt(eta * (eta - 4. * r * (1. + r))));
 }
 
-__global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
-    extern __shared__ __align__(16) double sh[];
-    const int w = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
+// Inputs of one product evaluation.  All array pointers may point to shared or global memory.
+struct PionIn {
+    int species, Ng, Ni, Np, Nt, Nnu, Nout;
+    const double *g_el, *nu_ic, *E_nu;        // output grids (only the one of the product is read; g_el[Ng-1] always for e+-)
+    const double *lgp, *lNp;                  // [Np] log10(g_pr), log10(N_pr)
+    const double *lnt, *lpt;                  // [Nt] log10(nu_target), log10(photons)
+    double gpr0, gprN, nu_max;                // g_pr[0], g_pr[-1], nu_target[-1]
+    HadTables T;
+};
+__host__ __device__ inline size_t pion_work_doubles(int ntab) { return (size_t)4 * ntab + 3 * PG_NG + 8 * PG_N; }
+__host__ __device__ inline size_t pion_smem_doubles(int Nt, int Np, int ntab) {
+    return (size_t)2 * Nt + 2 * Np + pion_work_doubles(ntab);
+}
+
+// Qp_g_opt for one product of one walker, by the whole CTA (HAD_NT threads).  out[k] = scale * Q(E_k) for k in
+// [0, Nout); `add` accumulates into out instead of overwriting.  Ends with a barrier.
+__device__ void pion_eval(const PionIn& I, double* work, double* out, double scale, bool add) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
     const HadConst& K = kHC;
-    const int Nt = A.Nt, Np = A.Np, sp = A.species;
+    const int Nt = I.Nt, Np = I.Np, sp = I.species;
     const double h_0 = 0.313, r = 0.1458;
     const double mpc2 = K.m_pr * K.c * K.c, mec2 = K.m_el * K.c * K.c;
     // species-dependent pieces (LeHaMoC_f.py:359-461, 466-563)
     const bool is_em = (sp == SP_EM || sp == SP_ANUE);
     const double thr = is_em ? 2.14 * h_0 : h_0;
     const double* tab; int ntab, ncol, c_s;
-    if (sp == SP_2G) { tab = A.T.phi_g; ntab = A.T.n_phi_g; ncol = 4; c_s = 1; }
-    else if (is_em) { tab = A.T.phi_el1; ntab = A.T.n_phi_el1; ncol = 7; c_s = (sp == SP_EM) ? 1 : 4; }
-    else { tab = A.T.phi_el; ntab = A.T.n_phi_el; ncol = 13;
+    if (sp == SP_2G) { tab = I.T.phi_g; ntab = I.T.n_phi_g; ncol = 4; c_s = 1; }
+    else if (is_em) { tab = I.T.phi_el1; ntab = I.T.n_phi_el1; ncol = 7; c_s = (sp == SP_EM) ? 1 : 4; }
+    else { tab = I.T.phi_el; ntab = I.T.n_phi_el; ncol = 13;
            c_s = (sp == SP_EP) ? 1 : (sp == SP_ANUMU) ? 4 : (sp == SP_NUMU) ? 7 : 10; }
-    const double* g_el = A.g_el + (size_t)w * A.Ng;
-    const double* nu_ic = A.nu_ic + (size_t)w * A.Ni;
-    const double* nu_t = A.nu_t + (size_t)w * Nt;
-    const double* g_pr = A.g_pr + (size_t)w * Np;
     double g_min_int, pref;
-    if (sp == SP_2G) { g_min_int = h_0 * mpc2 / (4. * K.h * nu_t[Nt - 1]); pref = K.h; }
-    else if (sp == SP_EP || sp == SP_EM) { g_min_int = thr * mpc2 / (4. * g_el[A.Ng - 1] * mec2); pref = mec2; }
-    else { g_min_int = thr * mpc2 / (4. * A.E_nu[A.Nnu - 1]); pref = K.h; }
+    if (sp == SP_2G) { g_min_int = h_0 * mpc2 / (4. * K.h * I.nu_max); pref = K.h; }
+    else if (sp == SP_EP || sp == SP_EM) { g_min_int = thr * mpc2 / (4. * I.g_el[I.Ng - 1] * mec2); pref = mec2; }
+    else { g_min_int = thr * mpc2 / (4. * I.E_nu[I.Nnu - 1]); pref = K.h; }
+    const double* lnt = I.lnt; const double* lpt = I.lpt; const double* lgp = I.lgp; const double* lNp = I.lNp;
 
-    double* lnt = sh;                  double* lpt = lnt + Nt;
-    double* lgp = lpt + Nt;            double* lNp = lgp + Np;
-    double* tx = lNp + Np;             double* ts = tx + ntab; double* td = ts + ntab; double* tB = td + ntab;
+    double* tx = work;                 double* ts = tx + ntab; double* td = ts + ntab; double* tB = td + ntab;
     double* g_t = tB + ntab;           double* coef = g_t + PG_NG;  double* act = coef + PG_NG;   // per gamma_p
     double* Wt = act + PG_NG;          // [PG_N] trapezoid weight x photons x nu
     double* Es = Wt + PG_N;            double* Ed = Es + PG_N;    double* EB = Ed + PG_N;
     double* Epsi = EB + PG_N;          double* Exm = Epsi + PG_N; double* Exp = Exm + PG_N; double* Elow = Exp + PG_N;
 
-    for (int k = tid; k < Nt; k += HAD_NT) {
-        lnt[k] = log10(nu_t[k]);
-        lpt[k] = log10(A.photons[(size_t)w * Nt + k]);
-    }
-    for (int k = tid; k < Np; k += HAD_NT) { lgp[k] = log10(g_pr[k]); lNp[k] = log10(A.N_pr[(size_t)w * Np + k]); }
     for (int k = tid; k < ntab; k += HAD_NT) {
         tx[k] = tab[k * ncol]; ts[k] = tab[k * ncol + c_s]; td[k] = tab[k * ncol + c_s + 1]; tB[k] = tab[k * ncol + c_s + 2];
     }
     __syncthreads();
-    const double ga = log10(fmax(g_min_int, g_pr[0])), gb = log10(g_pr[Np - 1]);
+    const double ga = log10(fmax(g_min_int, I.gpr0)), gb = log10(I.gprN);
     for (int gi = tid; gi < PG_NG; gi += HAD_NT) {
         const double lg = logspace_exp(ga, gb, gi, PG_NG);
         const double gp = exp10(lg);
@@ -240,14 +260,14 @@ __global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
         const double wg = (((gi > 0) ? (lc - lm) : 0.0) + ((gi < PG_NG - 1) ? (lq - lc) : 0.0)) * 0.5;
         coef[gi] = wg * (pref * Nt_ / mpc2);
         const double c_t = mpc2 / (4. * gp);
-        act[gi] = (log10(thr * c_t / K.h) < log10(nu_t[Nt - 1])) ? 1.0 : 0.0;
+        act[gi] = (log10(thr * c_t / K.h) < log10(I.nu_max)) ? 1.0 : 0.0;
     }
     __syncthreads();
     for (int e = tid; e < PG_N; e += HAD_NT) {
         const int gi = e / PG_NE, ei = e - gi * PG_NE;
         const double gp = g_t[gi];
         const double c_t = mpc2 / (4. * gp);
-        const double eta_max = 4. * K.h * nu_t[Nt - 1] * gp / mpc2;
+        const double eta_max = 4. * K.h * I.nu_max * gp / mpc2;
         const double ea = log10(thr), eb = log10(eta_max);
         auto eta_at = [&](int i) { return exp10(logspace_exp(ea, eb, i, PG_NE)); };
         const double eta = eta_at(ei);
@@ -279,11 +299,11 @@ __global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
     }
     __syncthreads();
     const bool nan_to_num = (sp != SP_2G);
-    for (int k = warp; k < A.Nout; k += NW) {
+    for (int k = warp; k < I.Nout; k += NW) {
         double Eo;
-        if (sp == SP_2G) Eo = K.h * nu_ic[k];
-        else if (sp == SP_EP || sp == SP_EM) Eo = g_el[k] * mec2;
-        else Eo = A.E_nu[k];
+        if (sp == SP_2G) Eo = K.h * I.nu_ic[k];
+        else if (sp == SP_EP || sp == SP_EM) Eo = I.g_el[k] * mec2;
+        else Eo = I.E_nu[k];
         double acc = 0.0;
         for (int e = lane; e < PG_N; e += 32) {
             const int gi = e / PG_NE;
@@ -304,8 +324,33 @@ __global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
             acc += coef[gi] * (wv * Phi);
         }
         acc = warp_sum(acc);
-        if (lane == 0) A.out[(size_t)w * A.Nout + k] = acc;
+        if (lane == 0) out[k] = add ? out[k] + scale * acc : scale * acc;
     }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
+    extern __shared__ __align__(16) double sh[];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    const int Nt = A.Nt, Np = A.Np;
+    double* lnt = sh;                  double* lpt = lnt + Nt;
+    double* lgp = lpt + Nt;            double* lNp = lgp + Np;
+    double* work = lNp + Np;
+    const double* nu_t = A.nu_t + (size_t)w * Nt;
+    const double* g_pr = A.g_pr + (size_t)w * Np;
+    for (int k = tid; k < Nt; k += HAD_NT) {
+        lnt[k] = log10(nu_t[k]);
+        lpt[k] = log10(A.photons[(size_t)w * Nt + k]);
+    }
+    for (int k = tid; k < Np; k += HAD_NT) { lgp[k] = log10(g_pr[k]); lNp[k] = log10(A.N_pr[(size_t)w * Np + k]); }
+    __syncthreads();
+    PionIn I;
+    I.species = A.species; I.Ng = A.Ng; I.Ni = A.Ni; I.Np = Np; I.Nt = Nt; I.Nnu = A.Nnu; I.Nout = A.Nout;
+    I.g_el = A.g_el + (size_t)w * A.Ng; I.nu_ic = A.nu_ic + (size_t)w * A.Ni; I.E_nu = A.E_nu;
+    I.lgp = lgp; I.lNp = lNp; I.lnt = lnt; I.lpt = lpt;
+    I.gpr0 = g_pr[0]; I.gprN = g_pr[Np - 1]; I.nu_max = nu_t[Nt - 1];
+    I.T = A.T;
+    pion_eval(I, work, A.out + (size_t)w * A.Nout, 1.0, false);
 }
 
 }  // namespace lhm

@@ -6,6 +6,7 @@
 // in yet: this kernel covers runs with the hadronic flags off (leptonic processes + proton synchrotron).
 #pragma once
 #include "lhm_step.cuh"
+#include "lhm_had.cuh"
 
 namespace lhm {
 
@@ -27,6 +28,9 @@ __device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const doubl
         T[L.lgp + j] = log(g);
         T[L.g13p + j] = pow(g, 1.0 / 3.0);
         T[L.prinj + j] = prinj[j];
+        T[L.l10gp + j] = log10(g);
+        T[L.gpm + j] = (j < Np - 1) ? (gp[j + 1] + gp[(j == 0) ? (Np - 1) : (j - 1)]) / 2.0 : 0.0;     // g_pr_mp[j]
+        T[L.idgp + j] = (j < Np - 2) ? 1.0 / ((gp[j + 2] - gp[j]) / 2.0) : 0.0;
         if (j < Np - 2) {                                   // g_pr_mp / dg_pr, LeHaMoC.py:149-150 (negative-index wrap at 0)
             const double mp0 = (gp[j + 1] + gp[(j == 0) ? (Np - 1) : (j - 1)]) / 2.0;
             const double mp1 = (gp[j + 2] + gp[j]) / 2.0;
@@ -75,7 +79,18 @@ struct SmemLh {
     double *aggS, *aggSN;              // [Ns] a_gg on nu_syn: used by the current solve / computed for the next
     double *atmp;                      // [Nt] a_gg on nu_tot
     double *Lm2, *Ln2;                 // [Nt] log2 / log10 of the field Q_ee_f integrates (attenuated in the first two steps)
+    // photo-hadronic terms (only carved when a hadronic flag is set)
+    double *lossA, *lossB, *lNp;       // [Np] dg_dt_pg / dg_dt_BH at g_pr_mp, log10 of the proton distribution
+    double *Qpi, *Qpg;                 // [Ng] photopion pairs (e+ + e-), [Ni] photopion photons
+    double *Qnu, *Nnu, *Enu;           // [52] neutrino source x dt, neutrino state, E_nu_space (50 used)
+    double *lxpg, *lppg;               // [Nt] log10(h nu), log10(photons/h)
+    double *ltab;                      // loss tables (LossTab)
+    double *work;                      // pion_eval work area
 };
+constexpr int HAD_MAXTAB = 32, HAD_MAXLOSS = 2 * (128 + 64 + 128);
+__host__ __device__ inline size_t smem_lh_had_doubles(const Layout& L) {
+    return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB);
+}
 __host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
     return (size_t)3 * pad2(L.Np) + 3 * pad2(L.Ns) + 3 * pad2(L.Nt);
 }
@@ -84,6 +99,11 @@ __device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L) {
     H.Npr = take(pad2(L.Np)); H.up = take(pad2(L.Np)); H.inucp = take(pad2(L.Np));
     H.QsynP = take(pad2(L.Ns)); H.aggS = take(pad2(L.Ns)); H.aggSN = take(pad2(L.Ns));
     H.atmp = take(pad2(L.Nt)); H.Lm2 = take(pad2(L.Nt)); H.Ln2 = take(pad2(L.Nt));
+    H.lossA = take(pad2(L.Np)); H.lossB = take(pad2(L.Np)); H.lNp = take(pad2(L.Np));
+    H.Qpi = take(pad2(L.Ng)); H.Qpg = take(pad2(L.Ni));
+    H.Qnu = take(52); H.Nnu = take(52); H.Enu = take(52);
+    H.lxpg = take(pad2(L.Nt)); H.lppg = take(pad2(L.Nt));
+    H.ltab = take(HAD_MAXLOSS); H.work = p;            // only valid when the handle reserved smem_lh_had_doubles
 }
 
 // U_ph_f, LeHaMoC_f.py:171-182: per gamma a 50-point log resample of the photon field up to nu_T, linear-x trapezoid.
@@ -168,16 +188,40 @@ __device__ void phase_uph_lh(const Ctx& C, Smem& S) {
 
 // proton equation (LeHaMoC.py:330-335 with the hadronic loss terms off): synchrotron cooling + escape + injection
 template <int NT>
-__device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr) {
+__device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, const LossTab* Tb) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Np - 2;
+    const bool had = C.F.pg_l || C.F.bh_l;
+    if (had) {                                       // LeHaMoC.py:311-323: loss rates at the midpoints g_pr_mp[0..Np-2]
+        const int Nt = L.Nt;
+        const double hK = kHC.h;
+        for (int k = tid; k < Nt; k += NT) {
+            H.lxpg[k] = log10(hK * C.T[L.nt + k]);
+            H.lppg[k] = log10(S.n[k] / hK);
+        }
+        __syncthreads();
+        const double hnu_max = hK * C.T[L.nt + Nt - 1];
+        for (int k = tid >> 5; k < L.Np - 1; k += NT / 32) {
+            const double gm = C.T[L.gpm + k];
+            const double a = C.F.pg_l ? had_loss_warp(0, gm, Nt, hnu_max, H.lxpg, H.lppg, *Tb) : 0.0;
+            const double b = C.F.bh_l ? had_loss_warp(1, gm, Nt, hnu_max, S.lxtS, S.Ln, *Tb) : 0.0;
+            if ((tid & 31) == 0) { H.lossA[k] = a; H.lossB[k] = b; }
+        }
+        __syncthreads();
+    }
     const double m_el = 9.1093837015e-28, m_pr = 1.67262192369e-24;
     const double rm = m_el / m_pr;
     const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (rm * rm * rm) * (C.B * C.B) : 0.0;      // const_pr * M_F**2
     const double esc = kPC.c / C.Rad * (double)esc_pr;
     for (int j = tid; j < n; j += NT) {
-        const double V2 = 1.0 + C.dt * (esc + b_syn * C.T[L.spm + j]);
-        const double V3 = -C.dt * (b_syn * C.T[L.spp + j]);
+        double lm = 0.0, lp = 0.0;
+        if (had) {
+            const double idg = C.T[L.idgp + j];
+            lm = (H.lossA[j] + H.lossB[j]) * idg;
+            lp = (H.lossA[j + 1] + H.lossB[j + 1]) * idg;
+        }
+        const double V2 = 1.0 + C.dt * (esc + b_syn * C.T[L.spm + j] + lm);
+        const double V3 = -C.dt * (b_syn * C.T[L.spp + j] + lp);
         const double d = H.Npr[j + 1] + (C.T[L.prinj + j + 1] * C.dt) * C.V;
         S.cp[j] = V3 / V2;
         S.dp[j] = d / V2;
@@ -189,7 +233,7 @@ __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr) {
 
 // electron equation, LeHaMoC.py:359-367 (injection per volume; Q_ee aligned with the interior points)
 template <int NT>
-__device__ void phase_electrons_lh(const Ctx& C, Smem& S) {
+__device__ void phase_electrons_lh(const Ctx& C, Smem& S, const double* Qpi) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Ng - 2;
     const double dt = C.dt;
@@ -203,6 +247,7 @@ __device__ void phase_electrons_lh(const Ctx& C, Smem& S) {
         const double V2 = 1.0 + dt * (esc + b_syn * smj + ic_m + b_ad * C.T[L.am + j]);
         const double V3 = -dt * (b_syn * spj + ic_p + b_ad * C.T[L.ap + j]);
         double src = S.qee[j + 1];
+        if (Qpi) src += Qpi[j + 1];
         if (C.F.inj) src += C.T[L.elinj + j + 1];
         const double d = S.N[j + 1] + (src * dt) * C.V;
         S.cp[j] = V3 / V2;
@@ -250,10 +295,40 @@ __device__ void phase_syn_protons(const Ctx& C, Smem& S, SmemLh& H) {
     __syncthreads();
 }
 
+// photopion secondaries, LeHaMoC.py:343-352: pairs and photons from dN_pr/dV, neutrinos (x dt) from N_pr
+template <int NT>
+__device__ void phase_photopion(const Ctx& C, Smem& S, SmemLh& H, const HadTables& T) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, Np = L.Np;
+    PionIn I;
+    I.Ng = L.Ng; I.Ni = L.Ni; I.Np = Np; I.Nt = L.Nt; I.Nnu = 50;
+    I.g_el = S.gS; I.nu_ic = S.nuoS; I.E_nu = H.Enu;
+    I.lgp = C.T + L.l10gp; I.lNp = H.lNp; I.lnt = C.T + L.lt; I.lpt = S.Ln;
+    I.gpr0 = C.T[L.gp]; I.gprN = C.T[L.gp + Np - 1]; I.nu_max = C.T[L.nt + L.Nt - 1];
+    I.T = T;
+    for (int j = tid; j < Np; j += NT) H.lNp[j] = log10(H.Npr[j] / C.V);
+    __syncthreads();
+    I.species = SP_EP; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, false);
+    I.species = SP_EM; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, true);
+    I.species = SP_2G; I.Nout = L.Ni; pion_eval(I, H.work, H.Qpg, 1.0, false);
+    if (C.F.nu) {
+        for (int j = tid; j < Np; j += NT) H.lNp[j] = log10(H.Npr[j]);          // LeHaMoC.py:347 passes N_pr itself
+        __syncthreads();
+        I.Nout = 50;
+        I.species = SP_NUMU;  pion_eval(I, H.work, H.Qnu, C.dt, false);
+        I.species = SP_ANUMU; pion_eval(I, H.work, H.Qnu, C.dt, true);
+        I.species = SP_NUE;   pion_eval(I, H.work, H.Qnu, C.dt, true);
+        I.species = SP_ANUE;  pion_eval(I, H.work, H.Qnu, C.dt, true);
+    } else {
+        for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0;
+        __syncthreads();
+    }
+}
+
 // photon equations, LeHaMoC.py:397-407: as the leptonic ones plus gamma-gamma absorption on the synchrotron grid and
 // the proton synchrotron source
 template <int NT>
-__device__ void phase_photon_solves_lh(const Ctx& C, Smem& S, SmemLh& H, double cor) {
+__device__ void phase_photon_solves_lh(const Ctx& C, Smem& S, SmemLh& H, double cor, const double* Qpg) {
     const Layout& L = C.L;
     const int tid = threadIdx.x;
     const double dt = C.dt, cc = kPC.c;
@@ -277,7 +352,8 @@ __device__ void phase_photon_solves_lh(const Ctx& C, Smem& S, SmemLh& H, double 
         const double aI = C.F.ssa ? -fabs(S.aI[j + 1]) : 0.0;
         const double V2 = 1.0 + dt * (esc + b_ad * C.T[L.aim + j] - aI * cc + S.agg[j + 1] * cc);
         const double V3 = -dt * (b_ad * C.T[L.aip + j]);
-        const double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
+        double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
+        if (Qpg) Q += Qpg[j + 1];
         const double d = S.pic[j + 1] + (Q * dt) * C.V;
         S.cp[j] = V3 / V2;
         S.dp[j] = d / V2;

@@ -127,13 +127,20 @@ class Engine:
         return N, sed
 
     def run_lh(self, snapshots: int = 0):
-        """Driver 1 (LeHaMoC.py): returns (n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np]) device tensors."""
+        """Driver 1 (LeHaMoC.py): returns (n_e [W,S,Ng], nuLnu [W,S,Nt], n_p [W,S,Np], N_nu [W,S,50]) device tensors."""
         S = snapshots if snapshots > 0 else 1
         N = self._new(self.W, S, self.Ng)
         sed = self._new(self.W, S, self.Nt)
         Npr = self._new(self.W, S, self.cfg["Np"])
-        check(self.lib.lhm_run_batch_lh(self.h, _ptr(N), _ptr(sed), _ptr(Npr), int(snapshots)), "lhm_run_batch_lh")
-        return N, sed, Npr
+        Nnu = self._new(self.W, S, 50)
+        check(self.lib.lhm_run_batch_lh(self.h, _ptr(N), _ptr(sed), _ptr(Npr), _ptr(Nnu), int(snapshots)),
+              "lhm_run_batch_lh")
+        return N, sed, Npr, Nnu
+
+    def set_had_tables(self, tables_struct):
+        """Driver 1 with photo-hadronic flags: ctypes lhm_had_tables of device pointers (lehamoc_b200.hadronic)."""
+        self._had_tables = tables_struct
+        check(self.lib.lhm_set_had_tables(self.h, C.byref(tables_struct)), "lhm_set_had_tables")
 
     def run_into(self, N, sed, snapshots: int = 0):
         check(self.lib.lhm_run_batch(self.h, _ptr(N), _ptr(sed), int(snapshots)), "lhm_run_batch")
