@@ -104,3 +104,16 @@ def test_product_never_imports_oracle():
         if fn.endswith(".py"):
             src = open(os.path.join(pkg, fn)).read()
             assert "lehamoc_oracle" not in src and "run_reference" not in src, fn
+
+
+def test_integration_md_stub_matches_binding():
+    """The ctypes stub printed in INTEGRATION.md declares the same lhm_config as the binding and the header."""
+    text = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = re.search(r"class lhm_config\(C.Structure\):.*?\)\]", text, re.S).group(0)
+    names = re.findall(r'"(\w+)"', block)
+    assert names == [n for n, _ in _lib.lhm_config._fields_]
+    header = open(os.path.join(ROOT, "include", "lhm.h")).read()
+    body = re.search(r"typedef struct \{(.*?)\} lhm_config;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    hdr_names = [n.strip() for decl in body.split(";") for n in decl.replace("int", "", 1).split(",") if n.strip()]
+    assert hdr_names == names
