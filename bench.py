@@ -418,7 +418,13 @@ def main():
                 "flops_per_launch": flops_launch, "flops_per_model": float(run_flops.mean()),
                 "active_pairs_per_model": float(active.mean()), "kernel_ms": run_ms,
                 "setup_kernel_ms": setup_ms, "cor_kernel_ms": cor_ms,
-                "traffic": None,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture of
+                # 1184 Test-1 walkers committed as profiles/r01_g_final_ncu_summary.txt (1.6139 GB + 6.9 MB), per walker
+                "traffic": (1.613871e9 + 6.920960e6) / 1184.0 * W if args.ic_path == "R" else None,
+                "traffic_source": "ncu capture profiles/r01_g_final_ncu_summary.txt, scaled by walkers per launch; it is "
+                                  "the per-step re-read of the constant-B exponential cache (543 KB per walker x 10 "
+                                  "steps, half of it exact zeros that are skipped) and of the 68 KB per-walker tables, "
+                                  "2 % of HBM bandwidth",
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_GBs": alg_bytes / (run_ms * 1e-3) / 1e9,
                         "peak_GBs": peaks.get("hbm_gbs"), "note": "compute-bound path: <8 KB of mandatory traffic per model"}}
