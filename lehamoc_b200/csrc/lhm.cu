@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
     Smem S;
     carve(S, smem_raw, A.L, NW);
     SmemLh H;
-    carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L);
+    carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L, S);
     Ctx C;
     load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
     const Layout& L = C.L;

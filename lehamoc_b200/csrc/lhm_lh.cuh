@@ -76,9 +76,10 @@ __device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const doubl
 struct SmemLh {
     double *Npr, *up, *inucp;          // [Np] proton number, weight x n_p x g^(1/3), 1/(a_cr_pr g^2)
     double *QsynP;                     // [Ns] proton synchrotron emissivity
-    double *aggS, *aggSN;              // [Ns] a_gg on nu_syn: used by the current solve / computed for the next
+    double *aggS;                      // [Ns] a_gg on nu_syn (computed at the end of a step, used by the next solve)
     double *atmp;                      // [Nt] a_gg on nu_tot
-    double *Lm2, *Ln2;                 // [Nt] log2 / log10 of the field Q_ee_f integrates (attenuated in the first two steps)
+    double *Lm2, *Ln2;                 // [Nt] log2 / log10 of the field Q_ee_f integrates (attenuated in the first two steps);
+                                       //      alias Smem::y / Smem::cum, which only the leptonic U_ph_f uses
     // photo-hadronic terms (only carved when a hadronic flag is set)
     double *lossA, *lossB, *lNp;       // [Np] dg_dt_pg / dg_dt_BH at g_pr_mp, log10 of the proton distribution
     double *Qpi, *Qpg;                 // [Ng] photopion pairs (e+ + e-), [Ni] photopion photons
@@ -92,13 +93,13 @@ __host__ __device__ inline size_t smem_lh_had_doubles(const Layout& L) {
     return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB);
 }
 __host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
-    return (size_t)3 * pad2(L.Np) + 3 * pad2(L.Ns) + 3 * pad2(L.Nt);
+    return (size_t)3 * pad2(L.Np) + 2 * pad2(L.Ns) + pad2(L.Nt);
 }
-__device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L) {
+__device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L, const Smem& S) {
     auto take = [&](int n) { double* r = p; p += n; return r; };
     H.Npr = take(pad2(L.Np)); H.up = take(pad2(L.Np)); H.inucp = take(pad2(L.Np));
-    H.QsynP = take(pad2(L.Ns)); H.aggS = take(pad2(L.Ns)); H.aggSN = take(pad2(L.Ns));
-    H.atmp = take(pad2(L.Nt)); H.Lm2 = take(pad2(L.Nt)); H.Ln2 = take(pad2(L.Nt));
+    H.QsynP = take(pad2(L.Ns)); H.aggS = take(pad2(L.Ns));
+    H.atmp = take(pad2(L.Nt)); H.Lm2 = S.y; H.Ln2 = S.cum;
     H.lossA = take(pad2(L.Np)); H.lossB = take(pad2(L.Np)); H.lNp = take(pad2(L.Np));
     H.Qpi = take(pad2(L.Ng)); H.Qpg = take(pad2(L.Ni));
     H.Qnu = take(52); H.Nnu = take(52); H.Enu = take(52);
