@@ -59,7 +59,10 @@ typedef struct {
                                by the *_host entry points; needs ic_pair_table */
     int driver;             /* 0: LeMoC/LeMoC.py and Fit_emcee/Code.py (leptonic); 1: `LeHaMoC Code and Tests/LeHaMoC.py`
                                (electron + proton equations, proton synchrotron, f_had variants of U_ph_f / a_gg /
-                               Q_ee_f with gg_npts = 100, gamma-gamma pre-attenuation of the first two steps) */
+                               Q_ee_f with gg_npts = 100, gamma-gamma pre-attenuation of the first two steps);
+                               2: Fit_emcee/Code.py::LeHaMoC (Code.py:280-535: the leptonic Code.py step + proton equation with
+                               synchrotron cooling + proton synchrotron source; lhm_set_protons / lhm_run_batch_lh as for 1,
+                               pr_inj then is a number rate, Code.py:422) */
     int Np;                 /* len(g_pr) = int(grid_g_pr), driver 1 only                   LeHaMoC.py:147 */
     int esc_flag_pr;        /* proton escape flag, driver 1 only                            LeHaMoC.py:331 */
     int pg_pi_l_flag, pg_BH_l_flag;     /* driver 1: photopion / Bethe-Heitler proton loss terms   LeHaMoC.py:311-323 */

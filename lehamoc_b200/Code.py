@@ -10,7 +10,7 @@ from __future__ import annotations
 import numpy as np
 
 from .engine import Engine
-from .setup_host import pack_code, read_parameter_file
+from .setup_host import pack_code, pack_code_lehamoc, read_parameter_file
 
 _engines = {}
 
@@ -43,6 +43,18 @@ def LeMoC(params, fileName):
     return (nu_tot[0], sed[0])
 
 
+def LeHaMoC_batch(params, fileName, ic_path="R"):
+    """`params` [W,10] (Code.py:285-295); returns (nu_tot [W,Nt], nuLnu [W,Nt]) of Fit_emcee/Code.py::LeHaMoC, the
+    leptonic model plus a proton population that cools and radiates by synchrotron only."""
+    frozen = fileName if isinstance(fileName, dict) else read_parameter_file(fileName)
+    batch = pack_code_lehamoc(params, frozen)
+    eng = _engine_for(batch, ic_path, batch.W)
+    eng.setup(batch)
+    _, sed, _, _ = eng.run_lh(snapshots=0)
+    return batch.nu_tot, sed[:, 0].cpu().numpy()
+
+
 def LeHaMoC(params, fileName):
-    """Fit_emcee/Code.py:280 (proton-synchrotron variant): hadronic stage, SURVEY.md section 8 rows A11-A15."""
-    raise NotImplementedError("the leptohadronic driver is scheduled after the leptonic path (SURVEY.md 8f-2)")
+    """Fit_emcee/Code.py:280: one evaluation of the proton-synchrotron model."""
+    nu_tot, sed = LeHaMoC_batch(np.asarray(params, dtype=np.float64)[None, :], fileName)
+    return (nu_tot[0], sed[0])

@@ -231,6 +231,81 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
     }
 }
 
+// Fit_emcee/Code.py::LeHaMoC (Code.py:280-535): the leptonic Code.py step + a proton equation with synchrotron cooling
+// and the proton synchrotron source; no adiabatic terms.  Same phases as run_kernel plus three proton phases.
+__global__ void __launch_bounds__(NT, 2) run_code_lh_kernel(RunArgs A) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    SmemLh H;
+    carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L, S);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+    for (int j = tid; j < Ng; j += NT) {
+        S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];
+        S.qee[j] = 0.0;
+    }
+    for (int j = tid; j < Np; j += NT) H.Npr[j] = (j == 0 || j == Np - 1) ? LHM_SENT : C.T[L.prinj + j];   // Code.py:423-425
+    for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.QsynP[k] = 0.0; }
+    for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    ic_prepare<NT>(C, S);
+    double t = C.tinit;
+    for (int step = 0; step < nsteps; ++step) {
+        t += C.dt;
+        C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.V = volume_of(C.Rad);
+        phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        phase_electrons<NT>(C, S);
+        phase_protons<NT>(C, S, H, C.F.esc, nullptr, false, C.F.inj != 0);
+        phase_vectors<NT>(C, S);
+        phase_syn_rows<NT>(C, S, false);
+        phase_syn_protons<NT>(C, S, H, false);
+        if (C.F.ic_e) {
+            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
+        }
+        __syncthreads();
+        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        phase_photon_solves<NT>(C, S, cor, C.F.syn_e ? H.QsynP : nullptr);
+        if (C.F.gg) {
+            const double* Lng = S.Ln;
+            if (C.F.qee_from_ic) {
+                for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
+                __syncthreads();
+                Lng = S.Lic;
+            }
+            phase_gg<NT>(C, S, Lng, S.agg, S.qee);
+            __syncthreads();
+        }
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && step == nsteps - 1)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT)
+                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            if (A.Np_out) {
+                double* o = A.Np_out + ((size_t)w * S_ + slot) * Np;
+                for (int j = tid; j < Np; j += NT) o[j] = H.Npr[j] / C.V;
+            }
+            __syncthreads();
+        }
+    }
+}
+
 // =================================================================================================
 // function-level kernels: same device code, one phase each (unit-test twins of LeHaMoC_f.py)
 // =================================================================================================
@@ -512,9 +587,9 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     h->cfg = *cfg;
     h->device = device;
     h->stream = (cudaStream_t)cuda_stream;
-    if (cfg->driver != 0 && cfg->driver != 1) return LHM_ERR_ARG;
-    if (cfg->driver == 1 && cfg->Np < 4) return LHM_ERR_ARG;
-    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts, cfg->driver == 1 ? cfg->Np : 0);
+    if (cfg->driver < 0 || cfg->driver > 2) return LHM_ERR_ARG;
+    if (cfg->driver >= 1 && cfg->Np < 4) return LHM_ERR_ARG;
+    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts, cfg->driver >= 1 ? cfg->Np : 0);
     StepFlags& F = h->F;
     F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
     F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
@@ -522,7 +597,7 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
     if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu)) { delete h; return LHM_ERR_ARG; }
     h->smem = smem_bytes(h->L, NW);
-    if (cfg->driver == 1) {
+    if (cfg->driver >= 1) {
         h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
         if (F.pg_l || F.bh_l || F.pg_e) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
     }
@@ -532,6 +607,7 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     CUDA_TRY(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CUDA_TRY(cudaFuncSetAttribute(unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CUDA_TRY(cudaFuncSetAttribute(run_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+    CUDA_TRY(cudaFuncSetAttribute(run_code_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
     CUDA_TRY(cudaFuncSetAttribute(cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cor_smem_bytes(cfg->Ng)));
     const size_t W = cfg->max_walkers;
     CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
@@ -574,7 +650,7 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.g_pr = nullptr; A.pr_inj = nullptr;
-    if (h->cfg.driver == 1) {
+    if (h->cfg.driver >= 1) {
         if (!h->g_pr || !h->pr_inj) return LHM_ERR_STATE;
         A.g_pr = h->g_pr; A.pr_inj = h->pr_inj;
     }
@@ -608,7 +684,7 @@ static HadTables to_dev_tables(const lhm_had_tables* t);
 
 int lhm_set_protons(lhm_handle* h, const double* g_pr, const double* pr_inj) {
     if (!h || !g_pr || !pr_inj) return LHM_ERR_ARG;
-    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    if (h->cfg.driver < 1) return LHM_ERR_STATE;
     h->g_pr = g_pr; h->pr_inj = pr_inj;
     return LHM_OK;
 }
@@ -631,7 +707,7 @@ static double* g_nnu_out = nullptr;     // per-call output slot of lhm_run_batch
 
 int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
-    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    if (h->cfg.driver < 1) return LHM_ERR_STATE;
     if ((h->F.pg_l || h->F.bh_l || h->F.pg_e) && !h->have_HT) return LHM_ERR_STATE;
     g_nnu_out = N_nu_out;
     int rc = run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
@@ -665,7 +741,8 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-    if (lh) run_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    if (lh && h->cfg.driver == 2) run_code_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    else if (lh) run_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     else run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -18,7 +18,7 @@ struct LhSetup {
 
 template <int NT>
 __device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const double* gp, const double* prinj,
-                                const double* ns, const double* nt) {
+                                const double* ns, const double* nt, double one) {
     const int tid = threadIdx.x, Np = L.Np, Ns = L.Ns, Nt = L.Nt, Ng = L.Ng, NP = L.NP;
     const PhysConst& pc = kPC;
     const double m_pr = 1.67262192369e-24;
@@ -35,8 +35,8 @@ __device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const doubl
             const double mp0 = (gp[j + 1] + gp[(j == 0) ? (Np - 1) : (j - 1)]) / 2.0;
             const double mp1 = (gp[j + 2] + gp[j]) / 2.0;
             const double dg = (gp[j + 2] - gp[j]) / 2.0;
-            T[L.spm + j] = (mp0 * mp0 - 1.0) / dg;          // LeHaMoC.py:296-297
-            T[L.spp + j] = (mp1 * mp1 - 1.0) / dg;
+            T[L.spm + j] = (mp0 * mp0 - one) / dg;          // LeHaMoC.py:296-297 (gamma^2-1) / Code.py:452-453 (gamma^2)
+            T[L.spp + j] = (mp1 * mp1 - one) / dg;
         } else {
             T[L.spm + j] = T[L.spp + j] = 0.0;
         }
@@ -189,7 +189,8 @@ __device__ void phase_uph_lh(const Ctx& C, Smem& S) {
 
 // proton equation (LeHaMoC.py:330-335 with the hadronic loss terms off): synchrotron cooling + escape + injection
 template <int NT>
-__device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, const LossTab* Tb) {
+__device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, const LossTab* Tb, bool per_volume = true,
+                              bool inject = true) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Np - 2;
     const bool had = C.F.pg_l || C.F.bh_l;
@@ -223,7 +224,8 @@ __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, cons
         }
         const double V2 = 1.0 + C.dt * (esc + b_syn * C.T[L.spm + j] + lm);
         const double V3 = -C.dt * (b_syn * C.T[L.spp + j] + lp);
-        const double d = H.Npr[j + 1] + (C.T[L.prinj + j + 1] * C.dt) * C.V;
+        double d = H.Npr[j + 1];
+        if (inject) d += per_volume ? (C.T[L.prinj + j + 1] * C.dt) * C.V : C.T[L.prinj + j + 1] * C.dt;
         S.cp[j] = V3 / V2;
         S.dp[j] = d / V2;
     }
@@ -261,7 +263,7 @@ __device__ void phase_electrons_lh(const Ctx& C, Smem& S, const double* Qpi) {
 
 // proton synchrotron emissivity Q_syn_space(dN_pr, M_F, nu, a_cr_pr, C_syn_pr, g_pr, m_pr), LeHaMoC.py:372
 template <int NT>
-__device__ void phase_syn_protons(const Ctx& C, Smem& S, SmemLh& H) {
+__device__ void phase_syn_protons(const Ctx& C, Smem& S, SmemLh& H, bool use_mask = true) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, Np = L.Np, Ns = L.Ns;
     const double m_el = 9.1093837015e-28, m_pr = 1.67262192369e-24;
@@ -278,7 +280,7 @@ __device__ void phase_syn_protons(const Ctx& C, Smem& S, SmemLh& H) {
         double s0 = 0.0, s1 = 0.0;
         if (C.F.syn_e && k >= 1 && k <= Ns - 2) {
             const double nu = C.T[L.nsyn + k];
-            const int jm = C.TI[L.jm_p + k];
+            const int jm = use_mask ? C.TI[L.jm_p + k] : 0;     // Q_syn_space_pr of Fit_emcee/LeHaMoC_f.py:95-98 has no mask
             for (int j0 = 0; j0 < Np; j0 += 4) {
                 double x[4], Ev[4];
 #pragma unroll

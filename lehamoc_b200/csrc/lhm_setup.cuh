@@ -38,7 +38,7 @@ __device__ __forceinline__ double logspace_pt(double a, double b, int s, int NP)
 
 template <int NT>
 __device__ void setup_lh_tables(const Layout& L, double* T, int* TI, const double* gp, const double* prinj,
-                                const double* ns, const double* nt);
+                                const double* ns, const double* nt, double one);
 
 template <int NT>
 __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
@@ -316,7 +316,7 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
     }
     if (L.Np > 0 && A.g_pr) {
         __syncthreads();
-        setup_lh_tables<NT>(L, T, TI, A.g_pr + (size_t)w * L.Np, A.pr_inj + (size_t)w * L.Np, ns, nt);
+        setup_lh_tables<NT>(L, T, TI, A.g_pr + (size_t)w * L.Np, A.pr_inj + (size_t)w * L.Np, ns, nt, one);
     }
 }
 

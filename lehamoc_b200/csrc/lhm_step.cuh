@@ -621,7 +621,7 @@ __device__ void phase_ic_finish_R(const Ctx& C, Smem& S) {
 
 // Phase G: photon equations (LeMoC.py:267-277)
 template <int NT>
-__device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
+__device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor, const double* QsynP = nullptr) {
     const Layout& L = C.L;
     const int tid = threadIdx.x;
     const double dt = C.dt, cc = kPC.c;
@@ -635,6 +635,7 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor) {
         double V3 = -dt * (b_ad * C.T[L.asp_ + j]);
         double Q = C.F.syn_e ? S.Qsyn[j + 1] / cor : 0.0;                // np.divide(Q_syn, cor_factor)
         double d = S.psyn[j + 1] + 4.0 * M_PI * (Q * dt) * C.V;
+        if (QsynP) d += 4.0 * M_PI * (QsynP[j + 1] * dt) * C.V;          // proton synchrotron, Code.py:515
         S.cp[j] = V3 / V2;
         S.dp[j] = d / V2;
     }

@@ -96,7 +96,7 @@ class Engine:
         W = batch.W
         self._check_shared(batch)
         dev = [self._dev(a) for a in batch.arrays()]
-        if self.cfg.get("driver", 0) == 1:
+        if self.cfg.get("driver", 0) >= 1:
             self._keep_pr = (self._dev(batch.g_pr), self._dev(batch.pr_inj))
             check(self.lib.lhm_set_protons(self.h, _ptr(self._keep_pr[0]), _ptr(self._keep_pr[1])), "lhm_set_protons")
         self.setup_device(W, *dev)

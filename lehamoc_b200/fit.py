@@ -32,7 +32,7 @@ from . import _lib, shard
 from ._lib import check
 from .constants import eV, pc
 from .engine import Engine, _ptr, _require_cuda
-from .setup_host import pack_code, read_parameter_file
+from .setup_host import pack_code, pack_code_lehamoc, read_parameter_file
 
 # fit_emcee.py:31-32
 D_DEFAULT = 3262    # luminosity distance (Mpc)
@@ -64,12 +64,22 @@ _PRIOR_LO = np.array([14., -2., 0., 5.0, -6., 1.5, 0., -6.0])
 _PRIOR_HI = np.array([17., 2., 4.5, 7., -2., 3., 3., 1.0])
 
 
-def log_prior_batch(thetas):
+# log_prior_LeHaMoC, fit_emcee.py:181-188: [P1..P11, log_f]
+_PRIOR_LH_LO = np.array([14., -1., 0., 4., -5., 1.1, 0., 6., -5., 1.1, 0., -7.0])
+_PRIOR_LH_HI = np.array([17., 3., 3., 6., 0., 3., 5., 10., 0., 3., 3., 1.0])
+
+
+def log_prior_batch(thetas, flag_c="LeMoC"):
     thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-    if thetas.shape[1] != 8:
-        raise ValueError("LeMoC fit: theta = [P1..P7, log_f] (8 values, fit_emcee.py:174)")
-    ok = np.all((thetas > _PRIOR_LO) & (thetas < _PRIOR_HI), axis=1)
+    lo, hi = (_PRIOR_LO, _PRIOR_HI) if flag_c == "LeMoC" else (_PRIOR_LH_LO, _PRIOR_LH_HI)
+    if thetas.shape[1] != len(lo):
+        raise ValueError(f"{flag_c} fit: theta must have {len(lo)} values (fit_emcee.py:174,182)")
+    ok = np.all((thetas > lo) & (thetas < hi), axis=1)
     return np.where(ok, 0.0, -np.inf)
+
+
+def log_prior_LeHaMoC(theta):
+    return float(log_prior_batch(np.asarray(theta, dtype=np.float64)[None, :], "LeHaMoC")[0])
 
 
 def log_prior_LeMoC(theta):
@@ -83,7 +93,11 @@ class FitEvaluator:
     """Owns the engine, the frozen parameter file and the device copy of the observed SED."""
 
     def __init__(self, x, y, yerr, yerr1, flags, param_file="Parameters.txt", D=D_DEFAULT, z=Z_DEFAULT,
-                 ic_path="R", device=None):
+                 ic_path="R", device=None, flag_c="LeMoC"):
+        if flag_c not in ("LeMoC", "LeHaMoC"):
+            raise ValueError("flag_c must be 'LeMoC' or 'LeHaMoC' (fit_emcee.py:23)")
+        self.flag_c = flag_c
+        self.nfree = 6 if flag_c == "LeMoC" else 10                 # free parameters of the numerical model
         _require_cuda()
         self.lib = _lib.load()
         self.frozen = param_file if isinstance(param_file, dict) else read_parameter_file(param_file)
@@ -113,18 +127,24 @@ class FitEvaluator:
         return self.eng
 
     def model_and_loglike(self, thetas, want_model=False):
-        """thetas [W, 8] = [P1..P6, log10 delta, log_f] -> (logl [W] device tensor, y_model [W, nd] or None).
-        No prior here (the reference evaluates the likelihood whatever the prior says, fit_emcee.py:192-193)."""
+        """thetas [W, nfree+2] = [model parameters, log10 delta, log_f] -> (logl [W] device tensor, y_model [W, nd] or
+        None).  No prior here (the reference evaluates the likelihood whatever the prior says, fit_emcee.py:192-193)."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-        W = thetas.shape[0]
-        batch = pack_code(thetas[:, :6], self.frozen)
-        eng = self._engine(batch)
-        eng.setup(batch)
-        _, sed = eng.run(want_N=False)                               # [W, Nt] on the device
+        W, nf = thetas.shape[0], self.nfree
+        if self.flag_c == "LeMoC":
+            batch = pack_code(thetas[:, :nf], self.frozen)
+            eng = self._engine(batch)
+            eng.setup(batch)
+            _, sed = eng.run(want_N=False)                           # [W, Nt] on the device
+        else:
+            batch = pack_code_lehamoc(thetas[:, :nf], self.frozen)
+            eng = self._engine(batch)
+            eng.setup(batch)
+            sed = eng.run_lh(snapshots=0)[1][:, 0]
         nu_tot = eng._keep[4]
         dev = sed.device
-        dop = torch.from_numpy(np.ascontiguousarray(thetas[:, 6])).to(dev)
-        logf = torch.from_numpy(np.ascontiguousarray(thetas[:, 7])).to(dev)
+        dop = torch.from_numpy(np.ascontiguousarray(thetas[:, nf])).to(dev)
+        logf = torch.from_numpy(np.ascontiguousarray(thetas[:, nf + 1])).to(dev)
         logl = torch.empty(W, dtype=torch.float64, device=dev)
         ym = torch.empty((W, self.nd), dtype=torch.float64, device=dev) if want_model else None
         sed = sed.contiguous()
@@ -137,7 +157,7 @@ class FitEvaluator:
     def log_probability(self, thetas):
         """[W] NumPy array; -inf outside the prior box (those walkers are not evolved at all)."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
-        lp = log_prior_batch(thetas)
+        lp = log_prior_batch(thetas, self.flag_c)
         out = np.full(thetas.shape[0], -np.inf)
         inside = np.isfinite(lp)
         if inside.any():
@@ -157,11 +177,11 @@ class FitEvaluator:
 _evaluators = {}
 
 
-def _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path):
-    key = (param_file if isinstance(param_file, str) else id(param_file), D, z, ic_path)
+def _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c="LeMoC"):
+    key = (param_file if isinstance(param_file, str) else id(param_file), D, z, ic_path, flag_c)
     ev = _evaluators.get(key)
     if ev is None:
-        ev = FitEvaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path)
+        ev = FitEvaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c=flag_c)
         _evaluators[key] = ev
     else:
         ev.set_data(x, y, yerr, yerr1, flags)
@@ -192,13 +212,17 @@ def log_likelihood_LeMoC(theta, x, y, yerr, yerr1, flags, param_file="Parameters
     return float(logl[0].item())
 
 
+def log_likelihood_LeHaMoC(theta, x, y, yerr, yerr1, flags, param_file="Parameters.txt", D=D_DEFAULT, z=Z_DEFAULT):
+    """fit_emcee.py:147-171: theta = [P1..P11, log_f], model Code.LeHaMoC."""
+    ev = _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, "R", "LeHaMoC")
+    logl, _ = ev.model_and_loglike(np.asarray(theta, dtype=np.float64)[None, :])
+    return float(logl[0].item())
+
+
 def log_probability_batch(thetas, x, y, yerr, yerr1, flags, flag_c="LeMoC", param_file="Parameters.txt",
                           D=D_DEFAULT, z=Z_DEFAULT, ic_path="R"):
-    """fit_emcee.py:190-199 for thetas [W, 8] at once -> [W]."""
-    if flag_c != "LeMoC":
-        raise NotImplementedError("flag_c='LeHaMoC': the leptohadronic model is scheduled after the leptonic "
-                                  "path (DESIGN.md section 8)")
-    return _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path).log_probability_sharded(thetas)
+    """fit_emcee.py:190-199 for thetas [W, 8] (LeMoC) or [W, 12] (LeHaMoC) at once -> [W]."""
+    return _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c).log_probability_sharded(thetas)
 
 
 def log_probability(theta, x, y, yerr, yerr1, flags, flag_c):
@@ -270,7 +294,10 @@ def main(argv=None):
     flag_c, steps = argv[1], int(argv[2])
     directory = 'chains' + argv[3] + '/' + flag_c
     os.makedirs(directory, exist_ok=True)
-    params = [15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3]                   # fit_emcee.py:208
+    if flag_c == 'LeMoC':
+        params = [15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3]               # fit_emcee.py:208
+    else:
+        params = [15.5, 1., 0.5, 5., -3., 1.2, 0.5, 7.3, -4.5, 2., 1.]          # fit_emcee.py:212
     xd, yd, yderr_hi, yderr_lo, flags = read_data('OUsed_5BZBJ09553551-11jan2020.txt', 'SED_fermi_data.txt')
     init = [*params, -2]
     pos = init + 1e-2 * np.random.default_rng(0).standard_normal((48, len(init)))   # fit_emcee.py:224-225

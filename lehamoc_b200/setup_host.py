@@ -399,3 +399,36 @@ def pack_code(thetas, frozen: dict) -> Batch:
     comp_cor = thetas[:, 4].copy()                                             # Code.py:237 passes the log value
     return _pack("code", frozen, R0, B0, g_PL_min - 1., g_PL_max + 1., g_PL_min, g_PL_max, thetas[:, 5].copy(),
                  comp_inj, comp_cor)
+
+
+def pack_code_lehamoc(thetas, frozen: dict) -> Batch:
+    """Batch for Fit_emcee/Code.py::LeHaMoC (Code.py:280-535, leptonic + proton synchrotron).  thetas [W,10] =
+    [log R0, log B0, log g_min, log g_max, log l_e, p_e, log g_min_pr, log g_max_pr, log l_p, p_p]."""
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    if thetas.shape[1] != 10:
+        raise ValueError("Code.LeHaMoC takes 10 free parameters (Code.py:285-295)")
+    missing = [k for k in CODE_KEYS + ("grid_g_pr",) if k not in frozen and k != "Ad_l_flag"]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    F = dict(frozen, Ad_l_flag=0.)                                              # Code.py:281: no adiabatic losses
+    R0 = np.array([10 ** x for x in thetas[:, 0].tolist()])
+    B0 = np.array([10 ** x for x in thetas[:, 1].tolist()])
+    g_PL_min, g_PL_max = thetas[:, 2].copy(), thetas[:, 3].copy()
+    comp_inj = np.array([10 ** x for x in thetas[:, 4].tolist()])
+    b = _pack("code", F, R0, B0, g_PL_min - 0.5, g_PL_max + 0.5, g_PL_min, g_PL_max, thetas[:, 5].copy(),
+              comp_inj, thetas[:, 4].copy())                                    # Code.py:297-298
+    W, Np = b.W, int(float(F["grid_g_pr"]))
+    g_pr = np.empty((W, Np))
+    pr_inj = np.full((W, Np), SENTINEL)
+    for w in range(W):                                                          # Code.py:299-300,325-347,419-422
+        gmin_pr, gmax_pr = float(thetas[w, 6]) - 0.1, float(thetas[w, 7]) + 0.5
+        gp = np.logspace(gmin_pr, gmax_pr, Np)
+        ip_max = -1 if float(thetas[w, 7]) == gmax_pr else int(np.min(np.where(gp > 10 ** float(thetas[w, 7]))[0]))
+        ip_min = 1 if float(thetas[w, 6]) == 0. else int(np.max(np.where(gp < 10 ** float(thetas[w, 6]))[0]))
+        Lp = 4. * np.pi * R0[w] * m_pr_ * c ** 3. * (10 ** float(thetas[w, 8])) / sigmaT
+        pr_inj[w, ip_min:ip_max] = _Q_pr_Lum(Lp, float(thetas[w, 9]), gp[ip_min], gp[ip_max]) * gp[ip_min:ip_max] ** (-float(thetas[w, 9]))
+        g_pr[w] = gp
+    b.cfg.update(driver=2, Np=Np, esc_flag_pr=b.cfg["esc_flag"], shared_ic_grids=0)
+    b.variant = "code_lh"
+    b.g_pr, b.pr_inj = g_pr, pr_inj
+    return b

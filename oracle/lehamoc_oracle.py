@@ -340,11 +340,27 @@ class LeptonicRun:
             self.g_max_el = self.g_PL_max + 1.
             self.comp_inj = 10 ** theta[4]                        # Code.py:163
             self.comp_cor = theta[4]                              # Code.py:237 (raw log value)
+        elif variant == "code_lh":                                # Code.py:280-300 (proton-synchrotron model)
+            self.R0 = 10 ** theta[0]
+            self.B0 = 10 ** theta[1]
+            self.g_PL_min, self.g_PL_max = theta[2], theta[3]
+            self.p_el = theta[5]
+            self.g_min_el = self.g_PL_min - 0.5
+            self.g_max_el = self.g_PL_max + 0.5
+            self.comp_inj = 10 ** theta[4]
+            self.comp_cor = theta[4]
+            self.g_PL_min_pr, self.g_PL_max_pr, self.comp_pr, self.p_pr = theta[6], theta[7], theta[8], theta[9]
+            self.g_min_pr = self.g_PL_min_pr - 0.1
+            self.g_max_pr = self.g_PL_max_pr + 0.5
+            self.grid_g_pr = g('grid_g_pr')
         else:
             raise ValueError(variant)
         self.grid_g_el, self.grid_nu = g('grid_g_el'), g('grid_nu')
         self.Vexp = g('Vexp') * c
         self.m = g('m')
+        if variant == "code_lh":
+            P = dict(P, Ad_l_flag=0.)                             # Code.py:281: no adiabatic losses in this model
+            g = lambda k: float(P[k])
         for k in ('inj_flag', 'Ad_l_flag', 'Syn_l_flag', 'Syn_emis_flag', 'IC_l_flag', 'IC_emis_flag',
                   'SSA_l_flag', 'gg_flag', 'esc_flag', 'BB_flag', 'GB_ext', 'PL_flag', 'dE_dV_ph',
                   'nu_min_ph', 'nu_max_ph', 's_ph', 'User_ph'):
@@ -419,10 +435,28 @@ class LeptonicRun:
         self.Radius = R0
         self.nstep = 0
         self.trace = {}
+        if self.variant == "code_lh":                             # Code.py:325-331,341-347,419-425
+            gp = np.logspace(self.g_min_pr, self.g_max_pr, int(self.grid_g_pr))
+            self.g_pr = gp
+            self.g_pr_mp = np.array([(gp[i + 1] + gp[i - 1]) / 2. for i in range(0, len(gp) - 1)])
+            self.dg_pr = np.array([(gp[i + 1] - gp[i - 1]) / 2. for i in range(1, len(gp) - 1)])
+            ipmax = -1 if self.g_PL_max_pr == self.g_max_pr else int(np.min(np.where(gp > 10 ** self.g_PL_max_pr)[0]))
+            ipmin = 1 if self.g_PL_min_pr == 0. else int(np.max(np.where(gp < 10 ** self.g_PL_min_pr)[0]))
+            pr_inj = np.ones(len(gp)) * SENT
+            Lp = 4. * np.pi * R0 * m_pr * c ** 3. * (10 ** self.comp_pr) / sigmaT
+            if self.p_pr == 2.:
+                Q0 = Lp / (m_pr * c ** 2. * np.log(gp[ipmax] / gp[ipmin]))
+            else:
+                Q0 = Lp * (-self.p_pr + 2.) / (m_pr * c ** 2. * (gp[ipmax] ** (-self.p_pr + 2.) - gp[ipmin] ** (-self.p_pr + 2.)))
+            pr_inj[ipmin:ipmax] = Q0 * gp[ipmin:ipmax] ** (-self.p_pr)
+            self.pr_inj = pr_inj
+            self.N_pr = pr_inj.copy()
+            self.N_pr[0] = self.N_pr[-1] = SENT
 
     def n_steps(self):
         if self.variant == "script":
             return int(self.time_end)                             # LeMoC.py:196
+        # Code.py:183 / :447
         n, t = 0, self.time_init                                  # Code.py:183
         while t < self.time_end * self.R0 / c:
             t += self.dt
@@ -489,6 +523,28 @@ class LeptonicRun:
             raise ValueError("inj_flag must be 0 or 1 (the reference leaves S_ij undefined otherwise)")
         self.N_el[1:-1] = bidiag_solve(V2, V3, S)
         ne = np.array(self.N_el / V)
+        Q_syn_pr = None
+        if self.variant == "code_lh":                             # Code.py:480-490,494
+            pm, dgp = self.g_pr_mp, self.dg_pr
+            if self.Syn_l_flag == 1.:
+                b_p = (4. / 3.) * sigmaT / (8. * np.pi * m_el * c) * M_F ** 2. * (m_el / m_pr) ** 3.
+                sp_m, sp_p = b_p * np.power(pm[0:-1], 2.) / dgp, b_p * np.power(pm[1:], 2.) / dgp
+            else:
+                sp_m = sp_p = np.zeros(len(self.g_pr) - 2)
+            V2p = 1. + dt * (c / Radius * self.esc_flag + sp_m)
+            V3p = -dt * sp_p
+            Sp = self.N_pr[1:-1] + (np.multiply(self.pr_inj[1:-1], dt) if self.inj_flag == 1. else 0.)
+            self.N_pr[1:-1] = bidiag_solve(V2p, V3p, Sp)
+            if self.Syn_emis_flag == 1.:
+                n_p = np.array(self.N_pr / V)
+                a_cr_pr = 3. * q * M_F / (4. * np.pi * m_pr * c)
+                C_pr = sigmaT * c / (h * 24. * np.pi ** 2. * 0.8975) * (4. * np.pi * m_pr * c / (3. * q)) ** (4. / 3.) * (m_el / m_pr) ** 2.
+                nus = np.asarray(nu_syn[:-1])[:, None]
+                with np.errstate(under="ignore"):
+                    integ = n_p[None, :] * self.g_pr[None, :] ** (1. / 3.) * np.exp(-nus / (a_cr_pr * self.g_pr[None, :] ** 2.))
+                Q_syn_pr = C_pr * M_F ** (2. / 3.) * nus[:, 0] ** (-2. / 3.) * np.trapz(integ, np.log(self.g_pr), axis=1)
+            else:
+                Q_syn_pr = np.zeros(len(nu_syn) - 1)
         if self.Syn_emis_flag == 1.:
             if self.literal:
                 Qs = np.array([Q_syn_space(ne, M_F, nu_syn[k], a_cr, g_el) for k in range(len(nu_syn) - 1)])
@@ -520,6 +576,8 @@ class LeptonicRun:
         V2 = 1. + dt * (c / Radius + ads_m - np.multiply(aS[1:-1], 1) * c)
         V3 = -dt * ads_p
         S = self.photons_syn[1:-1] + 4. * np.pi * np.multiply(Q_syn, dt)[1:] * V
+        if Q_syn_pr is not None:
+            S = S + 4. * np.pi * np.multiply(Q_syn_pr, dt)[1:] * V  # Code.py:515
         self.photons_syn[1:-1] = bidiag_solve(V2, V3, S)
         V2 = 1. + dt * (c / Radius + adi_m + np.multiply(self.a_gg_f[1:-1], c) - np.multiply(aI[1:-1], 1) * c)
         V3 = -dt * adi_p
@@ -566,6 +624,14 @@ def run_script(param_file_or_dict, literal=False, record=False, hoist_cor=True):
     run = LeptonicRun(P, "script", literal=literal, hoist_cor=hoist_cor)
     ne, sed = run.run(record=record)
     return run, ne, sed
+
+
+def code_LeHaMoC(theta, param_file_or_dict, literal=False, hoist_cor=True):
+    """Fit_emcee/Code.py::LeHaMoC(params[10], fileName) -> (nu_tot, nuLnu of the last step)."""
+    P = param_file_or_dict if isinstance(param_file_or_dict, dict) else read_parameter_file(param_file_or_dict)
+    run = LeptonicRun(P, "code_lh", theta=list(theta), literal=literal, hoist_cor=hoist_cor)
+    _, sed = run.run()
+    return run.nu_tot, sed[-1]
 
 
 def code_LeMoC(theta, param_file_or_dict, literal=False, hoist_cor=True):

@@ -83,5 +83,32 @@ def main():
     print("logprob", np.array(lprob))
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and (len(sys.argv) == 1 or sys.argv[1] != "code_lehamoc"):
     main()
+
+
+def make_code_lehamoc():
+    """tests/golden/code_lh_fit.npz: Fit_emcee/Code.py::LeHaMoC (proton-synchrotron model) at the reference's hadronic
+    start point (fit_emcee.py:212) and perturbed walkers, run unmodified."""
+    cf = np.load(os.path.join(GOLD, "code_fit.npz"))
+    keys = [str(k) for k in cf["param_keys"]]
+    rng = np.random.default_rng(77)
+    start = np.array([15.5, 1., 0.5, 5., -3., 1.2, 0.5, 7.3, -4.5, 2.])
+    lo = np.array([14.5, -0.5, 0.2, 4.2, -4.5, 1.3, 0.3, 6.5, -5.0, 1.6])
+    hi = np.array([16.5, 2.0, 2.5, 5.8, -2.0, 2.8, 2.0, 9.0, -2.0, 2.8])
+    thetas = [start] + [lo + (hi - lo) * rng.random(10) for _ in range(4)]
+    thetas[1][9] = 2.0                                              # p_pr == 2 branch of Q_pr_Lum
+    nus, seds = [], []
+    for th in thetas:
+        nu, sed, wall = rr.run_code_lehamoc(th, "Parameters.txt")
+        nus.append(nu), seds.append(sed)
+        print(f"Code.LeHaMoC {np.round(th, 3)}: {wall:.1f} s")
+    out = {"thetas": np.array(thetas), "nu_tot": np.array(nus), "nuLnu": np.array(seds),
+           "param_keys": cf["param_keys"], "param_vals": cf["param_vals"]}
+    path = os.path.join(GOLD, "code_lh_fit.npz")
+    np.savez_compressed(path, **out)
+    print("wrote", path)
+
+
+if __name__ == "__main__" and len(sys.argv) > 1 and sys.argv[1] == "code_lehamoc":
+    make_code_lehamoc()

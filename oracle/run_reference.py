@@ -204,6 +204,20 @@ def run_code_lemoc(params, param_file="Parameters.txt", memo_cor: bool = True):
     return np.array(nu), np.array(sed), wall
 
 
+def run_code_lehamoc(params, param_file="Parameters.txt", memo_cor: bool = True):
+    """Fit_emcee/Code.py::LeHaMoC(params[10], fileName) -> (nu_tot, nuLnu), wall seconds (proton-synchrotron model)."""
+    with _ref_env("Fit_emcee") as (ref_dir, tmp):
+        f = importlib.import_module("LeHaMoC_f")
+        Recorder(f, memo_cor=memo_cor)
+        code = importlib.import_module("Code")
+        pf = param_file if os.path.isabs(param_file) else os.path.join(ref_dir, param_file)
+        t0 = time.perf_counter()
+        with np.errstate(all="ignore"):
+            nu, sed = code.LeHaMoC(list(params), pf)
+        wall = time.perf_counter() - t0
+    return np.array(nu), np.array(sed), wall
+
+
 def reference_functions(subdir="LeMoC"):
     """Context manager yielding the reference's function library module (unwrapped)."""
     @contextlib.contextmanager

@@ -137,3 +137,37 @@ def test_gpu_mcmc_smoke(gold):
                                               gold["flags"], "LeMoC", param_file=P)
     res = fit.run_mcmc(fn, pos, 3, seed=1)
     assert res["chain"].shape == (3, 16, 8) and np.all(np.isfinite(res["log_prob"]))
+
+
+def test_lehamoc_prior():
+    from lehamoc_b200 import fit
+    th = [15.5, 1., 0.5, 5., -3., 1.2, 0.5, 7.3, -4.5, 2., 1., -2.]          # fit_emcee.py:212 + log_f
+    assert fit.log_prior_LeHaMoC(th) == 0.0
+    bad = list(th); bad[7] = 10.5
+    assert fit.log_prior_LeHaMoC(bad) == -np.inf
+    with pytest.raises(ValueError):
+        fit.log_prior_batch(np.zeros((2, 8)), "LeHaMoC")
+
+
+@pytest.mark.gpu
+def test_gpu_loglike_lehamoc_model(gold):
+    """flag_c = 'LeHaMoC': Code.LeHaMoC spectra through the same epilogue; checked against the restated likelihood
+    evaluated on the REFERENCE's Code.LeHaMoC spectra."""
+    from lehamoc_b200 import fit
+    z, P = load_golden("code_lh_fit")
+    W = len(z["thetas"])
+    th12 = np.column_stack([z["thetas"], np.linspace(0.8, 1.6, W), np.linspace(-3., -1., W)])
+    ev = fit.FitEvaluator(gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"], param_file=P,
+                          D=float(gold["D_Mpc"]), z=float(gold["z"]), flag_c="LeHaMoC")
+    logl, ym = ev.model_and_loglike(th12, want_model=True)
+    m = orc.Model(lambda th, f: None, D=float(gold["D_Mpc"]), z=float(gold["z"]))
+    for k in range(W):
+        ym_ref = m.transform(gold["xd"], z["nu_tot"][k], z["nuLnu"][k], th12[k, 10])
+        assert np.max(np.abs(ym[k].cpu().numpy() - ym_ref)) <= 4.3e-9
+        ll_ref = orc.log_likelihood_from_model(ym_ref, th12[k, 11], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"])
+        if np.isinf(ll_ref):                      # an upper limit violated by many sigma: log(1 + erf(-x)) = -inf in both
+            assert float(logl[k]) == ll_ref
+        else:
+            assert abs(float(logl[k]) - ll_ref) <= 1e-6 * abs(ll_ref)
+    lp = ev.log_probability(th12)
+    assert lp.shape == (W,)

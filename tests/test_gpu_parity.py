@@ -337,3 +337,16 @@ def test_run_many_matches_run():
     for (_, N, sed), (_, Nr, sedr) in zip(got, ref):
         np.testing.assert_array_equal(sed, sedr[:, 0])
         np.testing.assert_array_equal(N, Nr[:, 0])
+
+
+def test_code_lehamoc_matches_reference():
+    """Fit_emcee/Code.py::LeHaMoC (leptonic + proton synchrotron) at the reference's hadronic start point and four
+    perturbed walkers, one launch."""
+    from lehamoc_b200 import Code
+    z, P = load_golden("code_lh_fit")
+    nu, sed = Code.LeHaMoC_batch(z["thetas"], P)
+    for i in range(len(z["thetas"])):
+        np.testing.assert_array_equal(nu[i], z["nu_tot"][i])
+        assert_spectra_close(sed[i], z["nuLnu"][i], f"Code.LeHaMoC walker {i}")
+    nu1, sed1 = Code.LeHaMoC(list(z["thetas"][2]), P)
+    np.testing.assert_array_equal(sed1, sed[2])

@@ -106,3 +106,13 @@ def test_likelihood_restatement_self_consistency():
     assert ll0 > ll1
     assert orc.log_prior_LeMoC([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2]) == 0.0
     assert orc.log_prior_LeMoC([13.0, 0.038818, 3., 6.081445, -4., 2., 1.3, -2]) == -np.inf
+
+
+def test_oracle_code_lehamoc():
+    """Fit_emcee/Code.py::LeHaMoC (proton-synchrotron model) against the unmodified reference."""
+    z, P = load_golden("code_lh_fit")
+    for th, nu, sed in zip(z["thetas"], z["nu_tot"], z["nuLnu"]):
+        nu_o, sed_o = orc.code_LeHaMoC(th, P)
+        np.testing.assert_array_equal(nu_o, nu)
+        m = sed > sed.max() * 1e-200
+        assert _rel(sed_o[m], sed[m]) < 1e-11
