@@ -124,3 +124,87 @@ def Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons_targ, nu_target, flag_product):
                                   C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lhm_photopion_batch")
     r = out.cpu().numpy()
     return r[0] if np.ndim(g_el) == 1 else r
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# A13 Bethe-Heitler pair injection: host set-up (LeHaMoC_f.py:238-341).  The reference tabulates the energy-integrated
+# differential cross section on a 30 x 30 x 30 lattice (27 000 Simpson integrals) and fits two smoothing bivariate
+# splines with scipy.interpolate.bisplrep; that fit stays on the host (SciPy/FITPACK, as in the reference), the spline
+# EVALUATION (4.8 M bisplev calls per step in the reference) runs on the GPU.
+# ---------------------------------------------------------------------------------------------------------------------
+def _cs_BH_diff(E_, g_pr, g_el, k):
+    """Differential Bethe-Heitler cross section d sigma/(d theta dE_) of Blumenthal (1970), LeHaMoC_f.py:238-273,
+    for an array of electron energies E_ (same elementwise arithmetic, so the doubles are the reference's)."""
+    from .constants import sigmaT
+    with np.errstate(all="ignore"):
+        E_p = k - E_
+        E_p = np.where(np.isnan(E_p), 0, E_p)
+        E_p[E_p < 0] = 0
+        p_ = np.sqrt(E_ ** 2 - 1.)
+        p_[p_ < 0] = 0.
+        p_p = np.sqrt(E_p ** 2. - 1.)
+        p_p = np.where(np.isnan(p_p), 0, p_p)
+        p_p[p_p < 0] = 0
+        cos_th_ = (g_pr * E_ - g_el) / (g_pr * p_)
+        T = np.sqrt(k ** 2. + p_ ** 2. - 2. * k * p_ * cos_th_)
+        T[T < 0] = 0.
+        D_ = (E_ - p_ * cos_th_)
+        D_ = np.where(np.isnan(D_), 0, D_)
+        D_[D_ < 0.] = 0.
+        Y = (2. / p_ ** 2.) * np.log((E_ * E_p + p_ * p_p + 1.) / k)
+        Y = np.where(np.isnan(Y), 0, Y)
+        Y[Y < 0] = 0.
+        y_plus = p_p ** (-1.) * np.log((E_p + p_p) / (E_p - p_p))
+        y_plus = np.where(np.isnan(y_plus), 0, y_plus)
+        y_plus[y_plus < 0.] = 0.
+        d_plus_T = np.log((T + p_p) / (T - p_p))
+        d_plus_T = np.where(np.isnan(d_plus_T), 0, d_plus_T)
+        d_plus_T[d_plus_T < 0.] = 0.
+        sin2 = (np.sin(np.arccos(cos_th_))) ** 2.
+        return 3. / (8. * np.pi * 137.) * sigmaT * p_p * p_ / k ** 3. * (
+            -4. * sin2 * (2. * E_ ** 2. + 1.) / (p_ ** 2. * D_ ** 4.)
+            + (5. * E_ ** 2. - 2. * E_ * E_p + 3.) / (p_ ** 2. * D_ ** 2.) + (p_ ** 2. - k ** 2.) / (T ** 2. * D_ ** 2.)
+            + 2. * E_p / (p_ ** 2. * D_)
+            + Y / (p_ * p_p) * (2. * E_ * sin2 * (3. * k + p_ ** 2. * E_p) / D_ ** 4.
+                                + (2. * E_ ** 2 * (E_ ** 2. + E_p ** 2.) - 7. * E_ ** 2. - 3. * E_ * E_p - E_p ** 2. + 1.) / D_ ** 2.
+                                + k * (E_ ** 2. - E_ * E_p - 1.) / D_)
+            - d_plus_T / (p_p * T) * (2. / D_ ** 2. - 3. * k / D_ - k * (p_ ** 2. - k ** 2.) / (T ** 2. * D_))
+            - 2. * y_plus / D_) / p_
+
+
+def interp_cs_BH_int(g_pr, g_el, nu_int_min, nu_int_max):
+    """LeHaMoC_f.py:276-341: returns (tck_m, tck_p, max_m, max_p), the two smoothing-spline surfaces of
+    log10 int sigma_BH E dlnE over (log10 Ee_min, log10 Ee_max) for gamma_p < gamma_e and gamma_p > gamma_e."""
+    from scipy import integrate, interpolate
+    from .constants import h, m_el, c
+    if not hasattr(np, "trapz"):
+        np.trapz = np.trapezoid
+    gp_i = np.logspace(np.log10(g_pr[0]), np.log10(g_pr[-1]), 30)
+    ge_i = np.logspace(np.log10(g_el[0]), np.log10(g_el[-1]), 30)
+    x = np.logspace(np.log10(h * nu_int_min / (m_el * c ** 2.)), np.log10(h * nu_int_max / (m_el * c ** 2.)), 30)
+    lists = {"p": ([], [], []), "m": ([], [], [])}
+    with np.errstate(all="ignore"):
+        for gp in gp_i:
+            for ge in ge_i:
+                if gp == ge:
+                    continue
+                key = "p" if gp > ge else "m"
+                E_min = (gp ** 2. + ge ** 2.) / (2. * gp * ge)
+                for xj in x:
+                    w = (2. * gp * xj)
+                    E_array = np.logspace(np.log10(E_min), np.log10(w - 1.))
+                    if E_array[0] < E_array[-1]:
+                        sBH = _cs_BH_diff(E_array, gp, ge, w)
+                        sBH = np.where(np.isnan(sBH), 0., sBH)
+                        res = integrate.simpson(sBH * E_array, x=np.log(E_array))
+                        lists[key][0].append(E_array[0]); lists[key][1].append(E_array[-1]); lists[key][2].append(res)
+    out = {}
+    for key in ("m", "p"):
+        Emin, Emax, tot = (np.array(v) for v in lists[key])
+        with np.errstate(all="ignore"):
+            z = np.where(np.isnan(np.log10(tot)), 0.1, np.log10(tot))
+        z[z == -np.inf] = 0.
+        keep = np.where(z < -15)[0]
+        xs, ys, zs = np.log10(Emin)[keep], np.log10(Emax)[keep], z[keep]
+        out[key] = (interpolate.bisplrep(list(xs), list(ys), list(zs), s=2), max(zs))
+    return out["m"][0], out["p"][0], out["m"][1], out["p"][1]

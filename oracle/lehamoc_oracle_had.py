@@ -192,3 +192,54 @@ def Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons_targ, nu_target, flag, T, h_0=H_0,
             inner[gi] = np.trapz(ph * Phi * nu_t, np.log(h * nu_t))
         out[k] = np.trapz(pref * N_t * inner / (m_pr * c ** 2.), np.log(g_t))
     return out
+
+
+# ---- A13 Bethe-Heitler pair injection, LeHaMoC_f.py:566-616 ------------------------------------------------------------
+def Q_BH_sol(g_el, g_pr, N_pr, nu_trgt, photons_trgt, intrp_cs_m, intrp_cs_p, max_m, max_p):
+    """nu_trgt is the dimensionless photon energy grid h nu/(m_e c^2) (LeHaMoC.py:338).  The spline surfaces come from
+    SciPy's bisplrep (host set-up interp_cs_BH_int); evaluation by scipy.interpolate.bisplev, integrals by
+    scipy.integrate.simpson of the installed SciPy (its treatment of an even number of samples is part of the pin)."""
+    from scipy import integrate, interpolate
+    dnde = np.zeros(len(g_el))
+    with np.errstate(divide="ignore"):
+        lph = np.log10(photons_trgt)
+    for i, ge in enumerate(g_el):
+        g_pr_int = []
+        for j, gp in enumerate(g_pr):
+            Emin = (gp + ge) ** 2 / (4. * gp ** 2 * ge)
+            Emax = m_pr / (gp * m_el)
+            if Emin < Emax:
+                E_arr = np.logspace(np.log10(1.001 * Emin), np.log10(Emax), 10)
+                f_ph = 10 ** np.interp(E_arr, nu_trgt, lph) * m_el * c ** 2. / (h * E_arr ** 2)      # linear-x interpolation
+                temp_ph = []
+                Ee_min = (gp ** 2 + ge ** 2) / (2 * gp * ge)
+                wmin = (gp + ge) ** 2 / (2 * gp * ge)
+                for Eph in E_arr:
+                    wmax = 2 * gp * Eph
+                    if wmin < wmax:
+                        w_arr = np.logspace(np.log10(wmin), np.log10(wmax), 10)
+                        tw = []
+                        for w in w_arr:
+                            Ee_max = w - 1
+                            ok = Ee_min < Ee_max and Ee_min < 80. / 100. * Ee_max
+                            if ok and gp > ge:
+                                zn = interpolate.bisplev(np.log10(Ee_min), np.log10(Ee_max), intrp_cs_p)
+                                if zn > max_p:
+                                    zn = 0.
+                                tw.append(w * 10 ** zn)
+                            elif ok and gp < ge:
+                                zn = interpolate.bisplev(np.log10(Ee_min), np.log10(Ee_max), intrp_cs_m)
+                                if zn > max_m:
+                                    zn = 0.
+                                tw.append(w * 10 ** zn)
+                            else:
+                                tw.append(0)
+                        temp_ph.append(integrate.simpson(tw * w_arr, x=np.log(w_arr)))
+                    else:
+                        temp_ph.append(0)
+                    temp_ph = list(np.where(np.array(temp_ph) < 0., 0., np.array(temp_ph, dtype=np.float64)))
+                g_pr_int.append(N_pr[j] * integrate.simpson(f_ph * temp_ph * E_arr, x=np.log(E_arr)) / (2. * gp ** 3.))
+            else:
+                g_pr_int.append(0.)
+        dnde[i] = integrate.simpson(g_pr_int * g_pr, x=np.log(g_pr)) if len(g_pr_int) else 0.
+    return c * dnde

@@ -88,6 +88,24 @@ def main():
                         f.Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons, nu, sp))
                     print(f"case {case}: Qp_g_opt {sp!r} {time.time() - t0:.1f} s")
         out["E_nu_space"] = np.array(f.E_nu_space)
+        # A13: the Bethe-Heitler spline surfaces (host set-up, 8 s) and Q_BH_sol on a reduced (gamma_e, gamma_p) lattice
+        with np.errstate(all="ignore"):
+            t0 = time.time()
+            nu0, nu1 = 10 ** 7.5, 1e32
+            tm, tp, mm, mp_ = f.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu0, nu1)
+            print(f"interp_cs_BH_int {time.time() - t0:.1f} s")
+            for nm, t in (("m", tm), ("p", tp)):
+                out[f"bh_t{nm}_tx"], out[f"bh_t{nm}_ty"], out[f"bh_t{nm}_c"] = (np.asarray(a) for a in t[:3])
+                assert t[3] == 3 and t[4] == 3
+            out["bh_max_m"], out["bh_max_p"], out["bh_nu_range"] = np.float64(mm), np.float64(mp_), np.array([nu0, nu1])
+            for case in range(2):
+                nu, photons, g_pr, N_pr, g_el, nu_ic = fields(100 + case)
+                ge, gp = np.logspace(0., 9., 14), g_pr[::2]
+                t0 = time.time()
+                out[f"c{case}_bh_g_el"], out[f"c{case}_bh_g_pr"], out[f"c{case}_bh_N_pr"] = ge, gp, N_pr[::2]
+                out[f"c{case}_Q_BH"] = np.array(f.Q_BH_sol(ge, gp, N_pr[::2], nu * f.h / (f.m_el * f.c ** 2.), photons,
+                                                           tm, tp, mm, mp_))
+                print(f"case {case}: Q_BH_sol {time.time() - t0:.1f} s", out[f"c{case}_Q_BH"][:4])
     path = os.path.join(GOLD, "had_functions.npz")
     np.savez_compressed(path, **out)
     print("wrote", path)

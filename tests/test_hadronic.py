@@ -99,3 +99,31 @@ def test_gpu_hadronic_batch_equals_single(gold):
     lb = had.dg_dt_pg(np.stack([gold["c0_g_pr"], gold["c1_g_pr"]]), np.stack([gold["c0_nu"], gold["c1_nu"]]),
                       np.stack([gold["c0_photons"], gold["c1_photons"]]))
     np.testing.assert_array_equal(lb[1], had.dg_dt_pg(gold["c1_g_pr"], gold["c1_nu"], gold["c1_photons"]))
+
+
+# ---- A13 Bethe-Heitler pair injection -------------------------------------------------------------------------
+def bh_tck(gold, which):
+    return [gold[f"bh_t{which}_tx"], gold[f"bh_t{which}_ty"], gold[f"bh_t{which}_c"], 3, 3]
+
+
+@pytest.mark.parametrize("case", [0, 1])
+def test_oracle_Q_BH_sol(gold, case):
+    from lehamoc_oracle import c, h, m_el
+    p = f"c{case}_"
+    x = gold[p + "nu"] * h / (m_el * c ** 2.)
+    got = oh.Q_BH_sol(gold[p + "bh_g_el"], gold[p + "bh_g_pr"], gold[p + "bh_N_pr"], x, gold[p + "photons"],
+                      bh_tck(gold, "m"), bh_tck(gold, "p"), float(gold["bh_max_m"]), float(gold["bh_max_p"]))
+    rel_close(got, gold[p + "Q_BH"], 1e-12, "Q_BH_sol")
+    assert np.any(got > 0)
+
+
+def test_host_bh_surface_setup_is_the_references(gold):
+    """lehamoc_b200.hadronic.interp_cs_BH_int (27 000 Simpson integrals + two bisplrep fits, host) reproduces the
+    reference's spline surfaces bit for bit (same SciPy)."""
+    from lehamoc_b200 import hadronic
+    nu0, nu1 = gold["bh_nu_range"]
+    tm, tp, mm, mp_ = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu0, nu1)
+    for ours, which in ((tm, "m"), (tp, "p")):
+        for a, b in zip(ours[:3], bh_tck(gold, which)[:3]):
+            np.testing.assert_array_equal(np.asarray(a), b)
+    assert mm == float(gold["bh_max_m"]) and mp_ == float(gold["bh_max_p"])
