@@ -205,6 +205,19 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
                         const double* photons, const double* nu_target, const lhm_had_tables* tables, double* out,
                         void* cuda_stream);
 
+/* A13 Bethe-Heitler pair injection Q_BH_sol (LeHaMoC_f.py:566-616).  The two smoothing-spline surfaces (tck of
+ * scipy.interpolate.bisplrep, kx = ky = 3; host set-up interp_cs_BH_int, LeHaMoC_f.py:276-341) are given as DEVICE
+ * pointers: knots tx [nx], ty [ny], coefficients c [(nx-4)*(ny-4)]; zmax = max_intrp_cs.  g_el [W,Ng]; g_pr, N_pr [W,Np]
+ * (dN_pr/dV dgamma); x_target [W,Nt] = h nu/(m_e c^2); photons [W,Nt]; out [W,Ng] (the driver uses [1:-1]). */
+typedef struct {
+    const double *tx, *ty, *c;
+    int nx, ny;
+    double zmax;
+} lhm_bh_surface;
+int lhm_bh_emis_batch(int W, int Ng, int Np, int Nt, const double* g_el, const double* g_pr, const double* N_pr,
+                      const double* x_target, const double* photons, const lhm_bh_surface* surf_m,
+                      const lhm_bh_surface* surf_p, double* out, void* cuda_stream);
+
 /* measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator */
 int lhm_fp64_peak_probe(int device, void* cuda_stream, double* tflops_out);
 

@@ -945,6 +945,33 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
     return LHM_OK;
 }
 
+static BhSurf to_surf(const lhm_bh_surface* s) {
+    BhSurf b; b.tx = s->tx; b.ty = s->ty; b.c = s->c; b.nx = s->nx; b.ny = s->ny; b.zmax = s->zmax;
+    return b;
+}
+
+int lhm_bh_emis_batch(int W, int Ng, int Np, int Nt, const double* g_el, const double* g_pr, const double* N_pr,
+                      const double* x_target, const double* photons, const lhm_bh_surface* sm, const lhm_bh_surface* sp,
+                      double* out, void* stream) {
+    if (W < 1 || Ng < 1 || Np < 2 || Nt < 2 || !g_el || !g_pr || !N_pr || !x_target || !photons || !sm || !sp || !out)
+        return LHM_ERR_ARG;
+    if (sm->nx < 8 || sm->ny < 8 || sp->nx < 8 || sp->ny < 8 || !sm->tx || !sm->ty || !sm->c || !sp->tx || !sp->ty || !sp->c)
+        return LHM_ERR_ARG;
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    BhArgs A;
+    A.W = W; A.Ng = Ng; A.Np = Np; A.Nt = Nt; A.g_el = g_el; A.g_pr = g_pr; A.N_pr = N_pr; A.xt = x_target;
+    A.photons = photons; A.Sm = to_surf(sm); A.Sp = to_surf(sp); A.out = out;
+    const size_t smem = bh_smem_doubles(Nt, Np, A.Sm, A.Sp) * sizeof(double);
+    if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaFuncSetAttribute(had_bh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid(W, (Ng + BH_CH - 1) / BH_CH);
+    had_bh_kernel<<<grid, HAD_NT, smem, (cudaStream_t)stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
 int lhm_fp64_peak_probe(int device, void* stream, double* tflops_out) {
     if (!tflops_out) return LHM_ERR_ARG;
     int ndev = 0;

@@ -354,3 +354,197 @@ __global__ void __launch_bounds__(HAD_NT) had_pion_kernel(PionArgs A) {
 }
 
 }  // namespace lhm
+
+// =================================================================================================================
+// A13: Bethe-Heitler pair injection Q_BH_sol (LeHaMoC_f.py:566-616).  The two smoothing-spline surfaces of the
+// energy-integrated cross section come from SciPy's bisplrep on the host (interp_cs_BH_int, LeHaMoC_f.py:276-341); the
+// device evaluates them (FITPACK bispev/fpbspl restated: cubic x cubic tensor-product B-splines, arguments clamped to
+// the knot range) and does the three nested Simpson integrals with scipy.integrate.simpson's rule for irregular
+// spacing, including its last-interval correction for an even number of samples.
+// =================================================================================================================
+namespace lhm {
+
+struct BhSurf {            // one tck of bisplrep with kx = ky = 3 (pointers to shared or global memory)
+    const double *tx, *ty, *c;
+    int nx, ny;
+    double zmax;           // max_intrp_cs: values above it are replaced by 0 (LeHaMoC_f.py:592-593)
+};
+
+// FITPACK fpbspl: the 4 non-zero cubic B-splines at x in the knot interval l (t[l] <= x < t[l+1])
+__device__ __forceinline__ void bh_fpbspl(const double* __restrict__ t, double x, int l, double* h) {
+    double hh[3];
+    h[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const int li = l + 1 + i, lj = li - j;
+            const double f = hh[i] / (t[li] - t[lj]);
+            h[i] = h[i] + f * (t[li] - x);
+            h[i + 1] = f * (x - t[lj]);
+        }
+    }
+}
+__device__ __forceinline__ int bh_interval(const double* __restrict__ t, int n, double& arg) {
+    const double tb = t[3], te = t[n - 4];
+    if (arg < tb) arg = tb;
+    if (arg > te) arg = te;
+    int l = 3;
+    while (!(arg < t[l + 1]) && l != n - 5) ++l;
+    return l;
+}
+
+// scipy.integrate.simpson(y, x=x) for N samples (N >= 2)
+__device__ double simpson_irregular(const double* y, const double* x, int N) {
+    auto basic = [&](int stop) {                 // pairs of intervals starting at 0, 2, ... < stop
+        double r = 0.0;
+        for (int i = 0; i < stop; i += 2) {
+            const double h0 = x[i + 1] - x[i], h1 = x[i + 2] - x[i + 1];
+            const double hsum = h0 + h1, hprod = h0 * h1;
+            const double h0d = (h1 != 0.0) ? h0 / h1 : 0.0;
+            r += hsum / 6.0 * (y[i] * (2.0 - ((h0d != 0.0) ? 1.0 / h0d : 0.0))
+                               + y[i + 1] * (hsum * ((hprod != 0.0) ? hsum / hprod : 0.0)) + y[i + 2] * (2.0 - h0d));
+        }
+        return r;
+    };
+    if (N % 2 == 1) return basic(N - 2);
+    if (N == 2) return 0.5 * (x[1] - x[0]) * (y[1] + y[0]);
+    double r = basic(N - 3);
+    const double h0 = x[N - 2] - x[N - 3], h1 = x[N - 1] - x[N - 2];
+    double num = 2 * h1 * h1 + 3 * h0 * h1, den = 6 * (h1 + h0);
+    const double alpha = (den != 0.0) ? num / den : 0.0;
+    num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0;
+    const double beta = (den != 0.0) ? num / den : 0.0;
+    num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
+    const double eta = (den != 0.0) ? num / den : 0.0;
+    r += alpha * y[N - 1] + beta * y[N - 2] - eta * y[N - 3];
+    return r;
+}
+
+// g_pr_int of one (gamma_e, gamma_p) pair (LeHaMoC_f.py:571-610), one thread.
+// xt [Nt] = h nu/(m_e c^2) ascending, lph [Nt] = log10(photons)
+__device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double* __restrict__ xt,
+                          const double* __restrict__ lph, const BhSurf& Sm, const BhSurf& Sp) {
+    const HadConst& K = kHC;
+    const double LN10 = 2.302585092994045684;
+    const double Emin = (gp + ge) * (gp + ge) / (4. * (gp * gp) * ge);
+    const double Emax = K.m_pr / (gp * K.m_el);
+    if (!(Emin < Emax)) return 0.0;
+    const double Ee_min = (gp * gp + ge * ge) / (2 * gp * ge);
+    const double wmin = (gp + ge) * (gp + ge) / (2 * gp * ge);
+    const BhSurf* Sf = (gp > ge) ? &Sp : (gp < ge) ? &Sm : nullptr;
+    double hx[4]; int lx = 0;
+    if (Sf) {
+        double ax = log10(Ee_min);
+        lx = bh_interval(Sf->tx, Sf->nx, ax);
+        bh_fpbspl(Sf->tx, ax, lx, hx);
+    }
+    const double ea = log10(1.001 * Emin), eb = log10(Emax);
+    double yE[10], xE[10];
+    for (int e = 0; e < 10; ++e) {
+        const double Eph = exp10(logspace_exp(ea, eb, e, 10));
+        // 10**np.interp(E_arr, nu_trgt, log10(photons)): interpolation LINEAR in x (LeHaMoC_f.py:577)
+        const double f_ph = exp10(interp_clamped(Eph, xt, lph, Nt)) * K.m_el * K.c * K.c / (K.h * (Eph * Eph));
+        const double wmax = 2 * gp * Eph;
+        double temp = 0.0;
+        if (wmin < wmax) {
+            const double wa = log10(wmin), wb = log10(wmax);
+            double yw[10], xw[10];
+            for (int q = 0; q < 10; ++q) {
+                const double w = exp10(logspace_exp(wa, wb, q, 10));
+                const double Ee_max = w - 1;
+                double res = 0.0;
+                if (Sf && Ee_min < Ee_max && Ee_min < 80. / 100. * Ee_max) {
+                    double ay = log10(Ee_max);
+                    const int ly = bh_interval(Sf->ty, Sf->ny, ay);
+                    double hy[4];
+                    bh_fpbspl(Sf->ty, ay, ly, hy);
+                    const int nky1 = Sf->ny - 4;
+                    double sp = 0.0;
+#pragma unroll
+                    for (int a = 0; a < 4; ++a) {
+                        const double* cr = Sf->c + (size_t)(lx - 3 + a) * nky1 + (ly - 3);
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) sp = sp + cr[b] * hx[a] * hy[b];
+                    }
+                    if (sp > Sf->zmax) sp = 0.;
+                    res = w * exp10(sp);
+                }
+                yw[q] = res * w;
+                xw[q] = log(w);
+            }
+            temp = simpson_irregular(yw, xw, 10);
+            if (temp < 0.) temp = 0.;
+        }
+        yE[e] = f_ph * temp * Eph;
+        xE[e] = log(Eph);
+    }
+    (void)LN10;
+    return n_p * simpson_irregular(yE, xE, 10) / (2. * (gp * gp * gp));
+}
+
+constexpr int BH_CH = 8;        // gamma_e values per chunk
+
+struct BhArgs {
+    int W, Ng, Np, Nt;
+    const double *g_el, *g_pr, *N_pr;      // [W,Ng], [W,Np], [W,Np] (dN_pr/dV dgamma)
+    const double *xt, *photons;            // [W,Nt]: h nu/(m_e c^2), photons
+    BhSurf Sm, Sp;                         // device pointers
+    double* out;                           // [W,Ng] = c * dnde
+};
+
+__host__ __device__ inline size_t bh_smem_doubles(int Nt, int Np, const BhSurf& a, const BhSurf& b) {
+    return (size_t)2 * Nt + 3 * Np + BH_CH * Np + a.nx + a.ny + (size_t)(a.nx - 4) * (a.ny - 4) + b.nx + b.ny +
+           (size_t)(b.nx - 4) * (b.ny - 4) + 8;
+}
+
+// stage a surface into shared memory (all threads; no barrier)
+__device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, int nthreads) {
+    const int nc = (src.nx - 4) * (src.ny - 4);
+    double* tx = sm; double* ty = tx + src.nx; double* cc = ty + src.ny;
+    for (int k = threadIdx.x; k < src.nx; k += nthreads) tx[k] = src.tx[k];
+    for (int k = threadIdx.x; k < src.ny; k += nthreads) ty[k] = src.ty[k];
+    for (int k = threadIdx.x; k < nc; k += nthreads) cc[k] = src.c[k];
+    dst = src; dst.tx = tx; dst.ty = ty; dst.c = cc;
+    return cc + nc;
+}
+
+// Q_BH_sol for the gamma_e range [i0, i1) of one walker by the whole CTA: buf [BH_CH][Np] scratch, gp/lgp/np_ [Np] staged
+__device__ void bh_chunk(int i0, int i1, int Np, int Nt, const double* ge_arr, const double* gp, const double* lgp,
+                         const double* np_, const double* xt, const double* lph, const BhSurf& Sm, const BhSurf& Sp,
+                         double* buf, double* out, int nthreads) {
+    const int n = (i1 - i0) * Np;
+    for (int e = threadIdx.x; e < n; e += nthreads) {
+        const int ii = e / Np, j = e - ii * Np;
+        buf[e] = bh_pair(ge_arr[i0 + ii], gp[j], np_[j], Nt, xt, lph, Sm, Sp) * gp[j];      // g_pr_int * g_pr
+    }
+    __syncthreads();
+    for (int ii = threadIdx.x; ii < i1 - i0; ii += nthreads)
+        out[i0 + ii] = kHC.c * simpson_irregular(buf + (size_t)ii * Np, lgp, Np);               // c * simpson(., ln g_pr)
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
+    extern __shared__ __align__(16) double sh[];
+    const int w = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
+    const int Nt = A.Nt, Np = A.Np;
+    double* xt = sh; double* lph = xt + Nt; double* gp = lph + Nt; double* lgp = gp + Np; double* np_ = lgp + Np;
+    double* buf = np_ + Np;
+    BhSurf Sm, Sp;
+    double* p = bh_stage(Sm, A.Sm, buf + (size_t)BH_CH * Np, HAD_NT);
+    bh_stage(Sp, A.Sp, p, HAD_NT);
+    for (int k = tid; k < Nt; k += HAD_NT) { xt[k] = A.xt[(size_t)w * Nt + k]; lph[k] = log10(A.photons[(size_t)w * Nt + k]); }
+    for (int k = tid; k < Np; k += HAD_NT) {
+        const double g = A.g_pr[(size_t)w * Np + k];
+        gp[k] = g; lgp[k] = log(g); np_[k] = A.N_pr[(size_t)w * Np + k];
+    }
+    __syncthreads();
+    const int i0 = chunk * BH_CH, i1 = min(i0 + BH_CH, A.Ng);
+    if (i0 < A.Ng)
+        bh_chunk(i0, i1, Np, Nt, A.g_el + (size_t)w * A.Ng, gp, lgp, np_, xt, lph, Sm, Sp, buf, A.out + (size_t)w * A.Ng, HAD_NT);
+}
+
+}  // namespace lhm

@@ -208,3 +208,37 @@ def interp_cs_BH_int(g_pr, g_el, nu_int_min, nu_int_max):
         xs, ys, zs = np.log10(Emin)[keep], np.log10(Emax)[keep], z[keep]
         out[key] = (interpolate.bisplrep(list(xs), list(ys), list(zs), s=2), max(zs))
     return out["m"][0], out["p"][0], out["m"][1], out["p"][1]
+
+
+class lhm_bh_surface(C.Structure):
+    _fields_ = [("tx", C.c_void_p), ("ty", C.c_void_p), ("c", C.c_void_p), ("nx", C.c_int), ("ny", C.c_int),
+                ("zmax", C.c_double)]
+
+
+def bh_surface(tck, zmax, device="cuda"):
+    """(ctypes lhm_bh_surface, tensors to keep alive) from a bisplrep tck = [tx, ty, c, 3, 3] and max_intrp_cs."""
+    if int(tck[3]) != 3 or int(tck[4]) != 3:
+        raise ValueError("the Bethe-Heitler surfaces are bicubic (bisplrep default kx = ky = 3)")
+    ts = [torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(device) for a in tck[:3]]
+    if ts[2].numel() != (ts[0].numel() - 4) * (ts[1].numel() - 4):
+        raise ValueError("tck: len(c) != (nx-4)*(ny-4)")
+    s = lhm_bh_surface(ts[0].data_ptr(), ts[1].data_ptr(), ts[2].data_ptr(), ts[0].numel(), ts[1].numel(), float(zmax))
+    return s, ts
+
+
+def Q_BH_sol(g_el, g_pr, N_pr, nu_trgt, photons_trgt, intrp_cs_m, intrp_cs_p, max_intrp_cs_m, max_intrp_cs_p):
+    """LeHaMoC_f.py:566-616, same arguments (nu_trgt is h nu/(m_e c^2), N_pr is dN/dV dgamma); 1-D inputs: one
+    walker, 2-D [W, n]: a batch sharing the two spline surfaces."""
+    _require_cuda()
+    lib = _lib.load()
+    ge, gp, Np_, xt, ph = (_dev2(x) for x in (g_el, g_pr, N_pr, nu_trgt, photons_trgt))
+    W = ge.shape[0]
+    sm, keep_m = bh_surface(intrp_cs_m, max_intrp_cs_m)
+    sp, keep_p = bh_surface(intrp_cs_p, max_intrp_cs_p)
+    out = torch.empty_like(ge)
+    check(lib.lhm_bh_emis_batch(W, ge.shape[1], gp.shape[1], xt.shape[1], _p(ge), _p(gp), _p(Np_), _p(xt), _p(ph),
+                                C.byref(sm), C.byref(sp), _p(out), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+          "lhm_bh_emis_batch")
+    r = out.cpu().numpy()
+    del keep_m, keep_p
+    return r[0] if np.ndim(g_el) == 1 else r

@@ -127,3 +127,16 @@ def test_host_bh_surface_setup_is_the_references(gold):
         for a, b in zip(ours[:3], bh_tck(gold, which)[:3]):
             np.testing.assert_array_equal(np.asarray(a), b)
     assert mm == float(gold["bh_max_m"]) and mp_ == float(gold["bh_max_p"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", [0, 1])
+def test_gpu_Q_BH_sol(gold, case):
+    """Device spline evaluation + nested Simpson integrals against the reference's Q_BH_sol (SciPy bisplev/simpson)."""
+    from lehamoc_b200 import hadronic
+    from lehamoc_oracle import c, h, m_el
+    p = f"c{case}_"
+    x = gold[p + "nu"] * h / (m_el * c ** 2.)
+    got = hadronic.Q_BH_sol(gold[p + "bh_g_el"], gold[p + "bh_g_pr"], gold[p + "bh_N_pr"], x, gold[p + "photons"],
+                            bh_tck(gold, "m"), bh_tck(gold, "p"), float(gold["bh_max_m"]), float(gold["bh_max_p"]))
+    rel_close(got, gold[p + "Q_BH"], 1e-8, "Q_BH_sol")
