@@ -67,6 +67,7 @@ typedef struct {
     int esc_flag_pr;        /* proton escape flag, driver 1 only                            LeHaMoC.py:331 */
     int pg_pi_l_flag, pg_BH_l_flag;     /* driver 1: photopion / Bethe-Heitler proton loss terms   LeHaMoC.py:311-323 */
     int pg_pi_emis_flag, neutrino_flag; /* driver 1: photopion pairs + photons, neutrinos           LeHaMoC.py:343-352 */
+    int pg_BH_emis_flag;                /* driver 1: Bethe-Heitler pair injection (lhm_set_bh_surfaces) LeHaMoC.py:337-340 */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 
@@ -126,7 +127,10 @@ int lhm_set_protons(lhm_handle*, const double* g_pr, const double* pr_inj);
  * neutrino distribution N_nu [W,(S),50] on E_nu_space (either may be NULL).  With a photo-hadronic flag set the tables
  * must have been given with lhm_set_had_tables (struct declared below). */
 struct lhm_had_tables_s;
+struct lhm_bh_surface_s;
 int lhm_set_had_tables(lhm_handle*, const struct lhm_had_tables_s* tables);
+/* pg_BH_emis_flag: the two bisplrep surfaces of interp_cs_BH_int (gamma_p < gamma_e, gamma_p > gamma_e), declared below */
+int lhm_set_bh_surfaces(lhm_handle*, const struct lhm_bh_surface_s* surf_m, const struct lhm_bh_surface_s* surf_p);
 int lhm_run_batch_lh(lhm_handle*, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
                      int snapshots);
 
@@ -209,7 +213,7 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
  * scipy.interpolate.bisplrep, kx = ky = 3; host set-up interp_cs_BH_int, LeHaMoC_f.py:276-341) are given as DEVICE
  * pointers: knots tx [nx], ty [ny], coefficients c [(nx-4)*(ny-4)]; zmax = max_intrp_cs.  g_el [W,Ng]; g_pr, N_pr [W,Np]
  * (dN_pr/dV dgamma); x_target [W,Nt] = h nu/(m_e c^2); photons [W,Nt]; out [W,Ng] (the driver uses [1:-1]). */
-typedef struct {
+typedef struct lhm_bh_surface_s {
     const double *tx, *ty, *c;
     int nx, ny;
     double zmax;

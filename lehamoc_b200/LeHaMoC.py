@@ -5,8 +5,7 @@
 writes Pairs_Distribution<suffix>.txt, Photons_Distribution<suffix>.txt, Protons_Distribution<suffix>.txt and
 Neutrinos_Distribution<suffix>.txt in the reference's text format (one block per timestep).  `run()` is the importable
 form and takes several parameter sets at once.  The photopion and Bethe-Heitler proton loss terms, the photopion pairs / photons and the neutrinos
-are part of the fused timestep; the Bethe-Heitler emissivity (pg_BH_emis_flag) and the pp channels raise
-NotImplementedError.
+and the Bethe-Heitler pair injection are part of the fused timestep; the pp channels raise NotImplementedError.
 """
 from __future__ import annotations
 
@@ -30,10 +29,32 @@ def run(param_sets, ic_path="R", snapshots=True, engine=None):
     if any(batch.cfg[k] for k in ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag")):
         from . import hadronic
         eng.set_had_tables(hadronic._need_tables())
+    if batch.cfg["pg_BH_emis_flag"]:
+        from . import hadronic
+        if not (np.all(batch.nu_tot[:, 0] == batch.nu_tot[0, 0]) and np.all(batch.nu_tot[:, -1] == batch.nu_tot[0, -1])):
+            raise ValueError("pg_BH_emis_flag: the walkers of one batch must share the nu_tot range (one pair of "
+                             "Bethe-Heitler surfaces per batch, LeHaMoC.py:263)")
+        tm, tp, mm, mp_ = bh_surfaces(batch.nu_tot[0, 0], batch.nu_tot[0, -1])
+        sm, km = hadronic.bh_surface(tm, mm)
+        sp, kp = hadronic.bh_surface(tp, mp_)
+        eng.set_bh_surfaces(sm, sp, (km, kp))
     eng.setup(batch)
     S = int(batch.nsteps.max()) if snapshots else 0
     N, sed, Npr, Nnu = eng.run_lh(snapshots=S)
     return batch, N.cpu().numpy(), sed.cpu().numpy(), Npr.cpu().numpy(), Nnu.cpu().numpy()
+
+
+_bh_cache = {}
+
+
+def bh_surfaces(nu_min, nu_max):
+    """interp_cs_BH_int(np.logspace(0,8,50), np.logspace(0,10,50), nu_tot[0], nu_tot[-1]) of LeHaMoC.py:263 (host: 27 000
+    Simpson integrals + two SciPy bisplrep fits, a few seconds), cached per frequency range."""
+    from . import hadronic
+    key = (float(nu_min), float(nu_max))
+    if key not in _bh_cache:
+        _bh_cache[key] = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu_min, nu_max)
+    return _bh_cache[key]
 
 
 def write_outputs(batch, N, sed, Npr, Nnu, out_s, w=0):

@@ -26,7 +26,7 @@ class lhm_config(C.Structure):
         "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag", "SSA_l_flag",
         "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "ic_pair_table",
         "shared_ic_grids", "driver", "Np", "esc_flag_pr", "pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag",
-        "neutrino_flag", "max_walkers")]
+        "neutrino_flag", "pg_BH_emis_flag", "max_walkers")]
 
 
 # every symbol include/lhm.h declares: (restype, argtypes)
@@ -45,6 +45,7 @@ SIGNATURES = {
     "lhm_run_batch": (C.c_int, [_P, _P, _P, C.c_int]),
     "lhm_set_protons": (C.c_int, [_P, _P, _P]),
     "lhm_set_had_tables": (C.c_int, [_P, _P]),
+    "lhm_set_bh_surfaces": (C.c_int, [_P, _P, _P]),
     "lhm_run_batch_lh": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),

@@ -40,6 +40,7 @@ struct RunArgs {
     double* Nnu_out;        // [W,(S),50] or null
     int esc_pr, had;        // had: photo-hadronic terms switched on (shared memory reserved for them)
     HadTables HT;
+    BhSurf BSm, BSp;        // Bethe-Heitler spline surfaces (device pointers), F.bh_e
     double* sed_out;        // [W,(S),Nt] or null
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
@@ -176,8 +177,13 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
             H.Nnu[k] = 0.0; H.Qnu[k] = 0.0;
             H.Enu[k] = (k < 50) ? exp10(logspace_exp(10., 22., k, 50)) * kHC.eV : 0.0;     // E_nu_space, LeHaMoC_f.py:41
         }
-        for (int j = tid; j < Ng; j += NT) H.Qpi[j] = 0.0;
+        for (int j = tid; j < Ng; j += NT) { H.Qpi[j] = 0.0; H.Qbh[j] = 0.0; }
         for (int k = tid; k < Ni; k += NT) H.Qpg[k] = 0.0;
+    }
+    BhSurf BSm, BSp;
+    if (A.had && C.F.bh_e) {
+        double* p2 = bh_stage(BSm, A.BSm, H.bhsurf, NT);
+        bh_stage(BSp, A.BSp, p2, NT);
     }
     ic_prepare<NT>(C, S);
     double t = C.tinit;
@@ -189,8 +195,9 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
         phase_photons<NT>(C, S, true);
         if (C.F.ic_l) phase_uph_lh<NT>(C, S);
         phase_protons<NT>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr);
+        if (C.F.bh_e) phase_bh_emis<NT>(C, S, H, BSm, BSp);
         if (C.F.pg_e) phase_photopion<NT>(C, S, H, A.HT);
-        phase_electrons_lh<NT>(C, S, C.F.pg_e ? H.Qpi : nullptr);
+        phase_electrons_lh<NT>(C, S, C.F.pg_e ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
         phase_vectors<NT>(C, S);
         phase_syn_rows<NT>(C, S, false);
         phase_syn_protons<NT>(C, S, H);
@@ -519,6 +526,8 @@ struct lhm_handle {
     const double* pr_inj;
     HadTables HT;             // driver 1 with photo-hadronic flags: device tables (lhm_set_had_tables)
     bool have_HT;
+    BhSurf BSm, BSp;          // Bethe-Heitler surfaces (lhm_set_bh_surfaces)
+    bool have_BS;
     const double* consts;     // device pointers of the current batch (caller- or staging-owned)
     const double* g_el;
     // staging for the *_host entry points
@@ -595,11 +604,12 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
     F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
     F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
-    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu)) { delete h; return LHM_ERR_ARG; }
+    F.bh_e = cfg->pg_BH_emis_flag;
+    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu || F.bh_e)) { delete h; return LHM_ERR_ARG; }
     h->smem = smem_bytes(h->L, NW);
     if (cfg->driver >= 1) {
         h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
-        if (F.pg_l || F.bh_l || F.pg_e) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
+        if (F.pg_l || F.bh_l || F.pg_e || F.bh_e) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
     }
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
     PhysConst pc = make_consts();
@@ -703,12 +713,29 @@ int lhm_set_had_tables(lhm_handle* h, const lhm_had_tables* t) {
     return LHM_OK;
 }
 
+static BhSurf to_surf(const lhm_bh_surface* s);
+
+int lhm_set_bh_surfaces(lhm_handle* h, const lhm_bh_surface* sm, const lhm_bh_surface* sp) {
+    if (!h || !sm || !sp) return LHM_ERR_ARG;
+    if (h->cfg.driver != 1) return LHM_ERR_STATE;
+    if (sm->nx < 8 || sm->ny < 8 || sp->nx < 8 || sp->ny < 8 || !sm->tx || !sm->ty || !sm->c || !sp->tx || !sp->ty || !sp->c)
+        return LHM_ERR_ARG;
+    const size_t need = (size_t)sm->nx + sm->ny + (size_t)(sm->nx - 4) * (sm->ny - 4) + sp->nx + sp->ny + (size_t)(sp->nx - 4) * (sp->ny - 4);
+    if (need > (size_t)BH_MAXSURF) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaSetDevice(h->device));
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    h->BSm = to_surf(sm); h->BSp = to_surf(sp); h->have_BS = true;
+    return LHM_OK;
+}
+
 static double* g_nnu_out = nullptr;     // per-call output slot of lhm_run_batch_lh (single-threaded per handle)
 
 int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
     if (h->cfg.driver < 1) return LHM_ERR_STATE;
     if ((h->F.pg_l || h->F.bh_l || h->F.pg_e) && !h->have_HT) return LHM_ERR_STATE;
+    if (h->F.bh_e && !h->have_BS) return LHM_ERR_STATE;
     g_nnu_out = N_nu_out;
     int rc = run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
     g_nnu_out = nullptr;
@@ -735,8 +762,10 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
     A.Np_out = N_pr_out; A.esc_pr = h->cfg.esc_flag_pr;
     A.Nnu_out = lh ? g_nnu_out : nullptr;
-    A.had = lh && (h->F.pg_l || h->F.bh_l || h->F.pg_e);
-    if (A.had) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
+    A.had = lh && (h->F.pg_l || h->F.bh_l || h->F.pg_e || h->F.bh_e);
+    if (A.had && h->have_HT) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
+    std::memset(&A.BSm, 0, sizeof(A.BSm)); std::memset(&A.BSp, 0, sizeof(A.BSp));
+    if (lh && h->F.bh_e) { A.BSm = h->BSm; A.BSp = h->BSp; }
     A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;

@@ -87,10 +87,12 @@ struct SmemLh {
     double *lxpg, *lppg;               // [Nt] log10(h nu), log10(photons/h)
     double *ltab;                      // loss tables (LossTab)
     double *work;                      // pion_eval work area
+    double *bhbuf, *npl, *Qbh, *bhsurf; // [BH_CH*Np] scratch, [Np] dN_pr/dV, [Ng] Q_BH_sol, staged spline surfaces
 };
-constexpr int HAD_MAXTAB = 32, HAD_MAXLOSS = 2 * (128 + 64 + 128);
+constexpr int HAD_MAXTAB = 32, HAD_MAXLOSS = 2 * (128 + 64 + 128), BH_MAXSURF = 2048;
 __host__ __device__ inline size_t smem_lh_had_doubles(const Layout& L) {
-    return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB);
+    return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB)
+           + (size_t)BH_CH * pad2(L.Np) + pad2(L.Np) + pad2(L.Ng) + BH_MAXSURF;
 }
 __host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
     return (size_t)3 * pad2(L.Np) + 2 * pad2(L.Ns) + pad2(L.Nt);
@@ -104,7 +106,8 @@ __device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L, const Sme
     H.Qpi = take(pad2(L.Ng)); H.Qpg = take(pad2(L.Ni));
     H.Qnu = take(52); H.Nnu = take(52); H.Enu = take(52);
     H.lxpg = take(pad2(L.Nt)); H.lppg = take(pad2(L.Nt));
-    H.ltab = take(HAD_MAXLOSS); H.work = p;            // only valid when the handle reserved smem_lh_had_doubles
+    H.ltab = take(HAD_MAXLOSS); H.work = take((int)pion_work_doubles(HAD_MAXTAB));     // only valid when the handle
+    H.bhbuf = take(BH_CH * pad2(L.Np)); H.npl = take(pad2(L.Np)); H.Qbh = take(pad2(L.Ng)); H.bhsurf = p;   // reserved smem_lh_had_doubles
 }
 
 // U_ph_f, LeHaMoC_f.py:171-182: per gamma a 50-point log resample of the photon field up to nu_T, linear-x trapezoid.
@@ -236,7 +239,7 @@ __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, cons
 
 // electron equation, LeHaMoC.py:359-367 (injection per volume; Q_ee aligned with the interior points)
 template <int NT>
-__device__ void phase_electrons_lh(const Ctx& C, Smem& S, const double* Qpi) {
+__device__ void phase_electrons_lh(const Ctx& C, Smem& S, const double* Qpi, const double* Qbh) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Ng - 2;
     const double dt = C.dt;
@@ -251,6 +254,7 @@ __device__ void phase_electrons_lh(const Ctx& C, Smem& S, const double* Qpi) {
         const double V3 = -dt * (b_syn * spj + ic_p + b_ad * C.T[L.ap + j]);
         double src = S.qee[j + 1];
         if (Qpi) src += Qpi[j + 1];
+        if (Qbh) src += Qbh[j + 1];
         if (C.F.inj) src += C.T[L.elinj + j + 1];
         const double d = S.N[j + 1] + (src * dt) * C.V;
         S.cp[j] = V3 / V2;
@@ -326,6 +330,17 @@ __device__ void phase_photopion(const Ctx& C, Smem& S, SmemLh& H, const HadTable
         for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0;
         __syncthreads();
     }
+}
+
+// Bethe-Heitler pair injection Q_BH_sol(g_el, g_pr, dN_pr/dV, h nu_tot/mc2, photons, ...)[1:-1], LeHaMoC.py:337-340
+template <int NT>
+__device__ void phase_bh_emis(const Ctx& C, Smem& S, SmemLh& H, const BhSurf& Sm, const BhSurf& Sp) {
+    const Layout& L = C.L;
+    for (int j = threadIdx.x; j < L.Np; j += NT) H.npl[j] = H.Npr[j] / C.V;
+    __syncthreads();
+    for (int i0 = 0; i0 < L.Ng; i0 += BH_CH)
+        bh_chunk(i0, min(i0 + BH_CH, L.Ng), L.Np, L.Nt, S.gS, C.T + L.gp, C.T + L.lgp, H.npl, C.T + L.xt, S.Ln, Sm, Sp,
+                 H.bhbuf, H.Qbh, NT);
 }
 
 // photon equations, LeHaMoC.py:397-407: as the leptonic ones plus gamma-gamma absorption on the synchrotron grid and

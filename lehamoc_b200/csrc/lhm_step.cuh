@@ -18,7 +18,8 @@ namespace lhm {
 
 struct StepFlags {
     int inj, ad, syn_l, syn_e, ic_l, ic_e, ssa, gg, esc, qee_from_ic, ic_path;
-    int pg_l, bh_l, pg_e, nu;       // LeHaMoC.py driver: photopion / Bethe-Heitler loss, photopion emission, neutrinos
+    int pg_l, bh_l, pg_e, nu, bh_e; // LeHaMoC.py driver: photopion / Bethe-Heitler loss, photopion emission, neutrinos,
+                                    // Bethe-Heitler pair injection
 };
 
 // shared-memory carve-up; all pointers are into dynamic shared memory

@@ -137,6 +137,11 @@ class Engine:
               "lhm_run_batch_lh")
         return N, sed, Npr, Nnu
 
+    def set_bh_surfaces(self, surf_m, surf_p, keep):
+        """Driver 1 with pg_BH_emis_flag: ctypes lhm_bh_surface pair (lehamoc_b200.hadronic.bh_surface)."""
+        self._bh = (surf_m, surf_p, keep)
+        check(self.lib.lhm_set_bh_surfaces(self.h, C.byref(surf_m), C.byref(surf_p)), "lhm_set_bh_surfaces")
+
     def set_had_tables(self, tables_struct):
         """Driver 1 with photo-hadronic flags: ctypes lhm_had_tables of device pointers (lehamoc_b200.hadronic)."""
         self._had_tables = tables_struct

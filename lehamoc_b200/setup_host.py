@@ -215,7 +215,7 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
                qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
                const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
                ic_pair_table=1, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0,
-               neutrino_flag=0,
+               neutrino_flag=0, pg_BH_emis_flag=0,
                # fixed-grid sweeps (every walker has the same g_el / nu_ic / nu_tot): one IC pair table per batch
                shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))))
     for k in FLAG_KEYS:
@@ -233,8 +233,8 @@ LH_KEYS = ("time_init", "time_end", "step_alg", "PL_inj", "g_min_el", "g_max_el"
            "pg_BH_emis_flag", "n_H", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
            "neutrino_flag", "esc_flag_el", "esc_flag_pr", "BB_flag", "temperature", "GB_ext", "PL_flag", "dE_dV_ph",
            "nu_min_ph", "nu_max_ph", "s_ph", "User_ph")
-UNSUPPORTED_FLAGS = ("pg_BH_emis_flag", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag")
-PHOTOHADRONIC_FLAGS = ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag", "neutrino_flag")
+UNSUPPORTED_FLAGS = ("pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag")
+PHOTOHADRONIC_FLAGS = ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag", "neutrino_flag", "pg_BH_emis_flag")
 m_pr_ = 1.67262192369e-24
 
 
@@ -254,7 +254,7 @@ def pack_lehamoc(param_sets) -> Batch:
     Parameters.txt).  Set-up with the reference's own expressions, LeHaMoC.py:132-259, one walker at a time (this
     driver is not on the headline path; the loop costs ~50 us per walker).  Supported: leptonic processes, proton
     equation with synchrotron / photopion / Bethe-Heitler losses, proton synchrotron, photopion pairs, photons and
-    neutrinos; the Bethe-Heitler emissivity and the pp channels raise NotImplementedError."""
+    neutrinos, Bethe-Heitler pair injection; the pp channels raise NotImplementedError."""
     from ._lib import LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B
     if isinstance(param_sets, dict):
         param_sets = [param_sets]
@@ -267,8 +267,7 @@ def pack_lehamoc(param_sets) -> Batch:
     for P in param_sets:
         for k in UNSUPPORTED_FLAGS:
             if float(P[k]) != 0.:
-                raise NotImplementedError(f"{k} = {P[k]}: the Bethe-Heitler emissivity (SciPy spline surface) and the pp "
-                                          "channels are not built yet (DESIGN.md section 8)")
+                raise NotImplementedError(f"{k} = {P[k]}: the pp channels are not built yet (DESIGN.md section 8)")
         if float(P["User_ph"]) != 0.:
             raise NotImplementedError("User_ph: Photons_spec_user.txt input is not supported yet")
         for k in LH_KEYS:

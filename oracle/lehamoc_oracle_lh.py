@@ -7,8 +7,8 @@ Restates the driver LeHaMoC.py:132-453 with the `f_had` variants of the function
 (100 samples), Q_ee_f :158-168 (100 samples, full length), U_ph_f :171-182 (50-point resample), photons_tot :1025.
 Electron AND proton equations, proton synchrotron, the gamma-gamma pre-attenuation of the first two steps
 (LeHaMoC.py:418-426) and the neutrino equation are included; of the hadronic channels the photopion and Bethe-Heitler
-LOSS terms and the photopion emissivities are wired to lehamoc_oracle_had.py, the Bethe-Heitler and pp emissivities
-(SciPy spline surface / linregress matching) raise NotImplementedError.
+LOSS terms, the photopion emissivities and the Bethe-Heitler pair injection (spline surfaces handed in as `bh_surf`)
+are wired to lehamoc_oracle_had.py; the pp channels (linregress matching) raise NotImplementedError.
 
 Parity pinning: oracle/make_golden_lh.py runs the unmodified script (oracle/run_reference_lh.py) and stores every
 step's four output snapshots in tests/golden/lh_*.npz; tests/test_lehamoc_driver.py checks this restatement against them.
@@ -205,9 +205,9 @@ class LeptoHadronicRun:
         self.N_el[0] = self.N_el[-1] = SENT
         self.interv = 0.
         self.Radius = R0
-        if self.pg_BH_emis_flag == 1. or self.pp_l_flag == 1. or self.pp_ee_emis_flag == 1. or self.pp_g_emis_flag == 1. \
-                or self.pp_nu_emis_flag == 1.:
-            raise NotImplementedError("Bethe-Heitler emissivity and pp channels are not restated yet")
+        if self.pp_l_flag == 1. or self.pp_ee_emis_flag == 1. or self.pp_g_emis_flag == 1. or self.pp_nu_emis_flag == 1.:
+            raise NotImplementedError("pp channels are not restated yet")
+        self.bh_surf = None                                   # (tck_m, tck_p, max_m, max_p) of interp_cs_BH_int
 
     def n_steps(self):
         return int(self.time_end / self.step_alg)            # LeHaMoC.py:267
@@ -267,6 +267,10 @@ class LeptoHadronicRun:
         S = self.N_pr[1:-1] + np.multiply(self.pr_inj[1:-1], dt) * V
         self.N_pr[1:-1] = bidiag_solve(V2, V3, S)
         n_p = np.array(self.N_pr / V)
+        if self.pg_BH_emis_flag == 1.:                          # LeHaMoC.py:337-340
+            Q_pg_BH = oh.Q_BH_sol(g_el, g_pr, n_p, nu_tot * h / (m_el * c ** 2.), np.array(photons), *self.bh_surf)[1:-1]
+        else:
+            Q_pg_BH = np.zeros(ne_)
         if self.pg_pi_emis_flag == 1.:
             T = self.tables
             Q_pg_pi = oh.Qp_g_opt(g_el, nu_ic, n_p, g_pr, photons, nu_tot, "e+", T)[1:-1] \
@@ -282,9 +286,9 @@ class LeptoHadronicRun:
         V2 = 1. + dt * (c / Radius * self.esc_flag_el + syn_el_m + ic_m + ad_el_m)
         V3 = -dt * (syn_el_p + ic_p + ad_el_p)
         if self.inj_flag == 1.:
-            S = self.N_el[1:-1] + np.multiply(self.el_inj[1:-1] + self.Q_ee + Q_pg_pi, dt) * V
+            S = self.N_el[1:-1] + np.multiply(self.el_inj[1:-1] + self.Q_ee + Q_pg_pi + Q_pg_BH, dt) * V
         elif self.inj_flag == 0.:
-            S = self.N_el[1:-1] + (self.Q_ee + Q_pg_pi) * dt * V
+            S = self.N_el[1:-1] + (self.Q_ee + Q_pg_pi + Q_pg_BH) * dt * V
         else:
             raise ValueError("inj_flag must be 0 or 1")
         self.N_el[1:-1] = bidiag_solve(V2, V3, S)
