@@ -140,3 +140,26 @@ def test_gpu_Q_BH_sol(gold, case):
     got = hadronic.Q_BH_sol(gold[p + "bh_g_el"], gold[p + "bh_g_pr"], gold[p + "bh_N_pr"], x, gold[p + "photons"],
                             bh_tck(gold, "m"), bh_tck(gold, "p"), float(gold["bh_max_m"]), float(gold["bh_max_p"]))
     rel_close(got, gold[p + "Q_BH"], 1e-8, "Q_BH_sol")
+
+
+# ---- A14 pp channels --------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def gold_pp():
+    return np.load(os.path.join(GOLD, "pp_functions.npz"))
+
+
+PP_FUNCS = (("Q_e_pp", "g_el"), ("Q_g_pp", "nu_ic"), ("Q_nu_mu_pp", "nu_nu"), ("Q_nu_e_pp", "nu_nu"))
+
+
+def test_oracle_pp_channels(gold_pp):
+    g = gold_pp
+    np.testing.assert_allclose(oh.cs_pp_inel(g["cs_E"]), g["cs_pp_inel"], rtol=1e-15, atol=0)
+    for case in (0, 1):
+        for p in (2.01, 2.5):
+            tag = f"c{case}_p{int(p * 100)}_"
+            for name, grid in PP_FUNCS:
+                with np.errstate(all="ignore"):
+                    got = np.array(getattr(oh, name)(g[grid], g[f"c{case}_g_pr"], g[f"c{case}_N_pr_TeV"], p, 1.5), dtype=np.float64)
+                ref = g[tag + name]
+                nz = ref != 0
+                assert np.array_equal(got[~nz], ref[~nz]) and np.max(np.abs(got[nz] / ref[nz] - 1)) < 1e-13, (tag, name)
