@@ -222,6 +222,12 @@ int lhm_bh_emis_batch(int W, int Ng, int Np, int Nt, const double* g_el, const d
                       const double* x_target, const double* photons, const lhm_bh_surface* surf_m,
                       const lhm_bh_surface* surf_p, double* out, void* cuda_stream);
 
+/* A14 pp channels (LeHaMoC_f.py:860-1014): product 0 Q_e_pp (grid = g_el), 1 Q_g_pp (grid = nu_ic), 2 Q_nu_mu_pp,
+ * 3 Q_nu_e_pp (grid = nu_nu = E_nu/h).  grid [W,Nout]; g_pr, N_pr_TeV [W,Np] (dN_pr/dV dgamma divided by
+ * m_p c^2 * 0.624151, LeHaMoC.py:355); p_pr, n_H [W]; out [W,Nout]. */
+int lhm_pp_batch(int W, int product, int Nout, int Np, const double* grid, const double* g_pr, const double* N_pr_TeV,
+                 const double* p_pr, const double* n_H, double* out, void* cuda_stream);
+
 /* measured FP64 FMA throughput of this device (TFLOP/s, FMA = 2 flop): the roofline denominator */
 int lhm_fp64_peak_probe(int device, void* cuda_stream, double* tflops_out);
 

@@ -166,3 +166,8 @@ def thomas(a, b, c, d):
     if np.any(np.asarray(a) != 0.):
         raise NotImplementedError("thomas() with a non-zero sub-diagonal is not on the hot path")
     return bidiag_solve(b, c, d)[0].cpu().numpy()
+
+
+# --- A11-A14: the hadronic functions of `LeHaMoC Code and Tests/LeHaMoC_f.py` live in lehamoc_b200.hadronic ----------
+from .hadronic import (dg_dt_BH, dg_dt_pg, Qp_g_opt, interp_cs_BH_int, Q_BH_sol,            # noqa: E402,F401
+                       Q_e_pp, Q_g_pp, Q_nu_mu_pp, Q_nu_e_pp)

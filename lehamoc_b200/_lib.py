@@ -60,6 +60,7 @@ SIGNATURES = {
     "lhm_had_loss_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P]),
     "lhm_photopion_batch": (C.c_int, [C.c_int] * 7 + [_P] * 9 + [_P]),
     "lhm_bh_emis_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P, _P, _P, _P]),
+    "lhm_pp_batch": (C.c_int, [C.c_int] * 4 + [_P] * 6 + [_P]),
     "lhm_fp64_peak_probe": (C.c_int, [C.c_int, _P, C.POINTER(C.c_double)]),
 }
 

@@ -974,6 +974,24 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
     return LHM_OK;
 }
 
+int lhm_pp_batch(int W, int product, int Nout, int Np, const double* grid, const double* g_pr, const double* N_pr_TeV,
+                 const double* p_pr, const double* n_H, double* out, void* stream) {
+    if (W < 1 || product < 0 || product >= PP_COUNT || Nout < 3 || Np < 2 || !grid || !g_pr || !N_pr_TeV || !p_pr || !n_H || !out)
+        return LHM_ERR_ARG;
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    PpArgs A;
+    A.W = W; A.product = product; A.Nout = Nout; A.Np = Np; A.grid = grid; A.g_pr = g_pr; A.N_pr_TeV = N_pr_TeV;
+    A.p_pr = p_pr; A.n_H = n_H; A.out = out;
+    const size_t smem = ((size_t)3 * Np + 2 * Nout) * sizeof(double) + (size_t)Nout * sizeof(int) + 16;
+    if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaFuncSetAttribute(had_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    had_pp_kernel<<<W, HAD_NT, smem, (cudaStream_t)stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
 static BhSurf to_surf(const lhm_bh_surface* s) {
     BhSurf b; b.tx = s->tx; b.ty = s->ty; b.c = s->c; b.nx = s->nx; b.ny = s->ny; b.zmax = s->zmax;
     return b;

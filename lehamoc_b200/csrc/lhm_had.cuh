@@ -548,3 +548,246 @@ __global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
 }
 
 }  // namespace lhm
+
+// =================================================================================================================
+// A14: pp channels (LeHaMoC_f.py:681-1014; Kelner, Aharonian & Bugayov 2006).  Cheap (the reference spends ~10 ms per
+// call), so one THREAD per outgoing energy; the reference's data-dependent list partitioning becomes index ranges
+// because x = E/E_p falls monotonically along the proton grid.
+// =================================================================================================================
+namespace lhm {
+
+enum { PP_E = 0, PP_G, PP_NUMU, PP_NUE, PP_COUNT };      // Q_e_pp, Q_g_pp, Q_nu_mu_pp, Q_nu_e_pp
+enum { PPS_G = 0, PPS_NUMU1, PPS_NUMU2, PPS_E, PPS_NUE };
+
+struct PpConst {
+    double E_th_pi, x_m_pr, x_m_el, x_m_pi, x_m_pi0, x_m_mu, K_pi, tev;
+};
+__device__ __forceinline__ PpConst pp_const() {
+    PpConst P;
+    P.E_th_pi = 1.22 * 1e-3; P.x_m_pr = 938.272046 * 1e-6; P.x_m_el = 0.511 * 1e-6; P.x_m_pi = 139.57 * 1e-6;
+    P.x_m_pi0 = 134.9766 * 1e-6; P.x_m_mu = 105.66 * 1e-6; P.K_pi = 0.17; P.tev = 0.624151;
+    return P;
+}
+
+__device__ __forceinline__ double pp_cs_inel(double E_p) {                   // LeHaMoC_f.py:687-692
+    if (!(E_p > 1.22 * 1e-3)) return 0.0;
+    const double L = log(E_p);
+    const double a = 1. - pow(1.22 * 1e-3 / E_p, 4.);
+    return 1e-27 * (34.3 + 1.88 * L + 0.25 * (L * L)) * (a * a);
+}
+
+// eta of q_pi (LeHaMoC_f.py:695-714): the np.interp fall-back is called with swapped arguments and, for any spectral
+// index above 0.91 that is not exactly 2, 2.5 or 3, returns 3.0
+__device__ __forceinline__ double pp_eta(double p_pr, bool is_g) {
+    if (p_pr == 2.) return is_g ? 1.1 : 0.77;
+    if (p_pr == 2.5) return is_g ? 0.86 : 0.62;
+    if (p_pr == 3.) return is_g ? 0.91 : 0.67;
+    // np.interp(p_pr, [1.1, 0.86, 0.91], [2., 2.5, 3.]) on an unsorted xp: above xp[-1] -> fp[-1], below xp[0] -> fp[0]
+    if (p_pr > 0.91) return 3.0;
+    if (p_pr < 1.1) return 2.0;                                    // (only reachable for p_pr <= 0.91)
+    return 3.0;
+}
+
+// 10**np.interp(log10(Ep), log10(g_pr*x_m_pr), log10(N_pr_TeV)) with the tables lEg / lN staged by the caller
+__device__ __forceinline__ double pp_Np(double Ep, const double* __restrict__ lEg, const double* __restrict__ lN, int Np) {
+    return exp10(interp_clamped(log10(Ep), lEg, lN, Np));
+}
+
+__device__ __forceinline__ double pp_q_pi(double E_pi, double eta, double n_H, const double* lEg, const double* lN, int Np) {
+    const PpConst P = pp_const();
+    const double Ep = P.x_m_pr + E_pi / P.K_pi;
+    return eta * kHC.c * n_H / P.K_pi * pp_cs_inel(Ep) * pp_Np(Ep, lEg, lN, Np);
+}
+
+__device__ __forceinline__ double pp_g_nu_mu(double x, double r) { return (3. - 2. * r) / (9. * ((1. - r) * (1. - r))) * (9. * (x * x) - 6. * log(x) - 4. * (x * x * x) - 5.); }
+__device__ __forceinline__ double pp_h_nu_mu_1(double r) { return (3. - 2. * r) / (9. * ((1. - r) * (1. - r))) * (9. * (r * r) - 6. * log(r) - 4. * (r * r * r) - 5.); }
+__device__ __forceinline__ double pp_h_nu_mu_2(double x, double r) { return (1. + 2. * r) * (r - x) / (9. * (r * r)) * (9. * (r + x) - 4. * (r * r + r * x + x * x)); }
+__device__ __forceinline__ double pp_g_nu_e(double x, double r) { return 2. * (1. - x) / (3. * ((1. - r) * (1. - r))) * (6. * ((1. - x) * (1. - x)) + r * (5. + 5. * x - 4. * (x * x)) + 6. * r * log(x)); }
+__device__ __forceinline__ double pp_h_nu_e_1(double r) { return 2. / (3. * ((1. - r) * (1. - r))) * ((1. - r) * (6. - 7. * r + 11. * (r * r) - 4. * (r * r * r)) + 6. * r * log(r)); }
+__device__ __forceinline__ double pp_h_nu_e_2(double x, double r) { return 2. * (r - x) / (3. * (r * r)) * (7. * (r * r) - 4. * (r * r * r) + 7. * x * (r * r) - 2. * (x * x) - 4. * (x * x) * r); }
+
+// Q_pp_sub2 (LeHaMoC_f.py:735-778) over the proton indices j = jhi, jhi-1, ..., jlo (x ascending)
+__device__ double pp_sub2(int sp, double E, int jlo, int jhi, const double* __restrict__ Ep_grid, double n_H,
+                          const double* lEg, const double* lN, int Np) {
+    double acc = 0.0, prev_l = 0.0, prev_y = 0.0;
+    bool first = true;
+    for (int j = jhi; j >= jlo; --j) {
+        const double x = E / Ep_grid[j];
+        const double Ep = E / x;                                    // E/x_sub2, as the reference recomputes it
+        const double L = log(Ep);
+        const double src = kHC.c * n_H * pp_cs_inel(Ep) * pp_Np(Ep, lEg, lN, Np);
+        double F;
+        if (sp == PPS_G || sp == PPS_NUMU1) {
+            double y, Bg, bg, kg;
+            if (sp == PPS_G) { y = x; Bg = 1.3 + 0.14 * L + 0.011 * (L * L); bg = 1. / (1.79 + 0.11 * L + 0.008 * (L * L)); kg = 1. / (0.801 + 0.049 * L + 0.014 * (L * L)); }
+            else { y = x / 0.427; Bg = 1.75 + 0.204 * L + 0.01 * (L * L); bg = 1. / (1.67 + 0.111 * L + 0.0038 * (L * L)); kg = 1.07 - 0.086 * L + 0.002 * (L * L); }
+            const double yb = pow(y, bg), ly = log(y);
+            const double q = (1. - yb) / (1. + kg * yb * (1. - yb));
+            F = Bg * ly / y * ((q * q) * (q * q)) * (1. / ly - 4. * bg * yb / (1. - yb) - (4. * kg * bg * yb * (1. - 2. * yb)) / (1. + kg * yb * (1. - yb)));
+        } else {
+            const double Be = 1. / (69.5 + 2.65 * L + 0.3 * (L * L));
+            const double be = 1. / pow(0.201 + 0.062 * L + 0.00042 * (L * L), 1. / 4.);
+            const double ke = (0.279 + 0.141 * L + 0.0172 * (L * L)) / (0.3 + (2.3 + L) * (2.3 + L));
+            const double lx = log(x);
+            const double t = 1. + ke * (lx * lx);
+            F = Be * (t * t * t) / (x * (1. + 0.3 / pow(x, be))) * pow(-lx, 5.);
+        }
+        const double yv = src * F, lx = log(x);
+        if (!first) acc += (lx - prev_l) * (yv + prev_y) / 2.0;
+        first = false; prev_l = lx; prev_y = yv;
+    }
+    return acc;
+}
+
+// Q_pp_sub1 (LeHaMoC_f.py:780-858) over the proton indices j = jhi ... jlo (x ascending, E_p = E/x descending)
+__device__ double pp_sub1(int sp, double E, int jlo, int jhi, const double* __restrict__ Ep_grid, double p_pr, double n_H,
+                          const double* lEg, const double* lN, int Np) {
+    const PpConst P = pp_const();
+    const double r = (P.x_m_mu / P.x_m_pi) * (P.x_m_mu / P.x_m_pi);
+    // Es = x*E_p recomputed element by element like np.multiply(x, E/x)
+    double mn_a = 1e308, mx_a = -1e308, mx_b = -1e308, mx_x = -1e308, mx_Ep = -1e308, mnEs = 1e308, mxEs = -1e308;
+    const double mass = (sp == PPS_G) ? P.x_m_pi0 : (sp == PPS_NUMU1) ? P.x_m_pi : (sp == PPS_NUMU2) ? P.x_m_mu : P.x_m_el;
+    for (int j = jhi; j >= jlo; --j) {
+        const double x = E / Ep_grid[j], Ep = E / x, Es = x * Ep;
+        const double a = Es + mass * mass / (4. * Es);
+        mn_a = fmin(mn_a, a); mx_a = fmax(mx_a, a);
+        mx_b = fmax(mx_b, Es / (1. - (P.x_m_mu / P.x_m_pi) * (P.x_m_mu / P.x_m_pi)));
+        mx_x = fmax(mx_x, x); mx_Ep = fmax(mx_Ep, Ep); mnEs = fmin(mnEs, Es); mxEs = fmax(mxEs, Es);
+    }
+    double la, lb, pre = 2.;
+    if (sp == PPS_G) { la = log10(mn_a); lb = 3.; }
+    else if (sp == PPS_NUMU1) { la = log10(fmax(mx_b, mx_a)); lb = log10(mx_x * (mx_Ep - P.x_m_pr)); pre = 2. / 0.427; }
+    else { la = log10(mx_a); lb = log10(((sp == PPS_NUE) ? 100. : 1000.) * mx_a); }
+    const bool shaped = (sp == PPS_NUMU2 || sp == PPS_E || sp == PPS_NUE);
+    const double top = (sp == PPS_E) ? mnEs : mxEs;
+    const double eta = pp_eta(p_pr, sp == PPS_G);
+    const double mpi = (sp == PPS_G) ? P.x_m_pi0 : P.x_m_pi;
+    auto E_pi_at = [&](int k) { return exp10(logspace_exp(la, lb, k, 40)); };
+    auto shape_at = [&](int k) {                       // f(x_new[k]), x_new = sorted(top/E_pi) ascending = top/E_pi[39-k]
+        const double xe = top / E_pi_at(39 - k);
+        if (sp == PPS_NUE) return (xe > r) ? pp_g_nu_e(xe, r) : pp_h_nu_e_1(r) + pp_h_nu_e_2(xe, r);
+        if (sp == PPS_NUMU2) return (xe > r) ? pp_g_nu_mu(xe, r) : pp_h_nu_mu_1(r) + pp_h_nu_mu_2(xe, r);
+        if (xe > r) { const double gv = pp_g_nu_mu(xe, r); return (gv < 0.) ? 0. : gv; }
+        const double h1 = pp_h_nu_mu_1(r), h2 = pp_h_nu_mu_2(xe, r);
+        const double f1 = (h1 < 0. || h2 < 0.) ? 0. : 1.;      // the reference zeroes flag_h_nu_mu_1 in both cases
+        return f1 * h1 + 1. * h2;                               // flag_h_nu_mu_2 stays 1 (h2 >= 0 for x <= r)
+    };
+    double norm = 1.0;
+    if (shaped) {                                       // 1/np.trapz(f, x_new)
+        double s = 0.0, px = 0.0, pf = 0.0;
+        for (int k = 0; k < 40; ++k) {
+            const double xe = top / E_pi_at(39 - k), fv = shape_at(k);
+            if (k > 0) s += (xe - px) * (fv + pf) / 2.0;
+            px = xe; pf = fv;
+        }
+        norm = 1. / s;
+    }
+    double acc = 0.0, pl = 0.0, py = 0.0;
+    for (int k = 0; k < 40; ++k) {
+        const double Epi = E_pi_at(k);
+        double yv = pp_q_pi(Epi, eta, n_H, lEg, lN, Np) / sqrt(Epi * Epi - 0. * (mpi * mpi)) * Epi;
+        if (shaped) yv = (norm * shape_at(k)) * yv;     // element k of the shape multiplies element k of E_pi (sic)
+        const double le = log(Epi);
+        if (k > 0) acc += (le - pl) * (yv + py) / 2.0;
+        pl = le; py = yv;
+    }
+    return pre * acc;
+}
+
+// One outgoing energy of one product: the un-normalised value and whether the delta-function range contributed
+__device__ double pp_value(int product, double E, int Np, const double* __restrict__ Ep_grid, double p_pr, double n_H,
+                           const double* lEg, const double* lN, bool& used_sub1) {
+    const bool nu = (product == PP_NUMU || product == PP_NUE);
+    // x_j = E/E_p[j] falls with j: {x < a} = {j >= first j with x_j < a}
+    auto first_below = [&](double a) { int lo = 0, hi = Np; while (lo < hi) { int m = (lo + hi) >> 1; if (E / Ep_grid[m] < a) hi = m; else lo = m + 1; } return lo; };
+    double q = 0.0;
+    used_sub1 = false;
+    if (E > 0.1) {
+        const int jlo = first_below(0.427);
+        const int jhi = nu ? first_below(1e-3) - 1 : Np - 1;       // neutrinos: x > 1e-3 as well; x == 1e-3 belongs to neither
+        int jh = jhi;
+        if (nu) { while (jh >= jlo && !(E / Ep_grid[jh] > 1e-3)) --jh; }
+        if (jh >= jlo) {
+            if (product == PP_E) q += pp_sub2(PPS_E, E, jlo, jh, Ep_grid, n_H, lEg, lN, Np);
+            else if (product == PP_G) q += pp_sub2(PPS_G, E, jlo, jh, Ep_grid, n_H, lEg, lN, Np);
+            else if (product == PP_NUE) q += pp_sub2(PPS_NUE, E, jlo, jh, Ep_grid, n_H, lEg, lN, Np);
+            else q += pp_sub2(PPS_NUMU1, E, jlo, jh, Ep_grid, n_H, lEg, lN, Np) + pp_sub2(PPS_NUMU2, E, jlo, jh, Ep_grid, n_H, lEg, lN, Np);
+        }
+    } else if (E < 0.1) {
+        const int jlo = first_below(nu ? 1e-3 : 1.);
+        if (jlo <= Np - 1) {
+            used_sub1 = true;
+            if (product == PP_E) q += pp_sub1(PPS_E, E, jlo, Np - 1, Ep_grid, p_pr, n_H, lEg, lN, Np);
+            else if (product == PP_G) q += pp_sub1(PPS_G, E, jlo, Np - 1, Ep_grid, p_pr, n_H, lEg, lN, Np);
+            else if (product == PP_NUE) q += pp_sub1(PPS_NUE, E, jlo, Np - 1, Ep_grid, p_pr, n_H, lEg, lN, Np);
+            else q += pp_sub1(PPS_NUMU1, E, jlo, Np - 1, Ep_grid, p_pr, n_H, lEg, lN, Np) + pp_sub1(PPS_NUMU2, E, jlo, Np - 1, Ep_grid, p_pr, n_H, lEg, lN, Np);
+        }
+    }
+    return q;
+}
+
+// the whole function (LeHaMoC_f.py:860-1014) for one product by the CTA: out[k], k < Nout; flag [Nout] scratch ints
+// Es[k] = outgoing energies in TeV (caller-provided array in shared/global memory)
+__device__ void pp_product(int product, int Nout, const double* Es, int Np, const double* Ep_grid, double p_pr, double n_H,
+                           const double* lEg, const double* lN, double* out, int* flag, int nthreads) {
+    for (int k = threadIdx.x; k < Nout; k += nthreads) {
+        bool u1;
+        out[k] = pp_value(product, Es[k], Np, Ep_grid, p_pr, n_H, lEg, lN, u1);
+        flag[k] = u1 ? 1 : 0;
+    }
+    __syncthreads();
+    // norm_ind = number of energies whose delta-function range contributed; two-point linregress at norm_ind, norm_ind+1
+    if (threadIdx.x == 0) {
+        int ni = 0;
+        for (int k = 0; k < Nout; ++k) ni += flag[k];
+        flag[0] = ni;
+    }
+    __syncthreads();
+    const int ni = flag[0];
+    __syncthreads();
+    if (ni >= 1 && ni + 1 < Nout) {
+        const double x0 = log10(Es[ni]), x1 = log10(Es[ni + 1]), y0 = log10(out[ni]), y1 = log10(out[ni + 1]);
+        // scipy.stats.linregress on two points: slope = ssxym/ssxm with biased second moments about the means
+        const double xm = (x0 + x1) / 2., ym = (y0 + y1) / 2.;
+        const double ssxm = ((x0 - xm) * (x0 - xm) + (x1 - xm) * (x1 - xm)) / 2.;
+        const double ssxym = ((x0 - xm) * (y0 - ym) + (x1 - xm) * (y1 - ym)) / 2.;
+        const double slope = ssxym / ssxm, intercept = ym - slope * xm;
+        const double y_fit = exp10(slope * log10(Es[ni - 1]) + intercept);
+        const double norm = y_fit / out[ni - 1];
+        __syncthreads();
+        for (int k = threadIdx.x; k < ni; k += nthreads) out[k] = norm * out[k];
+    }
+    __syncthreads();
+}
+
+struct PpArgs {
+    int W, product, Nout, Np;
+    const double *grid;                 // [W,Nout]: g_el, nu_ic or nu_nu of the product
+    const double *g_pr, *N_pr_TeV;      // [W,Np]
+    const double *p_pr, *n_H;           // [W]
+    double* out;                        // [W,Nout]
+};
+
+__global__ void __launch_bounds__(HAD_NT) had_pp_kernel(PpArgs A) {
+    extern __shared__ __align__(16) double sh[];
+    const int w = blockIdx.x, tid = threadIdx.x, Np = A.Np, Nout = A.Nout;
+    const PpConst P = pp_const();
+    const HadConst& K = kHC;
+    double* Ep = sh; double* lEg = Ep + Np; double* lN = lEg + Np; double* Es = lN + Np; double* out = Es + Nout;
+    int* flag = reinterpret_cast<int*>(out + Nout);
+    for (int j = tid; j < Np; j += HAD_NT) {
+        const double g = A.g_pr[(size_t)w * Np + j];
+        Ep[j] = g * K.m_pr * (K.c * K.c) * P.tev;                        // E_p_space, LeHaMoC_f.py:864
+        lEg[j] = log10(g * P.x_m_pr);
+        lN[j] = log10(A.N_pr_TeV[(size_t)w * Np + j]);
+    }
+    for (int k = tid; k < Nout; k += HAD_NT) {
+        const double v = A.grid[(size_t)w * Nout + k];
+        Es[k] = (A.product == PP_E) ? v * K.m_el * (K.c * K.c) * P.tev : K.h * v * P.tev;
+    }
+    __syncthreads();
+    pp_product(A.product, Nout, Es, Np, Ep, A.p_pr[w], A.n_H[w], lEg, lN, out, flag, HAD_NT);
+    for (int k = tid; k < Nout; k += HAD_NT) A.out[(size_t)w * Nout + k] = out[k];
+}
+
+}  // namespace lhm

@@ -127,6 +127,45 @@ def Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons_targ, nu_target, flag_product):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
+# A14 pp channels (LeHaMoC_f.py:687-1014).  Same signatures as the reference; 1-D inputs: one walker, 2-D: a batch.
+# ---------------------------------------------------------------------------------------------------------------------
+def _pp(product, grid, g_pr, N_pr_TeV, p_pr, n_H):
+    lib = _lib.load()
+    one = np.ndim(grid) == 1
+    gr, gp, NT = _dev2(grid), _dev2(g_pr), _dev2(N_pr_TeV)
+    W = gr.shape[0]
+    if gp.shape[0] != W or NT.shape != gp.shape:
+        raise ValueError("grid [W,Nout], g_pr and N_pr_TeV [W,Np] must agree on W")
+    pp = torch.from_numpy(np.broadcast_to(np.asarray(p_pr, dtype=np.float64), (W,)).copy()).cuda()
+    nh = torch.from_numpy(np.broadcast_to(np.asarray(n_H, dtype=np.float64), (W,)).copy()).cuda()
+    out = torch.empty_like(gr)
+    check(lib.lhm_pp_batch(W, product, gr.shape[1], gp.shape[1], _p(gr), _p(gp), _p(NT), _p(pp), _p(nh), _p(out),
+                           C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lhm_pp_batch")
+    r = out.cpu().numpy()
+    return r[0] if one else r
+
+
+def Q_e_pp(g_el, g_pr, N_pr_TeV, p_pr, n_H):
+    """Secondary e+- from pp collisions per electron energy in TeV (LeHaMoC_f.py:860-895)."""
+    return _pp(0, g_el, g_pr, N_pr_TeV, p_pr, n_H)
+
+
+def Q_g_pp(nu_ic, g_pr, N_pr_TeV, p_pr, n_H):
+    """pi0-decay photons from pp collisions (LeHaMoC_f.py:897-932)."""
+    return _pp(1, nu_ic, g_pr, N_pr_TeV, p_pr, n_H)
+
+
+def Q_nu_mu_pp(nu_nu, g_pr, N_pr_TeV, p_pr, n_H):
+    """Muon neutrinos from pp collisions, both decay stages (LeHaMoC_f.py:934-975)."""
+    return _pp(2, nu_nu, g_pr, N_pr_TeV, p_pr, n_H)
+
+
+def Q_nu_e_pp(nu_nu, g_pr, N_pr_TeV, p_pr, n_H):
+    """Electron neutrinos from pp collisions (LeHaMoC_f.py:977-1014)."""
+    return _pp(3, nu_nu, g_pr, N_pr_TeV, p_pr, n_H)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
 # A13 Bethe-Heitler pair injection: host set-up (LeHaMoC_f.py:238-341).  The reference tabulates the energy-integrated
 # differential cross section on a 30 x 30 x 30 lattice (27 000 Simpson integrals) and fits two smoothing bivariate
 # splines with scipy.interpolate.bisplrep; that fit stays on the host (SciPy/FITPACK, as in the reference), the spline

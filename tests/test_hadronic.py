@@ -163,3 +163,30 @@ def test_oracle_pp_channels(gold_pp):
                 ref = g[tag + name]
                 nz = ref != 0
                 assert np.array_equal(got[~nz], ref[~nz]) and np.max(np.abs(got[nz] / ref[nz] - 1)) < 1e-13, (tag, name)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,grid", PP_FUNCS)
+def test_gpu_pp_channels(gold_pp, name, grid):
+    """lhm_pp_batch against the live reference's Q_*_pp (LeHaMoC_f.py:860-1014): 1e-8 relative, zeros exact."""
+    from lehamoc_b200 import hadronic as had
+    g = gold_pp
+    for case in (0, 1):
+        for p in (2.01, 2.5):
+            tag = f"c{case}_p{int(p * 100)}_"
+            got = getattr(had, name)(g[grid], g[f"c{case}_g_pr"], g[f"c{case}_N_pr_TeV"], p, 1.5)
+            ref = g[tag + name]
+            nz = ref != 0
+            assert np.array_equal(got[~nz], ref[~nz]), (tag, name, got[~nz])
+            err = np.max(np.abs(got[nz] / ref[nz] - 1))
+            assert err < 1e-8, (tag, name, err, np.argmax(np.abs(got[nz] / ref[nz] - 1)))
+
+
+@pytest.mark.gpu
+def test_gpu_pp_batch_equals_single(gold_pp):
+    from lehamoc_b200 import hadronic as had
+    g = gold_pp
+    gp = np.stack([g["c0_g_pr"], g["c1_g_pr"]]); NT = np.stack([g["c0_N_pr_TeV"], g["c1_N_pr_TeV"]])
+    both = had.Q_nu_mu_pp(np.stack([g["nu_nu"]] * 2), gp, NT, np.array([2.01, 2.5]), np.array([1.5, 1.5]))
+    for c, p in ((0, 2.01), (1, 2.5)):
+        np.testing.assert_array_equal(both[c], had.Q_nu_mu_pp(g["nu_nu"], gp[c], NT[c], p, 1.5))
