@@ -68,6 +68,9 @@ typedef struct {
     int pg_pi_l_flag, pg_BH_l_flag;     /* driver 1: photopion / Bethe-Heitler proton loss terms   LeHaMoC.py:311-323 */
     int pg_pi_emis_flag, neutrino_flag; /* driver 1: photopion pairs + photons, neutrinos           LeHaMoC.py:343-352 */
     int pg_BH_emis_flag;                /* driver 1: Bethe-Heitler pair injection (lhm_set_bh_surfaces) LeHaMoC.py:337-340 */
+    int pp_l_flag;                      /* driver 1: pp loss term of the proton equation            LeHaMoC.py:322-328 */
+    int pp_ee_emis_flag, pp_g_emis_flag, pp_nu_emis_flag; /* driver 1: pp pairs, pi0 photons, neutrinos (n_H, p_pr in
+                                           the per-walker scalar block)                               LeHaMoC.py:354-395 */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 
@@ -83,6 +86,8 @@ enum {
     LHM_C_COR_P,            /* p_el passed to cor_factor_syn_el          LeMoC.py:251 */
     LHM_C_COR_Q0,           /* Q_el_Lum(L, p, g[1], g[-2])               LeHaMoC_f.py:202 */
     LHM_C_COR_B,            /* 1e4 G                                     LeMoC.py:251 */
+    LHM_C_NH,               /* cold proton density n_H, cm^-3 (pp)       LeHaMoC.py:114 */
+    LHM_C_PPR,              /* p_pr as the pp functions receive it        LeHaMoC.py:95  */
     LHM_NCONST = 12
 };
 

@@ -13,7 +13,7 @@ LHM_IC_PATH_R = 0
 LHM_IC_PATH_S = 1
 LHM_NCONST = 12
 # indices of the per-walker scalar block (include/lhm.h)
-C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B = range(10)
+C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B, C_NH, C_PPR = range(12)
 
 
 class LhmError(RuntimeError):
@@ -26,7 +26,8 @@ class lhm_config(C.Structure):
         "inj_flag", "Ad_l_flag", "Syn_l_flag", "Syn_emis_flag", "IC_l_flag", "IC_emis_flag", "SSA_l_flag",
         "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "ic_pair_table",
         "shared_ic_grids", "driver", "Np", "esc_flag_pr", "pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag",
-        "neutrino_flag", "pg_BH_emis_flag", "max_walkers")]
+        "neutrino_flag", "pg_BH_emis_flag", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
+        "max_walkers")]
 
 
 # every symbol include/lhm.h declares: (restype, argtypes)

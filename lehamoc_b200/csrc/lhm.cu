@@ -161,6 +161,7 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
     const double cor = A.cor ? A.cor[w] : 1.0;
+    const double n_H = A.consts[(size_t)w * LHM_NCONST + LHM_C_NH], p_pr = A.consts[(size_t)w * LHM_NCONST + LHM_C_PPR];
     // initial state (LeHaMoC.py:222-259): N_el = el_inj * Volume(R0), N_pr = 0, photons 1e-260
     const double V0 = volume_of(C.R0);
     for (int j = tid; j < Ng; j += NT) {
@@ -194,10 +195,12 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
         C.V = volume_of(C.Rad);
         phase_photons<NT>(C, S, true);
         if (C.F.ic_l) phase_uph_lh<NT>(C, S);
-        phase_protons<NT>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr);
+        phase_protons<NT>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
         if (C.F.bh_e) phase_bh_emis<NT>(C, S, H, BSm, BSp);
         if (C.F.pg_e) phase_photopion<NT>(C, S, H, A.HT);
-        phase_electrons_lh<NT>(C, S, C.F.pg_e ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
+        else if (A.had) { for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0; }
+        if (C.F.pp_ee || C.F.pp_g || C.F.pp_nu) phase_pp<NT>(C, S, H, n_H, p_pr);
+        phase_electrons_lh<NT>(C, S, (C.F.pg_e || C.F.pp_ee) ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
         phase_vectors<NT>(C, S);
         phase_syn_rows<NT>(C, S, false);
         phase_syn_protons<NT>(C, S, H);
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
         }
         __syncthreads();
         if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
-        phase_photon_solves_lh<NT>(C, S, H, cor, C.F.pg_e ? H.Qpg : nullptr);
+        phase_photon_solves_lh<NT>(C, S, H, cor, (C.F.pg_e || C.F.pp_g) ? H.Qpg : nullptr);
         if (C.F.gg) phase_gg_lh<NT>(C, S, H, step);
         if (A.had) {                                             // neutrino equation: escape only, LeHaMoC.py:430-434
             const double V2 = 1.0 + C.dt * (kPC.c / C.Rad);
@@ -605,11 +608,12 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
     F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
     F.bh_e = cfg->pg_BH_emis_flag;
-    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu || F.bh_e)) { delete h; return LHM_ERR_ARG; }
+    F.pp_l = cfg->pp_l_flag; F.pp_ee = cfg->pp_ee_emis_flag; F.pp_g = cfg->pp_g_emis_flag; F.pp_nu = cfg->pp_nu_emis_flag;
+    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu || F.bh_e || F.pp_l || F.pp_ee || F.pp_g || F.pp_nu)) { delete h; return LHM_ERR_ARG; }
     h->smem = smem_bytes(h->L, NW);
     if (cfg->driver >= 1) {
         h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
-        if (F.pg_l || F.bh_l || F.pg_e || F.bh_e) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
+        if (any_hadronic(F)) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
     }
     if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
     PhysConst pc = make_consts();
@@ -736,6 +740,7 @@ int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double*
     if (h->cfg.driver < 1) return LHM_ERR_STATE;
     if ((h->F.pg_l || h->F.bh_l || h->F.pg_e) && !h->have_HT) return LHM_ERR_STATE;
     if (h->F.bh_e && !h->have_BS) return LHM_ERR_STATE;
+    if (any_hadronic(h->F)) { int rc0 = had_init(); if (rc0 != LHM_OK) return rc0; }
     g_nnu_out = N_nu_out;
     int rc = run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
     g_nnu_out = nullptr;
@@ -762,7 +767,7 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
     A.Np_out = N_pr_out; A.esc_pr = h->cfg.esc_flag_pr;
     A.Nnu_out = lh ? g_nnu_out : nullptr;
-    A.had = lh && (h->F.pg_l || h->F.bh_l || h->F.pg_e || h->F.bh_e);
+    A.had = lh && any_hadronic(h->F);
     if (A.had && h->have_HT) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
     std::memset(&A.BSm, 0, sizeof(A.BSm)); std::memset(&A.BSp, 0, sizeof(A.BSp));
     if (lh && h->F.bh_e) { A.BSm = h->BSm; A.BSp = h->BSp; }

@@ -726,25 +726,18 @@ __device__ double pp_value(int product, double E, int Np, const double* __restri
     return q;
 }
 
-// the whole function (LeHaMoC_f.py:860-1014) for one product by the CTA: out[k], k < Nout; flag [Nout] scratch ints
-// Es[k] = outgoing energies in TeV (caller-provided array in shared/global memory)
+// the whole function (LeHaMoC_f.py:860-1014) for one product by the CTA (all `nthreads` threads must call): out[k],
+// k < Nout; Es[k] = outgoing energies in TeV (shared memory).  Ends with a barrier.
 __device__ void pp_product(int product, int Nout, const double* Es, int Np, const double* Ep_grid, double p_pr, double n_H,
-                           const double* lEg, const double* lN, double* out, int* flag, int nthreads) {
-    for (int k = threadIdx.x; k < Nout; k += nthreads) {
-        bool u1;
-        out[k] = pp_value(product, Es[k], Np, Ep_grid, p_pr, n_H, lEg, lN, u1);
-        flag[k] = u1 ? 1 : 0;
-    }
-    __syncthreads();
+                           const double* lEg, const double* lN, double* out, int nthreads) {
     // norm_ind = number of energies whose delta-function range contributed; two-point linregress at norm_ind, norm_ind+1
-    if (threadIdx.x == 0) {
-        int ni = 0;
-        for (int k = 0; k < Nout; ++k) ni += flag[k];
-        flag[0] = ni;
+    int ni = 0;
+    for (int k0 = 0; k0 < Nout; k0 += nthreads) {
+        const int k = k0 + threadIdx.x;
+        bool u1 = false;
+        if (k < Nout) out[k] = pp_value(product, Es[k], Np, Ep_grid, p_pr, n_H, lEg, lN, u1);
+        ni += __syncthreads_count(u1 ? 1 : 0);
     }
-    __syncthreads();
-    const int ni = flag[0];
-    __syncthreads();
     if (ni >= 1 && ni + 1 < Nout) {
         const double x0 = log10(Es[ni]), x1 = log10(Es[ni + 1]), y0 = log10(out[ni]), y1 = log10(out[ni + 1]);
         // scipy.stats.linregress on two points: slope = ssxym/ssxm with biased second moments about the means
@@ -774,7 +767,6 @@ __global__ void __launch_bounds__(HAD_NT) had_pp_kernel(PpArgs A) {
     const PpConst P = pp_const();
     const HadConst& K = kHC;
     double* Ep = sh; double* lEg = Ep + Np; double* lN = lEg + Np; double* Es = lN + Np; double* out = Es + Nout;
-    int* flag = reinterpret_cast<int*>(out + Nout);
     for (int j = tid; j < Np; j += HAD_NT) {
         const double g = A.g_pr[(size_t)w * Np + j];
         Ep[j] = g * K.m_pr * (K.c * K.c) * P.tev;                        // E_p_space, LeHaMoC_f.py:864
@@ -786,7 +778,7 @@ __global__ void __launch_bounds__(HAD_NT) had_pp_kernel(PpArgs A) {
         Es[k] = (A.product == PP_E) ? v * K.m_el * (K.c * K.c) * P.tev : K.h * v * P.tev;
     }
     __syncthreads();
-    pp_product(A.product, Nout, Es, Np, Ep, A.p_pr[w], A.n_H[w], lEg, lN, out, flag, HAD_NT);
+    pp_product(A.product, Nout, Es, Np, Ep, A.p_pr[w], A.n_H[w], lEg, lN, out, HAD_NT);
     for (int k = tid; k < Nout; k += HAD_NT) A.out[(size_t)w * Nout + k] = out[k];
 }
 

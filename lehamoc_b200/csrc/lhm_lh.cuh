@@ -193,7 +193,7 @@ __device__ void phase_uph_lh(const Ctx& C, Smem& S) {
 // proton equation (LeHaMoC.py:330-335 with the hadronic loss terms off): synchrotron cooling + escape + injection
 template <int NT>
 __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, const LossTab* Tb, bool per_volume = true,
-                              bool inject = true) {
+                              bool inject = true, double n_H = 0.0) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Np - 2;
     const bool had = C.F.pg_l || C.F.bh_l;
@@ -224,6 +224,14 @@ __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, cons
             const double idg = C.T[L.idgp + j];
             lm = (H.lossA[j] + H.lossB[j]) * idg;
             lp = (H.lossA[j + 1] + H.lossB[j + 1]) * idg;
+        }
+        if (C.F.pp_l) {                              // LeHaMoC.py:322-326: 0.65 c n_H sigma_inel(E_kin [TeV])/(m_p c^2)/dg_pr
+            const double idg = C.T[L.idgp + j];
+            const double mpc2 = kHC.m_pr * (kHC.c * kHC.c);
+            const double rest = mpc2 * 0.624151;
+            const double gm0 = C.T[L.gpm + j], gm1 = C.T[L.gpm + j + 1];
+            lm += 0.65 * kHC.c * n_H * pp_cs_inel(gm0 * kHC.m_pr * (kHC.c * kHC.c) * 0.624151 - rest) / mpc2 * idg;
+            lp += 0.65 * kHC.c * n_H * pp_cs_inel(gm1 * kHC.m_pr * (kHC.c * kHC.c) * 0.624151 - rest) / mpc2 * idg;
         }
         const double V2 = 1.0 + C.dt * (esc + b_syn * C.T[L.spm + j] + lm);
         const double V3 = -C.dt * (b_syn * C.T[L.spp + j] + lp);
@@ -328,6 +336,55 @@ __device__ void phase_photopion(const Ctx& C, Smem& S, SmemLh& H, const HadTable
         I.species = SP_ANUE;  pion_eval(I, H.work, H.Qnu, C.dt, true);
     } else {
         for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0;
+        __syncthreads();
+    }
+}
+
+// pp secondaries, LeHaMoC.py:354-357, 387-395.  Adds m_e c^2 Q_e_pp onto the photopion pair source H.Qpi, h Q_g_pp onto
+// H.Qpg and 2 (Q_nu_e_pp + Q_nu_mu_pp) dt h V onto H.Qnu (each zeroed first when photopion production is off).
+// Scratch: the Bethe-Heitler chunk buffer (free after phase_bh_emis) and the solver scratch S.cp / S.dp.
+template <int NT>
+__device__ void phase_pp(const Ctx& C, Smem& S, SmemLh& H, double n_H, double p_pr) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, Np = L.Np;
+    const PpConst P = pp_const();
+    double* Ep = H.bhbuf; double* lEg = Ep + pad2(Np); double* lN = lEg + pad2(Np);
+    double* Es = S.cp; double* out = S.dp;
+    const double mc2e = kHC.m_el * (kHC.c * kHC.c);
+    for (int j = tid; j < Np; j += NT) {
+        const double g = C.T[L.gp + j];
+        Ep[j] = g * kHC.m_pr * (kHC.c * kHC.c) * P.tev;
+        lEg[j] = log10(g * P.x_m_pr);
+        lN[j] = log10((H.Npr[j] / C.V) / (kHC.m_pr * (kHC.c * kHC.c) * 0.624151));
+    }
+    if (!C.F.pg_e) {
+        for (int j = tid; j < L.Ng; j += NT) H.Qpi[j] = 0.0;
+        for (int k = tid; k < L.Ni; k += NT) H.Qpg[k] = 0.0;
+    }
+    __syncthreads();
+    if (C.F.pp_ee) {
+        for (int j = tid; j < L.Ng; j += NT) Es[j] = S.gS[j] * kHC.m_el * (kHC.c * kHC.c) * P.tev;
+        __syncthreads();
+        pp_product(PP_E, L.Ng, Es, Np, Ep, p_pr, n_H, lEg, lN, out, NT);
+        for (int j = tid; j < L.Ng; j += NT) H.Qpi[j] += out[j] * mc2e;
+        __syncthreads();
+    }
+    if (C.F.pp_g) {
+        for (int k = tid; k < L.Ni; k += NT) Es[k] = kHC.h * S.nuoS[k] * P.tev;
+        __syncthreads();
+        pp_product(PP_G, L.Ni, Es, Np, Ep, p_pr, n_H, lEg, lN, out, NT);
+        for (int k = tid; k < L.Ni; k += NT) H.Qpg[k] += out[k] * kHC.h;
+        __syncthreads();
+    }
+    if (C.F.pp_nu) {
+        for (int k = tid; k < 50; k += NT) Es[k] = kHC.h * (H.Enu[k] / kHC.h) * P.tev;     // nu_nu = E_nu/h, LeHaMoC.py:173
+        __syncthreads();
+        double q = 0.0;
+        pp_product(PP_NUE, 50, Es, Np, Ep, p_pr, n_H, lEg, lN, out, NT);
+        if (tid < 50) q = 2. * (out[tid] * C.dt) * kHC.h * C.V;
+        __syncthreads();
+        pp_product(PP_NUMU, 50, Es, Np, Ep, p_pr, n_H, lEg, lN, out, NT);
+        if (tid < 50) H.Qnu[tid] += q + 2. * (out[tid] * C.dt) * kHC.h * C.V;
         __syncthreads();
     }
 }

@@ -18,9 +18,14 @@ namespace lhm {
 
 struct StepFlags {
     int inj, ad, syn_l, syn_e, ic_l, ic_e, ssa, gg, esc, qee_from_ic, ic_path;
+    int pp_l, pp_ee, pp_g, pp_nu;   // LeHaMoC.py driver: pp loss term, pp pairs / pi0 photons / neutrinos
     int pg_l, bh_l, pg_e, nu, bh_e; // LeHaMoC.py driver: photopion / Bethe-Heitler loss, photopion emission, neutrinos,
                                     // Bethe-Heitler pair injection
 };
+
+__host__ __device__ inline bool any_hadronic(const StepFlags& F) {
+    return F.pg_l || F.bh_l || F.pg_e || F.bh_e || F.pp_l || F.pp_ee || F.pp_g || F.pp_nu;
+}
 
 // shared-memory carve-up; all pointers are into dynamic shared memory
 struct Smem {
@@ -49,7 +54,7 @@ __host__ __device__ inline int pad2(int n) { return (n + 1) & ~1; }
 
 __host__ __device__ inline size_t smem_doubles(const Layout& L, int NW) {
     int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
-    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, 0);
+    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, L.Np > 0 ? imax3(L.Np, 52, 0) : 0);   // LeHaMoC.py driver: proton and neutrino (50) solves too
     size_t d = 0;
     d += pad2(Ng) * 2 + pad2(Ns) + pad2(Ni) * 2;            // state
     d += pad2(Ns) + pad2(Ni);                               // logs
@@ -80,7 +85,7 @@ __host__ __device__ inline size_t smem_bytes(const Layout& L, int NW) {
 
 __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
-    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, 0);
+    int Nmax = imax3(imax3(Ng, Ns, Ni), Nt, L.Np > 0 ? imax3(L.Np, 52, 0) : 0);   // LeHaMoC.py driver: proton and neutrino (50) solves too
     double* p = base;
     auto take = [&](int n) { double* r = p; p += n; return r; };
     S.N = take(pad2(Ng)); S.qee = take(pad2(Ng)); S.psyn = take(pad2(Ns)); S.pic = take(pad2(Ni)); S.agg = take(pad2(Ni));

@@ -233,8 +233,9 @@ LH_KEYS = ("time_init", "time_end", "step_alg", "PL_inj", "g_min_el", "g_max_el"
            "pg_BH_emis_flag", "n_H", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
            "neutrino_flag", "esc_flag_el", "esc_flag_pr", "BB_flag", "temperature", "GB_ext", "PL_flag", "dE_dV_ph",
            "nu_min_ph", "nu_max_ph", "s_ph", "User_ph")
-UNSUPPORTED_FLAGS = ("pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag")
+UNSUPPORTED_FLAGS = ()
 PHOTOHADRONIC_FLAGS = ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag", "neutrino_flag", "pg_BH_emis_flag")
+PP_FLAGS = ("pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag")
 m_pr_ = 1.67262192369e-24
 
 
@@ -254,8 +255,9 @@ def pack_lehamoc(param_sets) -> Batch:
     Parameters.txt).  Set-up with the reference's own expressions, LeHaMoC.py:132-259, one walker at a time (this
     driver is not on the headline path; the loop costs ~50 us per walker).  Supported: leptonic processes, proton
     equation with synchrotron / photopion / Bethe-Heitler losses, proton synchrotron, photopion pairs, photons and
-    neutrinos, Bethe-Heitler pair injection; the pp channels raise NotImplementedError."""
-    from ._lib import LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B
+    neutrinos, Bethe-Heitler pair injection, pp loss term and pp secondaries (n_H and p_pr may differ per walker)."""
+    from ._lib import (LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B, C_NH,
+                       C_PPR)
     if isinstance(param_sets, dict):
         param_sets = [param_sets]
     F = param_sets[0]
@@ -263,11 +265,8 @@ def pack_lehamoc(param_sets) -> Batch:
     if missing:
         raise KeyError(f"parameter file lacks {missing}")
     per_walker = ("g_min_el", "g_max_el", "g_el_PL_min", "g_el_PL_max", "g_min_pr", "g_max_pr", "g_pr_PL_min",
-                  "g_pr_PL_max", "p_el", "L_el", "p_pr", "L_pr", "R0", "B0")
+                  "g_pr_PL_max", "p_el", "L_el", "p_pr", "L_pr", "R0", "B0", "n_H")
     for P in param_sets:
-        for k in UNSUPPORTED_FLAGS:
-            if float(P[k]) != 0.:
-                raise NotImplementedError(f"{k} = {P[k]}: the pp channels are not built yet (DESIGN.md section 8)")
         if float(P["User_ph"]) != 0.:
             raise NotImplementedError("User_ph: Photons_spec_user.txt input is not supported yet")
         for k in LH_KEYS:
@@ -315,11 +314,12 @@ def pack_lehamoc(param_sets) -> Batch:
         consts[w, C_COR_P] = f("p_el")
         consts[w, C_COR_Q0] = _Q_el_Lum(_Lum_e_inj(comp_el, R0), f("p_el"), ge[1], ge[-2])     # LeHaMoC_f.py:646
         consts[w, C_COR_B] = 10 ** 4.
+        consts[w, C_NH], consts[w, C_PPR] = f("n_H"), f("p_pr")                                # LeHaMoC.py:95,114
     cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=100, loss_minus_one=1, qee_from_ic=0,
                const_B=int(float(F["m"]) == 0. or Vexp == 0.), ic_pair_table=1,
                shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))),
                driver=1, Np=Np, esc_flag_pr=_flag01(F, "esc_flag_pr"))
-    for k in PHOTOHADRONIC_FLAGS:
+    for k in PHOTOHADRONIC_FLAGS + PP_FLAGS:
         cfg[k] = _flag01(F, k)
     if cfg["neutrino_flag"] and not cfg["pg_pi_emis_flag"]:
         cfg["neutrino_flag"] = 0                 # LeHaMoC.py:346 only looks at it inside the pg_pi_emis branch

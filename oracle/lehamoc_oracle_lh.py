@@ -8,7 +8,7 @@ Restates the driver LeHaMoC.py:132-453 with the `f_had` variants of the function
 Electron AND proton equations, proton synchrotron, the gamma-gamma pre-attenuation of the first two steps
 (LeHaMoC.py:418-426) and the neutrino equation are included; of the hadronic channels the photopion and Bethe-Heitler
 LOSS terms, the photopion emissivities and the Bethe-Heitler pair injection (spline surfaces handed in as `bh_surf`)
-are wired to lehamoc_oracle_had.py; the pp channels (linregress matching) raise NotImplementedError.
+and the pp loss term and secondaries (LeHaMoC.py:322-328, 354-357, 387-395) are wired to lehamoc_oracle_had.py.
 
 Parity pinning: oracle/make_golden_lh.py runs the unmodified script (oracle/run_reference_lh.py) and stores every
 step's four output snapshots in tests/golden/lh_*.npz; tests/test_lehamoc_driver.py checks this restatement against them.
@@ -205,8 +205,6 @@ class LeptoHadronicRun:
         self.N_el[0] = self.N_el[-1] = SENT
         self.interv = 0.
         self.Radius = R0
-        if self.pp_l_flag == 1. or self.pp_ee_emis_flag == 1. or self.pp_g_emis_flag == 1. or self.pp_nu_emis_flag == 1.:
-            raise NotImplementedError("pp channels are not restated yet")
         self.bh_surf = None                                   # (tck_m, tck_p, max_m, max_p) of interp_cs_BH_int
 
     def n_steps(self):
@@ -262,8 +260,14 @@ class LeptoHadronicRun:
             bh_p = oh.dg_dt_BH(pmp[1:], nu_tot, photons, self.tables) / dgp
         else:
             bh_m = bh_p = np.zeros(np_)
-        V2 = 1. + dt * (c / Radius * self.esc_flag_pr + syn_pr_m + pg_m + bh_m)
-        V3 = -dt * (syn_pr_p + pg_p + bh_p)
+        if self.pp_l_flag == 1.:                               # LeHaMoC.py:322-328
+            rest = m_pr * c ** 2. * 0.624151
+            pp_m = np.divide(0.65 * c * self.n_H * oh.cs_pp_inel(pmp[0:-1] * m_pr * c ** 2. * 0.624151 - rest) / (m_pr * c ** 2.), dgp)
+            pp_p = np.divide(0.65 * c * self.n_H * oh.cs_pp_inel(pmp[1:] * m_pr * c ** 2. * 0.624151 - rest) / (m_pr * c ** 2.), dgp)
+        else:
+            pp_m = pp_p = np.zeros(np_)
+        V2 = 1. + dt * (c / Radius * self.esc_flag_pr + syn_pr_m + pg_m + bh_m + pp_m)
+        V3 = -dt * (syn_pr_p + pg_p + bh_p + pp_p)
         S = self.N_pr[1:-1] + np.multiply(self.pr_inj[1:-1], dt) * V
         self.N_pr[1:-1] = bidiag_solve(V2, V3, S)
         n_p = np.array(self.N_pr / V)
@@ -283,12 +287,28 @@ class LeptoHadronicRun:
                 Q_pg_nu = np.zeros(48)
         else:
             Q_pg_pi, Q_pg_g, Q_pg_nu = np.zeros(ne_), np.zeros(len(nu_ic) - 2), np.zeros(48)
+        N_TeV = n_p / (m_pr * c ** 2. * 0.624151)
+        nu_nu = np.logspace(10., 22., 50) * eV / h               # LeHaMoC.py:173
+        with np.errstate(all="ignore"):
+            if self.pp_ee_emis_flag == 1.:                       # LeHaMoC.py:354-357
+                Q_pp_ee = np.multiply(oh.Q_e_pp(g_el, g_pr, N_TeV, self.p_pr, self.n_H)[1:-1], m_el * c ** 2.)
+            else:
+                Q_pp_ee = np.zeros(ne_)
+            if self.pp_g_emis_flag == 1.:                        # LeHaMoC.py:387-390
+                Q_pp_g = np.multiply(oh.Q_g_pp(nu_ic, g_pr, N_TeV, self.p_pr, self.n_H)[1:-1], h)
+            else:
+                Q_pp_g = np.zeros(len(nu_ic) - 2)
+            if self.pp_nu_emis_flag == 1.:                       # LeHaMoC.py:392-395
+                Q_pp_nu = 2. * np.multiply(oh.Q_nu_e_pp(nu_nu, g_pr, N_TeV, self.p_pr, self.n_H)[1:-1], dt) * h * V \
+                    + 2. * np.multiply(oh.Q_nu_mu_pp(nu_nu, g_pr, N_TeV, self.p_pr, self.n_H)[1:-1], dt) * h * V
+            else:
+                Q_pp_nu = np.zeros(48)
         V2 = 1. + dt * (c / Radius * self.esc_flag_el + syn_el_m + ic_m + ad_el_m)
         V3 = -dt * (syn_el_p + ic_p + ad_el_p)
         if self.inj_flag == 1.:
-            S = self.N_el[1:-1] + np.multiply(self.el_inj[1:-1] + self.Q_ee + Q_pg_pi + Q_pg_BH, dt) * V
+            S = self.N_el[1:-1] + np.multiply(self.el_inj[1:-1] + self.Q_ee + Q_pg_pi + Q_pg_BH + Q_pp_ee, dt) * V
         elif self.inj_flag == 0.:
-            S = self.N_el[1:-1] + (self.Q_ee + Q_pg_pi + Q_pg_BH) * dt * V
+            S = self.N_el[1:-1] + (self.Q_ee + Q_pg_pi + Q_pg_BH + Q_pp_ee) * dt * V
         else:
             raise ValueError("inj_flag must be 0 or 1")
         self.N_el[1:-1] = bidiag_solve(V2, V3, S)
@@ -313,7 +333,7 @@ class LeptoHadronicRun:
         self.photons_syn[1:-1] = bidiag_solve(V2, V3, S)
         V2 = 1. + dt * (c / Radius + adi_m - aI * c + self.a_gg_ic * c)
         V3 = -dt * adi_p
-        S = self.photons_IC[1:-1] + (Q_IC + Q_pg_g) * dt * V
+        S = self.photons_IC[1:-1] + (Q_IC + Q_pg_g + Q_pp_g) * dt * V
         self.photons_IC[1:-1] = bidiag_solve(V2, V3, S)
         if self.gg_flag == 0.:
             self.a_gg_ic = np.zeros(len(nu_ic) - 2)
@@ -331,7 +351,7 @@ class LeptoHadronicRun:
             else:
                 self.Q_ee = Q_ee_f(nu_tot, photons, nu_tot, photons, g_el, Radius)[1:-1]
         V2 = 1. + dt * (c / Radius * np.ones(48))
-        self.N_nu[1:-1] = (self.N_nu[1:-1] + Q_pg_nu) / V2
+        self.N_nu[1:-1] = (self.N_nu[1:-1] + Q_pp_nu + Q_pg_nu) / V2
         self.interv += 1
         self.n_e, self.n_p = n_e, n_p
 

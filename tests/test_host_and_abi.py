@@ -81,7 +81,7 @@ def test_library_exports_every_declared_symbol():
     n_int_fields = len(re.search(r"typedef struct \{(.*?)\} lhm_config;", header, re.S).group(1)
                        .replace("\n", " ").split(";")) - 1
     assert ctypes.sizeof(_lib.lhm_config) == 4 * len(_lib.lhm_config._fields_)
-    assert len(_lib.lhm_config._fields_) == 29 and n_int_fields >= 8
+    assert len(_lib.lhm_config._fields_) == 33 and n_int_fields >= 8
 
 
 def test_no_cpu_fallback_without_gpu():

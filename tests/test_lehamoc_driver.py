@@ -16,8 +16,9 @@ def log_close(got, ref_log, what, tol=4.3e-9, floor_decades=200., tol_floor=1e-6
     ref_log = np.asarray(ref_log, dtype=np.float64)
     assert lg.shape == ref_log.shape, what
     # exact zeros must be zeros -- except at the bottom of the double range, where products of 1e-260 sentinels
-    # underflow: there (below 1e-290) "zero" and "denormal junk" are the same statement
-    tiny = -290.0
+    # underflow: there (below 1e-280, i.e. a 1e-260 sentinel times a further small factor, against physical values
+    # above 1e-100) "zero" and "denormal junk" are the same statement
+    tiny = -280.0
     ninf = np.isneginf(ref_log)
     assert np.all(lg[ninf] < tiny), f"{what}: zeros of the reference are not (near-)zeros here"
     assert np.all(ref_log[np.isneginf(lg)] < tiny), f"{what}: zeros where the reference has values"
@@ -73,7 +74,12 @@ def test_pack_lehamoc_matches_oracle_setup():
         np.testing.assert_allclose(b.ext[0], ext_ref, rtol=1e-14, atol=0)
     _, P = load_golden("lh_shipped")
     with pytest.raises(NotImplementedError):
-        pack_lehamoc(dict(P, pp_l_flag=1.))
+        pack_lehamoc(dict(P, User_ph=1.))
+    b = pack_lehamoc([dict(P, pp_l_flag=1., n_H=3.), dict(P, pp_l_flag=1., n_H=5., p_pr=2.5)])
+    from lehamoc_b200 import _lib
+    assert b.cfg["pp_l_flag"] == 1 and b.cfg["pp_g_emis_flag"] == 0
+    np.testing.assert_array_equal(b.consts[:, _lib.C_NH], [3., 5.])
+    np.testing.assert_array_equal(b.consts[:, _lib.C_PPR], [float(P["p_pr"]), 2.5])
 
 
 @pytest.mark.gpu
@@ -179,3 +185,34 @@ def test_gpu_test4_small():
     log_close(sed[0], z["nuLnu"], "test4small nuLnu")
     log_close(Npr[0], z["n_p"], "test4small n_p")
     log_close(Nnu[0, 1:], z["N_nu"][1:], "test4small N_nu")
+
+
+@pytest.mark.parametrize("name", ["lh_pp", "lh_pp_pg"])
+def test_oracle_with_pp_channels(name):
+    """pp loss term + pp pairs / pi0 photons / neutrinos (alone, and together with the photopion channels): pins the
+    wiring of the pp restatement into the driver against the unmodified script."""
+    z, P = load_golden(name)
+    run = olh.LeptoHadronicRun(P, tables=tables())
+    ne, sed, n_p, N_nu = run.run()
+    log_close(ne, z["n_e"], f"{name} n_e", tol=1e-10)
+    log_close(sed, z["nuLnu"], f"{name} nuLnu", tol=1e-10)
+    log_close(n_p, z["n_p"], f"{name} n_p", tol=1e-10)
+    log_close(N_nu, z["N_nu"], f"{name} N_nu", tol=1e-10)
+    assert np.any(N_nu[-1] > 0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["lh_pp", "lh_pp_pg"])
+def test_gpu_lehamoc_pp_run(name):
+    """pp channels inside the fused timestep, every step against the unmodified script."""
+    from lehamoc_b200 import LeHaMoC, hadronic
+    T = tables()
+    hadronic.set_tables({"phi_g": T["Phi_g"], "phi_el": T["Phi_el"], "phi_el1": T["Phi_el_1"], "fk": T["f_k_i"],
+                         "cs": T["cross_section"], "kp": T["kp_pg"]})
+    z, P = load_golden(name)
+    batch, N, sed, Npr, Nnu = LeHaMoC.run(P)
+    log_close(N[0], z["n_e"], f"{name} n_e")
+    log_close(sed[0], z["nuLnu"], f"{name} nuLnu")
+    log_close(Npr[0], z["n_p"], f"{name} n_p")
+    log_close(Nnu[0], z["N_nu"], f"{name} N_nu")
+    assert np.any(Nnu[0, -1] > 0)
