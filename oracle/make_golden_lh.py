@@ -53,6 +53,13 @@ VARIANTS = {
     "lh_pp_pg": variant(grid_g_el=40., grid_g_pr=30., g_max_pr=8., g_pr_PL_max=7., p_pr=2., L_pr=46.5, grid_nu=60.,
                         time_end=3., n_H=1e8, PL_inj=0., pp_l_flag=1., pp_ee_emis_flag=1., pp_g_emis_flag=1.,
                         pp_nu_emis_flag=1., pg_pi_l_flag=1., pg_pi_emis_flag=1., neutrino_flag=1., B0=10.),
+    # BASELINE config 3 in full: every hadronic channel at once (photopion, Bethe-Heitler AND pp, losses + emission +
+    # neutrinos) with adiabatic expansion, on reduced grids
+    "lh_all": variant(time_end=6., step_alg=2., PL_inj=0., g_max_el=11., g_el_PL_max=5.5, grid_g_el=44.,
+                      g_max_pr=8., g_pr_PL_max=6.93, grid_g_pr=32., grid_nu=60., p_el=2.01, L_el=40.6, p_pr=2.01,
+                      L_pr=46.46, R0=16., B0=0.1, Ad_l_flag=1., pg_pi_l_flag=1., pg_pi_emis_flag=1.,
+                      pg_BH_l_flag=1., pg_BH_emis_flag=1., neutrino_flag=1., n_H=1e5, pp_l_flag=1.,
+                      pp_ee_emis_flag=1., pp_g_emis_flag=1., pp_nu_emis_flag=1.),
 }
 
 

@@ -155,10 +155,12 @@ def bh_surf_from_gold():
     return tck("m"), tck("p"), float(g["bh_max_m"]), float(g["bh_max_p"]), g["bh_nu_range"]
 
 
-def test_oracle_test4_small():
+@pytest.mark.parametrize("name", ["lh_test4small", "lh_all"])
+def test_oracle_test4_small(name):
     """lh_test4small: the flags of the reference's Test 4 (BASELINE config 3: photopion + Bethe-Heitler losses and
-    emissivities, neutrinos, exponential cut-off injection, adiabatic losses) on reduced grids."""
-    z, P = load_golden("lh_test4small")
+    emissivities, neutrinos, exponential cut-off injection, adiabatic losses) on reduced grids; lh_all: the same with
+    the pp loss term and the three pp emissivities on top (every hadronic channel at once)."""
+    z, P = load_golden(name)
     run = olh.LeptoHadronicRun(P, tables=tables())
     tm, tp, mm, mp_, rng = bh_surf_from_gold()
     assert run.nu_tot[0] == rng[0] and run.nu_tot[-1] == rng[1]      # the stored surfaces belong to this nu_tot range
@@ -171,15 +173,17 @@ def test_oracle_test4_small():
 
 
 @pytest.mark.gpu
-def test_gpu_test4_small():
-    """BASELINE config 3 on reduced grids: the whole leptohadronic timestep on the GPU (host: spline-surface set-up)."""
+@pytest.mark.parametrize("name", ["lh_test4small", "lh_all"])
+def test_gpu_test4_small(name):
+    """BASELINE config 3 on reduced grids: the whole leptohadronic timestep on the GPU (host: spline-surface set-up);
+    lh_all adds the pp channels."""
     from lehamoc_b200 import LeHaMoC, hadronic
     T = tables()
     hadronic.set_tables({"phi_g": T["Phi_g"], "phi_el": T["Phi_el"], "phi_el1": T["Phi_el_1"], "fk": T["f_k_i"],
                          "cs": T["cross_section"], "kp": T["kp_pg"]})
     tm, tp, mm, mp_, rng = bh_surf_from_gold()
     LeHaMoC._bh_cache[(float(rng[0]), float(rng[1]))] = (tm, tp, mm, mp_)      # skip the 7 s host fit (tested on CPU)
-    z, P = load_golden("lh_test4small")
+    z, P = load_golden(name)
     batch, N, sed, Npr, Nnu = LeHaMoC.run(P)
     log_close(N[0], z["n_e"], "test4small n_e")
     log_close(sed[0], z["nuLnu"], "test4small nuLnu")
