@@ -227,6 +227,35 @@ int lhm_bh_emis_batch(int W, int Ng, int Np, int Nt, const double* g_el, const d
                       const double* x_target, const double* photons, const lhm_bh_surface* surf_m,
                       const lhm_bh_surface* surf_p, double* out, void* cuda_stream);
 
+/* Set-up of the leptonic drivers on the device: what LeMoC.py:107-191 / Code.py:51-180 build with NumPy per model --
+ * g_el, nu_syn (+ appended point), el_inj, the per-walker scalar block -- from one row of parameters per walker.
+ * Same expressions in the same order; 10**y, log10 and g**-p come from the CUDA math library, so g_el agrees with the
+ * NumPy grid to <= 2 ulp and nu_syn / el_inj to ~1e-14 relative (one ulp of a log10 that ends up in an exponent); the
+ * host packer in lehamoc_b200/setup_host.py stays the bit-for-bit statement of the reference.
+ * The outputs are the seven arrays lhm_setup_batch takes (device pointers, [W, n] row-major). */
+enum {
+    LHM_PK_R0 = 0,          /* cm (10**R0 evaluated by the host like the reference, LeMoC.py:79 / Code.py:53) */
+    LHM_PK_B0,              /* G */
+    LHM_PK_GMIN, LHM_PK_GMAX,       /* log10 limits of the gamma grid                       LeMoC.py:115 / Code.py:77 */
+    LHM_PK_GPLMIN, LHM_PK_GPLMAX,   /* log10 limits of the injection power law              LeMoC.py:120-128 */
+    LHM_PK_P,               /* p_el */
+    LHM_PK_COMP_INJ,        /* compactness used for the injection                           LeMoC.py:110,174 / Code.py:163 */
+    LHM_PK_COMP_COR,        /* value handed to cor_factor_syn_el (Code.py:237 passes the log)                  */
+    LHM_PK_THRMIN, LHM_PK_THRMAX,   /* 10**g_PL_min, 10**g_PL_max (host pow, like the reference's scalars)      */
+    LHM_PACK_NPAR = 12
+};
+typedef struct lhm_pack_args {
+    int W, Ng, Nh, Nt;      /* Nh = int(grid_g_el/2): len(nu_ic); len(nu_syn) = Nh + 1 */
+    int variant;            /* 0: LeMoC.py (nsteps = int(time_end)), 1: Code.py (while time_real < time_end R0/c) */
+    double time_init, time_end, step_alg, Vexp_cm_s, m;
+    double c, c3, m_el, mc2, sigmaT, four_pi, nuc_pref;   /* c, c**3., m_el, m_el*c**2., sigmaT, 4.*pi, 3./(4.*pi)*q as
+                                                             Python evaluates them */
+    const double* walker_params;                          /* device [W, LHM_PACK_NPAR] */
+    const double *nu_ic_row, *nu_tot_row, *ext_row;       /* device [Nh], [Nt], [Nt]: the same for every walker    */
+    double *consts, *g_el, *nu_syn, *nu_ic, *nu_tot, *el_inj, *ext;   /* device outputs */
+} lhm_pack_args;
+int lhm_pack_batch(const lhm_pack_args* args, void* cuda_stream);
+
 /* A14 pp channels (LeHaMoC_f.py:860-1014): product 0 Q_e_pp (grid = g_el), 1 Q_g_pp (grid = nu_ic), 2 Q_nu_mu_pp,
  * 3 Q_nu_e_pp (grid = nu_nu = E_nu/h).  grid [W,Nout]; g_pr, N_pr_TeV [W,Np] (dN_pr/dV dgamma divided by
  * m_p c^2 * 0.624151, LeHaMoC.py:355); p_pr, n_H [W]; out [W,Nout]. */

@@ -30,6 +30,18 @@ class lhm_config(C.Structure):
         "max_walkers")]
 
 
+LHM_PACK_NPAR = 12
+(PK_R0, PK_B0, PK_GMIN, PK_GMAX, PK_GPLMIN, PK_GPLMAX, PK_P, PK_COMP_INJ, PK_COMP_COR, PK_THRMIN, PK_THRMAX) = range(11)
+
+
+class lhm_pack_args(C.Structure):                    # include/lhm.h: lhm_pack_args
+    _fields_ = ([(n, C.c_int) for n in ("W", "Ng", "Nh", "Nt", "variant")]
+                + [(n, C.c_double) for n in ("time_init", "time_end", "step_alg", "Vexp_cm_s", "m", "c", "c3", "m_el",
+                                             "mc2", "sigmaT", "four_pi", "nuc_pref")]
+                + [(n, C.c_void_p) for n in ("walker_params", "nu_ic_row", "nu_tot_row", "ext_row", "consts", "g_el",
+                                             "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext")])
+
+
 # every symbol include/lhm.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -61,6 +73,7 @@ SIGNATURES = {
     "lhm_had_loss_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P]),
     "lhm_photopion_batch": (C.c_int, [C.c_int] * 7 + [_P] * 9 + [_P]),
     "lhm_bh_emis_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P, _P, _P, _P]),
+    "lhm_pack_batch": (C.c_int, [_P, _P]),
     "lhm_pp_batch": (C.c_int, [C.c_int] * 4 + [_P] * 6 + [_P]),
     "lhm_fp64_peak_probe": (C.c_int, [C.c_int, _P, C.POINTER(C.c_double)]),
 }

@@ -15,6 +15,7 @@
 #include "lhm_lh.cuh"
 #include "lhm_cor.cuh"
 #include "lhm_had.cuh"
+#include "lhm_pack.cuh"
 
 namespace lhm {
 
@@ -974,6 +975,24 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
     if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
     CUDA_TRY(cudaFuncSetAttribute(had_pion_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     had_pion_kernel<<<W, HAD_NT, smem, (cudaStream_t)stream>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_pack_batch(const lhm_pack_args* a, void* stream) {
+    if (!a || a->W < 1 || a->Ng < 4 || a->Nh < 3 || a->Nt < 4 || a->variant < 0 || a->variant > 1) return LHM_ERR_ARG;
+    if (!a->walker_params || !a->nu_ic_row || !a->nu_tot_row || !a->ext_row || !a->consts || !a->g_el || !a->nu_syn
+        || !a->nu_ic || !a->nu_tot || !a->el_inj || !a->ext) return LHM_ERR_ARG;
+    PackArgs A;
+    A.W = a->W; A.Ng = a->Ng; A.Nh = a->Nh; A.Nt = a->Nt; A.variant = a->variant;
+    A.time_init = a->time_init; A.time_end = a->time_end; A.step_alg = a->step_alg; A.Vexp = a->Vexp_cm_s; A.m = a->m;
+    A.c = a->c; A.c3 = a->c3; A.m_el = a->m_el; A.mc2 = a->mc2; A.sigmaT = a->sigmaT; A.four_pi = a->four_pi;
+    A.nuc_pref = a->nuc_pref;
+    A.wp = a->walker_params; A.nu_ic_row = a->nu_ic_row; A.nu_tot_row = a->nu_tot_row; A.ext_row = a->ext_row;
+    A.consts = a->consts; A.g_el = a->g_el; A.nu_syn = a->nu_syn; A.nu_ic = a->nu_ic; A.nu_tot = a->nu_tot;
+    A.el_inj = a->el_inj; A.ext = a->ext;
+    pack_kernel<<<a->W, PACK_NT, 0, (cudaStream_t)stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     return LHM_OK;

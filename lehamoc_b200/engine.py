@@ -115,6 +115,54 @@ class Engine:
         check(self.lib.lhm_setup_batch(self.h, int(W), *[_ptr(t) for t in self._keep]), "lhm_setup_batch")
         self.W = int(W)
 
+    def setup_packed(self, req):
+        """Set-up on the device from a setup_host.PackRequest: one small H2D copy (a row of scalars per walker and the
+        three shared grids), lhm_pack_batch builds the [W, n] arrays in device buffers this engine owns, then the tables
+        (lhm_setup_batch).  The arrays stay available as self._keep (device tensors, order of Batch.arrays())."""
+        from .constants import c, m_el, sigmaT, q
+        cfg = req.cfg
+        for k in ("Ng", "Ns", "Ni", "Nt"):
+            if cfg[k] != self.cfg[k]:
+                raise LhmError(f"batch {k}={cfg[k]} does not match the engine ({self.cfg[k]})")
+        if bool(self.cfg.get("shared_ic_grids")) and not cfg["shared_ic_grids"]:
+            raise LhmError("this engine was created for batches whose walkers share g_el/nu_ic/nu_tot "
+                           "(cfg.shared_ic_grids); the batch does not")
+        W, Ng, Nh, Nt = req.W, cfg["Ng"], cfg["Ni"], cfg["Nt"]
+        if W > self.max_walkers:
+            raise LhmError(f"batch of {W} walkers exceeds the engine capacity {self.max_walkers}")
+        # one pinned staging buffer -> one H2D copy
+        n_in = W * _lib.LHM_PACK_NPAR + Nh + 2 * Nt
+        sv = self._pinned("pack_in", (self.max_walkers * _lib.LHM_PACK_NPAR + Nh + 2 * Nt,))
+        stage = self._pin["pack_in"]
+        if getattr(self, "_pack_ev", None) is not None:
+            self._pack_ev.synchronize()              # the previous copy out of the staging buffer has completed
+        o = W * _lib.LHM_PACK_NPAR
+        sv[:o] = req.walker_params.ravel()
+        sv[o:o + Nh] = req.nu_ic_row
+        sv[o + Nh:o + Nh + Nt] = req.nu_tot_row
+        sv[o + Nh + Nt:n_in] = req.ext_row
+        if getattr(self, "_pack_dev", None) is None:
+            Wm = self.max_walkers
+            self._pack_dev = (self._new(len(sv)), self._new(Wm, _lib.LHM_NCONST), self._new(Wm, Ng),
+                              self._new(Wm, Nh + 1), self._new(Wm, Nh), self._new(Wm, Nt), self._new(Wm, Ng),
+                              self._new(Wm, Nt))
+        din, consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext = self._pack_dev
+        with torch.cuda.stream(self.stream):
+            din[:n_in].copy_(stage[:n_in], non_blocking=True)
+            self._pack_ev = torch.cuda.Event()
+            self._pack_ev.record(self.stream)
+        base = din.data_ptr()
+        a = _lib.lhm_pack_args(W=W, Ng=Ng, Nh=Nh, Nt=Nt, variant=0 if req.variant == "script" else 1,
+                               c=c, c3=c ** 3., m_el=m_el, mc2=m_el * c ** 2., sigmaT=sigmaT, four_pi=4. * np.pi,
+                               nuc_pref=3. / (4. * np.pi) * q, **req.scalars)
+        a.walker_params = base
+        a.nu_ic_row, a.nu_tot_row, a.ext_row = base + 8 * o, base + 8 * (o + Nh), base + 8 * (o + Nh + Nt)
+        outs = (consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext)
+        for name, t in zip(("consts", "g_el", "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext"), outs):
+            setattr(a, name, t.data_ptr())
+        check(self.lib.lhm_pack_batch(C.byref(a), C.c_void_p(self.stream.cuda_stream)), "lhm_pack_batch")
+        self.setup_device(W, *[t[:W] for t in outs])
+
     # -- the whole time integration ---------------------------------------------------------------
     def run(self, snapshots: int = 0, want_N: bool = True, want_sed: bool = True):
         S = snapshots if snapshots > 0 else 1

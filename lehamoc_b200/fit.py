@@ -32,7 +32,7 @@ from . import _lib, shard
 from ._lib import check
 from .constants import eV, pc
 from .engine import Engine, _ptr, _require_cuda
-from .setup_host import pack_code, pack_code_lehamoc, read_parameter_file
+from .setup_host import pack_code, pack_code_lehamoc, pack_code_request, read_parameter_file
 
 # fit_emcee.py:31-32
 D_DEFAULT = 3262    # luminosity distance (Mpc)
@@ -93,10 +93,11 @@ class FitEvaluator:
     """Owns the engine, the frozen parameter file and the device copy of the observed SED."""
 
     def __init__(self, x, y, yerr, yerr1, flags, param_file="Parameters.txt", D=D_DEFAULT, z=Z_DEFAULT,
-                 ic_path="R", device=None, flag_c="LeMoC"):
+                 ic_path="R", device=None, flag_c="LeMoC", device_pack=True):
         if flag_c not in ("LeMoC", "LeHaMoC"):
             raise ValueError("flag_c must be 'LeMoC' or 'LeHaMoC' (fit_emcee.py:23)")
         self.flag_c = flag_c
+        self.device_pack = bool(device_pack)    # False: NumPy set-up on the host (bit-identical grids, 2-3x slower)
         self.nfree = 6 if flag_c == "LeMoC" else 10                 # free parameters of the numerical model
         _require_cuda()
         self.lib = _lib.load()
@@ -131,11 +132,16 @@ class FitEvaluator:
         None).  No prior here (the reference evaluates the likelihood whatever the prior says, fit_emcee.py:192-193)."""
         thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
         W, nf = thetas.shape[0], self.nfree
-        if self.flag_c == "LeMoC":
+        if self.flag_c == "LeMoC" and self.device_pack:
+            req = pack_code_request(thetas[:, :nf], self.frozen)     # grids and injection are built on the device
+            eng = self._engine(req)
+            eng.setup_packed(req)
+            _, sed = eng.run(want_N=False)                           # [W, Nt] on the device
+        elif self.flag_c == "LeMoC":
             batch = pack_code(thetas[:, :nf], self.frozen)
             eng = self._engine(batch)
             eng.setup(batch)
-            _, sed = eng.run(want_N=False)                           # [W, Nt] on the device
+            _, sed = eng.run(want_N=False)
         else:
             batch = pack_code_lehamoc(thetas[:, :nf], self.frozen)
             eng = self._engine(batch)

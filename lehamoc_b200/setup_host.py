@@ -120,6 +120,62 @@ def external_fields(F: dict, nu_tot: np.ndarray) -> np.ndarray:
     return bb + pl
 
 
+def _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp, shared):
+    cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=50,
+               loss_minus_one=1 if variant == "script" else 0,       # LeMoC.py:224 vs Code.py:210
+               qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
+               const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
+               ic_pair_table=1, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0,
+               neutrino_flag=0, pg_BH_emis_flag=0, shared_ic_grids=int(shared))
+    for k in FLAG_KEYS:
+        cfg[k] = _flag01(F, k)
+    # gg_flag is tested with `== 0.` (LeMoC.py:279): anything else switches it on; inj_flag is tested both ways
+    return cfg
+
+
+@dataclass
+class PackRequest:
+    """What the device-side packer (lhm_pack_batch) needs instead of the seven [W, n] arrays of a Batch: one row of
+    scalars per walker and the three grids every walker shares."""
+    variant: str
+    cfg: dict
+    walker_params: np.ndarray      # [W, LHM_PACK_NPAR]
+    nu_ic_row: np.ndarray          # [Nh]
+    nu_tot_row: np.ndarray         # [Nt]
+    ext_row: np.ndarray            # [Nt]
+    scalars: dict                  # time_init, time_end, step_alg, Vexp_cm_s, m
+
+    @property
+    def W(self):
+        return self.walker_params.shape[0]
+
+
+def _pack_request(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> PackRequest:
+    """Host part of the device-side set-up: the scalars the reference evaluates with Python floats (10**x thresholds)
+    and the grids that do not depend on the walker (nu_ic, nu_tot, external photon fields), with the reference's NumPy
+    expressions; everything that is [W, n] is left to lhm_pack_batch."""
+    from . import _lib
+    W = len(R0)
+    Ng, Nh, Nt = int(float(F["grid_g_el"])), int(float(F["grid_g_el"]) / 2), int(float(F["grid_nu"]))
+    if np.any((g_PL_max != g_max_el) & ~(g_PL_max < g_max_el)) or np.any((g_PL_min != 0.) & ~(g_PL_min > g_min_el)):
+        raise ValueError("power-law window outside the gamma grid (the reference raises here too)")
+    wp = np.zeros((W, _lib.LHM_PACK_NPAR))
+    wp[:, _lib.PK_R0], wp[:, _lib.PK_B0] = R0, B0
+    wp[:, _lib.PK_GMIN], wp[:, _lib.PK_GMAX] = g_min_el, g_max_el
+    wp[:, _lib.PK_GPLMIN], wp[:, _lib.PK_GPLMAX] = g_PL_min, g_PL_max
+    wp[:, _lib.PK_P], wp[:, _lib.PK_COMP_INJ], wp[:, _lib.PK_COMP_COR] = p_el, comp_inj, comp_cor
+    wp[:, _lib.PK_THRMIN] = [10 ** x for x in np.asarray(g_PL_min).tolist()]
+    wp[:, _lib.PK_THRMAX] = [10 ** x for x in np.asarray(g_PL_max).tolist()]
+    nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
+    nu_tot = np.logspace(np.log10(np.logspace(7.5, 8.5, 2)[0]), np.log10(nu_ic[-1]), Nt)   # LeMoC.py:131,133
+    Vexp = float(F["Vexp"]) * c
+    cfg = _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp,
+                        shared=W > 1 and bool(np.all(g_min_el == g_min_el[0]) and np.all(g_max_el == g_max_el[0])))
+    scal = dict(time_init=float(F["time_init"]), time_end=float(F["time_end"]), step_alg=float(F["step_alg"]),
+                Vexp_cm_s=Vexp, m=float(F["m"]))
+    return PackRequest(variant, cfg, wp, nu_ic, nu_tot, external_fields(F, nu_tot), scal)
+
+
 def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> Batch:
     from ._lib import LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B
     W = len(R0)
@@ -210,17 +266,9 @@ def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp
     consts[:, C_COR_P] = p_el
     consts[:, C_COR_Q0] = cor_Q0
     consts[:, C_COR_B] = 10 ** 4.
-    cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=50,
-               loss_minus_one=1 if variant == "script" else 0,       # LeMoC.py:224 vs Code.py:210
-               qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
-               const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
-               ic_pair_table=1, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0,
-               neutrino_flag=0, pg_BH_emis_flag=0,
-               # fixed-grid sweeps (every walker has the same g_el / nu_ic / nu_tot): one IC pair table per batch
-               shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))))
-    for k in FLAG_KEYS:
-        cfg[k] = _flag01(F, k)
-    # gg_flag is tested with `== 0.` (LeMoC.py:279): anything else switches it on; inj_flag is tested both ways
+    # fixed-grid sweeps (every walker has the same g_el / nu_ic / nu_tot): one IC pair table per batch
+    cfg = _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp,
+                        shared=W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0])))
     cont = np.ascontiguousarray
     return Batch(variant, cfg, cont(consts), cont(g_el), cont(nu_syn), cont(nu_ic), cont(nu_tot), cont(el_inj),
                  cont(ext), nsteps, index_PL_min, index_PL_max)
@@ -398,6 +446,44 @@ def pack_code(thetas, frozen: dict) -> Batch:
     comp_cor = thetas[:, 4].copy()                                             # Code.py:237 passes the log value
     return _pack("code", frozen, R0, B0, g_PL_min - 1., g_PL_max + 1., g_PL_min, g_PL_max, thetas[:, 5].copy(),
                  comp_inj, comp_cor)
+
+
+def pack_code_request(thetas, frozen: dict) -> PackRequest:
+    """Device-packed twin of pack_code (same arguments)."""
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    missing = [k for k in CODE_KEYS if k not in frozen]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    R0 = np.array([10 ** x for x in thetas[:, 0].tolist()])
+    B0 = np.array([10 ** x for x in thetas[:, 1].tolist()])
+    g_PL_min, g_PL_max = thetas[:, 2].copy(), thetas[:, 3].copy()
+    comp_inj = np.array([10 ** x for x in thetas[:, 4].tolist()])
+    return _pack_request("code", frozen, R0, B0, g_PL_min - 1., g_PL_max + 1., g_PL_min, g_PL_max, thetas[:, 5].copy(),
+                         comp_inj, thetas[:, 4].copy())
+
+
+def pack_script_request(param_sets) -> PackRequest:
+    """Device-packed twin of pack_script (same arguments)."""
+    if isinstance(param_sets, dict):
+        param_sets = [param_sets]
+    F = param_sets[0]
+    missing = [k for k in SCRIPT_KEYS if k not in F]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    shared_keys = [k for k in SCRIPT_KEYS if k not in WALKER_KEYS]
+    get_shared, get_walker = itemgetter(*shared_keys), itemgetter(*WALKER_KEYS)
+    ref = tuple(float(v) for v in get_shared(F))
+    for P in param_sets[1:]:
+        if get_shared(P) != ref and tuple(float(v) for v in get_shared(P)) != ref:
+            bad = [k for k in shared_keys if float(P[k]) != float(F[k])]
+            raise ValueError(f"walkers of one batch must share '{bad[0]}'")
+    table = np.array([get_walker(P) for P in param_sets], dtype=np.float64)
+    col = lambda k: np.ascontiguousarray(table[:, WALKER_KEYS.index(k)])
+    R0 = np.array([10 ** x for x in col("R0").tolist()])
+    L_el = np.array([10 ** x for x in col("L_el").tolist()])
+    comp_el = sigmaT * L_el / (4. * np.pi * R0 * m_el * c ** 3)
+    return _pack_request("script", F, R0, col("B0"), col("g_min_el"), col("g_max_el"), col("g_PL_min"),
+                         col("g_PL_max"), col("p_el"), comp_el, comp_el)
 
 
 def pack_code_lehamoc(thetas, frozen: dict) -> Batch:

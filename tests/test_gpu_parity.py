@@ -350,3 +350,54 @@ def test_code_lehamoc_matches_reference():
         assert_spectra_close(sed[i], z["nuLnu"][i], f"Code.LeHaMoC walker {i}")
     nu1, sed1 = Code.LeHaMoC(list(z["thetas"][2]), P)
     np.testing.assert_array_equal(sed1, sed[2])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("variant", ["code", "script"])
+def test_gpu_device_packer_matches_host_packer(variant):
+    """lhm_pack_batch (grids, injection and scalar block built on the device) against setup_host._pack (NumPy, the
+    reference's expressions): identical window indices, sentinels and step counts, <= 2 ulp on g_el, 1e-13 relative on
+    what carries a rounded log10 in an exponent (nu_syn) or a g**-p, and the same spectra within the parity tolerance."""
+    import torch
+    from lehamoc_b200 import setup_host as sh
+    from lehamoc_b200.engine import Engine
+    if variant == "code":
+        cf, P = load_golden("code_fit")
+        thetas = np.array(cf["thetas"])
+        thetas = np.vstack([thetas, thetas[0] + [0.3, -0.2, 0.4, -0.3, 0.2, 0.]])       # p_el == 2 row included below
+        thetas[-1, 5] = 2.0
+        hb, req = sh.pack_code(thetas, P), sh.pack_code_request(thetas, P)
+    else:
+        from lehamoc_b200.presets import test1_walkers
+        sets = test1_walkers(12)
+        sets[3] = dict(sets[3], g_PL_min=1.5, g_PL_max=5.0, p_el=2.0)
+        hb, req = sh.pack_script(sets), sh.pack_script_request(sets)
+    assert {k: v for k, v in req.cfg.items()} == {k: hb.cfg[k] for k in req.cfg}
+    eng = Engine(req.cfg, req.W)
+    eng.setup_packed(req)
+    torch.cuda.synchronize()
+    dev = [t.cpu().numpy() for t in eng._keep]
+    names = ("consts", "g_el", "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext")
+    for name, d, h in zip(names, dev, hb.arrays()):
+        assert d.shape == h.shape, name
+        if name in ("nu_ic", "nu_tot", "ext"):
+            np.testing.assert_array_equal(d, h, err_msg=name)          # host rows, replicated
+            continue
+        sent = h == sh.SENTINEL
+        assert np.array_equal(d == sh.SENTINEL, sent), name + ": injection window differs"
+        nz = (h != 0) & ~sent
+        assert np.array_equal(d[~nz & ~sent], h[~nz & ~sent]), name
+        if name == "g_el":                                           # same exponents, 10**y from two math libraries
+            ulp = np.abs(d[nz] - h[nz]) / np.spacing(np.abs(h[nz]))
+            assert ulp.max() <= 2, (name, ulp.max())
+        else:       # nu_syn: its upper exponent carries one ulp of a log10 -> ln(10)*|y|*eps ~ 1e-14 relative
+            rel = np.abs(d[nz] / h[nz] - 1.0)
+            assert rel.max() <= 1e-13, (name, rel.max())
+    from lehamoc_b200 import _lib
+    np.testing.assert_array_equal(dev[0][:, _lib.C_NSTEPS], hb.consts[:, _lib.C_NSTEPS])
+    N1, sed1 = eng.run()
+    eng2 = Engine(hb.cfg, hb.W)
+    eng2.setup(hb)
+    N2, sed2 = eng2.run()
+    assert_spectra_close(sed1.cpu().numpy(), sed2.cpu().numpy(), "device-packed vs host-packed nuLnu")
+    assert_spectra_close(N1.cpu().numpy(), N2.cpu().numpy(), "device-packed vs host-packed n_e")

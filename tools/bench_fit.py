@@ -1,0 +1,62 @@
+"""BASELINE config 4: batched model evaluation of the Fit_emcee SSC fit (fit_emcee.py:190-245 with flag_c='LeMoC').
+
+One "evaluation" = log_probability(theta) of one walker: Code.LeMoC(theta[:6], Parameters.txt) evolved to steady state,
+observation transform, log-likelihood, prior.  The ensemble starts like the reference's (init + 1e-2 randn,
+fit_emcee.py:225) but with `--walkers` walkers (the reference: 48); an emcee iteration evaluates the two half-ensembles
+one after the other, so the unit timed here is ONE HALF-ENSEMBLE CALL through the public API
+(`lehamoc_b200.fit.FitEvaluator.log_probability`, host thetas in, host log-probabilities out).
+
+    python tools/bench_fit.py [--walkers 1024] [--reps 10] [--ic-path R]
+Observations and frozen parameters come from tests/golden (the reference's data files do not travel to the GPU box).
+"""
+import argparse
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+
+from lehamoc_b200 import fit  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--walkers", type=int, default=1024)
+    ap.add_argument("--reps", type=int, default=10)
+    ap.add_argument("--ic-path", default="R")
+    a = ap.parse_args()
+    g = np.load(os.path.join(ROOT, "tests", "golden", "fit_loglike.npz"))
+    cf = np.load(os.path.join(ROOT, "tests", "golden", "code_fit.npz"))
+    frozen = {str(k): float(v) for k, v in zip(cf["param_keys"], cf["param_vals"])}
+    ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
+                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path)
+    init = np.array([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2.])          # fit_emcee.py:207
+    rng = np.random.default_rng(1)
+    half = a.walkers // 2
+    calls = [init + 1e-2 * rng.standard_normal((half, len(init))) for _ in range(a.reps + 2)]
+    for th in calls[:2]:
+        lp = ev.log_probability(th)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    tm = {"pack": 0.0}
+    for th in calls[2:]:
+        lp = ev.log_probability(th)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / a.reps
+    # where the time goes: host packing alone, and the GPU kernels alone
+    t1 = time.perf_counter()
+    for th in calls[2:]:
+        b = fit.pack_code(th[:, :6], frozen)
+    pack = (time.perf_counter() - t1) / a.reps
+    su, co, ru = ev.eng.last_timings()
+    print(f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
+          f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
+          f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
+
+
+if __name__ == "__main__":
+    main()
