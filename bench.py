@@ -248,7 +248,7 @@ def main():
     from lehamoc_b200 import LeMoC, _lib
     from lehamoc_b200.engine import Engine, fp64_peak_tflops
     from lehamoc_b200.presets import test1_walkers
-    from lehamoc_b200.setup_host import pack_script
+    from lehamoc_b200.setup_host import pack_script, pack_script_request
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -333,13 +333,17 @@ def main():
     # ---- end-to-end through the public API (host parameter sets in, host spectra out), every step:
     #      host packing + pinned H2D + set-up + cor-factor + fused kernel + D2H
     # public API of the throughput path: LeMoC.run_many(stream of parameter-dict batches) -> host spectra per batch.
-    # Every batch is packed on the host (NumPy, worker thread), copied H2D from pinned memory, evolved, and its
-    # spectra copied D2H and touched on the host, all inside the timed region.
+    # Every batch: the host turns the parameter dicts into one row of scalars per walker (worker thread), copies them
+    # H2D from pinned memory, the device builds grids + injection (lhm_pack_batch) and tables, evolves the walkers, and
+    # the spectra are copied D2H into pinned memory and touched on the host -- all inside the timed region.
     e2e_engines = [None, None]                      # two engines, one per worker thread / CUDA stream
+    e2e_engines_h = [None, None]
 
-    def e2e_run(nb):
+    def e2e_run(nb, device_pack=True):
         tot = 0.0
-        for b2, N_h, sed_h in LeMoC.run_many((sets for _ in range(nb)), ic_path=args.ic_path, engines=e2e_engines):
+        for b2, N_h, sed_h in LeMoC.run_many((sets for _ in range(nb)), ic_path=args.ic_path,
+                                             engines=e2e_engines if device_pack else e2e_engines_h,
+                                             device_pack=device_pack):
             tot += float(sed_h[0, 0]) + float(N_h[-1, -1])
         return tot
     e2e_run(2)
@@ -348,6 +352,15 @@ def main():
     e2e_run(args.steps)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    # the same with the NumPy packer on the host (bit-identical set-up; 9.4 MB of H2D per batch instead of 0.1 MB)
+    e2e_run(2, False)
+    t0 = time.perf_counter()
+    e2e_run(args.steps, False)
+    torch.cuda.synchronize()
+    e2e_hostpack_s = time.perf_counter() - t0
+    for e in e2e_engines_h:
+        if e is not None:
+            e.close()
     # the same without overlap: one synchronous LeMoC.run per batch
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -365,7 +378,9 @@ def main():
     t0 = time.perf_counter()
     pack_script(sets)
     pack_s = time.perf_counter() - t0
-    h2d = int(sum(a.nbytes for a in batch.arrays()))
+    h2d_hostpack = int(sum(a.nbytes for a in batch.arrays()))
+    req = pack_script_request(sets)
+    h2d = int(req.walker_params.nbytes + req.nu_ic_row.nbytes + req.nu_tot_row.nbytes + req.ext_row.nbytes)
     d2h = int(W * (eng.Ng + eng.Nt) * 8)
 
     if rank != 0:
@@ -441,10 +456,13 @@ def main():
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * W * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
-                    "what": "LeMoC.run_many(stream of batches of parameter dicts) -> host spectra; every batch: NumPy "
-                            "packing + pinned H2D + set-up + cor-factor + fused kernel + D2H; two worker threads with "
-                            "their own engine and CUDA stream, so one batch's host work and copies overlap the other's "
-                            "kernels",
+                    "what": "LeMoC.run_many(stream of batches of parameter dicts) -> host spectra; every batch: parameter "
+                            "dicts -> one row of scalars per walker (host) + pinned H2D + device-side grid/injection "
+                            "set-up (lhm_pack_batch) + tables + cor-factor + fused kernel + D2H into pinned memory; "
+                            "two worker threads with their own engine and CUDA stream, so one batch's host work and "
+                            "copies overlap the other's kernels",
+                    "host_packed_value": world * W * args.steps / e2e_hostpack_s,
+                    "host_packed_h2d_bytes_per_step": h2d_hostpack,
                     "synchronous_value": world * W * args.steps / e2e_sync_s,
                     "c_abi_only_value": world * W * args.steps / abi_s, "host_packing_ms": 1e3 * pack_s},
             "parity_check_max_dlog10_walker0": parity}

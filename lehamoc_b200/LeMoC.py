@@ -13,7 +13,7 @@ import time
 import numpy as np
 
 from .engine import Engine
-from .setup_host import pack_script, read_parameter_file
+from .setup_host import pack_script, pack_script_request, read_parameter_file
 
 
 def run(param_sets, ic_path="R", snapshots=True, engine=None, pinned=False):
@@ -28,7 +28,7 @@ def run(param_sets, ic_path="R", snapshots=True, engine=None, pinned=False):
     return batch, N, sed
 
 
-def run_many(batches, ic_path="R", engines=None, depth=2):
+def run_many(batches, ic_path="R", engines=None, depth=2, device_pack=True):
     """Evolve a stream of walker batches (an iterable of lists of parameter dicts) and yield
     (batch, n_e [W,Ng], nuLnu [W,Nt]) per batch in order, final state only.
 
@@ -36,7 +36,12 @@ def run_many(batches, ic_path="R", engines=None, depth=2):
     stream and do packing (NumPy) -> pinned H2D -> set-up + cor-factor + fused kernel -> D2H for their batch, so the
     host work and the copies of one batch overlap the kernels of the other (NumPy and the ctypes call release the
     GIL).  The yielded spectra are views of that engine's page-locked buffers: they stay valid until `depth` more
-    batches have been drawn; copy them if they must live longer."""
+    batches have been drawn; copy them if they must live longer.
+
+    device_pack=True (default): the grids, the injection and the scalar block of every walker are built on the device
+    (lhm_pack_batch) from one row of scalars per walker; the yielded `batch` is then a setup_host.PackRequest (cfg,
+    walker_params, nu_tot / nu_ic / g_el axes).  False: NumPy packing on the host, bit-identical to the reference's
+    set-up, and a setup_host.Batch."""
     from concurrent.futures import ThreadPoolExecutor
     import torch
     depth = max(1, int(depth))
@@ -46,12 +51,15 @@ def run_many(batches, ic_path="R", engines=None, depth=2):
     streams = [torch.cuda.Stream() for _ in range(depth)]
 
     def work(slot, sets):
-        batch = pack_script(sets)
+        batch = pack_script_request(sets) if device_pack else pack_script(sets)
         with torch.cuda.stream(streams[slot]):
             eng = engines[slot]
             if eng is None or eng.max_walkers < batch.W or any(eng.cfg.get(k) != v for k, v in batch.cfg.items()):
                 eng = engines[slot] = Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
-            N, sed = eng.run_host(batch, snapshots=0, pinned=True)
+            if device_pack:
+                N, sed = eng.run_packed_host(batch)
+            else:
+                N, sed = eng.run_host(batch, snapshots=0, pinned=True)
         return batch, N, sed
 
     it = iter(batches)

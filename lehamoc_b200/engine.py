@@ -236,6 +236,22 @@ class Engine:
             return N_out.reshape(W, S, self.Ng)[:, 0], sed_out.reshape(W, S, self.Nt)[:, 0]
         return N_out, sed_out
 
+    def run_packed_host(self, req):
+        """Device-packed twin of run_host(pinned=True): PackRequest in, (n_e [W,Ng], nuLnu [W,Nt]) out as views of
+        page-locked host buffers; final state only.  H2D: one row of scalars per walker + three shared grids."""
+        self.setup_packed(req)
+        W = req.W
+        if getattr(self, "_out_dev", None) is None:
+            self._out_dev = (self._new(self.max_walkers, 1, self.Ng), self._new(self.max_walkers, 1, self.Nt))
+        Nd, sd = self._out_dev
+        self.run_into(Nd, sd, 0)
+        Nh_, sh_ = self._pinned("N", (W, self.Ng)), self._pinned("sed", (W, self.Nt))
+        with torch.cuda.stream(self.stream):
+            self._pin["N"][:W * self.Ng].copy_(Nd.view(-1)[:W * self.Ng], non_blocking=True)
+            self._pin["sed"][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
+        self.stream.synchronize()
+        return Nh_, sh_
+
     def last_timings(self):
         """(setup_ms, cor_ms, run_ms) of the most recent launches, measured with CUDA events on the stream."""
         a, b, c = C.c_float(), C.c_float(), C.c_float()

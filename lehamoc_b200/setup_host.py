@@ -149,6 +149,23 @@ class PackRequest:
     def W(self):
         return self.walker_params.shape[0]
 
+    # the axes a caller needs next to the spectra, as the host packer would have built them (NumPy)
+    @property
+    def nu_tot(self):
+        return np.broadcast_to(self.nu_tot_row, (self.W, len(self.nu_tot_row)))
+
+    @property
+    def nu_ic(self):
+        return np.broadcast_to(self.nu_ic_row, (self.W, len(self.nu_ic_row)))
+
+    @property
+    def g_el(self):
+        from . import _lib
+        lo, hi = self.walker_params[:, _lib.PK_GMIN], self.walker_params[:, _lib.PK_GMAX]
+        if np.all(lo == lo[0]) and np.all(hi == hi[0]):
+            return np.broadcast_to(np.logspace(lo[0], hi[0], self.cfg["Ng"]), (self.W, self.cfg["Ng"]))
+        return np.logspace(lo, hi, self.cfg["Ng"], axis=-1)
+
 
 def _pack_request(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> PackRequest:
     """Host part of the device-side set-up: the scalars the reference evaluates with Python floats (10**x thresholds)

@@ -325,18 +325,27 @@ def test_ic_pair_table_modes_are_bit_identical():
         eng.setup(ragged)
 
 
-def test_run_many_matches_run():
-    """The pipelined throughput API gives, batch by batch and in order, exactly what the synchronous call gives."""
+@pytest.mark.parametrize("device_pack", [False, True])
+def test_run_many_matches_run(device_pack):
+    """The pipelined throughput API gives, batch by batch and in order, what the synchronous call gives: exactly with
+    host packing, within the parity tolerance when the grids are built on the device."""
     from lehamoc_b200 import LeMoC
     _, P = load_golden("test1")
     P.update(grid_g_el=70., grid_nu=40., time_end=3.)
     batches = [[dict(P, B0=0.5 + 0.1 * (i + 3 * k), p_el=1.7 + 0.05 * i) for i in range(3 + k)] for k in range(5)]
     ref = [LeMoC.run(b, snapshots=False) for b in batches]
-    got = [(b.W, N.copy(), sed.copy()) for b, N, sed in LeMoC.run_many(iter(batches))]
+    got = [(b.W, N.copy(), sed.copy(), np.array(b.nu_tot), np.array(b.g_el))
+           for b, N, sed in LeMoC.run_many(iter(batches), device_pack=device_pack)]
     assert [g[0] for g in got] == [len(b) for b in batches]
-    for (_, N, sed), (_, Nr, sedr) in zip(got, ref):
-        np.testing.assert_array_equal(sed, sedr[:, 0])
-        np.testing.assert_array_equal(N, Nr[:, 0])
+    for (_, N, sed, nu, g), (br, Nr, sedr) in zip(got, ref):
+        np.testing.assert_array_equal(nu, br.nu_tot)
+        np.testing.assert_array_equal(g, br.g_el)
+        if device_pack:
+            assert_spectra_close(sed, sedr[:, 0], "run_many(device_pack) nuLnu")
+            assert_spectra_close(N, Nr[:, 0], "run_many(device_pack) n_e")
+        else:
+            np.testing.assert_array_equal(sed, sedr[:, 0])
+            np.testing.assert_array_equal(N, Nr[:, 0])
 
 
 def test_code_lehamoc_matches_reference():
