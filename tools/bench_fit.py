@@ -6,7 +6,8 @@ fit_emcee.py:225) but with `--walkers` walkers (the reference: 48); an emcee ite
 one after the other, so the unit timed here is ONE HALF-ENSEMBLE CALL through the public API
 (`lehamoc_b200.fit.FitEvaluator.log_probability`, host thetas in, host log-probabilities out).
 
-    python tools/bench_fit.py [--walkers 1024] [--reps 10] [--ic-path R]
+    python tools/bench_fit.py [--walkers 1024] [--reps 10] [--ic-path R] [--host-pack]
+    python -m torch.distributed.run --nproc-per-node N --master-addr 127.0.0.1 tools/bench_fit.py   # walkers sharded
 Observations and frozen parameters come from tests/golden (the reference's data files do not travel to the GPU box).
 """
 import argparse
@@ -28,34 +29,50 @@ def main():
     ap.add_argument("--walkers", type=int, default=1024)
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ic-path", default="R")
+    ap.add_argument("--host-pack", action="store_true", help="NumPy set-up on the host instead of lhm_pack_batch")
     a = ap.parse_args()
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        dist.init_process_group("nccl")
     g = np.load(os.path.join(ROOT, "tests", "golden", "fit_loglike.npz"))
     cf = np.load(os.path.join(ROOT, "tests", "golden", "code_fit.npz"))
     frozen = {str(k): float(v) for k, v in zip(cf["param_keys"], cf["param_vals"])}
     ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
-                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path)
+                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path, device_pack=not a.host_pack)
+    logp = ev.log_probability_sharded if world > 1 else ev.log_probability
     init = np.array([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2.])          # fit_emcee.py:207
     rng = np.random.default_rng(1)
     half = a.walkers // 2
     calls = [init + 1e-2 * rng.standard_normal((half, len(init))) for _ in range(a.reps + 2)]
     for th in calls[:2]:
-        lp = ev.log_probability(th)
+        lp = logp(th)
     torch.cuda.synchronize()
     t0 = time.perf_counter()
-    tm = {"pack": 0.0}
     for th in calls[2:]:
-        lp = ev.log_probability(th)
+        lp = logp(th)
     torch.cuda.synchronize()
     dt = (time.perf_counter() - t0) / a.reps
+    if world > 1:
+        tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        dt = float(tmax.item())
+        if rank != 0:
+            dist.destroy_process_group()
+            return
     # where the time goes: host packing alone, and the GPU kernels alone
     t1 = time.perf_counter()
     for th in calls[2:]:
         b = fit.pack_code(th[:, :6], frozen)
     pack = (time.perf_counter() - t1) / a.reps
     su, co, ru = ev.eng.last_timings()
-    print(f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
+    print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up: "
+          f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
           f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
           f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
+    if world > 1:
+        dist.destroy_process_group()
 
 
 if __name__ == "__main__":
