@@ -504,6 +504,20 @@ using namespace lhm;
 static thread_local std::string g_cuda_err;
 static std::atomic<long long> g_launches{0};
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a property of the FUNCTION, shared by every handle of the process: raise
+// it to the high-water mark before a launch instead of setting it per handle (a small-grid engine created after a
+// large-grid one must not shrink it)
+template <typename K>
+static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& mark) {
+    size_t cur = mark.load();
+    if (bytes <= cur) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e == cudaSuccess) { while (bytes > cur && !mark.compare_exchange_weak(cur, bytes)) {} }
+    return e;
+}
+constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
+static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV];
+
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
         cudaError_t _e = (expr);                                                       \
@@ -583,6 +597,46 @@ const char* lhm_strerror(int s) {
 const char* lhm_last_cuda_error(void) { return g_cuda_err.c_str(); }
 long long lhm_launch_count(void) { return g_launches.load(); }
 
+void lhm_destroy(lhm_handle* h);
+// everything of lhm_create that can fail after the handle exists; the caller destroys the handle on error
+static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* cuda_stream, const cudaDeviceProp& prop) {
+    h->cfg = *cfg;
+    h->device = device;
+    h->stream = (cudaStream_t)cuda_stream;
+    if (cfg->driver < 0 || cfg->driver > 2) return LHM_ERR_ARG;
+    if (cfg->driver >= 1 && cfg->Np < 4) return LHM_ERR_ARG;
+    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts, cfg->driver >= 1 ? cfg->Np : 0);
+    StepFlags& F = h->F;
+    F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
+    F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
+    F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
+    F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
+    F.bh_e = cfg->pg_BH_emis_flag;
+    F.pp_l = cfg->pp_l_flag; F.pp_ee = cfg->pp_ee_emis_flag; F.pp_g = cfg->pp_g_emis_flag; F.pp_nu = cfg->pp_nu_emis_flag;
+    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu || F.bh_e || F.pp_l || F.pp_ee || F.pp_g || F.pp_nu)) return LHM_ERR_ARG;
+    h->smem = smem_bytes(h->L, NW);
+    if (cfg->driver >= 1) {
+        h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
+        if (any_hadronic(F)) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
+    }
+    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) return LHM_ERR_CAPACITY;
+    PhysConst pc = make_consts();
+    CUDA_TRY(cudaMemcpyToSymbol(kPC, &pc, sizeof(pc)));
+    const size_t W = cfg->max_walkers;
+    CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
+    CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
+    CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
+    if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
+        CUDA_TRY(cudaMalloc(&h->d_E, W * (size_t)(cfg->Ns + cfg->Ni) * cfg->Ng * sizeof(double)));
+    if (cfg->ic_pair_table && cfg->IC_emis_flag) {
+        const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);
+        CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));
+    }
+    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    return LHM_OK;
+}
+
+
 int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle** out) {
     if (!cfg || !out) return LHM_ERR_ARG;
     if (cfg->Ng < 4 || cfg->Ns < 3 || cfg->Ni < 3 || cfg->Nt < 4 || cfg->gg_npts < 3 || cfg->max_walkers < 1) return LHM_ERR_ARG;
@@ -597,44 +651,8 @@ int lhm_create(const lhm_config* cfg, int device, void* cuda_stream, lhm_handle*
     lhm_handle* h = new (std::nothrow) lhm_handle();
     if (!h) return LHM_ERR_ARG;
     std::memset(h, 0, sizeof(*h));
-    h->cfg = *cfg;
-    h->device = device;
-    h->stream = (cudaStream_t)cuda_stream;
-    if (cfg->driver < 0 || cfg->driver > 2) return LHM_ERR_ARG;
-    if (cfg->driver >= 1 && cfg->Np < 4) return LHM_ERR_ARG;
-    h->L = make_layout(cfg->Ng, cfg->Ns, cfg->Ni, cfg->Nt, cfg->gg_npts, cfg->driver >= 1 ? cfg->Np : 0);
-    StepFlags& F = h->F;
-    F.inj = cfg->inj_flag; F.ad = cfg->Ad_l_flag; F.syn_l = cfg->Syn_l_flag; F.syn_e = cfg->Syn_emis_flag;
-    F.ic_l = cfg->IC_l_flag; F.ic_e = cfg->IC_emis_flag; F.ssa = cfg->SSA_l_flag; F.gg = cfg->gg_flag;
-    F.esc = cfg->esc_flag; F.qee_from_ic = cfg->qee_from_ic; F.ic_path = cfg->ic_path;
-    F.pg_l = cfg->pg_pi_l_flag; F.bh_l = cfg->pg_BH_l_flag; F.pg_e = cfg->pg_pi_emis_flag; F.nu = cfg->neutrino_flag;
-    F.bh_e = cfg->pg_BH_emis_flag;
-    F.pp_l = cfg->pp_l_flag; F.pp_ee = cfg->pp_ee_emis_flag; F.pp_g = cfg->pp_g_emis_flag; F.pp_nu = cfg->pp_nu_emis_flag;
-    if (cfg->driver != 1 && (F.pg_l || F.bh_l || F.pg_e || F.nu || F.bh_e || F.pp_l || F.pp_ee || F.pp_g || F.pp_nu)) { delete h; return LHM_ERR_ARG; }
-    h->smem = smem_bytes(h->L, NW);
-    if (cfg->driver >= 1) {
-        h->smem = (h->smem + 15) / 16 * 16 + smem_lh_doubles(h->L) * sizeof(double);
-        if (any_hadronic(F)) h->smem += smem_lh_had_doubles(h->L) * sizeof(double);
-    }
-    if (h->smem > (size_t)prop.sharedMemPerBlockOptin) { delete h; return LHM_ERR_CAPACITY; }
-    PhysConst pc = make_consts();
-    CUDA_TRY(cudaMemcpyToSymbol(kPC, &pc, sizeof(pc)));
-    CUDA_TRY(cudaFuncSetAttribute(run_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CUDA_TRY(cudaFuncSetAttribute(unit_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CUDA_TRY(cudaFuncSetAttribute(run_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CUDA_TRY(cudaFuncSetAttribute(run_code_lh_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
-    CUDA_TRY(cudaFuncSetAttribute(cor_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cor_smem_bytes(cfg->Ng)));
-    const size_t W = cfg->max_walkers;
-    CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
-    CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
-    CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
-    if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
-        CUDA_TRY(cudaMalloc(&h->d_E, W * (size_t)(cfg->Ns + cfg->Ni) * cfg->Ng * sizeof(double)));
-    if (cfg->ic_pair_table && cfg->IC_emis_flag) {
-        const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);
-        CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));
-    }
-    for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    const int rc = init_handle(h, cfg, device, cuda_stream, prop);
+    if (rc != LHM_OK) { lhm_destroy(h); return rc; }
     *out = h;
     return LHM_OK;
 }
@@ -685,6 +703,7 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
     CUDA_TRY(cudaSetDevice(h->device));
     CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
     CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
+    CUDA_TRY(ensure_dyn_smem(cor_kernel, cor_smem_bytes(h->cfg.Ng), g_smem_cor[h->device % MAX_DEV]));
     cor_kernel<<<(h->W + COR_WARPS - 1) / COR_WARPS, COR_WARPS * 32, cor_smem_bytes(h->cfg.Ng), h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -693,7 +712,8 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
     return LHM_OK;
 }
 
-static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots, bool lh);
+static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
+                      int snapshots, bool lh);
 static int had_init();
 static HadTables to_dev_tables(const lhm_had_tables* t);
 
@@ -734,7 +754,6 @@ int lhm_set_bh_surfaces(lhm_handle* h, const lhm_bh_surface* sm, const lhm_bh_su
     return LHM_OK;
 }
 
-static double* g_nnu_out = nullptr;     // per-call output slot of lhm_run_batch_lh (single-threaded per handle)
 
 int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
@@ -742,19 +761,17 @@ int lhm_run_batch_lh(lhm_handle* h, double* N_el_out, double* nuLnu_out, double*
     if ((h->F.pg_l || h->F.bh_l || h->F.pg_e) && !h->have_HT) return LHM_ERR_STATE;
     if (h->F.bh_e && !h->have_BS) return LHM_ERR_STATE;
     if (any_hadronic(h->F)) { int rc0 = had_init(); if (rc0 != LHM_OK) return rc0; }
-    g_nnu_out = N_nu_out;
-    int rc = run_common(h, N_el_out, nuLnu_out, N_pr_out, snapshots, true);
-    g_nnu_out = nullptr;
-    return rc;
+    return run_common(h, N_el_out, nuLnu_out, N_pr_out, N_nu_out, snapshots, true);
 }
 
 int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapshots) {
     if (!h || snapshots < 0) return LHM_ERR_ARG;
     if (h->cfg.driver != 0) return LHM_ERR_STATE;
-    return run_common(h, N_el_out, nuLnu_out, nullptr, snapshots, false);
+    return run_common(h, N_el_out, nuLnu_out, nullptr, nullptr, snapshots, false);
 }
 
-static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, int snapshots, bool lh) {
+static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
+                      int snapshots, bool lh) {
     if (h->W < 1) return LHM_ERR_STATE;
     CUDA_TRY(cudaSetDevice(h->device));
     const double* cor = nullptr;
@@ -767,7 +784,7 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.L = h->L; A.F = h->F; A.W = h->W; A.snapshots = snapshots; A.consts = h->consts;
     A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.cor = cor; A.N_out = N_el_out; A.sed_out = nuLnu_out;
     A.Np_out = N_pr_out; A.esc_pr = h->cfg.esc_flag_pr;
-    A.Nnu_out = lh ? g_nnu_out : nullptr;
+    A.Nnu_out = lh ? N_nu_out : nullptr;
     A.had = lh && any_hadronic(h->F);
     if (A.had && h->have_HT) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
     std::memset(&A.BSm, 0, sizeof(A.BSm)); std::memset(&A.BSp, 0, sizeof(A.BSp));
@@ -776,9 +793,16 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-    if (lh && h->cfg.driver == 2) run_code_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
-    else if (lh) run_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
-    else run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    if (lh && h->cfg.driver == 2) {
+        CUDA_TRY(ensure_dyn_smem(run_code_lh_kernel, h->smem, g_smem_codelh[h->device % MAX_DEV]));
+        run_code_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    } else if (lh) {
+        CUDA_TRY(ensure_dyn_smem(run_lh_kernel, h->smem, g_smem_lh[h->device % MAX_DEV]));
+        run_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    } else {
+        CUDA_TRY(ensure_dyn_smem(run_kernel, h->smem, g_smem_run[h->device % MAX_DEV]));
+        run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+    }
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
@@ -862,6 +886,7 @@ static int launch_unit(lhm_handle* h, int mode, const double* in0, const double*
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     if (ic_path >= 0) A.F.ic_path = ic_path;
     A.in0 = in0; A.in1 = in1; A.in2 = in2; A.out0 = out0; A.out1 = out1; A.out2 = out2; A.mode = mode;
+    CUDA_TRY(ensure_dyn_smem(unit_kernel, h->smem, g_smem_unit[h->device % MAX_DEV]));
     unit_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());

@@ -410,3 +410,25 @@ def test_gpu_device_packer_matches_host_packer(variant):
     N2, sed2 = eng2.run()
     assert_spectra_close(sed1.cpu().numpy(), sed2.cpu().numpy(), "device-packed vs host-packed nuLnu")
     assert_spectra_close(N1.cpu().numpy(), N2.cpu().numpy(), "device-packed vs host-packed n_e")
+
+
+@pytest.mark.gpu
+def test_engines_of_different_size_coexist():
+    """The dynamic shared-memory opt-in is a property of the kernel, not of a handle: an engine for small grids created
+    after one for large grids must not make the large one's launches fail."""
+    from lehamoc_b200 import LeMoC
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    _, P = load_golden("test1")
+    big = pack_script(dict(P, grid_g_el=400., grid_nu=200., time_end=2.))
+    small = pack_script(dict(P, grid_g_el=60., grid_nu=40., time_end=2.))
+    e_big = Engine(big.cfg, 1)
+    e_small = Engine(small.cfg, 1)
+    assert e_big.smem_bytes() > e_small.smem_bytes()
+    e_small.setup(small)
+    Ns, _ = e_small.run()
+    e_big.setup(big)
+    Nb, sedb = e_big.run()
+    _, Nb2, sedb2 = LeMoC.run(dict(P, grid_g_el=400., grid_nu=200., time_end=2.), snapshots=False)
+    np.testing.assert_array_equal(sedb.cpu().numpy(), sedb2[:, 0])
+    assert np.isfinite(Ns.cpu().numpy()[:, 1:-1]).all()
