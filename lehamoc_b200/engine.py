@@ -82,7 +82,10 @@ class Engine:
     def _dev(self, a):
         if isinstance(a, torch.Tensor):
             return a.to(device=f"cuda:{self.device}", dtype=torch.float64).contiguous()
-        return torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(f"cuda:{self.device}", non_blocking=True)
+        a = np.ascontiguousarray(a, dtype=np.float64)
+        if not a.flags.writeable:                  # broadcast views of shared grids: torch wants a writable buffer
+            a = a.copy()
+        return torch.from_numpy(a).to(f"cuda:{self.device}", non_blocking=True)
 
     def _new(self, *shape):
         return torch.empty(shape, dtype=torch.float64, device=f"cuda:{self.device}")
