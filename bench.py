@@ -346,16 +346,19 @@ def main():
                                              device_pack=device_pack):
             tot += float(sed_h[0, 0]) + float(N_h[-1, -1])
         return tot
+    # a stream of batches has a fill and a drain of about one batch each: time enough batches for the steady state to
+    # dominate (30 at the default 10 steps; every one of them is a full step with its own H2D and D2H)
+    e2e_nb = max(3 * args.steps, 12)
     e2e_run(2)
     barrier()
     t0 = time.perf_counter()
-    e2e_run(args.steps)
+    e2e_run(e2e_nb)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     # the same with the NumPy packer on the host (bit-identical set-up; 9.4 MB of H2D per batch instead of 0.1 MB)
     e2e_run(2, False)
     t0 = time.perf_counter()
-    e2e_run(args.steps, False)
+    e2e_run(e2e_nb, False)
     torch.cuda.synchronize()
     e2e_hostpack_s = time.perf_counter() - t0
     for e in e2e_engines_h:
@@ -454,14 +457,14 @@ def main():
             "us_per_walker_timestep": total_ms * 1e3 / (args.steps * W * nts),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
-            "e2e": {"value": world * W * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+            "e2e": {"value": world * W * e2e_nb / e2e_s, "batches_timed": e2e_nb, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
                     "what": "LeMoC.run_many(stream of batches of parameter dicts) -> host spectra; every batch: parameter "
                             "dicts -> one row of scalars per walker (host) + pinned H2D + device-side grid/injection "
                             "set-up (lhm_pack_batch) + tables + cor-factor + fused kernel + D2H into pinned memory; "
                             "two worker threads with their own engine and CUDA stream, so one batch's host work and "
                             "copies overlap the other's kernels",
-                    "host_packed_value": world * W * args.steps / e2e_hostpack_s,
+                    "host_packed_value": world * W * e2e_nb / e2e_hostpack_s,
                     "host_packed_h2d_bytes_per_step": h2d_hostpack,
                     "synchronous_value": world * W * args.steps / e2e_sync_s,
                     "c_abi_only_value": world * W * args.steps / abi_s, "host_packing_ms": 1e3 * pack_s},
