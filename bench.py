@@ -436,6 +436,8 @@ def main():
                 "flops_per_launch": flops_launch, "flops_per_model": float(run_flops.mean()),
                 "active_pairs_per_model": float(active.mean()), "kernel_ms": run_ms,
                 "setup_kernel_ms": setup_ms, "cor_kernel_ms": cor_ms,
+                "setup_cor_note": "cor_kernel runs on the handle's second stream concurrently with setup_kernel (both "
+                                  "durations are measured while they share the GPU); run_kernel waits for both",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture of
                 # 1184 Test-1 walkers committed as profiles/r01_g_final_ncu_summary.txt (1.6139 GB + 6.9 MB), per walker
                 "traffic": (1.613871e9 + 6.920960e6) / 1184.0 * W if args.ic_path == "R" else None,

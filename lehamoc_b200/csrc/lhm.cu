@@ -557,6 +557,11 @@ struct lhm_handle {
     // device-side timing of the last setup / cor / run launches (lhm_last_timings)
     cudaEvent_t ev[6];
     bool ev_set[3];
+    // cor_factor_syn_el depends on the inputs only (consts, g_el): lhm_setup_batch launches it on a second stream so that
+    // its ~0.3 ms of serial latency hides behind the table set-up; the run waits on ev_join
+    cudaStream_t aux;
+    cudaEvent_t ev_fork, ev_join;
+    bool cor_valid;
 };
 
 static PhysConst make_consts() {
@@ -633,6 +638,9 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
         CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));
     }
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
+    CUDA_TRY(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
     return LHM_OK;
 }
 
@@ -663,6 +671,9 @@ void lhm_destroy(lhm_handle* h) {
     cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E); cudaFree(h->d_ptab);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
+    if (h->aux) cudaStreamDestroy(h->aux);
     delete h;
 }
 
@@ -670,6 +681,8 @@ int lhm_step_smem_bytes(const lhm_handle* h) { return h ? (int)h->smem : LHM_ERR
 long long lhm_table_bytes_per_walker(const lhm_handle* h) {
     return h ? (long long)h->L.n_doubles * 8 + (long long)h->L.n_ints * 4 : LHM_ERR_ARG;
 }
+
+static int launch_cor(lhm_handle* h, double* out, cudaStream_t st);
 
 int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_el, const double* nu_syn,
                     const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext) {
@@ -687,13 +700,34 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
         if (!h->g_pr || !h->pr_inj) return LHM_ERR_STATE;
         A.g_pr = h->g_pr; A.pr_inj = h->pr_inj;
     }
+    h->W = W; h->consts = consts; h->g_el = g_el;
+    h->cor_valid = false;
+    if (h->cfg.Syn_emis_flag) {                    // fork: the cor-factor of this batch next to its table set-up
+        CUDA_TRY(cudaEventRecord(h->ev_fork, h->stream));          // after everything queued so far (inputs, last run)
+        CUDA_TRY(cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+        int rc = launch_cor(h, h->d_cor, h->aux);
+        if (rc != LHM_OK) return rc;
+        CUDA_TRY(cudaEventRecord(h->ev_join, h->aux));
+        h->cor_valid = true;
+    }
     CUDA_TRY(cudaEventRecord(h->ev[0], h->stream));
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
     h->ev_set[0] = true;
-    h->W = W; h->consts = consts; h->g_el = g_el;
+    return LHM_OK;
+}
+
+static int launch_cor(lhm_handle* h, double* out, cudaStream_t st) {
+    CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
+    CUDA_TRY(cudaEventRecord(h->ev[2], st));
+    CUDA_TRY(ensure_dyn_smem(cor_kernel, cor_smem_bytes(h->cfg.Ng), g_smem_cor[h->device % MAX_DEV]));
+    cor_kernel<<<(h->W + COR_WARPS - 1) / COR_WARPS, COR_WARPS * 32, cor_smem_bytes(h->cfg.Ng), st>>>(A);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    CUDA_TRY(cudaEventRecord(h->ev[3], st));
+    h->ev_set[1] = true;
     return LHM_OK;
 }
 
@@ -701,15 +735,7 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
     if (!h || !out) return LHM_ERR_ARG;
     if (h->W < 1) return LHM_ERR_STATE;
     CUDA_TRY(cudaSetDevice(h->device));
-    CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
-    CUDA_TRY(cudaEventRecord(h->ev[2], h->stream));
-    CUDA_TRY(ensure_dyn_smem(cor_kernel, cor_smem_bytes(h->cfg.Ng), g_smem_cor[h->device % MAX_DEV]));
-    cor_kernel<<<(h->W + COR_WARPS - 1) / COR_WARPS, COR_WARPS * 32, cor_smem_bytes(h->cfg.Ng), h->stream>>>(A);
-    g_launches++;
-    CUDA_TRY(cudaGetLastError());
-    CUDA_TRY(cudaEventRecord(h->ev[3], h->stream));
-    h->ev_set[1] = true;
-    return LHM_OK;
+    return launch_cor(h, out, h->stream);
 }
 
 static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
@@ -776,8 +802,11 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     CUDA_TRY(cudaSetDevice(h->device));
     const double* cor = nullptr;
     if (h->cfg.Syn_emis_flag) {
-        int rc = lhm_cor_factor_batch(h, h->d_cor);
-        if (rc != LHM_OK) return rc;
+        if (h->cor_valid) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // launched by lhm_setup_batch
+        else {
+            int rc = launch_cor(h, h->d_cor, h->stream);
+            if (rc != LHM_OK) return rc;
+        }
         cor = h->d_cor;
     }
     RunArgs A;
