@@ -699,10 +699,8 @@ __device__ __forceinline__ double fast_exp2(double x, const double* __restrict__
 constexpr int GG_U = 4;
 
 // one row: sum_k w_k * cf * (1 - s_k^-2) * ln s_k * 2^(interp of Lm at y_k),  y_k = a + k*step, k = 0..NP-1
-// e_begin (a multiple of GG_U) .. e_end: the samples this call sums; the default is the whole row
 __device__ __forceinline__ double gg_row_sum(const Smem& S, const double* __restrict__ Lm, int Nt, int NP, double a,
-                                             double step, double cf, double r2, bool is_a, int e_begin = 0,
-                                             int e_end = 1 << 30) {
+                                             double step, double cf, double r2, bool is_a) {
     const double* __restrict__ lxt = S.lxtS;
     const double* __restrict__ ilx = S.ilxS;
     const double* __restrict__ tab = S.e2tab;
@@ -717,13 +715,12 @@ __device__ __forceinline__ double gg_row_sum(const Smem& S, const double* __rest
         const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
         double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
         inv[0] = is_a ? (1.0 / 1.69) : 1.0;
-        if (e_begin > 0) inv[0] *= pow(r2, (double)e_begin);    // a row split between two threads: start mid-row
 #pragma unroll
         for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
         double rU = r2;
 #pragma unroll
         for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
-        for (int e0 = e_begin; e0 < min(NP, e_end); e0 += GG_U) {
+        for (int e0 = 0; e0 < NP; e0 += GG_U) {
             double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
             int j[GG_U];
 #pragma unroll
@@ -768,44 +765,6 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
     const Layout& L = C.L;
     const int NP = L.NP, Ni = L.Ni, Ng = L.Ng, Nt = L.Nt;
     const int nrows = Ni + (Ng - 1);
-    // Test 1 has 389 rows for 256 threads: row-per-thread leaves the second pass half empty.  Balanced form: the work
-    // unit is one batch of GG_U samples of one row; every thread takes the same number of consecutive units.  A row is
-    // shared by at most two threads as long as a thread owns at least a row's worth of units, so the two partial sums
-    // meet in a shared-memory atomicAdd whose result does not depend on the order (a + b == b + a).
-    const int NB = (NP + GG_U - 1) / GG_U;
-    const int upt = (nrows * NB + NT - 1) / NT;
-    if (upt >= NB && nrows > NT) {
-        double* sum = S.cp;                                  // cp|dp are contiguous and 2*Nmax >= Ni + Ng doubles
-        for (int r = threadIdx.x; r < nrows; r += NT) sum[r] = 0.0;
-        __syncthreads();
-        int u = threadIdx.x * upt;
-        const int uend = min(nrows * NB, u + upt);
-        while (u < uend) {
-            const int row = u / NB, b0 = u - row * NB, b1 = min(NB, b0 + (uend - u));
-            const bool is_a = row < Ni;
-            const int r = is_a ? row : row - Ni;
-            const double a = __ldg(C.T + (is_a ? L.agg_a : L.qee_a) + r);
-            const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
-            const double cf = __ldg(C.T + (is_a ? L.agg_c : L.qee_c) + r);
-            const double r2 = __ldg(C.T + (is_a ? L.agg_r2 : L.qee_r2) + r);
-            const double part = gg_row_sum(S, S.Lm, Nt, NP, a, step, cf, r2, is_a, b0 * GG_U, b1 * GG_U);
-            if (b0 == 0 && b1 == NB) sum[row] = part;
-            else atomicAdd(sum + row, part);
-            u += b1 - b0;
-        }
-        __syncthreads();
-        for (int row = threadIdx.x; row < nrows; row += NT) {
-            if (row < Ni) agg_out[row] = sum[row];
-            else {
-                const int r = row - Ni;
-                double ng = 0.0;
-                if (2.0 * S.gS[r] > 1.0)
-                    ng = exp10(interp_eval(Lng, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
-                qee_out[r] = kPC.qee_pref * (ng * sum[row]);
-            }
-        }
-        return;
-    }
     for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
