@@ -668,7 +668,7 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor, const dou
 // of an empty photon bin); x <= ~1000.  x = n/64 + f, |f| <= 1/128: 2^f by a degree-5 polynomial (truncation 4e-17),
 // 2^(n mod 64 / 64) from a 64-entry table, 2^(n div 64) by two exponent-field multiplies (gradual underflow kept).
 __device__ __forceinline__ double fast_exp2(double x, const double* __restrict__ tab) {
-    if (!(x > -1100.0)) x = -1100.0;
+    x = fmax(x, -1100.0);                                         // NaN and -inf -> -1100 (fmax drops the NaN)
     const double MAGIC = 6755399441055744.0;                      // 2^52 + 2^51: round-to-nearest-integer by addition
     const double zm = fma(x, 64.0, MAGIC);
     const int n = __double2loint(zm);
@@ -681,7 +681,9 @@ __device__ __forceinline__ double fast_exp2(double x, const double* __restrict__
     p = fma(p, r, 1.0);
     p = fma(p, r, 1.0);
     p *= tab[n & 63];
-    const int k = n >> 6, k1 = k >> 1, k2 = k - k1;
+    const int k = n >> 6;
+    if (k >= -1020) return p * __hiloint2double((k + 1023) << 20, 0);     // normal range: one exact scaling
+    const int k1 = k >> 1, k2 = k - k1;                                       // gradual underflow: two steps
     p *= __hiloint2double((k1 + 1023) << 20, 0);
     p *= __hiloint2double((k2 + 1023) << 20, 0);
     return p;
@@ -720,30 +722,43 @@ __device__ __forceinline__ double gg_row_sum(const Smem& S, const double* __rest
         double rU = r2;
 #pragma unroll
         for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
+        const double dlcf = dl * cf;                        // weight of an interior sample x the row's prefactor
+        double ed[GG_U];
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) ed[u] = (double)u;
         for (int e0 = 0; e0 < NP; e0 += GG_U) {
             double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
             int j[GG_U];
 #pragma unroll
             for (int u = 0; u < GG_U; ++u) {
-                const int e = e0 + u;
-                const double ed = (double)e;
-                y[u] = (e >= NP - 1) ? lxN : fma(ed, step, a);
-                const double wgt = (e == 0 || e == NP - 1) ? 0.5 * dl : ((e < NP) ? dl : 0.0);
-                Kv[u] = wgt * cf * (1.0 - inv[u]) * fma(ed, dl, lns0);
+                y[u] = fma(ed[u], step, a);
+                Kv[u] = dlcf * (1.0 - inv[u]) * fma(ed[u], dl, lns0);
                 inv[u] *= rU;
+                ed[u] += (double)GG_U;
+            }
+            // trapezoid end weights and the exact last abscissa: only the first and the last batch (uniform branches)
+            if (e0 == 0) Kv[0] *= 0.5;
+            if (e0 + GG_U >= NP) {
+#pragma unroll
+                for (int u = 0; u < GG_U; ++u) {
+                    const int e = e0 + u;
+                    if (e == NP - 1) { y[u] = lxN; Kv[u] *= 0.5; }
+                    else if (e >= NP) { y[u] = lxN; Kv[u] = 0.0; }
+                }
             }
 #pragma unroll
             for (int u = 0; u < GG_U; ++u) {
-                int jj = (int)((y[u] - lx0) * invD);
-                jj = max(0, min(jj, Nt - 2));
-                while (jj > 0 && y[u] < lxt[jj]) --jj;
-                while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                y[u] = fmax(y[u], lx0);                         // np.interp clamps below the grid (t = 0 in segment 0)
+                int jj = (int)((y[u] - lx0) * invD);            // both grids are log-uniform: the guess is right
+                jj = max(0, min(jj, Nt - 2));                   // except next to a node ...
+                double lo = lxt[jj];
+                if (!(y[u] >= lo && y[u] < lxt[jj + 1])) {      // ... where it is corrected against the actual doubles
+                    while (jj > 0 && y[u] < lxt[jj]) --jj;
+                    while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                    lo = lxt[jj];
+                }
                 j[u] = jj;
-            }
-#pragma unroll
-            for (int u = 0; u < GG_U; ++u) {
-                t[u] = (y[u] - lxt[j[u]]) * ilx[j[u]];
-                if (y[u] <= lx0) t[u] = 0.0;                // np.interp clamps below the grid
+                t[u] = (y[u] - lo) * ilx[jj];
             }
 #pragma unroll
             for (int u = 0; u < GG_U; ++u) {
