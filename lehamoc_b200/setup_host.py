@@ -88,6 +88,31 @@ def _Lum_e_inj(comp, R):                           # LeHaMoC_f.py:66-67
     return 4. * np.pi * R * m_el * c ** 3. * comp / sigmaT
 
 
+USER_SPECTRUM_FILE = "Photons_spec_user.txt"      # read from the working directory, LeMoC.py:165 / LeHaMoC.py:206
+USER_SPECTRUM_KEY = "_user_spectrum"              # optional (log10 nu, log10 dN/dVdnu) pair in a parameter dict instead
+
+
+def user_photon_field(F: dict, nu_tot: np.ndarray) -> np.ndarray:
+    """External user-defined photon field on nu_tot (LeMoC.py:160-169, LeHaMoC.py:201-210): a two-column CSV of
+    log10(nu), log10(dN/dV dnu); last ordinate replaced by 1e-160, log-log np.interp with its end clamping."""
+    if float(F["User_ph"]) == 0.:
+        return np.zeros(len(nu_tot))
+    if USER_SPECTRUM_KEY in F:
+        logx, logy = (np.asarray(a, dtype=np.float64) for a in F[USER_SPECTRUM_KEY])
+    else:
+        try:
+            tab = np.loadtxt(USER_SPECTRUM_FILE, delimiter=",", ndmin=2)
+        except OSError as e:
+            raise FileNotFoundError(f"User_ph = {F['User_ph']}: {USER_SPECTRUM_FILE} not found in the working "
+                                    "directory (the reference reads it from there)") from e
+        logx, logy = tab[:, 0], tab[:, 1]
+    nu_user = 10 ** np.array(logx)
+    tmp = 10 ** np.array(logy)
+    tmp[-1] = 10 ** (-160.)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return 10 ** np.interp(np.log10(nu_tot), np.log10(nu_user), np.log10(tmp))
+
+
 def external_fields(F: dict, nu_tot: np.ndarray) -> np.ndarray:
     """BB + PL + user photon densities on nu_tot as they come out of photons_tot (LeMoC.py:140-169 through
     LeHaMoC_f.py:154-156), for one nu_tot grid.  With BB_flag = 0 the BB term is log10(0) = -inf everywhere
@@ -115,9 +140,7 @@ def external_fields(F: dict, nu_tot: np.ndarray) -> np.ndarray:
         sp[-1] = 0.
         with np.errstate(divide="ignore", invalid="ignore"):
             pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(k_ph * sp ** (-float(F["s_ph"]))))
-    if F["User_ph"] != 0.:
-        raise NotImplementedError("User_ph: Photons_spec_user.txt input (LeMoC.py:165) is not supported yet")
-    return bb + pl
+    return bb + pl + user_photon_field(F, nu_tot)                 # order of photons_tot, LeHaMoC_f.py:156
 
 
 def _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp, shared):
@@ -332,8 +355,6 @@ def pack_lehamoc(param_sets) -> Batch:
     per_walker = ("g_min_el", "g_max_el", "g_el_PL_min", "g_el_PL_max", "g_min_pr", "g_max_pr", "g_pr_PL_min",
                   "g_pr_PL_max", "p_el", "L_el", "p_pr", "L_pr", "R0", "B0", "n_H")
     for P in param_sets:
-        if float(P["User_ph"]) != 0.:
-            raise NotImplementedError("User_ph: Photons_spec_user.txt input is not supported yet")
         for k in LH_KEYS:
             if k not in per_walker and float(P[k]) != float(F[k]):
                 raise ValueError(f"walkers of one batch must share '{k}'")
@@ -421,7 +442,7 @@ def external_fields_lh(F: dict, nu_tot: np.ndarray) -> np.ndarray:
         tmp = k_ph * sp ** (-float(F["s_ph"]))
         tmp[-1] = SENTINEL
         pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(tmp))
-    return bb + pl
+    return bb + pl + user_photon_field(F, nu_tot)
 
 
 def pack_script(param_sets) -> Batch:

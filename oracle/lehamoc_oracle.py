@@ -194,6 +194,20 @@ def Q_ee_f(nu_target, photons_target, nu_ic, photons_IC, g, R0=None):
 
 
 # --- A1 photon-field merge, LeHaMoC_f.py:154-156 -------------------------------------------------
+def user_field(User_ph, user_spectrum, nu_tot):
+    """LeMoC.py:160-169 / LeHaMoC.py:201-210: the user table (log10 nu, log10 dN/dVdnu), as read from
+    Photons_spec_user.txt, on nu_tot."""
+    if User_ph == 0.:
+        return np.zeros(len(nu_tot))
+    if user_spectrum is None:
+        raise ValueError("User_ph != 0 needs the (logx, logy) table of Photons_spec_user.txt")
+    nu_user = 10 ** np.array(user_spectrum[0], dtype=np.float64)
+    tmp = 10 ** np.array(user_spectrum[1], dtype=np.float64)
+    tmp[-1] = 10 ** (-160.)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        return 10 ** np.interp(np.log10(nu_tot), np.log10(nu_user), np.log10(tmp))
+
+
 def photons_tot(nu_syn, nu_bb, photons_syn, nu_ic, photons_IC, nu_tot, photons_bb, photons_pl, photons_user):
     with np.errstate(divide="ignore", invalid="ignore"):
         lt = np.log10(nu_tot)
@@ -366,6 +380,7 @@ class LeptonicRun:
                   'nu_min_ph', 'nu_max_ph', 's_ph', 'User_ph'):
             setattr(self, k, g(k))
         self.temperature = 10 ** g('BB_temperature')
+        self.user_spectrum = P.get("_user_spectrum")
         self._setup()
 
     # LeMoC.py:107-191 (== Code.py:96-180)
@@ -411,9 +426,7 @@ class LeptonicRun:
             sp[-1] = 0.
             with np.errstate(divide="ignore", invalid="ignore"):
                 pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(k_ph * sp ** (-self.s_ph)))
-        if self.User_ph != 0.:
-            raise NotImplementedError("User_ph table input (LeMoC.py:165) is host I/O, not on the path")
-        user = np.zeros(len(nu_tot))
+        user = user_field(self.User_ph, self.user_spectrum, nu_tot)
         self.Q_ee = np.zeros(n - 1)
         el_inj = np.ones(n) * SENT
         a, b_ = self.index_PL_min, self.index_PL_max

@@ -119,6 +119,7 @@ class LeptoHadronicRun:
         self.R0 = 10 ** float(P["R0"])
         self.temperature = 10 ** float(P["temperature"])
         self.tables = tables
+        self.user_spectrum = P.get("_user_spectrum")
         self._setup()
 
     def _setup(self):                                        # LeHaMoC.py:132-264
@@ -163,9 +164,7 @@ class LeptoHadronicRun:
             tmp = k_ph * sp ** (-self.s_ph)
             tmp[-1] = 10 ** (-260.)
             pl = 10 ** np.interp(np.log10(nu_tot), np.log10(sp), np.log10(tmp))
-        if self.User_ph != 0.:
-            raise NotImplementedError("User_ph table input is host I/O, not on the path")
-        self.user = np.zeros(len(nu_tot))
+        self.user = lo.user_field(self.User_ph, self.user_spectrum, nu_tot)
         self.pl = pl
         el_inj = np.ones(len(g_el)) * SENT
         pr_inj = np.ones(len(g_pr)) * SENT

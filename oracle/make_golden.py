@@ -89,6 +89,35 @@ def thin(cap, every):
     return out
 
 
+USER_LOGX = np.linspace(11., 16., 26)
+USER_LOGY = -3. - 0.4 * (USER_LOGX - 13.2) ** 2                 # a log-parabola photon field, cm^-3 Hz^-1
+USER_TXT = "".join(f"{x!r},{y!r}\n" for x, y in zip(USER_LOGX.tolist(), USER_LOGY.tolist()))
+
+
+def make_user():
+    """var_user / lh_user: User_ph = 1 with a Photons_spec_user.txt in the working directory (LeMoC.py:160-169,
+    LeHaMoC.py:201-210), unmodified scripts."""
+    warnings.filterwarnings("ignore")
+    tmp = tempfile.mkdtemp(prefix="lhm_gold_")
+    p = variant(grid_g_el=100., grid_nu=60., User_ph=1., time_end=4.)
+    pf = os.path.join(tmp, "Parameters_user.txt")
+    rr.write_params(pf, p)
+    cap, wall, _ = rr.run_lemoc_script(pf, extra_files={"Photons_spec_user.txt": USER_TXT})
+    print(f"variant user: {wall:.1f} s")
+    save("var_user", cap, p, {"wall_s": np.float64(wall), "user_logx": USER_LOGX, "user_logy": USER_LOGY})
+    import run_reference_lh as rl
+    import make_golden_lh as mgl
+    P = mgl.variant(grid_g_el=80., grid_nu=60., time_end=4., User_ph=1.)
+    r = rl.run_lehamoc_script(P, extra_files={"Photons_spec_user.txt": USER_TXT})
+    keys = sorted(P)
+    out = {"param_keys": np.array(keys), "param_vals": np.array([P[k] for k in keys], dtype=np.float64),
+           "user_logx": USER_LOGX, "user_logy": USER_LOGY}
+    out.update({k: v for k, v in r.items() if k != "wall_s"})
+    out["wall_s"] = np.float64(r["wall_s"])
+    np.savez_compressed(os.path.join(GOLD, "lh_user.npz"), **out)
+    print(f"lh_user: {r['wall_s']:.1f} s")
+
+
 def main():
     warnings.filterwarnings("ignore")
     os.makedirs(GOLD, exist_ok=True)
@@ -157,4 +186,7 @@ def main():
 
 
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "user":
+        make_user()
+    else:
+        main()

@@ -123,9 +123,13 @@ def read_params(path: str) -> dict:
     return out
 
 
-def run_lemoc_script(param_file: str, memo_cor: bool = True):
-    """exec LeMoC/LeMoC.py on `param_file`; returns (capture dict, wall seconds)."""
+def run_lemoc_script(param_file: str, memo_cor: bool = True, extra_files: dict | None = None):
+    """exec LeMoC/LeMoC.py on `param_file`; returns (capture dict, wall seconds).  `extra_files` {name: text} are
+    written into the temporary working directory first (Photons_spec_user.txt for User_ph = 1, LeMoC.py:165)."""
     with _ref_env("LeMoC") as (ref_dir, tmp):
+        for name, text in (extra_files or {}).items():
+            with open(os.path.join(tmp, name), "w") as fh:
+                fh.write(text)
         f = importlib.import_module("LeHaMoC_f")
         rec = Recorder(f, memo_cor=memo_cor)
         src = open(os.path.join(ref_dir, "LeMoC.py")).read()

@@ -22,7 +22,7 @@ HAD_DIR = os.path.join(rr.REF_ROOT, "LeHaMoC Code and Tests")
 TABLES = ("Phi_g_K&A.txt", "Phi_g_leptons_K&A.txt", "Phi_e-nu_e_K&A.txt", "f(xi).csv", "cross_section.csv", "kp_pg.txt")
 
 
-def run_lehamoc_script(params: dict):
+def run_lehamoc_script(params: dict, extra_files: dict | None = None):
     """-> dict(g_el, n_e [S,Ng], nu_tot, nuLnu [S,Nt], g_pr, n_p [S,Np], nu_nu, N_nu [S,50], wall_s)."""
     if not rr.reference_available():
         raise RuntimeError("reference tree not present (build container only)")
@@ -31,6 +31,9 @@ def run_lehamoc_script(params: dict):
     tmp = tempfile.mkdtemp(prefix="lhm_lh_")
     for t in TABLES:
         os.symlink(os.path.join(HAD_DIR, t), os.path.join(tmp, t))
+    for name, text in (extra_files or {}).items():          # Photons_spec_user.txt for User_ph = 1 (LeHaMoC.py:206)
+        with open(os.path.join(tmp, name), "w") as fh:
+            fh.write(text)
     pf = os.path.join(tmp, "Parameters_run.txt")
     rr.write_params(pf, params)
     saved = (os.getcwd(), list(sys.path), list(sys.argv))

@@ -152,7 +152,7 @@ def test_function_twins(orc):
 # ---------------------------------------------------------------------------------------------------
 # whole time integrations against the golden vectors of the unmodified reference
 # ---------------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly"])
+@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly", "var_user"])
 @pytest.mark.parametrize("path", ["R", "S"])
 def test_script_runs_match_reference(name, path):
     z, P = load_golden(name)

@@ -40,7 +40,7 @@ def tables():
     return {k[len("table_"):]: g[k] for k in g.files if k.startswith("table_")}
 
 
-@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg"])
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user"])
 def test_oracle_reproduces_lehamoc_script(name):
     z, P = load_golden(name)
     run = olh.LeptoHadronicRun(P)
@@ -73,8 +73,8 @@ def test_pack_lehamoc_matches_oracle_setup():
             ext_ref = 10 ** np.interp(np.log10(run.nu_tot), np.log10(run.nu_bb), np.log10(run.bb * V)) + run.pl
         np.testing.assert_allclose(b.ext[0], ext_ref, rtol=1e-14, atol=0)
     _, P = load_golden("lh_shipped")
-    with pytest.raises(NotImplementedError):
-        pack_lehamoc(dict(P, User_ph=1.))
+    with pytest.raises(FileNotFoundError):
+        pack_lehamoc(dict(P, User_ph=1.))           # no Photons_spec_user.txt in the working directory
     b = pack_lehamoc([dict(P, pp_l_flag=1., n_H=3.), dict(P, pp_l_flag=1., n_H=5., p_pr=2.5)])
     from lehamoc_b200 import _lib
     assert b.cfg["pp_l_flag"] == 1 and b.cfg["pp_g_emis_flag"] == 0
@@ -83,7 +83,7 @@ def test_pack_lehamoc_matches_oracle_setup():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg"])
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user"])
 @pytest.mark.parametrize("path", ["R", "S"])
 def test_gpu_lehamoc_driver_matches_reference(name, path):
     """Every step's pairs, photons and protons against what the unmodified LeHaMoC.py wrote."""

@@ -18,7 +18,7 @@ def _rel(a, b):
     return float(np.max(np.abs(a[m] / b[m] - 1.))) if m.any() else 0.0
 
 
-@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly"])
+@pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_synonly", "var_user"])
 def test_oracle_reproduces_reference_every_step(name):
     z, P = load_golden(name)
     run, ne, sed = orc.run_script(P, record=True)

@@ -18,6 +18,8 @@ TOL_LOG10_FLOOR = 1e-6
 def load_golden(name):
     z = np.load(os.path.join(GOLD, name + ".npz"))
     P = dict(zip([str(k) for k in z["param_keys"]], [float(v) for v in z["param_vals"]]))
+    if "user_logx" in z.files:          # User_ph = 1 fixtures: the table the reference read from Photons_spec_user.txt
+        P["_user_spectrum"] = (np.array(z["user_logx"]), np.array(z["user_logy"]))
     return z, P
 
 
