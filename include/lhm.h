@@ -174,6 +174,10 @@ int lhm_gg_batch(lhm_handle*, const double* n, const double* photons_IC_dens, do
 /* A3 thomas() with a == 0 (every call site: LeMoC.py:239,267,273): x = upper-bidiagonal solve, [W,n] */
 int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const double* d, double* x,
                            void* cuda_stream);
+/* thomas(a,b,c,d) with a non-zero sub-diagonal (LeHaMoC_f.py:241-264), [W,n] systems; work2: caller-owned scratch of
+ * 2*W*n doubles.  Unit-test twin: every call site of the drivers has a == 0 (lhm_bidiag_solve_batch). */
+int lhm_tridiag_solve_batch(int W, int n, const double* a, const double* b, const double* c, const double* d,
+                            double* work2, double* x, void* cuda_stream);
 
 /* A10 fit epilogue for W walkers, one warp per walker (handle-free, like lhm_bidiag_solve_batch):
  *   Model.__call__ (Fit_emcee/fit_emcee.py:103-115): xp = log10(nu_tot) + doppler - log10(1+z),

@@ -4,8 +4,9 @@
 
 writes Pairs_Distribution<suffix>.txt, Photons_Distribution<suffix>.txt, Protons_Distribution<suffix>.txt and
 Neutrinos_Distribution<suffix>.txt in the reference's text format (one block per timestep).  `run()` is the importable
-form and takes several parameter sets at once.  The photopion and Bethe-Heitler proton loss terms, the photopion pairs / photons and the neutrinos
-and the Bethe-Heitler pair injection are part of the fused timestep; the pp channels raise NotImplementedError.
+form and takes several parameter sets at once.  The photopion, Bethe-Heitler and pp proton loss terms, the photopion
+pairs / photons / neutrinos, the Bethe-Heitler pair injection and the pp pairs / pi0 photons / neutrinos are all part
+of the fused timestep.
 """
 from __future__ import annotations
 

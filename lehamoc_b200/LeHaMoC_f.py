@@ -11,7 +11,7 @@ import numpy as np
 
 from . import _lib
 from .constants import G, c, Ro, Mo, yr, kpc, pc, m_pr, m_el, kb, h, q, sigmaT, eV, B_cr  # noqa: F401
-from .engine import Engine, bidiag_solve
+from .engine import Engine, bidiag_solve, tridiag_solve
 from .setup_host import Batch, _Lum_e_inj, _Q_el_Lum, _nu_c
 
 
@@ -162,9 +162,10 @@ def cor_factor_syn_el(g_el_space, R0, B0, p_el, Lum_e_injected):
 
 # --- A3  LeHaMoC_f.py:241-264 --------------------------------------------------------------------------
 def thomas(a, b, c, d):
-    """Every call site of the drivers passes a == 0 (LeMoC.py:239,267,273), i.e. an upper-bidiagonal system."""
+    """Every call site of the drivers passes a == 0 (LeMoC.py:239,267,273), i.e. an upper-bidiagonal system; a
+    non-zero sub-diagonal takes the general forward-sweep kernel."""
     if np.any(np.asarray(a) != 0.):
-        raise NotImplementedError("thomas() with a non-zero sub-diagonal is not on the hot path")
+        return tridiag_solve(a, b, c, d)[0].cpu().numpy()
     return bidiag_solve(b, c, d)[0].cpu().numpy()
 
 

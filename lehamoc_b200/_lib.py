@@ -68,6 +68,7 @@ SIGNATURES = {
     "lhm_syn_ssa_batch": (C.c_int, [_P] * 6),
     "lhm_ic_emissivity_batch": (C.c_int, [_P] * 4 + [C.c_int]),
     "lhm_gg_batch": (C.c_int, [_P] * 5),
+    "lhm_tridiag_solve_batch": (C.c_int, [C.c_int, C.c_int] + [_P] * 7),
     "lhm_bidiag_solve_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, _P]),
     "lhm_loglike_batch": (C.c_int, [C.c_int, C.c_int, _P, _P, _P, _P, C.c_double, C.c_double, C.c_int] + [_P] * 8),
     "lhm_had_loss_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P]),

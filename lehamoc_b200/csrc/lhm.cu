@@ -944,6 +944,34 @@ int lhm_gg_batch(lhm_handle* h, const double* n, const double* photons_IC_dens, 
     return launch_unit(h, U_GG, n, photons_IC_dens, nullptr, a_gg, Q_ee, nullptr, -1);
 }
 
+// thomas(a, b, c, d) in full (LeHaMoC_f.py:241-264): forward sweep + back substitution, the reference's operation order
+// without FMA contraction.  One thread per system (function-level twin only: every call site of the drivers has a == 0
+// and goes through the bidiagonal path).
+__global__ void __launch_bounds__(128) tridiag_kernel(int W, int n, const double* a, const double* b, const double* c,
+                                                      const double* d, double* cp, double* dp, double* x) {
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= W) return;
+    const size_t o = (size_t)w * n;
+    cp[o] = c[o] / b[o];
+    dp[o] = d[o] / b[o];
+    for (int i = 1; i < n; ++i) {
+        const double dnum = __dsub_rn(b[o + i], __dmul_rn(a[o + i], cp[o + i - 1]));
+        cp[o + i] = c[o + i] / dnum;
+        dp[o + i] = __dsub_rn(d[o + i], __dmul_rn(a[o + i], dp[o + i - 1])) / dnum;
+    }
+    x[o + n - 1] = dp[o + n - 1];
+    for (int i = n - 2; i >= 0; --i) x[o + i] = __dsub_rn(dp[o + i], __dmul_rn(cp[o + i], x[o + i + 1]));
+}
+
+int lhm_tridiag_solve_batch(int W, int n, const double* a, const double* b, const double* c, const double* d,
+                            double* work2, double* x, void* stream) {
+    if (W < 1 || n < 1 || !a || !b || !c || !d || !work2 || !x) return LHM_ERR_ARG;
+    tridiag_kernel<<<(W + 127) / 128, 128, 0, (cudaStream_t)stream>>>(W, n, a, b, c, d, work2, work2 + (size_t)W * n, x);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
 int lhm_bidiag_solve_batch(int W, int n, const double* b, const double* c, const double* d, double* x, void* stream) {
     if (W < 1 || n < 1 || !b || !c || !d || !x) return LHM_ERR_ARG;
     if ((size_t)n * 2 * sizeof(double) > 48 * 1024) return LHM_ERR_CAPACITY;

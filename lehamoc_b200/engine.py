@@ -316,6 +316,20 @@ def bidiag_solve(b, c, d, device=None):
     return x
 
 
+def tridiag_solve(a, b, c, d, device=None):
+    """thomas(a, b, c, d) for a batch of systems [W, n] (lhm_tridiag_solve_batch)."""
+    _require_cuda()
+    lib = _lib.load()
+    dev = f"cuda:{torch.cuda.current_device() if device is None else device}"
+    ta, tb, tc, td = (torch.as_tensor(np.atleast_2d(x), dtype=torch.float64).to(dev).contiguous() for x in (a, b, c, d))
+    x = torch.empty_like(td)
+    W, n = td.shape
+    work = torch.empty((2, W, n), dtype=torch.float64, device=dev)
+    check(lib.lhm_tridiag_solve_batch(W, n, _ptr(ta), _ptr(tb), _ptr(tc), _ptr(td), _ptr(work), _ptr(x),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)), "lhm_tridiag_solve_batch")
+    return x
+
+
 def fp64_peak_tflops(device: int = 0) -> float:
     _require_cuda()
     lib = _lib.load()

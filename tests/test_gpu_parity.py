@@ -122,8 +122,8 @@ def test_function_twins(orc):
     assert abs(got / float(fz["cor_factor_fitgrid"]) - 1.) < 1e-11
     x = f.thomas(np.zeros(17), fz["thomas_in_b"], fz["thomas_in_c"], fz["thomas_in_d"])
     np.testing.assert_allclose(x, fz["thomas_out_bidiag"], rtol=1e-14)
-    with pytest.raises(NotImplementedError):
-        f.thomas(fz["thomas_in_a"], fz["thomas_in_b"], fz["thomas_in_c"], fz["thomas_in_d"])
+    x = f.thomas(fz["thomas_in_a"], fz["thomas_in_b"], fz["thomas_in_c"], fz["thomas_in_d"])      # general tridiagonal
+    np.testing.assert_array_equal(x, fz["thomas_out_tridiag"])         # same operations in the same order, no FMA
     # per-frequency functions against the oracle's literal restatement on a synthetic state
     rng = np.random.default_rng(3)
     gs = np.logspace(0., 5., 40)
