@@ -246,7 +246,12 @@ enum {
     LHM_PK_COMP_INJ,        /* compactness used for the injection                           LeMoC.py:110,174 / Code.py:163 */
     LHM_PK_COMP_COR,        /* value handed to cor_factor_syn_el (Code.py:237 passes the log)                  */
     LHM_PK_THRMIN, LHM_PK_THRMAX,   /* 10**g_PL_min, 10**g_PL_max (host pow, like the reference's scalars)      */
-    LHM_PACK_NPAR = 12
+    /* protons of Code.py::LeHaMoC (Code.py:299-300,325-347,419-422); used when lhm_pack_args.g_pr != NULL */
+    LHM_PK_GMIN_PR, LHM_PK_GMAX_PR,         /* log10 limits of the proton grid                                  */
+    LHM_PK_GPLMIN_PR, LHM_PK_GPLMAX_PR,     /* log10 limits of the proton power law                             */
+    LHM_PK_THRMIN_PR, LHM_PK_THRMAX_PR,     /* 10** of the two above                                            */
+    LHM_PK_P_PR, LHM_PK_COMP_PR,            /* p_pr, proton compactness 10**P9                                  */
+    LHM_PACK_NPAR = 20
 };
 typedef struct lhm_pack_args {
     int W, Ng, Nh, Nt;      /* Nh = int(grid_g_el/2): len(nu_ic); len(nu_syn) = Nh + 1 */
@@ -257,6 +262,9 @@ typedef struct lhm_pack_args {
     const double* walker_params;                          /* device [W, LHM_PACK_NPAR] */
     const double *nu_ic_row, *nu_tot_row, *ext_row;       /* device [Nh], [Nt], [Nt]: the same for every walker    */
     double *consts, *g_el, *nu_syn, *nu_ic, *nu_tot, *el_inj, *ext;   /* device outputs */
+    int Np;                                 /* len(g_pr) when the proton outputs are wanted */
+    double m_pr, mpc2;                      /* m_pr, m_pr*c**2. */
+    double *g_pr, *pr_inj;                  /* device outputs [W, Np] for lhm_set_protons, or NULL */
 } lhm_pack_args;
 int lhm_pack_batch(const lhm_pack_args* args, void* cuda_stream);
 

@@ -30,8 +30,9 @@ class lhm_config(C.Structure):
         "max_walkers")]
 
 
-LHM_PACK_NPAR = 12
-(PK_R0, PK_B0, PK_GMIN, PK_GMAX, PK_GPLMIN, PK_GPLMAX, PK_P, PK_COMP_INJ, PK_COMP_COR, PK_THRMIN, PK_THRMAX) = range(11)
+LHM_PACK_NPAR = 20
+(PK_R0, PK_B0, PK_GMIN, PK_GMAX, PK_GPLMIN, PK_GPLMAX, PK_P, PK_COMP_INJ, PK_COMP_COR, PK_THRMIN, PK_THRMAX,
+ PK_GMIN_PR, PK_GMAX_PR, PK_GPLMIN_PR, PK_GPLMAX_PR, PK_THRMIN_PR, PK_THRMAX_PR, PK_P_PR, PK_COMP_PR) = range(19)
 
 
 class lhm_pack_args(C.Structure):                    # include/lhm.h: lhm_pack_args
@@ -39,7 +40,9 @@ class lhm_pack_args(C.Structure):                    # include/lhm.h: lhm_pack_a
                 + [(n, C.c_double) for n in ("time_init", "time_end", "step_alg", "Vexp_cm_s", "m", "c", "c3", "m_el",
                                              "mc2", "sigmaT", "four_pi", "nuc_pref")]
                 + [(n, C.c_void_p) for n in ("walker_params", "nu_ic_row", "nu_tot_row", "ext_row", "consts", "g_el",
-                                             "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext")])
+                                             "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext")]
+                + [("Np", C.c_int), ("m_pr", C.c_double), ("mpc2", C.c_double), ("g_pr", C.c_void_p),
+                   ("pr_inj", C.c_void_p)])
 
 
 # every symbol include/lhm.h declares: (restype, argtypes)

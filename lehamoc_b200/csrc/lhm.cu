@@ -1074,6 +1074,8 @@ int lhm_pack_batch(const lhm_pack_args* a, void* stream) {
     A.wp = a->walker_params; A.nu_ic_row = a->nu_ic_row; A.nu_tot_row = a->nu_tot_row; A.ext_row = a->ext_row;
     A.consts = a->consts; A.g_el = a->g_el; A.nu_syn = a->nu_syn; A.nu_ic = a->nu_ic; A.nu_tot = a->nu_tot;
     A.el_inj = a->el_inj; A.ext = a->ext;
+    A.Np = a->Np; A.m_pr = a->m_pr; A.mpc2 = a->mpc2; A.g_pr = a->g_pr; A.pr_inj = a->pr_inj;
+    if ((A.g_pr != nullptr) != (A.pr_inj != nullptr) || (A.g_pr && (A.Np < 4 || A.variant != 1))) return LHM_ERR_ARG;
     pack_kernel<<<a->W, PACK_NT, 0, (cudaStream_t)stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());

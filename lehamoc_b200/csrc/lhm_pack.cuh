@@ -19,6 +19,9 @@ struct PackArgs {
     const double* wp;                       // [W, LHM_PACK_NPAR]
     const double *nu_ic_row, *nu_tot_row, *ext_row;       // [Nh], [Nt], [Nt]: identical for every walker of these drivers
     double *consts, *g_el, *nu_syn, *nu_ic, *nu_tot, *el_inj, *ext;
+    int Np;
+    double m_pr, mpc2;
+    double *g_pr, *pr_inj;                  // null: leptonic model
 };
 
 // np.linspace(lo, hi, n)[i]: arange * step + start, two roundings, last point exactly hi
@@ -40,8 +43,37 @@ __global__ void __launch_bounds__(PACK_NT) pack_kernel(PackArgs A) {
     const double R0 = P[LHM_PK_R0], B0 = P[LHM_PK_B0], g_min = P[LHM_PK_GMIN], g_max = P[LHM_PK_GMAX];
     const double p_el = P[LHM_PK_P], thr_min = P[LHM_PK_THRMIN], thr_max = P[LHM_PK_THRMAX];
     double* g = A.g_el + (size_t)w * Ng;
-    __shared__ int s_imax, s_below;
-    if (tid == 0) { s_imax = Ng; s_below = 0; }
+    __shared__ int s_imax, s_below, s_imax_p, s_below_p;
+    if (tid == 0) { s_imax = Ng; s_below = 0; s_imax_p = A.Np; s_below_p = 0; }
+    // protons of Code.py::LeHaMoC (Code.py:299-300,325-347,419-422): grid, power-law window, number-rate injection
+    if (A.g_pr) {
+        const int Np = A.Np;
+        double* gp = A.g_pr + (size_t)w * Np;
+        const double thr_lo = P[LHM_PK_THRMIN_PR], thr_hi = P[LHM_PK_THRMAX_PR], p_pr = P[LHM_PK_P_PR];
+        for (int j = tid; j < Np; j += PACK_NT) gp[j] = exp10(linspace_pt(P[LHM_PK_GMIN_PR], P[LHM_PK_GMAX_PR], j, Np));
+        __syncthreads();
+        int imax = Np, below = 0;
+        for (int j = tid; j < Np; j += PACK_NT) {
+            if (gp[j] > thr_hi) imax = min(imax, j);
+            if (gp[j] < thr_lo) below++;
+        }
+        atomicMin(&s_imax_p, imax);
+        atomicAdd(&s_below_p, below);
+        __syncthreads();
+        const int ip_max = (P[LHM_PK_GPLMAX_PR] == P[LHM_PK_GMAX_PR]) ? -1 : s_imax_p;
+        const int ip_min = (P[LHM_PK_GPLMIN_PR] == 0.) ? 1 : s_below_p - 1;
+        const int stop_p = ip_max < 0 ? Np + ip_max : ip_max;
+        const double g_lo = gp[ip_min], g_hi = gp[ip_max < 0 ? Np - 1 : min(ip_max, Np - 1)];
+        const double Lp = A.four_pi * R0 * A.m_pr * A.c3 * P[LHM_PK_COMP_PR] / A.sigmaT;
+        double Q0;                                                                    // Q_pr_Lum, LeHaMoC_f.py:75-79
+        if (p_pr == 2.) Q0 = Lp / (A.mpc2 * log(g_hi / g_lo));
+        else {
+            const double e = -p_pr + 2.;
+            Q0 = __dmul_rn(Lp, e) / __dmul_rn(A.mpc2, __dsub_rn(pow(g_hi, e), pow(g_lo, e)));
+        }
+        double* pin = A.pr_inj + (size_t)w * Np;
+        for (int j = tid; j < Np; j += PACK_NT) pin[j] = (j >= ip_min && j < stop_p) ? Q0 * pow(gp[j], -p_pr) : LHM_SENT;
+    }
     for (int j = tid; j < Ng; j += PACK_NT) g[j] = exp10(linspace_pt(g_min, g_max, j, Ng));         // LeMoC.py:115
     __syncthreads();
     // power-law window, LeMoC.py:120-128: first index above 10**g_PL_max (or -1), last index below 10**g_PL_min (or 1)

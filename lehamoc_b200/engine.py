@@ -158,6 +158,17 @@ class Engine:
         a = _lib.lhm_pack_args(W=W, Ng=Ng, Nh=Nh, Nt=Nt, variant=0 if req.variant == "script" else 1,
                                c=c, c3=c ** 3., m_el=m_el, mc2=m_el * c ** 2., sigmaT=sigmaT, four_pi=4. * np.pi,
                                nuc_pref=3. / (4. * np.pi) * q, **req.scalars)
+        if self.cfg.get("driver", 0) == 2:          # Code.py::LeHaMoC: proton grid and injection as well
+            from .constants import m_pr
+            Np = self.cfg["Np"]
+            if getattr(self, "_pack_pr", None) is None:
+                self._pack_pr = (self._new(self.max_walkers, Np), self._new(self.max_walkers, Np))
+            a.Np, a.m_pr, a.mpc2 = Np, m_pr, m_pr * c ** 2.
+            a.g_pr, a.pr_inj = self._pack_pr[0].data_ptr(), self._pack_pr[1].data_ptr()
+            self._keep_pr = (self._pack_pr[0][:W], self._pack_pr[1][:W])
+            check(self.lib.lhm_set_protons(self.h, _ptr(self._keep_pr[0]), _ptr(self._keep_pr[1])), "lhm_set_protons")
+        elif self.cfg.get("driver", 0) != 0:
+            raise LhmError("device-side set-up covers the leptonic drivers and Code.LeHaMoC only")
         a.walker_params = base
         a.nu_ic_row, a.nu_tot_row, a.ext_row = base + 8 * o, base + 8 * (o + Nh), base + 8 * (o + Nh + Nt)
         outs = (consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext)

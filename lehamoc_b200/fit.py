@@ -32,7 +32,8 @@ from . import _lib, shard
 from ._lib import check
 from .constants import eV, pc
 from .engine import Engine, _ptr, _require_cuda
-from .setup_host import pack_code, pack_code_lehamoc, pack_code_request, read_parameter_file
+from .setup_host import (pack_code, pack_code_lehamoc, pack_code_lehamoc_request, pack_code_request,
+                         read_parameter_file)
 
 # fit_emcee.py:31-32
 D_DEFAULT = 3262    # luminosity distance (Mpc)
@@ -142,6 +143,11 @@ class FitEvaluator:
             eng = self._engine(batch)
             eng.setup(batch)
             _, sed = eng.run(want_N=False)
+        elif self.device_pack:
+            req = pack_code_lehamoc_request(thetas[:, :nf], self.frozen)
+            eng = self._engine(req)
+            eng.setup_packed(req)
+            sed = eng.run_lh(snapshots=0)[1][:, 0]
         else:
             batch = pack_code_lehamoc(thetas[:, :nf], self.frozen)
             eng = self._engine(batch)

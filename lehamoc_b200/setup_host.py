@@ -500,6 +500,39 @@ def pack_code_request(thetas, frozen: dict) -> PackRequest:
                          comp_inj, thetas[:, 4].copy())
 
 
+def pack_code_lehamoc_request(thetas, frozen: dict) -> PackRequest:
+    """Device-packed twin of pack_code_lehamoc (same arguments): the proton grid and injection are built by
+    lhm_pack_batch as well."""
+    from . import _lib
+    thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+    if thetas.shape[1] != 10:
+        raise ValueError("Code.LeHaMoC takes 10 free parameters (Code.py:285-295)")
+    missing = [k for k in CODE_KEYS + ("grid_g_pr",) if k not in frozen and k != "Ad_l_flag"]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    F = dict(frozen, Ad_l_flag=0.)
+    R0 = np.array([10 ** x for x in thetas[:, 0].tolist()])
+    B0 = np.array([10 ** x for x in thetas[:, 1].tolist()])
+    g_PL_min, g_PL_max = thetas[:, 2].copy(), thetas[:, 3].copy()
+    comp_inj = np.array([10 ** x for x in thetas[:, 4].tolist()])
+    req = _pack_request("code", F, R0, B0, g_PL_min - 0.5, g_PL_max + 0.5, g_PL_min, g_PL_max, thetas[:, 5].copy(),
+                        comp_inj, thetas[:, 4].copy())
+    lo_t, hi_t = thetas[:, 6], thetas[:, 7]
+    gmin, gmax = lo_t - 0.1, hi_t + 0.5
+    if np.any((hi_t != gmax) & ~(hi_t < gmax)) or np.any((lo_t != 0.) & ~(lo_t > gmin)):
+        raise ValueError("proton power-law window outside the gamma grid (the reference raises here too)")
+    wp = req.walker_params
+    wp[:, _lib.PK_GMIN_PR], wp[:, _lib.PK_GMAX_PR] = gmin, gmax
+    wp[:, _lib.PK_GPLMIN_PR], wp[:, _lib.PK_GPLMAX_PR] = lo_t, hi_t
+    wp[:, _lib.PK_THRMIN_PR] = [10 ** x for x in lo_t.tolist()]
+    wp[:, _lib.PK_THRMAX_PR] = [10 ** x for x in hi_t.tolist()]
+    wp[:, _lib.PK_P_PR] = thetas[:, 9]
+    wp[:, _lib.PK_COMP_PR] = [10 ** x for x in thetas[:, 8].tolist()]
+    req.cfg.update(driver=2, Np=int(float(F["grid_g_pr"])), esc_flag_pr=req.cfg["esc_flag"], shared_ic_grids=0)
+    req.variant = "code_lh"
+    return req
+
+
 def pack_script_request(param_sets) -> PackRequest:
     """Device-packed twin of pack_script (same arguments)."""
     if isinstance(param_sets, dict):
@@ -524,6 +557,56 @@ def pack_script_request(param_sets) -> PackRequest:
                          col("g_PL_max"), col("p_el"), comp_el, comp_el)
 
 
+def _protons_code_lh_loop(thetas, R0, Np):
+    """Proton grid and injection of Code.py::LeHaMoC (Code.py:299-300,325-347,419-422), one walker at a time with the
+    reference's own expressions.  Kept as the statement the vectorised form below is tested against."""
+    W = thetas.shape[0]
+    g_pr = np.empty((W, Np))
+    pr_inj = np.full((W, Np), SENTINEL)
+    for w in range(W):
+        gmin_pr, gmax_pr = float(thetas[w, 6]) - 0.1, float(thetas[w, 7]) + 0.5
+        gp = np.logspace(gmin_pr, gmax_pr, Np)
+        ip_max = -1 if float(thetas[w, 7]) == gmax_pr else int(np.min(np.where(gp > 10 ** float(thetas[w, 7]))[0]))
+        ip_min = 1 if float(thetas[w, 6]) == 0. else int(np.max(np.where(gp < 10 ** float(thetas[w, 6]))[0]))
+        Lp = 4. * np.pi * R0[w] * m_pr_ * c ** 3. * (10 ** float(thetas[w, 8])) / sigmaT
+        pr_inj[w, ip_min:ip_max] = _Q_pr_Lum(Lp, float(thetas[w, 9]), gp[ip_min], gp[ip_max]) * gp[ip_min:ip_max] ** (-float(thetas[w, 9]))
+        g_pr[w] = gp
+    return g_pr, pr_inj
+
+
+def _protons_code_lh(thetas, R0, Np):
+    """The same for all walkers at once (bit-identical: scalar powers through Python floats like the reference's
+    scalars, elementwise NumPy arithmetic in the same order)."""
+    W = thetas.shape[0]
+    lo_t, hi_t, lcomp, p_pr = thetas[:, 6], thetas[:, 7], thetas[:, 8], thetas[:, 9]
+    gmin, gmax = lo_t - 0.1, hi_t + 0.5
+    g_pr = np.logspace(gmin, gmax, Np, axis=-1)                                   # [W, Np]
+    thr_hi = np.array([10 ** x for x in hi_t.tolist()])
+    thr_lo = np.array([10 ** x for x in lo_t.tolist()])
+    gt, lt = g_pr > thr_hi[:, None], g_pr < thr_lo[:, None]
+    same = hi_t == gmax
+    if np.any(~same & ~gt.any(axis=1)) or np.any((lo_t != 0.) & ~lt.any(axis=1)):
+        raise ValueError("proton power-law window outside the gamma grid (the reference raises here too)")
+    ip_max = np.where(same, -1, gt.argmax(axis=1))
+    ip_min = np.where(lo_t == 0., 1, lt.sum(axis=1) - 1)
+    rows = np.arange(W)
+    g_lo, g_hi = g_pr[rows, ip_min], g_pr[rows, ip_max]
+    comp = np.array([10 ** x for x in lcomp.tolist()])
+    Lp = 4. * np.pi * R0 * m_pr_ * c ** 3. * comp / sigmaT
+    e = -p_pr + 2.
+    pw_hi = np.array([x ** y for x, y in zip(g_hi.tolist(), e.tolist())])
+    pw_lo = np.array([x ** y for x, y in zip(g_lo.tolist(), e.tolist())])
+    with np.errstate(divide="ignore", invalid="ignore"):
+        Q0 = Lp * e / (m_pr_ * c ** 2. * (pw_hi - pw_lo))                           # LeHaMoC_f.py:75-79
+    for w in np.flatnonzero(p_pr == 2.):
+        Q0[w] = Lp[w] / (m_pr_ * c ** 2. * np.log(g_hi[w] / g_lo[w]))
+    stop = np.where(ip_max < 0, Np + ip_max, ip_max)
+    col = np.arange(Np)[None, :]
+    inside = (col >= ip_min[:, None]) & (col < stop[:, None])
+    pr_inj = np.where(inside, Q0[:, None] * g_pr ** (-p_pr[:, None]), SENTINEL)
+    return g_pr, pr_inj
+
+
 def pack_code_lehamoc(thetas, frozen: dict) -> Batch:
     """Batch for Fit_emcee/Code.py::LeHaMoC (Code.py:280-535, leptonic + proton synchrotron).  thetas [W,10] =
     [log R0, log B0, log g_min, log g_max, log l_e, p_e, log g_min_pr, log g_max_pr, log l_p, p_p]."""
@@ -540,17 +623,8 @@ def pack_code_lehamoc(thetas, frozen: dict) -> Batch:
     comp_inj = np.array([10 ** x for x in thetas[:, 4].tolist()])
     b = _pack("code", F, R0, B0, g_PL_min - 0.5, g_PL_max + 0.5, g_PL_min, g_PL_max, thetas[:, 5].copy(),
               comp_inj, thetas[:, 4].copy())                                    # Code.py:297-298
-    W, Np = b.W, int(float(F["grid_g_pr"]))
-    g_pr = np.empty((W, Np))
-    pr_inj = np.full((W, Np), SENTINEL)
-    for w in range(W):                                                          # Code.py:299-300,325-347,419-422
-        gmin_pr, gmax_pr = float(thetas[w, 6]) - 0.1, float(thetas[w, 7]) + 0.5
-        gp = np.logspace(gmin_pr, gmax_pr, Np)
-        ip_max = -1 if float(thetas[w, 7]) == gmax_pr else int(np.min(np.where(gp > 10 ** float(thetas[w, 7]))[0]))
-        ip_min = 1 if float(thetas[w, 6]) == 0. else int(np.max(np.where(gp < 10 ** float(thetas[w, 6]))[0]))
-        Lp = 4. * np.pi * R0[w] * m_pr_ * c ** 3. * (10 ** float(thetas[w, 8])) / sigmaT
-        pr_inj[w, ip_min:ip_max] = _Q_pr_Lum(Lp, float(thetas[w, 9]), gp[ip_min], gp[ip_max]) * gp[ip_min:ip_max] ** (-float(thetas[w, 9]))
-        g_pr[w] = gp
+    Np = int(float(F["grid_g_pr"]))
+    g_pr, pr_inj = _protons_code_lh(thetas, R0, Np)
     b.cfg.update(driver=2, Np=Np, esc_flag_pr=b.cfg["esc_flag"], shared_ic_grids=0)
     b.variant = "code_lh"
     b.g_pr, b.pr_inj = g_pr, pr_inj

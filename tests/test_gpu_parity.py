@@ -362,7 +362,7 @@ def test_code_lehamoc_matches_reference():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("variant", ["code", "script"])
+@pytest.mark.parametrize("variant", ["code", "script", "code_lh"])
 def test_gpu_device_packer_matches_host_packer(variant):
     """lhm_pack_batch (grids, injection and scalar block built on the device) against setup_host._pack (NumPy, the
     reference's expressions): identical window indices, sentinels and step counts, <= 2 ulp on g_el, 1e-13 relative on
@@ -376,6 +376,12 @@ def test_gpu_device_packer_matches_host_packer(variant):
         thetas = np.vstack([thetas, thetas[0] + [0.3, -0.2, 0.4, -0.3, 0.2, 0.]])       # p_el == 2 row included below
         thetas[-1, 5] = 2.0
         hb, req = sh.pack_code(thetas, P), sh.pack_code_request(thetas, P)
+    elif variant == "code_lh":
+        cf, P = load_golden("code_lh_fit")
+        thetas = np.array(cf["thetas"])
+        thetas = np.vstack([thetas, thetas[0] + [0.2, -0.1, 0.3, -0.2, 0.1, 0.3, -0.5, 0.2, 0.3, 0.4]])
+        thetas[-1, 6] = 0.0                                                           # g_PL_min_pr == 0 -> index 1
+        hb, req = sh.pack_code_lehamoc(thetas, P), sh.pack_code_lehamoc_request(thetas, P)
     else:
         from lehamoc_b200.presets import test1_walkers
         sets = test1_walkers(12)
@@ -404,9 +410,19 @@ def test_gpu_device_packer_matches_host_packer(variant):
             assert rel.max() <= 1e-13, (name, rel.max())
     from lehamoc_b200 import _lib
     np.testing.assert_array_equal(dev[0][:, _lib.C_NSTEPS], hb.consts[:, _lib.C_NSTEPS])
-    N1, sed1 = eng.run()
     eng2 = Engine(hb.cfg, hb.W)
     eng2.setup(hb)
+    if variant == "code_lh":
+        for name, d, h in zip(("g_pr", "pr_inj"), [t.cpu().numpy() for t in eng._keep_pr], (hb.g_pr, hb.pr_inj)):
+            sent = h == sh.SENTINEL
+            assert np.array_equal(d == sh.SENTINEL, sent), name + ": proton injection window differs"
+            rel = np.abs(d[~sent] / h[~sent] - 1.0)
+            assert rel.max() <= 1e-13, (name, rel.max())
+        r1, r2 = eng.run_lh(), eng2.run_lh()
+        assert_spectra_close(r1[1][:, 0].cpu().numpy(), r2[1][:, 0].cpu().numpy(), "device-packed vs host-packed nuLnu")
+        assert_spectra_close(r1[2][:, 0].cpu().numpy(), r2[2][:, 0].cpu().numpy(), "device-packed vs host-packed n_p")
+        return
+    N1, sed1 = eng.run()
     N2, sed2 = eng2.run()
     assert_spectra_close(sed1.cpu().numpy(), sed2.cpu().numpy(), "device-packed vs host-packed nuLnu")
     assert_spectra_close(N1.cpu().numpy(), N2.cpu().numpy(), "device-packed vs host-packed n_e")

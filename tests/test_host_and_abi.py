@@ -117,3 +117,19 @@ def test_integration_md_stub_matches_binding():
     body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
     hdr_names = [n.strip() for decl in body.split(";") for n in decl.replace("int", "", 1).split(",") if n.strip()]
     assert hdr_names == names
+
+
+def test_vectorised_proton_packing_is_the_loop():
+    """pack_code_lehamoc builds the proton grid / injection of all walkers at once; the per-walker loop with the
+    reference's own expressions (Code.py:299-300,325-347,419-422) gives the same doubles."""
+    from lehamoc_b200 import setup_host as sh
+    rng = np.random.default_rng(3)
+    start = np.array([15.5, 1., 0.5, 5., -3., 1.2, 0.5, 7.3, -4.5, 2.])
+    th = start + 0.3 * rng.standard_normal((64, 10))
+    th[5, 9] = 2.0                      # p_pr == 2 branch of Q_pr_Lum
+    th[7, 6] = 0.0                      # g_PL_min_pr == 0 -> index 1
+    R0 = np.array([10 ** x for x in th[:, 0].tolist()])
+    a = sh._protons_code_lh_loop(th, R0, 160)
+    b = sh._protons_code_lh(th, R0, 160)
+    np.testing.assert_array_equal(a[0], b[0])
+    np.testing.assert_array_equal(a[1], b[1])

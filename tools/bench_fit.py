@@ -30,6 +30,8 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ic-path", default="R")
     ap.add_argument("--host-pack", action="store_true", help="NumPy set-up on the host instead of lhm_pack_batch")
+    ap.add_argument("--flag-c", default="LeMoC", choices=["LeMoC", "LeHaMoC"],
+                    help="numerical model of the fit (fit_emcee.py:23): SSC or SSC + proton synchrotron")
     a = ap.parse_args()
     world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     if world > 1:
@@ -40,9 +42,12 @@ def main():
     cf = np.load(os.path.join(ROOT, "tests", "golden", "code_fit.npz"))
     frozen = {str(k): float(v) for k, v in zip(cf["param_keys"], cf["param_vals"])}
     ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
-                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path, device_pack=not a.host_pack)
+                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path, device_pack=not a.host_pack,
+                          flag_c=a.flag_c)
     logp = ev.log_probability_sharded if world > 1 else ev.log_probability
     init = np.array([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2.])          # fit_emcee.py:207
+    if a.flag_c == "LeHaMoC":
+        init = np.array([15.5, 1., 0.5, 5., -3., 1.2, 0.5, 7.3, -4.5, 2., 1., -2.])   # fit_emcee.py:212,224
     rng = np.random.default_rng(1)
     half = a.walkers // 2
     calls = [init + 1e-2 * rng.standard_normal((half, len(init))) for _ in range(a.reps + 2)]
@@ -64,7 +69,7 @@ def main():
     # where the time goes: host packing alone, and the GPU kernels alone
     t1 = time.perf_counter()
     for th in calls[2:]:
-        b = fit.pack_code(th[:, :6], frozen)
+        b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
     pack = (time.perf_counter() - t1) / a.reps
     su, co, ru = ev.eng.last_timings()
     print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up: "
