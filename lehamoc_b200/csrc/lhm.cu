@@ -189,29 +189,40 @@ __global__ void __launch_bounds__(NT, 1) run_lh_kernel(RunArgs A) {
     }
     ic_prepare<NT>(C, S);
     double t = C.tinit;
+    long long tprev = clock64();            // LHM_TICK: per-phase cycles of thread 0 (lhm_set_phase_profile), see run_kernel
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeHaMoC.py:268-272
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
         C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
         C.V = volume_of(C.Rad);
+        LHM_TICK(0);
         phase_photons<NT>(C, S, true);
         if (C.F.ic_l) phase_uph_lh<NT>(C, S);
+        LHM_TICK(1);
         phase_protons<NT>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
+        LHM_TICK(2);
         if (C.F.bh_e) phase_bh_emis<NT>(C, S, H, BSm, BSp);
+        LHM_TICK(3);
         if (C.F.pg_e) phase_photopion<NT>(C, S, H, A.HT);
         else if (A.had) { for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0; }
+        LHM_TICK(4);
         if (C.F.pp_ee || C.F.pp_g || C.F.pp_nu) phase_pp<NT>(C, S, H, n_H, p_pr);
+        LHM_TICK(5);
         phase_electrons_lh<NT>(C, S, (C.F.pg_e || C.F.pp_ee) ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
         phase_vectors<NT>(C, S);
         phase_syn_rows<NT>(C, S, false);
         phase_syn_protons<NT>(C, S, H);
+        LHM_TICK(6);
         if (C.F.ic_e) {
             if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
         }
         __syncthreads();
         if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        LHM_TICK(7);
         phase_photon_solves_lh<NT>(C, S, H, cor, (C.F.pg_e || C.F.pp_g) ? H.Qpg : nullptr);
+        LHM_TICK(8);
         if (C.F.gg) phase_gg_lh<NT>(C, S, H, step);
+        LHM_TICK(9);
         if (A.had) {                                             // neutrino equation: escape only, LeHaMoC.py:430-434
             const double V2 = 1.0 + C.dt * (kPC.c / C.Rad);
             for (int k = tid + 1; k < 49; k += NT) H.Nnu[k] = (H.Nnu[k] + H.Qnu[k]) / V2;
@@ -771,7 +782,8 @@ int lhm_set_bh_surfaces(lhm_handle* h, const lhm_bh_surface* sm, const lhm_bh_su
     if (h->cfg.driver != 1) return LHM_ERR_STATE;
     if (sm->nx < 8 || sm->ny < 8 || sp->nx < 8 || sp->ny < 8 || !sm->tx || !sm->ty || !sm->c || !sp->tx || !sp->ty || !sp->c)
         return LHM_ERR_ARG;
-    const size_t need = (size_t)sm->nx + sm->ny + (size_t)(sm->nx - 4) * (sm->ny - 4) + sp->nx + sp->ny + (size_t)(sp->nx - 4) * (sp->ny - 4);
+    const size_t need = (size_t)4 * (sm->nx + sm->ny) + (size_t)(sm->nx - 4) * (sm->ny - 4) + 4 * (sp->nx + sp->ny)
+                        + (size_t)(sp->nx - 4) * (sp->ny - 4);          // knots + reciprocal tables + coefficients
     if (need > (size_t)BH_MAXSURF) return LHM_ERR_CAPACITY;
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = had_init();
@@ -1102,6 +1114,7 @@ int lhm_pp_batch(int W, int product, int Nout, int Np, const double* grid, const
 
 static BhSurf to_surf(const lhm_bh_surface* s) {
     BhSurf b; b.tx = s->tx; b.ty = s->ty; b.c = s->c; b.nx = s->nx; b.ny = s->ny; b.zmax = s->zmax;
+    b.rx = nullptr; b.ry = nullptr;
     return b;
 }
 

@@ -368,6 +368,8 @@ struct BhSurf {            // one tck of bisplrep with kx = ky = 3 (pointers to 
     const double *tx, *ty, *c;
     int nx, ny;
     double zmax;           // max_intrp_cs: values above it are replaced by 0 (LeHaMoC_f.py:592-593)
+    const double *rx, *ry; // [3][n]: 1/(t[i] - t[i-j]), j = 1..3 -- the denominators of the de Boor recurrence, built by
+                           // bh_stage (null: divide)
 };
 
 // FITPACK fpbspl: the 4 non-zero cubic B-splines at x in the knot interval l (t[l] <= x < t[l+1])
@@ -383,6 +385,25 @@ __device__ __forceinline__ void bh_fpbspl(const double* __restrict__ t, double x
         for (int i = 0; i < j; ++i) {
             const int li = l + 1 + i, lj = li - j;
             const double f = hh[i] / (t[li] - t[lj]);
+            h[i] = h[i] + f * (t[li] - x);
+            h[i + 1] = f * (x - t[lj]);
+        }
+    }
+}
+// the same with the knot-difference reciprocals tabulated (r = BhSurf::rx / ry): no division in the recurrence
+__device__ __forceinline__ void bh_fpbspl_r(const double* __restrict__ t, const double* __restrict__ r, int n, double x,
+                                            int l, double* h) {
+    double hh[3];
+    h[0] = 1.0;
+#pragma unroll
+    for (int j = 1; j <= 3; ++j) {
+#pragma unroll
+        for (int i = 0; i < j; ++i) hh[i] = h[i];
+        h[0] = 0.0;
+#pragma unroll
+        for (int i = 0; i < j; ++i) {
+            const int li = l + 1 + i, lj = li - j;
+            const double f = hh[i] * r[(j - 1) * n + li];
             h[i] = h[i] + f * (t[li] - x);
             h[i + 1] = f * (x - t[lj]);
         }
@@ -440,28 +461,42 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
     if (Sf) {
         double ax = log10(Ee_min);
         lx = bh_interval(Sf->tx, Sf->nx, ax);
-        bh_fpbspl(Sf->tx, ax, lx, hx);
+        if (Sf->rx) bh_fpbspl_r(Sf->tx, Sf->rx, Sf->nx, ax, lx, hx); else bh_fpbspl(Sf->tx, ax, lx, hx);
     }
     const double ea = log10(1.001 * Emin), eb = log10(Emax);
-    double yE[10], xE[10];
+    // Both inner integrals are scipy.integrate.simpson over 10 samples of a np.logspace grid, i.e. over abscissae
+    // ln(x_q) that are equidistant up to rounding: composite Simpson on the first nine points plus the last-interval
+    // correction for an even number of samples (SciPy >= 1.11) collapse to fixed weights x the spacing.  The samples
+    // are accumulated as they are produced (no per-thread arrays), the abscissae advance by one multiplication.
+    const double SW[10] = {1. / 3., 4. / 3., 2. / 3., 4. / 3., 2. / 3., 4. / 3., 2. / 3., 4. / 3. - 1. / 12., 1. / 3. + 2. / 3.,
+                           5. / 12.};
+    const double dE = (eb - ea) / 9.0, rE = exp10(dE);
+    double Eph = exp10(ea), accE = 0.0;
+#pragma unroll 1
     for (int e = 0; e < 10; ++e) {
-        const double Eph = exp10(logspace_exp(ea, eb, e, 10));
         // 10**np.interp(E_arr, nu_trgt, log10(photons)): interpolation LINEAR in x (LeHaMoC_f.py:577)
         const double f_ph = exp10(interp_clamped(Eph, xt, lph, Nt)) * K.m_el * K.c * K.c / (K.h * (Eph * Eph));
         const double wmax = 2 * gp * Eph;
         double temp = 0.0;
         if (wmin < wmax) {
             const double wa = log10(wmin), wb = log10(wmax);
-            double yw[10], xw[10];
+            const double dw = (wb - wa) / 9.0, rw = exp10(dw);
+            double w = exp10(wa), accw = 0.0;
+            int ly = 3;                              // log10(Ee_max) rises with q: the knot interval only moves forward
+#pragma unroll 1
             for (int q = 0; q < 10; ++q) {
-                const double w = exp10(logspace_exp(wa, wb, q, 10));
                 const double Ee_max = w - 1;
                 double res = 0.0;
                 if (Sf && Ee_min < Ee_max && Ee_min < 80. / 100. * Ee_max) {
                     double ay = log10(Ee_max);
-                    const int ly = bh_interval(Sf->ty, Sf->ny, ay);
+                    {                                // bh_interval, resumed from the previous sample's interval
+                        const double tb = Sf->ty[3], te = Sf->ty[Sf->ny - 4];
+                        if (ay < tb) ay = tb;
+                        if (ay > te) ay = te;
+                        while (!(ay < Sf->ty[ly + 1]) && ly != Sf->ny - 5) ++ly;
+                    }
                     double hy[4];
-                    bh_fpbspl(Sf->ty, ay, ly, hy);
+                    if (Sf->ry) bh_fpbspl_r(Sf->ty, Sf->ry, Sf->ny, ay, ly, hy); else bh_fpbspl(Sf->ty, ay, ly, hy);
                     const int nky1 = Sf->ny - 4;
                     double sp = 0.0;
 #pragma unroll
@@ -473,17 +508,16 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
                     if (sp > Sf->zmax) sp = 0.;
                     res = w * exp10(sp);
                 }
-                yw[q] = res * w;
-                xw[q] = log(w);
+                accw = fma(SW[q], res * w, accw);
+                w *= rw;
             }
-            temp = simpson_irregular(yw, xw, 10);
+            temp = accw * (dw * LN10);
             if (temp < 0.) temp = 0.;
         }
-        yE[e] = f_ph * temp * Eph;
-        xE[e] = log(Eph);
+        accE = fma(SW[e], f_ph * temp * Eph, accE);
+        Eph *= rE;
     }
-    (void)LN10;
-    return n_p * simpson_irregular(yE, xE, 10) / (2. * (gp * gp * gp));
+    return n_p * (accE * (dE * LN10)) / (2. * (gp * gp * gp));
 }
 
 constexpr int BH_CH = 8;        // gamma_e values per chunk
@@ -497,7 +531,7 @@ struct BhArgs {
 };
 
 __host__ __device__ inline size_t bh_smem_doubles(int Nt, int Np, const BhSurf& a, const BhSurf& b) {
-    return (size_t)2 * Nt + 3 * Np + BH_CH * Np + a.nx + a.ny + (size_t)(a.nx - 4) * (a.ny - 4) + b.nx + b.ny +
+    return (size_t)2 * Nt + 3 * Np + BH_CH * Np + 4 * (a.nx + a.ny) + (size_t)(a.nx - 4) * (a.ny - 4) + 4 * (b.nx + b.ny) +
            (size_t)(b.nx - 4) * (b.ny - 4) + 8;
 }
 
@@ -505,11 +539,20 @@ __host__ __device__ inline size_t bh_smem_doubles(int Nt, int Np, const BhSurf& 
 __device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, int nthreads) {
     const int nc = (src.nx - 4) * (src.ny - 4);
     double* tx = sm; double* ty = tx + src.nx; double* cc = ty + src.ny;
+    double* rx = cc + nc; double* ry = rx + 3 * src.nx;
     for (int k = threadIdx.x; k < src.nx; k += nthreads) tx[k] = src.tx[k];
     for (int k = threadIdx.x; k < src.ny; k += nthreads) ty[k] = src.ty[k];
     for (int k = threadIdx.x; k < nc; k += nthreads) cc[k] = src.c[k];
-    dst = src; dst.tx = tx; dst.ty = ty; dst.c = cc;
-    return cc + nc;
+    for (int k = threadIdx.x; k < 3 * src.nx; k += nthreads) {
+        const int j = k / src.nx + 1, i = k % src.nx;
+        rx[k] = (i >= j) ? 1.0 / (src.tx[i] - src.tx[i - j]) : 0.0;          // inf on the repeated end knots: never read
+    }
+    for (int k = threadIdx.x; k < 3 * src.ny; k += nthreads) {
+        const int j = k / src.ny + 1, i = k % src.ny;
+        ry[k] = (i >= j) ? 1.0 / (src.ty[i] - src.ty[i - j]) : 0.0;
+    }
+    dst = src; dst.tx = tx; dst.ty = ty; dst.c = cc; dst.rx = rx; dst.ry = ry;
+    return ry + 3 * src.ny;
 }
 
 // Q_BH_sol for the gamma_e range [i0, i1) of one walker by the whole CTA: buf [BH_CH][Np] scratch, gp/lgp/np_ [Np] staged

@@ -63,3 +63,19 @@ print(f"Test 4 (Ng=300, Np=160, Nt=100, 5 steps, all photo-hadronic channels): {
 print(f"  reference: 748 s per model (author's desktop), 1987 s (survey container)  ->  x{748e3 / (ms / a.walkers):.2e} / x{1987e3 / (ms / a.walkers):.2e}")
 s0 = sed[0, 0].cpu().numpy(); nn = Nnu[0, 0].cpu().numpy()
 print("  walker 0: peak nuLnu %.3e erg/s, neutrino bins > 0: %d, finite: %s" % (s0.max(), int((nn > 0).sum()), bool(np.all(np.isfinite(s0)))))
+
+# per-phase cycle breakdown of thread 0 (diagnostic counters inside run_lh_kernel)
+import ctypes as C  # noqa: E402
+prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+eng.lib.lhm_set_phase_profile(eng.h, C.c_void_p(prof.data_ptr()))
+eng.setup(b)
+eng.run_lh()
+torch.cuda.synchronize()
+eng.lib.lhm_set_phase_profile(eng.h, None)
+p = prof.cpu().numpy().astype(float)
+names = ["loop/out", "photons+uph", "protons (loss rates)", "bh_emis", "photopion", "pp", "electrons+syn rows", "ic",
+         "photon solves", "gg"]
+tot = p[:10].sum()
+print("phase cycles per walker-step (thread 0), total %.0f:" % (tot / a.walkers / 5))
+for n_, v in zip(names, p):
+    print(f"  {n_:22s} {v / a.walkers / 5:12.0f}  {100 * v / tot:5.1f}%")
