@@ -216,9 +216,9 @@ __host__ __device__ inline size_t pion_smem_doubles(int Nt, int Np, int ntab) {
 }
 
 // Qp_g_opt for one product of one walker, by the whole CTA (HAD_NT threads).  out[k] = scale * Q(E_k) for k in
-// [0, Nout); `add` accumulates into out instead of overwriting.  Ends with a barrier.
-__device__ void pion_eval(const PionIn& I, double* work, double* out, double scale, bool add) {
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = HAD_NT / 32;
+// [0, Nout); `add` accumulates into out instead of overwriting.  Ends with a barrier.  `nthreads` = blockDim.x.
+__device__ void pion_eval(const PionIn& I, double* work, double* out, double scale, bool add, int nthreads = HAD_NT) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = nthreads / 32;
     const HadConst& K = kHC;
     const int Nt = I.Nt, Np = I.Np, sp = I.species;
     const double h_0 = 0.313, r = 0.1458;
@@ -245,12 +245,12 @@ __device__ void pion_eval(const PionIn& I, double* work, double* out, double sca
     double* Elxm = Elow + PG_N;        double* Erinv = Elxm + PG_N;      // ln(x_-), 1/(x_+ - x_-)
     double* lgm = Erinv + PG_N;        double* igm = lgm + PG_NG;        // per gamma_p: ln(gamma_p m_p c^2) and its inverse
 
-    for (int k = tid; k < ntab; k += HAD_NT) {
+    for (int k = tid; k < ntab; k += nthreads) {
         tx[k] = tab[k * ncol]; ts[k] = tab[k * ncol + c_s]; td[k] = tab[k * ncol + c_s + 1]; tB[k] = tab[k * ncol + c_s + 2];
     }
     __syncthreads();
     const double ga = log10(fmax(g_min_int, I.gpr0)), gb = log10(I.gprN);
-    for (int gi = tid; gi < PG_NG; gi += HAD_NT) {
+    for (int gi = tid; gi < PG_NG; gi += nthreads) {
         const double lg = logspace_exp(ga, gb, gi, PG_NG);
         const double gp = exp10(lg);
         g_t[gi] = gp;
@@ -267,7 +267,7 @@ __device__ void pion_eval(const PionIn& I, double* work, double* out, double sca
         igm[gi] = 1.0 / (gp * mpc2);
     }
     __syncthreads();
-    for (int e = tid; e < PG_N; e += HAD_NT) {
+    for (int e = tid; e < PG_N; e += nthreads) {
         const int gi = e / PG_NE, ei = e - gi * PG_NE;
         const double gp = g_t[gi];
         const double c_t = mpc2 / (4. * gp);

@@ -323,17 +323,17 @@ __device__ void phase_photopion(const Ctx& C, Smem& S, SmemLh& H, const HadTable
     I.T = T;
     for (int j = tid; j < Np; j += NT) H.lNp[j] = log10(H.Npr[j] / C.V);
     __syncthreads();
-    I.species = SP_EP; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, false);
-    I.species = SP_EM; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, true);
-    I.species = SP_2G; I.Nout = L.Ni; pion_eval(I, H.work, H.Qpg, 1.0, false);
+    I.species = SP_EP; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, false, NT);
+    I.species = SP_EM; I.Nout = L.Ng; pion_eval(I, H.work, H.Qpi, 1.0, true, NT);
+    I.species = SP_2G; I.Nout = L.Ni; pion_eval(I, H.work, H.Qpg, 1.0, false, NT);
     if (C.F.nu) {
         for (int j = tid; j < Np; j += NT) H.lNp[j] = log10(H.Npr[j]);          // LeHaMoC.py:347 passes N_pr itself
         __syncthreads();
         I.Nout = 50;
-        I.species = SP_NUMU;  pion_eval(I, H.work, H.Qnu, C.dt, false);
-        I.species = SP_ANUMU; pion_eval(I, H.work, H.Qnu, C.dt, true);
-        I.species = SP_NUE;   pion_eval(I, H.work, H.Qnu, C.dt, true);
-        I.species = SP_ANUE;  pion_eval(I, H.work, H.Qnu, C.dt, true);
+        I.species = SP_NUMU;  pion_eval(I, H.work, H.Qnu, C.dt, false, NT);
+        I.species = SP_ANUMU; pion_eval(I, H.work, H.Qnu, C.dt, true, NT);
+        I.species = SP_NUE;   pion_eval(I, H.work, H.Qnu, C.dt, true, NT);
+        I.species = SP_ANUE;  pion_eval(I, H.work, H.Qnu, C.dt, true, NT);
     } else {
         for (int k = tid; k < 52; k += NT) H.Qnu[k] = 0.0;
         __syncthreads();

@@ -130,7 +130,7 @@ template <int NT>
 __device__ void ic_prepare(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
     const int tid = threadIdx.x;
-    static_assert(NT / 32 == IC_NW, "the tile schedule is built for IC_NW warps");
+    static_assert(NT / 32 >= IC_NW, "the tile schedule is built for IC_NW warps (further warps sit the IC phase out)");
     for (int j = tid; j < L.Ng; j += NT) {
         S.gS[j] = C.T[L.g + j]; S.lgS[j] = C.T[L.lg + j]; S.inv4gS[j] = C.T[L.inv4g + j];
     }
@@ -485,6 +485,7 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ng = L.Ng, No = L.Ni - 1, Ntar = L.Nt - 1;
     const int NiPad = ((L.Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    if (warp >= IC_NW) return;                      // 512-thread callers: the static schedule feeds IC_NW warps
     double* part = S.partial + warp * NiPad;
     for (int o = lane; o < NiPad; o += 32) part[o] = 0.0;
     __syncwarp();
@@ -615,7 +616,7 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
 
 template <int NT>
 __device__ void phase_ic_finish_R(const Ctx& C, Smem& S) {
-    const int NW = NT / 32;
+    const int NW = IC_NW;
     const int No = C.L.Ni - 1;
     const int NiPad = ((C.L.Ni + IC_OG - 1) / IC_OG) * IC_OG;
     for (int o = threadIdx.x; o < No; o += NT) {
