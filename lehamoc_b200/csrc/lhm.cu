@@ -190,6 +190,7 @@ __global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
     if (A.had && C.F.bh_e) {
         double* p2 = bh_stage(BSm, A.BSm, H.bhsurf, NT_LH);
         bh_stage(BSp, A.BSp, p2, NT_LH);
+        if (tid == 0) simpson_weights_irregular(C.T + L.lgp, Np, H.bhw);      // made visible by ic_prepare's barrier
     }
     ic_prepare<NT_LH>(C, S);
     double t = C.tinit;

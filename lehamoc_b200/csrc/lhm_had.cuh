@@ -463,6 +463,32 @@ __device__ double simpson_irregular(const double* y, const double* x, int N) {
 __constant__ double kSimpson10[10] = {1. / 3., 4. / 3., 2. / 3., 4. / 3., 2. / 3., 4. / 3., 2. / 3., 4. / 3. - 1. / 12.,
                                       1. / 3. + 2. / 3., 5. / 12.};
 
+// scipy.integrate.simpson(y, x=x) is linear in y: W[j] with simpson(y, x) == sum_j W[j] y[j], same pair-of-intervals
+// formula and even-N last-interval correction as simpson_irregular above.  One thread, once per walker (the abscissae
+// are ln(g_pr)); the per-gamma_e integrals then are dot products a warp can do.
+__device__ void simpson_weights_irregular(const double* x, int N, double* W) {
+    for (int j = 0; j < N; ++j) W[j] = 0.0;
+    if (N == 2) { W[0] = W[1] = 0.5 * (x[1] - x[0]); return; }
+    const int stop = (N % 2 == 1) ? N - 2 : N - 3;
+    for (int i = 0; i < stop; i += 2) {
+        const double h0 = x[i + 1] - x[i], h1 = x[i + 2] - x[i + 1];
+        const double hsum = h0 + h1, hprod = h0 * h1;
+        const double h0d = (h1 != 0.0) ? h0 / h1 : 0.0;
+        W[i] += hsum / 6.0 * (2.0 - ((h0d != 0.0) ? 1.0 / h0d : 0.0));
+        W[i + 1] += hsum / 6.0 * (hsum * ((hprod != 0.0) ? hsum / hprod : 0.0));
+        W[i + 2] += hsum / 6.0 * (2.0 - h0d);
+    }
+    if (N % 2 == 0) {
+        const double h0 = x[N - 2] - x[N - 3], h1 = x[N - 1] - x[N - 2];
+        double num = 2 * h1 * h1 + 3 * h0 * h1, den = 6 * (h1 + h0);
+        W[N - 1] += (den != 0.0) ? num / den : 0.0;
+        num = h1 * h1 + 3.0 * h0 * h1; den = 6 * h0;
+        W[N - 2] += (den != 0.0) ? num / den : 0.0;
+        num = 1 * h1 * h1 * h1; den = 6 * h0 * (h0 + h1);
+        W[N - 3] -= (den != 0.0) ? num / den : 0.0;
+    }
+}
+
 // g_pr_int of one (gamma_e, gamma_p) pair (LeHaMoC_f.py:571-610), one thread.
 // xt [Nt] = h nu/(m_e c^2) ascending, lph [Nt] = log10(photons)
 __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double* __restrict__ xt,
@@ -537,7 +563,7 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
     return n_p * (accE * (dE * LN10)) / (2. * (gp * gp * gp));
 }
 
-constexpr int BH_CH = 8;        // gamma_e values per chunk
+constexpr int BH_CH = 16;       // gamma_e values per chunk
 
 struct BhArgs {
     int W, Ng, Np, Nt;
@@ -548,7 +574,7 @@ struct BhArgs {
 };
 
 __host__ __device__ inline size_t bh_smem_doubles(int Nt, int Np, const BhSurf& a, const BhSurf& b) {
-    return (size_t)2 * Nt + 3 * Np + BH_CH * Np + 4 * (a.nx + a.ny) + (size_t)(a.nx - 4) * (a.ny - 4) + 4 * (b.nx + b.ny) +
+    return (size_t)2 * Nt + 4 * Np + BH_CH * Np + 4 * (a.nx + a.ny) + (size_t)(a.nx - 4) * (a.ny - 4) + 4 * (b.nx + b.ny) +
            (size_t)(b.nx - 4) * (b.ny - 4) + 8;
 }
 
@@ -572,8 +598,9 @@ __device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, i
     return ry + 3 * src.ny;
 }
 
-// Q_BH_sol for the gamma_e range [i0, i1) of one walker by the whole CTA: buf [BH_CH][Np] scratch, gp/lgp/np_ [Np] staged
-__device__ void bh_chunk(int i0, int i1, int Np, int Nt, const double* ge_arr, const double* gp, const double* lgp,
+// Q_BH_sol for the gamma_e range [i0, i1) of one walker by the whole CTA: buf [BH_CH][Np] scratch, gp/np_ [Np] staged,
+// Wp [Np] = Simpson weights over ln(g_pr) (simpson_weights_irregular)
+__device__ void bh_chunk(int i0, int i1, int Np, int Nt, const double* ge_arr, const double* gp, const double* Wp,
                          const double* np_, const double* xt, const double* lph, const BhSurf& Sm, const BhSurf& Sp,
                          double* buf, double* out, int nthreads) {
     const int n = (i1 - i0) * Np;
@@ -582,8 +609,13 @@ __device__ void bh_chunk(int i0, int i1, int Np, int Nt, const double* ge_arr, c
         buf[e] = bh_pair(ge_arr[i0 + ii], gp[j], np_[j], Nt, xt, lph, Sm, Sp) * gp[j];      // g_pr_int * g_pr
     }
     __syncthreads();
-    for (int ii = threadIdx.x; ii < i1 - i0; ii += nthreads)
-        out[i0 + ii] = kHC.c * simpson_irregular(buf + (size_t)ii * Np, lgp, Np);               // c * simpson(., ln g_pr)
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    for (int ii = warp; ii < i1 - i0; ii += nthreads / 32) {                                 // c * simpson(., ln g_pr)
+        double s = 0.0;
+        for (int j = lane; j < Np; j += 32) s = fma(Wp[j], buf[(size_t)ii * Np + j], s);
+        s = warp_sum(s);
+        if (lane == 0) out[i0 + ii] = kHC.c * s;
+    }
     __syncthreads();
 }
 
@@ -592,7 +624,8 @@ __global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
     const int w = blockIdx.x, chunk = blockIdx.y, tid = threadIdx.x;
     const int Nt = A.Nt, Np = A.Np;
     double* xt = sh; double* lph = xt + Nt; double* gp = lph + Nt; double* lgp = gp + Np; double* np_ = lgp + Np;
-    double* buf = np_ + Np;
+    double* Wp = np_ + Np;
+    double* buf = Wp + Np;
     BhSurf Sm, Sp;
     double* p = bh_stage(Sm, A.Sm, buf + (size_t)BH_CH * Np, HAD_NT);
     bh_stage(Sp, A.Sp, p, HAD_NT);
@@ -602,9 +635,11 @@ __global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
         gp[k] = g; lgp[k] = log(g); np_[k] = A.N_pr[(size_t)w * Np + k];
     }
     __syncthreads();
+    if (tid == 0) simpson_weights_irregular(lgp, Np, Wp);
+    __syncthreads();
     const int i0 = chunk * BH_CH, i1 = min(i0 + BH_CH, A.Ng);
     if (i0 < A.Ng)
-        bh_chunk(i0, i1, Np, Nt, A.g_el + (size_t)w * A.Ng, gp, lgp, np_, xt, lph, Sm, Sp, buf, A.out + (size_t)w * A.Ng, HAD_NT);
+        bh_chunk(i0, i1, Np, Nt, A.g_el + (size_t)w * A.Ng, gp, Wp, np_, xt, lph, Sm, Sp, buf, A.out + (size_t)w * A.Ng, HAD_NT);
 }
 
 }  // namespace lhm

@@ -88,11 +88,12 @@ struct SmemLh {
     double *ltab;                      // loss tables (LossTab)
     double *work;                      // pion_eval work area
     double *bhbuf, *npl, *Qbh, *bhsurf; // [BH_CH*Np] scratch, [Np] dN_pr/dV, [Ng] Q_BH_sol, staged spline surfaces
+    double *bhw;                        // [Np] Simpson weights over ln(g_pr) (simpson_weights_irregular)
 };
 constexpr int HAD_MAXTAB = 32, HAD_MAXLOSS = 2 * (128 + 64 + 128), BH_MAXSURF = 2048;
 __host__ __device__ inline size_t smem_lh_had_doubles(const Layout& L) {
     return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB)
-           + (size_t)BH_CH * pad2(L.Np) + pad2(L.Np) + pad2(L.Ng) + BH_MAXSURF;
+           + (size_t)BH_CH * pad2(L.Np) + 2 * pad2(L.Np) + pad2(L.Ng) + BH_MAXSURF;
 }
 __host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
     return (size_t)3 * pad2(L.Np) + 2 * pad2(L.Ns) + pad2(L.Nt);
@@ -107,7 +108,8 @@ __device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L, const Sme
     H.Qnu = take(52); H.Nnu = take(52); H.Enu = take(52);
     H.lxpg = take(pad2(L.Nt)); H.lppg = take(pad2(L.Nt));
     H.ltab = take(HAD_MAXLOSS); H.work = take((int)pion_work_doubles(HAD_MAXTAB));     // only valid when the handle
-    H.bhbuf = take(BH_CH * pad2(L.Np)); H.npl = take(pad2(L.Np)); H.Qbh = take(pad2(L.Ng)); H.bhsurf = p;   // reserved smem_lh_had_doubles
+    H.bhbuf = take(BH_CH * pad2(L.Np)); H.npl = take(pad2(L.Np)); H.Qbh = take(pad2(L.Ng)); H.bhw = take(pad2(L.Np));
+    H.bhsurf = p;                                                                        // reserved smem_lh_had_doubles
 }
 
 // U_ph_f, LeHaMoC_f.py:171-182: per gamma a 50-point log resample of the photon field up to nu_T, linear-x trapezoid.
@@ -396,7 +398,7 @@ __device__ void phase_bh_emis(const Ctx& C, Smem& S, SmemLh& H, const BhSurf& Sm
     for (int j = threadIdx.x; j < L.Np; j += NT) H.npl[j] = H.Npr[j] / C.V;
     __syncthreads();
     for (int i0 = 0; i0 < L.Ng; i0 += BH_CH)
-        bh_chunk(i0, min(i0 + BH_CH, L.Ng), L.Np, L.Nt, S.gS, C.T + L.gp, C.T + L.lgp, H.npl, C.T + L.xt, S.Ln, Sm, Sp,
+        bh_chunk(i0, min(i0 + BH_CH, L.Ng), L.Np, L.Nt, S.gS, C.T + L.gp, H.bhw, H.npl, C.T + L.xt, S.Ln, Sm, Sp,
                  H.bhbuf, H.Qbh, NT);
 }
 
