@@ -186,10 +186,13 @@ __global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
         for (int j = tid; j < Ng; j += NT_LH) { H.Qpi[j] = 0.0; H.Qbh[j] = 0.0; }
         for (int k = tid; k < Ni; k += NT_LH) H.Qpg[k] = 0.0;
     }
-    BhSurf BSm, BSp;
+    BhStaged BG;
+    BG.base = H.bhsurf; BG.zmax = H.bhsurf; BG.desc = reinterpret_cast<const int*>(H.bhsurf + 2);
     if (A.had && C.F.bh_e) {
-        double* p2 = bh_stage(BSm, A.BSm, H.bhsurf, NT_LH);
-        bh_stage(BSp, A.BSp, p2, NT_LH);
+        BhSurf tmp;
+        int* desc = reinterpret_cast<int*>(H.bhsurf + 2);
+        double* p2 = bh_stage(tmp, A.BSm, H.bhsurf + 2 + BH_DESC_INTS, NT_LH, H.bhsurf, desc, H.bhsurf);
+        bh_stage(tmp, A.BSp, p2, NT_LH, H.bhsurf, desc + BH_DESC_INTS, H.bhsurf + 1);
         if (tid == 0) simpson_weights_irregular(C.T + L.lgp, Np, H.bhw);      // made visible by ic_prepare's barrier
     }
     ic_prepare<NT_LH>(C, S);
@@ -206,7 +209,7 @@ __global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
         LHM_TICK(1);
         phase_protons<NT_LH>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
         LHM_TICK(2);
-        if (C.F.bh_e) phase_bh_emis<NT_LH>(C, S, H, BSm, BSp);
+        if (C.F.bh_e) phase_bh_emis<NT_LH>(C, S, H, BG);
         LHM_TICK(3);
         if (C.F.pg_e) phase_photopion<NT_LH>(C, S, H, A.HT);
         else if (A.had) { for (int k = tid; k < 52; k += NT_LH) H.Qnu[k] = 0.0; }
@@ -788,7 +791,7 @@ int lhm_set_bh_surfaces(lhm_handle* h, const lhm_bh_surface* sm, const lhm_bh_su
     if (sm->nx < 8 || sm->ny < 8 || sp->nx < 8 || sp->ny < 8 || !sm->tx || !sm->ty || !sm->c || !sp->tx || !sp->ty || !sp->c)
         return LHM_ERR_ARG;
     const size_t need = (size_t)4 * (sm->nx + sm->ny) + (size_t)(sm->nx - 4) * (sm->ny - 4) + 4 * (sp->nx + sp->ny)
-                        + (size_t)(sp->nx - 4) * (sp->ny - 4);          // knots + reciprocal tables + coefficients
+                        + (size_t)(sp->nx - 4) * (sp->ny - 4) + 2 + BH_DESC_INTS;   // knots + reciprocal tables + coefficients + descriptor
     if (need > (size_t)BH_MAXSURF) return LHM_ERR_CAPACITY;
     CUDA_TRY(cudaSetDevice(h->device));
     int rc = had_init();

@@ -384,6 +384,16 @@ struct BhSurf {            // one tck of bisplrep with kx = ky = 3 (pointers to 
     const double *rx, *ry; // [3][n]: 1/(t[i] - t[i-j]), j = 1..3 -- the denominators of the de Boor recurrence, built by
                            // bh_stage (null: divide)
 };
+// What bh_pair reads of a staged surface: offsets (in doubles, from the start of the staging area) of tx, ty, c, rx, ry,
+// then nx, ny; zmax follows as a double.  Lives in shared memory: a pair picks one of the two surfaces at run time, and
+// selecting between two structs by address would push both into local memory (it did: 1.9 G local-load sectors per
+// Test-4 launch).
+constexpr int BH_DESC_INTS = 8;                        // 7 used
+struct BhStaged {
+    const double* base;                                // staging area (shared memory)
+    const int* desc;                                   // [2][BH_DESC_INTS]: surface "m" (gp < ge), surface "p" (gp > ge)
+    const double* zmax;                                // [2]
+};
 
 // FITPACK fpbspl: the 4 non-zero cubic B-splines at x in the knot interval l (t[l] <= x < t[l+1])
 __device__ __forceinline__ void bh_fpbspl(const double* __restrict__ t, double x, int l, double* h) {
@@ -492,7 +502,7 @@ __device__ void simpson_weights_irregular(const double* x, int N, double* W) {
 // g_pr_int of one (gamma_e, gamma_p) pair (LeHaMoC_f.py:571-610), one thread.
 // xt [Nt] = h nu/(m_e c^2) ascending, lph [Nt] = log10(photons)
 __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double* __restrict__ xt,
-                          const double* __restrict__ lph, const BhSurf& Sm, const BhSurf& Sp) {
+                          const double* __restrict__ lph, const BhStaged& G) {
     const HadConst& K = kHC;
     const double LN10 = 2.302585092994045684;
     const double Emin = (gp + ge) * (gp + ge) / (4. * (gp * gp) * ge);
@@ -500,12 +510,22 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
     if (!(Emin < Emax)) return 0.0;
     const double Ee_min = (gp * gp + ge * ge) / (2 * gp * ge);
     const double wmin = (gp + ge) * (gp + ge) / (2 * gp * ge);
-    const BhSurf* Sf = (gp > ge) ? &Sp : (gp < ge) ? &Sm : nullptr;
+    const bool have = (gp != ge);                           // gp == ge: neither surface applies (LeHaMoC_f.py:586-591)
+    const int which = (gp > ge) ? 1 : 0;
+    const int* D = G.desc + which * BH_DESC_INTS;
+    const double* __restrict__ ty = G.base + D[1];
+    const double* __restrict__ cc = G.base + D[2];
+    const double* __restrict__ ry = G.base + D[4];
+    const int ny = D[6], nky1 = ny - 4;
+    const double zmax = G.zmax[which];
+    const double tb = ty[3], te = ty[ny - 4];
     double hx[4]; int lx = 0;
-    if (Sf) {
+    if (have) {
+        const double* __restrict__ tx = G.base + D[0];
+        const int nx = D[5];
         double ax = log10(Ee_min);
-        lx = bh_interval(Sf->tx, Sf->nx, ax);
-        if (Sf->rx) bh_fpbspl_r(Sf->tx, Sf->rx, Sf->nx, ax, lx, hx); else bh_fpbspl(Sf->tx, ax, lx, hx);
+        lx = bh_interval(tx, nx, ax);
+        bh_fpbspl_r(tx, G.base + D[3], nx, ax, lx, hx);
     }
     const double ea = log10(1.001 * Emin), eb = log10(Emax);
     // Both inner integrals are scipy.integrate.simpson over 10 samples of a np.logspace grid, i.e. over abscissae
@@ -530,25 +550,20 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
             for (int q = 0; q < 10; ++q) {
                 const double Ee_max = w - 1;
                 double res = 0.0;
-                if (Sf && Ee_min < Ee_max && Ee_min < 80. / 100. * Ee_max) {
+                if (have && Ee_min < Ee_max && Ee_min < 80. / 100. * Ee_max) {
                     double ay = log10(Ee_max);
-                    {                                // bh_interval, resumed from the previous sample's interval
-                        const double tb = Sf->ty[3], te = Sf->ty[Sf->ny - 4];
-                        if (ay < tb) ay = tb;
-                        if (ay > te) ay = te;
-                        while (!(ay < Sf->ty[ly + 1]) && ly != Sf->ny - 5) ++ly;
-                    }
+                    ay = fmin(fmax(ay, tb), te);     // bh_interval, resumed from the previous sample's interval
+                    while (!(ay < ty[ly + 1]) && ly != ny - 5) ++ly;
                     double hy[4];
-                    if (Sf->ry) bh_fpbspl_r(Sf->ty, Sf->ry, Sf->ny, ay, ly, hy); else bh_fpbspl(Sf->ty, ay, ly, hy);
-                    const int nky1 = Sf->ny - 4;
+                    bh_fpbspl_r(ty, ry, ny, ay, ly, hy);
                     double sp = 0.0;
 #pragma unroll
                     for (int a = 0; a < 4; ++a) {
-                        const double* cr = Sf->c + (size_t)(lx - 3 + a) * nky1 + (ly - 3);
+                        const double* cr = cc + (lx - 3 + a) * nky1 + (ly - 3);
 #pragma unroll
                         for (int b = 0; b < 4; ++b) sp = sp + cr[b] * hx[a] * hy[b];
                     }
-                    if (sp > Sf->zmax) sp = 0.;
+                    if (sp > zmax) sp = 0.;
                     res = w * exp10(sp);
                 }
                 accw = fma(SW[q], res * w, accw);
@@ -575,11 +590,13 @@ struct BhArgs {
 
 __host__ __device__ inline size_t bh_smem_doubles(int Nt, int Np, const BhSurf& a, const BhSurf& b) {
     return (size_t)2 * Nt + 4 * Np + BH_CH * Np + 4 * (a.nx + a.ny) + (size_t)(a.nx - 4) * (a.ny - 4) + 4 * (b.nx + b.ny) +
-           (size_t)(b.nx - 4) * (b.ny - 4) + 8;
+           (size_t)(b.nx - 4) * (b.ny - 4) + 8 + 2 + BH_DESC_INTS;
 }
 
-// stage a surface into shared memory (all threads; no barrier)
-__device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, int nthreads) {
+// stage a surface into shared memory (all threads; no barrier); `area` = start of the staging area, `desc`/`zmax` = this
+// surface's slot of the BhStaged descriptor
+__device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, int nthreads, const double* area = nullptr,
+                                   int* desc = nullptr, double* zmax = nullptr) {
     const int nc = (src.nx - 4) * (src.ny - 4);
     double* tx = sm; double* ty = tx + src.nx; double* cc = ty + src.ny;
     double* rx = cc + nc; double* ry = rx + 3 * src.nx;
@@ -595,18 +612,23 @@ __device__ inline double* bh_stage(BhSurf& dst, const BhSurf& src, double* sm, i
         ry[k] = (i >= j) ? 1.0 / (src.ty[i] - src.ty[i - j]) : 0.0;
     }
     dst = src; dst.tx = tx; dst.ty = ty; dst.c = cc; dst.rx = rx; dst.ry = ry;
+    if (desc && threadIdx.x == 0) {
+        desc[0] = (int)(tx - area); desc[1] = (int)(ty - area); desc[2] = (int)(cc - area); desc[3] = (int)(rx - area);
+        desc[4] = (int)(ry - area); desc[5] = src.nx; desc[6] = src.ny; desc[7] = 0;
+        *zmax = src.zmax;
+    }
     return ry + 3 * src.ny;
 }
 
 // Q_BH_sol for the gamma_e range [i0, i1) of one walker by the whole CTA: buf [BH_CH][Np] scratch, gp/np_ [Np] staged,
 // Wp [Np] = Simpson weights over ln(g_pr) (simpson_weights_irregular)
 __device__ void bh_chunk(int i0, int i1, int Np, int Nt, const double* ge_arr, const double* gp, const double* Wp,
-                         const double* np_, const double* xt, const double* lph, const BhSurf& Sm, const BhSurf& Sp,
+                         const double* np_, const double* xt, const double* lph, const BhStaged& G,
                          double* buf, double* out, int nthreads) {
     const int n = (i1 - i0) * Np;
     for (int e = threadIdx.x; e < n; e += nthreads) {
         const int ii = e / Np, j = e - ii * Np;
-        buf[e] = bh_pair(ge_arr[i0 + ii], gp[j], np_[j], Nt, xt, lph, Sm, Sp) * gp[j];      // g_pr_int * g_pr
+        buf[e] = bh_pair(ge_arr[i0 + ii], gp[j], np_[j], Nt, xt, lph, G) * gp[j];            // g_pr_int * g_pr
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -627,8 +649,11 @@ __global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
     double* Wp = np_ + Np;
     double* buf = Wp + Np;
     BhSurf Sm, Sp;
-    double* p = bh_stage(Sm, A.Sm, buf + (size_t)BH_CH * Np, HAD_NT);
-    bh_stage(Sp, A.Sp, p, HAD_NT);
+    double* area = buf + (size_t)BH_CH * Np;
+    double* zm = area; int* desc = reinterpret_cast<int*>(area + 2);           // [2] zmax, [2][BH_DESC_INTS] ints
+    double* p = bh_stage(Sm, A.Sm, area + 2 + BH_DESC_INTS, HAD_NT, area, desc, zm);
+    bh_stage(Sp, A.Sp, p, HAD_NT, area, desc + BH_DESC_INTS, zm + 1);
+    BhStaged G; G.base = area; G.desc = desc; G.zmax = zm;
     for (int k = tid; k < Nt; k += HAD_NT) { xt[k] = A.xt[(size_t)w * Nt + k]; lph[k] = log10(A.photons[(size_t)w * Nt + k]); }
     for (int k = tid; k < Np; k += HAD_NT) {
         const double g = A.g_pr[(size_t)w * Np + k];
@@ -639,7 +664,7 @@ __global__ void __launch_bounds__(HAD_NT) had_bh_kernel(BhArgs A) {
     __syncthreads();
     const int i0 = chunk * BH_CH, i1 = min(i0 + BH_CH, A.Ng);
     if (i0 < A.Ng)
-        bh_chunk(i0, i1, Np, Nt, A.g_el + (size_t)w * A.Ng, gp, Wp, np_, xt, lph, Sm, Sp, buf, A.out + (size_t)w * A.Ng, HAD_NT);
+        bh_chunk(i0, i1, Np, Nt, A.g_el + (size_t)w * A.Ng, gp, Wp, np_, xt, lph, G, buf, A.out + (size_t)w * A.Ng, HAD_NT);
 }
 
 }  // namespace lhm

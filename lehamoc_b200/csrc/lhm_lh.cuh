@@ -393,12 +393,12 @@ __device__ void phase_pp(const Ctx& C, Smem& S, SmemLh& H, double n_H, double p_
 
 // Bethe-Heitler pair injection Q_BH_sol(g_el, g_pr, dN_pr/dV, h nu_tot/mc2, photons, ...)[1:-1], LeHaMoC.py:337-340
 template <int NT>
-__device__ void phase_bh_emis(const Ctx& C, Smem& S, SmemLh& H, const BhSurf& Sm, const BhSurf& Sp) {
+__device__ void phase_bh_emis(const Ctx& C, Smem& S, SmemLh& H, const BhStaged& G) {
     const Layout& L = C.L;
     for (int j = threadIdx.x; j < L.Np; j += NT) H.npl[j] = H.Npr[j] / C.V;
     __syncthreads();
     for (int i0 = 0; i0 < L.Ng; i0 += BH_CH)
-        bh_chunk(i0, min(i0 + BH_CH, L.Ng), L.Np, L.Nt, S.gS, C.T + L.gp, H.bhw, H.npl, C.T + L.xt, S.Ln, Sm, Sp,
+        bh_chunk(i0, min(i0 + BH_CH, L.Ng), L.Np, L.Nt, S.gS, C.T + L.gp, H.bhw, H.npl, C.T + L.xt, S.Ln, G,
                  H.bhbuf, H.Qbh, NT);
 }
 
