@@ -18,6 +18,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--walkers", type=int, default=296)
 ap.add_argument("--grids", type=int, nargs="+", default=[100, 200, 400, 800])
 ap.add_argument("--check", type=int, default=0, help="grid size at which walker 0 is compared with the CPU oracle")
+ap.add_argument("--phases", action="store_true", help="per-phase cycle breakdown of thread 0 (run_lh_kernel counters)")
 a = ap.parse_args()
 z = np.load(os.path.join(ROOT, "tests", "golden", "lh_bbpl.npz"))
 BASE = dict(zip([str(k) for k in z["param_keys"]], [float(v) for v in z["param_vals"]]))
@@ -50,6 +51,18 @@ for grid in a.grids:
     ms = float(np.median(ts))
     print(f"grid {grid:4d}: {ms:9.2f} ms per {a.walkers} models x 10 steps = {1e3 * ms / a.walkers:8.1f} us per model "
           f"({a.walkers / (ms * 1e-3):9.0f} model-evals/s; smem {eng.smem_bytes() / 1024:.0f} KB/CTA; host packing {pack_s:.2f} s)")
+    if a.phases:
+        import ctypes as C
+        prof = torch.zeros(16, dtype=torch.int64, device="cuda")
+        eng.lib.lhm_set_phase_profile(eng.h, C.c_void_p(prof.data_ptr()))
+        eng.setup(b)
+        eng.run_lh()
+        torch.cuda.synchronize()
+        eng.lib.lhm_set_phase_profile(eng.h, None)
+        p = prof.cpu().numpy().astype(float)
+        names = ["loop/out", "photons+uph", "protons", "bh_emis", "photopion", "pp", "electrons+syn rows", "ic",
+                 "photon solves", "gg"]
+        print("          cycles per walker-step: " + ", ".join(f"{n_} {v / a.walkers / 10:.0f}" for n_, v in zip(names, p) if v > 0))
     if a.check == grid:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import lehamoc_oracle_lh as olh
