@@ -30,6 +30,7 @@ def main():
     ap.add_argument("--reps", type=int, default=10)
     ap.add_argument("--ic-path", default="R")
     ap.add_argument("--host-pack", action="store_true", help="NumPy set-up on the host instead of lhm_pack_batch")
+    ap.add_argument("--mcmc", type=int, default=0, help="also run this many ensemble iterations of fit.run_mcmc")
     ap.add_argument("--flag-c", default="LeMoC", choices=["LeMoC", "LeHaMoC"],
                     help="numerical model of the fit (fit_emcee.py:23): SSC or SSC + proton synchrotron")
     a = ap.parse_args()
@@ -63,19 +64,30 @@ def main():
         tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         dt = float(tmax.item())
-        if rank != 0:
-            dist.destroy_process_group()
-            return
-    # where the time goes: host packing alone, and the GPU kernels alone
-    t1 = time.perf_counter()
-    for th in calls[2:]:
-        b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
-    pack = (time.perf_counter() - t1) / a.reps
-    su, co, ru = ev.eng.last_timings()
-    print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up: "
-          f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
-          f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
-          f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
+    if rank == 0:
+        # where the time goes: host packing alone, and the GPU kernels alone
+        t1 = time.perf_counter()
+        for th in calls[2:]:
+            b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
+        pack = (time.perf_counter() - t1) / a.reps
+        su, co, ru = ev.eng.last_timings()
+        print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up: "
+              f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
+              f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
+              f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
+    if a.mcmc:
+        # the whole sampler loop (stretch move on the host, two half-ensemble evaluations per iteration on the GPU)
+        pos = init + 1e-2 * rng.standard_normal((a.walkers, len(init)))
+        fit.run_mcmc(logp, pos, 2, seed=1)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res = fit.run_mcmc(logp, pos, a.mcmc, seed=2)
+        torch.cuda.synchronize()
+        dtm = time.perf_counter() - t0
+        if rank == 0:
+            print(f"run_mcmc: {a.walkers} walkers x {a.mcmc} iterations in {dtm:.2f} s = {a.mcmc / dtm:.1f} iterations/s = "
+                  f"{a.walkers * a.mcmc / dtm:.0f} model evaluations/s; acceptance {res['acceptance_fraction'].mean():.2f}; "
+                  f"max log-prob {res['log_prob'].max():.2f}")
     if world > 1:
         dist.destroy_process_group()
 
