@@ -2,9 +2,9 @@
 """bench.py -- model-evals/s of the Test-1 SSC model (LeMoC/Parameters_Test1.txt evolved for its 10 timesteps)
 on N B200s, one process per GPU.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--walkers 1024] [--ic-path R|S] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--walkers 1184] [--ic-path R|S] [--impl reference]
 
-A "step" is one pass of the hot path over one batch: every walker of the batch (default 1024 per GPU)
+A "step" is one pass of the hot path over one batch: every walker of the batch (default 1184 per GPU = 4 waves of 148 SMs x 2 CTAs)
 is evolved from its initial condition through all timesteps (set-up tables + cor-factor + fused step kernel).
 Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for the flop accounting.
 """
