@@ -325,7 +325,9 @@ __device__ void pion_eval(const PionIn& I, double* work, double* out, double sca
                 // y with the tabulated 1/(x_+ - x_-): 4 ln + 2 exp instead of 2 pow + 2 ln + 1 exp + 3 divisions
                 // (relative deviation from the pow form < 1e-13, far inside the parity tolerance)
                 const double y = (x - xm) * Erinv[e];
-                const double L = (lEo - lgm[gi]) - Elxm[e];
+                double L = (lEo - lgm[gi]) - Elxm[e];
+                if (L < 0.0) L = 0.0;        // last-bit case of the tabulated difference for x barely above x_-; a NaN
+                                             // (x_- <= 0 next to the threshold) stays a NaN, as in the reference
                 const double t1 = exp(Ed[e] * log(L));
                 const double L2 = log(0.693147180559945309417 - log1p(y * y));
                 Phi = EB[e] * exp(fma(Epsi[e], L2, -Es[e] * t1));
