@@ -860,15 +860,22 @@ __device__ void pp_product(int product, int Nout, const double* Es, int Np, cons
         if (k < Nout) out[k] = pp_value(product, Es[k], Np, Ep_grid, p_pr, n_H, lEg, lN, u1);
         ni += __syncthreads_count(u1 ? 1 : 0);
     }
-    if (ni >= 1 && ni + 1 < Nout) {
-        const double x0 = log10(Es[ni]), x1 = log10(Es[ni + 1]), y0 = log10(out[ni]), y1 = log10(out[ni + 1]);
-        // scipy.stats.linregress on two points: slope = ssxym/ssxm with biased second moments about the means
-        const double xm = (x0 + x1) / 2., ym = (y0 + y1) / 2.;
-        const double ssxm = ((x0 - xm) * (x0 - xm) + (x1 - xm) * (x1 - xm)) / 2.;
-        const double ssxym = ((x0 - xm) * (y0 - ym) + (x1 - xm) * (y1 - ym)) / 2.;
-        const double slope = ssxym / ssxm, intercept = ym - slope * xm;
-        const double y_fit = exp10(slope * log10(Es[ni - 1]) + intercept);
-        const double norm = y_fit / out[ni - 1];
+    if (ni >= 1) {
+        double norm;
+        if (ni + 1 < Nout) {
+            const double x0 = log10(Es[ni]), x1 = log10(Es[ni + 1]), y0 = log10(out[ni]), y1 = log10(out[ni + 1]);
+            // scipy.stats.linregress on two points: slope = ssxym/ssxm with biased second moments about the means
+            const double xm = (x0 + x1) / 2., ym = (y0 + y1) / 2.;
+            const double ssxm = ((x0 - xm) * (x0 - xm) + (x1 - xm) * (x1 - xm)) / 2.;
+            const double ssxym = ((x0 - xm) * (y0 - ym) + (x1 - xm) * (y1 - ym)) / 2.;
+            const double slope = ssxym / ssxm, intercept = ym - slope * xm;
+            const double y_fit = exp10(slope * log10(Es[ni - 1]) + intercept);
+            norm = y_fit / out[ni - 1];
+        } else {
+            // fewer than two energies above the delta-function range (a grid that does not reach 0.1 TeV): SciPy >= 1.10
+            // returns NaN from linregress on a one-point sample, and the reference multiplies the low-energy part by it
+            norm = nan("");
+        }
         __syncthreads();
         for (int k = threadIdx.x; k < ni; k += nthreads) out[k] = norm * out[k];
     }

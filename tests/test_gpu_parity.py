@@ -448,3 +448,50 @@ def test_engines_of_different_size_coexist():
     _, Nb2, sedb2 = LeMoC.run(dict(P, grid_g_el=400., grid_nu=200., time_end=2.), snapshots=False)
     np.testing.assert_array_equal(sedb.cpu().numpy(), sedb2[:, 0])
     assert np.isfinite(Ns.cpu().numpy()[:, 1:-1]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_random_flag_combinations_vs_oracle(orc, seed):
+    """Randomly drawn switches, grids, step sizes and physical parameters on small grids: every step of the CUDA path
+    against the oracle (itself pinned on the live reference for each of these branches)."""
+    from lehamoc_b200 import LeMoC
+    _, P = load_golden("test1")
+    rng = np.random.default_rng(1000 + seed)
+    flag = lambda p=0.5: float(rng.random() < p)
+    gmax = float(rng.uniform(4.5, 6.5))
+    Q = dict(P, grid_g_el=float(rng.integers(24, 45) * 2), grid_nu=float(rng.integers(30, 70)),
+             time_end=float(rng.integers(2, 5)), step_alg=float(rng.choice([0.5, 1., 2., 3.])),
+             g_min_el=0., g_max_el=gmax, g_PL_min=float(rng.choice([0., rng.uniform(0.5, 2.5)])),
+             g_PL_max=float(rng.choice([gmax, rng.uniform(3.5, gmax - 0.2)])),
+             p_el=float(rng.choice([2., rng.uniform(1.5, 3.)])), L_el=float(rng.uniform(39., 44.)),
+             R0=float(rng.uniform(14., 16.5)), B0=float(10 ** rng.uniform(-2, 1.5)),
+             Vexp=float(rng.choice([1e-13, rng.uniform(0.01, 0.3)])), m=float(rng.choice([0., 1., 2.])),
+             inj_flag=flag(0.7), Ad_l_flag=flag(), Syn_l_flag=flag(0.8), Syn_emis_flag=flag(0.8), IC_l_flag=flag(0.7),
+             IC_emis_flag=flag(0.7), SSA_l_flag=flag(), gg_flag=flag(), esc_flag=flag(0.7), BB_flag=flag(0.3),
+             BB_temperature=float(rng.uniform(3., 6.)), GB_ext=float(10 ** rng.uniform(-4, 0)))
+    ge, ne_ref, sed_ref = orc.run_script(Q)
+    for path in ("R", "S"):
+        batch, N, sed = LeMoC.run(Q, ic_path=path)
+        assert N.shape[1] == len(ne_ref), (seed, path)
+        # path S: the suffix sums cancel in bins that only hold the 1e-260 start-up photons, so bins more than 200 decades
+        # below the peak agree to ~1e-4 there instead of 1e-6 (every other bin to the same 1e-8 as path R)
+        tf = 1e-6 if path == "R" else 1e-3
+        for s in range(len(ne_ref)):
+            assert_spectra_close(N[0, s], ne_ref[s], f"seed {seed} path {path} n_e step {s + 1}: {Q}", tol_floor=tf)
+            assert_spectra_close(sed[0, s], sed_ref[s], f"seed {seed} path {path} nuLnu step {s + 1}: {Q}", tol_floor=tf)
+
+
+@pytest.mark.gpu
+def test_full_size_linearity_without_feedback():
+    """Size-independent property at the Test-1 grid size: with inverse-Compton, gamma-gamma and self-absorption off
+    nothing feeds back on the electrons, so doubling the injected luminosity doubles every bin of both spectra."""
+    from lehamoc_b200 import LeMoC
+    _, P = load_golden("test1")
+    base = dict(P, IC_l_flag=0., IC_emis_flag=0., gg_flag=0., SSA_l_flag=0.)
+    two = dict(base, L_el=P["L_el"] + np.log10(2.))
+    _, N, sed = LeMoC.run([base, two], snapshots=False)
+    inner = slice(1, -1)                                  # the boundary bins hold the 1e-260 sentinels
+    np.testing.assert_allclose(N[1, 0][inner] / N[0, 0][inner], 2.0, rtol=1e-12)
+    big = sed[0, 0] > sed[0, 0].max() * 1e-60            # below: bins that still hold the 1e-260 initial photons
+    np.testing.assert_allclose(sed[1, 0][big] / sed[0, 0][big], 2.0, rtol=1e-12)

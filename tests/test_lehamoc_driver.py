@@ -22,6 +22,8 @@ def log_close(got, ref_log, what, tol=4.3e-9, floor_decades=200., tol_floor=1e-6
     ninf = np.isneginf(ref_log)
     assert np.all(lg[ninf] < tiny), f"{what}: zeros of the reference are not (near-)zeros here"
     assert np.all(ref_log[np.isneginf(lg)] < tiny), f"{what}: zeros where the reference has values"
+    # NaNs flow through like in the reference (e.g. the pp low-energy matching on a too short energy range)
+    assert np.array_equal(np.isnan(lg), np.isnan(ref_log)), f"{what}: NaN pattern differs from the reference's"
     ok = ~ninf & ~np.isnan(ref_log) & ~np.isneginf(lg)
     assert np.all(np.isfinite(lg[ok])), what
     peak = np.max(np.where(ok, ref_log, -np.inf), axis=-1, keepdims=True)
@@ -220,3 +222,49 @@ def test_gpu_lehamoc_pp_run(name):
     log_close(Npr[0], z["n_p"], f"{name} n_p")
     log_close(Nnu[0], z["N_nu"], f"{name} N_nu")
     assert np.any(Nnu[0, -1] > 0)
+
+
+def _random_lh_params(seed):
+    _, P = load_golden("lh_shipped")
+    rng = np.random.default_rng(2000 + seed)
+    flag = lambda p=0.5: float(rng.random() < p)
+    ge_max, gp_max = float(rng.uniform(4.5, 7.)), float(rng.uniform(5., 9.))
+    pp = flag(0.5)
+    Q = dict(P, grid_g_el=float(rng.integers(20, 40) * 2), grid_g_pr=float(rng.integers(20, 50)),
+             grid_nu=float(rng.integers(30, 70)), time_end=float(rng.integers(2, 5)) * 2., step_alg=2.,
+             PL_inj=flag(0.6), g_max_el=ge_max, g_el_PL_min=float(rng.choice([0., rng.uniform(0.5, 2.)])),
+             g_el_PL_max=float(rng.uniform(3., ge_max - 0.3)), g_max_pr=gp_max,
+             g_pr_PL_min=float(rng.choice([0., rng.uniform(0.3, 1.5)])), g_pr_PL_max=float(rng.uniform(3.5, gp_max - 0.3)),
+             p_el=float(rng.uniform(1.6, 2.8)), p_pr=float(rng.choice([2., 2.5, rng.uniform(1.7, 2.8)])),
+             L_el=float(rng.uniform(40., 44.)), L_pr=float(rng.uniform(42., 47.)), R0=float(rng.uniform(14.5, 16.5)),
+             B0=float(10 ** rng.uniform(-1.5, 1.5)), Vexp=float(rng.choice([1e-13, rng.uniform(0.02, 0.3)])),
+             m=float(rng.choice([0., 1.])), inj_flag=flag(0.7), Ad_l_flag=flag(), Syn_l_flag=flag(0.8),
+             Syn_emis_flag=flag(0.8), IC_l_flag=flag(0.7), IC_emis_flag=flag(0.7), SSA_l_flag=flag(), gg_flag=flag(),
+             esc_flag_el=flag(0.7), esc_flag_pr=flag(0.7), BB_flag=flag(0.3), temperature=float(rng.uniform(3., 6.)),
+             GB_ext=float(10 ** rng.uniform(-4, 0)), PL_flag=flag(0.3), dE_dV_ph=float(10 ** rng.uniform(-5, -1)),
+             nu_min_ph=12., nu_max_ph=16., s_ph=float(rng.uniform(1.5, 2.5)),
+             n_H=float(10 ** rng.uniform(2, 8)) if pp else 0., pp_l_flag=pp * flag(0.7), pp_ee_emis_flag=pp * flag(0.7),
+             pp_g_emis_flag=pp * flag(0.7), pp_nu_emis_flag=pp * flag(0.7))
+    return Q
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", range(24))
+def test_gpu_random_lehamoc_configurations_vs_oracle(seed):
+    """Randomly drawn switches (leptonic processes, proton synchrotron, pp channels, external fields, expansion), grids
+    and parameters of the LeHaMoC.py driver on small grids: every step against the oracle restatement, which is pinned
+    on the unmodified script for each of these branches (tests above).  Photopion / Bethe-Heitler stay with the
+    fixtures: their oracle needs minutes per run."""
+    from lehamoc_b200 import LeHaMoC
+    Q = _random_lh_params(seed)
+    run = olh.LeptoHadronicRun(Q)
+    with np.errstate(all="ignore"):
+        ne, sed, n_p, N_nu = run.run()
+    for path in ("R", "S"):
+        tf = 1e-6 if path == "R" else 1e-3
+        batch, N, s_, Npr, Nnu = LeHaMoC.run(Q, ic_path=path)
+        log_close(N[0], np.log10(ne), f"seed {seed} {path} n_e {Q}", tol_floor=tf)
+        log_close(s_[0], np.log10(sed), f"seed {seed} {path} nuLnu {Q}", tol_floor=tf)
+        log_close(Npr[0], np.log10(n_p), f"seed {seed} {path} n_p {Q}", tol_floor=tf)
+        if Q["pp_nu_emis_flag"]:
+            log_close(Nnu[0], np.log10(N_nu), f"seed {seed} {path} N_nu {Q}", tol_floor=tf)

@@ -30,6 +30,7 @@ def assert_spectra_close(got, ref, what="", tol=TOL_LOG10, tol_floor=TOL_LOG10_F
     assert got.shape == ref.shape, f"{what}: shape {got.shape} vs {ref.shape}"
     with np.errstate(divide="ignore", invalid="ignore"):
         lg, lr = np.log10(got), np.log10(ref)
+    assert np.array_equal(np.isnan(got), np.isnan(ref)), f"{what}: NaN pattern differs from the reference's"
     zero = ref == 0
     assert np.array_equal(got[zero], ref[zero]), f"{what}: exact zeros of the reference not reproduced"
     pos = ref > 0
