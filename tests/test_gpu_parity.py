@@ -495,3 +495,33 @@ def test_full_size_linearity_without_feedback():
     np.testing.assert_allclose(N[1, 0][inner] / N[0, 0][inner], 2.0, rtol=1e-12)
     big = sed[0, 0] > sed[0, 0].max() * 1e-60            # below: bins that still hold the 1e-260 initial photons
     np.testing.assert_allclose(sed[1, 0][big] / sed[0, 0][big], 2.0, rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_random_fit_walkers_vs_oracle(orc):
+    """Walkers drawn over the whole prior box of the fit (fit_emcee.py:173-188) in one launch, both numerical models
+    (Code.LeMoC: per-walker gamma grids; Code.LeHaMoC: + protons), each against its own oracle run."""
+    from lehamoc_b200 import Code
+    _, P = load_golden("code_fit")
+    rng = np.random.default_rng(4242)
+    lo = np.array([14.2, -1.8, 0.2, 5.1, -5.8, 1.6])
+    hi = np.array([16.8, 1.8, 4.3, 6.9, -2.2, 2.9])
+    th = lo + (hi - lo) * rng.random((12, 6))
+    th[3, 5] = 2.0
+    nu, sed = Code.LeMoC_batch(th, P)
+    nuS, sedS = Code.LeMoC_batch(th, P, ic_path="S")
+    for i in range(len(th)):
+        nu_ref, sed_ref = orc.code_LeMoC(th[i], P)
+        np.testing.assert_array_equal(nu[i], nu_ref)
+        assert_spectra_close(sed[i], sed_ref, f"Code.LeMoC random walker {i} {th[i]}")
+        assert_spectra_close(sedS[i], sed_ref, f"Code.LeMoC random walker {i} path S {th[i]}", tol_floor=1e-3)
+    _, P2 = load_golden("code_lh_fit")
+    lo2 = np.array([14.2, -0.8, 0.2, 4.1, -4.8, 1.2, 0.2, 6.2, -4.8, 1.2])
+    hi2 = np.array([16.8, 2.8, 2.8, 5.9, -0.5, 2.9, 4.5, 9.5, -0.5, 2.9])
+    th2 = lo2 + (hi2 - lo2) * rng.random((8, 10))
+    th2[2, 9] = 2.0
+    nu2, sed2 = Code.LeHaMoC_batch(th2, P2)
+    for i in range(len(th2)):
+        nu_ref, sed_ref = orc.code_LeHaMoC(th2[i], P2)
+        np.testing.assert_array_equal(nu2[i], nu_ref)
+        assert_spectra_close(sed2[i], sed_ref, f"Code.LeHaMoC random walker {i} {th2[i]}")
