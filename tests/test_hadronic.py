@@ -190,3 +190,46 @@ def test_gpu_pp_batch_equals_single(gold_pp):
     both = had.Q_nu_mu_pp(np.stack([g["nu_nu"]] * 2), gp, NT, np.array([2.01, 2.5]), np.array([1.5, 1.5]))
     for c, p in ((0, 2.01), (1, 2.5)):
         np.testing.assert_array_equal(both[c], had.Q_nu_mu_pp(g["nu_nu"], gp[c], NT[c], p, 1.5))
+
+
+def _random_fields(seed):
+    """Same construction as oracle/make_golden_had.py::fields (photon field with a synchrotron bump and a sentinel-level
+    tail, cut-off power-law protons), other seeds, plus pp inputs."""
+    rng = np.random.default_rng(seed)
+    nu = np.logspace(7.5, 32., int(rng.integers(50, 90)))
+    l = np.log10(nu)
+    a1, a2 = rng.uniform(0.4, 0.9), rng.uniform(0.3, 0.8)
+    logn = rng.uniform(2., 6.) - 1.5 * (l - 12.) - a1 * np.maximum(l - rng.uniform(14., 17.), 0.) ** 1.5 + 0.3 * np.sin(a2 * l)
+    photons = 10 ** logn
+    photons[-3:] = 10 ** (-260.)
+    g_pr = np.logspace(0., rng.uniform(7., 8.5), int(rng.integers(25, 45)))
+    p = rng.uniform(1.7, 2.4)
+    N_pr = 10 ** rng.uniform(-2., 2.) * g_pr ** (-p) * np.exp(-g_pr / g_pr[-4])
+    N_pr[0] = N_pr[-1] = 10 ** (-260.)
+    g_el = np.logspace(0., rng.uniform(9., 11.), int(rng.integers(16, 30)))
+    nu_ic = np.logspace(15., 32., int(rng.integers(12, 24)))
+    return nu, photons, g_pr, N_pr, g_el, nu_ic, float(p)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("seed", [301, 302, 303])
+def test_gpu_hadronic_functions_random_inputs_vs_oracle(gold, seed):
+    """Other photon fields, proton distributions and grid sizes than the fixtures: the device functions against the
+    oracle restatement (pinned on the live reference functions by the tests above)."""
+    had = _load(gold)
+    T = tables_of(gold)
+    nu, photons, g_pr, N_pr, g_el, nu_ic, p = _random_fields(seed)
+    rel_close(had.dg_dt_BH(g_pr, nu, photons), oh.dg_dt_BH(g_pr, nu, photons, T), 1e-8, f"dg_dt_BH seed {seed}")
+    rel_close(had.dg_dt_pg(g_pr, nu, photons), oh.dg_dt_pg(g_pr, nu, photons, T), 1e-8, f"dg_dt_pg seed {seed}")
+    for sp in ("2_g", "e+", "\bar_nu_e"):
+        rel_close(had.Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons, nu, sp), oh.Qp_g_opt(g_el, nu_ic, N_pr, g_pr, photons, nu, sp, T),
+                  1e-8, f"Qp_g_opt {sp!r} seed {seed}")
+    NT = N_pr / (oh.m_pr * oh.c ** 2. * 0.624151)
+    nu_nu = oh.E_NU_SPACE / oh.h
+    with np.errstate(all="ignore"):
+        for name, grid in (("Q_e_pp", g_el), ("Q_g_pp", nu_ic), ("Q_nu_mu_pp", nu_nu), ("Q_nu_e_pp", nu_nu)):
+            ref = np.array(getattr(oh, name)(grid, g_pr, NT, p, 7.5), dtype=np.float64)
+            got = getattr(had, name)(grid, g_pr, NT, p, 7.5)
+            assert np.array_equal(np.isnan(got), np.isnan(ref)), (name, seed)
+            ok = ~np.isnan(ref)
+            rel_close(got[ok], ref[ok], 1e-8, f"{name} seed {seed}")
