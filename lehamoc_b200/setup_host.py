@@ -338,12 +338,9 @@ def _Q_pr_Lum(L_pr, p_pr, g_min_pr, g_max_pr):           # LeHaMoC_f.py:75-79
     return L_pr * (-p_pr + 2.) / (m_pr_ * c ** 2. * (g_max_pr ** (-p_pr + 2.) - g_min_pr ** (-p_pr + 2.)))
 
 
-def pack_lehamoc(param_sets) -> Batch:
-    """Batch for the `LeHaMoC Code and Tests/LeHaMoC.py` driver (one dict or a list of dicts with the 53 keys of its
-    Parameters.txt).  Set-up with the reference's own expressions, LeHaMoC.py:132-259, one walker at a time (this
-    driver is not on the headline path; the loop costs ~50 us per walker).  Supported: leptonic processes, proton
-    equation with synchrotron / photopion / Bethe-Heitler losses, proton synchrotron, photopion pairs, photons and
-    neutrinos, Bethe-Heitler pair injection, pp loss term and pp secondaries (n_H and p_pr may differ per walker)."""
+def _pack_lehamoc_loop(param_sets) -> Batch:
+    """pack_lehamoc one walker at a time with the reference's own expressions (LeHaMoC.py:132-259): the statement the
+    vectorised packer below is tested against (~50 us per walker)."""
     from ._lib import (LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B, C_NH,
                        C_PPR)
     if isinstance(param_sets, dict):
@@ -414,6 +411,128 @@ def pack_lehamoc(param_sets) -> Batch:
     nsteps = np.full(W, int(time_end / step_alg), dtype=np.int64)
     b = Batch("lehamoc", cfg, consts, g_el, nu_syn, nu_ic, nu_tot, el_inj, ext, nsteps)
     b.g_pr, b.pr_inj = g_prs, pr_inj
+    return b
+
+
+def pack_lehamoc(param_sets) -> Batch:
+    """Batch for the `LeHaMoC Code and Tests/LeHaMoC.py` driver (one dict or a list of dicts with the 53 keys of its
+    Parameters.txt).  Set-up with the reference's own expressions, LeHaMoC.py:132-259, for all walkers at once (scalar
+    powers through Python floats like the reference's scalars, elementwise NumPy arithmetic in the same order: the
+    doubles are those of `_pack_lehamoc_loop`).  Supported: leptonic processes, proton equation with synchrotron /
+    photopion / Bethe-Heitler losses, proton synchrotron, photopion pairs, photons and neutrinos, Bethe-Heitler pair
+    injection, pp loss term and pp secondaries, user photon field (n_H and p_pr may differ per walker)."""
+    from ._lib import (LHM_NCONST, C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B, C_NH,
+                       C_PPR)
+    if isinstance(param_sets, dict):
+        param_sets = [param_sets]
+    F = param_sets[0]
+    missing = [k for k in LH_KEYS if k not in F]
+    if missing:
+        raise KeyError(f"parameter file lacks {missing}")
+    per_walker = ("g_min_el", "g_max_el", "g_el_PL_min", "g_el_PL_max", "g_min_pr", "g_max_pr", "g_pr_PL_min",
+                  "g_pr_PL_max", "p_el", "L_el", "p_pr", "L_pr", "R0", "B0", "n_H")
+    shared_keys = [k for k in LH_KEYS if k not in per_walker]
+    get_shared, get_walker = itemgetter(*shared_keys), itemgetter(*per_walker)
+    ref = tuple(float(v) for v in get_shared(F))
+    for P in param_sets[1:]:
+        if get_shared(P) != ref and tuple(float(v) for v in get_shared(P)) != ref:
+            bad = [k for k in shared_keys if float(P[k]) != float(F[k])]
+            raise ValueError(f"walkers of one batch must share '{bad[0]}'")
+    table = np.array([get_walker(P) for P in param_sets], dtype=np.float64)
+    col = lambda k: np.ascontiguousarray(table[:, per_walker.index(k)])
+    pw10 = lambda a: np.array([10 ** x for x in a.tolist()])
+    W = len(param_sets)
+    Ng, Nh, Np, Nt = int(float(F["grid_g_el"])), int(float(F["grid_g_el"]) / 2), int(float(F["grid_g_pr"])), int(float(F["grid_nu"]))
+    time_init, time_end, step_alg = float(F["time_init"]), float(F["time_end"]), float(F["step_alg"])
+    Vexp = float(F["Vexp"]) * c
+    R0, B0, p_el, p_pr = pw10(col("R0")), col("B0"), col("p_el"), col("p_pr")
+    comp_el = sigmaT * pw10(col("L_el")) / (4. * np.pi * R0 * m_el * c ** 3)                     # LeHaMoC.py:136
+    comp_pr = sigmaT * pw10(col("L_pr")) / (4. * np.pi * R0 * m_pr_ * c ** 3)
+
+    def rows_logspace(lo, hi, n):
+        lo, hi = np.broadcast_to(np.asarray(lo, dtype=np.float64), (W,)), np.broadcast_to(np.asarray(hi, dtype=np.float64), (W,))
+        if W > 1 and np.all(lo == lo[0]) and np.all(hi == hi[0]):
+            return np.broadcast_to(np.logspace(lo[0], hi[0], n), (W, n))
+        return np.logspace(lo, hi, n, axis=-1)
+
+    def window(g, lo_t, hi_t, gmax_t, shift):
+        """index_PL_min / index_PL_max of LeHaMoC.py:150-169 (the proton ones are shifted by one)."""
+        gt, lt = g > pw10(hi_t)[:, None], g < pw10(lo_t)[:, None]
+        same = hi_t == gmax_t
+        if np.any(~same & ~gt.any(axis=1)) or np.any((lo_t != 0.) & ~lt.any(axis=1)):
+            raise ValueError("power-law window outside the gamma grid (the reference raises here too)")
+        i_max = np.where(same, -1, gt.argmax(axis=1) + shift)
+        i_min = np.where(lo_t == 0., 1, lt.sum(axis=1) - 1 + shift)
+        return i_min, i_max
+
+    g_el = rows_logspace(col("g_min_el"), col("g_max_el"), Ng)
+    g_prs = rows_logspace(col("g_min_pr"), col("g_max_pr"), Np)
+    ie_min, ie_max = window(g_el, col("g_el_PL_min"), col("g_el_PL_max"), col("g_max_el"), 0)
+    ip_min, ip_max = window(g_prs, col("g_pr_PL_min"), col("g_pr_PL_max"), col("g_max_pr"), 1)
+    ns = rows_logspace(7.5, np.log10(7. * _nu_c(g_el[:, -1], B0)) + 1.4, Nh)                   # LeHaMoC.py:171
+    ni1 = np.logspace(15., 32., Nh)
+    nu_tot = rows_logspace(np.log10(ns[:, 0]), np.log10(np.maximum(ni1[-1], ns[:, -1])), Nt)
+    nu_syn = np.concatenate([ns, nu_tot[:, -1:]], axis=1)                                       # LeHaMoC.py:234
+    nu_ic = np.broadcast_to(ni1, (W, Nh))
+    V0 = np.array([4. * np.pi / 3. * x ** 3. for x in R0.tolist()])       # scalar pow, like the reference's Volume(R0)
+    rows = np.arange(W)
+
+    def Q_Lum_rows(L, p, g_lo, g_hi, mass):                                                     # LeHaMoC_f.py:52-56,75-79
+        e = -p + 2.
+        pw_hi = np.array([x ** y for x, y in zip(g_hi.tolist(), e.tolist())])
+        pw_lo = np.array([x ** y for x, y in zip(g_lo.tolist(), e.tolist())])
+        with np.errstate(divide="ignore", invalid="ignore"):
+            out = L * e / (mass * c ** 2. * (pw_hi - pw_lo))
+        for w in np.flatnonzero(p == 2.):
+            out[w] = L[w] / (mass * c ** 2. * np.log(g_hi[w] / g_lo[w]))
+        return out
+
+    def inside(n, i_min, i_max):
+        stop = np.where(i_max < 0, n + i_max, i_max)
+        k = np.arange(n)[None, :]
+        return (k >= i_min[:, None]) & (k < stop[:, None])
+
+    if float(F["PL_inj"]) == 1.:                                                                # LeHaMoC.py:256-261
+        Qe = Q_Lum_rows(_Lum_e_inj(comp_el, R0), p_el, g_el[rows, ie_min], g_el[rows, ie_max], m_el)
+        el_inj = np.where(inside(Ng, ie_min, ie_max), Qe[:, None] * g_el ** (-p_el[:, None]) / V0[:, None], SENTINEL)
+        Lp = 4. * np.pi * R0 * m_pr_ * c ** 3. * comp_pr / sigmaT
+        Qp = Q_Lum_rows(Lp, p_pr, g_prs[rows, ip_min], g_prs[rows, ip_max], m_pr_)
+        pr_inj = np.where(inside(Np, ip_min, ip_max), Qp[:, None] * g_prs ** (-p_pr[:, None]) / V0[:, None], SENTINEL)
+    else:
+        # the normalisation integrates over g[:index_PL_max] (np.trapz, pairwise summation: length-dependent rounding),
+        # so that scalar stays a per-walker call; the arrays are built at once
+        Np_n = np.array([_Q_norm_exp_c(R0[w], comp_pr[w], g_prs[w], int(ip_max[w]), p_pr[w]) for w in range(W)])
+        Ne_n = np.array([_Q_norm_exp_c(R0[w], comp_el[w], g_el[w], int(ie_max[w]), p_el[w]) for w in range(W)])
+        pr_inj = Np_n[:, None] * g_prs ** (-p_pr[:, None]) * np.exp(-g_prs / g_prs[rows, ip_max][:, None]) / V0[:, None]
+        el_inj = Ne_n[:, None] * g_el ** (-p_el[:, None]) * np.exp(-g_el / g_el[rows, ie_max][:, None]) / V0[:, None]
+    ext1 = external_fields_lh(F, nu_tot[0])
+    ext = np.broadcast_to(ext1, (W, Nt))
+    if not np.all(nu_tot == nu_tot[0]):
+        ext = ext.copy()
+        for w in range(1, W):
+            ext[w] = external_fields_lh(F, nu_tot[w])
+    consts = np.zeros((W, LHM_NCONST))
+    consts[:, C_R0], consts[:, C_B0], consts[:, C_M], consts[:, C_VEXP] = R0, B0, float(F["m"]), Vexp
+    consts[:, C_DT] = step_alg * R0 / c
+    consts[:, C_TINIT], consts[:, C_NSTEPS] = time_init, int(time_end / step_alg)
+    consts[:, C_COR_P] = p_el
+    consts[:, C_COR_Q0] = Q_Lum_rows(_Lum_e_inj(comp_el, R0), p_el, g_el[:, 1], g_el[:, -2], m_el)       # LeHaMoC_f.py:646
+    consts[:, C_COR_B] = 10 ** 4.
+    consts[:, C_NH], consts[:, C_PPR] = col("n_H"), p_pr                                        # LeHaMoC.py:95,114
+    cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=100, loss_minus_one=1, qee_from_ic=0,
+               const_B=int(float(F["m"]) == 0. or Vexp == 0.), ic_pair_table=1,
+               shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))),
+               driver=1, Np=Np, esc_flag_pr=_flag01(F, "esc_flag_pr"))
+    for k in PHOTOHADRONIC_FLAGS + PP_FLAGS:
+        cfg[k] = _flag01(F, k)
+    if cfg["neutrino_flag"] and not cfg["pg_pi_emis_flag"]:
+        cfg["neutrino_flag"] = 0                 # LeHaMoC.py:346 only looks at it inside the pg_pi_emis branch
+    for k in FLAG_KEYS:
+        cfg[k] = _flag01(F, "esc_flag_el" if k == "esc_flag" else k)
+    cont = np.ascontiguousarray
+    nsteps = np.full(W, int(time_end / step_alg), dtype=np.int64)
+    b = Batch("lehamoc", cfg, consts, cont(g_el), cont(nu_syn), cont(nu_ic), cont(nu_tot), cont(el_inj), cont(ext), nsteps)
+    b.g_pr, b.pr_inj = cont(g_prs), cont(pr_inj)
     return b
 
 

@@ -268,3 +268,26 @@ def test_gpu_random_lehamoc_configurations_vs_oracle(seed):
         log_close(Npr[0], np.log10(n_p), f"seed {seed} {path} n_p {Q}", tol_floor=tf)
         if Q["pp_nu_emis_flag"]:
             log_close(Nnu[0], np.log10(N_nu), f"seed {seed} {path} N_nu {Q}", tol_floor=tf)
+
+
+def test_vectorised_lehamoc_packing_is_the_loop():
+    """pack_lehamoc builds all walkers at once; `_pack_lehamoc_loop` (one walker at a time, the reference's own
+    expressions) gives the same doubles -- fixtures with perturbed walkers and 40 random configurations."""
+    from lehamoc_b200 import setup_host as sh
+    names = ("consts", "g_el", "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext", "g_pr", "pr_inj")
+
+    def same(a, b, what):
+        assert a.cfg == b.cfg, what
+        for x, y, n in zip(a.arrays() + (a.g_pr, a.pr_inj), b.arrays() + (b.g_pr, b.pr_inj), names):
+            np.testing.assert_array_equal(x, y, err_msg=f"{what}: {n}")
+    for name in ("lh_shipped", "lh_bbpl", "lh_expand", "lh_test4small", "lh_all", "lh_user"):
+        _, P = load_golden(name)
+        rng = np.random.default_rng(5)
+        sets = [dict(P)] + [dict(P, R0=float(rng.uniform(14.5, 16.)), B0=float(10 ** rng.uniform(-1, 1)),
+                                 L_el=float(P["L_el"] + rng.uniform(-1, 1)), p_el=float(rng.uniform(1.6, 2.6)),
+                                 p_pr=float(rng.choice([2., rng.uniform(1.7, 2.6)])),
+                                 L_pr=float(P["L_pr"] + rng.uniform(-1, 1))) for _ in range(5)]
+        same(sh._pack_lehamoc_loop(sets), sh.pack_lehamoc(sets), name)
+    for seed in range(40):
+        Q = _random_lh_params(seed)
+        same(sh._pack_lehamoc_loop(Q), sh.pack_lehamoc(Q), f"seed {seed}")
