@@ -152,7 +152,8 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
 // tile schedule stays one for IC_NW = 8 warps (that phase is < 1 % of a hadronic step).
 // =================================================================================================
 constexpr int NT_LH = 512;
-__global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
+template <int NTL, int MINB>
+__global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
     extern __shared__ __align__(16) double smem_raw[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x;
@@ -169,33 +170,33 @@ __global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
     const double n_H = A.consts[(size_t)w * LHM_NCONST + LHM_C_NH], p_pr = A.consts[(size_t)w * LHM_NCONST + LHM_C_PPR];
     // initial state (LeHaMoC.py:222-259): N_el = el_inj * Volume(R0), N_pr = 0, photons 1e-260
     const double V0 = volume_of(C.R0);
-    for (int j = tid; j < Ng; j += NT_LH) {
+    for (int j = tid; j < Ng; j += NTL) {
         S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j] * V0;
         S.qee[j] = 0.0;
     }
-    for (int j = tid; j < Np; j += NT_LH) H.Npr[j] = 0.0;
-    for (int k = tid; k < Ns; k += NT_LH) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.aggS[k] = 0.0; H.QsynP[k] = 0.0; }
-    for (int k = tid; k < Ni; k += NT_LH) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    for (int j = tid; j < Np; j += NTL) H.Npr[j] = 0.0;
+    for (int k = tid; k < Ns; k += NTL) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.aggS[k] = 0.0; H.QsynP[k] = 0.0; }
+    for (int k = tid; k < Ni; k += NTL) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
     LossTab Tb;
     if (A.had) {
-        loss_tab_stage(Tb, H.ltab, A.HT, NT_LH);
-        for (int k = tid; k < 52; k += NT_LH) {
+        loss_tab_stage(Tb, H.ltab, A.HT, NTL);
+        for (int k = tid; k < 52; k += NTL) {
             H.Nnu[k] = 0.0; H.Qnu[k] = 0.0;
             H.Enu[k] = (k < 50) ? exp10(logspace_exp(10., 22., k, 50)) * kHC.eV : 0.0;     // E_nu_space, LeHaMoC_f.py:41
         }
-        for (int j = tid; j < Ng; j += NT_LH) { H.Qpi[j] = 0.0; H.Qbh[j] = 0.0; }
-        for (int k = tid; k < Ni; k += NT_LH) H.Qpg[k] = 0.0;
+        for (int j = tid; j < Ng; j += NTL) { H.Qpi[j] = 0.0; H.Qbh[j] = 0.0; }
+        for (int k = tid; k < Ni; k += NTL) H.Qpg[k] = 0.0;
     }
     BhStaged BG;
     BG.base = H.bhsurf; BG.zmax = H.bhsurf; BG.desc = reinterpret_cast<const int*>(H.bhsurf + 2);
     if (A.had && C.F.bh_e) {
         BhSurf tmp;
         int* desc = reinterpret_cast<int*>(H.bhsurf + 2);
-        double* p2 = bh_stage(tmp, A.BSm, H.bhsurf + 2 + BH_DESC_INTS, NT_LH, H.bhsurf, desc, H.bhsurf);
-        bh_stage(tmp, A.BSp, p2, NT_LH, H.bhsurf, desc + BH_DESC_INTS, H.bhsurf + 1);
+        double* p2 = bh_stage(tmp, A.BSm, H.bhsurf + 2 + BH_DESC_INTS, NTL, H.bhsurf, desc, H.bhsurf);
+        bh_stage(tmp, A.BSp, p2, NTL, H.bhsurf, desc + BH_DESC_INTS, H.bhsurf + 1);
         if (tid == 0) simpson_weights_irregular(C.T + L.lgp, Np, H.bhw);      // made visible by ic_prepare's barrier
     }
-    ic_prepare<NT_LH>(C, S);
+    ic_prepare<NTL>(C, S);
     double t = C.tinit;
     long long tprev = clock64();            // LHM_TICK: per-phase cycles of thread 0 (lhm_set_phase_profile), see run_kernel
     for (int step = 0; step < nsteps; ++step) {
@@ -204,57 +205,57 @@ __global__ void __launch_bounds__(NT_LH, 1) run_lh_kernel(RunArgs A) {
         C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
         C.V = volume_of(C.Rad);
         LHM_TICK(0);
-        phase_photons<NT_LH>(C, S, true);
-        if (C.F.ic_l) phase_uph_lh<NT_LH>(C, S);
+        phase_photons<NTL>(C, S, true);
+        if (C.F.ic_l) phase_uph_lh<NTL>(C, S);
         LHM_TICK(1);
-        phase_protons<NT_LH>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
+        phase_protons<NTL>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
         LHM_TICK(2);
-        if (C.F.bh_e) phase_bh_emis<NT_LH>(C, S, H, BG);
+        if (C.F.bh_e) phase_bh_emis<NTL>(C, S, H, BG);
         LHM_TICK(3);
-        if (C.F.pg_e) phase_photopion<NT_LH>(C, S, H, A.HT);
-        else if (A.had) { for (int k = tid; k < 52; k += NT_LH) H.Qnu[k] = 0.0; }
+        if (C.F.pg_e) phase_photopion<NTL>(C, S, H, A.HT);
+        else if (A.had) { for (int k = tid; k < 52; k += NTL) H.Qnu[k] = 0.0; }
         LHM_TICK(4);
-        if (C.F.pp_ee || C.F.pp_g || C.F.pp_nu) phase_pp<NT_LH>(C, S, H, n_H, p_pr);
+        if (C.F.pp_ee || C.F.pp_g || C.F.pp_nu) phase_pp<NTL>(C, S, H, n_H, p_pr);
         LHM_TICK(5);
-        phase_electrons_lh<NT_LH>(C, S, (C.F.pg_e || C.F.pp_ee) ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
-        phase_vectors<NT_LH>(C, S);
-        phase_syn_rows<NT_LH>(C, S, false);
-        phase_syn_protons<NT_LH>(C, S, H);
+        phase_electrons_lh<NTL>(C, S, (C.F.pg_e || C.F.pp_ee) ? H.Qpi : nullptr, C.F.bh_e ? H.Qbh : nullptr);
+        phase_vectors<NTL>(C, S);
+        phase_syn_rows<NTL>(C, S, false);
+        phase_syn_protons<NTL>(C, S, H);
         LHM_TICK(6);
         if (C.F.ic_e) {
-            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT_LH>(C, S); else phase_ic_S<NT_LH>(C, S);
+            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NTL>(C, S); else phase_ic_S<NTL>(C, S);
         }
         __syncthreads();
-        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT_LH>(C, S); __syncthreads(); }
+        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NTL>(C, S); __syncthreads(); }
         LHM_TICK(7);
-        phase_photon_solves_lh<NT_LH>(C, S, H, cor, (C.F.pg_e || C.F.pp_g) ? H.Qpg : nullptr);
+        phase_photon_solves_lh<NTL>(C, S, H, cor, (C.F.pg_e || C.F.pp_g) ? H.Qpg : nullptr);
         LHM_TICK(8);
-        if (C.F.gg) phase_gg_lh<NT_LH>(C, S, H, step);
+        if (C.F.gg) phase_gg_lh<NTL>(C, S, H, step);
         LHM_TICK(9);
         if (A.had) {                                             // neutrino equation: escape only, LeHaMoC.py:430-434
             const double V2 = 1.0 + C.dt * (kPC.c / C.Rad);
-            for (int k = tid + 1; k < 49; k += NT_LH) H.Nnu[k] = (H.Nnu[k] + H.Qnu[k]) / V2;
+            for (int k = tid + 1; k < 49; k += NTL) H.Nnu[k] = (H.Nnu[k] + H.Qnu[k]) / V2;
         }
         const int slot = A.snapshots > 0 ? step : 0;
         if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && step == nsteps - 1)) {
             const int S_ = A.snapshots > 0 ? A.snapshots : 1;
             if (A.sed_out) {
-                phase_photons<NT_LH>(C, S, false);
+                phase_photons<NTL>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
-                for (int k = tid; k < Nt; k += NT_LH)
+                for (int k = tid; k < Nt; k += NTL)
                     o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
-                for (int j = tid; j < Ng; j += NT_LH) o[j] = S.N[j] / C.V;
+                for (int j = tid; j < Ng; j += NTL) o[j] = S.N[j] / C.V;
             }
             if (A.Np_out) {
                 double* o = A.Np_out + ((size_t)w * S_ + slot) * Np;
-                for (int j = tid; j < Np; j += NT_LH) o[j] = H.Npr[j] / C.V;
+                for (int j = tid; j < Np; j += NTL) o[j] = H.Npr[j] / C.V;
             }
             if (A.Nnu_out) {
                 double* o = A.Nnu_out + ((size_t)w * S_ + slot) * 50;
-                for (int k = tid; k < 50; k += NT_LH) o[k] = A.had ? H.Nnu[k] : 0.0;
+                for (int k = tid; k < 50; k += NTL) o[k] = A.had ? H.Nnu[k] : 0.0;
             }
             __syncthreads();
         }
@@ -535,7 +536,7 @@ static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& 
     return e;
 }
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
-static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV];
+static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -846,8 +847,15 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
         CUDA_TRY(ensure_dyn_smem(run_code_lh_kernel, h->smem, g_smem_codelh[h->device % MAX_DEV]));
         run_code_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     } else if (lh) {
-        CUDA_TRY(ensure_dyn_smem(run_lh_kernel, h->smem, g_smem_lh[h->device % MAX_DEV]));
-        run_lh_kernel<<<h->W, NT_LH, h->smem, h->stream>>>(A);
+        // hadronic runs: 512 threads, one CTA per SM (the work areas fill its shared memory); leptonic-only runs of
+        // this driver (BASELINE config 5): 256 threads so that two walkers share an SM whenever their state fits
+        if (A.had) {
+            CUDA_TRY(ensure_dyn_smem(run_lh_kernel<NT_LH, 1>, h->smem, g_smem_lh[h->device % MAX_DEV]));
+            run_lh_kernel<NT_LH, 1><<<h->W, NT_LH, h->smem, h->stream>>>(A);
+        } else {
+            CUDA_TRY(ensure_dyn_smem(run_lh_kernel<NT, 2>, h->smem, g_smem_lh2[h->device % MAX_DEV]));
+            run_lh_kernel<NT, 2><<<h->W, NT, h->smem, h->stream>>>(A);
+        }
     } else {
         CUDA_TRY(ensure_dyn_smem(run_kernel, h->smem, g_smem_run[h->device % MAX_DEV]));
         run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
