@@ -34,6 +34,55 @@ __host__ __device__ inline size_t cor_smem_bytes(int Ng) {
     return (size_t)COR_WARPS * ((size_t)6 * cor_chunk(Ng) * 32 + ((Ng + 1) & ~1) + 2 * COR_NNU) * sizeof(double);
 }
 
+// The 200-step loop with the lane's chunk of every array in registers (CN = chunk length, compile time): no shared-memory
+// round trips inside the recurrences.  The luminosity functional Lambda <- (Lambda + z.N)/bph is linear, so every lane
+// carries its own share of it and the lanes are only summed when the reference samples the ratio (every 10th step).
+template <int CN>
+__device__ __forceinline__ double cor_time_loop(const double* m_, const double* binv, const double* injdt, const double* Mp,
+                                                const double* z, const double (&Mlev)[5], double lam_lane, double zb,
+                                                double ends, double El, double dt, double R0, int lane) {
+    const PhysConst& pc = kPC;
+    double rm[CN], rb[CN], ri[CN], rM[CN], rz[CN], rN[CN];
+#pragma unroll
+    for (int i = 0; i < CN; ++i) {
+        const int s = i * 32 + lane;
+        rm[i] = m_[s]; rb[i] = binv[s]; ri[i] = injdt[s]; rM[i] = Mp[s]; rz[i] = z[s]; rN[i] = 0.0;
+    }
+    const double bph = 1.0 + dt * (pc.c / R0);               // photon equation is diagonal (:226)
+    const double t_end = 20.0 * R0 / pc.c;
+    double t = 0.0, day = 0.0, ratio = 0.0;
+    while (t < t_end) {
+        t += dt;
+        double x0 = 0.0;
+#pragma unroll
+        for (int i = CN - 1; i >= 0; --i) {
+            x0 = fma(rm[i], x0, (rN[i] + ri[i]) * rb[i]);
+            rN[i] = x0;
+        }
+        double Aacc = x0;
+#pragma unroll
+        for (int l = 0; l < 5; ++l) {
+            const double Ao = __shfl_down_sync(0xffffffffu, Aacc, 1 << l);
+            if (lane + (1 << l) < 32) Aacc = fma(Mlev[l], Ao, Aacc);
+        }
+        double xin = __shfl_down_sync(0xffffffffu, Aacc, 1);
+        if (lane == 31) xin = 0.0;
+        double zn = (lane == 0) ? zb : 0.0;
+#pragma unroll
+        for (int i = 0; i < CN; ++i) {
+            const double xv = fma(rM[i], xin, rN[i]);
+            rN[i] = xv;
+            zn = fma(rz[i], xv, zn);
+        }
+        lam_lane = (lam_lane + zn) / bph;
+        if (day < t) {                                       // (:231-236)
+            day = day + 1.0 * R0 / pc.c;
+            ratio = (warp_sum(lam_lane) + ends) / El;
+        }
+    }
+    return ratio;
+}
+
 __global__ void __launch_bounds__(COR_WARPS * 32) cor_kernel(CorArgs A) {
     extern __shared__ double smc[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -80,6 +129,7 @@ __global__ void __launch_bounds__(COR_WARPS * 32) cor_kernel(CorArgs A) {
             ends += om * LHM_SENT;                           // boundary bins are never updated
         }
     }
+    const double lam_lane0 = lam0_part;                      // this lane's share of the initial luminosity functional
     double Lam = warp_sum(lam0_part);
     ends = warp_sum(ends);
     __syncwarp();
@@ -142,7 +192,20 @@ __global__ void __launch_bounds__(COR_WARPS * 32) cor_kernel(CorArgs A) {
             M = (lane + (1 << l) < 32) ? M * Mo : M;
         }
     }
-    // time loop (:204-236)
+    if (Cn <= 12) {
+        __syncwarp();
+        double r;
+        switch (Cn) {
+#define LHM_COR_CASE(n) case n: r = cor_time_loop<n>(m_, binv, injdt, Mp, z, Mlev, lam_lane0, zb, ends, El, dt, R0, lane); break;
+            LHM_COR_CASE(1) LHM_COR_CASE(2) LHM_COR_CASE(3) LHM_COR_CASE(4) LHM_COR_CASE(5) LHM_COR_CASE(6)
+            LHM_COR_CASE(7) LHM_COR_CASE(8) LHM_COR_CASE(9) LHM_COR_CASE(10) LHM_COR_CASE(11) default:
+            LHM_COR_CASE(12)
+#undef LHM_COR_CASE
+        }
+        if (lane == 0) A.out[w] = r;
+        return;
+    }
+    // time loop (:204-236), chunk arrays in shared memory (grids beyond 12 * 32 + 2 points)
     const double bph = 1.0 + dt * (pc.c / R0);               // photon equation is diagonal (:226)
     const double t_end = 20.0 * R0 / pc.c;
     double t = 0.0, day = 0.0, ratio = 0.0;
