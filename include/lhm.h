@@ -1,5 +1,6 @@
-/* lhm.h -- C ABI of liblhm.so: B200 (sm_100a) implementation of LeHaMoC's leptonic per-timestep
- * kinetic update, batched over independent parameter sets ("walkers").
+/* lhm.h -- C ABI of liblhm.so: B200 (sm_100a) implementation of LeHaMoC's per-timestep kinetic update (leptonic
+ * drivers LeMoC.py / Code.py, leptohadronic driver LeHaMoC.py with photopion, Bethe-Heitler and pp channels), batched
+ * over independent parameter sets ("walkers").
  *
  * The reference (mariapetro/LeHaMoC) is pure Python and has no FFI; its boundary is the Python
  * surface  `python LeMoC.py <Parameters.txt> <suffix>`  (LeMoC/LeMoC.py:45-58,290-296),
@@ -22,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LHM_VERSION 100
+#define LHM_VERSION 101
 
 typedef enum {
     LHM_OK = 0,

@@ -328,7 +328,6 @@ LH_KEYS = ("time_init", "time_end", "step_alg", "PL_inj", "g_min_el", "g_max_el"
            "pg_BH_emis_flag", "n_H", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
            "neutrino_flag", "esc_flag_el", "esc_flag_pr", "BB_flag", "temperature", "GB_ext", "PL_flag", "dE_dV_ph",
            "nu_min_ph", "nu_max_ph", "s_ph", "User_ph")
-UNSUPPORTED_FLAGS = ()
 PHOTOHADRONIC_FLAGS = ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag", "neutrino_flag", "pg_BH_emis_flag")
 PP_FLAGS = ("pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag")
 m_pr_ = 1.67262192369e-24

@@ -75,7 +75,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lhm_version() == 100
+    assert lib.lhm_version() == 101
     assert b"no CPU fallback" in lib.lhm_strerror(-3)
     # struct layout agreed between header and binding
     n_int_fields = len(re.search(r"typedef struct \{(.*?)\} lhm_config;", header, re.S).group(1)
