@@ -440,8 +440,8 @@ def main():
                                   "durations are measured while they share the GPU); run_kernel waits for both",
                 # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture of
                 # 1184 Test-1 walkers committed as profiles/r01_g_final_ncu_summary.txt (1.6139 GB + 6.9 MB), per walker
-                "traffic": (1.613871e9 + 6.920960e6) / 1184.0 * W if args.ic_path == "R" else None,
-                "traffic_source": "ncu capture profiles/r01_g_final_ncu_summary.txt, scaled by walkers per launch; it is "
+                "traffic": (1.642121e9 + 7.229952e6) / 1184.0 * W if args.ic_path == "R" else None,
+                "traffic_source": "ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is "
                                   "the per-step re-read of the constant-B exponential cache (543 KB per walker x 10 "
                                   "steps, half of it exact zeros that are skipped) and of the 68 KB per-walker tables, "
                                   "2 % of HBM bandwidth",
