@@ -10,7 +10,8 @@ from __future__ import annotations
 import numpy as np
 
 from .engine import Engine
-from .setup_host import pack_code, pack_code_lehamoc, read_parameter_file
+from .setup_host import (pack_code, pack_code_lehamoc, pack_code_lehamoc_request, pack_code_request,
+                         read_parameter_file)
 
 _engines = {}
 
@@ -26,9 +27,17 @@ def _engine_for(batch, ic_path, capacity):
     return eng
 
 
-def LeMoC_batch(params, fileName, ic_path="R", return_particles=False):
-    """`params` [W,6]; returns (nu_tot [W,Nt], nuLnu [W,Nt]) (and n_e = N_el/V [W,Ng] if asked)."""
+def LeMoC_batch(params, fileName, ic_path="R", return_particles=False, device_pack=False):
+    """`params` [W,6]; returns (nu_tot [W,Nt], nuLnu [W,Nt]) (and n_e = N_el/V [W,Ng] if asked).
+    device_pack=True builds grids and injection on the device (lhm_pack_batch: 2-3x less host time per call, grids
+    equal to the NumPy ones to ~1e-14 instead of bit for bit); the returned arrays are then views of page-locked
+    buffers that the next call reuses."""
     frozen = fileName if isinstance(fileName, dict) else read_parameter_file(fileName)
+    if device_pack:
+        req = pack_code_request(params, frozen)
+        eng = _engine_for(req, ic_path, req.W)
+        N, sed = eng.run_packed_host(req)
+        return (req.nu_tot, sed, N) if return_particles else (req.nu_tot, sed)
     batch = pack_code(params, frozen)
     eng = _engine_for(batch, ic_path, batch.W)
     N, sed = eng.run_host(batch, snapshots=0)
@@ -43,10 +52,16 @@ def LeMoC(params, fileName):
     return (nu_tot[0], sed[0])
 
 
-def LeHaMoC_batch(params, fileName, ic_path="R"):
+def LeHaMoC_batch(params, fileName, ic_path="R", device_pack=False):
     """`params` [W,10] (Code.py:285-295); returns (nu_tot [W,Nt], nuLnu [W,Nt]) of Fit_emcee/Code.py::LeHaMoC, the
-    leptonic model plus a proton population that cools and radiates by synchrotron only."""
+    leptonic model plus a proton population that cools and radiates by synchrotron only.  device_pack: as LeMoC_batch."""
     frozen = fileName if isinstance(fileName, dict) else read_parameter_file(fileName)
+    if device_pack:
+        req = pack_code_lehamoc_request(params, frozen)
+        eng = _engine_for(req, ic_path, req.W)
+        eng.setup_packed(req)
+        _, sed, _, _ = eng.run_lh(snapshots=0)
+        return req.nu_tot, sed[:, 0].cpu().numpy()
     batch = pack_code_lehamoc(params, frozen)
     eng = _engine_for(batch, ic_path, batch.W)
     eng.setup(batch)

@@ -521,7 +521,15 @@ def test_random_fit_walkers_vs_oracle(orc):
     th2 = lo2 + (hi2 - lo2) * rng.random((8, 10))
     th2[2, 9] = 2.0
     nu2, sed2 = Code.LeHaMoC_batch(th2, P2)
+    nu2d, sed2d = Code.LeHaMoC_batch(th2, P2, device_pack=True)
+    nud, sedd = Code.LeMoC_batch(th, P, device_pack=True)
+    sedd = sedd.copy()
     for i in range(len(th2)):
         nu_ref, sed_ref = orc.code_LeHaMoC(th2[i], P2)
         np.testing.assert_array_equal(nu2[i], nu_ref)
+        np.testing.assert_array_equal(nu2d[i], nu_ref)
         assert_spectra_close(sed2[i], sed_ref, f"Code.LeHaMoC random walker {i} {th2[i]}")
+        assert_spectra_close(sed2d[i], sed_ref, f"Code.LeHaMoC random walker {i}, device-side set-up")
+    for i in range(len(th)):
+        np.testing.assert_array_equal(nud[i], nu[i])
+        assert_spectra_close(sedd[i], sed[i], f"Code.LeMoC random walker {i}, device-side set-up")
