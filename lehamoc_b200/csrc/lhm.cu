@@ -95,13 +95,16 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
         C.V = volume_of(C.Rad);
 
         LHM_TICK(0);
-        phase_photons<NT>(C, S, true);
+        // the photon field of the top of the step feeds the Compton losses, the IC emissivity and the gamma-gamma block;
+        // the per-gamma vectors feed the synchrotron / SSA rows and the IC pairs: runs with all of those switched off
+        // (Parameters_Test3.txt: adiabatic losses only, 600 steps) skip both
+        if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
         LHM_TICK(1);
         if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
         LHM_TICK(2);
         phase_electrons<NT>(C, S);
         LHM_TICK(3);
-        phase_vectors<NT>(C, S);
+        if (C.F.syn_e || C.F.ssa || C.F.ic_e) phase_vectors<NT>(C, S);
         LHM_TICK(4);
         phase_syn_rows<NT>(C, S, false);
         LHM_TICK(5);
