@@ -53,6 +53,17 @@ VARIANTS = {
     "lh_pp_pg": variant(grid_g_el=40., grid_g_pr=30., g_max_pr=8., g_pr_PL_max=7., p_pr=2., L_pr=46.5, grid_nu=60.,
                         time_end=3., n_H=1e8, PL_inj=0., pp_l_flag=1., pp_ee_emis_flag=1., pp_g_emis_flag=1.,
                         pp_nu_emis_flag=1., pg_pi_l_flag=1., pg_pi_emis_flag=1., neutrino_flag=1., B0=10.),
+    # BASELINE config 3 at FULL size: the reference's Test 4 exactly as Tests.ipynb:780-833 sets it up (Ng=300, Np=160,
+    # Nt=100, 5 steps; photopion + Bethe-Heitler losses and emissivities, neutrinos, adiabatic losses).  ~30 min of reference
+    "lh_test4full": variant(time_init=0., time_end=10., step_alg=2., PL_inj=0., g_min_el=0., g_max_el=11., g_el_PL_min=0.,
+                            g_el_PL_max=5.5, grid_g_el=300., g_min_pr=0., g_max_pr=8., g_pr_PL_min=0., g_pr_PL_max=6.93,
+                            grid_g_pr=160., grid_nu=100., p_el=2.01, L_el=40.6, p_pr=2.01, L_pr=46.46,
+                            Vexp=0.000000000000000003, R0=16., B0=0.1, m=0., delta=1., inj_flag=1., Ad_l_flag=1.,
+                            Syn_l_flag=1., Syn_emis_flag=1., IC_l_flag=1., IC_emis_flag=1., SSA_l_flag=1., gg_flag=1.,
+                            pg_pi_l_flag=1., pg_pi_emis_flag=1., pg_BH_l_flag=1., pg_BH_emis_flag=1., n_H=0., pp_l_flag=0.,
+                            pp_ee_emis_flag=0., pp_g_emis_flag=0., pp_nu_emis_flag=0., neutrino_flag=1., esc_flag_el=1.,
+                            esc_flag_pr=1., BB_flag=0., temperature=5., GB_ext=0., PL_flag=0., dE_dV_ph=0., nu_min_ph=0.,
+                            nu_max_ph=0., s_ph=2.01, User_ph=0.),
     # BASELINE config 3 in full: every hadronic channel at once (photopion, Bethe-Heitler AND pp, losses + emission +
     # neutrinos) with adiabatic expansion, on reduced grids
     "lh_all": variant(time_end=6., step_alg=2., PL_inj=0., g_max_el=11., g_el_PL_max=5.5, grid_g_el=44.,
