@@ -430,6 +430,9 @@ def main():
                         "ncu sm__pipe_fp64_cycles_active"}
     roofline = {"bound": "fp64", "kernel": "lhm::run_kernel (fused timestep loop, one CTA per walker)",
                 "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
+                "frac_note": "algorithmic count of SURVEY 8d (15 flop per (o,gamma,nu_i) element of the reference formula); "
+                             "the kernel executes 4 DFMA = 8 flop per element, so frac can exceed 1: the share of the "
+                             "FP64 pipe actually used is executed.fp64_pipe_frac",
                 "executed": pipe,
                 "peak_source": "measured live by lhm_fp64_peak_probe (DFMA, 8 independent chains/thread); "
                                "MEASURED_PEAKS.json carries no FP64 figure",
