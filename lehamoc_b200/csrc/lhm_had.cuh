@@ -563,7 +563,10 @@ __device__ double bh_pair(double ge, double gp, double n_p, int Nt, const double
                     for (int a = 0; a < 4; ++a) {
                         const double* cr = cc + (lx - 3 + a) * nky1 + (ly - 3);
 #pragma unroll
-                        for (int b = 0; b < 4; ++b) sp = sp + cr[b] * hx[a] * hy[b];
+                        double ta = cr[0] * hy[0];                         // row of the tensor product first: 5 DFMA per a
+#pragma unroll
+                        for (int b = 1; b < 4; ++b) ta = fma(cr[b], hy[b], ta);
+                        sp = fma(hx[a], ta, sp);
                     }
                     if (sp > zmax) sp = 0.;
                     res = w * exp10(sp);
