@@ -533,3 +533,35 @@ def test_random_fit_walkers_vs_oracle(orc):
     for i in range(len(th)):
         np.testing.assert_array_equal(nud[i], nu[i])
         assert_spectra_close(sedd[i], sed[i], f"Code.LeMoC random walker {i}, device-side set-up")
+
+
+@pytest.mark.gpu
+def test_ragged_step_counts_in_one_batch():
+    """Walkers of one launch that stop after different numbers of timesteps (the Code.py drivers count steps per walker,
+    Code.py:183): every walker's final state is bit-identical to the same walker in a batch where all share its count.
+    A walker with zero steps produces no output, like the reference's loop (LeMoC.py:196, range(0) writes no row): its
+    rows are unspecified, and its presence must not disturb the other walkers of the launch."""
+    from lehamoc_b200._lib import C_NSTEPS
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_script
+    _, P = load_golden("test1")
+    P.update(grid_g_el=60., grid_nu=40., time_end=7.)
+    sets = [dict(P, B0=0.3 + 0.2 * i, p_el=1.8 + 0.1 * i) for i in range(5)]
+    counts = [7, 1, 4, 0, 2]
+    b = pack_script(sets)
+    b.nsteps[:] = counts
+    b.consts[:, C_NSTEPS] = counts
+    eng = Engine(b.cfg, b.W)
+    N = np.full((b.W, 1, b.cfg["Ng"]), -1.0)
+    sed = np.full((b.W, 1, b.cfg["Nt"]), -1.0)
+    eng.run_host(b, N_out=N, sed_out=sed)
+    for i, k in enumerate(counts):
+        if k == 0:
+            continue
+        u = pack_script(sets)
+        u.nsteps[:] = k
+        u.consts[:, C_NSTEPS] = k
+        Nu, su = eng.run_host(u)
+        np.testing.assert_array_equal(N[i, 0], Nu[i])
+        np.testing.assert_array_equal(sed[i, 0], su[i])
+        assert np.all(np.isfinite(N[i])) and np.all(sed[i] >= 0)
