@@ -66,6 +66,12 @@ class Batch:
     g_pr: np.ndarray = field(default=None)         # [W, Np]   LeHaMoC.py driver only
     pr_inj: np.ndarray = field(default=None)       # [W, Np]
 
+    def __post_init__(self):
+        # zero timesteps: LeMoC.py:196 / LeHaMoC.py loop over range(0) and write no row, Code.py:277 fails on the unbound
+        # Spec_temp_tot -- there is no output to reproduce, so the request is refused here rather than answered
+        if self.nsteps is not None and len(self.nsteps) and int(np.min(self.nsteps)) < 1:
+            raise ValueError("time_init/time_end/step_alg give a walker zero timesteps: the reference produces no output")
+
     @property
     def W(self):
         return self.consts.shape[0]

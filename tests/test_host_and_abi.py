@@ -133,3 +133,11 @@ def test_vectorised_proton_packing_is_the_loop():
     b = sh._protons_code_lh(th, R0, 160)
     np.testing.assert_array_equal(a[0], b[0])
     np.testing.assert_array_equal(a[1], b[1])
+
+
+def test_zero_timesteps_are_refused():
+    """time_end = 0: the reference's loop body never runs (LeMoC.py:196 writes no row, Code.py:277 raises on the unbound
+    spectrum), so there is nothing to reproduce and the packers say so."""
+    _, P = load_golden("test1")
+    with pytest.raises(ValueError):
+        setup_host.pack_script(dict(P, time_end=0.))
