@@ -30,6 +30,14 @@ VARIANTS = {
     # BASELINE config 5: external black body + power-law photon fields (the sane PL form of LeHaMoC.py:195-199)
     "lh_bbpl": variant(grid_g_el=100., grid_nu=100., time_end=6., BB_flag=1., temperature=4., GB_ext=1e-3, PL_flag=1.,
                        dE_dV_ph=1e-3, nu_min_ph=12., nu_max_ph=16., s_ph=2.),
+    # BASELINE config 5 at the larger sweep sizes (grid_g_el = grid_nu = 200, 400, 800): same external fields as lh_bbpl;
+    # the CUDA driver switches to its 1-CTA/SM instantiation with aliased shared memory at these sizes
+    "lh_bbpl200": variant(grid_g_el=200., grid_nu=200., time_end=6., BB_flag=1., temperature=4., GB_ext=1e-3, PL_flag=1.,
+                          dE_dV_ph=1e-3, nu_min_ph=12., nu_max_ph=16., s_ph=2.),
+    "lh_bbpl400": variant(grid_g_el=400., grid_nu=400., time_end=6., BB_flag=1., temperature=4., GB_ext=1e-3, PL_flag=1.,
+                          dE_dV_ph=1e-3, nu_min_ph=12., nu_max_ph=16., s_ph=2.),
+    "lh_bbpl800": variant(grid_g_el=800., grid_nu=800., time_end=5., BB_flag=1., temperature=4., GB_ext=1e-3, PL_flag=1.,
+                          dE_dV_ph=1e-3, nu_min_ph=12., nu_max_ph=16., s_ph=2.),
     # expansion + decaying field + protons that matter (proton synchrotron), exponential cut-off injection
     "lh_expand": variant(grid_g_el=120., grid_g_pr=60., g_max_pr=7., g_pr_PL_max=6., L_pr=46., time_end=8.,
                          step_alg=2., Ad_l_flag=1., Vexp=0.1, m=1., PL_inj=0., g_el_PL_max=5., B0=10.),

@@ -47,7 +47,9 @@ def tables():
     return {k[len("table_"):]: g[k] for k in g.files if k.startswith("table_")}
 
 
-@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user"])
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user", "lh_bbpl200", "lh_bbpl400",
+                                  pytest.param("lh_bbpl800", marks=pytest.mark.skipif(
+                                      os.environ.get("LHM_SLOW") != "1", reason="a minute of NumPy: LHM_SLOW=1 runs it"))])
 def test_oracle_reproduces_lehamoc_script(name):
     z, P = load_golden(name)
     run = olh.LeptoHadronicRun(P)
@@ -89,11 +91,26 @@ def test_pack_lehamoc_matches_oracle_setup():
     np.testing.assert_array_equal(b.consts[:, _lib.C_PPR], [float(P["p_pr"]), 2.5])
 
 
+SWEEP_FIXTURES = {100: "lh_bbpl", 200: "lh_bbpl200", 400: "lh_bbpl400", 800: "lh_bbpl800"}
+
+
+def test_sweep_preset_is_the_fixture_parameter_set():
+    """presets.sweep_walkers (bench.py's config-5 workload) walker 0 == the parameter set the live-reference fixtures
+    lh_bbpl* were generated from, up to the grid size and the number of steps."""
+    from lehamoc_b200.presets import sweep_walkers
+    for grid, name in SWEEP_FIXTURES.items():
+        _, P = load_golden(name)
+        assert sweep_walkers(grid, 3, time_end=P["time_end"])[0] == P
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user"])
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user", "lh_bbpl200", "lh_bbpl400",
+                                  "lh_bbpl800"])
 @pytest.mark.parametrize("path", ["R", "S"])
 def test_gpu_lehamoc_driver_matches_reference(name, path):
-    """Every step's pairs, photons and protons against what the unmodified LeHaMoC.py wrote."""
+    """Every step's pairs, photons and protons against what the unmodified LeHaMoC.py wrote.  lh_bbpl200/400/800 are
+    BASELINE config 5 at its larger sweep sizes: 52 / 105 / 216 KB of shared memory per walker CTA, i.e. two, two and
+    ONE walker per SM (at grid 800 the IC partial sums alias the solver scratch, lhm_step.cuh smem_doubles)."""
     from lehamoc_b200 import LeHaMoC
     z, P = load_golden(name)
     batch, N, sed, Npr, Nnu = LeHaMoC.run(P, ic_path=path)
@@ -122,6 +139,34 @@ def test_gpu_lehamoc_cli_and_batch(tmp_path, monkeypatch):
         _, N1, sed1, Np1, _ = LeHaMoC.run(Q, snapshots=False)
         np.testing.assert_array_equal(sed2[i], sed1[0])
         np.testing.assert_array_equal(Np2[i], Np1[0])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("grid,W", [(100, 4096), (200, 592), (400, 296), (800, 148)])
+def test_gpu_sweep_batch_equals_single_walkers(grid, W):
+    """BASELINE config 5 at its own batch size (4096 walkers at grid 100; full waves at the larger grids): walker 0 of
+    the batch is the live-reference fixture, every walker of the batch equals the same walker evolved in a smaller
+    launch bit for bit, and sampled walkers equal their batch-of-one run."""
+    from lehamoc_b200 import LeHaMoC
+    from lehamoc_b200.presets import sweep_walkers
+    z, P0 = load_golden(SWEEP_FIXTURES[grid])
+    sets = sweep_walkers(grid, W, time_end=P0["time_end"])
+    batch, N, sed, Npr, _ = LeHaMoC.run(sets)
+    assert batch.cfg["shared_ic_grids"] == 1
+    log_close(N[0], z["n_e"], f"sweep {grid} walker 0 n_e")
+    log_close(sed[0], z["nuLnu"], f"sweep {grid} walker 0 nuLnu")
+    assert np.all(np.isfinite(sed)) and np.all(sed > 0)
+    nchunk = 8
+    for c in range(nchunk):
+        a, b = c * W // nchunk, (c + 1) * W // nchunk
+        _, N1, sed1, Np1, _ = LeHaMoC.run(sets[a:b])
+        np.testing.assert_array_equal(sed[a:b], sed1)
+        np.testing.assert_array_equal(N[a:b], N1)
+        np.testing.assert_array_equal(Npr[a:b], Np1)
+    for i in np.random.default_rng(grid).choice(W, size=6, replace=False):
+        _, N1, sed1, _, _ = LeHaMoC.run(sets[int(i)])
+        np.testing.assert_array_equal(sed[int(i)], sed1[0])
+        np.testing.assert_array_equal(N[int(i)], N1[0])
 
 
 def test_oracle_with_photohadronic_terms():
