@@ -25,6 +25,11 @@ import numpy as np  # noqa: E402
 
 METRIC = "model-evals/sec (Test-1 SSC to steady state)"
 UNIT = "model-evals/s"
+# dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch of 1184 Test-1 walkers (ncu --set full)
+NCU_DRAM_BYTES_PER_WALKER = (1.642121e9 + 7.229952e6) / 1184.0
+NCU_DRAM_SOURCE = ("ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is the per-step re-read of "
+                   "the constant-B exponential cache (543 KB per walker x 10 steps, half of it exact zeros that are "
+                   "skipped) and of the 68 KB per-walker tables, 2 % of HBM bandwidth")
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -125,34 +130,66 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-# CPU arm: the loop-structured NumPy port of the reference (oracle/lehamoc_oracle.py, literal=True,
-# cor_factor recomputed every step exactly like LeMoC.py:251), farmed over a process pool like
-# fit_emcee.py:239 does.  This is the ONLY place bench.py executes oracle/ code.
+# CPU arm: the reference's own CPU implementation of the path on the host cores.  kind "reference": the UNMODIFIED
+# LeMoC/LeMoC.py exec'd under oracle/shim (from /root/reference in the build container, from the git-ignored copy
+# baseline/_ref/ that oracle/install_reference.py makes on the GPU box); kind "port" (only when neither exists): the
+# loop-structured NumPy restatement oracle/lehamoc_oracle.py with cor_factor recomputed every step like LeMoC.py:251.
+# One model per core through a process pool, like fit_emcee.py:239.  This is the ONLY place bench.py executes oracle/.
 # ------------------------------------------------------------------------------------------------------
-def _cpu_one(args):
-    P, nts, literal = args
+def _cpu_init():
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import warnings
     warnings.filterwarnings("ignore")
-    import lehamoc_oracle as orc
+    import run_reference  # noqa: F401  (numpy / scipy / pandas / tqdm imports happen here, outside every timed region)
+    import lehamoc_oracle  # noqa: F401
+
+
+def _cpu_one(args):
+    P, nts, hoist, kind = args
     Q = dict(P)
     Q["time_end"] = float(nts)
     t0 = time.perf_counter()
-    orc.run_script(Q, literal=literal, hoist_cor=not literal)
+    if kind == "reference":
+        import run_reference as rr
+        rr.time_lemoc_script(Q, hoist_cor=hoist)
+    else:
+        import lehamoc_oracle as orc
+        orc.run_script(Q, literal=not hoist, hoist_cor=hoist)
     return time.perf_counter() - t0
 
 
-def cpu_sample(param_sets, cores, timesteps=10, literal=True):
-    """Evolve one model per core for `timesteps` of its 10 timesteps; returns (model-evals/s, wall)."""
-    import multiprocessing as mp
-    ctx = mp.get_context("fork")
-    jobs = [(param_sets[i % len(param_sets)], timesteps, literal) for i in range(cores)]
-    t0 = time.perf_counter()
-    with ctx.Pool(cores) as pool:
-        pool.map(_cpu_one, jobs, chunksize=1)
-    wall = time.perf_counter() - t0
-    full = float(param_sets[0]["time_end"])
-    return cores * (timesteps / full) / wall, wall
+class CpuArm:
+    def __init__(self, cores):
+        import multiprocessing as mp
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import run_reference as rr
+        self.kind = "reference" if rr.reference_available() else "port"
+        self.where = rr.REF_ROOT if self.kind == "reference" else "oracle/lehamoc_oracle.py"
+        self.cores = cores
+        self.pool = mp.get_context("fork").Pool(cores, initializer=_cpu_init)
+        self.pool.map(abs, range(cores))                      # workers forked and initialised before any timing
+
+    def sample(self, param_sets, timesteps=10, hoist=False):
+        """One model per core, `timesteps` of the model's 10 timesteps (10 = the whole script as shipped);
+        returns (model-evals/s, wall seconds)."""
+        jobs = [(param_sets[i % len(param_sets)], timesteps, hoist, self.kind) for i in range(self.cores)]
+        t0 = time.perf_counter()
+        self.pool.map(_cpu_one, jobs, chunksize=1)
+        wall = time.perf_counter() - t0
+        full = float(param_sets[0]["time_end"])
+        return self.cores * (timesteps / full) / wall, wall
+
+    def describe(self, nts):
+        what = ("the UNMODIFIED LeMoC/LeMoC.py exec'd from %s under oracle/shim (astropy/shapely stand-ins)" % self.where
+                if self.kind == "reference" else
+                "loop-structured NumPy port of LeMoC.py (oracle/lehamoc_oracle.py; no reference tree on this machine) with "
+                "cor_factor_syn_el recomputed every step as the reference does")
+        steps = "all 10 timesteps" if nts == 10 else f"{nts} of 10 timesteps (time_end = {nts} in the parameter file), scaled"
+        return (f"per step: {self.cores} Test-1 models, one per core (multiprocessing.Pool like fit_emcee.py:239), "
+                f"{steps}; {what}")
+
+    def close(self):
+        self.pool.terminate()
 
 
 def host_cores():
@@ -164,33 +201,32 @@ def host_cores():
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's CPU algorithm on the host cores, same metric/config as the GPU arm."""
+    """--impl reference: the reference's CPU implementation on the host cores, same metric/config as the GPU arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     from lehamoc_b200.presets import test1_walkers
     cores = host_cores()
     sets = test1_walkers(max(cores, 2))
-    total = args.steps + args.warmup
-    # one Test-1 timestep of the loop-structured port costs ~1.1 s/core: keep the whole run near 2.5 minutes
-    nts = int(max(1, min(10, 150.0 / (1.15 * max(total, 1)))))
-    for _ in range(args.warmup):
-        cpu_sample(sets, cores, nts)
+    arm = CpuArm(cores)
+    # warm-up steps run one timestep of the model each (they are untimed; their job is a warm pool); the first one
+    # also calibrates the cost of a full model so that an unusually long --steps cannot run away
+    _, w1 = arm.sample(sets, 1)
+    for _ in range(max(args.warmup - 1, 0)):
+        arm.sample(sets, 1)
+    est_full = 10.0 * w1
+    nts = 10 if est_full * args.steps <= 600.0 else int(max(1, min(10, 600.0 / (w1 * max(args.steps, 1)))))
     t0 = time.perf_counter()
-    vals = []
     for _ in range(args.steps):
-        v, _w = cpu_sample(sets, cores, nts)
-        vals.append(v)
+        arm.sample(sets, nts)
     wall = time.perf_counter() - t0
+    arm.close()
     value = cores * (nts / 10.0) * args.steps / wall
-    sample = (f"per step: {cores} Test-1 models (one per core, multiprocessing.Pool like fit_emcee.py:239), "
-              f"{nts} of 10 timesteps each, scaled by timesteps; loop-structured NumPy port of LeMoC.py with "
-              f"cor_factor_syn_el recomputed every step as the reference does")
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "walkers_per_gpu": args.walkers},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": arm.kind, "sample": arm.describe(nts)},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -199,6 +235,14 @@ def run_reference_arm(args):
 def workload_name(args):
     return (f"Test-1 SSC (LeMoC/Parameters_Test1.txt: Ng=260 Ns=131 Ni=130 Nt=100, 10 timesteps, syn+IC+SSA+gg+escape), "
             f"{args.walkers} walkers per GPU, parameters perturbed around Test 1 (seed 20231), shared grids")
+
+
+def config_dict(args):
+    """The same dictionary in both arms (the driver compares them key by key)."""
+    return {"workload": workload_name(args), "walkers_per_gpu": args.walkers, "ic_path": args.ic_path,
+            "timesteps_per_model": 10,
+            "l2": "flushed between steps (256 MiB write); the per-batch tables + exponential cache (%.0f MB at 0.61 MB per "
+                  "walker) also exceed the 126 MB L2 on their own" % (args.walkers * 0.611)}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -236,12 +280,17 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the short measurements of BASELINE configs 2-5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
     if args.impl == "reference":
         run_reference_arm(args)
         return
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
 
     import torch
     import torch.distributed as dist
@@ -250,13 +299,28 @@ def main():
     from lehamoc_b200.presets import test1_walkers
     from lehamoc_b200.setup_host import pack_script, pack_script_request
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback; use --impl reference for the CPU arm)")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+
+    # ---- CPU baseline, rank 0 at N = 1 only, BEFORE any GPU work: the host cores are idle (at N > 1 the other ranks would
+    #      be spinning in NCCL next to it; the driver's separate --impl reference run covers those N)
+    cpu_line = None
+    if not args.no_cpu_baseline and world == 1:
+        cores = host_cores()
+        csets = test1_walkers(max(cores, 2))
+        arm = CpuArm(cores)
+        arm.sample(csets, 1)
+        v, wall = arm.sample(csets, 10)
+        vh, wallh = arm.sample(csets, 10, hoist=True)
+        cpu_line = {"value": v, "unit": UNIT, "cores": cores, "kind": arm.kind,
+                    "sample": arm.describe(10) + f"; one step, {wall:.1f} s wall",
+                    "hoisted_cor_factor_value": vh,
+                    "hoisted_note": f"same models with cor_factor_syn_el memoised (its arguments are constants of a run, "
+                                    f"LeMoC.py:251: identical results); {wallh:.1f} s wall"}
+        arm.close()
+
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
@@ -296,7 +360,6 @@ def main():
         sampler.start()
     launches0 = lib.lhm_launch_count()
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    kt = []
     barrier()
     t_wall0 = time.perf_counter()
     for e0, e1 in evs:
@@ -304,15 +367,13 @@ def main():
         e0.record()
         one_step()
         e1.record()
-        kt.append(None)
     barrier()
     t_wall = time.perf_counter() - t_wall0
     launches = lib.lhm_launch_count() - launches0
     step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
     total_ms = float(sum(step_ms))
-    # per-kernel device times of the last step (CUDA events recorded inside liblhm.so on the launch stream)
-    setup_ms, cor_ms, run_ms = eng.last_timings()
-    # run-kernel time averaged over a few extra launches (same inputs, L2 flushed), for the roofline
+    # run-kernel time averaged over a few extra launches (same inputs, L2 flushed), for the roofline: CUDA events
+    # recorded inside liblhm.so on the launch stream around each kernel
     run_times = []
     for _ in range(min(args.steps, 5)):
         flush.fill_(1.0)
@@ -320,8 +381,7 @@ def main():
         eng.run_into(N_out, sed, 0)
         torch.cuda.synchronize()
         run_times.append(eng.last_timings())
-    run_times = np.array(run_times)
-    setup_ms, cor_ms, run_ms = [float(x) for x in run_times.mean(axis=0)]
+    setup_ms, cor_ms, run_ms = [float(x) for x in np.array(run_times).mean(axis=0)]
     clocks = sampler.stop() if rank == 0 else None
 
     if world > 1:
@@ -330,20 +390,47 @@ def main():
         total_ms = float(tmax.item())
     value = world * W * args.steps / (total_ms * 1e-3)
 
-    # ---- end-to-end through the public API (host parameter sets in, host spectra out), every step:
-    #      host packing + pinned H2D + set-up + cor-factor + fused kernel + D2H
-    # public API of the throughput path: LeMoC.run_many(stream of parameter-dict batches) -> host spectra per batch.
-    # Every batch: the host turns the parameter dicts into one row of scalars per walker (worker thread), copies them
-    # H2D from pinned memory, the device builds grids + injection (lhm_pack_batch) and tables, evolves the walkers, and
-    # the spectra are copied D2H into pinned memory and touched on the host -- all inside the timed region.
+    # ---- the exchange step is checked, not just timed: every rank's block of the gathered array is that rank's own
+    #      result bit for bit, and rank 0 re-evolves every other rank's walkers (same seeds) on its own GPU and finds the
+    #      same bits in the gathered rows
+    allgather_check = None
+    if world > 1:
+        one_step()
+        torch.cuda.synchronize()
+        ok = bool(torch.equal(sed_all[rank * W:(rank + 1) * W], sed.view(W, eng.Nt)))
+        if rank == 0:
+            keep = sed_all.clone()
+            for r in range(1, world):
+                br = pack_script(test1_walkers(W, seed=20231 + r))
+                eng.setup(br)
+                _, sr = eng.run(want_N=False)
+                ok = ok and bool(torch.equal(keep[r * W:(r + 1) * W], sr))
+            eng.setup_device(W, *dev_in)
+        flag = torch.tensor([1.0 if ok else 0.0], dtype=torch.float64, device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        allgather_check = bool(flag.item() == 1.0)
+
+    # ---- end to end through the public API of the throughput path: LeMoC.run_many(stream of batches of parameter
+    #      dicts) -> host spectra per batch.  Every batch: the host turns the parameter dicts into one row of scalars per
+    #      walker (worker thread), pinned H2D, device-side grids + injection (lhm_pack_batch), tables, cor-factor, fused
+    #      kernel, D2H into pinned memory, results touched on the host.  At N > 1 the exchange step is inside as well:
+    #      the SEDs of the batch are all-gathered over NCCL from the engine's device buffer and the gathered rows are what
+    #      is copied to the host (every rank ends up with every walker's SED, like shard.evaluate_sharded).
     e2e_engines = [None, None]                      # two engines, one per worker thread / CUDA stream
     e2e_engines_h = [None, None]
+    gathered_host = torch.empty((world * W, eng.Nt), dtype=torch.float64, pin_memory=True) if world > 1 else None
 
     def e2e_run(nb, device_pack=True):
         tot = 0.0
-        for b2, N_h, sed_h in LeMoC.run_many((sets for _ in range(nb)), ic_path=args.ic_path,
-                                             engines=e2e_engines if device_pack else e2e_engines_h,
-                                             device_pack=device_pack):
+        engines = e2e_engines if device_pack else e2e_engines_h
+        for k, (b2, N_h, sed_h) in enumerate(LeMoC.run_many((sets for _ in range(nb)), ic_path=args.ic_path,
+                                                            engines=engines, device_pack=device_pack)):
+            if world > 1 and device_pack:
+                src = engines[k % 2]._out_dev[1]                # device SEDs of this batch (the engine is idle until the
+                dist.all_gather_into_tensor(sed_all, src.view(-1, eng.Nt)[:W])          # next batch is drawn)
+                gathered_host.copy_(sed_all, non_blocking=True)
+                torch.cuda.current_stream().synchronize()
+                tot += float(gathered_host[-1, 0])
             tot += float(sed_h[0, 0]) + float(N_h[-1, -1])
         return tot
     # a stream of batches has a fill and a drain of about one batch each: time enough batches for the steady state to
@@ -355,6 +442,10 @@ def main():
     e2e_run(e2e_nb)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        e2e_s = float(tmax.item())
     # the same with the NumPy packer on the host (bit-identical set-up; 9.4 MB of H2D per batch instead of 0.1 MB)
     e2e_run(2, False)
     t0 = time.perf_counter()
@@ -369,10 +460,6 @@ def main():
     for _ in range(args.steps):
         LeMoC.run(sets, ic_path=args.ic_path, snapshots=False, engine=eng, pinned=True)
     e2e_sync_s = time.perf_counter() - t0
-    if world > 1:
-        tmax = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        e2e_s = float(tmax.item())
     # C-ABI only (packed host arrays -> host spectra), without the NumPy packing
     t0 = time.perf_counter()
     for _ in range(args.steps):
@@ -384,7 +471,24 @@ def main():
     h2d_hostpack = int(sum(a.nbytes for a in batch.arrays()))
     req = pack_script_request(sets)
     h2d = int(req.walker_params.nbytes + req.nu_ic_row.nbytes + req.nu_tot_row.nbytes + req.ext_row.nbytes)
-    d2h = int(W * (eng.Ng + eng.Nt) * 8)
+    d2h = int(W * (eng.Ng + eng.Nt) * 8) + (int(world * W * eng.Nt * 8) if world > 1 else 0)
+
+    # ---- BASELINE configs 2-5, short (a few launches each), with a parity scalar against a committed fixture.  Config 4
+    #      is the strong-scaling case: the 1024-walker ensemble is cut over all ranks; the others run on rank 0.
+    configs = None
+    if not args.no_configs:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import config_benches as cb
+        configs = {}
+        c4 = cb.config4(1024)
+        if rank == 0:
+            configs["4_fit_emcee_1024_walkers"] = c4
+            for key, fn in (("2_test3_600_steps", lambda: cb.config2(W)), ("3_test4_full_size", lambda: cb.config3(148)),
+                            ("5_sweep_grid400_batch4096", lambda: cb.config5(400, 4096))):
+                try:
+                    configs[key] = fn()
+                except Exception as e:                              # a config that fails must not take the headline down
+                    configs[key] = {"error": f"{type(e).__name__}: {e}"}
 
     if rank != 0:
         if world > 1:
@@ -397,22 +501,24 @@ def main():
     parity = None
     if os.path.exists(gold):
         z = np.load(gold)
+        eng.setup_device(W, *dev_in)
+        eng.run_into(N_out, sed, 0)
         got = np.log10(sed[0, 0].cpu().numpy())
         parity = float(np.max(np.abs(got - z["out_log_nuLnu"][-1])[z["out_log_nuLnu"][-1] > -200]))
 
     # ---- roofline of the dominant kernel (fused step kernel): FP64 FMA pipe
     peak_tf = fp64_peak_tflops(local)
     flops_launch = float(run_flops.sum())
-    achieved_tf = flops_launch / (run_ms * 1e-3) / 1e12
+    alg_tf = flops_launch / (run_ms * 1e-3) / 1e12
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
-    alg_bytes = float(h2d + d2h)
-    # executed FP64-pipe instructions of the IC phase (path R): 4 per tile element (3 DFMA for F + 1 accumulate)
-    # plus ~45 per (o,gamma) pair for the reciprocal + log preamble; 2 flops per instruction at the FMA peak
-    pipe = None
+    alg_bytes = float(h2d + int(W * (eng.Ng + eng.Nt) * 8))
+    # executed FP64-pipe instructions of the IC phase (path R): per visited (o,gamma,nu_i) element 3 DFMA for F + 1 for
+    # the accumulation, plus ~45 per (o,gamma) pair for the reciprocal + log preamble when not tabulated
+    pipe, exe_tf = None, None
     if args.ic_path == "R":
         shared = bool(np.all(batch.g_el == batch.g_el[0]) and np.all(batch.nu_tot == batch.nu_tot[0])
                       and np.all(batch.nu_ic == batch.nu_ic[0]))
@@ -421,33 +527,35 @@ def main():
         pre = 0 if batch.cfg.get("ic_pair_table") else 45      # reciprocal + log per pair unless tabulated at set-up
         inst_step = sched[1] * 128 * 4 + sched[0] * 128 * pre
         inst_launch = inst_step * float(batch.nsteps.sum())
+        exe_tf = 2.0 * inst_launch / (run_ms * 1e-3) / 1e12
         pipe = {"ic_tiles_per_step": sched[0], "ic_tile_iterations_per_step": sched[1],
-                "ic_clamped_iterations_per_step": sched[2],
-                "executed_fp64_inst_per_launch": inst_launch,
-                "fp64_pipe_frac": 2.0 * inst_launch / (run_ms * 1e-3) / 1e12 / peak_tf,
-                "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element (+ ~45 per pair when "
-                        "the pair constants are not tabulated), inactive lanes of a tile included; compare with "
-                        "ncu sm__pipe_fp64_cycles_active"}
+                "ic_clamped_iterations_per_step": sched[2], "executed_fp64_inst_per_launch": inst_launch,
+                "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element (+ ~45 per pair when the "
+                        "pair constants are not tabulated), inactive lanes of a tile included; compare with ncu "
+                        "sm__pipe_fp64_cycles_active"}
     roofline = {"bound": "fp64", "kernel": "lhm::run_kernel (fused timestep loop, one CTA per walker)",
-                "achieved": achieved_tf, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / peak_tf,
-                "frac_note": "algorithmic count of SURVEY 8d (15 flop per (o,gamma,nu_i) element of the reference formula); "
-                             "the kernel executes 4 DFMA = 8 flop per element, so frac can exceed 1: the share of the "
-                             "FP64 pipe actually used is executed.fp64_pipe_frac",
+                "achieved": exe_tf if exe_tf is not None else alg_tf, "peak": peak_tf, "unit": "TFLOP/s",
+                "frac": (exe_tf if exe_tf is not None else alg_tf) / peak_tf,
+                "frac_is": ("EXECUTED FP64 instructions of the IC phase x 2 / kernel time / measured DFMA peak: the share of "
+                            "the FP64 pipe the kernel keeps busy (ncu sm__pipe_fp64_cycles_active is the cross-check)"
+                            if exe_tf is not None else "algorithmic flops of this path / kernel time / peak"),
+                "algorithmic": {"achieved": alg_tf, "frac": alg_tf / peak_tf, "flops_per_launch": flops_launch,
+                                "flops_per_model": float(run_flops.mean()),
+                                "note": "SURVEY 8d count: 15 flop per (o,gamma,nu_i) element of the reference formula x units "
+                                        "per launch / kernel time; the kernel's exact regrouping executes 4 DFMA = 8 flop per "
+                                        "element, so this fraction can exceed 1 -- it says how fast the reference's "
+                                        "arithmetic is delivered, not how busy the pipe is"},
                 "executed": pipe,
-                "peak_source": "measured live by lhm_fp64_peak_probe (DFMA, 8 independent chains/thread); "
-                               "MEASURED_PEAKS.json carries no FP64 figure",
-                "flops_per_launch": flops_launch, "flops_per_model": float(run_flops.mean()),
+                "peak_source": "measured live by lhm_fp64_peak_probe (DFMA, 8 independent chains/thread; 64 DFMA/clk/SM x "
+                               "148 SMs x 1.965 GHz = 37.2 nominal); MEASURED_PEAKS.json carries no FP64 figure",
                 "active_pairs_per_model": float(active.mean()), "kernel_ms": run_ms,
                 "setup_kernel_ms": setup_ms, "cor_kernel_ms": cor_ms,
                 "setup_cor_note": "cor_kernel runs on the handle's second stream concurrently with setup_kernel (both "
                                   "durations are measured while they share the GPU); run_kernel waits for both",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture of
-                # 1184 Test-1 walkers committed as profiles/r01_g_final_ncu_summary.txt (1.6139 GB + 6.9 MB), per walker
-                "traffic": (1.642121e9 + 7.229952e6) / 1184.0 * W if args.ic_path == "R" else None,
-                "traffic_source": "ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is "
-                                  "the per-step re-read of the constant-B exponential cache (543 KB per walker x 10 "
-                                  "steps, half of it exact zeros that are skipped) and of the 68 KB per-walker tables, "
-                                  "2 % of HBM bandwidth",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture
+                # committed under profiles/ (per walker, scaled by the walkers of this launch)
+                "traffic": NCU_DRAM_BYTES_PER_WALKER * W if args.ic_path == "R" else None,
+                "traffic_source": NCU_DRAM_SOURCE,
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_GBs": alg_bytes / (run_ms * 1e-3) / 1e9,
                         "peak_GBs": peaks.get("hbm_gbs"), "note": "compute-bound path: <8 KB of mandatory traffic per model"}}
@@ -455,12 +563,10 @@ def main():
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": workload_name(args), "walkers_per_gpu": W, "ic_path": args.ic_path,
-                       "timesteps_per_model": nts,
-                       "l2": "flushed between steps (256 MiB write); per-batch tables %.0f MB > 126 MB L2"
-                             % (W * eng.table_bytes_per_walker() / 1e6)},
+            "config": config_dict(args),
             "us_per_walker_timestep": total_ms * 1e3 / (args.steps * W * nts),
             "wall_ms_per_step_incl_flush": 1e3 * t_wall / args.steps,
+            "table_bytes_per_walker": eng.table_bytes_per_walker(),
             "roofline": roofline, "clocks": clocks, "gpu_launches": int(launches),
             "e2e": {"value": world * W * e2e_nb / e2e_s, "batches_timed": e2e_nb, "unit": UNIT, "h2d_bytes_per_step": h2d,
                     "d2h_bytes_per_step": d2h,
@@ -468,12 +574,18 @@ def main():
                             "dicts -> one row of scalars per walker (host) + pinned H2D + device-side grid/injection "
                             "set-up (lhm_pack_batch) + tables + cor-factor + fused kernel + D2H into pinned memory; "
                             "two worker threads with their own engine and CUDA stream, so one batch's host work and "
-                            "copies overlap the other's kernels",
+                            "copies overlap the other's kernels"
+                            + ("; at N > 1 the SEDs of every batch are also all-gathered over NCCL and the gathered "
+                               "[N*W, Nt] rows copied to the host on every rank" if world > 1 else ""),
                     "host_packed_value": world * W * e2e_nb / e2e_hostpack_s,
                     "host_packed_h2d_bytes_per_step": h2d_hostpack,
                     "synchronous_value": world * W * args.steps / e2e_sync_s,
                     "c_abi_only_value": world * W * args.steps / abi_s, "host_packing_ms": 1e3 * pack_s},
             "parity_check_max_dlog10_walker0": parity}
+    if allgather_check is not None:
+        line["allgather_check"] = allgather_check
+    if configs is not None:
+        line["configs"] = configs
 
     if not args.no_fast_path and args.ic_path == "R":
         # the exact suffix-sum formulation (path S) reported next to the triple-sum kernel, with its OWN flop count
@@ -497,17 +609,8 @@ def main():
                              "note": "latency/transcendental-bound; never divide this time by path-R flops"}
         engS.close()
 
-    if not args.no_cpu_baseline:
-        cores = host_cores()
-        v, wall = cpu_sample(sets[:max(cores, 1)], cores, timesteps=10, literal=True)
-        vh, wallh = cpu_sample(sets[:max(cores, 1)], cores, timesteps=10, literal=False)
-        line["cpu_baseline"] = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": f"{cores} Test-1 models, one per core (multiprocessing.Pool as fit_emcee.py:239), "
-                                          f"all 10 timesteps, loop-structured NumPy port with cor_factor_syn_el recomputed "
-                                          f"every step like LeMoC.py:251; {wall:.1f} s wall",
-                                "hoisted_vectorised_port_value": vh,
-                                "hoisted_note": f"same models with cor_factor hoisted and the gamma loop broadcast "
-                                                f"(bit-identical results); {wallh:.1f} s wall"}
+    if cpu_line is not None:
+        line["cpu_baseline"] = cpu_line
     emit(line)
     if world > 1:
         dist.barrier()

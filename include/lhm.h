@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LHM_VERSION 101
+#define LHM_VERSION 102
 
 typedef enum {
     LHM_OK = 0,
@@ -246,11 +246,14 @@ enum {
     LHM_PK_P,               /* p_el */
     LHM_PK_COMP_INJ,        /* compactness used for the injection                           LeMoC.py:110,174 / Code.py:163 */
     LHM_PK_COMP_COR,        /* value handed to cor_factor_syn_el (Code.py:237 passes the log)                  */
-    LHM_PK_THRMIN, LHM_PK_THRMAX,   /* 10**g_PL_min, 10**g_PL_max (host pow, like the reference's scalars)      */
+    LHM_PK_IDXMIN, LHM_PK_IDXMAX,   /* index_PL_min, index_PL_max (-1: g_PL_max == g_max_el) as the reference's own
+                                       comparison `g_el > 10**g_PL_max` on the NumPy grid gives them: integers computed
+                                       by the host (LeMoC.py:120-128), so that a grid point that coincides with a
+                                       threshold cannot move the window by a bin                                  */
     /* protons of Code.py::LeHaMoC (Code.py:299-300,325-347,419-422); used when lhm_pack_args.g_pr != NULL */
     LHM_PK_GMIN_PR, LHM_PK_GMAX_PR,         /* log10 limits of the proton grid                                  */
     LHM_PK_GPLMIN_PR, LHM_PK_GPLMAX_PR,     /* log10 limits of the proton power law                             */
-    LHM_PK_THRMIN_PR, LHM_PK_THRMAX_PR,     /* 10** of the two above                                            */
+    LHM_PK_IDXMIN_PR, LHM_PK_IDXMAX_PR,     /* window indices on the proton grid, host-computed like the two above */
     LHM_PK_P_PR, LHM_PK_COMP_PR,            /* p_pr, proton compactness 10**P9                                  */
     LHM_PACK_NPAR = 20
 };

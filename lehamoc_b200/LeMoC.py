@@ -35,8 +35,10 @@ def run_many(batches, ic_path="R", engines=None, depth=2, device_pack=True):
     This is the throughput path for sweeps and samplers: `depth` worker threads each own an engine on its own CUDA
     stream and do packing (NumPy) -> pinned H2D -> set-up + cor-factor + fused kernel -> D2H for their batch, so the
     host work and the copies of one batch overlap the kernels of the other (NumPy and the ctypes call release the
-    GIL).  The yielded spectra are views of that engine's page-locked buffers: they stay valid until `depth` more
-    batches have been drawn; copy them if they must live longer.
+    GIL).  The yielded spectra are views of page-locked buffers of the engine that produced them; every engine
+    alternates between two such buffer pairs, so the arrays of batch k stay valid until `depth` more batches have been
+    DRAWN from the generator (batch k + 2*depth, the next user of the same pair, is submitted when batch k + depth + 1
+    is requested); copy them if they must live longer.
 
     device_pack=True (default): the grids, the injection and the scalar block of every walker are built on the device
     (lhm_pack_batch) from one row of scalars per walker; the yielded `batch` is then a setup_host.PackRequest (cfg,
@@ -50,16 +52,17 @@ def run_many(batches, ic_path="R", engines=None, depth=2, device_pack=True):
         engines.append(None)
     streams = [torch.cuda.Stream() for _ in range(depth)]
 
-    def work(slot, sets):
+    def work(k, sets):
+        slot, pair = k % depth, (k // depth) % 2
         batch = pack_script_request(sets) if device_pack else pack_script(sets)
         with torch.cuda.stream(streams[slot]):
             eng = engines[slot]
-            if eng is None or eng.max_walkers < batch.W or any(eng.cfg.get(k) != v for k, v in batch.cfg.items()):
+            if eng is None or eng.max_walkers < batch.W or any(eng.cfg.get(k_) != v for k_, v in batch.cfg.items()):
                 eng = engines[slot] = Engine(batch.cfg, max(batch.W, 1), ic_path=ic_path)
             if device_pack:
-                N, sed = eng.run_packed_host(batch)
+                N, sed = eng.run_packed_host(batch, out_slot=pair)
             else:
-                N, sed = eng.run_host(batch, snapshots=0, pinned=True)
+                N, sed = eng.run_host(batch, snapshots=0, pinned=True, out_slot=pair)
         return batch, N, sed
 
     it = iter(batches)
@@ -67,7 +70,7 @@ def run_many(batches, ic_path="R", engines=None, depth=2, device_pack=True):
         window = []
         k = 0
         for sets in it:
-            window.append(pool.submit(work, k % depth, sets))
+            window.append(pool.submit(work, k, sets))
             k += 1
             if len(window) == depth:
                 yield window.pop(0).result()

@@ -31,8 +31,8 @@ class lhm_config(C.Structure):
 
 
 LHM_PACK_NPAR = 20
-(PK_R0, PK_B0, PK_GMIN, PK_GMAX, PK_GPLMIN, PK_GPLMAX, PK_P, PK_COMP_INJ, PK_COMP_COR, PK_THRMIN, PK_THRMAX,
- PK_GMIN_PR, PK_GMAX_PR, PK_GPLMIN_PR, PK_GPLMAX_PR, PK_THRMIN_PR, PK_THRMAX_PR, PK_P_PR, PK_COMP_PR) = range(19)
+(PK_R0, PK_B0, PK_GMIN, PK_GMAX, PK_GPLMIN, PK_GPLMAX, PK_P, PK_COMP_INJ, PK_COMP_COR, PK_IDXMIN, PK_IDXMAX,
+ PK_GMIN_PR, PK_GMAX_PR, PK_GPLMIN_PR, PK_GPLMAX_PR, PK_IDXMIN_PR, PK_IDXMAX_PR, PK_P_PR, PK_COMP_PR) = range(19)
 
 
 class lhm_pack_args(C.Structure):                    # include/lhm.h: lhm_pack_args

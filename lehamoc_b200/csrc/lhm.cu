@@ -60,6 +60,20 @@ __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlag
     C.Rad = C.R0; C.B = C.B0; C.V = volume_of(C.R0);
 }
 
+
+// A walker with zero timesteps has no output in the reference (LeMoC.py:196 loops over range(0), Code.py:277 fails on
+// an unbound name): the host packers refuse such requests; a caller that packs its own `consts` gets NaN rows instead
+// of whatever the output buffers held.
+template <int NTH>
+__device__ void no_step_outputs(const RunArgs& A, int w, int Ng, int Nt, int Np) {
+    const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    if (A.sed_out) for (int k = threadIdx.x; k < S_ * Nt; k += NTH) A.sed_out[(size_t)w * S_ * Nt + k] = nan;
+    if (A.N_out) for (int k = threadIdx.x; k < S_ * Ng; k += NTH) A.N_out[(size_t)w * S_ * Ng + k] = nan;
+    if (A.Np_out) for (int k = threadIdx.x; k < S_ * Np; k += NTH) A.Np_out[(size_t)w * S_ * Np + k] = nan;
+    if (A.Nnu_out) for (int k = threadIdx.x; k < S_ * 50; k += NTH) A.Nnu_out[(size_t)w * S_ * 50 + k] = nan;
+}
+
 #ifndef LHM_MIN_CTAS
 #define LHM_MIN_CTAS 2
 #endif
@@ -75,6 +89,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
     const double cor = A.cor ? A.cor[w] : 1.0;
+    if (nsteps < 1) { no_step_outputs<NT>(A, w, Ng, Nt, 0); return; }
 
     // initial state (LeMoC.py:172-183)
     for (int j = tid; j < Ng; j += NT) {
@@ -171,6 +186,7 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
     const double cor = A.cor ? A.cor[w] : 1.0;
     const double n_H = A.consts[(size_t)w * LHM_NCONST + LHM_C_NH], p_pr = A.consts[(size_t)w * LHM_NCONST + LHM_C_PPR];
+    if (nsteps < 1) { no_step_outputs<NTL>(A, w, Ng, Nt, Np); return; }
     // initial state (LeHaMoC.py:222-259): N_el = el_inj * Volume(R0), N_pr = 0, photons 1e-260
     const double V0 = volume_of(C.R0);
     for (int j = tid; j < Ng; j += NTL) {
@@ -281,6 +297,7 @@ __global__ void __launch_bounds__(NT, 2) run_code_lh_kernel(RunArgs A) {
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
     const double cor = A.cor ? A.cor[w] : 1.0;
+    if (nsteps < 1) { no_step_outputs<NT>(A, w, Ng, Nt, Np); return; }
     for (int j = tid; j < Ng; j += NT) {
         S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];
         S.qee[j] = 0.0;

@@ -41,27 +41,18 @@ __global__ void __launch_bounds__(PACK_NT) pack_kernel(PackArgs A) {
     const int Ng = A.Ng, Nh = A.Nh, Nt = A.Nt;
     const double* P = A.wp + (size_t)w * LHM_PACK_NPAR;
     const double R0 = P[LHM_PK_R0], B0 = P[LHM_PK_B0], g_min = P[LHM_PK_GMIN], g_max = P[LHM_PK_GMAX];
-    const double p_el = P[LHM_PK_P], thr_min = P[LHM_PK_THRMIN], thr_max = P[LHM_PK_THRMAX];
+    const double p_el = P[LHM_PK_P];
     double* g = A.g_el + (size_t)w * Ng;
-    __shared__ int s_imax, s_below, s_imax_p, s_below_p;
-    if (tid == 0) { s_imax = Ng; s_below = 0; s_imax_p = A.Np; s_below_p = 0; }
     // protons of Code.py::LeHaMoC (Code.py:299-300,325-347,419-422): grid, power-law window, number-rate injection
     if (A.g_pr) {
         const int Np = A.Np;
         double* gp = A.g_pr + (size_t)w * Np;
-        const double thr_lo = P[LHM_PK_THRMIN_PR], thr_hi = P[LHM_PK_THRMAX_PR], p_pr = P[LHM_PK_P_PR];
+        const double p_pr = P[LHM_PK_P_PR];
         for (int j = tid; j < Np; j += PACK_NT) gp[j] = exp10(linspace_pt(P[LHM_PK_GMIN_PR], P[LHM_PK_GMAX_PR], j, Np));
         __syncthreads();
-        int imax = Np, below = 0;
-        for (int j = tid; j < Np; j += PACK_NT) {
-            if (gp[j] > thr_hi) imax = min(imax, j);
-            if (gp[j] < thr_lo) below++;
-        }
-        atomicMin(&s_imax_p, imax);
-        atomicAdd(&s_below_p, below);
-        __syncthreads();
-        const int ip_max = (P[LHM_PK_GPLMAX_PR] == P[LHM_PK_GMAX_PR]) ? -1 : s_imax_p;
-        const int ip_min = (P[LHM_PK_GPLMIN_PR] == 0.) ? 1 : s_below_p - 1;
+        // power-law window: the host's integers (the reference's comparison on the NumPy grid), clamped into the grid
+        const int ip_max = min((int)P[LHM_PK_IDXMAX_PR], Np - 1);
+        const int ip_min = max(0, min((int)P[LHM_PK_IDXMIN_PR], Np - 1));
         const int stop_p = ip_max < 0 ? Np + ip_max : ip_max;
         const double g_lo = gp[ip_min], g_hi = gp[ip_max < 0 ? Np - 1 : min(ip_max, Np - 1)];
         const double Lp = A.four_pi * R0 * A.m_pr * A.c3 * P[LHM_PK_COMP_PR] / A.sigmaT;
@@ -76,19 +67,11 @@ __global__ void __launch_bounds__(PACK_NT) pack_kernel(PackArgs A) {
     }
     for (int j = tid; j < Ng; j += PACK_NT) g[j] = exp10(linspace_pt(g_min, g_max, j, Ng));         // LeMoC.py:115
     __syncthreads();
-    // power-law window, LeMoC.py:120-128: first index above 10**g_PL_max (or -1), last index below 10**g_PL_min (or 1)
-    {
-        int imax = Ng, below = 0;
-        for (int j = tid; j < Ng; j += PACK_NT) {
-            if (g[j] > thr_max) imax = min(imax, j);
-            if (g[j] < thr_min) below++;
-        }
-        atomicMin(&s_imax, imax);
-        atomicAdd(&s_below, below);
-    }
-    __syncthreads();
-    const int idx_max = (P[LHM_PK_GPLMAX] == g_max) ? -1 : s_imax;
-    const int idx_min = (P[LHM_PK_GPLMIN] == 0.) ? 1 : s_below - 1;
+    // power-law window, LeMoC.py:120-128: first index above 10**g_PL_max (or -1), last index below 10**g_PL_min (or 1) --
+    // evaluated by the host with the reference's comparison on the NumPy grid (this kernel's exp10 may differ from
+    // np.logspace in the last bits, which must not move the window)
+    const int idx_max = min((int)P[LHM_PK_IDXMAX], Ng - 1);
+    const int idx_min = max(0, min((int)P[LHM_PK_IDXMIN], Ng - 1));
     const int stop = idx_max < 0 ? Ng + idx_max : idx_max;
     const double g_lo = g[idx_min], g_hi = g[idx_max < 0 ? Ng - 1 : min(idx_max, Ng - 1)];
     // frequency grids, LeMoC.py:131-133,185

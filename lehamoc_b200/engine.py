@@ -222,9 +222,10 @@ class Engine:
             pool[key] = t
         return t.numpy()[:n].reshape(shape)
 
-    def run_host(self, batch: Batch, snapshots: int = 0, N_out=None, sed_out=None, pinned: bool = False):
+    def run_host(self, batch: Batch, snapshots: int = 0, N_out=None, sed_out=None, pinned: bool = False, out_slot: int = 0):
         """lhm_run_batch_host: host buffers in, host buffers out (H2D + set-up + run + D2H + sync).
-        With pinned=True the returned arrays are views of reusable page-locked buffers."""
+        With pinned=True the returned arrays are views of reusable page-locked buffers: the pair named by `out_slot`,
+        overwritten by the next call with the same slot."""
         W = batch.W
         S = snapshots if snapshots > 0 else 1
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
@@ -235,9 +236,9 @@ class Engine:
             for dst, src in zip(ins, batch.arrays()):
                 np.copyto(dst, src)
             if N_out is None:
-                N_out = self._pinned("N", (W, S, self.Ng))
+                N_out = self._pinned(f"N{out_slot}", (W, S, self.Ng))
             if sed_out is None:
-                sed_out = self._pinned("sed", (W, S, self.Nt))
+                sed_out = self._pinned(f"sed{out_slot}", (W, S, self.Nt))
         if N_out is None:
             N_out = np.empty((W, S, self.Ng))
         if sed_out is None:
@@ -250,19 +251,21 @@ class Engine:
             return N_out.reshape(W, S, self.Ng)[:, 0], sed_out.reshape(W, S, self.Nt)[:, 0]
         return N_out, sed_out
 
-    def run_packed_host(self, req):
+    def run_packed_host(self, req, out_slot: int = 0):
         """Device-packed twin of run_host(pinned=True): PackRequest in, (n_e [W,Ng], nuLnu [W,Nt]) out as views of
-        page-locked host buffers; final state only.  H2D: one row of scalars per walker + three shared grids."""
+        page-locked host buffers (the pair named by `out_slot`, overwritten by the next call with the same slot);
+        final state only.  H2D: one row of scalars per walker + three shared grids."""
         self.setup_packed(req)
         W = req.W
         if getattr(self, "_out_dev", None) is None:
             self._out_dev = (self._new(self.max_walkers, 1, self.Ng), self._new(self.max_walkers, 1, self.Nt))
         Nd, sd = self._out_dev
         self.run_into(Nd, sd, 0)
-        Nh_, sh_ = self._pinned("N", (W, self.Ng)), self._pinned("sed", (W, self.Nt))
+        kN, kS = f"N{out_slot}", f"sed{out_slot}"
+        Nh_, sh_ = self._pinned(kN, (W, self.Ng)), self._pinned(kS, (W, self.Nt))
         with torch.cuda.stream(self.stream):
-            self._pin["N"][:W * self.Ng].copy_(Nd.view(-1)[:W * self.Ng], non_blocking=True)
-            self._pin["sed"][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
+            self._pin[kN][:W * self.Ng].copy_(Nd.view(-1)[:W * self.Ng], non_blocking=True)
+            self._pin[kS][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
         self.stream.synchronize()
         return Nh_, sh_
 

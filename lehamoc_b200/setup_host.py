@@ -203,6 +203,50 @@ def _pow10(x):
     return np.power(10., np.asarray(x, dtype=np.float64))
 
 
+def _logspace_points(lo, hi, n, idx):
+    """np.logspace(lo[w], hi[w], n)[idx[w, k]] without building the rows: np.linspace is `arange*step + start` with
+    the last point set to `stop`, np.logspace raises 10 to it with np.power -- the same two expressions here, on the
+    requested points only (same doubles as the full rows; tests/test_host_and_abi.py checks that)."""
+    step = (hi - lo) / (n - 1)
+    y = idx * step[:, None] + lo[:, None]
+    y = np.where(idx == n - 1, hi[:, None], y)
+    return np.power(10., y)
+
+
+def _window_indices(lo, hi, n, pl_min, pl_max):
+    """index_PL_min, index_PL_max of LeMoC.py:120-128 / Code.py:82-90 for every walker, with the reference's own
+    comparisons (`g_el > 10**g_PL_max`, `g_el < 10**g_PL_min`; thresholds through Python's float pow) on the NumPy
+    grid values -- evaluated only on a few candidates around the arithmetic position of the threshold, O(W) instead
+    of O(W*Ng).  Walkers whose candidates do not bracket the threshold fall back to the full row."""
+    W = len(lo)
+    thr_max = np.array([10 ** x for x in pl_max.tolist()])
+    thr_min = np.array([10 ** x for x in pl_min.tolist()])
+    step = (hi - lo) / (n - 1)
+    off = np.arange(-2, 4)[None, :]
+
+    def first_true(thr, target, pred):
+        """first index j with pred(g[j], thr) for a predicate that is monotone along the grid; n if none"""
+        with np.errstate(invalid="ignore", divide="ignore"):
+            guess = np.floor((target - lo) / step)
+        guess = np.nan_to_num(guess, nan=0., posinf=n - 1., neginf=0.)
+        cand = np.clip(guess[:, None].astype(np.int64) + off, 0, n - 1)
+        ok = pred(_logspace_points(lo, hi, n, cand), thr[:, None])
+        out = np.where(ok.any(axis=1), cand[np.arange(W), ok.argmax(axis=1)], n)
+        # bracket check: predicate false on the first candidate (or it is grid index 0 and true) and true on the last
+        # (or it is the last grid index and false)
+        good = (~ok[:, 0] | (cand[:, 0] == 0)) & (ok[:, -1] | (cand[:, -1] == n - 1))
+        for w in np.flatnonzero(~good):
+            row = pred(np.logspace(lo[w], hi[w], n), thr[w])
+            out[w] = int(row.argmax()) if row.any() else n
+        return out
+    first_gt = first_true(thr_max, pl_max, lambda g, t: g > t)
+    first_ge = first_true(thr_min, pl_min, lambda g, t: ~(g < t))          # count of g < thr
+    same = pl_max == hi
+    if np.any(~same & (first_gt >= n)) or np.any((pl_min != 0.) & (first_ge < 1)):
+        raise ValueError("power-law window outside the gamma grid (the reference raises here too)")
+    return np.where(pl_min == 0., 1, first_ge - 1), np.where(same, -1, first_gt)
+
+
 def _pack_request(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> PackRequest:
     """Host part of the device-side set-up: the scalars the reference evaluates with Python floats (10**x thresholds)
     and the grids that do not depend on the walker (nu_ic, nu_tot, external photon fields), with the reference's NumPy
@@ -217,8 +261,15 @@ def _pack_request(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_
     wp[:, _lib.PK_GMIN], wp[:, _lib.PK_GMAX] = g_min_el, g_max_el
     wp[:, _lib.PK_GPLMIN], wp[:, _lib.PK_GPLMAX] = g_PL_min, g_PL_max
     wp[:, _lib.PK_P], wp[:, _lib.PK_COMP_INJ], wp[:, _lib.PK_COMP_COR] = p_el, comp_inj, comp_cor
-    wp[:, _lib.PK_THRMIN] = _pow10(g_PL_min)
-    wp[:, _lib.PK_THRMAX] = _pow10(g_PL_max)
+    wp[:, _lib.PK_IDXMIN], wp[:, _lib.PK_IDXMAX] = _window_indices(g_min_el, g_max_el, Ng, g_PL_min, g_PL_max)
+    # zero timesteps (LeMoC.py:196 loops over range(0), Code.py:183 never enters its while): the reference produces no
+    # output, so the request is refused like Batch.__post_init__ does for the host-packed path
+    if variant == "script":
+        zero = int(float(F["time_end"])) < 1
+    else:
+        zero = bool(np.any(~(float(F["time_init"]) < float(F["time_end"]) * R0 / c)))
+    if zero:
+        raise ValueError("time_init/time_end/step_alg give a walker zero timesteps: the reference produces no output")
     nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
     nu_tot = np.logspace(np.log10(np.logspace(7.5, 8.5, 2)[0]), np.log10(nu_ic[-1]), Nt)   # LeMoC.py:131,133
     Vexp = float(F["Vexp"]) * c
@@ -655,8 +706,7 @@ def pack_code_lehamoc_request(thetas, frozen: dict) -> PackRequest:
     wp = req.walker_params
     wp[:, _lib.PK_GMIN_PR], wp[:, _lib.PK_GMAX_PR] = gmin, gmax
     wp[:, _lib.PK_GPLMIN_PR], wp[:, _lib.PK_GPLMAX_PR] = lo_t, hi_t
-    wp[:, _lib.PK_THRMIN_PR] = _pow10(lo_t)
-    wp[:, _lib.PK_THRMAX_PR] = _pow10(hi_t)
+    wp[:, _lib.PK_IDXMIN_PR], wp[:, _lib.PK_IDXMAX_PR] = _window_indices(gmin, gmax, int(float(F["grid_g_pr"])), lo_t, hi_t)
     wp[:, _lib.PK_P_PR] = thetas[:, 9]
     wp[:, _lib.PK_COMP_PR] = _pow10(thetas[:, 8])
     req.cfg.update(driver=2, Np=int(float(F["grid_g_pr"])), esc_flag_pr=req.cfg["esc_flag"], shared_ic_grids=0)

@@ -28,8 +28,12 @@ import time
 
 import numpy as np
 
-REF_ROOT = "/root/reference"
 SHIM = os.path.join(os.path.dirname(os.path.abspath(__file__)), "shim")
+# the reference tree: /root/reference in the build container; on the GPU box the git-ignored copy of the few files the
+# CPU arm of bench.py executes, made by oracle/install_reference.py (baseline/_ref travels with the snapshot)
+INSTALLED = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+REF_ROOT = next((d for d in (os.environ.get("LHM_REF_ROOT", ""), "/root/reference", INSTALLED)
+                 if d and os.path.isdir(os.path.join(d, "LeMoC"))), "/root/reference")
 
 
 def reference_available() -> bool:
@@ -192,6 +196,40 @@ def run_lemoc_script(param_file: str, memo_cor: bool = True, extra_files: dict |
     if rec.cor:
         cap["cor_factor"] = np.float64(rec.cor[0])
     return cap, wall, (part_txt, phot_txt)
+
+
+def time_lemoc_script(params: dict, hoist_cor: bool = False) -> float:
+    """Wall seconds of one UNMODIFIED `python LeMoC.py <file> <suffix>` run on the parameter set `params` (the CPU arm
+    of bench.py): the script is exec'd as it stands -- parameter parsing, set-up, every timestep, both output files --
+    with nothing wrapped or recorded.  hoist_cor=True memoises cor_factor_syn_el (its arguments are constants of a
+    run, LeMoC.py:251: same results, reported next to the plain number so that the reference's redundant work is
+    visible)."""
+    with _ref_env("LeMoC") as (ref_dir, tmp):
+        pf = os.path.join(tmp, "Parameters_run.txt")
+        write_params(pf, params)
+        f = importlib.import_module("LeHaMoC_f")
+        if hoist_cor:
+            orig, memo = f.cor_factor_syn_el, {}
+
+            def cor(g, R0, B0, p, L):
+                key = (np.asarray(g).tobytes(), float(R0), float(B0), float(p), float(L))
+                if key not in memo:
+                    memo[key] = orig(g, R0, B0, p, L)
+                return memo[key]
+            f.cor_factor_syn_el = cor
+        src = open(os.path.join(ref_dir, "LeMoC.py")).read()
+        sys.argv[:] = ["LeMoC.py", pf, "run"]
+        import tqdm as _tqdm
+        real_tqdm = _tqdm.tqdm
+        _tqdm.tqdm = lambda it, **k: it
+        code = compile(src, "LeMoC.py", "exec")
+        t0 = time.perf_counter()
+        try:
+            with contextlib.redirect_stdout(io.StringIO()), np.errstate(all="ignore"):
+                exec(code, {"__name__": "__main__"})
+        finally:
+            _tqdm.tqdm = real_tqdm
+        return time.perf_counter() - t0
 
 
 def run_code_lemoc(params, param_file="Parameters.txt", memo_cor: bool = True):

@@ -348,6 +348,67 @@ def test_run_many_matches_run(device_pack):
             np.testing.assert_array_equal(N, Nr[:, 0])
 
 
+@pytest.mark.parametrize("device_pack", [False, True])
+def test_run_many_results_outlive_the_next_draws(device_pack):
+    """The yielded arrays are views of page-locked buffers: held WITHOUT copying, result k must still be intact after
+    `depth` further batches have been drawn (the docstring's promise; each engine alternates two buffer pairs)."""
+    from lehamoc_b200 import LeMoC
+    _, P = load_golden("test1")
+    P.update(grid_g_el=70., grid_nu=40., time_end=3.)
+    depth = 2
+    batches = [[dict(P, B0=0.5 + 0.07 * (i + 3 * k), p_el=1.7 + 0.05 * i) for i in range(4)] for k in range(9)]
+    ref = [LeMoC.run(b, snapshots=False) for b in batches]
+    held = []
+    for k, (b, N, sed) in enumerate(LeMoC.run_many(iter(batches), depth=depth, device_pack=device_pack)):
+        held.append((N, sed))                      # no copy
+        j = k - depth                              # `depth` more batches have been drawn since result j
+        if j >= 0:
+            Nj, sedj = held[j]
+            if device_pack:
+                assert_spectra_close(sedj, ref[j][2][:, 0], f"held result {j} nuLnu")
+                assert_spectra_close(Nj, ref[j][1][:, 0], f"held result {j} n_e")
+            else:
+                np.testing.assert_array_equal(sedj, ref[j][2][:, 0])
+                np.testing.assert_array_equal(Nj, ref[j][1][:, 0])
+
+
+@pytest.mark.parametrize("variant", ["script", "code"])
+def test_device_packed_path_refuses_zero_timesteps(variant):
+    """time_end <= 0 (script) / time_init >= time_end*R0/c (Code.py): the reference produces no output; the
+    device-packed default path refuses the request like the host packer does, and a caller that bypasses the packers
+    gets NaN rows, never stale or uninitialised memory."""
+    import torch
+    from lehamoc_b200 import setup_host as sh
+    from lehamoc_b200.engine import Engine
+    if variant == "script":
+        _, P = load_golden("test1")
+        P.update(grid_g_el=60., grid_nu=40.)
+        with pytest.raises(ValueError):
+            sh.pack_script_request([dict(P, time_end=0.5)])
+        with pytest.raises(ValueError):
+            sh.pack_script([dict(P, time_end=0.5)])
+        b = sh.pack_script([dict(P, time_end=2.), dict(P, time_end=2., B0=2.)])
+    else:
+        cf, P = load_golden("code_fit")
+        th = np.array(cf["thetas"])[:2]
+        with pytest.raises(ValueError):
+            sh.pack_code_request(th, dict(P, time_init=1e30))
+        with pytest.raises(ValueError):
+            sh.pack_code(th, dict(P, time_init=1e30))
+        b = sh.pack_code(th, P)
+    from lehamoc_b200 import _lib
+    b.consts[1, _lib.C_NSTEPS] = 0.                 # bypass the packers
+    eng = Engine(b.cfg, b.W)
+    eng.setup(b)
+    N = torch.full((b.W, 1, eng.Ng), 7.0, dtype=torch.float64, device="cuda")
+    sed = torch.full((b.W, 1, eng.Nt), 7.0, dtype=torch.float64, device="cuda")
+    eng.run_into(N, sed, 0)
+    torch.cuda.synchronize()
+    assert torch.isfinite(sed[0]).all() and torch.isfinite(N[0]).all() and not (sed[0] == 7.0).any()
+    assert torch.isnan(sed[1]).all() and torch.isnan(N[1]).all()
+    eng.close()
+
+
 def test_code_lehamoc_matches_reference():
     """Fit_emcee/Code.py::LeHaMoC (leptonic + proton synchrotron) at the reference's hadronic start point and four
     perturbed walkers, one launch."""

@@ -75,7 +75,7 @@ def test_library_exports_every_declared_symbol():
     lib = _lib.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.lhm_version() == 101
+    assert lib.lhm_version() == 102
     assert b"no CPU fallback" in lib.lhm_strerror(-3)
     # struct layout agreed between header and binding
     n_int_fields = len(re.search(r"typedef struct \{(.*?)\} lhm_config;", header, re.S).group(1)
@@ -141,3 +141,32 @@ def test_zero_timesteps_are_refused():
     _, P = load_golden("test1")
     with pytest.raises(ValueError):
         setup_host.pack_script(dict(P, time_end=0.))
+
+
+def test_window_indices_are_the_references():
+    """The device-packed path gets index_PL_min / index_PL_max from the host (setup_host._window_indices evaluates the
+    reference's comparison on a few NumPy grid points around the threshold): identical to LeMoC.py:120-128 on the full
+    np.logspace row, also when a threshold coincides with a grid point to the last bit."""
+    from lehamoc_b200 import setup_host as sh
+    rng = np.random.default_rng(1)
+    W = 4000
+    for n in (160, 260, 37):
+        lo = rng.uniform(-1, 2, W)
+        hi = lo + rng.uniform(3, 7, W)
+        pl_min = np.where(rng.random(W) < 0.2, 0., lo + rng.uniform(0.01, 1.5, W))
+        pl_max = np.where(rng.random(W) < 0.2, hi, hi - rng.uniform(0.01, 1.5, W))
+        for w in range(W // 2):                     # adversarial half: thresholds sitting on a grid point
+            g = np.logspace(lo[w], hi[w], n)
+            j = rng.integers(2, n - 2)
+            if w % 2:
+                pl_max[w] = np.log10(g[j])
+            else:
+                pl_min[w] = np.log10(g[j])
+        imin, imax = sh._window_indices(lo, hi, n, pl_min, pl_max)
+        for w in range(W):
+            g = np.logspace(lo[w], hi[w], n)
+            rmax = -1 if pl_max[w] == hi[w] else int(np.min(np.where(g > 10 ** pl_max[w])[0]))
+            rmin = 1 if pl_min[w] == 0. else int(np.max(np.where(g < 10 ** pl_min[w])[0]))
+            assert (rmin, rmax) == (imin[w], imax[w]), (n, w)
+    with pytest.raises(ValueError):                 # window above the grid: the reference raises (min of empty)
+        sh._window_indices(np.array([0.]), np.array([4.]), 50, np.array([1.]), np.array([5.]))
