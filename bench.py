@@ -26,10 +26,11 @@ import numpy as np  # noqa: E402
 METRIC = "model-evals/sec (Test-1 SSC to steady state)"
 UNIT = "model-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch of 1184 Test-1 walkers (ncu --set full)
-NCU_DRAM_BYTES_PER_WALKER = (1.642121e9 + 7.229952e6) / 1184.0
-NCU_DRAM_SOURCE = ("ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is the per-step re-read of "
-                   "the constant-B exponential cache (543 KB per walker x 10 steps, half of it exact zeros that are "
-                   "skipped) and of the 68 KB per-walker tables, 2 % of HBM bandwidth")
+NCU_DRAM_BYTES_PER_WALKER = {"R": (1.642121e9 + 7.229952e6) / 1184.0, "G": None}
+NCU_DRAM_SOURCE = {"R": ("ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is the per-step "
+                         "re-read of the constant-B exponential cache (543 KB per walker x 10 steps, half of it exact zeros "
+                         "that are skipped) and of the 68 KB per-walker tables, 2 % of HBM bandwidth"),
+                   "G": None}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -80,6 +81,37 @@ def ic_tile_schedule(batch, w=0, OG=8, GB=16):
             iters += Ntar - i0
             clamped += max(i1 - i0, 0)
     return tiles, iters, clamped
+
+
+def icg_schedule(batch, w=0):
+    """Replays icg_setup_kernel (lhm_icg.cuh) for the shared grids of the batch: returns (gamma-pair tiles with work,
+    k-steps executed, k-steps executed with the clamp) of one contraction launch per 32-walker block.  One k-step of a
+    tile = 2 A fragments (8 nu_out x 4 nu_in each) against 4 blocks of 8 walkers: 8 DMMA + 6 DFMA warp instructions."""
+    h, m_el, c = 6.62607015e-27, 9.1093837015e-28, 2.99792458e10
+    g = batch.g_el[w]
+    no = batch.nu_ic[w, :-1]
+    x = 1.0 / batch.nu_tot[w, :-1]
+    Ntar, Ng, No = len(x), len(g), len(no)
+    KS = (Ntar + 3) // 4
+    eps = h * no / (m_el * c ** 2.)
+    act = g[None, :] > eps[:, None]
+    with np.errstate(divide="ignore", invalid="ignore"):
+        A = no[:, None] * (1.0 / (g[None, :] - eps[:, None])) * (1.0 / (4.0 * g))[None, :]
+    tiles = ksteps = kclamp = 0
+    for o0 in range(0, No, 8):
+        for j0 in range(0, Ng, 2):
+            a = act[o0:o0 + 8, j0:j0 + 2]
+            if not a.any():
+                continue
+            Av = A[o0:o0 + 8, j0:j0 + 2][a]
+            lo, hi = Av.min() * x < 1.0, Av.max() * x < 1.0
+            is0 = int(np.argmax(lo)) if lo.any() else Ntar
+            is1 = int(np.argmax(hi)) if hi.any() else Ntar
+            ks0, ksc = max(is0 - 1, 0) // 4, (min(is1 + 1, Ntar) + 3) // 4
+            tiles += 1
+            ksteps += KS - ks0
+            kclamp += max(min(ksc, KS) - ks0, 0)
+    return tiles, ksteps, kclamp
 
 
 class ClockSampler:
@@ -276,7 +308,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--walkers", type=int, default=1184,
                     help="walkers per GPU (default 1184 = 4 full waves of 148 SMs x 2 resident walker CTAs)")
-    ap.add_argument("--ic-path", default="R", choices=["R", "S"])
+    ap.add_argument("--ic-path", default="R", choices=["R", "S", "G"])
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true")
@@ -329,7 +361,9 @@ def main():
     sets = test1_walkers(W, seed=20231 + rank)                                # weak scaling: W new walkers per rank
     batch = pack_script(sets)
     eng = Engine(batch.cfg, W, ic_path=args.ic_path)
-    run_flops, cor_flops, active = algorithmic_flops_per_model(batch, args.ic_path)
+    if args.ic_path == "G":
+        eng.set_lockstep(batch.nsteps)
+    run_flops, cor_flops, active = algorithmic_flops_per_model(batch, "S" if args.ic_path == "S" else "R")
     nts = int(batch.nsteps[0])
 
     # inputs resident in HBM
@@ -519,6 +553,9 @@ def main():
     # executed FP64-pipe instructions of the IC phase (path R): per visited (o,gamma,nu_i) element 3 DFMA for F + 1 for
     # the accumulation, plus ~45 per (o,gamma) pair for the reciprocal + log preamble when not tabulated
     pipe, exe_tf = None, None
+    kernel_name = "lhm::run_kernel (fused timestep loop, one CTA per walker)"
+    kernel_ms, launches_per_step = run_ms, 1
+    shares = None
     if args.ic_path == "R":
         shared = bool(np.all(batch.g_el == batch.g_el[0]) and np.all(batch.nu_tot == batch.nu_tot[0])
                       and np.all(batch.nu_ic == batch.nu_ic[0]))
@@ -533,29 +570,55 @@ def main():
                 "note": "IC phase only: 4 FP64 instructions per visited (o,gamma,nu_i) element (+ ~45 per pair when the "
                         "pair constants are not tabulated), inactive lanes of a tile included; compare with ncu "
                         "sm__pipe_fp64_cycles_active"}
-    roofline = {"bound": "fp64", "kernel": "lhm::run_kernel (fused timestep loop, one CTA per walker)",
+    elif args.ic_path == "G":
+        # the roofline-graded kernel of path G is the contraction (one launch per timestep): its own launches are timed by
+        # CUDA events inside liblhm.so on the launch stream
+        icg_ms, icg_n, icg_ctas, icg_smem = eng.last_icg_timing()
+        tiles, ksteps, kclamp = icg_schedule(batch)
+        nblk = (W + 31) // 32
+        fma_launch = float(ksteps) * (8 * 256 + 6 * 32) * nblk + float(tiles) * 16 * 32 * nblk
+        exe_tf = 2.0 * fma_launch / (icg_ms * 1e-3) / 1e12
+        ic_flops_launch = 15.0 * (eng.Nt - 1) * float(active.sum())           # SURVEY 8d, one timestep of every walker
+        flops_launch = ic_flops_launch
+        alg_tf = flops_launch / (icg_ms * 1e-3) / 1e12
+        kernel_name = ("lhm::icg_kernel (IC emissivity of one timestep for the whole batch: clamped kernel formed in "
+                       "registers, contracted over walkers with mma.sync m8n8k4 f64)")
+        kernel_ms, launches_per_step = icg_ms, nts
+        pipe = {"gamma_pair_tiles": tiles, "k_steps": ksteps, "k_steps_clamped": kclamp, "walker_blocks": nblk,
+                "executed_fp64_fma_per_launch": fma_launch, "dmma_share_of_fma": float(ksteps) * 8 * 256 * nblk / fma_launch,
+                "ctas": icg_ctas, "smem_bytes_per_cta": icg_smem, "launches_timed": icg_n,
+                "note": "per k-step of a tile and 32-walker block: 8 DMMA (256 FMA each) + 6 DFMA warp instructions (the two "
+                        "A fragments); per tile 16 DFMA for the gamma weights; padded rows / k included"}
+        shares = {"contraction_ms_per_step": icg_ms * nts, "per_walker_half_steps_ms_per_step": run_ms - icg_ms * nts,
+                  "pipeline_ms_per_step": run_ms, "contraction_share": icg_ms * nts / run_ms,
+                  "note": "one step of the bench = nts + 1 launches of stepG_kernel (per-walker phases) around nts launches "
+                          "of icg_kernel; device times from CUDA events on the launch stream"}
+    roofline = {"bound": "fp64", "kernel": kernel_name,
                 "achieved": exe_tf if exe_tf is not None else alg_tf, "peak": peak_tf, "unit": "TFLOP/s",
                 "frac": (exe_tf if exe_tf is not None else alg_tf) / peak_tf,
-                "frac_is": ("EXECUTED FP64 instructions of the IC phase x 2 / kernel time / measured DFMA peak: the share of "
-                            "the FP64 pipe the kernel keeps busy (ncu sm__pipe_fp64_cycles_active is the cross-check)"
+                "frac_is": ("EXECUTED FP64 FMAs of the kernel's IC arithmetic x 2 / kernel time / measured DFMA peak: the share "
+                            "of the FP64 pipe the kernel keeps busy (ncu sm__pipe_fp64_cycles_active is the cross-check)"
                             if exe_tf is not None else "algorithmic flops of this path / kernel time / peak"),
                 "algorithmic": {"achieved": alg_tf, "frac": alg_tf / peak_tf, "flops_per_launch": flops_launch,
                                 "flops_per_model": float(run_flops.mean()),
                                 "note": "SURVEY 8d count: 15 flop per (o,gamma,nu_i) element of the reference formula x units "
-                                        "per launch / kernel time; the kernel's exact regrouping executes 4 DFMA = 8 flop per "
-                                        "element, so this fraction can exceed 1 -- it says how fast the reference's "
-                                        "arithmetic is delivered, not how busy the pipe is"},
-                "executed": pipe,
+                                        "per launch / kernel time; the kernels' exact regrouping executes far fewer FP64 "
+                                        "operations per element (path R: 4 DFMA; path G: 1 tensor-core FMA + 3/32 DFMA), so "
+                                        "this fraction can exceed 1 -- it says how fast the reference's arithmetic is "
+                                        "delivered, not how busy the pipe is"},
+                "executed": pipe, "step_shares": shares,
                 "peak_source": "measured live by lhm_fp64_peak_probe (DFMA, 8 independent chains/thread; 64 DFMA/clk/SM x "
-                               "148 SMs x 1.965 GHz = 37.2 nominal); MEASURED_PEAKS.json carries no FP64 figure",
-                "active_pairs_per_model": float(active.mean()), "kernel_ms": run_ms,
+                               "148 SMs x 1.965 GHz = 37.2 nominal); DMMA issues on the same unit "
+                               "(profiles/r01_c_fp64_microbench.txt); MEASURED_PEAKS.json carries no FP64 figure",
+                "active_pairs_per_model": float(active.mean()), "kernel_ms": kernel_ms,
+                "kernel_launches_per_step": launches_per_step, "time_loop_ms": run_ms,
                 "setup_kernel_ms": setup_ms, "cor_kernel_ms": cor_ms,
                 "setup_cor_note": "cor_kernel runs on the handle's second stream concurrently with setup_kernel (both "
-                                  "durations are measured while they share the GPU); run_kernel waits for both",
-                # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch, from the ncu --set full capture
+                                  "durations are measured while they share the GPU); the time loop waits for both",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch of the kernel, from the ncu --set full capture
                 # committed under profiles/ (per walker, scaled by the walkers of this launch)
-                "traffic": NCU_DRAM_BYTES_PER_WALKER * W if args.ic_path == "R" else None,
-                "traffic_source": NCU_DRAM_SOURCE,
+                "traffic": NCU_DRAM_BYTES_PER_WALKER[args.ic_path] * W if NCU_DRAM_BYTES_PER_WALKER.get(args.ic_path) else None,
+                "traffic_source": NCU_DRAM_SOURCE.get(args.ic_path),
                 "hbm": {"algorithmic_bytes_per_launch": alg_bytes,
                         "achieved_GBs": alg_bytes / (run_ms * 1e-3) / 1e9,
                         "peak_GBs": peaks.get("hbm_gbs"), "note": "compute-bound path: <8 KB of mandatory traffic per model"}}
@@ -587,27 +650,37 @@ def main():
     if configs is not None:
         line["configs"] = configs
 
-    if not args.no_fast_path and args.ic_path == "R":
-        # the exact suffix-sum formulation (path S) reported next to the triple-sum kernel, with its OWN flop count
-        engS = Engine(batch.cfg, W, ic_path="S")
-        fS, _, _ = algorithmic_flops_per_model(batch, "S")
-        ts = []
-        for i in range(args.warmup + min(args.steps, 10)):
-            flush.fill_(1.0)
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            engS.setup_device(W, *dev_in)
-            engS.run_into(N_out, sed, 0)
-            e1.record()
-            torch.cuda.synchronize()
-            if i >= args.warmup:
-                ts.append((e0.elapsed_time(e1), engS.last_timings()[2]))
-        ts = np.array(ts)
-        line["fast_path"] = {"ic_path": "S", "value": W / (ts[:, 0].mean() * 1e-3), "unit": UNIT + " per GPU",
-                             "kernel_ms": float(ts[:, 1].mean()), "flops_per_model": float(fS.mean()),
-                             "achieved_TFLOPs": float(fS.sum() / (ts[:, 1].mean() * 1e-3) / 1e12),
-                             "note": "latency/transcendental-bound; never divide this time by path-R flops"}
-        engS.close()
+    if not args.no_fast_path:
+        # the other IC formulations on the same batch, each with its OWN flop count: R = per-walker triple sum (4 DFMA per
+        # element), G = the same triple sum contracted over walkers on the tensor cores (shared grids only), S = the exact
+        # suffix-sum collapse (100x fewer flops, latency-bound; never divide its time by path-R flops)
+        line["other_ic_paths"] = {}
+        for path in [q for q in ("G", "R", "S") if q != args.ic_path]:
+            try:
+                engP = Engine(batch.cfg, W, ic_path=path)
+            except Exception as e:
+                line["other_ic_paths"][path] = {"unavailable": str(e)}
+                continue
+            if path == "G":
+                engP.set_lockstep(batch.nsteps)
+            fP, _, _ = algorithmic_flops_per_model(batch, "S" if path == "S" else "R")
+            ts = []
+            for i in range(args.warmup + min(args.steps, 10)):
+                flush.fill_(1.0)
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                engP.setup_device(W, *dev_in)
+                engP.run_into(N_out, sed, 0)
+                e1.record()
+                torch.cuda.synchronize()
+                if i >= args.warmup:
+                    ts.append((e0.elapsed_time(e1), engP.last_timings()[2]))
+            ts = np.array(ts)
+            line["other_ic_paths"][path] = {"value": W / (ts[:, 0].mean() * 1e-3), "unit": UNIT + " per GPU",
+                                            "ms_per_step": float(ts[:, 0].mean()), "time_loop_ms": float(ts[:, 1].mean()),
+                                            "flops_per_model": float(fP.mean()),
+                                            "algorithmic_TFLOPs": float(fP.sum() / (ts[:, 1].mean() * 1e-3) / 1e12)}
+            engP.close()
 
     if cpu_line is not None:
         line["cpu_baseline"] = cpu_line

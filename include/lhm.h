@@ -37,6 +37,10 @@ typedef enum {
 /* IC emissivity formulation */
 #define LHM_IC_PATH_R 0        /* triple sum nu_out x gamma x nu_in, kernel recomputed in registers */
 #define LHM_IC_PATH_S 1        /* exact suffix-sum collapse of the nu_in sum */
+#define LHM_IC_PATH_G 2        /* shared-grid batches (lhm_config::shared_ic_grids, driver 0): the triple sum as a dense
+                                  contraction over walkers on the FP64 tensor cores (mma.sync m8n8k4 f64), the clamped
+                                  kernel formed in registers once per 32 walkers; the batch advances in lock-step, two
+                                  launches per timestep (lhm_set_lockstep gives the common number of timesteps) */
 
 /* Static description of a batch: grid sizes, process flags, driver variant.
  * Flags are the reference's float flags compared with ==1. / ==0. (LeMoC/LeMoC.py:206-279). */
@@ -50,7 +54,7 @@ typedef struct {
     int loss_minus_one;     /* 1: (gamma^2-1) loss shape LeMoC.py:224-234; 0: gamma^2 Code.py:210-220 */
     int qee_from_ic;        /* 0: Q_ee_f(nu_tot,n,nu_tot,n) LeMoC.py:283; 1: (...,nu_ic,photons_IC/V) Code.py:269 */
     int gg_npts;            /* resample points of a_gg / Q_ee_f: 50 in LeMoC/LeHaMoC_f.py:132,144 */
-    int ic_path;            /* LHM_IC_PATH_R or LHM_IC_PATH_S */
+    int ic_path;            /* LHM_IC_PATH_R, LHM_IC_PATH_S or LHM_IC_PATH_G */
     int const_B;            /* 1: B(t) == B0 for every walker (m == 0 or Vexp == 0, LeMoC.py:200): the synchrotron
                                exponentials are tabulated once per walker instead of every step */
     int ic_pair_table;      /* 1: the four per-(nu_out, gamma) constants of the IC kernel are tabulated at set-up (32 B per
@@ -114,6 +118,13 @@ long long lhm_table_bytes_per_walker(const lhm_handle*);
  * interpolated on nu_tot (LeMoC.py:140-169 through LeHaMoC_f.py:154-156). */
 int lhm_setup_batch(lhm_handle*, int W, const double* consts, const double* g_el, const double* nu_syn,
                     const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext);
+
+/* ic_path G only: the number of timesteps every walker of the following batches runs (the lock-step loop is driven by
+ * the host: nsteps + 1 launches of the per-walker half-steps around nsteps contractions; LeMoC.py:196 range(int(time_end))). */
+int lhm_set_lockstep(lhm_handle*, int nsteps);
+/* ic_path G only: mean device time of the contraction launches of the last run (CUDA events on the stream), how many
+ * were timed, the grid size and the dynamic shared memory per CTA */
+int lhm_last_icg_timing(lhm_handle*, float* mean_ms, int* launches, int* ctas, int* smem_bytes);
 
 /* A5: cor_factor_syn_el (LeHaMoC_f.py:175-237) for every walker of the current batch -> out[W].
  * One warp per walker; the 200-step inner simulation is advanced with a warp-level affine scan. */

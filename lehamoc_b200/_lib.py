@@ -11,6 +11,7 @@ LIB_PATH = os.environ.get("LHM_LIB", os.path.join(HERE, "liblhm.so"))     # LHM_
 LHM_OK = 0
 LHM_IC_PATH_R = 0
 LHM_IC_PATH_S = 1
+LHM_IC_PATH_G = 2
 LHM_NCONST = 12
 # indices of the per-walker scalar block (include/lhm.h)
 C_R0, C_B0, C_M, C_VEXP, C_DT, C_TINIT, C_NSTEPS, C_COR_P, C_COR_Q0, C_COR_B, C_NH, C_PPR = range(12)
@@ -65,6 +66,8 @@ SIGNATURES = {
     "lhm_run_batch_lh": (C.c_int, [_P, _P, _P, _P, _P, C.c_int]),
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),
+    "lhm_set_lockstep": (C.c_int, [_P, C.c_int]),
+    "lhm_last_icg_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),
     "lhm_photons_tot_batch": (C.c_int, [_P] * 5),
     "lhm_uph_batch": (C.c_int, [_P] * 4),

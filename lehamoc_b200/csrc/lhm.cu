@@ -16,6 +16,7 @@
 #include "lhm_cor.cuh"
 #include "lhm_had.cuh"
 #include "lhm_pack.cuh"
+#include "lhm_icg.cuh"
 
 namespace lhm {
 
@@ -161,6 +162,165 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
             __syncthreads();
         }
     }
+}
+
+// =================================================================================================
+// path G (lhm_icg.cuh): the same timestep cut at the IC emissivity.  All walkers of a shared-grid batch advance in
+// lock-step: launch k runs, per walker, the second half of step k (IC partial sums -> Q_IC, photon solves, gamma-gamma,
+// output) and the first half of step k+1 (photon field, Compton losses, electron solve, per-gamma vectors, synchrotron /
+// SSA rows), then parks what the other half needs in HBM and hands p[w,i], av[w,gamma] to the contraction kernel.
+// Same phase functions, same order of operations as run_kernel: only Q_IC comes from a different summation.
+// =================================================================================================
+struct GState { int N, psyn, pic, agg, Qsyn, aS, aI, Ln, Lm, total; };
+__host__ __device__ inline GState gstate_layout(const Layout& L) {
+    GState O; int o = 0;
+    auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
+    O.N = take(L.Ng); O.psyn = take(L.Ns); O.pic = take(L.Ni); O.agg = take(L.Ni);
+    O.Qsyn = take(L.Ns); O.aS = take(L.Ns); O.aI = take(L.Ni); O.Ln = take(L.Nt); O.Lm = take(L.Nt);
+    O.total = o;
+    return O;
+}
+
+struct GArgs {
+    RunArgs R;
+    IcgDims D;
+    int Wpad;
+    double* state;          // [W][gstate_layout().total]
+    double* gp;             // [Wpad][Kp]
+    double* gav;            // [Wpad][NgP]
+    const double* part;     // [NGC][Wpad][NoPad]
+    int step;               // timesteps whose first half has run before this launch
+    int do_B, do_A;
+};
+
+__device__ __forceinline__ void set_time(Ctx& C, double t) {                 // LeMoC.py:198-201
+    C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+    C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+    C.V = volume_of(C.Rad);
+}
+
+#ifndef LHM_G_MIN_CTAS
+#define LHM_G_MIN_CTAS 2
+#endif
+__global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const RunArgs& A = G.R;
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+    if (nsteps < 1) { if (G.step == 0) no_step_outputs<NT>(A, w, Ng, Nt, 0); return; }
+    const GState O = gstate_layout(L);
+    double* st = G.state + (size_t)w * O.total;
+    ic_prepare<NT>(C, S);
+    double t = C.tinit;
+    for (int k = 0; k < G.step; ++k) t += C.dt;                 // the reference's own accumulation, LeMoC.py:198
+    if (G.do_B && G.step >= 1 && G.step <= nsteps) {
+        set_time(C, t);
+        for (int j = tid; j < Ng; j += NT) { S.N[j] = st[O.N + j]; S.qee[j] = 0.0; }
+        for (int k = tid; k < Ns; k += NT) { S.psyn[k] = st[O.psyn + k]; S.Qsyn[k] = st[O.Qsyn + k]; S.aS[k] = st[O.aS + k]; }
+        for (int k = tid; k < Ni; k += NT) { S.pic[k] = st[O.pic + k]; S.agg[k] = st[O.agg + k]; S.aI[k] = st[O.aI + k]; }
+        for (int k = tid; k < Nt; k += NT) { S.Ln[k] = st[O.Ln + k]; S.Lm[k] = st[O.Lm + k]; }
+        icg_finish<NT>(G.part, G.D, G.Wpad, w, S.QIC);
+        __syncthreads();
+        phase_photon_solves<NT>(C, S, cor);
+        if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
+            const double* Lng = S.Ln;
+            if (C.F.qee_from_ic) {
+                for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
+                __syncthreads();
+                Lng = S.Lic;
+            }
+            phase_gg<NT>(C, S, Lng, S.agg, S.qee);
+            __syncthreads();
+        }
+        const int step = G.step - 1;
+        const bool last = (step == nsteps - 1);
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && last)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT)
+                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            __syncthreads();
+        }
+    }
+    if (G.do_A && G.step < nsteps) {
+        if (G.step == 0) {                                       // initial state (LeMoC.py:172-183)
+            for (int j = tid; j < Ng; j += NT) {
+                S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];
+                S.qee[j] = 0.0;
+            }
+            for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; }
+            for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+            __syncthreads();
+        }
+        t += C.dt;
+        set_time(C, t);
+        phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        phase_electrons<NT>(C, S);
+        phase_vectors<NT>(C, S);
+        phase_syn_rows<NT>(C, S, false);
+        __syncthreads();
+        for (int j = tid; j < Ng; j += NT) st[O.N + j] = S.N[j];
+        for (int k = tid; k < Ns; k += NT) { st[O.psyn + k] = S.psyn[k]; st[O.Qsyn + k] = S.Qsyn[k]; st[O.aS + k] = S.aS[k]; }
+        for (int k = tid; k < Ni; k += NT) { st[O.pic + k] = S.pic[k]; st[O.agg + k] = S.agg[k]; st[O.aI + k] = S.aI[k]; }
+        for (int k = tid; k < Nt; k += NT) { st[O.Ln + k] = S.Ln[k]; st[O.Lm + k] = S.Lm[k]; }
+        double* gp = G.gp + (size_t)w * G.D.Kp;
+        for (int i = tid; i < G.D.Kp; i += NT) gp[i] = (i < G.D.Ntar) ? S.tri[4 * i + 2] : 0.0;     // the last target bin is dropped
+        double* gav = G.gav + (size_t)w * G.D.NgP;
+        for (int j = tid; j < G.D.NgP; j += NT) gav[j] = (j < Ng) ? S.av[j] : 0.0;
+    }
+}
+
+// function-level twin of the contraction (lhm_ic_emissivity_batch with ic_path G): stage p and av of caller-supplied
+// n_e, n; the contraction kernel; scale the partial sums
+struct GUnitArgs {
+    Layout L; StepFlags F; IcgDims D; int W, Wpad;
+    const double* consts; const double* tabd; const int* tabi;
+    const double *n_e, *n;
+    double *gp, *gav;
+    const double* part;
+    double* Q_out;
+    int finish;
+};
+__global__ void __launch_bounds__(NT, 2) icg_unit_kernel(GUnitArgs U) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x, tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, U.L, NW);
+    if (U.finish) {
+        icg_finish<NT>(U.part, U.D, U.Wpad, w, S.QIC);
+        __syncthreads();
+        for (int k = tid; k < U.L.Ni - 1; k += NT) U.Q_out[(size_t)w * (U.L.Ni - 1) + k] = S.QIC[k];
+        return;
+    }
+    Ctx C;
+    load_ctx(C, U.L, U.F, U.consts, U.tabd, U.tabi, nullptr, nullptr, 0, w);
+    const Layout& L = C.L;
+    ic_prepare<NT>(C, S);
+    C.V = 1.0;
+    for (int j = tid; j < L.Ng; j += NT) S.N[j] = U.n_e[(size_t)w * L.Ng + j];
+    __syncthreads();
+    phase_vectors<NT>(C, S);
+    double* gp = U.gp + (size_t)w * U.D.Kp;
+    for (int i = tid; i < U.D.Kp; i += NT) gp[i] = (i < U.D.Ntar) ? C.T[L.wt + i] * U.n[(size_t)w * L.Nt + i] : 0.0;
+    double* gav = U.gav + (size_t)w * U.D.NgP;
+    for (int j = tid; j < U.D.NgP; j += NT) gav[j] = (j < L.Ng) ? S.av[j] : 0.0;
 }
 
 // =================================================================================================
@@ -555,8 +715,10 @@ static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& 
     if (e == cudaSuccess) { while (bytes > cur && !mark.compare_exchange_weak(cur, bytes)) {} }
     return e;
 }
+constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
-static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV];
+static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
+    g_smem_icgu[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -602,6 +764,17 @@ struct lhm_handle {
     cudaStream_t aux;
     cudaEvent_t ev_fork, ev_join;
     bool cor_valid;
+    // path G (lhm_icg.cuh): grid-only tables of the contraction, the exchange buffers between the two kernels of a
+    // timestep, the lock-step count, and an event pair per contraction launch (lhm_last_icg_timing)
+    bool pathG;
+    IcgDims GD;
+    int Wpad_cap;
+    double *d_ptg, *d_xs, *d_gp, *d_gav, *d_part, *d_state;
+    ushort2* d_kinfo;
+    int *d_tasks, *d_cost;
+    int lock_steps;
+    cudaEvent_t evg[2 * LHM_G_MAXEV];
+    int evg_n;
 };
 
 static PhysConst make_consts() {
@@ -677,6 +850,31 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
         const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);
         CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));
     }
+    h->pathG = false;
+    if (cfg->ic_path == LHM_IC_PATH_G) {
+        // the lock-step contraction needs one set of IC grids for the whole batch; leptonic drivers only
+        if (cfg->driver != 0 || !cfg->shared_ic_grids) return LHM_ERR_ARG;
+        h->F.ic_path = LHM_IC_PATH_R;                  // what the fused kernel runs when IC emission is switched off
+        if (cfg->IC_emis_flag) {
+            h->pathG = true;
+            const IcgDims D = h->GD = icg_dims(cfg->Ng, cfg->Ni, cfg->Nt);
+            if (icg_smem_bytes(D) > (size_t)prop.sharedMemPerBlockOptin) return LHM_ERR_CAPACITY;
+            const size_t Wp = (W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
+            h->Wpad_cap = (int)Wp;
+            CUDA_TRY(cudaMalloc(&h->d_ptg, (size_t)D.NOG * D.NgP * 8 * 4 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_kinfo, (size_t)D.NOG * (D.NgP / 2) * sizeof(ushort2)));
+            CUDA_TRY(cudaMalloc(&h->d_xs, (size_t)D.Kp * 4 * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_tasks, (size_t)D.ntasks * sizeof(int)));
+            CUDA_TRY(cudaMalloc(&h->d_cost, (size_t)D.ntasks * sizeof(int)));
+            CUDA_TRY(cudaMalloc(&h->d_gp, Wp * D.Kp * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_gav, Wp * D.NgP * sizeof(double)));
+            CUDA_TRY(cudaMemset(h->d_gp, 0, Wp * D.Kp * sizeof(double)));       // padding walkers: p = av = 0
+            CUDA_TRY(cudaMemset(h->d_gav, 0, Wp * D.NgP * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_part, (size_t)D.NGC * Wp * D.NoPad * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_state, W * (size_t)gstate_layout(h->L).total * sizeof(double)));
+            for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) CUDA_TRY(cudaEventCreate(&h->evg[i]));
+        }
+    }
     for (int i = 0; i < 6; ++i) CUDA_TRY(cudaEventCreate(&h->ev[i]));
     CUDA_TRY(cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking));
     CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
@@ -710,6 +908,9 @@ void lhm_destroy(lhm_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E); cudaFree(h->d_ptab);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
+    cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
+    cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
+    for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) if (h->evg[i]) cudaEventDestroy(h->evg[i]);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
     if (h->ev_join) cudaEventDestroy(h->ev_join);
@@ -754,6 +955,14 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    if (h->pathG) {                                  // grid-only tables of the contraction, from walker 0's tables
+        IcgSetupArgs G;
+        G.L = h->L; G.D = h->GD; G.tabd = h->d_tabd; G.ptg = h->d_ptg; G.kinfo = h->d_kinfo; G.xs = h->d_xs;
+        G.tasks = h->d_tasks; G.cost = h->d_cost;
+        icg_setup_kernel<<<1, 256, 0, h->stream>>>(G);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
     h->ev_set[0] = true;
     return LHM_OK;
@@ -837,6 +1046,53 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     return run_common(h, N_el_out, nuLnu_out, nullptr, nullptr, snapshots, false);
 }
 
+static int icg_splits(int W) {
+    int dev = 0, sms = 148;
+    if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int nwb = (W + ICG_NBW - 1) / ICG_NBW;
+    int S = (2 * sms + nwb / 2) / nwb;                  // two resident CTAs per SM, about one wave
+    return S < 1 ? 1 : (S > 16 ? 16 : S);
+}
+
+static int launch_icg(lhm_handle* h, int ev_slot) {
+    IcgArgs I;
+    I.D = h->GD; I.W = h->W; I.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW; I.S = icg_splits(h->W);
+    I.ptg = h->d_ptg; I.kinfo = h->d_kinfo; I.xs = h->d_xs; I.tasks = h->d_tasks; I.gp = h->d_gp; I.gav = h->d_gav;
+    I.part = h->d_part;
+    const size_t smem = icg_smem_bytes(h->GD);
+    CUDA_TRY(ensure_dyn_smem(icg_kernel, smem, g_smem_icg[h->device % MAX_DEV]));
+    if (ev_slot >= 0) CUDA_TRY(cudaEventRecord(h->evg[2 * ev_slot], h->stream));
+    icg_kernel<<<(I.Wpad / ICG_NBW) * I.S, ICG_NT, smem, h->stream>>>(I);
+    g_launches++;
+    CUDA_TRY(cudaGetLastError());
+    if (ev_slot >= 0) CUDA_TRY(cudaEventRecord(h->evg[2 * ev_slot + 1], h->stream));
+    return LHM_OK;
+}
+
+// the lock-step time loop of path G: n + 1 launches of the per-walker half-steps around n contractions
+static int run_pathG(lhm_handle* h, const RunArgs& A) {
+    const int n = h->lock_steps;
+    if (n < 1) return LHM_ERR_STATE;                    // lhm_set_lockstep must precede the run
+    GArgs G;
+    G.R = A; G.D = h->GD; G.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
+    G.state = h->d_state; G.gp = h->d_gp; G.gav = h->d_gav; G.part = h->d_part;
+    CUDA_TRY(ensure_dyn_smem(stepG_kernel, h->smem, g_smem_stepg[h->device % MAX_DEV]));
+    h->evg_n = 0;
+    for (int k = 0; k <= n; ++k) {
+        G.step = k; G.do_B = k >= 1; G.do_A = k < n;
+        stepG_kernel<<<h->W, NT, h->smem, h->stream>>>(G);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        if (k < n) {
+            const int slot = k < LHM_G_MAXEV ? k : -1;
+            int rc = launch_icg(h, slot);
+            if (rc != LHM_OK) return rc;
+            if (slot >= 0) h->evg_n = slot + 1;
+        }
+    }
+    return LHM_OK;
+}
+
 static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
                       int snapshots, bool lh) {
     if (h->W < 1) return LHM_ERR_STATE;
@@ -863,7 +1119,10 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
-    if (lh && h->cfg.driver == 2) {
+    if (h->pathG) {
+        int rc = run_pathG(h, A);
+        if (rc != LHM_OK) return rc;
+    } else if (lh && h->cfg.driver == 2) {
         CUDA_TRY(ensure_dyn_smem(run_code_lh_kernel, h->smem, g_smem_codelh[h->device % MAX_DEV]));
         run_code_lh_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     } else if (lh) {
@@ -880,7 +1139,7 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
         CUDA_TRY(ensure_dyn_smem(run_kernel, h->smem, g_smem_run[h->device % MAX_DEV]));
         run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
     }
-    g_launches++;
+    if (!h->pathG) g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[5], h->stream));
     h->ev_set[2] = true;
@@ -903,6 +1162,33 @@ int lhm_last_timings(lhm_handle* h, float* setup_ms, float* cor_ms, float* run_m
         CUDA_TRY(cudaEventSynchronize(h->ev[2 * i + 1]));
         CUDA_TRY(cudaEventElapsedTime(outs[i], h->ev[2 * i], h->ev[2 * i + 1]));
     }
+    return LHM_OK;
+}
+
+int lhm_set_lockstep(lhm_handle* h, int nsteps) {
+    if (!h || nsteps < 1) return LHM_ERR_ARG;
+    h->lock_steps = nsteps;
+    return LHM_OK;
+}
+
+int lhm_last_icg_timing(lhm_handle* h, float* mean_ms, int* launches, int* ctas, int* smem_bytes) {
+    if (!h) return LHM_ERR_ARG;
+    if (mean_ms) *mean_ms = -1.f;
+    if (launches) *launches = 0;
+    if (ctas) *ctas = 0;
+    if (smem_bytes) *smem_bytes = 0;
+    if (!h->pathG || h->evg_n < 1) return LHM_OK;
+    double tot = 0.0;
+    for (int i = 0; i < h->evg_n; ++i) {
+        float ms = 0.f;
+        CUDA_TRY(cudaEventSynchronize(h->evg[2 * i + 1]));
+        CUDA_TRY(cudaEventElapsedTime(&ms, h->evg[2 * i], h->evg[2 * i + 1]));
+        tot += ms;
+    }
+    if (mean_ms) *mean_ms = (float)(tot / h->evg_n);
+    if (launches) *launches = h->evg_n;
+    if (ctas) *ctas = ((h->W + ICG_NBW - 1) / ICG_NBW) * icg_splits(h->W);
+    if (smem_bytes) *smem_bytes = (int)icg_smem_bytes(h->GD);
     return LHM_OK;
 }
 
@@ -983,7 +1269,28 @@ int lhm_syn_ssa_batch(lhm_handle* h, const double* n_e, const double* Bfield, do
     return launch_unit(h, U_SYN, n_e, nullptr, Bfield, Q, aS, aI, -1);
 }
 int lhm_ic_emissivity_batch(lhm_handle* h, const double* n_e, const double* n, double* Q, int ic_path) {
-    if (!n_e || !n || !Q || (ic_path != LHM_IC_PATH_R && ic_path != LHM_IC_PATH_S)) return LHM_ERR_ARG;
+    if (!n_e || !n || !Q || (ic_path != LHM_IC_PATH_R && ic_path != LHM_IC_PATH_S && ic_path != LHM_IC_PATH_G)) return LHM_ERR_ARG;
+    if (ic_path == LHM_IC_PATH_G) {
+        if (!h) return LHM_ERR_ARG;
+        if (!h->pathG || h->W < 1) return LHM_ERR_STATE;
+        CUDA_TRY(cudaSetDevice(h->device));
+        GUnitArgs U;
+        U.L = h->L; U.F = h->F; U.D = h->GD; U.W = h->W; U.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
+        U.consts = h->consts; U.tabd = h->d_tabd; U.tabi = h->d_tabi; U.n_e = n_e; U.n = n; U.gp = h->d_gp; U.gav = h->d_gav;
+        U.part = h->d_part; U.Q_out = Q;
+        CUDA_TRY(ensure_dyn_smem(icg_unit_kernel, h->smem, g_smem_icgu[h->device % MAX_DEV]));
+        U.finish = 0;
+        icg_unit_kernel<<<h->W, NT, h->smem, h->stream>>>(U);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        int rc = launch_icg(h, -1);
+        if (rc != LHM_OK) return rc;
+        U.finish = 1;
+        icg_unit_kernel<<<h->W, NT, h->smem, h->stream>>>(U);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+        return LHM_OK;
+    }
     return launch_unit(h, U_IC, n_e, n, nullptr, Q, nullptr, nullptr, ic_path);
 }
 int lhm_gg_batch(lhm_handle* h, const double* n, const double* photons_IC_dens, double* a_gg, double* Q_ee) {

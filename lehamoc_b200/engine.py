@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import LhmError, lhm_config, check
 from .setup_host import Batch
 
-IC_PATHS = {"R": _lib.LHM_IC_PATH_R, "S": _lib.LHM_IC_PATH_S}
+IC_PATHS = {"R": _lib.LHM_IC_PATH_R, "S": _lib.LHM_IC_PATH_S, "G": _lib.LHM_IC_PATH_G}
 
 
 def _require_cuda():
@@ -37,6 +37,9 @@ class Engine:
         if "LHM_CONST_B" in os.environ:                      # experiments: force the exponential cache on/off
             self.cfg["const_B"] = int(os.environ["LHM_CONST_B"])
         cfg = self.cfg
+        if ic_path == "G" and not (cfg.get("shared_ic_grids") and cfg.get("driver", 0) == 0):
+            raise LhmError("ic_path 'G' (dense contraction over walkers) needs a batch whose walkers share g_el / nu_ic / "
+                           "nu_tot (cfg.shared_ic_grids) and one of the leptonic drivers")
         self.ic_path = ic_path
         c = lhm_config()
         for k, v in cfg.items():
@@ -98,11 +101,20 @@ class Engine:
                 raise LhmError(f"batch {k}={batch.cfg[k]} does not match the engine ({self.cfg[k]})")
         W = batch.W
         self._check_shared(batch)
+        if self.ic_path == "G":
+            self.set_lockstep(batch.nsteps)
         dev = [self._dev(a) for a in batch.arrays()]
         if self.cfg.get("driver", 0) >= 1:
             self._keep_pr = (self._dev(batch.g_pr), self._dev(batch.pr_inj))
             check(self.lib.lhm_set_protons(self.h, _ptr(self._keep_pr[0]), _ptr(self._keep_pr[1])), "lhm_set_protons")
         self.setup_device(W, *dev)
+
+    def set_lockstep(self, nsteps):
+        """ic_path G advances the whole batch in lock-step: every walker must run the same number of timesteps."""
+        nsteps = np.atleast_1d(np.asarray(nsteps))
+        if not np.all(nsteps == nsteps[0]):
+            raise LhmError("ic_path 'G': the walkers of a batch must run the same number of timesteps")
+        check(self.lib.lhm_set_lockstep(self.h, int(nsteps[0])), "lhm_set_lockstep")
 
     def _check_shared(self, batch):
         if self.cfg.get("shared_ic_grids") and not (np.all(batch.g_el == batch.g_el[0])
@@ -131,6 +143,10 @@ class Engine:
             raise LhmError("this engine was created for batches whose walkers share g_el/nu_ic/nu_tot "
                            "(cfg.shared_ic_grids); the batch does not")
         W, Ng, Nh, Nt = req.W, cfg["Ng"], cfg["Ni"], cfg["Nt"]
+        if self.ic_path == "G":
+            if req.variant != "script":
+                raise LhmError("ic_path 'G': the step count of Code.py depends on the walker (Code.py:183)")
+            self.set_lockstep(int(req.scalars["time_end"]))                 # LeMoC.py:196 range(int(time_end))
         if W > self.max_walkers:
             raise LhmError(f"batch of {W} walkers exceeds the engine capacity {self.max_walkers}")
         # one pinned staging buffer -> one H2D copy
@@ -268,6 +284,13 @@ class Engine:
             self._pin[kS][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
         self.stream.synchronize()
         return Nh_, sh_
+
+    def last_icg_timing(self):
+        """ic_path G: (mean ms per contraction launch, launches timed, CTAs, dynamic smem bytes per CTA) of the last run."""
+        ms, n, ctas, smem = C.c_float(), C.c_int(), C.c_int(), C.c_int()
+        check(self.lib.lhm_last_icg_timing(self.h, C.byref(ms), C.byref(n), C.byref(ctas), C.byref(smem)),
+              "lhm_last_icg_timing")
+        return ms.value, n.value, ctas.value, smem.value
 
     def last_timings(self):
         """(setup_ms, cor_ms, run_ms) of the most recent launches, measured with CUDA events on the stream."""

@@ -63,8 +63,9 @@ def _worker(rank, ws, port, W, out_dir):
         _, P = load_golden("code_fit")
         ev = _evaluator(gold, P, rank)
         th = _thetas(W)
+        from lehamoc_b200 import fit
         lp = ev.log_probability_sharded(th)                                     # fit_emcee.py:239-242 semantics
-        inside = np.isfinite(lp)
+        inside = np.isfinite(fit.log_prior_batch(th))
         rows = shard.evaluate_sharded(lambda blk: _rows(ev, blk), th[inside])
         np.save(os.path.join(out_dir, f"lp_{W}_{rank}.npy"), lp)
         np.save(os.path.join(out_dir, f"rows_{W}_{rank}.npy"), rows)
@@ -84,9 +85,13 @@ def test_nccl_gathered_rows_equal_single_gpu(tmp_path, W):
     _, P = load_golden("code_fit")
     ev = _evaluator(gold, P, 0)
     th = _thetas(W)
+    from lehamoc_b200 import fit
     lp = ev.log_probability(th)                                                 # unsharded, one GPU
-    assert lp[3] == -np.inf and np.all(np.isfinite(np.delete(lp, 3)))
-    rows = _rows(ev, th[np.isfinite(lp)]).cpu().numpy()
+    inside = np.isfinite(fit.log_prior_batch(th))
+    # -inf also where an upper limit is violated by many sigma (log(1 + erf(-x)) underflows, in the reference as well)
+    assert lp[3] == -np.inf and not inside[3] and inside.sum() == W - 1 and np.isfinite(lp).sum() > W // 4
+    assert not np.any(np.isnan(lp))
+    rows = _rows(ev, th[inside]).cpu().numpy()
     for r in range(ws):
         np.testing.assert_array_equal(np.load(tmp_path / f"lp_{W}_{r}.npy"), lp)
         np.testing.assert_array_equal(np.load(tmp_path / f"rows_{W}_{r}.npy"), rows)
