@@ -308,7 +308,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--walkers", type=int, default=1184,
                     help="walkers per GPU (default 1184 = 4 full waves of 148 SMs x 2 resident walker CTAs)")
-    ap.add_argument("--ic-path", default="R", choices=["R", "S", "G"])
+    ap.add_argument("--ic-path", default="G", choices=["R", "S", "G"],
+                    help="IC formulation: G = triple sum contracted over the walkers of the shared-grid batch on the FP64 "
+                         "tensor cores (default), R = per-walker triple sum, S = exact suffix-sum collapse")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-fast-path", action="store_true")
@@ -450,17 +452,19 @@ def main():
     #      kernel, D2H into pinned memory, results touched on the host.  At N > 1 the exchange step is inside as well:
     #      the SEDs of the batch are all-gathered over NCCL from the engine's device buffer and the gathered rows are what
     #      is copied to the host (every rank ends up with every walker's SED, like shard.evaluate_sharded).
-    e2e_engines = [None, None]                      # two engines, one per worker thread / CUDA stream
-    e2e_engines_h = [None, None]
+    E2E_DEPTH = 3                                   # batches in flight: one engine + CUDA stream + worker thread each
+    e2e_engines = [None] * E2E_DEPTH
+    e2e_engines_h = [None] * E2E_DEPTH
     gathered_host = torch.empty((world * W, eng.Nt), dtype=torch.float64, pin_memory=True) if world > 1 else None
 
     def e2e_run(nb, device_pack=True):
         tot = 0.0
         engines = e2e_engines if device_pack else e2e_engines_h
         for k, (b2, N_h, sed_h) in enumerate(LeMoC.run_many((sets for _ in range(nb)), ic_path=args.ic_path,
-                                                            engines=engines, device_pack=device_pack)):
+                                                            engines=engines, device_pack=device_pack,
+                                                            depth=E2E_DEPTH)):
             if world > 1 and device_pack:
-                src = engines[k % 2]._out_dev[1]                # device SEDs of this batch (the engine is idle until the
+                src = engines[k % E2E_DEPTH]._out_dev[1]                # device SEDs of this batch (the engine is idle until the
                 dist.all_gather_into_tensor(sed_all, src.view(-1, eng.Nt)[:W])          # next batch is drawn)
                 gathered_host.copy_(sed_all, non_blocking=True)
                 torch.cuda.current_stream().synchronize()
@@ -636,8 +640,8 @@ def main():
                     "what": "LeMoC.run_many(stream of batches of parameter dicts) -> host spectra; every batch: parameter "
                             "dicts -> one row of scalars per walker (host) + pinned H2D + device-side grid/injection "
                             "set-up (lhm_pack_batch) + tables + cor-factor + fused kernel + D2H into pinned memory; "
-                            "two worker threads with their own engine and CUDA stream, so one batch's host work and "
-                            "copies overlap the other's kernels"
+                            "three worker threads with their own engine and CUDA stream, so one batch's host work and "
+                            "copies overlap the others' kernels"
                             + ("; at N > 1 the SEDs of every batch are also all-gathered over NCCL and the gathered "
                                "[N*W, Nt] rows copied to the host on every rank" if world > 1 else ""),
                     "host_packed_value": world * W * e2e_nb / e2e_hostpack_s,

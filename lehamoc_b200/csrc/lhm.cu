@@ -4,6 +4,7 @@
 #include <atomic>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -199,10 +200,23 @@ __device__ __forceinline__ void set_time(Ctx& C, double t) {                 // 
     C.V = volume_of(C.Rad);
 }
 
-#ifndef LHM_G_MIN_CTAS
-#define LHM_G_MIN_CTAS 2
-#endif
-__global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
+// static per-walker inputs of the half-step phases (the subset of ic_prepare they read)
+template <int NTH>
+__device__ void g_prepare(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x;
+    for (int j = tid; j < L.Ng; j += NTH) S.gS[j] = C.T[L.g + j];
+    for (int i = tid; i < 64; i += NTH) S.e2tab[i] = exp2((double)i / 64.0);
+    for (int i = tid; i < L.Nt; i += NTH) {
+        S.lxtS[i] = C.T[L.lxt + i];
+        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.T[L.lxt + i + 1] - C.T[L.lxt + i]) : 0.0;
+    }
+    __syncthreads();
+}
+
+// MINB resident CTAs per SM: without the IC body the half-step phases fit 80 (MINB 3) or 64 (MINB 4) registers
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
     extern __shared__ __align__(16) double smem_raw[];
     const RunArgs& A = G.R;
     const int w = blockIdx.x;
@@ -218,7 +232,8 @@ __global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
     if (nsteps < 1) { if (G.step == 0) no_step_outputs<NT>(A, w, Ng, Nt, 0); return; }
     const GState O = gstate_layout(L);
     double* st = G.state + (size_t)w * O.total;
-    ic_prepare<NT>(C, S);
+    g_prepare<NT>(C, S);
+    long long tprev = clock64();
     double t = C.tinit;
     for (int k = 0; k < G.step; ++k) t += C.dt;                 // the reference's own accumulation, LeMoC.py:198
     if (G.do_B && G.step >= 1 && G.step <= nsteps) {
@@ -229,7 +244,9 @@ __global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
         for (int k = tid; k < Nt; k += NT) { S.Ln[k] = st[O.Ln + k]; S.Lm[k] = st[O.Lm + k]; }
         icg_finish<NT>(G.part, G.D, G.Wpad, w, S.QIC);
         __syncthreads();
+        LHM_TICK(0);
         phase_photon_solves<NT>(C, S, cor);
+        LHM_TICK(8);
         if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
             const double* Lng = S.Ln;
             if (C.F.qee_from_ic) {
@@ -240,6 +257,7 @@ __global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
             phase_gg<NT>(C, S, Lng, S.agg, S.qee);
             __syncthreads();
         }
+        LHM_TICK(9);
         const int step = G.step - 1;
         const bool last = (step == nsteps - 1);
         const int slot = A.snapshots > 0 ? step : 0;
@@ -270,12 +288,18 @@ __global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
         }
         t += C.dt;
         set_time(C, t);
+        LHM_TICK(0);
         phase_photons<NT>(C, S, true);
+        LHM_TICK(1);
         if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        LHM_TICK(2);
         phase_electrons<NT>(C, S);
+        LHM_TICK(3);
         phase_vectors<NT>(C, S);
+        LHM_TICK(4);
         phase_syn_rows<NT>(C, S, false);
         __syncthreads();
+        LHM_TICK(5);
         for (int j = tid; j < Ng; j += NT) st[O.N + j] = S.N[j];
         for (int k = tid; k < Ns; k += NT) { st[O.psyn + k] = S.psyn[k]; st[O.Qsyn + k] = S.Qsyn[k]; st[O.aS + k] = S.aS[k]; }
         for (int k = tid; k < Ni; k += NT) { st[O.pic + k] = S.pic[k]; st[O.agg + k] = S.agg[k]; st[O.aI + k] = S.aI[k]; }
@@ -284,6 +308,7 @@ __global__ void __launch_bounds__(NT, LHM_G_MIN_CTAS) stepG_kernel(GArgs G) {
         for (int i = tid; i < G.D.Kp; i += NT) gp[i] = (i < G.D.Ntar) ? S.tri[4 * i + 2] : 0.0;     // the last target bin is dropped
         double* gav = G.gav + (size_t)w * G.D.NgP;
         for (int j = tid; j < G.D.NgP; j += NT) gav[j] = (j < Ng) ? S.av[j] : 0.0;
+        LHM_TICK(6);
     }
 }
 
@@ -715,6 +740,7 @@ static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& 
     if (e == cudaSuccess) { while (bytes > cur && !mark.compare_exchange_weak(cur, bytes)) {} }
     return e;
 }
+constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the registers are budgeted for (LHM_G_CTAS overrides)
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
 static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
@@ -1076,11 +1102,13 @@ static int run_pathG(lhm_handle* h, const RunArgs& A) {
     GArgs G;
     G.R = A; G.D = h->GD; G.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
     G.state = h->d_state; G.gp = h->d_gp; G.gav = h->d_gav; G.part = h->d_part;
-    CUDA_TRY(ensure_dyn_smem(stepG_kernel, h->smem, g_smem_stepg[h->device % MAX_DEV]));
+    static const int minb = [] { const char* e = std::getenv("LHM_G_CTAS"); const int v = e ? std::atoi(e) : 0; return (v >= 2 && v <= 4) ? v : LHM_G_DEFAULT_CTAS; }();
+    void (*kern)(GArgs) = minb == 4 ? stepG_kernel<4> : minb == 3 ? stepG_kernel<3> : stepG_kernel<2>;
+    CUDA_TRY(ensure_dyn_smem(kern, h->smem, g_smem_stepg[(h->device % MAX_DEV)]));
     h->evg_n = 0;
     for (int k = 0; k <= n; ++k) {
         G.step = k; G.do_B = k >= 1; G.do_A = k < n;
-        stepG_kernel<<<h->W, NT, h->smem, h->stream>>>(G);
+        kern<<<h->W, NT, h->smem, h->stream>>>(G);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
         if (k < n) {
@@ -1234,7 +1262,10 @@ int lhm_run_batch_host(lhm_handle* h, int W, const double* consts, const double*
     if (rc != LHM_OK) return rc;
     if (N_out) CUDA_TRY(cudaMemcpyAsync(N_out, h->d_Nout, nN * sizeof(double), cudaMemcpyDeviceToHost, s));
     if (sed_out) CUDA_TRY(cudaMemcpyAsync(sed_out, h->d_sed, nS * sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
+    // wait for THIS batch only: other handles may share the stream (lehamoc_b200.LeMoC.run_many queues the batches of
+    // all its worker threads on one stream so that the GPU works through them first in, first out)
+    CUDA_TRY(cudaEventRecord(h->ev_join, s));
+    CUDA_TRY(cudaEventSynchronize(h->ev_join));
     return LHM_OK;
 }
 

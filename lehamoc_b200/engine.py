@@ -245,6 +245,8 @@ class Engine:
         W = batch.W
         S = snapshots if snapshots > 0 else 1
         hp = lambda a: a.ctypes.data_as(C.c_void_p)
+        if self.ic_path == "G":
+            self.set_lockstep(batch.nsteps)
         ins = batch.arrays()
         if pinned:
             # stage through page-locked buffers so the copies run at full PCIe/NVLink-C2C rate
@@ -282,7 +284,9 @@ class Engine:
         with torch.cuda.stream(self.stream):
             self._pin[kN][:W * self.Ng].copy_(Nd.view(-1)[:W * self.Ng], non_blocking=True)
             self._pin[kS][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
-        self.stream.synchronize()
+            done = torch.cuda.Event()
+            done.record(self.stream)
+        done.synchronize()          # this batch only: other engines may have queued later batches on the same stream
         return Nh_, sh_
 
     def last_icg_timing(self):

@@ -724,12 +724,16 @@ def pack_script_request(param_sets) -> PackRequest:
         raise KeyError(f"parameter file lacks {missing}")
     shared_keys = [k for k in SCRIPT_KEYS if k not in WALKER_KEYS]
     get_shared, get_walker = itemgetter(*shared_keys), itemgetter(*WALKER_KEYS)
-    ref = tuple(float(v) for v in get_shared(F))
-    for P in param_sets[1:]:
-        if get_shared(P) != ref and tuple(float(v) for v in get_shared(P)) != ref:
-            bad = [k for k in shared_keys if float(P[k]) != float(F[k])]
-            raise ValueError(f"walkers of one batch must share '{bad[0]}'")
-    table = np.array([get_walker(P) for P in param_sets], dtype=np.float64)
+    ref = get_shared(F)
+    # the walkers of a batch differ in WALKER_KEYS only: one C-level pass over the dicts; sets whose shared values are
+    # equal but not identical objects (1 vs 1.0) take the slow comparison
+    if not all(map(ref.__eq__, map(get_shared, param_sets))):
+        reff = tuple(float(v) for v in ref)
+        for P in param_sets[1:]:
+            if tuple(float(v) for v in get_shared(P)) != reff:
+                bad = [k for k in shared_keys if float(P[k]) != float(F[k])]
+                raise ValueError(f"walkers of one batch must share '{bad[0]}'")
+    table = np.array(list(map(get_walker, param_sets)), dtype=np.float64)
     col = lambda k: np.ascontiguousarray(table[:, WALKER_KEYS.index(k)])
     R0 = _pow10(col("R0"))
     L_el = _pow10(col("L_el"))

@@ -33,6 +33,9 @@ torch.cuda.synchronize()
 eng.lib.lhm_set_phase_profile(eng.h, None)
 p = prof.cpu().numpy().astype(float)
 names = ["loop/out", "photons", "uph", "electrons", "vectors", "syn_rows(w0)", "ic(w0)", "wait_ic", "ic_fin+ph_solves", "gg"]
+if a.ic_path == "G":
+    names = ["load+Q_IC / time", "photons", "uph", "electrons", "vectors", "syn_rows", "store", "-", "photon solves", "gg"]
+    print("contraction (mean ms, launches, CTAs, smem):", eng.last_icg_timing())
 tot = p.sum()
 print("phase cycles per walker-step (thread 0), total %.0f:" % (tot / a.walkers / 10))
 for n_, v in zip(names, p):
