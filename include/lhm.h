@@ -76,6 +76,9 @@ typedef struct {
     int pp_l_flag;                      /* driver 1: pp loss term of the proton equation            LeHaMoC.py:322-328 */
     int pp_ee_emis_flag, pp_g_emis_flag, pp_nu_emis_flag; /* driver 1: pp pairs, pi0 photons, neutrinos (n_H, p_pr in
                                            the per-walker scalar block)                               LeHaMoC.py:354-395 */
+    int shared_had_grids;   /* driver 1 with photo-hadronic flags: 1 = all walkers of every batch share g_el, g_pr, nu_ic and nu_tot,
+                               so the state-independent operators of Q_BH_sol / Qp_g_opt / dg_dt_pg (lhm_hadtab.cuh) are
+                               tabulated once per batch instead of once per walker */
     int max_walkers;        /* capacity W of the handle's workspace */
 } lhm_config;
 
@@ -125,6 +128,11 @@ int lhm_set_lockstep(lhm_handle*, int nsteps);
 /* ic_path G only: mean device time of the contraction launches of the last run (CUDA events on the stream), how many
  * were timed, the grid size and the dynamic shared memory per CTA */
 int lhm_last_icg_timing(lhm_handle*, float* mean_ms, int* launches, int* ctas, int* smem_bytes);
+
+/* driver 1 with photo-hadronic flags: device time of the last build of the state-independent operator tables of Q_BH_sol /
+ * Qp_g_opt / dg_dt_pg (queued by lhm_setup_batch), the number of table sets (1 = shared by the batch) and their size;
+ * ms = -1 when the per-step evaluation is in use (tables switched off with LHM_HAD_TABLES=0 or too large) */
+int lhm_last_hadtab_timing(lhm_handle*, float* ms, int* table_sets, long long* bytes);
 
 /* A5: cor_factor_syn_el (LeHaMoC_f.py:175-237) for every walker of the current batch -> out[W].
  * One warp per walker; the 200-step inner simulation is advanced with a warp-level affine scan. */

@@ -63,7 +63,7 @@ def raw_batch(g=None, nu_syn=None, nu_ic=None, nu_tot=None, R0=1e15, B0=1., ext=
     if cor is not None:
         consts[0, _lib.C_COR_P], consts[0, _lib.C_COR_Q0], consts[0, _lib.C_COR_B] = cor
     cfg = dict(Ng=len(g), Ns=len(nu_syn), Ni=len(nu_ic), Nt=len(nu_tot), gg_npts=gg_npts,
-               loss_minus_one=loss_minus_one, qee_from_ic=qee_from_ic, const_B=0, ic_pair_table=1, shared_ic_grids=0, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0, neutrino_flag=0, pg_BH_emis_flag=0,
+               loss_minus_one=loss_minus_one, qee_from_ic=qee_from_ic, const_B=0, ic_pair_table=1, shared_ic_grids=0, shared_had_grids=0, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0, neutrino_flag=0, pg_BH_emis_flag=0,
                inj_flag=1, Ad_l_flag=0, Syn_l_flag=1, Syn_emis_flag=1, IC_l_flag=1, IC_emis_flag=1, SSA_l_flag=1,
                gg_flag=1, esc_flag=1)
     ext = np.zeros(len(nu_tot)) if ext is None else np.asarray(ext, dtype=np.float64)

@@ -28,7 +28,7 @@ class lhm_config(C.Structure):
         "gg_flag", "esc_flag", "loss_minus_one", "qee_from_ic", "gg_npts", "ic_path", "const_B", "ic_pair_table",
         "shared_ic_grids", "driver", "Np", "esc_flag_pr", "pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag",
         "neutrino_flag", "pg_BH_emis_flag", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag", "pp_nu_emis_flag",
-        "max_walkers")]
+        "shared_had_grids", "max_walkers")]
 
 
 LHM_PACK_NPAR = 20
@@ -67,6 +67,7 @@ SIGNATURES = {
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),
     "lhm_set_lockstep": (C.c_int, [_P, C.c_int]),
+    "lhm_last_hadtab_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "lhm_last_icg_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),
     "lhm_photons_tot_batch": (C.c_int, [_P] * 5),

@@ -18,6 +18,7 @@
 #include "lhm_had.cuh"
 #include "lhm_pack.cuh"
 #include "lhm_icg.cuh"
+#include "lhm_hadtab.cuh"
 
 namespace lhm {
 
@@ -45,6 +46,9 @@ struct RunArgs {
     HadTables HT;
     BhSurf BSm, BSp;        // Bethe-Heitler spline surfaces (device pointers), F.bh_e
     double* sed_out;        // [W,(S),Nt] or null
+    HadTabs HTab;           // state-independent photo-hadronic operators (lhm_hadtab.cuh) when use_tabs
+    HadTabDims HD;
+    int use_tabs;
     unsigned long long* prof;   // optional [16] per-phase clock64 totals of thread 0 (diagnostics)
 };
 
@@ -393,7 +397,8 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
     }
     BhStaged BG;
     BG.base = H.bhsurf; BG.zmax = H.bhsurf; BG.desc = reinterpret_cast<const int*>(H.bhsurf + 2);
-    if (A.had && C.F.bh_e) {
+    const HadTabs Tw = A.use_tabs ? hadtabs_of(A.HTab, w) : A.HTab;
+    if (A.had && C.F.bh_e && !A.use_tabs) {
         BhSurf tmp;
         int* desc = reinterpret_cast<int*>(H.bhsurf + 2);
         double* p2 = bh_stage(tmp, A.BSm, H.bhsurf + 2 + BH_DESC_INTS, NTL, H.bhsurf, desc, H.bhsurf);
@@ -412,11 +417,21 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
         phase_photons<NTL>(C, S, true);
         if (C.F.ic_l) phase_uph_lh<NTL>(C, S);
         LHM_TICK(1);
-        phase_protons<NTL>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H);
+        const bool pg_tab = A.use_tabs && C.F.pg_l;
+        if (pg_tab) {                                            // dg_dt_pg from the tabulated operator
+            for (int k = tid; k < Nt; k += NTL) {
+                H.lxpg[k] = log10(kHC.h * C.T[L.nt + k]);
+                H.lppg[k] = log10(S.n[k] / kHC.h);
+            }
+            __syncthreads();
+            phase_loss_pg_tab<NTL>(C, H, Tw, A.HD.nloss);
+            __syncthreads();
+        }
+        phase_protons<NTL>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H, pg_tab);
         LHM_TICK(2);
-        if (C.F.bh_e) phase_bh_emis<NTL>(C, S, H, BG);
+        if (C.F.bh_e) { if (A.use_tabs) phase_bh_emis_tab<NTL>(C, S, H, Tw, A.HD.npairs); else phase_bh_emis<NTL>(C, S, H, BG); }
         LHM_TICK(3);
-        if (C.F.pg_e) phase_photopion<NTL>(C, S, H, A.HT);
+        if (C.F.pg_e) { if (A.use_tabs) phase_photopion_tab<NTL>(C, S, H, A.HT, Tw, A.HD); else phase_photopion<NTL>(C, S, H, A.HT); }
         else if (A.had) { for (int k = tid; k < 52; k += NTL) H.Qnu[k] = 0.0; }
         LHM_TICK(4);
         if (C.F.pp_ee || C.F.pp_g || C.F.pp_nu) phase_pp<NTL>(C, S, H, n_H, p_pr);
@@ -801,6 +816,12 @@ struct lhm_handle {
     int lock_steps;
     cudaEvent_t evg[2 * LHM_G_MAXEV];
     int evg_n;
+    // state-independent photo-hadronic operators (lhm_hadtab.cuh), built by lhm_setup_batch
+    HadTabs HTab;
+    size_t htab_sets;         // capacity in table sets (1 when the grids are shared)
+    bool use_tabs;
+    cudaEvent_t ev_tab[2];
+    bool ev_tab_set;
 };
 
 static PhysConst make_consts() {
@@ -842,6 +863,12 @@ const char* lhm_last_cuda_error(void) { return g_cuda_err.c_str(); }
 long long lhm_launch_count(void) { return g_launches.load(); }
 
 void lhm_destroy(lhm_handle* h);
+static void free_had_tabs(lhm_handle* h) {
+    cudaFree(h->HTab.bhK); cudaFree(h->HTab.bhdx); cudaFree(h->HTab.bhcode); cudaFree(h->HTab.phi);
+    cudaFree(h->HTab.lossA); cudaFree(h->HTab.lossdx); cudaFree(h->HTab.losscode);
+    std::memset(&h->HTab, 0, sizeof(h->HTab));
+    h->htab_sets = 0;
+}
 // everything of lhm_create that can fail after the handle exists; the caller destroys the handle on error
 static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* cuda_stream, const cudaDeviceProp& prop) {
     h->cfg = *cfg;
@@ -936,6 +963,8 @@ void lhm_destroy(lhm_handle* h) {
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
     cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
     cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
+    free_had_tabs(h);
+    for (int i = 0; i < 2; ++i) if (h->ev_tab[i]) cudaEventDestroy(h->ev_tab[i]);
     for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) if (h->evg[i]) cudaEventDestroy(h->evg[i]);
     for (int i = 0; i < 6; ++i) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -950,6 +979,80 @@ long long lhm_table_bytes_per_walker(const lhm_handle* h) {
 }
 
 static int launch_cor(lhm_handle* h, double* out, cudaStream_t st);
+static int had_init();
+
+// The state-independent operators of the photo-hadronic phases (lhm_hadtab.cuh), once per batch when the walkers share
+// their grids, else once per walker; queued behind setup_kernel.  Falls back to the per-step evaluation (use_tabs =
+// false) when the tables would not fit or LHM_HAD_TABLES=0 is set.
+static int build_had_tabs(lhm_handle* h, int W) {
+    h->use_tabs = false;
+    const StepFlags& F = h->F;
+    if (h->cfg.driver != 1 || !(F.bh_e || F.pg_e || F.pg_l)) return LHM_OK;
+    const char* env = std::getenv("LHM_HAD_TABLES");
+    if (env && std::atoi(env) == 0) return LHM_OK;
+    if ((F.pg_e || F.pg_l) && !h->have_HT) return LHM_ERR_STATE;
+    if (F.bh_e && !h->have_BS) return LHM_ERR_STATE;
+    const HadTabDims D = hadtab_dims(h->L);
+    const bool shared = h->cfg.shared_had_grids != 0;
+    const size_t sets = shared ? 1 : (size_t)W;
+    const size_t nbh = (size_t)10 * D.npairs, nphi = (size_t)D.nout * PG_N, nloss = (size_t)D.nloss * LOSS_N;
+    if (sets > h->htab_sets || (h->HTab.shared != 0) != shared) {
+        free_had_tabs(h);
+        const size_t bytes = sets * ((F.bh_e ? nbh * 20 : 0) + (F.pg_e ? nphi * 8 : 0) + (F.pg_l ? nloss * 20 : 0));
+        size_t fr = 0, tot = 0;
+        CUDA_TRY(cudaMemGetInfo(&fr, &tot));
+        if (bytes > fr / 2) return LHM_OK;                       // does not fit comfortably: per-step evaluation
+        bool ok = true;
+        auto alloc = [&](void** p, size_t n) { if (ok && cudaMalloc(p, n) != cudaSuccess) { ok = false; cudaGetLastError(); } };
+        if (F.bh_e) { alloc((void**)&h->HTab.bhK, sets * nbh * 8); alloc((void**)&h->HTab.bhdx, sets * nbh * 8); alloc((void**)&h->HTab.bhcode, sets * nbh * 4); }
+        if (F.pg_e) alloc((void**)&h->HTab.phi, sets * nphi * 8);
+        if (F.pg_l) { alloc((void**)&h->HTab.lossA, sets * nloss * 8); alloc((void**)&h->HTab.lossdx, sets * nloss * 8); alloc((void**)&h->HTab.losscode, sets * nloss * 4); }
+        if (!ok) { free_had_tabs(h); return LHM_OK; }
+        h->htab_sets = sets;
+        h->HTab.shared = shared ? 1 : 0;
+        h->HTab.bh_stride = nbh; h->HTab.phi_stride = nphi; h->HTab.loss_stride = nloss;
+    }
+    HadTabArgs A;
+    A.L = h->L; A.D = D; A.W = (int)sets; A.tabd = h->d_tabd; A.T = h->HTab;
+    if (h->have_HT) A.HT = h->HT; else std::memset(&A.HT, 0, sizeof(A.HT));
+    std::memset(&A.Sm, 0, sizeof(A.Sm)); std::memset(&A.Sp, 0, sizeof(A.Sp));
+    if (h->have_BS) { A.Sm = h->BSm; A.Sp = h->BSp; }
+    A.do_bh = F.bh_e; A.do_pion = F.pg_e; A.do_loss = F.pg_l; A.do_nu = F.nu;
+    int rc = had_init();
+    if (rc != LHM_OK) return rc;
+    if (!h->ev_tab[0]) { CUDA_TRY(cudaEventCreate(&h->ev_tab[0])); CUDA_TRY(cudaEventCreate(&h->ev_tab[1])); }
+    CUDA_TRY(cudaEventRecord(h->ev_tab[0], h->stream));
+    if (F.bh_e) {
+        const size_t smem = ((size_t)h->L.Nt + 3 * h->L.Np + 4 * (A.Sm.nx + A.Sm.ny) + (size_t)(A.Sm.nx - 4) * (A.Sm.ny - 4)
+                             + 4 * (A.Sp.nx + A.Sp.ny) + (size_t)(A.Sp.nx - 4) * (A.Sp.ny - 4) + 8 + 2 + BH_DESC_INTS) * sizeof(double);
+        if (smem > 200 * 1024) return LHM_ERR_CAPACITY;
+        CUDA_TRY(cudaFuncSetAttribute(bh_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)sets, (h->L.Ng + BH_CH - 1) / BH_CH);
+        bh_table_kernel<<<grid, HAD_NT, smem, h->stream>>>(A);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (F.pg_e) {
+        const size_t smem = (52 + pion_work_doubles(HAD_MAXTAB)) * sizeof(double);
+        CUDA_TRY(cudaFuncSetAttribute(pion_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)sets, SP_COUNT);
+        pion_table_kernel<<<grid, HAD_NT, smem, h->stream>>>(A);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    if (F.pg_l) {
+        const size_t smem = ((size_t)h->L.Nt + loss_tab_doubles(A.HT)) * sizeof(double);
+        CUDA_TRY(cudaFuncSetAttribute(loss_table_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)sets, shared ? 20 : 1);
+        loss_table_kernel<<<grid, HAD_NT, smem, h->stream>>>(A);
+        g_launches++;
+        CUDA_TRY(cudaGetLastError());
+    }
+    CUDA_TRY(cudaEventRecord(h->ev_tab[1], h->stream));
+    h->ev_tab_set = true;
+    h->use_tabs = true;
+    return LHM_OK;
+}
 
 int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_el, const double* nu_syn,
                     const double* nu_ic, const double* nu_tot, const double* el_inj, const double* ext) {
@@ -981,6 +1084,10 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     setup_kernel<NT><<<W, NT, 0, h->stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    {
+        int rc = build_had_tabs(h, W);
+        if (rc != LHM_OK) return rc;
+    }
     if (h->pathG) {                                  // grid-only tables of the contraction, from walker 0's tables
         IcgSetupArgs G;
         G.L = h->L; G.D = h->GD; G.tabd = h->d_tabd; G.ptg = h->d_ptg; G.kinfo = h->d_kinfo; G.xs = h->d_xs;
@@ -1016,6 +1123,7 @@ int lhm_cor_factor_batch(lhm_handle* h, double* out) {
 static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double* N_pr_out, double* N_nu_out,
                       int snapshots, bool lh);
 static int had_init();
+int lhm_last_hadtab_timing(lhm_handle* h, float* ms, int* table_sets, long long* bytes);
 static HadTables to_dev_tables(const lhm_had_tables* t);
 
 int lhm_set_protons(lhm_handle* h, const double* g_pr, const double* pr_inj) {
@@ -1146,6 +1254,9 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     A.prof = h->d_prof;
+    A.use_tabs = (lh && h->use_tabs) ? 1 : 0;
+    A.HTab = h->HTab;
+    A.HD = hadtab_dims(h->L);
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     if (h->pathG) {
         int rc = run_pathG(h, A);
@@ -1189,6 +1300,22 @@ int lhm_last_timings(lhm_handle* h, float* setup_ms, float* cor_ms, float* run_m
         if (!h->ev_set[i]) continue;
         CUDA_TRY(cudaEventSynchronize(h->ev[2 * i + 1]));
         CUDA_TRY(cudaEventElapsedTime(outs[i], h->ev[2 * i], h->ev[2 * i + 1]));
+    }
+    return LHM_OK;
+}
+
+int lhm_last_hadtab_timing(lhm_handle* h, float* ms, int* table_sets, long long* bytes) {
+    if (!h) return LHM_ERR_ARG;
+    if (ms) *ms = -1.f;
+    if (table_sets) *table_sets = 0;
+    if (bytes) *bytes = 0;
+    if (!h->use_tabs || !h->ev_tab_set) return LHM_OK;
+    if (ms) { CUDA_TRY(cudaEventSynchronize(h->ev_tab[1])); CUDA_TRY(cudaEventElapsedTime(ms, h->ev_tab[0], h->ev_tab[1])); }
+    if (table_sets) *table_sets = (int)h->htab_sets;
+    if (bytes) {
+        const StepFlags& F = h->F;
+        *bytes = (long long)(h->htab_sets * ((F.bh_e ? h->HTab.bh_stride * 20 : 0) + (F.pg_e ? h->HTab.phi_stride * 8 : 0)
+                                             + (F.pg_l ? h->HTab.loss_stride * 20 : 0)));
     }
     return LHM_OK;
 }

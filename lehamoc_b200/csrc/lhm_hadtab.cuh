@@ -192,11 +192,11 @@ __global__ void __launch_bounds__(HAD_NT) bh_table_kernel(HadTabArgs A) {
 
 // Q_BH_sol with the table: Qbh[i] = c sum_j n_p[j] sum_e K[e][i,j] 10^interp(log10 photons at E_arr[e]); one warp per gamma_e
 template <int NT>
-__device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTabs& Tw, int npairs, double* DxT) {
+__device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTabs& Tw, int npairs) {
     const Layout& L = C.L;
     const int Np = L.Np, Ng = L.Ng, Nt = L.Nt;
+    const double* __restrict__ xt = C.T + L.xt;
     for (int j = threadIdx.x; j < Np; j += NT) H.npl[j] = H.Npr[j] / C.V;
-    for (int k = threadIdx.x; k < Nt - 1; k += NT) DxT[k] = C.T[L.xt + k + 1] - C.T[L.xt + k];
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = warp; i < Ng; i += NT / 32) {
@@ -210,7 +210,8 @@ __device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTab
                 if (K != 0.0) {
                     const int code = __ldg(Tw.bhcode + (size_t)e * npairs + pair);
                     const double dx = __ldg(Tw.bhdx + (size_t)e * npairs + pair);
-                    g = fma(K, exp10(interp_eval(S.Ln, code, dx, DxT[min(code >> 1, Nt - 2)])), g);
+                    const int jx = min(code >> 1, Nt - 2);
+                    g = fma(K, exp10(interp_eval(S.Ln, code, dx, __ldg(xt + jx + 1) - __ldg(xt + jx))), g);
                 }
             }
             s = fma(H.npl[j], g, s);
@@ -494,10 +495,11 @@ __global__ void __launch_bounds__(HAD_NT) loss_table_kernel(HadTabArgs A) {
     }
 }
 
-// dg_dt_pg at every midpoint with the table (one warp per midpoint); lp = log10(photons / h) staged by the caller in
-// H.lppg, DxL[j] = lx[j+1] - lx[j]
+// dg_dt_pg at every midpoint with the table (one warp per midpoint); the caller has staged lx = log10(h nu) in H.lxpg and
+// lp = log10(photons / h) in H.lppg
 template <int NT>
-__device__ void phase_loss_pg_tab(const Ctx& C, SmemLh& H, const HadTabs& Tw, int nloss, const double* DxL) {
+__device__ void phase_loss_pg_tab(const Ctx& C, SmemLh& H, const HadTabs& Tw, int nloss) {
+    const double* __restrict__ lx = H.lxpg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, Nt = C.L.Nt;
     for (int k = warp; k < nloss; k += NT / 32) {
         const double* __restrict__ Ak = Tw.lossA + (size_t)k * LOSS_N;
@@ -508,14 +510,16 @@ __device__ void phase_loss_pg_tab(const Ctx& C, SmemLh& H, const HadTabs& Tw, in
             const double A0 = __ldg(Ak + m);
             if (A0 != 0.0) {
                 const int code = __ldg(ck + m);
-                s0 = fma(A0, exp10(interp_eval(H.lppg, code, __ldg(dk + m), DxL[min(code >> 1, Nt - 2)])), s0);
+                const int jx = min(code >> 1, Nt - 2);
+                s0 = fma(A0, exp10(interp_eval(H.lppg, code, __ldg(dk + m), lx[jx + 1] - lx[jx])), s0);
             }
             const int m1 = m + 32;
             if (m1 < LOSS_N) {
                 const double A1 = __ldg(Ak + m1);
                 if (A1 != 0.0) {
                     const int code = __ldg(ck + m1);
-                    s1 = fma(A1, exp10(interp_eval(H.lppg, code, __ldg(dk + m1), DxL[min(code >> 1, Nt - 2)])), s1);
+                    const int jx = min(code >> 1, Nt - 2);
+                    s1 = fma(A1, exp10(interp_eval(H.lppg, code, __ldg(dk + m1), lx[jx + 1] - lx[jx])), s1);
                 }
             }
         }

@@ -195,7 +195,7 @@ __device__ void phase_uph_lh(const Ctx& C, Smem& S) {
 // proton equation (LeHaMoC.py:330-335 with the hadronic loss terms off): synchrotron cooling + escape + injection
 template <int NT>
 __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, const LossTab* Tb, bool per_volume = true,
-                              bool inject = true, double n_H = 0.0) {
+                              bool inject = true, double n_H = 0.0, bool pg_tabulated = false) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, n = L.Np - 2;
     const bool had = C.F.pg_l || C.F.bh_l;
@@ -210,9 +210,10 @@ __device__ void phase_protons(const Ctx& C, Smem& S, SmemLh& H, int esc_pr, cons
         const double hnu_max = hK * C.T[L.nt + Nt - 1];
         for (int k = tid >> 5; k < L.Np - 1; k += NT / 32) {
             const double gm = C.T[L.gpm + k];
-            const double a = C.F.pg_l ? had_loss_warp(0, gm, Nt, hnu_max, H.lxpg, H.lppg, *Tb) : 0.0;
+            // pg_tabulated: H.lossA already holds dg_dt_pg (phase_loss_pg_tab, lhm_hadtab.cuh)
+            const double a = (C.F.pg_l && !pg_tabulated) ? had_loss_warp(0, gm, Nt, hnu_max, H.lxpg, H.lppg, *Tb) : 0.0;
             const double b = C.F.bh_l ? had_loss_warp(1, gm, Nt, hnu_max, S.lxtS, S.Ln, *Tb) : 0.0;
-            if ((tid & 31) == 0) { H.lossA[k] = a; H.lossB[k] = b; }
+            if ((tid & 31) == 0) { if (!(C.F.pg_l && pg_tabulated)) H.lossA[k] = a; H.lossB[k] = b; }
         }
         __syncthreads();
     }

@@ -296,6 +296,12 @@ class Engine:
               "lhm_last_icg_timing")
         return ms.value, n.value, ctas.value, smem.value
 
+    def last_hadtab_timing(self):
+        """Driver 1 with photo-hadronic flags: (ms of the last operator-table build or -1, table sets, bytes)."""
+        ms, n, nb = C.c_float(), C.c_int(), C.c_longlong()
+        check(self.lib.lhm_last_hadtab_timing(self.h, C.byref(ms), C.byref(n), C.byref(nb)), "lhm_last_hadtab_timing")
+        return ms.value, n.value, nb.value
+
     def last_timings(self):
         """(setup_ms, cor_ms, run_ms) of the most recent launches, measured with CUDA events on the stream."""
         a, b, c = C.c_float(), C.c_float(), C.c_float()

@@ -155,7 +155,7 @@ def _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp, shared):
                qee_from_ic=0 if variant == "script" else 1,          # LeMoC.py:283 vs Code.py:269
                const_B=int(float(F["m"]) == 0. or Vexp == 0.),      # B = B0*(R0/R)**m never changes (LeMoC.py:199-200)
                ic_pair_table=1, driver=0, Np=0, esc_flag_pr=0, pg_pi_l_flag=0, pg_BH_l_flag=0, pg_pi_emis_flag=0,
-               neutrino_flag=0, pg_BH_emis_flag=0, shared_ic_grids=int(shared))
+               neutrino_flag=0, pg_BH_emis_flag=0, shared_ic_grids=int(shared), shared_had_grids=0)
     for k in FLAG_KEYS:
         cfg[k] = _flag01(F, k)
     # gg_flag is tested with `== 0.` (LeMoC.py:279): anything else switches it on; inj_flag is tested both ways
@@ -464,6 +464,9 @@ def _pack_lehamoc_loop(param_sets) -> Batch:
     cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=100, loss_minus_one=1, qee_from_ic=0,
                const_B=int(float(F["m"]) == 0. or Vexp == 0.), ic_pair_table=1,
                shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))),
+               # one set of photo-hadronic operator tables for the batch: g_el, g_pr, nu_ic and nu_tot shared
+               shared_had_grids=int(bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0])
+                                         and np.all(g_prs == g_prs[0]) and np.all(nu_ic == nu_ic[0]))),
                driver=1, Np=Np, esc_flag_pr=_flag01(F, "esc_flag_pr"))
     for k in PHOTOHADRONIC_FLAGS + PP_FLAGS:
         cfg[k] = _flag01(F, k)
@@ -585,6 +588,9 @@ def pack_lehamoc(param_sets) -> Batch:
     cfg = dict(Ng=Ng, Ns=Nh + 1, Ni=Nh, Nt=Nt, gg_npts=100, loss_minus_one=1, qee_from_ic=0,
                const_B=int(float(F["m"]) == 0. or Vexp == 0.), ic_pair_table=1,
                shared_ic_grids=int(W > 1 and bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0]))),
+               # one set of photo-hadronic operator tables for the batch: g_el, g_pr, nu_ic and nu_tot shared
+               shared_had_grids=int(bool(np.all(g_el == g_el[0]) and np.all(nu_tot == nu_tot[0])
+                                         and np.all(g_prs == g_prs[0]) and np.all(nu_ic == nu_ic[0]))),
                driver=1, Np=Np, esc_flag_pr=_flag01(F, "esc_flag_pr"))
     for k in PHOTOHADRONIC_FLAGS + PP_FLAGS:
         cfg[k] = _flag01(F, k)
@@ -709,7 +715,7 @@ def pack_code_lehamoc_request(thetas, frozen: dict) -> PackRequest:
     wp[:, _lib.PK_IDXMIN_PR], wp[:, _lib.PK_IDXMAX_PR] = _window_indices(gmin, gmax, int(float(F["grid_g_pr"])), lo_t, hi_t)
     wp[:, _lib.PK_P_PR] = thetas[:, 9]
     wp[:, _lib.PK_COMP_PR] = _pow10(thetas[:, 8])
-    req.cfg.update(driver=2, Np=int(float(F["grid_g_pr"])), esc_flag_pr=req.cfg["esc_flag"], shared_ic_grids=0)
+    req.cfg.update(driver=2, Np=int(float(F["grid_g_pr"])), esc_flag_pr=req.cfg["esc_flag"], shared_ic_grids=0, shared_had_grids=0)
     req.variant = "code_lh"
     return req
 
@@ -810,7 +816,7 @@ def pack_code_lehamoc(thetas, frozen: dict) -> Batch:
               comp_inj, thetas[:, 4].copy())                                    # Code.py:297-298
     Np = int(float(F["grid_g_pr"]))
     g_pr, pr_inj = _protons_code_lh(thetas, R0, Np)
-    b.cfg.update(driver=2, Np=Np, esc_flag_pr=b.cfg["esc_flag"], shared_ic_grids=0)
+    b.cfg.update(driver=2, Np=Np, esc_flag_pr=b.cfg["esc_flag"], shared_ic_grids=0, shared_had_grids=0)
     b.variant = "code_lh"
     b.g_pr, b.pr_inj = g_pr, pr_inj
     return b

@@ -262,6 +262,45 @@ def test_gpu_test4_small(name):
     log_close(Nnu[0, 1:], z["N_nu"][1:], "test4small N_nu")
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("shared", [True, False])
+def test_gpu_hadronic_operator_tables_equal_per_step_evaluation(shared, monkeypatch):
+    """The state-independent operators of Q_BH_sol / Qp_g_opt / dg_dt_pg are tabulated at set-up (lhm_hadtab.cuh): one set
+    for the batch when the walkers share their grids, one per walker otherwise.  Both must give what the per-step
+    evaluation of lhm_had.cuh gives (LHM_HAD_TABLES=0), which the fixtures above pin on the unmodified script."""
+    from lehamoc_b200 import LeHaMoC, hadronic
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.setup_host import pack_lehamoc
+    T = tables()
+    hadronic.set_tables({"phi_g": T["Phi_g"], "phi_el": T["Phi_el"], "phi_el1": T["Phi_el_1"], "fk": T["f_k_i"],
+                         "cs": T["cross_section"], "kp": T["kp_pg"]})
+    tm, tp, mm, mp_, rng = bh_surf_from_gold()
+    LeHaMoC._bh_cache[(float(rng[0]), float(rng[1]))] = (tm, tp, mm, mp_)
+    z, P = load_golden("lh_test4small")
+    if shared:
+        sets = [dict(P), dict(P, B0=0.3, L_pr=46.0, p_pr=2.2), dict(P, B0=0.05, L_el=41.)]
+    else:       # different proton / electron grids per walker (same nu_tot range: one pair of Bethe-Heitler surfaces)
+        sets = [dict(P), dict(P, g_max_pr=7.6, g_pr_PL_max=6.5, B0=0.3), dict(P, g_max_el=10.5, g_el_PL_max=5.2)]
+    b = pack_lehamoc(sets)
+    assert b.cfg["shared_had_grids"] == int(shared)
+    got = LeHaMoC.run(sets)
+    eng = Engine(b.cfg, b.W)
+    assert got[1].shape[0] == 3
+    monkeypatch.setenv("LHM_HAD_TABLES", "0")
+    ref = LeHaMoC.run(sets)
+    monkeypatch.delenv("LHM_HAD_TABLES")
+    for a, r, what in zip(got[1:], ref[1:], ("n_e", "nuLnu", "n_p", "N_nu")):
+        if what == "N_nu":          # step 1 only carries denormal junk (N_pr ~ 1e-260 there), see test_gpu_lehamoc_photohadronic_run
+            a, r = a[:, 1:], r[:, 1:]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            log_close(a, np.log10(r), f"tables vs per-step ({'shared' if shared else 'per walker'}) {what}", tol=1e-11)
+    log_close(got[1][0], z["n_e"], "tables: walker 0 n_e")
+    log_close(got[2][0], z["nuLnu"], "tables: walker 0 nuLnu")
+    log_close(got[3][0], z["n_p"], "tables: walker 0 n_p")
+    log_close(got[4][0, 1:], z["N_nu"][1:], "tables: walker 0 N_nu")
+    eng.close()
+
+
 @pytest.mark.parametrize("name", ["lh_pp", "lh_pp_pg"])
 def test_oracle_with_pp_channels(name):
     """pp loss term + pp pairs / pi0 photons / neutrinos (alone, and together with the photopion channels): pins the

@@ -121,10 +121,23 @@ def config3(W=148, reps=2, host_fit=True):
         eng.setup(b)
         out["r"] = eng.run_lh(snapshots=5)
     ms = _timed(go, reps)
+    tab_ms, tab_sets, tab_bytes = eng.last_hadtab_timing()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    eng.setup(b)
+    e0.record()
+    eng.run_lh(snapshots=5)
+    e1.record()
+    torch.cuda.synchronize()
+    loop_ms = e0.elapsed_time(e1)
     N, sed, Npr, Nnu = (t.cpu().numpy() for t in out["r"])
     res = {"what": "config 3: LeHaMoC.py, the reference's Test 4 at full size (Ng=300 Np=160 Nt=100, 5 timesteps, photopion "
                    "+ Bethe-Heitler losses and emissivities + neutrinos); H2D + set-up + fused kernel, every step written",
            "walkers": W, "ms_per_batch": ms, "ms_per_model": ms / W, "value": W / ms * 1e3, "unit": "model-evals/s",
+           "time_loop_ms": loop_ms,
+           "hadtab": {"build_ms": tab_ms, "table_sets": tab_sets, "bytes": tab_bytes,
+                      "what": "state-independent operators of Q_BH_sol / Qp_g_opt / dg_dt_pg tabulated at set-up (lhm_hadtab.cuh), "
+                              "inside ms_per_batch; build_ms = -1: per-step evaluation in use"},
            "host_setup_s": setup_s,
            "host_setup_what": ("interp_cs_BH_int (Bethe-Heitler spline surfaces: 27 000 Simpson integrals + two bisplrep "
                                "fits), once per nu_tot range and process" if host_fit else "stored tck (no host fit)"),
