@@ -48,13 +48,15 @@ def run(param_sets, ic_path="R", snapshots=True, engine=None):
 _bh_cache = {}
 
 
-def bh_surfaces(nu_min, nu_max):
+def bh_surfaces(nu_min, nu_max, disk_cache=True):
     """interp_cs_BH_int(np.logspace(0,8,50), np.logspace(0,10,50), nu_tot[0], nu_tot[-1]) of LeHaMoC.py:263 (host: 27 000
-    Simpson integrals + two SciPy bisplrep fits, a few seconds), cached per frequency range."""
+    Simpson integrals as one array expression + two SciPy bisplrep fits, ~0.5 s), kept per frequency range in the
+    process and, unless disk_cache is False, on disk (hadronic.interp_cs_BH_int)."""
     from . import hadronic
     key = (float(nu_min), float(nu_max))
     if key not in _bh_cache:
-        _bh_cache[key] = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu_min, nu_max)
+        _bh_cache[key] = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu_min, nu_max,
+                                                   cache=disk_cache)
     return _bh_cache[key]
 
 

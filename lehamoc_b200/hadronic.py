@@ -171,82 +171,117 @@ def Q_nu_e_pp(nu_nu, g_pr, N_pr_TeV, p_pr, n_H):
 # splines with scipy.interpolate.bisplrep; that fit stays on the host (SciPy/FITPACK, as in the reference), the spline
 # EVALUATION (4.8 M bisplev calls per step in the reference) runs on the GPU.
 # ---------------------------------------------------------------------------------------------------------------------
-def _cs_BH_diff(E_, g_pr, g_el, k):
-    """Differential Bethe-Heitler cross section d sigma/(d theta dE_) of Blumenthal (1970), LeHaMoC_f.py:238-273,
-    for an array of electron energies E_ (same elementwise arithmetic, so the doubles are the reference's)."""
+def _nonneg(a):
+    """NaN -> 0, negative -> 0 (the reference scrubs its intermediates this way, LeHaMoC_f.py:239-265)."""
+    a = np.where(np.isnan(a), 0., a)
+    return np.where(a < 0., 0., a)
+
+
+def _bh_lattice_integrand(E_el, gam_p, gam_e, kap):
+    """Blumenthal's (1970) Bethe-Heitler differential cross section d sigma / dE_- on a whole lattice at once.
+
+    E_el [M, n]: electron energies (m_e c^2) of M lattice points; gam_p, gam_e, kap [M, 1]: proton / electron Lorentz
+    factor and photon energy in the proton rest frame.  This is the formula `cs_BH_diff` of LeHaMoC_f.py:238-273
+    evaluates one lattice point at a time; every elementwise operation is kept in the reference's order (terms summed
+    left to right) so that the doubles -- and with them the knots SciPy's bisplrep picks -- come out identical."""
     from .constants import sigmaT
-    with np.errstate(all="ignore"):
-        E_p = k - E_
-        E_p = np.where(np.isnan(E_p), 0, E_p)
-        E_p[E_p < 0] = 0
-        p_ = np.sqrt(E_ ** 2 - 1.)
-        p_[p_ < 0] = 0.
-        p_p = np.sqrt(E_p ** 2. - 1.)
-        p_p = np.where(np.isnan(p_p), 0, p_p)
-        p_p[p_p < 0] = 0
-        cos_th_ = (g_pr * E_ - g_el) / (g_pr * p_)
-        T = np.sqrt(k ** 2. + p_ ** 2. - 2. * k * p_ * cos_th_)
-        T[T < 0] = 0.
-        D_ = (E_ - p_ * cos_th_)
-        D_ = np.where(np.isnan(D_), 0, D_)
-        D_[D_ < 0.] = 0.
-        Y = (2. / p_ ** 2.) * np.log((E_ * E_p + p_ * p_p + 1.) / k)
-        Y = np.where(np.isnan(Y), 0, Y)
-        Y[Y < 0] = 0.
-        y_plus = p_p ** (-1.) * np.log((E_p + p_p) / (E_p - p_p))
-        y_plus = np.where(np.isnan(y_plus), 0, y_plus)
-        y_plus[y_plus < 0.] = 0.
-        d_plus_T = np.log((T + p_p) / (T - p_p))
-        d_plus_T = np.where(np.isnan(d_plus_T), 0, d_plus_T)
-        d_plus_T[d_plus_T < 0.] = 0.
-        sin2 = (np.sin(np.arccos(cos_th_))) ** 2.
-        return 3. / (8. * np.pi * 137.) * sigmaT * p_p * p_ / k ** 3. * (
-            -4. * sin2 * (2. * E_ ** 2. + 1.) / (p_ ** 2. * D_ ** 4.)
-            + (5. * E_ ** 2. - 2. * E_ * E_p + 3.) / (p_ ** 2. * D_ ** 2.) + (p_ ** 2. - k ** 2.) / (T ** 2. * D_ ** 2.)
-            + 2. * E_p / (p_ ** 2. * D_)
-            + Y / (p_ * p_p) * (2. * E_ * sin2 * (3. * k + p_ ** 2. * E_p) / D_ ** 4.
-                                + (2. * E_ ** 2 * (E_ ** 2. + E_p ** 2.) - 7. * E_ ** 2. - 3. * E_ * E_p - E_p ** 2. + 1.) / D_ ** 2.
-                                + k * (E_ ** 2. - E_ * E_p - 1.) / D_)
-            - d_plus_T / (p_p * T) * (2. / D_ ** 2. - 3. * k / D_ - k * (p_ ** 2. - k ** 2.) / (T ** 2. * D_))
-            - 2. * y_plus / D_) / p_
+    # kap is a scalar per lattice point in the reference, and NumPy raises SCALARS to a power with libm's pow() but
+    # ARRAYS with its own SIMD loop (1 ulp apart on ~3 % of the lattice): take the scalar route for kap**2, kap**3.
+    kap_sq = np.array([v ** 2. for v in kap[:, 0]]).reshape(-1, 1)
+    kap_cu = np.array([v ** 3. for v in kap[:, 0]]).reshape(-1, 1)
+    E_pos = np.where(np.isnan(kap - E_el), 0., kap - E_el)              # positron energy, scrubbed
+    E_pos = np.where(E_pos < 0., 0., E_pos)
+    mom_el = np.sqrt(E_el ** 2 - 1.)
+    mom_el = np.where(mom_el < 0., 0., mom_el)
+    mom_pos = _nonneg(np.sqrt(E_pos ** 2. - 1.))
+    mu = (gam_p * E_el - gam_e) / (gam_p * mom_el)                      # cosine of the electron's polar angle
+    Tm = np.sqrt(kap_sq + mom_el ** 2. - 2. * kap * mom_el * mu)
+    Tm = np.where(Tm < 0., 0., Tm)
+    Dm = _nonneg(E_el - mom_el * mu)
+    Yl = _nonneg((2. / mom_el ** 2.) * np.log((E_el * E_pos + mom_el * mom_pos + 1.) / kap))
+    yp = _nonneg(mom_pos ** (-1.) * np.log((E_pos + mom_pos) / (E_pos - mom_pos)))
+    dT = _nonneg(np.log((Tm + mom_pos) / (Tm - mom_pos)))
+    sin2 = (np.sin(np.arccos(mu))) ** 2.
+    pref = 3. / (8. * np.pi * 137.) * sigmaT * mom_pos * mom_el / kap_cu
+    t1 = -4. * sin2 * (2. * E_el ** 2. + 1.) / (mom_el ** 2. * Dm ** 4.)
+    t2 = (5. * E_el ** 2. - 2. * E_el * E_pos + 3.) / (mom_el ** 2. * Dm ** 2.)
+    t3 = (mom_el ** 2. - kap_sq) / (Tm ** 2. * Dm ** 2.)
+    t4 = 2. * E_pos / (mom_el ** 2. * Dm)
+    t5 = Yl / (mom_el * mom_pos) * (2. * E_el * sin2 * (3. * kap + mom_el ** 2. * E_pos) / Dm ** 4.
+                                    + (2. * E_el ** 2 * (E_el ** 2. + E_pos ** 2.) - 7. * E_el ** 2. - 3. * E_el * E_pos
+                                       - E_pos ** 2. + 1.) / Dm ** 2.
+                                    + kap * (E_el ** 2. - E_el * E_pos - 1.) / Dm)
+    t6 = dT / (mom_pos * Tm) * (2. / Dm ** 2. - 3. * kap / Dm - kap * (mom_el ** 2. - kap_sq) / (Tm ** 2. * Dm))
+    t7 = 2. * yp / Dm
+    return pref * (t1 + t2 + t3 + t4 + t5 - t6 - t7) / mom_el
 
 
-def interp_cs_BH_int(g_pr, g_el, nu_int_min, nu_int_max):
+_BH_TCK_VERSION = 1
+
+
+def _bh_cache_file(key):
+    import hashlib
+    import scipy
+    d = os.environ.get("LHM_CACHE_DIR") or os.path.join(os.path.expanduser("~"), ".cache", "lehamoc_b200")
+    tag = hashlib.sha1(repr((key, scipy.__version__, np.__version__, _BH_TCK_VERSION)).encode()).hexdigest()[:20]
+    return os.path.join(d, f"bh_surfaces_{tag}.npz")
+
+
+def interp_cs_BH_int(g_pr, g_el, nu_int_min, nu_int_max, cache=True):
     """LeHaMoC_f.py:276-341: returns (tck_m, tck_p, max_m, max_p), the two smoothing-spline surfaces of
-    log10 int sigma_BH E dlnE over (log10 Ee_min, log10 Ee_max) for gamma_p < gamma_e and gamma_p > gamma_e."""
+    log10 int sigma_BH E dlnE over (log10 Ee_min, log10 Ee_max) for gamma_p < gamma_e and gamma_p > gamma_e.
+
+    The reference walks its 30 x 30 x 30 lattice in three Python loops (27 000 Simpson integrals over 50 electron
+    energies each, ~7 s); here the whole lattice is ONE array expression [27 000, 50] in the reference's loop order
+    (0.2 s), then SciPy's bisplrep exactly like the reference.  The result is persisted per (grid ends, frequency
+    range, SciPy / NumPy version) under ~/.cache/lehamoc_b200 (LHM_CACHE_DIR overrides; cache=False recomputes)."""
     from scipy import integrate, interpolate
     from .constants import h, m_el, c
-    if not hasattr(np, "trapz"):
-        np.trapz = np.trapezoid
+    key = tuple(float(v) for v in (g_pr[0], g_pr[-1], g_el[0], g_el[-1], nu_int_min, nu_int_max))
+    path = _bh_cache_file(key)
+    if cache and os.path.exists(path):
+        try:
+            z = np.load(path)
+            return ([z["m_tx"], z["m_ty"], z["m_c"], 3, 3], [z["p_tx"], z["p_ty"], z["p_c"], 3, 3],
+                    float(z["max_m"]), float(z["max_p"]))
+        except Exception:
+            pass
     gp_i = np.logspace(np.log10(g_pr[0]), np.log10(g_pr[-1]), 30)
     ge_i = np.logspace(np.log10(g_el[0]), np.log10(g_el[-1]), 30)
     x = np.logspace(np.log10(h * nu_int_min / (m_el * c ** 2.)), np.log10(h * nu_int_max / (m_el * c ** 2.)), 30)
-    lists = {"p": ([], [], []), "m": ([], [], [])}
     with np.errstate(all="ignore"):
-        for gp in gp_i:
-            for ge in ge_i:
-                if gp == ge:
-                    continue
-                key = "p" if gp > ge else "m"
-                E_min = (gp ** 2. + ge ** 2.) / (2. * gp * ge)
-                for xj in x:
-                    w = (2. * gp * xj)
-                    E_array = np.logspace(np.log10(E_min), np.log10(w - 1.))
-                    if E_array[0] < E_array[-1]:
-                        sBH = _cs_BH_diff(E_array, gp, ge, w)
-                        sBH = np.where(np.isnan(sBH), 0., sBH)
-                        res = integrate.simpson(sBH * E_array, x=np.log(E_array))
-                        lists[key][0].append(E_array[0]); lists[key][1].append(E_array[-1]); lists[key][2].append(res)
+        # lattice in the reference's loop order: proton, electron, photon
+        GP, GE, X = (a.reshape(-1, 1) for a in np.meshgrid(gp_i, ge_i, x, indexing="ij"))
+        kap = 2. * GP * X
+        E_lo = (GP ** 2. + GE ** 2.) / (2. * GP * GE)
+        E_el = np.logspace(np.log10(E_lo[:, 0]), np.log10(kap[:, 0] - 1.), 50, axis=-1)          # [27000, 50]
+        ok = (E_el[:, 0] < E_el[:, -1]) & (GP[:, 0] != GE[:, 0])
+        # filter BEFORE integrating: on a lattice that still holds its NaN rows SciPy's masked divisions change the
+        # memory order of the summands and np.sum then adds each row in another order than the reference's 1-D calls
+        E_el, GPk, GEk, kk = E_el[ok], GP[ok], GE[ok], kap[ok]
+        sBH = _bh_lattice_integrand(E_el, GPk, GEk, kk)
+        sBH = np.where(np.isnan(sBH), 0., sBH)
+        tot = integrate.simpson(sBH * E_el, x=np.log(E_el), axis=-1)
+    above = GPk[:, 0] > GEk[:, 0]
     out = {}
-    for key in ("m", "p"):
-        Emin, Emax, tot = (np.array(v) for v in lists[key])
+    for name, sel in (("m", ~above), ("p", above)):
         with np.errstate(all="ignore"):
-            z = np.where(np.isnan(np.log10(tot)), 0.1, np.log10(tot))
-        z[z == -np.inf] = 0.
-        keep = np.where(z < -15)[0]
-        xs, ys, zs = np.log10(Emin)[keep], np.log10(Emax)[keep], z[keep]
-        out[key] = (interpolate.bisplrep(list(xs), list(ys), list(zs), s=2), max(zs))
-    return out["m"][0], out["p"][0], out["m"][1], out["p"][1]
+            zz = np.where(np.isnan(np.log10(tot[sel])), 0.1, np.log10(tot[sel]))
+        zz[zz == -np.inf] = 0.
+        keep = np.where(zz < -15)[0]
+        xs, ys, zs = np.log10(E_el[sel, 0])[keep], np.log10(E_el[sel, -1])[keep], zz[keep]
+        out[name] = (interpolate.bisplrep(list(xs), list(ys), list(zs), s=2), max(zs))
+    res = (out["m"][0], out["p"][0], out["m"][1], out["p"][1])
+    if cache:
+        try:
+            os.makedirs(os.path.dirname(path), exist_ok=True)
+            tmp = path + f".{os.getpid()}.tmp.npz"
+            np.savez(tmp, m_tx=res[0][0], m_ty=res[0][1], m_c=res[0][2], p_tx=res[1][0], p_ty=res[1][1], p_c=res[1][2],
+                     max_m=res[2], max_p=res[3])
+            os.replace(tmp, path)
+        except OSError:
+            pass
+    return res
 
 
 class lhm_bh_surface(C.Structure):

@@ -122,11 +122,28 @@ def test_host_bh_surface_setup_is_the_references(gold):
     reference's spline surfaces bit for bit (same SciPy)."""
     from lehamoc_b200 import hadronic
     nu0, nu1 = gold["bh_nu_range"]
-    tm, tp, mm, mp_ = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu0, nu1)
+    tm, tp, mm, mp_ = hadronic.interp_cs_BH_int(np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu0, nu1,
+                                                cache=False)
     for ours, which in ((tm, "m"), (tp, "p")):
         for a, b in zip(ours[:3], bh_tck(gold, which)[:3]):
             np.testing.assert_array_equal(np.asarray(a), b)
     assert mm == float(gold["bh_max_m"]) and mp_ == float(gold["bh_max_p"])
+
+
+def test_host_bh_surface_disk_cache_round_trip(gold, tmp_path, monkeypatch):
+    """The persisted tck (one .npz per grid ends / frequency range / SciPy + NumPy version) reloads bit for bit."""
+    from lehamoc_b200 import hadronic
+    monkeypatch.setenv("LHM_CACHE_DIR", str(tmp_path))
+    nu0, nu1 = gold["bh_nu_range"]
+    args = (np.logspace(0., 8., 50), np.logspace(0., 10., 50), nu0, nu1)
+    first = hadronic.interp_cs_BH_int(*args)
+    assert len(list(tmp_path.glob("bh_surfaces_*.npz"))) == 1
+    again = hadronic.interp_cs_BH_int(*args)
+    for k in (0, 1):
+        for a, b in zip(first[k][:3], again[k][:3]):
+            np.testing.assert_array_equal(np.asarray(a), np.asarray(b))
+        assert first[k][3:] == again[k][3:] == [3, 3]
+    assert first[2:] == again[2:]
 
 
 @pytest.mark.gpu

@@ -105,7 +105,7 @@ def config3(W=148, reps=2, host_fit=True):
     t0 = time.perf_counter()
     if host_fit:
         LeHaMoC._bh_cache.clear()
-        surf = LeHaMoC.bh_surfaces(b.nu_tot[0, 0], b.nu_tot[0, -1])
+        surf = LeHaMoC.bh_surfaces(b.nu_tot[0, 0], b.nu_tot[0, -1], disk_cache=False)      # cold: nothing stored is used
     else:
         tck = lambda w: [g[f"bh_t{w}_tx"], g[f"bh_t{w}_ty"], g[f"bh_t{w}_c"], 3, 3]
         surf = (tck("m"), tck("p"), float(g["bh_max_m"]), float(g["bh_max_p"]))
@@ -139,8 +139,10 @@ def config3(W=148, reps=2, host_fit=True):
                       "what": "state-independent operators of Q_BH_sol / Qp_g_opt / dg_dt_pg tabulated at set-up (lhm_hadtab.cuh), "
                               "inside ms_per_batch; build_ms = -1: per-step evaluation in use"},
            "host_setup_s": setup_s,
-           "host_setup_what": ("interp_cs_BH_int (Bethe-Heitler spline surfaces: 27 000 Simpson integrals + two bisplrep "
-                               "fits), once per nu_tot range and process" if host_fit else "stored tck (no host fit)"),
+           "host_setup_what": ("interp_cs_BH_int computed cold, disk cache bypassed (Bethe-Heitler spline surfaces: 27 000 "
+                               "Simpson integrals as one array expression + two bisplrep fits); the product keeps the "
+                               "result per nu_tot range in the process and on disk" if host_fit
+                               else "stored tck (no host fit)"),
            "ms_per_model_incl_host_setup": (ms + 1e3 * setup_s) / W,
            "smem_bytes_per_cta": eng.smem_bytes(),
            "parity": {"vs": "tests/golden/lh_test4full.npz (2061 s of the unmodified LeHaMoC.py), all 5 steps, walker 0",
