@@ -8,8 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(HERE, "csrc", "lhm.cu")
 OUT = os.path.join(HERE, "liblhm.so")
-DEPS = [os.path.join(HERE, "csrc", f) for f in ("lhm.cu", "lhm_device.cuh", "lhm_setup.cuh", "lhm_step.cuh", "lhm_cor.cuh",
-                                                     "lhm_had.cuh", "lhm_lh.cuh", "lhm_pack.cuh")]
+DEPS = sorted(os.path.join(HERE, "csrc", f) for f in os.listdir(os.path.join(HERE, "csrc")) if f.endswith((".cu", ".cuh")))
 DEPS.append(os.path.join(os.path.dirname(HERE), "include", "lhm.h"))
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]
