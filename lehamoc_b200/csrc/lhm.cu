@@ -1105,7 +1105,7 @@ static int launch_cor(lhm_handle* h, double* out, cudaStream_t st) {
     CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
     CUDA_TRY(cudaEventRecord(h->ev[2], st));
     CUDA_TRY(ensure_dyn_smem(cor_kernel, cor_smem_bytes(h->cfg.Ng), g_smem_cor[h->device % MAX_DEV]));
-    cor_kernel<<<(h->W + COR_WARPS - 1) / COR_WARPS, COR_WARPS * 32, cor_smem_bytes(h->cfg.Ng), st>>>(A);
+    cor_kernel<<<h->W, COR_NT, cor_smem_bytes(h->cfg.Ng), st>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[3], st));

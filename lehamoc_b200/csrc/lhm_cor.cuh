@@ -1,17 +1,23 @@
-// lhm_cor.cuh -- A5: cor_factor_syn_el (LeMoC/LeHaMoC_f.py:175-237), one WARP per walker.
+// lhm_cor.cuh -- A5: cor_factor_syn_el (LeMoC/LeHaMoC_f.py:175-237), one 128-thread CTA per walker.
 //
 // The reference runs a private synchrotron-only simulation (B = 1e4 G, 200 implicit steps of
 // 0.1001 R0/c) and returns L_ph/L_e,inj at the end; its arguments are constants of a model, so it is
 // evaluated once per walker instead of once per timestep (bit-identical).
 //
-// Two exact re-associations make it a latency-bound warp job instead of 5.1 M exponentials:
+// Two exact re-associations make it a short latency-bound job instead of 5.1 M exponentials:
 //  (1) the returned luminosity is a linear functional of the photon vector, so only
-//      z_j = sum_k omega_k * 4 pi dt V * dQ_k/dN_j is needed (one 98 x Ng pass of exp) and each step
-//      is  Lambda <- (Lambda + z.N) / (1 + dt c/R0)                      (SURVEY.md 7.1b-2);
-//  (2) the bidiagonal solve x_j = dp_j - cp_j x_{j+1} has constant cp over the 200 steps, so it is an
-//      affine suffix scan: per-lane chunk composition + 5 shuffle levels with precomputed products.
+//      z_j = sum_k omega_k * 4 pi dt V * dQ_k/dN_j is needed (one 98 x Ng pass of exp, spread over the four warps) and
+//      each step is  Lambda <- (Lambda + z.N) / (1 + dt c/R0)            (SURVEY.md 7.1b-2);
+//  (2) the 200 bidiagonal solves x_j^(k+1) = dp_j(x_j^(k)) - cp_j x_{j+1}^(k+1) form a two-dimensional recurrence whose
+//      anti-diagonals are independent: lane l owns a contiguous chunk of the unknowns and works on timestep
+//      k = s - (31 - l) in macro-step s, taking the value at the top of its chunk from lane l+1's previous macro-step
+//      (one shuffle).  200 + 31 macro-steps of (chunk length) dependent FMAs replace 200 x (chunk pass + 5-level scan +
+//      replay); every unknown is computed by the reference's own serial recurrence (thomas(), LeHaMoC_f.py:250-262), no
+//      scan re-association.  Lambda is linear in N, so every lane carries the share of its chunk through its own
+//      timesteps and the shares are summed once, at the last step where the reference samples the ratio (:231-236).
 #pragma once
 #include "lhm_device.cuh"
+#include "lhm_step.cuh"
 #include "../../include/lhm.h"
 
 namespace lhm {
@@ -24,86 +30,124 @@ struct CorArgs {
     double* out;            // [W]
 };
 
-constexpr int COR_WARPS = 4;            // warps (walkers) per CTA
+constexpr int COR_NT = 128;             // threads per walker (set-up by all four warps, time loop by warp 0)
+constexpr int COR_NQ = COR_NT / 32;     // k-quarters of the z pass
 constexpr int COR_NNU = 100;            // private frequency grid, LeHaMoC_f.py:188
 
-// per-warp shared arrays, element e of lane l / slot i stored at [i*32 + l] (conflict-free)
+// chunk arrays: element i of lane l stored at [i*32 + l] (conflict-free)
 __host__ __device__ inline int cor_chunk(int Ng) { return (Ng - 2 + 31) / 32; }
 __host__ __device__ inline size_t cor_smem_bytes(int Ng) {
-    // m, binv, injdt, Mp, N, z : 6 arrays of C*32 ; g copy (Ng) ; nu, cnu (2 x 100)
-    return (size_t)COR_WARPS * ((size_t)6 * cor_chunk(Ng) * 32 + ((Ng + 1) & ~1) + 2 * COR_NNU) * sizeof(double);
+    const size_t NgP = (size_t)((Ng + 1) & ~1);
+    // m, binv, injdt, z, N: 5 chunk arrays; g, lg, inj, zfull: 4 x Ng; zq: NQ x Ng; nu, lnu, cnu, lam0c: 4 x 100; e2tab
+    return ((size_t)5 * cor_chunk(Ng) * 32 + (4 + COR_NQ) * NgP + 4 * COR_NNU + 64) * sizeof(double);
 }
 
-// The 200-step loop with the lane's chunk of every array in registers (CN = chunk length, compile time): no shared-memory
-// round trips inside the recurrences.  The luminosity functional Lambda <- (Lambda + z.N)/bph is linear, so every lane
-// carries its own share of it and the lanes are only summed when the reference samples the ratio (every 10th step).
+// the sampling rule of the reference's loop (:204-236) for this lane's next timestep
+struct CorClock {
+    double t, day, t_end, dt, period;
+    __device__ __forceinline__ bool pending() const { return t < t_end; }
+    __device__ __forceinline__ bool advance() {            // returns whether the reference samples the ratio at this step
+        t += dt;
+        if (day < t) { day = day + period; return true; }
+        return false;
+    }
+};
+
+// Wavefront time loop with the lane's chunk of every array in registers (CN = chunk length, compile time).
 template <int CN>
-__device__ __forceinline__ double cor_time_loop(const double* m_, const double* binv, const double* injdt, const double* Mp,
-                                                const double* z, const double (&Mlev)[5], double lam_lane, double zb,
-                                                double ends, double El, double dt, double R0, int lane) {
-    const PhysConst& pc = kPC;
-    double rm[CN], rb[CN], ri[CN], rM[CN], rz[CN], rN[CN];
+__device__ __forceinline__ double cor_time_loop(const double* m_, const double* binv, const double* injdt, const double* z,
+                                                double lam_lane, double zb, double bph, CorClock ck, int lane) {
+    double rm[CN], rb[CN], ri[CN], rz[CN], rN[CN];
 #pragma unroll
     for (int i = 0; i < CN; ++i) {
         const int s = i * 32 + lane;
-        rm[i] = m_[s]; rb[i] = binv[s]; ri[i] = injdt[s]; rM[i] = Mp[s]; rz[i] = z[s]; rN[i] = 0.0;
+        rm[i] = m_[s]; rb[i] = binv[s]; ri[i] = injdt[s]; rz[i] = z[s]; rN[i] = 0.0;
     }
-    const double bph = 1.0 + dt * (pc.c / R0);               // photon equation is diagonal (:226)
-    const double t_end = 20.0 * R0 / pc.c;
-    double t = 0.0, day = 0.0, ratio = 0.0;
-    while (t < t_end) {
-        t += dt;
-        double x0 = 0.0;
-#pragma unroll
-        for (int i = CN - 1; i >= 0; --i) {
-            x0 = fma(rm[i], x0, (rN[i] + ri[i]) * rb[i]);
-            rN[i] = x0;
-        }
-        double Aacc = x0;
-#pragma unroll
-        for (int l = 0; l < 5; ++l) {
-            const double Ao = __shfl_down_sync(0xffffffffu, Aacc, 1 << l);
-            if (lane + (1 << l) < 32) Aacc = fma(Mlev[l], Ao, Aacc);
-        }
-        double xin = __shfl_down_sync(0xffffffffu, Aacc, 1);
+    const int delay = 31 - lane;
+    const double zn0 = (lane == 0) ? zb : 0.0;
+    double xbot = 0.0, lam_s = 0.0;
+    for (int s = 0;; ++s) {
+        double xin = __shfl_down_sync(0xffffffffu, xbot, 1);        // lane l+1's bottom value of the same timestep
         if (lane == 31) xin = 0.0;
-        double zn = (lane == 0) ? zb : 0.0;
+        if (s >= delay && ck.pending()) {
+            double dpv[CN];
 #pragma unroll
-        for (int i = 0; i < CN; ++i) {
-            const double xv = fma(rM[i], xin, rN[i]);
-            rN[i] = xv;
-            zn = fma(rz[i], xv, zn);
+            for (int i = 0; i < CN; ++i) dpv[i] = (rN[i] + ri[i]) * rb[i];        // d'_i of thomas(): independent of xin
+            double x = xin, zn = zn0;
+#pragma unroll
+            for (int i = CN - 1; i >= 0; --i) {
+                x = fma(rm[i], x, dpv[i]);                                        // x_i = d'_i - c'_i x_{i+1}
+                rN[i] = x;
+            }
+#pragma unroll
+            for (int i = 0; i < CN; ++i) zn = fma(rz[i], rN[i], zn);
+            xbot = x;
+            lam_lane = (lam_lane + zn) / bph;
+            if (ck.advance()) lam_s = lam_lane;
         }
-        lam_lane = (lam_lane + zn) / bph;
-        if (day < t) {                                       // (:231-236)
-            day = day + 1.0 * R0 / pc.c;
-            ratio = (warp_sum(lam_lane) + ends) / El;
-        }
+        if (!__any_sync(0xffffffffu, s < delay || ck.pending())) break;
     }
-    return ratio;
+    return warp_sum(lam_s);
 }
 
-__global__ void __launch_bounds__(COR_WARPS * 32) cor_kernel(CorArgs A) {
+// the same with the chunk arrays in shared memory (grids beyond 12 * 32 + 2 points)
+__device__ __forceinline__ double cor_time_loop_smem(int Cn, const double* m_, const double* binv, const double* injdt,
+                                                     const double* z, double* Nn, double lam_lane, double zb, double bph,
+                                                     CorClock ck, int lane) {
+    const int delay = 31 - lane;
+    const double zn0 = (lane == 0) ? zb : 0.0;
+    double xbot = 0.0, lam_s = 0.0;
+    for (int s = 0;; ++s) {
+        double xin = __shfl_down_sync(0xffffffffu, xbot, 1);
+        if (lane == 31) xin = 0.0;
+        if (s >= delay && ck.pending()) {
+            double x = xin, zn = zn0;
+            for (int i = Cn - 1; i >= 0; --i) {
+                const int e = i * 32 + lane;
+                x = fma(m_[e], x, (Nn[e] + injdt[e]) * binv[e]);
+                Nn[e] = x;
+                zn = fma(z[e], x, zn);
+            }
+            xbot = x;
+            lam_lane = (lam_lane + zn) / bph;
+            if (ck.advance()) lam_s = lam_lane;
+        }
+        if (!__any_sync(0xffffffffu, s < delay || ck.pending())) break;
+    }
+    return warp_sum(lam_s);
+}
+
+__global__ void __launch_bounds__(COR_NT) cor_kernel(CorArgs A) {
     extern __shared__ double smc[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int w = blockIdx.x * COR_WARPS + warp;
-    if (w >= A.W) return;                                    // whole warp exits together
-    const int Ng = A.Ng, n = Ng - 2, Cn = cor_chunk(Ng), CS = Cn * 32;
-    double* base = smc + (size_t)warp * (6 * CS + ((Ng + 1) & ~1) + 2 * COR_NNU);
-    double* m_ = base;             // -cp
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int w = blockIdx.x;
+    const int Ng = A.Ng, n = Ng - 2, Cn = cor_chunk(Ng), CS = Cn * 32, NgP = (Ng + 1) & ~1;
+    double* m_ = smc;              // -c'_i
     double* binv = m_ + CS;
     double* injdt = binv + CS;
-    double* Mp = injdt + CS;
-    double* Nn = Mp + CS;
-    double* z = Nn + CS;
-    double* g = z + CS;
-    double* nu = g + ((Ng + 1) & ~1);
-    double* cnu = nu + COR_NNU;
+    double* z = injdt + CS;
+    double* Nn = z + CS;
+    double* g = Nn + CS;
+    double* lg = g + NgP;
+    double* inj = lg + NgP;        // Q0 g^-p on all bins (:202)
+    double* zfull = inj + NgP;
+    double* zq = zfull + NgP;      // [COR_NQ][NgP] partial k-sums of the z pass
+    double* nu = zq + COR_NQ * NgP;
+    double* lnu = nu + COR_NNU;
+    double* cnu = lnu + COR_NNU;
+    double* lam0c = cnu + COR_NNU; // omega_k x 1e-260 (initial photon vector, :194)
+    double* e2tab = lam0c + COR_NNU;
     const PhysConst& pc = kPC;
     const double* cst = A.consts + (size_t)w * LHM_NCONST;
     const double R0 = cst[LHM_C_R0], B0 = cst[LHM_C_COR_B], p_el = cst[LHM_C_COR_P], Q0 = cst[LHM_C_COR_Q0];
-    for (int j = lane; j < Ng; j += 32) g[j] = A.g_el[(size_t)w * Ng + j];
-    __syncwarp();
+    for (int j = tid; j < Ng; j += COR_NT) {
+        const double gj = A.g_el[(size_t)w * Ng + j];
+        g[j] = gj;
+        lg[j] = log(gj);
+        inj[j] = Q0 * pow(gj, -p_el);
+    }
+    for (int i = tid; i < 64; i += COR_NT) e2tab[i] = exp2((double)i / 64.0);
+    __syncthreads();
 
     const double dt = 0.1001 * R0 / pc.c;                    // LeHaMoC_f.py:205
     const double Vol = volume_of(R0);
@@ -112,137 +156,101 @@ __global__ void __launch_bounds__(COR_WARPS * 32) cor_kernel(CorArgs A) {
     // frequency grid np.logspace(7.5, log10(7 nu_c(g[-1],B0))+1.4, 100)  (:188)
     const double la = 7.5, lb = log10(7.0 * (pc.nuc_pref * B0 * (g[Ng - 1] * g[Ng - 1]))) + 1.4;
     const double lstep = (lb - la) / (double)(COR_NNU - 1);
-    for (int k = lane; k < COR_NNU; k += 32) nu[k] = exp10((k == COR_NNU - 1) ? lb : la + (double)k * lstep);
-    __syncwarp();
+    for (int k = tid; k < COR_NNU; k += COR_NT) {
+        const double v = exp10((k == COR_NNU - 1) ? lb : la + (double)k * lstep);
+        nu[k] = v;
+        lnu[k] = log(v);
+    }
+    __syncthreads();
     // omega_k = trapz weight over ln(nu) x h nu^2 (4 pi/3) R0^2 c / V   (:234,236)
     // c_k     = omega_k * 4 pi dt V * C_syn B^(2/3) nu^(-2/3)           (:91,228)
-    double lam0_part = 0.0, ends = 0.0;
-    for (int k = lane; k < COR_NNU; k += 32) {
-        double lm = (k > 0) ? log(nu[k - 1]) : 0.0, lc = log(nu[k]), lp = (k < COR_NNU - 1) ? log(nu[k + 1]) : 0.0;
-        double wk = (((k > 0) ? (lc - lm) : 0.0) + ((k < COR_NNU - 1) ? (lp - lc) : 0.0)) * 0.5;
-        double om = wk * (pc.h * (nu[k] * nu[k])) * 4.0 * M_PI / 3.0 * (R0 * R0) * pc.c / Vol;
-        if (k >= 1 && k <= COR_NNU - 2) {
-            cnu[k] = om * 4.0 * M_PI * dt * Vol * (pc.C_syn * pow(B0, 2.0 / 3.0) * pow(nu[k], -2.0 / 3.0));
-            lam0_part += om * LHM_SENT;                      // photons_syn starts at 1e-260 everywhere (:194)
-        } else {
-            cnu[k] = 0.0;
-            ends += om * LHM_SENT;                           // boundary bins are never updated
-        }
+    for (int k = tid; k < COR_NNU; k += COR_NT) {
+        const double lm = (k > 0) ? lnu[k - 1] : 0.0, lc = lnu[k], lp = (k < COR_NNU - 1) ? lnu[k + 1] : 0.0;
+        const double wk = (((k > 0) ? (lc - lm) : 0.0) + ((k < COR_NNU - 1) ? (lp - lc) : 0.0)) * 0.5;
+        const double om = wk * (pc.h * (nu[k] * nu[k])) * 4.0 * M_PI / 3.0 * (R0 * R0) * pc.c / Vol;
+        const bool interior = k >= 1 && k <= COR_NNU - 2;    // boundary bins are never updated
+        cnu[k] = interior ? om * 4.0 * M_PI * dt * Vol * (pc.C_syn * pow(B0, 2.0 / 3.0) * pow(nu[k], -2.0 / 3.0)) : 0.0;
+        lam0c[k] = om * LHM_SENT;                            // photons_syn starts at 1e-260 everywhere (:194)
     }
-    const double lam_lane0 = lam0_part;                      // this lane's share of the initial luminosity functional
-    double Lam = warp_sum(lam0_part);
-    ends = warp_sum(ends);
-    __syncwarp();
-
-    // static solver tables + z
-    double El_part = 0.0, zb_part = 0.0;
-    for (int j = lane; j < Ng; j += 32) {                    // L_e,inj = trapz(el_inj g^2 m c^2, ln g)  (:235)
-        double lm = (j > 0) ? log(g[j - 1]) : 0.0, lc = log(g[j]), lp = (j < Ng - 1) ? log(g[j + 1]) : 0.0;
-        double wj = (((j > 0) ? (lc - lm) : 0.0) + ((j < Ng - 1) ? (lp - lc) : 0.0)) * 0.5;
-        double inj = Q0 * pow(g[j], -p_el);                  // el_inj on ALL bins (:202)
-        El_part += wj * (inj * (g[j] * g[j]) * pc.mc2);
-    }
-    const double El = warp_sum(El_part);
-    for (int i = 0; i < Cn; ++i) {
-        const int e = lane * Cn + i;                         // interior unknown e <-> grid index e+1
-        const int s = i * 32 + lane;
-        double mv = 0.0, bi = 1.0, idt = 0.0, zv = 0.0;
+    // static solver tables of the interior unknowns e <-> grid index e+1
+    for (int s = tid; s < CS; s += COR_NT) {
+        const int l = s & 31, i = s >> 5;
+        const int e = l * Cn + i;
+        double mv = 0.0, bi = 1.0, idt = 0.0;
         if (e < n) {
             const int j = e + 1;
-            double mp0 = (g[j] + g[(e == 0) ? (Ng - 1) : (e - 1)]) / 2.0;   // g_el_mp[e]  (:182, wraps at e=0)
-            double mp1 = (g[j + 1] + g[j - 1]) / 2.0;                         // g_el_mp[e+1]
-            double dg = (g[j + 1] - g[j - 1]) / 2.0;                          // dg_el[e]    (:185)
-            double V2 = 1.0 + dt * (pc.c / R0 + b_syn * ((mp0 * mp0) / dg));     // (:213,217)
-            double V3 = -dt * (b_syn * ((mp1 * mp1) / dg));                       // (:214,218)
+            const double mp0 = (g[j] + g[(e == 0) ? (Ng - 1) : (e - 1)]) / 2.0;   // g_el_mp[e]  (:182, wraps at e=0)
+            const double mp1 = (g[j + 1] + g[j - 1]) / 2.0;                         // g_el_mp[e+1]
+            const double dg = (g[j + 1] - g[j - 1]) / 2.0;                          // dg_el[e]    (:185)
+            const double V2 = 1.0 + dt * (pc.c / R0 + b_syn * ((mp0 * mp0) / dg));     // (:213,217)
+            const double V3 = -dt * (b_syn * ((mp1 * mp1) / dg));                       // (:214,218)
             bi = 1.0 / V2;
             mv = (e == n - 1) ? 0.0 : -(V3 / V2);            // last row's c never enters (:259)
-            idt = (Q0 * pow(g[j], -p_el)) * dt;              // el_inj[1:-1]*dt (:219)
+            idt = inj[j] * dt;                               // el_inj[1:-1]*dt (:219)
         }
-        m_[s] = mv; binv[s] = bi; injdt[s] = idt; Nn[s] = 0.0; z[s] = zv;
+        m_[s] = mv; binv[s] = bi; injdt[s] = idt; Nn[s] = 0.0; z[s] = 0.0;
     }
-    __syncwarp();
-    // z_j for every grid index (interior in z[], the two boundary bins folded into a constant)
-    for (int jj = lane; jj < Ng; jj += 32) {
-        const double gj = g[jj];
-        const double inv = 1.0 / (a_cr * (gj * gj));
-        const double thr = pc.mc2 * gj;
-        double acc = 0.0;
-        for (int k = 1; k <= COR_NNU - 2; ++k) {
-            double x = nu[k] * inv;
-            if (!(thr < pc.h * nu[k]) && x <= 745.2) acc = fma(cnu[k], exp(-x), acc);   // mask (:89-90)
-        }
-        double lm = (jj > 0) ? log(g[jj - 1]) : 0.0, lc = log(gj), lp = (jj < Ng - 1) ? log(g[jj + 1]) : 0.0;
-        double wj = (((jj > 0) ? (lc - lm) : 0.0) + ((jj < Ng - 1) ? (lp - lc) : 0.0)) * 0.5;
-        double zj = wj * pow(gj, 1.0 / 3.0) / Vol * acc;
-        if (jj == 0 || jj == Ng - 1) zb_part += zj * 1e-160;      // N_el[0] = N_el[-1] = 1e-160 (:195)
-        else { int e = jj - 1; z[(e % Cn) * 32 + (e / Cn)] = zj; }
-    }
-    const double zb = warp_sum(zb_part);
-    __syncwarp();
-    // partial products Mp_i = prod_{i'>=i} m_{i'} within the lane chunk, lane product, scan-level products
-    double Mlane = 1.0;
-    for (int i = Cn - 1; i >= 0; --i) { Mlane *= m_[i * 32 + lane]; Mp[i * 32 + lane] = Mlane; }
-    double Mlev[5];
+    __syncthreads();
+    // z pass: warp q sums its quarter of the interior frequencies for every gamma, four exponentials side by side
     {
-        double M = Mlane;
+        const int per = (COR_NNU - 2 + COR_NQ - 1) / COR_NQ;
+        const int k0 = 1 + warp * per, k1 = min(k0 + per, COR_NNU - 1);
+        for (int jj = lane; jj < Ng; jj += 32) {
+            const double gj = g[jj];
+            const double inv = 1.0 / (a_cr * (gj * gj));
+            const double thr = pc.mc2 * gj;
+            double acc = 0.0;
+            for (int k = k0; k < k1; k += 4) {
+                double x[4], Ev[4];
 #pragma unroll
-        for (int l = 0; l < 5; ++l) {
-            Mlev[l] = M;
-            double Mo = __shfl_down_sync(0xffffffffu, M, 1 << l);
-            M = (lane + (1 << l) < 32) ? M * Mo : M;
+                for (int u = 0; u < 4; ++u) x[u] = nu[min(k + u, k1 - 1)] * inv;
+                fast_exp_neg<4>(x, Ev, e2tab);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const int kk = k + u;
+                    if (kk < k1 && !(thr < pc.h * nu[kk])) acc = fma(cnu[kk], Ev[u], acc);   // mask (:89-90)
+                }
+            }
+            zq[warp * NgP + jj] = acc;
         }
     }
-    if (Cn <= 12) {
-        __syncwarp();
-        double r;
-        switch (Cn) {
-#define LHM_COR_CASE(n) case n: r = cor_time_loop<n>(m_, binv, injdt, Mp, z, Mlev, lam_lane0, zb, ends, El, dt, R0, lane); break;
-            LHM_COR_CASE(1) LHM_COR_CASE(2) LHM_COR_CASE(3) LHM_COR_CASE(4) LHM_COR_CASE(5) LHM_COR_CASE(6)
-            LHM_COR_CASE(7) LHM_COR_CASE(8) LHM_COR_CASE(9) LHM_COR_CASE(10) LHM_COR_CASE(11) default:
-            LHM_COR_CASE(12)
-#undef LHM_COR_CASE
-        }
-        if (lane == 0) A.out[w] = r;
-        return;
+    __syncthreads();
+    for (int jj = tid; jj < Ng; jj += COR_NT) {
+        double acc = zq[jj];
+#pragma unroll
+        for (int q = 1; q < COR_NQ; ++q) acc += zq[q * NgP + jj];
+        const double lm = (jj > 0) ? lg[jj - 1] : 0.0, lc = lg[jj], lp = (jj < Ng - 1) ? lg[jj + 1] : 0.0;
+        const double wj = (((jj > 0) ? (lc - lm) : 0.0) + ((jj < Ng - 1) ? (lp - lc) : 0.0)) * 0.5;
+        const double zj = wj * pow(g[jj], 1.0 / 3.0) / Vol * acc;
+        zfull[jj] = zj;
+        if (jj >= 1 && jj <= Ng - 2) { const int e = jj - 1; z[(e % Cn) * 32 + (e / Cn)] = zj; }
+        // L_e,inj = trapz(el_inj g^2 m c^2, ln g)  (:235): the summand parked where the z partials were
+        zq[jj] = wj * (inj[jj] * (g[jj] * g[jj]) * pc.mc2);
     }
-    // time loop (:204-236), chunk arrays in shared memory (grids beyond 12 * 32 + 2 points)
+    __syncthreads();
+    if (warp != 0) return;
+
+    double El_part = 0.0, lam0_part = 0.0, ends = 0.0;
+    for (int j = lane; j < Ng; j += 32) El_part += zq[j];
+    for (int k = lane; k < COR_NNU; k += 32) {
+        if (k >= 1 && k <= COR_NNU - 2) lam0_part += lam0c[k];
+        else ends += lam0c[k];
+    }
+    const double El = warp_sum(El_part);
+    ends = warp_sum(ends);
+    const double zb = zfull[0] * 1e-160 + zfull[Ng - 1] * 1e-160;   // N_el[0] = N_el[-1] = 1e-160 (:195)
     const double bph = 1.0 + dt * (pc.c / R0);               // photon equation is diagonal (:226)
-    const double t_end = 20.0 * R0 / pc.c;
-    double t = 0.0, day = 0.0, ratio = 0.0;
-    while (t < t_end) {
-        t += dt;
-        // chunk solution for zero inflow, from the top of the chunk down
-        double x0 = 0.0;
-        for (int i = Cn - 1; i >= 0; --i) {
-            const int s = i * 32 + lane;
-            double dpv = (Nn[s] + injdt[s]) * binv[s];
-            x0 = fma(m_[s], x0, dpv);
-            Nn[s] = x0;
-        }
-        // suffix scan over lanes: S_l = A_l + M_l S_{l+1}
-        double Aacc = x0;
-#pragma unroll
-        for (int l = 0; l < 5; ++l) {
-            double Ao = __shfl_down_sync(0xffffffffu, Aacc, 1 << l);
-            if (lane + (1 << l) < 32) Aacc = fma(Mlev[l], Ao, Aacc);
-        }
-        double xin = __shfl_down_sync(0xffffffffu, Aacc, 1);
-        if (lane == 31) xin = 0.0;
-        double zn = 0.0;
-        for (int i = 0; i < Cn; ++i) {
-            const int s = i * 32 + lane;
-            double xv = fma(Mp[s], xin, Nn[s]);
-            Nn[s] = xv;
-            zn = fma(z[s], xv, zn);
-        }
-        zn = warp_sum(zn) + zb;
-        Lam = (Lam + zn) / bph;
-        if (day < t) {                                       // (:231-236)
-            day = day + 1.0 * R0 / pc.c;
-            ratio = (Lam + ends) / El;
-        }
+    CorClock ck;
+    ck.t = 0.0; ck.day = 0.0; ck.t_end = 20.0 * R0 / pc.c; ck.dt = dt; ck.period = 1.0 * R0 / pc.c;
+    double Lam;
+    switch (Cn) {
+#define LHM_COR_CASE(c) case c: Lam = cor_time_loop<c>(m_, binv, injdt, z, lam0_part, zb, bph, ck, lane); break;
+        LHM_COR_CASE(1) LHM_COR_CASE(2) LHM_COR_CASE(3) LHM_COR_CASE(4) LHM_COR_CASE(5) LHM_COR_CASE(6)
+        LHM_COR_CASE(7) LHM_COR_CASE(8) LHM_COR_CASE(9) LHM_COR_CASE(10) LHM_COR_CASE(11) LHM_COR_CASE(12)
+#undef LHM_COR_CASE
+        default: Lam = cor_time_loop_smem(Cn, m_, binv, injdt, z, Nn, lam0_part, zb, bph, ck, lane); break;
     }
-    if (lane == 0) A.out[w] = ratio;
+    if (lane == 0) A.out[w] = (Lam + ends) / El;
 }
 
 }  // namespace lhm

@@ -9,19 +9,22 @@ import lehamoc_oracle_lh as olh
 from util import GOLD, load_golden
 
 
-def log_close(got, ref_log, what, tol=4.3e-9, floor_decades=200., tol_floor=1e-6):
+def log_close(got, ref_log, what, tol=4.3e-9, floor_decades=200., tol_floor=1e-6, zero_floor=-300.0):
     """`got` linear, `ref_log` the log10 values the reference wrote; same rule as util.assert_spectra_close."""
     with np.errstate(divide="ignore", invalid="ignore"):
         lg = np.log10(np.asarray(got, dtype=np.float64))
     ref_log = np.asarray(ref_log, dtype=np.float64)
     assert lg.shape == ref_log.shape, what
-    # exact zeros must be zeros -- except at the bottom of the double range, where products of 1e-260 sentinels
-    # underflow: there (below 1e-280, i.e. a 1e-260 sentinel times a further small factor, against physical values
-    # above 1e-100) "zero" and "denormal junk" are the same statement
+    # exact zeros of the reference must be exact zeros here.  The one admitted exception is the denormal range: a product
+    # of 1e-260 sentinels that underflows to 0 in one evaluation order and to a denormal (< 2.2e-308) in another is the
+    # same statement, so a reference zero may be met by a value below 1e-300 and vice versa -- nothing larger.  Callers
+    # that compare a quantity whose reference value underflows through an INTERMEDIATE (named at the call) pass a higher
+    # zero_floor
     tiny = -280.0
+    denorm = zero_floor
     ninf = np.isneginf(ref_log)
-    assert np.all(lg[ninf] < tiny), f"{what}: zeros of the reference are not (near-)zeros here"
-    assert np.all(ref_log[np.isneginf(lg)] < tiny), f"{what}: zeros where the reference has values"
+    assert np.all(lg[ninf] < denorm), f"{what}: zeros of the reference are not zeros (or denormals) here"
+    assert np.all(ref_log[np.isneginf(lg)] < denorm), f"{what}: zeros where the reference has values"
     # NaNs flow through like in the reference (e.g. the pp low-energy matching on a too short energy range)
     assert np.array_equal(np.isnan(lg), np.isnan(ref_log)), f"{what}: NaN pattern differs from the reference's"
     ok = ~ninf & ~np.isnan(ref_log) & ~np.isneginf(lg)
@@ -328,7 +331,9 @@ def test_gpu_lehamoc_pp_run(name):
     log_close(N[0], z["n_e"], f"{name} n_e")
     log_close(sed[0], z["nuLnu"], f"{name} nuLnu")
     log_close(Npr[0], z["n_p"], f"{name} n_p")
-    log_close(Nnu[0], z["N_nu"], f"{name} N_nu")
+    # the last neutrino bins of lh_pp_pg: an intermediate of the reference underflows to 0.0 where the device's regrouped
+    # evaluation keeps 1e-290 ... 1e-299 (313 decades under the 1e+23 peak): admitted for this comparison only
+    log_close(Nnu[0], z["N_nu"], f"{name} N_nu", zero_floor=-280.0)
     assert np.any(Nnu[0, -1] > 0)
 
 
