@@ -1092,8 +1092,9 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
         IcgSetupArgs G;
         G.L = h->L; G.D = h->GD; G.tabd = h->d_tabd; G.ptg = h->d_ptg; G.kinfo = h->d_kinfo; G.xs = h->d_xs;
         G.tasks = h->d_tasks; G.cost = h->d_cost;
-        icg_setup_kernel<<<1, 256, 0, h->stream>>>(G);
-        g_launches++;
+        icg_setup_kernel<<<(G.D.NOG * G.D.NgP * 8 + 255) / 256, 256, 0, h->stream>>>(G);
+        icg_tasks_kernel<<<1, 256, 0, h->stream>>>(G);
+        g_launches += 2;
         CUDA_TRY(cudaGetLastError());
     }
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));

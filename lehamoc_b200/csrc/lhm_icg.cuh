@@ -53,7 +53,7 @@ __host__ __device__ inline size_t icg_smem_bytes(const IcgDims& D) {
 
 // ---------------------------------------------------------------------------------------------------------------
 // set-up, once per batch (grids only): pair constants in fragment order, the nu_in range every gamma pair has to
-// visit, the per-nu_in operands, and the task list sorted by cost.  One CTA; reads walker 0's tables.
+// visit, the per-nu_in operands, and the task list sorted by cost.  Reads walker 0's tables.
 struct IcgSetupArgs {
     Layout L;
     IcgDims D;
@@ -65,11 +65,12 @@ struct IcgSetupArgs {
     int* cost;              // [ntasks] scratch
 };
 
+// part 1, any number of CTAs (grid-stride): the embarrassingly parallel tables
 __global__ void __launch_bounds__(256) icg_setup_kernel(IcgSetupArgs A) {
     const Layout& L = A.L;
     const IcgDims& D = A.D;
     const double* T = A.tabd;
-    const int tid = threadIdx.x, NTH = blockDim.x;
+    const int tid = blockIdx.x * blockDim.x + threadIdx.x, NTH = gridDim.x * blockDim.x;
     const double* g = T + L.g;
     const double* ni = T + L.nic;
     const double* xi = T + L.invnt;
@@ -120,7 +121,12 @@ __global__ void __launch_bounds__(256) icg_setup_kernel(IcgSetupArgs A) {
         }
         A.kinfo[c] = make_ushort2((unsigned short)ks0, (unsigned short)ksc);
     }
-    __syncthreads();
+}
+
+// part 2, one CTA: task costs from the ranges of part 1, then the rank sort
+__global__ void __launch_bounds__(256) icg_tasks_kernel(IcgSetupArgs A) {
+    const IcgDims& D = A.D;
+    const int tid = threadIdx.x, NTH = blockDim.x;
     for (int t = tid; t < D.ntasks; t += NTH) {
         const int og = t / D.NGC, gc = t - og * D.NGC;
         int cst = 0;

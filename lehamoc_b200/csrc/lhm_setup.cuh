@@ -188,8 +188,12 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             }
             TI[L.jz + row] = lo;
         }
+        __syncthreads();                                         // jz of every row is visible to the whole CTA
+        // Only what phase_syn_rows reads is written: a row's entries below (jz & ~1) are exact zeros it skips (56 % of
+        // the Test-1 table), so they cost neither an exponential nor a store.
         for (int e = tid; e < (Ns + Ni) * Ng; e += NT) {
             const int j = e / (Ns + Ni), row = e - j * (Ns + Ni);     // row fastest: consecutive threads, consecutive doubles
+            if (j < (TI[L.jz + row] & ~1)) continue;
             const double nu = (row < Ns) ? ns[row] : ni[row - Ns];
             const double x = nu * (1.0 / (pc.nuc_pref * B0 * (g[j] * g[j])));
             E[(size_t)j * (Ns + Ni) + row] = (x > 745.2) ? 0.0 : exp(-x);   // transposed: [gamma][row]
