@@ -341,7 +341,7 @@ __global__ void __launch_bounds__(NT, 2) icg_unit_kernel(GUnitArgs U) {
     Ctx C;
     load_ctx(C, U.L, U.F, U.consts, U.tabd, U.tabi, nullptr, nullptr, 0, w);
     const Layout& L = C.L;
-    ic_prepare<NT>(C, S);
+    g_prepare<NT>(C, S);                                 // a path-G handle builds no tile schedule for ic_prepare to load
     C.V = 1.0;
     for (int j = tid; j < L.Ng; j += NT) S.N[j] = U.n_e[(size_t)w * L.Ng + j];
     __syncthreads();
@@ -1065,6 +1065,7 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
     A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
+    A.skip_ic_schedule = h->pathG ? 1 : 0;
     A.g_pr = nullptr; A.pr_inj = nullptr;
     if (h->cfg.driver >= 1) {
         if (!h->g_pr || !h->pr_inj) return LHM_ERR_STATE;
@@ -1450,6 +1451,7 @@ int lhm_ic_emissivity_batch(lhm_handle* h, const double* n_e, const double* n, d
         CUDA_TRY(cudaGetLastError());
         return LHM_OK;
     }
+    if (h && h->pathG && ic_path == LHM_IC_PATH_R) return LHM_ERR_STATE;    // no tile schedule on a path-G handle
     return launch_unit(h, U_IC, n_e, n, nullptr, Q, nullptr, nullptr, ic_path);
 }
 int lhm_gg_batch(lhm_handle* h, const double* n, const double* photons_IC_dens, double* a_gg, double* Q_ee) {

@@ -54,6 +54,7 @@ struct Layout {
     int ags_a, ags_d, ags_c, ags_r2;                // Ns: a_gg resample grid on nu_syn (LeHaMoC.py:415)
     int agt_a, agt_d, agt_c, agt_r2;                // Nt: a_gg resample grid on nu_tot (LeHaMoC.py:416)
     int uv_d;                                       // Ng: step (log10) of U_ph_f's 50-point resample (LeHaMoC_f.py:177)
+    int inuc0;                                      // Ng: 1/nu_c(gamma, B0), set-up scratch of the exponential cache
     int n_doubles;
     // int tables
     int ps_j, pi_j;                 // Nt
@@ -96,6 +97,7 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP, int Np = 0) {
     L.ags_a = take(nsl); L.ags_d = take(nsl); L.ags_c = take(nsl); L.ags_r2 = take(nsl);
     L.agt_a = take(ntl); L.agt_d = take(ntl); L.agt_c = take(ntl); L.agt_r2 = take(ntl);
     L.uv_d = take(ngl);
+    L.inuc0 = take(Ng);
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);

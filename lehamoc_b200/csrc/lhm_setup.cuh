@@ -25,6 +25,7 @@ struct SetupArgs {
     int* tabi;              // [W, L.n_ints]
     double2* ptab;          // IC pair table [W or 1, ic_maxT*IC_PT*2*32] or null
     int ptab_shared;        // 1: every walker has the same g_el / nu_ic / nu_tot, one table (walker 0 builds it)
+    int skip_ic_schedule;   // 1: the handle runs IC path G, nothing reads the per-walker tile schedule of paths R / S
     const double* g_pr;     // [W, Np] or null: proton grid / injection of the LeHaMoC.py driver
     const double* pr_inj;   // [W, Np]
 };
@@ -188,15 +189,38 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
             }
             TI[L.jz + row] = lo;
         }
+        // 1/nu_c(gamma, B0) once per gamma (the expression of phase_vectors), 2^(i/64) for the staged exponential
+        __shared__ double e2tab_s[64];
+        double* inuc = T + L.inuc0;
+        for (int j = tid; j < Ng; j += NT) inuc[j] = 1.0 / (pc.nuc_pref * B0 * (g[j] * g[j]));
+        for (int i = tid; i < 64; i += NT) e2tab_s[i] = exp2((double)i / 64.0);
         __syncthreads();                                         // jz of every row is visible to the whole CTA
         // Only what phase_syn_rows reads is written: a row's entries below (jz & ~1) are exact zeros it skips (56 % of
-        // the Test-1 table), so they cost neither an exponential nor a store.
-        for (int e = tid; e < (Ns + Ni) * Ng; e += NT) {
-            const int j = e / (Ns + Ni), row = e - j * (Ns + Ni);     // row fastest: consecutive threads, consecutive doubles
-            if (j < (TI[L.jz + row] & ~1)) continue;
-            const double nu = (row < Ns) ? ns[row] : ni[row - Ns];
-            const double x = nu * (1.0 / (pc.nuc_pref * B0 * (g[j] * g[j])));
-            E[(size_t)j * (Ns + Ni) + row] = (x > 745.2) ? 0.0 : exp(-x);   // transposed: [gamma][row]
+        // the Test-1 table), so they cost neither an exponential nor a store.  Four elements per thread and round, so
+        // that the four dependency chains of fast_exp_neg interleave; (j, row) advance without a division.
+        const int NR = Ns + Ni;
+        const int total = NR * Ng;
+        int jq[4], rq[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) { const int e = tid + u * NT; jq[u] = e / NR; rq[u] = e - jq[u] * NR; }
+        const int dj = (4 * NT) / NR, dr = 4 * NT - dj * NR;
+        for (int e0 = tid; e0 < total; e0 += 4 * NT) {
+            double x[4], Ev[4];
+            bool on[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int j = jq[u], row = rq[u];
+                on[u] = (e0 + u * NT < total) && j >= (TI[L.jz + min(row, NR - 1)] & ~1);
+                const double nu = (row < Ns) ? ns[row] : ni[min(row - Ns, Ni - 1)];
+                x[u] = on[u] ? nu * inuc[min(j, Ng - 1)] : 0.0;
+            }
+            fast_exp_neg<4>(x, Ev, e2tab_s);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                if (on[u]) E[(size_t)jq[u] * NR + rq[u]] = Ev[u];   // transposed: [gamma][row]; x > 745.2 gives exactly 0
+                jq[u] += dj; rq[u] += dr;
+                if (rq[u] >= NR) { rq[u] -= NR; ++jq[u]; }
+            }
         }
     }
     // ---- IC tile schedule (LeHaMoC_f.py:113-124; see phase_ic_R) ----------------------------------------
@@ -208,7 +232,10 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
     // the index i1 from which no pair clamps any more, and the tile costs (Ntar - i0) inner iterations.  Tiles are
     // dealt to the warps as contiguous, cost-balanced ranges -- a static schedule, so the summation order (and the
     // result bits) do not depend on timing.
-    {
+    if (A.skip_ic_schedule) {                             // path G contracts over walkers with its own task list (lhm_icg.cuh):
+        if (tid == 0) TI[L.ic_nt] = 0;                    // an empty schedule for whoever loads it (ic_prepare)
+        for (int k = tid; k <= IC_NW; k += NT) TI[L.ic_tb + k] = 0;
+    } else {
         const int No = Ni - 1, Ntar = Nt - 1;             // outgoing nu_ic[0..Ni-2], targets nu_tot[0..Nt-2]
         const int nog = (No + IC_OG - 1) / IC_OG, ngb = (Ng + IC_GB - 1) / IC_GB;
         const double* xi = T + L.invnt;
@@ -246,7 +273,10 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
         // same result as the obvious serial loop, which cost ~0.3 ms of global-memory latency per batch)
         if (tid < 32) {
             const int lane = tid, ncand = nog * ngb;
-            const int FIXED = A.ptab ? 2 : 12;                 // per-tile preamble in units of inner iterations
+            // per-tile preamble in units of inner iterations.  The same figure with and without the pair table (whose
+            // preamble is ~6x shorter): the schedule -- and with it the summation order and the result bits -- must
+            // not depend on how the pair constants are obtained (test_ic_pair_table_modes_are_bit_identical)
+            const int FIXED = 2;
             const unsigned lt_mask = (1u << lane) - 1u;
             int nt = 0;
             long long tot = 0;

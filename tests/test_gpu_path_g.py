@@ -4,6 +4,8 @@ against the live-reference fixtures at the north_star tolerance, and against pat
 import numpy as np
 import pytest
 
+from lehamoc_b200._lib import LhmError
+
 from util import TOL_LOG10, assert_spectra_close, load_golden, quiet
 
 pytestmark = pytest.mark.gpu
@@ -24,6 +26,10 @@ def test_ic_emissivity_steps_path_G():
     assert b.cfg["shared_ic_grids"] == 1
     eng = Engine(b.cfg, 3, ic_path="G")
     eng.setup(b)
+    engR = Engine(b.cfg, 3, ic_path="R")        # a path-G handle builds no per-walker tile schedule: R needs its own
+    engR.setup(b)
+    with pytest.raises(LhmError):
+        eng.ic_emissivity(np.ones((3, b.cfg["Ng"])), np.ones((3, b.cfg["Nt"])), "R")
     R0 = 10 ** P["R0"]
     sent = 10 ** (-260.)
     for s in range(1, 10):
@@ -33,13 +39,14 @@ def test_ic_emissivity_steps_path_G():
         Ns = np.stack([N, 2. * N, N])
         ns = np.stack([n, n, 4. * n])
         Q = eng.ic_emissivity(Ns, ns, "G").cpu().numpy()
-        QR = eng.ic_emissivity(Ns, ns, "R").cpu().numpy()
+        QR = engR.ic_emissivity(Ns, ns, "R").cpu().numpy()
         ref = z["step_Q_IC"][s]
         assert_spectra_close(Q[0], ref, f"Q_IC path G step {s + 1}", tol=1e-10)
         assert_spectra_close(Q[1], 2. * ref, f"Q_IC path G step {s + 1} (2 N_e)", tol=1e-10)
         assert_spectra_close(Q[2], 4. * ref, f"Q_IC path G step {s + 1} (4 n)", tol=1e-10)
         assert_spectra_close(Q, QR, f"Q_IC path G vs path R step {s + 1}", tol=1e-12)
     eng.close()
+    engR.close()
 
 
 @pytest.mark.parametrize("name", ["test1", "var_bb", "var_expand", "var_nogg", "var_user"])
