@@ -176,12 +176,15 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
 // SSA rows), then parks what the other half needs in HBM and hands p[w,i], av[w,gamma] to the contraction kernel.
 // Same phase functions, same order of operations as run_kernel: only Q_IC comes from a different summation.
 // =================================================================================================
-struct GState { int N, psyn, pic, agg, Qsyn, aS, aI, Ln, Lm, total; };
+struct GState { int N, psyn, pic, agg, Qsyn, aS, aI, Ln, Lm, Npr, aggS, QsynP, n, total; };
 __host__ __device__ inline GState gstate_layout(const Layout& L) {
     GState O; int o = 0;
     auto take = [&](int n) { int r = o; o += (n + 1) & ~1; return r; };
     O.N = take(L.Ng); O.psyn = take(L.Ns); O.pic = take(L.Ni); O.agg = take(L.Ni);
     O.Qsyn = take(L.Ns); O.aS = take(L.Ns); O.aI = take(L.Ni); O.Ln = take(L.Nt); O.Lm = take(L.Nt);
+    const bool lh = L.Np > 0;                                  // LeHaMoC.py driver: proton state, a_gg on nu_syn, proton
+    O.Npr = take(lh ? L.Np : 0); O.aggS = take(lh ? L.Ns : 0);  // synchrotron source, the photon field gamma-gamma reads
+    O.QsynP = take(lh ? L.Ns : 0); O.n = take(lh ? L.Nt : 0);
     O.total = o;
     return O;
 }
@@ -350,6 +353,123 @@ __global__ void __launch_bounds__(NT, 2) icg_unit_kernel(GUnitArgs U) {
     for (int i = tid; i < U.D.Kp; i += NT) gp[i] = (i < U.D.Ntar) ? C.T[L.wt + i] * U.n[(size_t)w * L.Nt + i] : 0.0;
     double* gav = U.gav + (size_t)w * U.D.NgP;
     for (int j = tid; j < U.D.NgP; j += NT) gav[j] = (j < L.Ng) ? S.av[j] : 0.0;
+}
+
+// -------------------------------------------------------------------------------------------------
+// path G for the LeHaMoC.py driver without hadronic channels (BASELINE config 5: fixed-grid sweeps with BB + PL photon
+// fields): run_lh_kernel's timestep cut at the IC emissivity exactly like stepG_kernel cuts run_kernel's.  Launch k runs
+// the second half of step k (Q_IC from the contraction, photon solves with the proton-synchrotron source, the three
+// gamma-gamma opacities + pre-attenuation + Q_ee_f, output) and the first half of step k+1 (photon field, U_ph_f, proton
+// equation, electron equation, per-gamma vectors, synchrotron / SSA rows of electrons and protons).
+// -------------------------------------------------------------------------------------------------
+template <int MINB>
+__global__ void __launch_bounds__(NT, MINB) stepG_lh_kernel(GArgs G) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const RunArgs& A = G.R;
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    SmemLh H;
+    carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L, S);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+    const double n_H = A.consts[(size_t)w * LHM_NCONST + LHM_C_NH];
+    if (nsteps < 1) { if (G.step == 0) no_step_outputs<NT>(A, w, Ng, Nt, Np); return; }
+    const GState O = gstate_layout(L);
+    double* st = G.state + (size_t)w * O.total;
+    g_prepare<NT>(C, S);
+    long long tprev = clock64();
+    double t = C.tinit;
+    for (int k = 0; k < G.step; ++k) t += C.dt;                 // the reference's own accumulation, LeHaMoC.py:268
+    if (G.do_B && G.step >= 1 && G.step <= nsteps) {
+        set_time(C, t);
+        for (int j = tid; j < Ng; j += NT) { S.N[j] = st[O.N + j]; S.qee[j] = 0.0; }
+        for (int j = tid; j < Np; j += NT) H.Npr[j] = st[O.Npr + j];
+        for (int k = tid; k < Ns; k += NT) {
+            S.psyn[k] = st[O.psyn + k]; S.Qsyn[k] = st[O.Qsyn + k]; S.aS[k] = st[O.aS + k];
+            H.aggS[k] = st[O.aggS + k]; H.QsynP[k] = st[O.QsynP + k];
+        }
+        for (int k = tid; k < Ni; k += NT) { S.pic[k] = st[O.pic + k]; S.agg[k] = st[O.agg + k]; S.aI[k] = st[O.aI + k]; }
+        for (int k = tid; k < Nt; k += NT) { S.Ln[k] = st[O.Ln + k]; S.Lm[k] = st[O.Lm + k]; S.n[k] = st[O.n + k]; }
+        icg_finish<NT>(G.part, G.D, G.Wpad, w, S.QIC);
+        __syncthreads();
+        LHM_TICK(0);
+        phase_photon_solves_lh<NT>(C, S, H, cor, nullptr);
+        LHM_TICK(8);
+        if (C.F.gg) phase_gg_lh<NT>(C, S, H, G.step - 1);
+        LHM_TICK(9);
+        const int step = G.step - 1;
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && step == nsteps - 1)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT)
+                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            if (A.Np_out) {
+                double* o = A.Np_out + ((size_t)w * S_ + slot) * Np;
+                for (int j = tid; j < Np; j += NT) o[j] = H.Npr[j] / C.V;
+            }
+            if (A.Nnu_out) {
+                double* o = A.Nnu_out + ((size_t)w * S_ + slot) * 50;
+                for (int k = tid; k < 50; k += NT) o[k] = 0.0;
+            }
+            __syncthreads();
+        }
+    }
+    if (G.do_A && G.step < nsteps) {
+        if (G.step == 0) {                                       // initial state (LeHaMoC.py:222-259)
+            const double V0 = volume_of(C.R0);
+            for (int j = tid; j < Ng; j += NT) {
+                S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j] * V0;
+                S.qee[j] = 0.0;
+            }
+            for (int j = tid; j < Np; j += NT) H.Npr[j] = 0.0;
+            for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; H.aggS[k] = 0.0; H.QsynP[k] = 0.0; }
+            for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+            __syncthreads();
+        }
+        t += C.dt;
+        set_time(C, t);
+        LHM_TICK(0);
+        phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph_lh<NT>(C, S);
+        LHM_TICK(1);
+        phase_protons<NT>(C, S, H, A.esc_pr, nullptr, true, true, n_H, false);
+        LHM_TICK(2);
+        phase_electrons_lh<NT>(C, S, nullptr, nullptr);
+        LHM_TICK(3);
+        phase_vectors<NT>(C, S);
+        LHM_TICK(4);
+        phase_syn_rows<NT>(C, S, false);
+        phase_syn_protons<NT>(C, S, H);
+        __syncthreads();
+        LHM_TICK(5);
+        for (int j = tid; j < Ng; j += NT) st[O.N + j] = S.N[j];
+        for (int j = tid; j < Np; j += NT) st[O.Npr + j] = H.Npr[j];
+        for (int k = tid; k < Ns; k += NT) {
+            st[O.psyn + k] = S.psyn[k]; st[O.Qsyn + k] = S.Qsyn[k]; st[O.aS + k] = S.aS[k];
+            st[O.aggS + k] = H.aggS[k]; st[O.QsynP + k] = H.QsynP[k];
+        }
+        for (int k = tid; k < Ni; k += NT) { st[O.pic + k] = S.pic[k]; st[O.agg + k] = S.agg[k]; st[O.aI + k] = S.aI[k]; }
+        for (int k = tid; k < Nt; k += NT) { st[O.Ln + k] = S.Ln[k]; st[O.Lm + k] = S.Lm[k]; st[O.n + k] = S.n[k]; }
+        double* gp = G.gp + (size_t)w * G.D.Kp;
+        for (int i = tid; i < G.D.Kp; i += NT) gp[i] = (i < G.D.Ntar) ? S.tri[4 * i + 2] : 0.0;     // the last target bin is dropped
+        double* gav = G.gav + (size_t)w * G.D.NgP;
+        for (int j = tid; j < G.D.NgP; j += NT) gav[j] = (j < Ng) ? S.av[j] : 0.0;
+        LHM_TICK(6);
+    }
 }
 
 // =================================================================================================
@@ -759,7 +879,7 @@ constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the regis
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
 static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
-    g_smem_icgu[MAX_DEV];
+    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -905,8 +1025,9 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
     }
     h->pathG = false;
     if (cfg->ic_path == LHM_IC_PATH_G) {
-        // the lock-step contraction needs one set of IC grids for the whole batch; leptonic drivers only
-        if (cfg->driver != 0 || !cfg->shared_ic_grids) return LHM_ERR_ARG;
+        // the lock-step contraction needs one set of IC grids for the whole batch; LeMoC.py / Code.py, or LeHaMoC.py
+        // without hadronic channels (stepG_lh_kernel)
+        if (cfg->driver > 1 || !cfg->shared_ic_grids || (cfg->driver == 1 && any_hadronic(h->F))) return LHM_ERR_ARG;
         h->F.ic_path = LHM_IC_PATH_R;                  // what the fused kernel runs when IC emission is switched off
         if (cfg->IC_emis_flag) {
             h->pathG = true;
@@ -1182,17 +1303,29 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
     return run_common(h, N_el_out, nuLnu_out, nullptr, nullptr, snapshots, false);
 }
 
-static int icg_splits(int W) {
+// CTAs per walker block: every CTA of a block takes every S-th task of the cost-sorted list, so the CTAs cost the same and
+// what matters is how full the last wave is.  S is the split (<= 16, at least two tasks per warp left) that fills the waves
+// best given how many contraction CTAs fit an SM (two up to ~113 KB of shared memory, else one); ties go to the smaller S.
+static int icg_splits(int W, const IcgDims& D) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     const int nwb = (W + ICG_NBW - 1) / ICG_NBW;
-    int S = (2 * sms + nwb / 2) / nwb;                  // two resident CTAs per SM, about one wave
-    return S < 1 ? 1 : (S > 16 ? 16 : S);
+    const int slots = sms * (2 * (icg_smem_bytes(D) + 1024) <= (size_t)227 * 1024 ? 2 : 1);
+    int smax = D.ntasks / (2 * (ICG_NT / 32));
+    smax = smax < 1 ? 1 : (smax > 16 ? 16 : smax);
+    int best = 1;
+    double best_eff = 0.0;
+    for (int S = 1; S <= smax; ++S) {
+        const int ctas = nwb * S, waves = (ctas + slots - 1) / slots;
+        const double eff = (double)ctas / ((double)waves * slots);
+        if (eff > best_eff + 1e-9) { best_eff = eff; best = S; }
+    }
+    return best;
 }
 
 static int launch_icg(lhm_handle* h, int ev_slot) {
     IcgArgs I;
-    I.D = h->GD; I.W = h->W; I.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW; I.S = icg_splits(h->W);
+    I.D = h->GD; I.W = h->W; I.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW; I.S = icg_splits(h->W, h->GD);
     I.ptg = h->d_ptg; I.kinfo = h->d_kinfo; I.xs = h->d_xs; I.tasks = h->d_tasks; I.gp = h->d_gp; I.gav = h->d_gav;
     I.part = h->d_part;
     const size_t smem = icg_smem_bytes(h->GD);
@@ -1214,7 +1347,13 @@ static int run_pathG(lhm_handle* h, const RunArgs& A) {
     G.state = h->d_state; G.gp = h->d_gp; G.gav = h->d_gav; G.part = h->d_part;
     static const int minb = [] { const char* e = std::getenv("LHM_G_CTAS"); const int v = e ? std::atoi(e) : 0; return (v >= 2 && v <= 4) ? v : LHM_G_DEFAULT_CTAS; }();
     void (*kern)(GArgs) = minb == 4 ? stepG_kernel<4> : minb == 3 ? stepG_kernel<3> : stepG_kernel<2>;
-    CUDA_TRY(ensure_dyn_smem(kern, h->smem, g_smem_stepg[(h->device % MAX_DEV)]));
+    std::atomic<size_t>* smem_slot = &g_smem_stepg[h->device % MAX_DEV];
+    if (h->cfg.driver == 1) {                            // two walkers per SM while their state fits, else one
+        const bool two = h->smem * 2 + 2048 <= (size_t)227 * 1024;
+        kern = two ? stepG_lh_kernel<2> : stepG_lh_kernel<1>;
+        smem_slot = two ? &g_smem_stepglh[h->device % MAX_DEV] : &g_smem_stepglh1[h->device % MAX_DEV];
+    }
+    CUDA_TRY(ensure_dyn_smem(kern, h->smem, *smem_slot));
     h->evg_n = 0;
     for (int k = 0; k <= n; ++k) {
         G.step = k; G.do_B = k >= 1; G.do_A = k < n;
@@ -1344,7 +1483,7 @@ int lhm_last_icg_timing(lhm_handle* h, float* mean_ms, int* launches, int* ctas,
     }
     if (mean_ms) *mean_ms = (float)(tot / h->evg_n);
     if (launches) *launches = h->evg_n;
-    if (ctas) *ctas = ((h->W + ICG_NBW - 1) / ICG_NBW) * icg_splits(h->W);
+    if (ctas) *ctas = ((h->W + ICG_NBW - 1) / ICG_NBW) * icg_splits(h->W, h->GD);
     if (smem_bytes) *smem_bytes = (int)icg_smem_bytes(h->GD);
     return LHM_OK;
 }

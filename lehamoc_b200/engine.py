@@ -37,9 +37,14 @@ class Engine:
         if "LHM_CONST_B" in os.environ:                      # experiments: force the exponential cache on/off
             self.cfg["const_B"] = int(os.environ["LHM_CONST_B"])
         cfg = self.cfg
-        if ic_path == "G" and not (cfg.get("shared_ic_grids") and cfg.get("driver", 0) == 0):
+        hadronic = any(cfg.get(k) for k in ("pg_pi_l_flag", "pg_BH_l_flag", "pg_pi_emis_flag", "neutrino_flag",
+                                            "pg_BH_emis_flag", "pp_l_flag", "pp_ee_emis_flag", "pp_g_emis_flag",
+                                            "pp_nu_emis_flag"))
+        if ic_path == "G" and not (cfg.get("shared_ic_grids") and (cfg.get("driver", 0) == 0
+                                                                   or (cfg.get("driver") == 1 and not hadronic))):
             raise LhmError("ic_path 'G' (dense contraction over walkers) needs a batch whose walkers share g_el / nu_ic / "
-                           "nu_tot (cfg.shared_ic_grids) and one of the leptonic drivers")
+                           "nu_tot (cfg.shared_ic_grids) and a leptonic run: LeMoC.py / Code.py, or LeHaMoC.py with "
+                           "every hadronic flag off")
         self.ic_path = ic_path
         c = lhm_config()
         for k, v in cfg.items():

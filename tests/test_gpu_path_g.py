@@ -108,6 +108,40 @@ def test_path_G_full_size_batch_and_device_packing():
     assert_spectra_close(got[0][0], N[:, 0], "run_many path G n_e")
 
 
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user", "lh_bbpl200", "lh_bbpl400"])
+def test_lehamoc_driver_path_G(name):
+    """Path G under the LeHaMoC.py driver (hadronic flags 0; BASELINE config 5 is such a fixed-grid sweep): walkers 0 and 2
+    of a shared-grid batch are the fixture's parameter set (every step against the unmodified script), walker 1 is
+    perturbed and checked against path R."""
+    from lehamoc_b200 import LeHaMoC
+    from test_lehamoc_driver import log_close
+    z, P = load_golden(name)
+    sets = [dict(P), dict(P, B0=P["B0"] * 1.7, p_el=P["p_el"] + 0.2, L_el=P["L_el"] - 0.3, L_pr=P["L_pr"] + 0.4), dict(P)]
+    batch, N, sed, Npr, Nnu = LeHaMoC.run(sets, ic_path="G")
+    _, NR, sedR, NprR, _ = LeHaMoC.run(sets, ic_path="R")
+    assert batch.cfg["shared_ic_grids"] == 1 and not Nnu.any()
+    for w in (0, 2):
+        log_close(N[w], z["n_e"], f"{name}/G n_e walker {w}")
+        log_close(sed[w], z["nuLnu"], f"{name}/G nuLnu walker {w}")
+        log_close(Npr[w], z["n_p"], f"{name}/G n_p walker {w}")
+    np.testing.assert_array_equal(sed[0], sed[2])
+    with np.errstate(divide="ignore"):
+        log_close(sed, np.log10(sedR), f"{name}: path G vs path R nuLnu", tol=1e-11)
+        log_close(N, np.log10(NR), f"{name}: path G vs path R n_e", tol=1e-11)
+        log_close(Npr, np.log10(NprR), f"{name}: path G vs path R n_p", tol=1e-11)
+
+
+def test_lehamoc_driver_path_G_limits():
+    """Grid 800 does not fit the contraction's shared-memory tiles (32 walkers x 800 target frequencies + 800 gammas):
+    refused with LHM_ERR_CAPACITY, the caller falls back to path R; a hadronic flag is refused outright."""
+    from lehamoc_b200 import LeHaMoC, _lib
+    _, P = load_golden("lh_bbpl")
+    with pytest.raises(_lib.LhmError):
+        LeHaMoC.run([dict(P, grid_g_el=800., grid_nu=800., time_end=1.)] * 2, ic_path="G")
+    with pytest.raises(_lib.LhmError):
+        LeHaMoC.run([dict(P, pg_pi_l_flag=1.)] * 2, ic_path="G")
+
+
 def test_path_G_refuses_what_it_cannot_do():
     from lehamoc_b200 import LeMoC, _lib
     from lehamoc_b200.engine import Engine

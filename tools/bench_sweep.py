@@ -19,6 +19,7 @@ ap.add_argument("--walkers", type=int, default=296)
 ap.add_argument("--grids", type=int, nargs="+", default=[100, 200, 400, 800])
 ap.add_argument("--check", type=int, default=0, help="grid size at which walker 0 is compared with the CPU oracle")
 ap.add_argument("--phases", action="store_true", help="per-phase cycle breakdown of thread 0 (run_lh_kernel counters)")
+ap.add_argument("--ic-path", default="R", choices=["R", "S", "G"], help="G: dense contraction over walkers (grid <= 400)")
 a = ap.parse_args()
 z = np.load(os.path.join(ROOT, "tests", "golden", "lh_bbpl.npz"))
 BASE = dict(zip([str(k) for k in z["param_keys"]], [float(v) for v in z["param_vals"]]))
@@ -35,7 +36,7 @@ for grid in a.grids:
     t0 = time.perf_counter()
     b = pack_lehamoc(sets)
     pack_s = time.perf_counter() - t0
-    eng = Engine(b.cfg, b.W)
+    eng = Engine(b.cfg, b.W, ic_path=a.ic_path)
     eng.setup(b)
     eng.run_lh()
     torch.cuda.synchronize()
@@ -51,6 +52,9 @@ for grid in a.grids:
     ms = float(np.median(ts))
     print(f"grid {grid:4d}: {ms:9.2f} ms per {a.walkers} models x 10 steps = {1e3 * ms / a.walkers:8.1f} us per model "
           f"({a.walkers / (ms * 1e-3):9.0f} model-evals/s; smem {eng.smem_bytes() / 1024:.0f} KB/CTA; host packing {pack_s:.2f} s)")
+    if a.ic_path == "G":
+        cm, cn, ctas, csm = eng.last_icg_timing()
+        print(f"          contraction: {cm:.3f} ms per launch x 10 = {10 * cm:.1f} ms of the {ms:.1f} ms loop ({ctas} CTAs, {csm / 1024:.0f} KB smem each)")
     if a.phases:
         import ctypes as C
         prof = torch.zeros(16, dtype=torch.int64, device="cuda")
@@ -62,6 +66,9 @@ for grid in a.grids:
         p = prof.cpu().numpy().astype(float)
         names = ["loop/out", "photons+uph", "protons", "bh_emis", "photopion", "pp", "electrons+syn rows", "ic",
                  "photon solves", "gg"]
+        if a.ic_path == "G":
+            names = ["load+Q_IC / time", "photons+uph", "protons", "electrons", "vectors", "syn rows (e, p)", "store", "-",
+                     "photon solves", "gg"]
         print("          cycles per walker-step: " + ", ".join(f"{n_} {v / a.walkers / 10:.0f}" for n_, v in zip(names, p) if v > 0))
     if a.check == grid:
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
