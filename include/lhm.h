@@ -291,6 +291,25 @@ typedef struct lhm_pack_args {
 } lhm_pack_args;
 int lhm_pack_batch(const lhm_pack_args* args, void* cuda_stream);
 
+/* ---- one call per fit evaluation (replaces `pool.map(log_probability, thetas)` of Fit_emcee/fit_emcee.py:190-199,239-242
+ * for flag_c = 'LeMoC', without the prior, which stays on the host): host in, host out.
+ * obs: the observation table of fit_emcee.py:61-93 as DEVICE pointers [nd] (flags as the reference's floats) and the two
+ * scalars of Model.__call__ (fit_emcee.py:108-115).
+ * pack: as for lhm_pack_batch, variant 1 (Code.py); its POINTER members are ignored -- the library packs into buffers the
+ *       handle owns.
+ * stage_host: [W*LHM_PACK_NPAR | Nh | Nt | Nt | W | W] doubles in HOST memory = walker_params, nu_ic_row, nu_tot_row,
+ *       ext_row, log10 of the Doppler factor per walker, log_f per walker.
+ * logl_host [W]: log-likelihood of every walker (fit_emcee.py:121-145).
+ * Inside: pinned staging + one H2D copy, pack_kernel, the table set-up next to the cor-factor, the fused time loop, the
+ * observation transform + likelihood, one D2H copy, one stream synchronisation.  Leptonic driver 0 handles only. */
+typedef struct lhm_fit_obs {
+    int nd;
+    const double *x, *y, *yerr_hi, *yerr_lo, *flags;
+    double log10_1pz, distance_norm;
+} lhm_fit_obs;
+int lhm_fit_logl_host(lhm_handle*, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                      double* logl_host);
+
 /* A14 pp channels (LeHaMoC_f.py:860-1014): product 0 Q_e_pp (grid = g_el), 1 Q_g_pp (grid = nu_ic), 2 Q_nu_mu_pp,
  * 3 Q_nu_e_pp (grid = nu_nu = E_nu/h).  grid [W,Nout]; g_pr, N_pr_TeV [W,Np] (dN_pr/dV dgamma divided by
  * m_p c^2 * 0.624151, LeHaMoC.py:355); p_pr, n_H [W]; out [W,Nout]. */

@@ -46,6 +46,11 @@ class lhm_pack_args(C.Structure):                    # include/lhm.h: lhm_pack_a
                    ("pr_inj", C.c_void_p)])
 
 
+class lhm_fit_obs(C.Structure):                      # include/lhm.h: lhm_fit_obs
+    _fields_ = [("nd", C.c_int)] + [(n, C.c_void_p) for n in ("x", "y", "yerr_hi", "yerr_lo", "flags")] + [
+        ("log10_1pz", C.c_double), ("distance_norm", C.c_double)]
+
+
 # every symbol include/lhm.h declares: (restype, argtypes)
 _P = C.c_void_p
 SIGNATURES = {
@@ -67,6 +72,7 @@ SIGNATURES = {
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),
     "lhm_set_lockstep": (C.c_int, [_P, C.c_int]),
+    "lhm_fit_logl_host": (C.c_int, [_P, C.POINTER(lhm_pack_args), _P, C.POINTER(lhm_fit_obs), _P]),
     "lhm_last_hadtab_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "lhm_last_icg_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),

@@ -915,6 +915,8 @@ struct lhm_handle {
     double* d_in;
     double* d_Nout;
     double* d_sed;
+    // lhm_fit_logl_host: pinned staging (in | out), device input row block, packed [W, n] arrays, SEDs, likelihoods
+    double* fit_pin; double* fit_din; double* fit_arr; double* fit_sed; double* fit_logl; size_t fit_cap;
     size_t Nout_cap, sed_cap;
     unsigned long long* d_prof;   // optional per-phase cycle counters (lhm_set_phase_profile)
     // device-side timing of the last setup / cor / run launches (lhm_last_timings)
@@ -1082,6 +1084,8 @@ void lhm_destroy(lhm_handle* h) {
     cudaSetDevice(h->device);
     cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E); cudaFree(h->d_ptab);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
+    if (h->fit_pin) cudaFreeHost(h->fit_pin);
+    cudaFree(h->fit_din); cudaFree(h->fit_arr); cudaFree(h->fit_sed); cudaFree(h->fit_logl);
     cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
     cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
     free_had_tabs(h);
@@ -1734,6 +1738,55 @@ int lhm_pack_batch(const lhm_pack_args* a, void* stream) {
     pack_kernel<<<a->W, PACK_NT, 0, (cudaStream_t)stream>>>(A);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
+    return LHM_OK;
+}
+
+int lhm_fit_logl_host(lhm_handle* h, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                      double* logl_host) {
+    if (!h || !pack || !stage_host || !obs || !logl_host) return LHM_ERR_ARG;
+    const lhm_config& c = h->cfg;
+    const int W = pack->W, Ng = c.Ng, Nh = c.Ni, Nt = c.Nt;
+    if (c.driver != 0 || h->pathG) return LHM_ERR_STATE;
+    if (W < 1 || pack->Ng != Ng || pack->Nh != Nh || pack->Nt != Nt || c.Ns != Nh + 1 || obs->nd < 1) return LHM_ERR_ARG;
+    if (W > c.max_walkers) return LHM_ERR_CAPACITY;
+    CUDA_TRY(cudaSetDevice(h->device));
+    const size_t Wm = (size_t)c.max_walkers;
+    const size_t n_in_max = Wm * (LHM_PACK_NPAR + 2) + Nh + 2 * (size_t)Nt;
+    const size_t per_w = (size_t)LHM_NCONST + 2 * Ng + (Nh + 1) + Nh + 2 * (size_t)Nt;   // consts g_el el_inj nu_syn nu_ic nu_tot ext
+    if (!h->fit_pin) {
+        CUDA_TRY(cudaHostAlloc(&h->fit_pin, (n_in_max + Wm) * sizeof(double), cudaHostAllocDefault));
+        CUDA_TRY(cudaMalloc(&h->fit_din, n_in_max * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->fit_arr, Wm * per_w * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->fit_sed, Wm * Nt * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->fit_logl, Wm * sizeof(double)));
+    }
+    cudaStream_t s = h->stream;
+    const size_t o_par = 0, o_ic = (size_t)W * LHM_PACK_NPAR, o_tot = o_ic + Nh, o_ext = o_tot + Nt, o_dop = o_ext + Nt,
+                 o_lf = o_dop + W, n_in = o_lf + W;
+    std::memcpy(h->fit_pin, stage_host, n_in * sizeof(double));
+    CUDA_TRY(cudaMemcpyAsync(h->fit_din, h->fit_pin, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    lhm_pack_args a = *pack;
+    double* p = h->fit_arr;
+    auto take = [&](size_t n) { double* r = p; p += Wm * n; return r; };
+    a.walker_params = h->fit_din + o_par; a.nu_ic_row = h->fit_din + o_ic; a.nu_tot_row = h->fit_din + o_tot;
+    a.ext_row = h->fit_din + o_ext;
+    a.consts = take(LHM_NCONST); a.g_el = take(Ng); a.el_inj = take(Ng); a.nu_syn = take(Nh + 1); a.nu_ic = take(Nh);
+    a.nu_tot = take(Nt); a.ext = take(Nt);
+    a.Np = 0; a.g_pr = nullptr; a.pr_inj = nullptr;
+    int rc = lhm_pack_batch(&a, s);
+    if (rc != LHM_OK) return rc;
+    rc = lhm_setup_batch(h, W, a.consts, a.g_el, a.nu_syn, a.nu_ic, a.nu_tot, a.el_inj, a.ext);
+    if (rc != LHM_OK) return rc;
+    rc = lhm_run_batch(h, nullptr, h->fit_sed, 0);
+    if (rc != LHM_OK) return rc;
+    rc = lhm_loglike_batch(W, Nt, a.nu_tot, h->fit_sed, h->fit_din + o_dop, h->fit_din + o_lf, obs->log10_1pz,
+                           obs->distance_norm, obs->nd, obs->x, obs->y, obs->yerr_hi, obs->yerr_lo, obs->flags, h->fit_logl,
+                           nullptr, s);
+    if (rc != LHM_OK) return rc;
+    double* pin_out = h->fit_pin + n_in_max;
+    CUDA_TRY(cudaMemcpyAsync(pin_out, h->fit_logl, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    std::memcpy(logl_host, pin_out, (size_t)W * sizeof(double));
     return LHM_OK;
 }
 

@@ -198,6 +198,37 @@ class Engine:
         check(self.lib.lhm_pack_batch(C.byref(a), C.c_void_p(self.stream.cuda_stream)), "lhm_pack_batch")
         self.setup_device(W, *[t[:W] for t in outs])
 
+    def fit_logl_host(self, req, doppler, log_f, obs):
+        """One fit evaluation in ONE library call (lhm_fit_logl_host): PackRequest of the Code.py variant + per-walker
+        log10 Doppler factor and log_f + the observation table (a _lib.lhm_fit_obs of device pointers) -> log-likelihoods
+        [W] as a NumPy array.  Packing, set-up, cor-factor, time loop, observation transform, likelihood and both copies
+        run inside the call."""
+        from .constants import c, m_el, sigmaT, q
+        cfg = req.cfg
+        for k in ("Ng", "Ns", "Ni", "Nt"):
+            if cfg[k] != self.cfg[k]:
+                raise LhmError(f"batch {k}={cfg[k]} does not match the engine ({self.cfg[k]})")
+        if req.variant != "code":
+            raise LhmError("fit_logl_host evaluates the Code.py variant (Fit_emcee)")
+        W, Nh, Nt = req.W, cfg["Ni"], cfg["Nt"]
+        if W > self.max_walkers:
+            raise LhmError(f"batch of {W} walkers exceeds the engine capacity {self.max_walkers}")
+        stage = np.empty(W * (_lib.LHM_PACK_NPAR + 2) + Nh + 2 * Nt)
+        o = W * _lib.LHM_PACK_NPAR
+        stage[:o] = req.walker_params.ravel()
+        stage[o:o + Nh] = req.nu_ic_row
+        stage[o + Nh:o + Nh + Nt] = req.nu_tot_row
+        stage[o + Nh + Nt:o + Nh + 2 * Nt] = req.ext_row
+        stage[o + Nh + 2 * Nt:o + Nh + 2 * Nt + W] = doppler
+        stage[o + Nh + 2 * Nt + W:] = log_f
+        a = _lib.lhm_pack_args(W=W, Ng=cfg["Ng"], Nh=Nh, Nt=Nt, variant=1, c=c, c3=c ** 3., m_el=m_el, mc2=m_el * c ** 2.,
+                               sigmaT=sigmaT, four_pi=4. * np.pi, nuc_pref=3. / (4. * np.pi) * q, **req.scalars)
+        out = np.empty(W)
+        check(self.lib.lhm_fit_logl_host(self.h, C.byref(a), stage.ctypes.data_as(C.c_void_p), C.byref(obs),
+                                         out.ctypes.data_as(C.c_void_p)), "lhm_fit_logl_host")
+        self.W = W
+        return out
+
     # -- the whole time integration ---------------------------------------------------------------
     def run(self, snapshots: int = 0, want_N: bool = True, want_sed: bool = True):
         S = snapshots if snapshots > 0 else 1

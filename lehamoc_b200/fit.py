@@ -119,6 +119,8 @@ class FitEvaluator:
         if any(len(a) != self.nd for a in arrs):
             raise ValueError("x, y, yerr, yerr1, flags must have the same length")
         self._data = [torch.from_numpy(a).to(dev) for a in arrs]
+        self._obs = _lib.lhm_fit_obs(nd=self.nd, log10_1pz=self.log1pz, distance_norm=self.distance_norm,
+                                     **{n: t.data_ptr() for n, t in zip(("x", "y", "yerr_hi", "yerr_lo", "flags"), self._data)})
 
     def _engine(self, batch):
         if self.eng is None or self.eng.max_walkers < batch.W or any(
@@ -173,8 +175,14 @@ class FitEvaluator:
         out = np.full(thetas.shape[0], -np.inf)
         inside = np.isfinite(lp)
         if inside.any():
-            logl, _ = self.model_and_loglike(thetas[inside])
-            out[inside] = lp[inside] + logl.cpu().numpy()
+            th = thetas[inside]
+            if self.flag_c == "LeMoC" and self.device_pack and self.ic_path != "G":
+                # the whole evaluation in one library call (lhm_fit_logl_host): no torch op, no second synchronisation
+                req = pack_code_request(th[:, :self.nfree], self.frozen)
+                logl = self._engine(req).fit_logl_host(req, th[:, self.nfree], th[:, self.nfree + 1], self._obs)
+            else:
+                logl = self.model_and_loglike(th)[0].cpu().numpy()
+            out[inside] = lp[inside] + logl
         return out
 
     def log_probability_sharded(self, thetas):

@@ -219,28 +219,30 @@ def _window_indices(lo, hi, n, pl_min, pl_max):
     grid values -- evaluated only on a few candidates around the arithmetic position of the threshold, O(W) instead
     of O(W*Ng).  Walkers whose candidates do not bracket the threshold fall back to the full row."""
     W = len(lo)
-    thr_max = np.array([10 ** x for x in pl_max.tolist()])
-    thr_min = np.array([10 ** x for x in pl_min.tolist()])
-    step = (hi - lo) / (n - 1)
-    off = np.arange(-2, 4)[None, :]
-
-    def first_true(thr, target, pred):
-        """first index j with pred(g[j], thr) for a predicate that is monotone along the grid; n if none"""
-        with np.errstate(invalid="ignore", divide="ignore"):
-            guess = np.floor((target - lo) / step)
-        guess = np.nan_to_num(guess, nan=0., posinf=n - 1., neginf=0.)
-        cand = np.clip(guess[:, None].astype(np.int64) + off, 0, n - 1)
-        ok = pred(_logspace_points(lo, hi, n, cand), thr[:, None])
-        out = np.where(ok.any(axis=1), cand[np.arange(W), ok.argmax(axis=1)], n)
-        # bracket check: predicate false on the first candidate (or it is grid index 0 and true) and true on the last
-        # (or it is the last grid index and false)
-        good = (~ok[:, 0] | (cand[:, 0] == 0)) & (ok[:, -1] | (cand[:, -1] == n - 1))
-        for w in np.flatnonzero(~good):
-            row = pred(np.logspace(lo[w], hi[w], n), thr[w])
-            out[w] = int(row.argmax()) if row.any() else n
-        return out
-    first_gt = first_true(thr_max, pl_max, lambda g, t: g > t)
-    first_ge = first_true(thr_min, pl_min, lambda g, t: ~(g < t))          # count of g < thr
+    # both thresholds in one stacked pass (rows 0..W-1: `g > 10**g_PL_max`, rows W..2W-1: `not g < 10**g_PL_min`): the
+    # call sits on the latency path of every fit evaluation, and at 24 walkers it is all NumPy call overhead
+    thr = np.array([10 ** x for x in pl_max.tolist()] + [10 ** x for x in pl_min.tolist()])
+    target = np.concatenate([pl_max, pl_min])
+    lo2, hi2 = np.concatenate([lo, lo]), np.concatenate([hi, hi])
+    step = (hi2 - lo2) / (n - 1)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        guess = np.floor((target - lo2) / step)
+        guess = np.where(np.isfinite(guess), guess, np.where(guess > 0, n - 1., 0.))     # nan, -inf -> 0; +inf -> n-1
+    cand = np.clip(guess[:, None].astype(np.int64) + np.arange(-2, 4)[None, :], 0, n - 1)
+    g = _logspace_points(lo2, hi2, n, cand)
+    ok = np.empty(cand.shape, dtype=bool)
+    ok[:W] = g[:W] > thr[:W, None]
+    ok[W:] = ~(g[W:] < thr[W:, None])
+    # first index j with the predicate true (it is monotone along the grid); n if none
+    out = np.where(ok.any(axis=1), cand[np.arange(2 * W), ok.argmax(axis=1)], n)
+    # bracket check: predicate false on the first candidate (or it is grid index 0 and true) and true on the last
+    # (or it is the last grid index and false); walkers whose candidates do not bracket fall back to the full row
+    good = (~ok[:, 0] | (cand[:, 0] == 0)) & (ok[:, -1] | (cand[:, -1] == n - 1))
+    for r in np.flatnonzero(~good):
+        row = np.logspace(lo2[r], hi2[r], n)
+        row = (row > thr[r]) if r < W else ~(row < thr[r])
+        out[r] = int(row.argmax()) if row.any() else n
+    first_gt, first_ge = out[:W], out[W:]                                  # first_ge = count of g < thr
     same = pl_max == hi
     if np.any(~same & (first_gt >= n)) or np.any((pl_min != 0.) & (first_ge < 1)):
         raise ValueError("power-law window outside the gamma grid (the reference raises here too)")
@@ -270,14 +272,33 @@ def _pack_request(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_
         zero = bool(np.any(~(float(F["time_init"]) < float(F["time_end"]) * R0 / c)))
     if zero:
         raise ValueError("time_init/time_end/step_alg give a walker zero timesteps: the reference produces no output")
-    nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
-    nu_tot = np.logspace(np.log10(np.logspace(7.5, 8.5, 2)[0]), np.log10(nu_ic[-1]), Nt)   # LeMoC.py:131,133
-    Vexp = float(F["Vexp"]) * c
-    cfg = _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp,
-                        shared=W > 1 and bool(np.all(g_min_el == g_min_el[0]) and np.all(g_max_el == g_max_el[0])))
-    scal = dict(time_init=float(F["time_init"]), time_end=float(F["time_end"]), step_alg=float(F["step_alg"]),
-                Vexp_cm_s=Vexp, m=float(F["m"]))
-    return PackRequest(variant, cfg, wp, nu_ic, nu_tot, external_fields(F, nu_tot), scal)
+    shared = W > 1 and bool(np.all(g_min_el == g_min_el[0]) and np.all(g_max_el == g_max_el[0]))
+    # what does not depend on the walkers is a function of the parameter file alone: memoised per file contents (a
+    # sampler calls this thousands of times with the same frozen parameters)
+    try:
+        key = (variant, shared, tuple(F.items()))
+        hit = _REQUEST_ROWS.get(key)
+    except TypeError:                                   # unhashable entry (a user-supplied photon spectrum array)
+        key = hit = None
+    if hit is None:
+        nu_ic = np.logspace(10., 30., Nh)                                                      # LeMoC.py:132
+        nu_tot = np.logspace(np.log10(np.logspace(7.5, 8.5, 2)[0]), np.log10(nu_ic[-1]), Nt)   # LeMoC.py:131,133
+        Vexp = float(F["Vexp"]) * c
+        cfg = _leptonic_cfg(variant, F, Ng, Nh, Nt, Vexp, shared=shared)
+        scal = dict(time_init=float(F["time_init"]), time_end=float(F["time_end"]), step_alg=float(F["step_alg"]),
+                    Vexp_cm_s=Vexp, m=float(F["m"]))
+        hit = (cfg, nu_ic, nu_tot, external_fields(F, nu_tot), scal)
+        for a in hit[1:4]:
+            a.flags.writeable = False
+        if key is not None:
+            if len(_REQUEST_ROWS) > 64:
+                _REQUEST_ROWS.clear()
+            _REQUEST_ROWS[key] = hit
+    cfg, nu_ic, nu_tot, ext, scal = hit
+    return PackRequest(variant, dict(cfg), wp, nu_ic, nu_tot, ext, dict(scal))
+
+
+_REQUEST_ROWS = {}
 
 
 def _pack(variant, F, R0, B0, g_min_el, g_max_el, g_PL_min, g_PL_max, p_el, comp_inj, comp_cor) -> Batch:

@@ -108,6 +108,32 @@ def test_gpu_loglike_matches_reference(gold, device_pack):
 
 
 @pytest.mark.gpu
+def test_gpu_one_call_fit_evaluation_equals_the_staged_path(gold):
+    """lhm_fit_logl_host (packing, set-up, cor-factor, time loop, likelihood and both copies in ONE library call -- what
+    FitEvaluator.log_probability uses) gives bit for bit what the call-by-call path gives, for the golden walkers, for
+    random walkers over the prior box, for a batch that grows the engine, and with walkers outside the prior."""
+    from lehamoc_b200 import fit
+    from lehamoc_b200.presets import fit_walkers
+    _, P = load_golden("code_fit")
+    ev = fit.FitEvaluator(gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"], param_file=P,
+                          D=float(gold["D_Mpc"]), z=float(gold["z"]))
+    rng = np.random.default_rng(11)
+    for W in (8, 40, 130):
+        th = gold["theta8"] if W == 8 else np.column_stack([fit_walkers(W, seed=W), rng.uniform(0.5, 2.5, W),
+                                                            rng.uniform(-5., 0., W)])
+        staged = fit.log_prior_batch(th, "LeMoC") + ev.model_and_loglike(th)[0].cpu().numpy()
+        one = ev.log_probability(th)
+        np.testing.assert_array_equal(one, staged)
+        assert np.isfinite(one).mean() > 0.5
+    np.testing.assert_allclose(ev.log_probability(gold["theta8"]), gold["logprob"], rtol=1e-6)
+    bad = gold["theta8"].copy()
+    bad[[1, 6], 0] = 17.5
+    lpb = ev.log_probability(bad)
+    assert np.isneginf(lpb[[1, 6]]).all()
+    np.testing.assert_array_equal(np.delete(lpb, [1, 6]), np.delete(ev.log_probability(gold["theta8"]), [1, 6]))
+
+
+@pytest.mark.gpu
 def test_gpu_loglike_epilogue_alone(gold):
     """lhm_loglike_batch on the REFERENCE's spectra (isolates the epilogue from the time integration)."""
     import ctypes as C
