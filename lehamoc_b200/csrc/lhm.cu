@@ -544,7 +544,7 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
                 H.lppg[k] = log10(S.n[k] / kHC.h);
             }
             __syncthreads();
-            phase_loss_pg_tab<NTL>(C, H, Tw, A.HD.nloss);
+            phase_loss_pg_tab<NTL>(C, S, H, Tw, A.HD.nloss);
             __syncthreads();
         }
         phase_protons<NTL>(C, S, H, A.esc_pr, A.had ? &Tb : nullptr, true, true, n_H, pg_tab);

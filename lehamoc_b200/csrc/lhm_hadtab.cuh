@@ -190,6 +190,35 @@ __global__ void __launch_bounds__(HAD_NT) bh_table_kernel(HadTabArgs A) {
     }
 }
 
+// The tabulated phases evaluate 10**np.interp(x_s, xp, fp) at ~10^6 fixed abscissae per step.  Per bracket the slope
+// (fp[j+1]-fp[j])/(xp[j+1]-xp[j]) is the same for every sample that falls into it, so it is formed once per step (Nt
+// divisions instead of one per sample), together with the left ordinate, both in units of log2: a sample is then one FMA
+// and the staged 2^x of the gamma-gamma phase (fast_exp2, 1e-15) instead of a division and an exp10.  np.interp's NaN
+// fall-backs (-inf ordinates) are taken by the exact routine on the rare sample that needs them.
+template <int NT>
+__device__ __forceinline__ void tab_interp_stage(const double* __restrict__ xp, const double* __restrict__ fp, int Nt,
+                                                 double* __restrict__ isl, double* __restrict__ if0) {
+    const double L2_10 = 3.321928094887362347870319429489390175865;
+    for (int j = threadIdx.x; j < Nt; j += NT) {
+        if0[j] = fp[j] * L2_10;
+        isl[j] = (j < Nt - 1) ? ((fp[j + 1] - fp[j]) / (xp[j + 1] - xp[j])) * L2_10 : 0.0;
+    }
+}
+__device__ __forceinline__ double tab_interp_pow10(const double* __restrict__ xp, const double* __restrict__ fp, int Nt,
+                                                   const double* __restrict__ isl, const double* __restrict__ if0,
+                                                   const double* __restrict__ e2tab, int code, double dx) {
+    const int j = code >> 1;
+    double r = if0[j];
+    if (!(code & 1)) {
+        r = fma(isl[j], dx, r);
+        if (isnan(r)) {                                       // -inf ordinates: np.interp's fall-backs
+            const int jx = min(j, Nt - 2);
+            r = interp_eval(fp, code, dx, xp[jx + 1] - xp[jx]) * 3.321928094887362347870319429489390175865;
+        }
+    }
+    return fast_exp2(r, e2tab);
+}
+
 // Q_BH_sol with the table: Qbh[i] = c sum_j n_p[j] sum_e K[e][i,j] 10^interp(log10 photons at E_arr[e]); one warp per gamma_e
 template <int NT>
 __device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTabs& Tw, int npairs) {
@@ -197,6 +226,7 @@ __device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTab
     const int Np = L.Np, Ng = L.Ng, Nt = L.Nt;
     const double* __restrict__ xt = C.T + L.xt;
     for (int j = threadIdx.x; j < Np; j += NT) H.npl[j] = H.Npr[j] / C.V;
+    tab_interp_stage<NT>(xt, S.Ln, Nt, H.isl, H.if0);
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     for (int i = warp; i < Ng; i += NT / 32) {
@@ -204,15 +234,18 @@ __device__ void phase_bh_emis_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTab
         for (int j = lane; j < Np; j += 32) {
             const size_t pair = (size_t)i * Np + j;
             double g = 0.0;
-#pragma unroll 5
-            for (int e = 0; e < 10; ++e) {
-                const double K = __ldg(Tw.bhK + (size_t)e * npairs + pair);
-                if (K != 0.0) {
-                    const int code = __ldg(Tw.bhcode + (size_t)e * npairs + pair);
-                    const double dx = __ldg(Tw.bhdx + (size_t)e * npairs + pair);
-                    const int jx = min(code >> 1, Nt - 2);
-                    g = fma(K, exp10(interp_eval(S.Ln, code, dx, __ldg(xt + jx + 1) - __ldg(xt + jx))), g);
+#pragma unroll
+            for (int e0 = 0; e0 < 10; e0 += 5) {              // all loads of five samples in flight before the first use
+                double K[5], dx[5];
+                int code[5];
+#pragma unroll
+                for (int u = 0; u < 5; ++u) {
+                    const size_t o = (size_t)(e0 + u) * npairs + pair;
+                    K[u] = __ldg(Tw.bhK + o); code[u] = __ldg(Tw.bhcode + o); dx[u] = __ldg(Tw.bhdx + o);
                 }
+#pragma unroll
+                for (int u = 0; u < 5; ++u)
+                    if (K[u] != 0.0) g = fma(K[u], tab_interp_pow10(xt, S.Ln, Nt, H.isl, H.if0, S.e2tab, code[u], dx[u]), g);
             }
             s = fma(H.npl[j], g, s);
         }
@@ -391,10 +424,18 @@ __device__ void pion_eval_tab(const PionIn& I, double* work, const double* __res
         const double* __restrict__ row = phi + (size_t)k * PG_N;
         double a0 = 0.0, a1 = 0.0;
         int e = lane;
+        for (; e + 96 < PG_N; e += 128) {                   // four table entries in flight per lane (the rows come from L2)
+            const double p0 = __ldg(row + e), p1 = __ldg(row + e + 32), p2 = __ldg(row + e + 64), p3 = __ldg(row + e + 96);
+            const double v0 = P.Wt[e], v1 = P.Wt[e + 32], v2 = P.Wt[e + 64], v3 = P.Wt[e + 96];
+            if (v0 != 0.0) a0 = fma(p0, v0, a0);            // act == 0 entries are skipped, as in pion_eval
+            if (v1 != 0.0) a1 = fma(p1, v1, a1);
+            if (v2 != 0.0) a0 = fma(p2, v2, a0);
+            if (v3 != 0.0) a1 = fma(p3, v3, a1);
+        }
         for (; e + 32 < PG_N; e += 64) {
             const double p0 = __ldg(row + e), p1 = __ldg(row + e + 32);
             const double v0 = P.Wt[e], v1 = P.Wt[e + 32];
-            if (v0 != 0.0) a0 = fma(p0, v0, a0);            // act == 0 entries are skipped, as in pion_eval
+            if (v0 != 0.0) a0 = fma(p0, v0, a0);
             if (v1 != 0.0) a1 = fma(p1, v1, a1);
         }
         for (; e < PG_N; e += 32) { const double v0 = P.Wt[e]; if (v0 != 0.0) a0 = fma(__ldg(row + e), v0, a0); }
@@ -498,28 +539,31 @@ __global__ void __launch_bounds__(HAD_NT) loss_table_kernel(HadTabArgs A) {
 // dg_dt_pg at every midpoint with the table (one warp per midpoint); the caller has staged lx = log10(h nu) in H.lxpg and
 // lp = log10(photons / h) in H.lppg
 template <int NT>
-__device__ void phase_loss_pg_tab(const Ctx& C, SmemLh& H, const HadTabs& Tw, int nloss) {
+__device__ void phase_loss_pg_tab(const Ctx& C, Smem& S, SmemLh& H, const HadTabs& Tw, int nloss) {
     const double* __restrict__ lx = H.lxpg;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, Nt = C.L.Nt;
+    tab_interp_stage<NT>(lx, H.lppg, Nt, H.isl, H.if0);
+    __syncthreads();
     for (int k = warp; k < nloss; k += NT / 32) {
         const double* __restrict__ Ak = Tw.lossA + (size_t)k * LOSS_N;
         const double* __restrict__ dk = Tw.lossdx + (size_t)k * LOSS_N;
         const int* __restrict__ ck = Tw.losscode + (size_t)k * LOSS_N;
-        double s0 = 0.0, s1 = 0.0;
-        for (int m = lane; m < LOSS_N; m += 64) {
-            const double A0 = __ldg(Ak + m);
-            if (A0 != 0.0) {
-                const int code = __ldg(ck + m);
-                const int jx = min(code >> 1, Nt - 2);
-                s0 = fma(A0, exp10(interp_eval(H.lppg, code, __ldg(dk + m), lx[jx + 1] - lx[jx])), s0);
+        double s0 = 0.0, s1 = 0.0;                            // s0: samples m = lane (mod 64), s1: lane + 32 (mod 64)
+        constexpr int LU = 8;                                 // samples per lane and round, all loads first
+        for (int m = lane; m < LOSS_N; m += 32 * LU) {
+            double A[LU], dx[LU];
+            int code[LU];
+#pragma unroll
+            for (int u = 0; u < LU; ++u) {
+                const int mm = m + 32 * u;
+                const bool in = mm < LOSS_N;
+                A[u] = in ? __ldg(Ak + mm) : 0.0; code[u] = in ? __ldg(ck + mm) : 0; dx[u] = in ? __ldg(dk + mm) : 0.0;
             }
-            const int m1 = m + 32;
-            if (m1 < LOSS_N) {
-                const double A1 = __ldg(Ak + m1);
-                if (A1 != 0.0) {
-                    const int code = __ldg(ck + m1);
-                    const int jx = min(code >> 1, Nt - 2);
-                    s1 = fma(A1, exp10(interp_eval(H.lppg, code, __ldg(dk + m1), lx[jx + 1] - lx[jx])), s1);
+#pragma unroll
+            for (int u = 0; u < LU; ++u) {
+                if (A[u] != 0.0) {
+                    const double v = tab_interp_pow10(lx, H.lppg, Nt, H.isl, H.if0, S.e2tab, code[u], dx[u]);
+                    if (u & 1) s1 = fma(A[u], v, s1); else s0 = fma(A[u], v, s0);
                 }
             }
         }

@@ -85,6 +85,7 @@ struct SmemLh {
     double *Qpi, *Qpg;                 // [Ng] photopion pairs (e+ + e-), [Ni] photopion photons
     double *Qnu, *Nnu, *Enu;           // [52] neutrino source x dt, neutrino state, E_nu_space (50 used)
     double *lxpg, *lppg;               // [Nt] log10(h nu), log10(photons/h)
+    double *isl, *if0;                 // [Nt] per-bracket slope and left ordinate (x log2 10) of the field a tabulated phase samples
     double *ltab;                      // loss tables (LossTab)
     double *work;                      // pion_eval work area
     double *bhbuf, *npl, *Qbh, *bhsurf; // [BH_CH*Np] scratch, [Np] dN_pr/dV, [Ng] Q_BH_sol, staged spline surfaces
@@ -92,7 +93,7 @@ struct SmemLh {
 };
 constexpr int HAD_MAXTAB = 32, HAD_MAXLOSS = 2 * (128 + 64 + 128), BH_MAXSURF = 2048;
 __host__ __device__ inline size_t smem_lh_had_doubles(const Layout& L) {
-    return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 2 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB)
+    return (size_t)3 * pad2(L.Np) + pad2(L.Ng) + pad2(L.Ni) + 3 * 52 + 4 * pad2(L.Nt) + HAD_MAXLOSS + pion_work_doubles(HAD_MAXTAB)
            + (size_t)BH_CH * pad2(L.Np) + 2 * pad2(L.Np) + pad2(L.Ng) + BH_MAXSURF;
 }
 __host__ __device__ inline size_t smem_lh_doubles(const Layout& L) {
@@ -107,6 +108,7 @@ __device__ inline void carve_lh(SmemLh& H, double* p, const Layout& L, const Sme
     H.Qpi = take(pad2(L.Ng)); H.Qpg = take(pad2(L.Ni));
     H.Qnu = take(52); H.Nnu = take(52); H.Enu = take(52);
     H.lxpg = take(pad2(L.Nt)); H.lppg = take(pad2(L.Nt));
+    H.isl = take(pad2(L.Nt)); H.if0 = take(pad2(L.Nt));
     H.ltab = take(HAD_MAXLOSS); H.work = take((int)pion_work_doubles(HAD_MAXTAB));     // only valid when the handle
     H.bhbuf = take(BH_CH * pad2(L.Np)); H.npl = take(pad2(L.Np)); H.Qbh = take(pad2(L.Ng)); H.bhw = take(pad2(L.Np));
     H.bhsurf = p;                                                                        // reserved smem_lh_had_doubles
