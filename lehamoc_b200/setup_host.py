@@ -79,6 +79,22 @@ class Batch:
     def arrays(self):
         return (self.consts, self.g_el, self.nu_syn, self.nu_ic, self.nu_tot, self.el_inj, self.ext)
 
+    def pin(self):
+        """Move the arrays into page-locked memory (torch pinned tensors, kept alive by this object): Engine.setup's H2D
+        copies then are asynchronous DMA transfers instead of staged copies out of pageable memory, and broadcast views
+        of shared grids are materialised once instead of on every set-up."""
+        import torch
+        keep = self.__dict__.setdefault("_pins", {})
+        for name in ("consts", "g_el", "nu_syn", "nu_ic", "nu_tot", "el_inj", "ext", "g_pr", "pr_inj"):
+            a = getattr(self, name)
+            if a is None or name in keep:
+                continue
+            t = torch.empty(a.shape, dtype=torch.float64, pin_memory=True)
+            t.numpy()[...] = a
+            keep[name] = t
+            setattr(self, name, t.numpy())
+        return self
+
 
 def _nu_c(gamma, B):                               # LeHaMoC_f.py:78-79
     return 3. / (4. * np.pi) * q * B / (m_el * c) * gamma ** 2.
