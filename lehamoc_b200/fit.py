@@ -253,11 +253,14 @@ def log_probability(theta, x, y, yerr, yerr1, flags, flag_c):
 # ---------------------------------------------------------------------------------------------------------
 # ensemble sampler: stretch move with emcee's red/blue split (emcee.moves.RedBlueMove / StretchMove, a = 2)
 # ---------------------------------------------------------------------------------------------------------
-def run_mcmc(log_prob_fn, pos, nsteps, seed=0, a=2.0, progress=False, chain_file=None):
+def run_mcmc(log_prob_fn, pos, nsteps, seed=0, a=2.0, progress=False, chain_file=None, checkpoint_every=0):
     """Advance an ensemble `pos` [nwalkers, ndim] for `nsteps` iterations.  `log_prob_fn(thetas[n, ndim]) -> [n]`
     is called with half an ensemble at a time (emcee's vectorize=True call pattern).  Every rank of a
     `torch.distributed` job must call this with the same arguments: the proposal RNG is seeded identically, so all
     ranks hold the same chain and only `log_prob_fn` is sharded.
+    A NaN log-probability of a proposal raises, like emcee does ("Probability function returned NaN").  With
+    `chain_file` and `checkpoint_every = N` rank 0 rewrites the file every N iterations (the iterations done so far), so a
+    crash does not lose the run -- the role of the reference's HDF backend (fit_emcee.py:229-233).
     Returns dict(chain [nsteps, nwalkers, ndim], log_prob [nsteps, nwalkers], accepted [nwalkers])."""
     rng = np.random.default_rng(seed)
     p = np.array(pos, dtype=np.float64)
@@ -283,6 +286,8 @@ def run_mcmc(log_prob_fn, pos, nsteps, seed=0, a=2.0, progress=False, chain_file
             rint = rng.integers(Nc, size=Ns)
             q = c[rint] - (c[rint] - s) * zz[:, None]
             new_lp = np.asarray(log_prob_fn(q), dtype=np.float64)
+            if np.any(np.isnan(new_lp)):
+                raise ValueError("Probability function returned NaN")          # emcee's behaviour and message
             lnpdiff = factors + new_lp - lp[S1]
             acc = lnpdiff > np.log(rng.random(Ns))
             idx = np.where(S1)[0][acc]
@@ -291,14 +296,42 @@ def run_mcmc(log_prob_fn, pos, nsteps, seed=0, a=2.0, progress=False, chain_file
             accepted[idx] += 1
         chain[it] = p
         lps[it] = lp
+        if chain_file and checkpoint_every and (it + 1) % checkpoint_every == 0 and it + 1 < nsteps \
+                and shard.world()[0] == 0:
+            _save_chain(chain_file, chain[:it + 1], lps[:it + 1], accepted, it + 1)
         if progress and shard.world()[0] == 0:
             print(f"\r{it + 1}/{nsteps}  max logp {lp.max():.3f}  {time.time() - t0:.1f} s", end="", flush=True)
     if progress and shard.world()[0] == 0:
         print()
     out = dict(chain=chain, log_prob=lps, accepted=accepted, acceptance_fraction=accepted / max(nsteps, 1))
     if chain_file and shard.world()[0] == 0:
-        np.savez_compressed(chain_file, **out)
+        _save_chain(chain_file, chain, lps, accepted, nsteps)
     return out
+
+
+def _save_chain(chain_file, chain, lps, accepted, done):
+    """Atomic rewrite (temporary file + rename): a reader or a crash never sees a half-written chain."""
+    tmp = chain_file + ".tmp.npz"
+    np.savez_compressed(tmp, chain=chain, log_prob=lps, accepted=accepted, acceptance_fraction=accepted / max(done, 1),
+                        iterations=done)
+    os.replace(tmp, chain_file)
+
+
+def chain_directory(base):
+    """fit_emcee.py:38-58: create `base`; if it exists create `base_1`, `base_2`, ... so that the chains of earlier
+    runs are never overwritten.  Returns the directory created."""
+    try:
+        os.makedirs(base)
+        return base
+    except FileExistsError:
+        suffix = 1
+        while True:
+            cand = f"{base}_{suffix}"
+            try:
+                os.makedirs(cand, exist_ok=False)
+                return cand
+            except OSError:
+                suffix += 1
 
 
 def main(argv=None):
@@ -312,8 +345,20 @@ def main(argv=None):
         print('python -m lehamoc_b200.fit LeMoC 1000 _folderName')
         return 1
     flag_c, steps = argv[1], int(argv[2])
+    # one process per GPU under torchrun: the walkers of every half-ensemble are sharded over the ranks (shard.py), all
+    # ranks hold the same chain, rank 0 writes it
+    if int(os.environ.get("WORLD_SIZE", "1")) > 1 and not torch.distributed.is_initialized():
+        torch.cuda.set_device(int(os.environ.get("LOCAL_RANK", "0")))
+        torch.distributed.init_process_group("nccl")
+    rank, world_size = shard.world()
     directory = 'chains' + argv[3] + '/' + flag_c
-    os.makedirs(directory, exist_ok=True)
+    if rank == 0:
+        directory = chain_directory(directory)
+        print("Directory '%s' created successfully" % directory)
+    if world_size > 1:
+        box = [directory]
+        torch.distributed.broadcast_object_list(box, src=0)
+        directory = box[0]
     if flag_c == 'LeMoC':
         params = [15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3]               # fit_emcee.py:208
     else:
@@ -323,9 +368,14 @@ def main(argv=None):
     pos = init + 1e-2 * np.random.default_rng(0).standard_normal((48, len(init)))   # fit_emcee.py:224-225
     start = time.perf_counter()
     fn = lambda th: log_probability_batch(th, xd, yd, yderr_hi, yderr_lo, flags, flag_c)
-    res = run_mcmc(fn, pos, steps, progress=True, chain_file=os.path.join(directory, "out.npz"))
-    print("GPU batch evaluation took {0:.1f} seconds".format(time.perf_counter() - start))
-    print("mean acceptance fraction {0:.3f}".format(float(np.mean(res["acceptance_fraction"]))))
+    res = run_mcmc(fn, pos, steps, progress=True, chain_file=os.path.join(directory, "out.npz"),
+                   checkpoint_every=max(1, min(100, steps // 10)))
+    if rank == 0:
+        print("GPU batch evaluation took {0:.1f} seconds".format(time.perf_counter() - start))
+        print("mean acceptance fraction {0:.3f}".format(float(np.mean(res["acceptance_fraction"]))))
+    if world_size > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
     return 0
 
 

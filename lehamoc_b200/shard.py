@@ -70,9 +70,24 @@ def evaluate_sharded(fn, thetas, device=None, group=None):
     W = thetas.shape[0]
     rank, ws = world()
     a, b = block_range(W, ws, rank)
-    rows = fn(thetas[a:b])
     if ws == 1:
+        rows = fn(thetas[a:b])
         return rows.detach().cpu().numpy() if isinstance(rows, torch.Tensor) else np.asarray(rows)
+    # a rank whose block fails (e.g. a packer ValueError for one of ITS walkers) must not leave the others waiting in
+    # the all-gather: every rank first learns whether all blocks were evaluated, then all raise together
+    err = None
+    try:
+        rows = fn(thetas[a:b])
+    except Exception as e:                                  # noqa: BLE001 -- re-raised below, on every rank
+        err, rows = e, None
+    nccl = dist.get_backend(group) == "nccl"
+    flag_dev = (device if device is not None else torch.device("cuda", torch.cuda.current_device())) if nccl else "cpu"
+    flag = torch.tensor([1 if err is not None else 0], dtype=torch.int32, device=flag_dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    if int(flag.item()):
+        if err is not None:
+            raise err
+        raise RuntimeError("evaluate_sharded: another rank failed to evaluate its block of walkers")
     t = rows if isinstance(rows, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(rows))
     if t.dim() == 0 or t.shape[0] != b - a:
         raise ValueError("fn must return one row per walker of its block")

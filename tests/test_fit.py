@@ -72,6 +72,37 @@ def test_sampler_recovers_gaussian():
         fit.run_mcmc(logp, pos[:5], 10)
 
 
+def test_sampler_nan_checkpoints_and_chain_directories(tmp_path):
+    """emcee's behaviours the CLI relies on: a NaN log-probability raises; the chain file is rewritten every N iterations
+    (a crash does not lose the run); chain directories get a numeric suffix instead of being overwritten
+    (fit_emcee.py:38-58)."""
+    from lehamoc_b200 import fit
+    rng = np.random.default_rng(2)
+    pos = rng.standard_normal((8, 2))
+    calls = [0]
+
+    def logp(th):
+        calls[0] += 1
+        out = -0.5 * np.sum(th ** 2, axis=1)
+        if calls[0] == 12:
+            out[0] = np.nan
+        return out
+    f = str(tmp_path / "out.npz")
+    with pytest.raises(ValueError, match="Probability function returned NaN"):
+        fit.run_mcmc(logp, pos, 50, seed=1, chain_file=f, checkpoint_every=2)
+    z = np.load(f)                                             # the checkpoint written before the failure
+    assert int(z["iterations"]) == 4 and z["chain"].shape == (4, 8, 2)
+    ok = fit.run_mcmc(lambda th: -0.5 * np.sum(th ** 2, axis=1), pos, 4, seed=1)
+    np.testing.assert_array_equal(z["chain"], ok["chain"])
+    with pytest.raises(ValueError, match="initial ensemble"):
+        fit.run_mcmc(lambda th: np.full(len(th), np.nan), pos, 2)
+    base = str(tmp_path / "chains_x" / "LeMoC")
+    assert fit.chain_directory(base) == base
+    assert fit.chain_directory(base) == base + "_1"
+    assert fit.chain_directory(base) == base + "_2"
+    assert os.path.isdir(base + "_2")
+
+
 # ---- GPU: the CUDA epilogue against the reference's numbers --------------------------------------------------
 @pytest.mark.gpu
 @pytest.mark.parametrize("device_pack", [False, True])

@@ -79,3 +79,38 @@ def test_world2_gather_and_mcmc(tmp_path, W):
         single = fit.run_mcmc(lambda th: _fake_model(th)[:, -1], thetas, 20, seed=11)["chain"]
         for r in range(ws):
             np.testing.assert_array_equal(np.load(tmp_path / f"chain_{W}_{r}.npy"), single)
+
+
+def _failing_worker(rank, ws, port, out_dir):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(ws))
+    dist.init_process_group("gloo", rank=rank, world_size=ws)
+    try:
+        from lehamoc_b200 import shard as sh
+
+        def fn(block):
+            if rank == 1:
+                raise ValueError("walker outside the gamma grid")
+            return _fake_model(block)
+        try:
+            sh.evaluate_sharded(fn, np.zeros((6, 3)))
+            what = "returned"
+        except ValueError as e:
+            what = f"ValueError: {e}"
+        except RuntimeError as e:
+            what = f"RuntimeError: {e}"
+        with open(os.path.join(out_dir, f"outcome_{rank}.txt"), "w") as f:
+            f.write(what)
+        # the group is still usable afterwards
+        np.save(os.path.join(out_dir, f"after_{rank}.npy"), sh.evaluate_sharded(_fake_model, np.ones((4, 3))))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_world2_failure_on_one_rank_raises_on_all(tmp_path):
+    """A rank whose block cannot be evaluated must not leave the others hanging in the all-gather: the failing rank
+    re-raises its own exception, the others raise a RuntimeError, and the process group stays usable."""
+    mp.spawn(_failing_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
+    assert (tmp_path / "outcome_0.txt").read_text().startswith("RuntimeError: evaluate_sharded: another rank failed")
+    assert (tmp_path / "outcome_1.txt").read_text() == "ValueError: walker outside the gamma grid"
+    for r in range(2):
+        np.testing.assert_array_equal(np.load(tmp_path / f"after_{r}.npy"), _fake_model(np.ones((4, 3))))
