@@ -60,6 +60,7 @@ __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlag
     C.TI = tabi + (size_t)w * L.n_ints;
     C.E = Ecache ? Ecache + (size_t)w * (L.Ns + L.Ni) * L.Ng : nullptr;
     C.P = ptab ? ptab + (ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)) : nullptr;
+    C.ggK = nullptr; C.ggT = nullptr; C.ggJ = nullptr; C.gg_rows = 0;
     const double* c = consts + (size_t)w * LHM_NCONST;
     C.R0 = c[LHM_C_R0]; C.B0 = c[LHM_C_B0]; C.m = c[LHM_C_M]; C.Vexp = c[LHM_C_VEXP];
     C.dt = c[LHM_C_DT]; C.tinit = c[LHM_C_TINIT];
@@ -199,6 +200,7 @@ struct GArgs {
     const double* part;     // [NGC][Wpad][NoPad]
     int step;               // timesteps whose first half has run before this launch
     int do_B, do_A;
+    const double* ggK; const double* ggT; const int* ggJ; int gg_rows;     // gamma-gamma sample table of the batch (gg_table_kernel)
 };
 
 __device__ __forceinline__ void set_time(Ctx& C, double t) {                 // LeMoC.py:198-201
@@ -221,6 +223,52 @@ __device__ void g_prepare(const Ctx& C, Smem& S) {
     __syncthreads();
 }
 
+// Shared-grid batches: the sample geometry of every gamma-gamma row (bracket, position, static factor -- what
+// gg_row_samples emits) is the same for all walkers, so it is tabulated once per batch from walker 0's tables.  Row order:
+// leptonic drivers a_gg on nu_ic [Ni], Q_ee_f [Ng-1]; LeHaMoC.py a_gg on nu_ic, nu_syn, nu_tot [Ni+Ns+Nt], Q_ee_f [Ng] --
+// the nu_syn rows of the latter are place-holders: that grid follows the walker's B0, phase_gg_lh evaluates them directly.
+struct GgTabArgs {
+    Layout L; int lh; int rows;
+    const double* tabd;                     // walker 0's double tables
+    double* K; double* T; int* J;           // [gg_batches(NP)*GG_U][rows]
+};
+__host__ __device__ inline int gg_table_rows(const Layout& L, bool lh) {
+    return lh ? L.Ni + L.Ns + L.Nt + L.Ng : L.Ni + L.Ng - 1;
+}
+__global__ void __launch_bounds__(256) gg_table_kernel(GgTabArgs A) {
+    extern __shared__ __align__(16) double sm_gt[];
+    const Layout& L = A.L;
+    const int Nt = L.Nt, NP = L.NP, Ni = L.Ni, Ns = L.Ns;
+    Smem S;
+    S.lxtS = sm_gt; S.ilxS = sm_gt + Nt;
+    for (int i = threadIdx.x; i < Nt; i += blockDim.x) {
+        S.lxtS[i] = A.tabd[L.lxt + i];
+        S.ilxS[i] = (i < Nt - 1) ? 1.0 / (A.tabd[L.lxt + i + 1] - A.tabd[L.lxt + i]) : 0.0;      // as g_prepare / ic_prepare
+    }
+    __syncthreads();
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= A.rows) return;
+    int r, oa, od, oc, orr; bool is_a = true;
+    const int n1 = A.lh ? Ni + Ns + Nt : Ni;
+    if (row < Ni) { r = row; oa = L.agg_a; od = L.agg_d; oc = L.agg_c; orr = L.agg_r2; }
+    else if (row < n1 && row < Ni + Ns) { r = row - Ni; oa = L.ags_a; od = L.ags_d; oc = L.ags_c; orr = L.ags_r2; }
+    else if (row < n1) { r = row - Ni - Ns; oa = L.agt_a; od = L.agt_d; oc = L.agt_c; orr = L.agt_r2; }
+    else { r = row - n1; oa = L.qee_a; od = L.qee_d; oc = L.qee_c; orr = L.qee_r2; is_a = false; }
+    const int nsamp = gg_batches(NP) * GG_U;
+    for (int e = 0; e < nsamp; ++e) {                       // rows that are switched off (step <= 0) emit nothing: zeros
+        const size_t o = (size_t)e * A.rows + row;
+        A.K[o] = 0.0; A.T[o] = 0.0; A.J[o] = 0;
+    }
+    gg_row_samples(S, Nt, NP, A.tabd[oa + r], A.tabd[od + r], A.tabd[oc + r], A.tabd[orr + r], is_a,
+                   [&](int e0, const int (&j)[GG_U], const double (&t)[GG_U], const double (&Kv)[GG_U]) {
+#pragma unroll
+                       for (int u = 0; u < GG_U; ++u) {
+                           const size_t o = (size_t)(e0 + u) * A.rows + row;
+                           A.K[o] = Kv[u]; A.T[o] = t[u]; A.J[o] = j[u];
+                       }
+                   });
+}
+
 // MINB resident CTAs per SM: without the IC body the half-step phases fit 80 (MINB 3) or 64 (MINB 4) registers
 template <int MINB>
 __global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
@@ -232,6 +280,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
     carve(S, smem_raw, A.L, NW);
     Ctx C;
     load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
+    C.ggK = G.ggK; C.ggT = G.ggT; C.ggJ = G.ggJ; C.gg_rows = G.gg_rows;
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -374,6 +423,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_lh_kernel(GArgs G) {
     carve_lh(H, smem_raw + (smem_bytes(A.L, NW) + 15) / 16 * 2, A.L, S);
     Ctx C;
     load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
+    C.ggK = G.ggK; C.ggT = G.ggT; C.ggJ = G.ggJ; C.gg_rows = G.gg_rows;
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -916,6 +966,7 @@ struct lhm_handle {
     double* d_Nout;
     double* d_sed;
     // lhm_fit_logl_host: pinned staging (in | out), device input row block, packed [W, n] arrays, SEDs, likelihoods
+    double* d_ggK; double* d_ggT; int* d_ggJ; int gg_rows;      // path G: gamma-gamma sample table of the batch
     double* fit_pin; double* fit_din; double* fit_arr; double* fit_sed; double* fit_logl; size_t fit_cap;
     size_t Nout_cap, sed_cap;
     unsigned long long* d_prof;   // optional per-phase cycle counters (lhm_set_phase_profile)
@@ -1048,6 +1099,13 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
             CUDA_TRY(cudaMemset(h->d_gav, 0, Wp * D.NgP * sizeof(double)));
             CUDA_TRY(cudaMalloc(&h->d_part, (size_t)D.NGC * Wp * D.NoPad * sizeof(double)));
             CUDA_TRY(cudaMalloc(&h->d_state, W * (size_t)gstate_layout(h->L).total * sizeof(double)));
+            if (cfg->gg_flag) {
+                h->gg_rows = gg_table_rows(h->L, cfg->driver == 1);
+                const size_t n = (size_t)gg_batches(cfg->gg_npts) * GG_U * h->gg_rows;
+                CUDA_TRY(cudaMalloc(&h->d_ggK, n * sizeof(double)));
+                CUDA_TRY(cudaMalloc(&h->d_ggT, n * sizeof(double)));
+                CUDA_TRY(cudaMalloc(&h->d_ggJ, n * sizeof(int)));
+            }
             for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) CUDA_TRY(cudaEventCreate(&h->evg[i]));
         }
     }
@@ -1088,6 +1146,7 @@ void lhm_destroy(lhm_handle* h) {
     cudaFree(h->fit_din); cudaFree(h->fit_arr); cudaFree(h->fit_sed); cudaFree(h->fit_logl);
     cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
     cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
+    cudaFree(h->d_ggK); cudaFree(h->d_ggT); cudaFree(h->d_ggJ);
     free_had_tabs(h);
     for (int i = 0; i < 2; ++i) if (h->ev_tab[i]) cudaEventDestroy(h->ev_tab[i]);
     for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) if (h->evg[i]) cudaEventDestroy(h->evg[i]);
@@ -1222,6 +1281,14 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
         icg_tasks_kernel<<<1, 256, 0, h->stream>>>(G);
         g_launches += 2;
         CUDA_TRY(cudaGetLastError());
+        if (h->d_ggK) {
+            GgTabArgs T;
+            T.L = h->L; T.lh = h->cfg.driver == 1; T.rows = h->gg_rows; T.tabd = h->d_tabd;
+            T.K = h->d_ggK; T.T = h->d_ggT; T.J = h->d_ggJ;
+            gg_table_kernel<<<(T.rows + 255) / 256, 256, 2 * (size_t)h->L.Nt * sizeof(double), h->stream>>>(T);
+            g_launches++;
+            CUDA_TRY(cudaGetLastError());
+        }
     }
     CUDA_TRY(cudaEventRecord(h->ev[1], h->stream));
     h->ev_set[0] = true;
@@ -1349,6 +1416,7 @@ static int run_pathG(lhm_handle* h, const RunArgs& A) {
     GArgs G;
     G.R = A; G.D = h->GD; G.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
     G.state = h->d_state; G.gp = h->d_gp; G.gav = h->d_gav; G.part = h->d_part;
+    G.ggK = h->d_ggK; G.ggT = h->d_ggT; G.ggJ = h->d_ggJ; G.gg_rows = h->gg_rows;
     static const int minb = [] { const char* e = std::getenv("LHM_G_CTAS"); const int v = e ? std::atoi(e) : 0; return (v >= 2 && v <= 4) ? v : LHM_G_DEFAULT_CTAS; }();
     void (*kern)(GArgs) = minb == 4 ? stepG_kernel<4> : minb == 3 ? stepG_kernel<3> : stepG_kernel<2>;
     std::atomic<size_t>* smem_slot = &g_smem_stepg[h->device % MAX_DEV];

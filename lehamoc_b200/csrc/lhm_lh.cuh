@@ -456,8 +456,11 @@ __device__ void phase_gg_lh(const Ctx& C, Smem& S, SmemLh& H, int interv) {
         if (row < Ni) { r = row; oa = L.agg_a; od = L.agg_d; oc = L.agg_c; orr = L.agg_r2; out = S.agg; }
         else if (row < Ni + Ns) { r = row - Ni; oa = L.ags_a; od = L.ags_d; oc = L.ags_c; orr = L.ags_r2; out = H.aggS; }
         else { r = row - Ni - Ns; oa = L.agt_a; od = L.agt_d; oc = L.agt_c; orr = L.agt_r2; out = H.atmp; }
-        out[r] = gg_row_sum(S, S.Lm, Nt, NP, __ldg(C.T + oa + r), __ldg(C.T + od + r), __ldg(C.T + oc + r),
-                            __ldg(C.T + orr + r), true);
+        // the nu_syn grid follows the walker's B0 (LeHaMoC.py:160): its rows are not in the batch-wide sample table
+        const bool tab = C.ggK && !(row >= Ni && row < Ni + Ns);
+        out[r] = tab ? gg_row_sum_tab(S, S.Lm, NP, C.ggK, C.ggT, C.ggJ, C.gg_rows, row)
+                       : gg_row_sum(S, S.Lm, Nt, NP, __ldg(C.T + oa + r), __ldg(C.T + od + r), __ldg(C.T + oc + r),
+                                    __ldg(C.T + orr + r), true);
     }
     __syncthreads();
     for (int k = tid; k < Nt; k += NT) {
@@ -471,8 +474,9 @@ __device__ void phase_gg_lh(const Ctx& C, Smem& S, SmemLh& H, int interv) {
     }
     __syncthreads();
     for (int r = tid; r < Ng; r += NT) {                            // Q_ee_f, full length; the driver uses [1:-1]
-        const double s = gg_row_sum(S, H.Lm2, Nt, NP, __ldg(C.T + L.qee_a + r), __ldg(C.T + L.qee_d + r),
-                                    __ldg(C.T + L.qee_c + r), __ldg(C.T + L.qee_r2 + r), false);
+        const double s = C.ggK ? gg_row_sum_tab(S, H.Lm2, NP, C.ggK, C.ggT, C.ggJ, C.gg_rows, nrows + r)
+                               : gg_row_sum(S, H.Lm2, Nt, NP, __ldg(C.T + L.qee_a + r), __ldg(C.T + L.qee_d + r),
+                                            __ldg(C.T + L.qee_c + r), __ldg(C.T + L.qee_r2 + r), false);
         double ng = 0.0;
         if (2.0 * S.gS[r] > 1.0)
             ng = exp10(interp_eval(H.Ln2, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));

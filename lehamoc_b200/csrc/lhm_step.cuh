@@ -119,6 +119,8 @@ struct Ctx {
     const int* TI;        // int tables of this walker
     const double* E;      // [(Ns+Ni), Ng] exp(-nu/nu_c(gamma,B)) of this walker when B is constant in time, else null
     const double2* P;     // IC pair table of this walker (ic_fill_pair_table), or null: recompute per step
+    // shared-grid batches (path G): the per-sample geometry of the gamma-gamma rows, tabulated once per batch, or null
+    const double* ggK; const double* ggT; const int* ggJ; int gg_rows;      // [gg_batches*GG_U][gg_rows] each
     StepFlags F;
     double R0, B0, m, Vexp, dt, tinit;
     double Rad, B, V;     // current step
@@ -700,75 +702,118 @@ __device__ __forceinline__ double fast_exp2(double x, const double* __restrict__
 // photon field (x mc^2/h), so 10**np.interp(log10 ...) becomes fast_exp2 of the same linear interpolant.
 // `Lng` gives n_g: log10 of the field Q_ee_f's n_g is interpolated from.
 constexpr int GG_U = 4;
+__host__ __device__ inline int gg_batches(int NP) { return (NP + GG_U - 1) / GG_U; }
+
+// The grid-only part of a row: for every batch of GG_U samples e0..e0+GG_U-1 the np.interp bracket j, the position t in
+// it and the static factor Kv = w_e * cf * (1 - s_e^-2) * ln s_e, handed to emit(e0, j, t, Kv).  y_e = a + e*step.
+template <class Emit>
+__device__ __forceinline__ void gg_row_samples(const Smem& S, int Nt, int NP, double a, double step, double cf, double r2,
+                                               bool is_a, Emit&& emit) {
+    const double* __restrict__ lxt = S.lxtS;
+    const double* __restrict__ ilx = S.ilxS;
+    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
+    const double invD = (double)(Nt - 1) / (lxN - lx0);
+    const double LN10 = 2.302585092994045684, LN13 = 0.262364264467491052;     // ln 10, ln 1.3
+    if (!(step > 0.0)) return;              // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
+    const double dl = step * LN10;                      // spacing of ln x' = trapezoid weight of inner samples
+    const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
+    double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
+    inv[0] = is_a ? (1.0 / 1.69) : 1.0;
+#pragma unroll
+    for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
+    double rU = r2;
+#pragma unroll
+    for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
+    const double dlcf = dl * cf;                        // weight of an interior sample x the row's prefactor
+    double ed[GG_U];
+#pragma unroll
+    for (int u = 0; u < GG_U; ++u) ed[u] = (double)u;
+    for (int e0 = 0; e0 < NP; e0 += GG_U) {
+        double y[GG_U], Kv[GG_U], t[GG_U];
+        int j[GG_U];
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) {
+            y[u] = fma(ed[u], step, a);
+            Kv[u] = dlcf * (1.0 - inv[u]) * fma(ed[u], dl, lns0);
+            inv[u] *= rU;
+            ed[u] += (double)GG_U;
+        }
+        // trapezoid end weights and the exact last abscissa: only the first and the last batch (uniform branches)
+        if (e0 == 0) Kv[0] *= 0.5;
+        if (e0 + GG_U >= NP) {
+#pragma unroll
+            for (int u = 0; u < GG_U; ++u) {
+                const int e = e0 + u;
+                if (e == NP - 1) { y[u] = lxN; Kv[u] *= 0.5; }
+                else if (e >= NP) { y[u] = lxN; Kv[u] = 0.0; }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) {
+            y[u] = fmax(y[u], lx0);                         // np.interp clamps below the grid (t = 0 in segment 0)
+            int jj = (int)((y[u] - lx0) * invD);            // both grids are log-uniform: the guess is right
+            jj = max(0, min(jj, Nt - 2));                   // except next to a node ...
+            double lo = lxt[jj];
+            if (!(y[u] >= lo && y[u] < lxt[jj + 1])) {      // ... where it is corrected against the actual doubles
+                while (jj > 0 && y[u] < lxt[jj]) --jj;
+                while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
+                lo = lxt[jj];
+            }
+            j[u] = jj;
+            t[u] = (y[u] - lo) * ilx[jj];
+        }
+        emit(e0, j, t, Kv);
+    }
+}
+
+// the state-dependent part of a batch: acc[u] += Kv[u] * 2^(interp of Lm at sample u)
+__device__ __forceinline__ void gg_batch_acc(const double* __restrict__ Lm, const double* __restrict__ tab,
+                                             const int (&j)[GG_U], const double (&t)[GG_U], const double (&Kv)[GG_U],
+                                             double (&acc)[GG_U]) {
+    double Lv[GG_U];
+#pragma unroll
+    for (int u = 0; u < GG_U; ++u) {
+        const double f0 = Lm[j[u]], f1 = Lm[j[u] + 1];
+        Lv[u] = fma(t[u], f1 - f0, f0);                     // NaN (from -inf ordinates) -> 0 inside fast_exp2
+    }
+#pragma unroll
+    for (int u = 0; u < GG_U; ++u) acc[u] = fma(Kv[u], fast_exp2(Lv[u], tab), acc[u]);
+}
 
 // one row: sum_k w_k * cf * (1 - s_k^-2) * ln s_k * 2^(interp of Lm at y_k),  y_k = a + k*step, k = 0..NP-1
 __device__ __forceinline__ double gg_row_sum(const Smem& S, const double* __restrict__ Lm, int Nt, int NP, double a,
                                              double step, double cf, double r2, bool is_a) {
-    const double* __restrict__ lxt = S.lxtS;
-    const double* __restrict__ ilx = S.ilxS;
-    const double* __restrict__ tab = S.e2tab;
-    const double lx0 = lxt[0], lxN = lxt[Nt - 1];
-    const double invD = (double)(Nt - 1) / (lxN - lx0);
-    const double LN10 = 2.302585092994045684, LN13 = 0.262364264467491052;     // ln 10, ln 1.3
     double acc[GG_U];
 #pragma unroll
     for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
-    if (step > 0.0) {                       // x_space[0] < x_space[1]  (LeHaMoC_f.py:133); else the row is 0
-        const double dl = step * LN10;                      // spacing of ln x' = trapezoid weight of inner samples
-        const double lns0 = is_a ? LN13 : 0.0;              // ln s_0
-        double inv[GG_U];                                   // s_e^-2 = s_0^-2 * r2^e
-        inv[0] = is_a ? (1.0 / 1.69) : 1.0;
+    gg_row_samples(S, Nt, NP, a, step, cf, r2, is_a,
+                   [&](int, const int (&j)[GG_U], const double (&t)[GG_U], const double (&Kv)[GG_U]) {
+                       gg_batch_acc(Lm, S.e2tab, j, t, Kv, acc);
+                   });
+    double s = acc[0];
 #pragma unroll
-        for (int u = 1; u < GG_U; ++u) inv[u] = inv[u - 1] * r2;
-        double rU = r2;
+    for (int u = 1; u < GG_U; ++u) s += acc[u];
+    return s;
+}
+
+// the same row from the batch-wide table of its sample geometry (shared-grid batches: what gg_row_samples emits does not
+// depend on the walker, so it is stored once per batch -- [sample][row], coalesced over the rows of a warp -- and a
+// sample costs two shared-memory reads, one FMA and the staged 2^x instead of ~20 further FP64 instructions).  Same
+// numbers in the same order as gg_row_sum: bit-identical.
+__device__ __forceinline__ double gg_row_sum_tab(const Smem& S, const double* __restrict__ Lm, int NP, const double* __restrict__ gK,
+                                                 const double* __restrict__ gT, const int* __restrict__ gJ, int stride, int row) {
+    double acc[GG_U];
 #pragma unroll
-        for (int u = 1; u < GG_U; ++u) rU *= r2;            // r2^GG_U
-        const double dlcf = dl * cf;                        // weight of an interior sample x the row's prefactor
-        double ed[GG_U];
+    for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
+    const int nb = gg_batches(NP);
+    for (int b = 0; b < nb; ++b) {
+        int j[GG_U]; double t[GG_U], Kv[GG_U];
 #pragma unroll
-        for (int u = 0; u < GG_U; ++u) ed[u] = (double)u;
-        for (int e0 = 0; e0 < NP; e0 += GG_U) {
-            double y[GG_U], Kv[GG_U], t[GG_U], Lv[GG_U];
-            int j[GG_U];
-#pragma unroll
-            for (int u = 0; u < GG_U; ++u) {
-                y[u] = fma(ed[u], step, a);
-                Kv[u] = dlcf * (1.0 - inv[u]) * fma(ed[u], dl, lns0);
-                inv[u] *= rU;
-                ed[u] += (double)GG_U;
-            }
-            // trapezoid end weights and the exact last abscissa: only the first and the last batch (uniform branches)
-            if (e0 == 0) Kv[0] *= 0.5;
-            if (e0 + GG_U >= NP) {
-#pragma unroll
-                for (int u = 0; u < GG_U; ++u) {
-                    const int e = e0 + u;
-                    if (e == NP - 1) { y[u] = lxN; Kv[u] *= 0.5; }
-                    else if (e >= NP) { y[u] = lxN; Kv[u] = 0.0; }
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < GG_U; ++u) {
-                y[u] = fmax(y[u], lx0);                         // np.interp clamps below the grid (t = 0 in segment 0)
-                int jj = (int)((y[u] - lx0) * invD);            // both grids are log-uniform: the guess is right
-                jj = max(0, min(jj, Nt - 2));                   // except next to a node ...
-                double lo = lxt[jj];
-                if (!(y[u] >= lo && y[u] < lxt[jj + 1])) {      // ... where it is corrected against the actual doubles
-                    while (jj > 0 && y[u] < lxt[jj]) --jj;
-                    while (jj < Nt - 2 && y[u] >= lxt[jj + 1]) ++jj;
-                    lo = lxt[jj];
-                }
-                j[u] = jj;
-                t[u] = (y[u] - lo) * ilx[jj];
-            }
-#pragma unroll
-            for (int u = 0; u < GG_U; ++u) {
-                const double f0 = Lm[j[u]], f1 = Lm[j[u] + 1];
-                Lv[u] = fma(t[u], f1 - f0, f0);             // NaN (from -inf ordinates) -> 0 inside fast_exp2
-            }
-#pragma unroll
-            for (int u = 0; u < GG_U; ++u) acc[u] = fma(Kv[u], fast_exp2(Lv[u], tab), acc[u]);
+        for (int u = 0; u < GG_U; ++u) {
+            const size_t o = (size_t)(b * GG_U + u) * stride + row;
+            Kv[u] = __ldg(gK + o); t[u] = __ldg(gT + o); j[u] = __ldg(gJ + o);
         }
+        gg_batch_acc(Lm, S.e2tab, j, t, Kv, acc);
     }
     double s = acc[0];
 #pragma unroll
@@ -788,7 +833,8 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
         const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
         const double cf = __ldg(C.T + (is_a ? L.agg_c : L.qee_c) + r);
         const double r2 = __ldg(C.T + (is_a ? L.agg_r2 : L.qee_r2) + r);
-        const double s = gg_row_sum(S, S.Lm, Nt, NP, a, step, cf, r2, is_a);
+        const double s = C.ggK ? gg_row_sum_tab(S, S.Lm, NP, C.ggK, C.ggT, C.ggJ, C.gg_rows, row)
+                               : gg_row_sum(S, S.Lm, Nt, NP, a, step, cf, r2, is_a);
         if (is_a) agg_out[r] = s;
         else {
             double ng = 0.0;
