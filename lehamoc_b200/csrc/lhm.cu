@@ -58,7 +58,7 @@ __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlag
     C.L = L; C.F = F;
     C.T = tabd + (size_t)w * L.n_doubles;
     C.TI = tabi + (size_t)w * L.n_ints;
-    C.E = Ecache ? Ecache + (size_t)w * (L.Ns + L.Ni) * L.Ng : nullptr;
+    C.E = Ecache ? Ecache + (size_t)w * ecache_doubles(L.Ns, L.Ni, L.Ng) : nullptr;
     C.P = ptab ? ptab + (ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)) : nullptr;
     C.ggK = nullptr; C.ggT = nullptr; C.ggJ = nullptr; C.gg_rows = 0;
     const double* c = consts + (size_t)w * LHM_NCONST;
@@ -1071,7 +1071,7 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
     CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
     if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
-        CUDA_TRY(cudaMalloc(&h->d_E, W * (size_t)(cfg->Ns + cfg->Ni) * cfg->Ng * sizeof(double)));
+        CUDA_TRY(cudaMalloc(&h->d_E, W * ecache_doubles(cfg->Ns, cfg->Ni, cfg->Ng) * sizeof(double)));
     if (cfg->ic_pair_table && cfg->IC_emis_flag) {
         const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);
         CUDA_TRY(cudaMalloc(&h->d_ptab, per * (cfg->shared_ic_grids ? 1 : W)));

@@ -61,6 +61,7 @@ struct Layout {
     int u_idx, u_j, q_j;            // Ng
     int jm_syn;                     // Ns
     int jz;                         // Ns+Ni: first gamma index whose exp(-nu/nu_c) is non-zero (const-B cache)
+    int jx;                         // Ns+Ni: first EVEN gamma index from which nu/nu_c < SYN_XSMALL (series instead of table)
     // IC tile schedule (lhm_setup.cuh: ic_build_schedule)
     int ic_maxT;                    // number of candidate tiles = ceil((Ni-1)/IC_OG) * ceil(Ng/IC_GB)
     int ic_nt;                      // 1: number of active tiles
@@ -101,7 +102,7 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP, int Np = 0) {
     L.n_doubles = o;
     o = 0;
     L.ps_j = take(Nt); L.pi_j = take(Nt); L.u_idx = take(Ng); L.u_j = take(Ng); L.q_j = take(Ng);
-    L.jm_syn = take(Ns); L.jz = take(Ns + Ni);
+    L.jm_syn = take(Ns); L.jz = take(Ns + Ni); L.jx = take(Ns + Ni);
     L.ic_maxT = ((Ni - 1 + IC_OG - 1) / IC_OG) * ((Ng + IC_GB - 1) / IC_GB);
     L.ic_nt = take(2); L.ic_task = take(L.ic_maxT); L.ic_i0 = take(L.ic_maxT); L.ic_i1 = take(L.ic_maxT);
     L.ic_tb = take(IC_NW + 1); L.ic_cand = take(2 * L.ic_maxT);
@@ -109,6 +110,12 @@ inline Layout make_layout(int Ng, int Ns, int Ni, int Nt, int NP, int Np = 0) {
     L.n_ints = o;
     return L;
 }
+
+// constant-B exponential cache of one walker: blocks of 32 frequency rows, gamma-major inside a block, so that the 32 rows
+// a warp of phase_syn_rows owns are ONE contiguous stream of 256-byte lines over its gamma loop (a [gamma][row] layout
+// made every warp hop 2 KB per gamma and the eight warps of a CTA interleave their lines in DRAM)
+__host__ __device__ inline size_t ecache_doubles(int Ns, int Ni, int Ng) { return (size_t)((Ns + Ni + 31) / 32) * Ng * 32; }
+__host__ __device__ inline size_t ecache_index(int row, int j, int Ng) { return ((size_t)(row >> 5) * Ng + j) * 32 + (row & 31); }
 
 // ---- np.interp semantics (NumPy C `arr_interp`) ---------------------------------
 // A stencil is (code, dx, Dx): code = (j << 1) | exact.  exact -> result fp[j] (clamped ends or

@@ -177,7 +177,7 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
     // ---- synchrotron exponentials when B(t) == B0 (m == 0 or Vexp == 0): same expressions as phase_vectors /
     //      phase_syn_rows evaluate per step, tabulated once ------------------------------------------------------
     if (A.Ecache) {
-        double* E = A.Ecache + (size_t)w * (Ns + Ni) * Ng;
+        double* E = A.Ecache + (size_t)w * ecache_doubles(Ns, Ni, Ng);
         const double B0 = A.consts[(size_t)w * LHM_NCONST + LHM_C_B0];
         for (int row = tid; row < Ns + Ni; row += NT) {
             const double nu = (row < Ns) ? ns[row] : ni[row - Ns];
@@ -188,6 +188,14 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
                 if (x > 745.2) lo = mid + 1; else hi = mid;
             }
             TI[L.jz + row] = lo;
+            int lo2 = lo, hi2 = Ng;                              // first j with x < SYN_XSMALL, rounded up to an even index
+            while (lo2 < hi2) {
+                int mid = (lo2 + hi2) >> 1;
+                double x = nu * (1.0 / (pc.nuc_pref * B0 * (g[mid] * g[mid])));
+                if (!(x < SYN_XSMALL)) lo2 = mid + 1; else hi2 = mid;
+            }
+            lo2 = max((lo2 + 1) & ~1, lo & ~1);
+            TI[L.jx + row] = min(lo2, Ng & ~1);
         }
         // 1/nu_c(gamma, B0) once per gamma (the expression of phase_vectors), 2^(i/64) for the staged exponential
         __shared__ double e2tab_s[64];
@@ -210,14 +218,16 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int j = jq[u], row = rq[u];
-                on[u] = (e0 + u * NT < total) && j >= (TI[L.jz + min(row, NR - 1)] & ~1);
+                const int rr = min(row, NR - 1);
+                const int jxr = TI[L.jx + rr];                  // [jz & ~1, jx) and the last gamma of an odd grid are what is read
+                on[u] = (e0 + u * NT < total) && j >= (TI[L.jz + rr] & ~1) && (j < jxr || ((Ng & 1) && j == Ng - 1));
                 const double nu = (row < Ns) ? ns[row] : ni[min(row - Ns, Ni - 1)];
                 x[u] = on[u] ? nu * inuc[min(j, Ng - 1)] : 0.0;
             }
             fast_exp_neg<4>(x, Ev, e2tab_s);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
-                if (on[u]) E[(size_t)jq[u] * NR + rq[u]] = Ev[u];   // transposed: [gamma][row]; x > 745.2 gives exactly 0
+                if (on[u]) E[ecache_index(rq[u], jq[u], Ng)] = Ev[u];   // x > 745.2 gives exactly 0
                 jq[u] += dj; rq[u] += dr;
                 if (rq[u] >= NR) { rq[u] -= NR; ++jq[u]; }
             }

@@ -378,6 +378,18 @@ __device__ __forceinline__ void fast_exp_neg(const double (&x)[U], double (&out)
     }
 }
 
+// exp(-x) for 0 <= x < SYN_XSMALL by its series: the truncation x^5/120 < 1e-17 is below the rounding of the result, so
+// the value agrees with exp() to the last bit or two.  In the constant-B mode the part of a row where nu/nu_c has become
+// this small (a third of the non-zero table at Test 1) is not tabulated at all: four FMAs replace an 8-byte stream from
+// HBM, which is what bounds the phase when a whole batch reaches it in lock-step (path G).
+constexpr double SYN_XSMALL = 1e-3;
+__device__ __forceinline__ double exp_neg_small(double x) {
+    double p = fma(x, 1.0 / 24.0, -1.0 / 6.0);
+    p = fma(p, x, 0.5);
+    p = fma(p, x, -1.0);
+    return fma(p, x, 1.0);
+}
+
 // Phase F1: synchrotron emissivity + SSA, one THREAD per frequency row, serial over gamma with two independent
 // accumulator chains.  exp(-nu/nu_c) is shared between Q_syn_space (nu/(a_cr g^2)) and aSSA (nu/nu_c(g,B)) on the
 // nu_syn grid.  When B is constant in time the exponentials come from the per-walker table built at set-up
@@ -389,7 +401,7 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni;
     const bool need_q = C.F.syn_e, need_a = C.F.ssa;
     if (!need_q && !need_a) return;
-    const int NR = Ns + Ni;                                  // row stride of the transposed table
+    constexpr int NR = 32;                                   // gamma stride inside a 32-row block of the table (ecache_index)
     const int nrows = Ns + (need_a ? Ni : 0);
     const double qpref = kPC.C_syn * pow(C.B, 2.0 / 3.0);
     const double apref = kPC.ssa_pref * C.B;
@@ -405,18 +417,28 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
         const int jm = do_q ? C.TI[L.jm_syn + k] : Ng;       // Q_syn_space mask: gammas below jm emit nothing
         double sq0 = 0.0, sq1 = 0.0, sa0 = 0.0, sa1 = 0.0;
         if (C.E) {
-            const double* __restrict__ Et = C.E + row;
+            const double* __restrict__ Et = C.E + ecache_index(row, 0, Ng);
             int j = C.TI[L.jz + row] & ~1;
+            const int jx = C.TI[L.jx + row];                 // even; from here on nu/nu_c < SYN_XSMALL: series, no table
 #pragma unroll 4
-            for (; j + 1 < Ng; j += 2) {
+            for (; j < jx; j += 2) {
                 const double E0 = __ldg(Et + (size_t)j * NR), E1 = __ldg(Et + (size_t)(j + 1) * NR);
                 if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
                 if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
                 sa0 = fma(E0, S.v[j], sa0);
                 sa1 = fma(E1, S.v[j + 1], sa1);
             }
-            if (j < Ng) {
-                const double E0 = __ldg(Et + (size_t)j * NR);
+#pragma unroll 2
+            for (; j + 1 < Ng; j += 2) {
+                const double E0 = exp_neg_small(nu * S.inuc[j]), E1 = exp_neg_small(nu * S.inuc[j + 1]);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                sa0 = fma(E0, S.v[j], sa0);
+                sa1 = fma(E1, S.v[j + 1], sa1);
+            }
+            if (j < Ng) {                                    // odd Ng: the last gamma, tabulated whatever its x
+                const double x = nu * S.inuc[j];
+                const double E0 = (x < SYN_XSMALL) ? exp_neg_small(x) : __ldg(Et + (size_t)j * NR);
                 if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
                 sa0 = fma(E0, S.v[j], sa0);
             }
