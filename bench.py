@@ -26,11 +26,13 @@ import numpy as np  # noqa: E402
 METRIC = "model-evals/sec (Test-1 SSC to steady state)"
 UNIT = "model-evals/s"
 # dram__bytes_read.sum + dram__bytes_write.sum of one run_kernel launch of 1184 Test-1 walkers (ncu --set full)
-NCU_DRAM_BYTES_PER_WALKER = {"R": (1.642121e9 + 7.229952e6) / 1184.0, "G": None}
+NCU_DRAM_BYTES_PER_WALKER = {"R": (1.642121e9 + 7.229952e6) / 1184.0, "G": 4.300544e6 / 1184.0}
 NCU_DRAM_SOURCE = {"R": ("ncu capture profiles/r01_k_ncu_summary.txt, scaled by walkers per launch; it is the per-step "
                          "re-read of the constant-B exponential cache (543 KB per walker x 10 steps, half of it exact zeros "
                          "that are skipped) and of the 68 KB per-walker tables, 2 % of HBM bandwidth"),
-                   "G": None}
+                   "G": ("ncu capture profiles/r02_i_icg_kernel_ncu_details.txt (one icg_kernel launch of 1184 walkers: 4.30 MB "
+                         "read, nothing written to DRAM -- the photon fields and electron weights of the batch, 2.9 MB "
+                         "algorithmic, plus the 1.2 MB of grid-only pair constants; partial sums stay in L2), scaled by walkers")}
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -273,8 +275,8 @@ def config_dict(args):
     """The same dictionary in both arms (the driver compares them key by key)."""
     return {"workload": workload_name(args), "walkers_per_gpu": args.walkers, "ic_path": args.ic_path,
             "timesteps_per_model": 10,
-            "l2": "flushed between steps (256 MiB write); the per-batch tables + exponential cache (%.0f MB at 0.61 MB per "
-                  "walker) also exceed the 126 MB L2 on their own" % (args.walkers * 0.611)}
+            "l2": "flushed between steps (256 MiB write); the per-walker tables of a batch (%.0f MB at 84 KB per walker; "
+                  "paths R and S add a 0.54 MB exponential cache per walker) are rebuilt by every step" % (args.walkers * 0.084)}
 
 
 # ------------------------------------------------------------------------------------------------------

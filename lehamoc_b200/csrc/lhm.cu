@@ -1070,7 +1070,13 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
     CUDA_TRY(cudaMalloc(&h->d_tabd, W * h->L.n_doubles * sizeof(double)));
     CUDA_TRY(cudaMalloc(&h->d_tabi, W * h->L.n_ints * sizeof(int)));
     CUDA_TRY(cudaMalloc(&h->d_cor, W * sizeof(double)));
-    if (cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag))
+    // The constant-B exponential cache pays where the rows of the synchrotron phase compete with an IC phase for the FP64
+    // pipe (paths R and S: 10.64 vs 10.81 ms and 6.06 vs 6.14 ms per 1184 Test-1 walkers, set-up included).  Under path G
+    // the half-step kernel has the pipe to itself and the whole batch reaches the phase at once: recomputing the
+    // non-zero, non-small part of a row (30 % of it) beats streaming it (4.29 vs 4.61 ms, and 0.37 vs 0.65 ms of set-up).
+    const bool want_cache = cfg->const_B && (cfg->Syn_emis_flag || cfg->SSA_l_flag)
+                            && !(cfg->ic_path == LHM_IC_PATH_G && cfg->IC_emis_flag);
+    if (want_cache)
         CUDA_TRY(cudaMalloc(&h->d_E, W * ecache_doubles(cfg->Ns, cfg->Ni, cfg->Ng) * sizeof(double)));
     if (cfg->ic_pair_table && cfg->IC_emis_flag) {
         const size_t per = (size_t)h->L.ic_maxT * (IC_PT * 2 * 32) * sizeof(double2);

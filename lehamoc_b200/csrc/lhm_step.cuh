@@ -443,9 +443,18 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
                 sa0 = fma(E0, S.v[j], sa0);
             }
         } else {
-            // recompute the exponentials: SYN_U gammas side by side, stage by stage (independent chains interleave)
+            // recompute the exponentials: SYN_U gammas side by side, stage by stage (independent chains interleave).
+            // x = nu/nu_c falls along the gamma grid, so the row splits like the table does: [0, jz) exp(-x) == 0 exactly
+            // (x > 745.2), skipped; [jz, jx) the staged exponential; [jx, Ng) x < SYN_XSMALL, the four-term series.
             constexpr int SYN_U = 4;
-            for (int j0 = 0; j0 < Ng; j0 += SYN_U) {
+            int lo = 0, hi = Ng;                                // first j with x <= 745.2
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (nu * S.inuc[mid] > 745.2) lo = mid + 1; else hi = mid; }
+            const int jz = lo & ~(SYN_U - 1);
+            hi = Ng;                                            // first j with x < SYN_XSMALL, rounded up to a multiple of SYN_U
+            while (lo < hi) { const int mid = (lo + hi) >> 1; if (!(nu * S.inuc[mid] < SYN_XSMALL)) lo = mid + 1; else hi = mid; }
+            const int jx = min((lo + SYN_U - 1) & ~(SYN_U - 1), Ng);
+            int j0 = jz;
+            for (; j0 < jx; j0 += SYN_U) {
                 double x[SYN_U], Ev[SYN_U];
 #pragma unroll
                 for (int u = 0; u < SYN_U; ++u) x[u] = nu * S.inuc[min(j0 + u, Ng - 1)];
@@ -462,6 +471,17 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
                             sa0 = fma(Ev[u], S.v[j], sa0);
                         }
                     }
+                }
+            }
+#pragma unroll 2
+            for (int j = j0; j < Ng; j += 2) {                  // j0 is even: the two chains keep their parity
+                const double E0 = exp_neg_small(nu * S.inuc[j]);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                sa0 = fma(E0, S.v[j], sa0);
+                if (j + 1 < Ng) {
+                    const double E1 = exp_neg_small(nu * S.inuc[j + 1]);
+                    if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                    sa1 = fma(E1, S.v[j + 1], sa1);
                 }
             }
         }
