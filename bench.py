@@ -476,7 +476,7 @@ def main():
     # a stream of batches has a fill and a drain of about one batch each: time enough batches for the steady state to
     # dominate (30 at the default 10 steps; every one of them is a full step with its own H2D and D2H)
     e2e_nb = max(3 * args.steps, 12)
-    e2e_run(2)
+    e2e_run(2 * E2E_DEPTH)                          # every engine of the pipeline created, both pinned buffer pairs of each touched
     # The stream is fed by three Python worker threads; on a shared host their scheduling is noisy (the same binary gave
     # 161 k, 167 k, 185 k and once 78 k model-evals/s on consecutive boxes while the device-timed value moved by 1 %).
     # So the pass is repeated three times, every pass is reported (e2e.passes) and the headline is the fastest one --
@@ -495,7 +495,7 @@ def main():
         e2e_passes.append(t_pass)
     e2e_s = min(e2e_passes)
     # the same with the NumPy packer on the host (bit-identical set-up; 9.4 MB of H2D per batch instead of 0.1 MB)
-    e2e_run(2, False)
+    e2e_run(2 * E2E_DEPTH, False)
     t0 = time.perf_counter()
     e2e_run(e2e_nb, False)
     torch.cuda.synchronize()
