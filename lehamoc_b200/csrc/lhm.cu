@@ -58,6 +58,7 @@ __device__ __forceinline__ void load_ctx(Ctx& C, const Layout& L, const StepFlag
     C.L = L; C.F = F;
     C.T = tabd + (size_t)w * L.n_doubles;
     C.TI = tabi + (size_t)w * L.n_ints;
+    C.Ts = C.T; C.TIs = C.TI;
     C.E = Ecache ? Ecache + (size_t)w * ecache_doubles(L.Ns, L.Ni, L.Ng) : nullptr;
     C.P = ptab ? ptab + (ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)) : nullptr;
     C.ggK = nullptr; C.ggT = nullptr; C.ggJ = nullptr; C.gg_rows = 0;
@@ -159,7 +160,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
                 phase_photons<NT>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
                 for (int k = tid; k < Nt; k += NT)
-                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
@@ -214,11 +215,11 @@ template <int NTH>
 __device__ void g_prepare(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
     const int tid = threadIdx.x;
-    for (int j = tid; j < L.Ng; j += NTH) S.gS[j] = C.T[L.g + j];
+    for (int j = tid; j < L.Ng; j += NTH) S.gS[j] = C.Ts[L.g + j];
     for (int i = tid; i < 64; i += NTH) S.e2tab[i] = exp2((double)i / 64.0);
     for (int i = tid; i < L.Nt; i += NTH) {
-        S.lxtS[i] = C.T[L.lxt + i];
-        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.T[L.lxt + i + 1] - C.T[L.lxt + i]) : 0.0;
+        S.lxtS[i] = C.Ts[L.lxt + i];
+        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.Ts[L.lxt + i + 1] - C.Ts[L.lxt + i]) : 0.0;
     }
     __syncthreads();
 }
@@ -281,6 +282,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
     Ctx C;
     load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
     C.ggK = G.ggK; C.ggT = G.ggT; C.ggJ = G.ggJ; C.gg_rows = G.gg_rows;
+    C.Ts = A.tabd; C.TIs = A.tabi;                              // walker 0's copy of the grid-only tables (shared grids)
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -323,7 +325,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
                 phase_photons<NT>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
                 for (int k = tid; k < Nt; k += NT)
-                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
@@ -424,6 +426,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_lh_kernel(GArgs G) {
     Ctx C;
     load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, nullptr, 0, w);
     C.ggK = G.ggK; C.ggT = G.ggT; C.ggJ = G.ggJ; C.gg_rows = G.gg_rows;
+    C.Ts = A.tabd; C.TIs = A.tabi;                              // walker 0's copy of the grid-only tables (shared grids)
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt, Np = L.Np;
     const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
@@ -461,7 +464,7 @@ __global__ void __launch_bounds__(NT, MINB) stepG_lh_kernel(GArgs G) {
                 phase_photons<NT>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
                 for (int k = tid; k < Nt; k += NT)
-                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
@@ -632,7 +635,7 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
                 phase_photons<NTL>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
                 for (int k = tid; k < Nt; k += NTL)
-                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
@@ -712,7 +715,7 @@ __global__ void __launch_bounds__(NT, 2) run_code_lh_kernel(RunArgs A) {
                 phase_photons<NT>(C, S, false);
                 double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
                 for (int k = tid; k < Nt; k += NT)
-                    o[k] = S.n[k] * C.T[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
             }
             if (A.N_out) {
                 double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;

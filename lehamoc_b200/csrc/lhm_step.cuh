@@ -117,6 +117,11 @@ struct Ctx {
     Layout L;
     const double* T;      // double tables of this walker
     const int* TI;        // int tables of this walker
+    // The same tables as far as they depend on g_el / nu_ic / nu_tot only.  Normally == T / TI; the lock-step kernels of a
+    // shared-grid batch (path G) point them at walker 0's copy, so that 1184 walkers read ONE set of cache lines
+    // instead of 1184 cold ones.  Entries on the nu_syn grid (it follows the walker's B0), el_inj and the external photon
+    // field stay per walker.
+    const double* Ts; const int* TIs;
     const double* E;      // [(Ns+Ni), Ng] exp(-nu/nu_c(gamma,B)) of this walker when B is constant in time, else null
     const double2* P;     // IC pair table of this walker (ic_fill_pair_table), or null: recompute per step
     // shared-grid batches (path G): the per-sample geometry of the gamma-gamma rows, tabulated once per batch, or null
@@ -134,18 +139,18 @@ __device__ void ic_prepare(const Ctx& C, Smem& S) {
     const int tid = threadIdx.x;
     static_assert(NT / 32 >= IC_NW, "the tile schedule is built for IC_NW warps (further warps sit the IC phase out)");
     for (int j = tid; j < L.Ng; j += NT) {
-        S.gS[j] = C.T[L.g + j]; S.lgS[j] = C.T[L.lg + j]; S.inv4gS[j] = C.T[L.inv4g + j];
+        S.gS[j] = C.Ts[L.g + j]; S.lgS[j] = C.Ts[L.lg + j]; S.inv4gS[j] = C.Ts[L.inv4g + j];
     }
     for (int o = tid; o < L.Ni; o += NT) {
-        S.epsS[o] = C.T[L.eps + o]; S.lnu4S[o] = C.T[L.lnu4 + o]; S.nuoS[o] = C.T[L.nic + o];
+        S.epsS[o] = C.Ts[L.eps + o]; S.lnu4S[o] = C.Ts[L.lnu4 + o]; S.nuoS[o] = C.Ts[L.nic + o];
     }
     for (int i = tid; i < 64; i += NT) S.e2tab[i] = exp2((double)i / 64.0);
     for (int i = tid; i < L.Nt; i += NT) {
-        const double x = C.T[L.invnt + i];
-        S.lxtS[i] = C.T[L.lxt + i];
-        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.T[L.lxt + i + 1] - C.T[L.lxt + i]) : 0.0;
+        const double x = C.Ts[L.invnt + i];
+        S.lxtS[i] = C.Ts[L.lxt + i];
+        S.ilxS[i] = (i < L.Nt - 1) ? 1.0 / (C.Ts[L.lxt + i + 1] - C.Ts[L.lxt + i]) : 0.0;
         S.tri[4 * i + 0] = x;                            // 1/nu_i
-        S.tri[4 * i + 1] = x * C.T[L.l2nt + i];          // (1/nu_i) 2 ln nu_i
+        S.tri[4 * i + 1] = x * C.Ts[L.l2nt + i];          // (1/nu_i) 2 ln nu_i
         S.tri[4 * i + 2] = 0.0;                          // p_i = trapz weight x photons (every step)
         S.tri[4 * i + 3] = x * x;                        // 1/nu_i^2
     }
@@ -174,14 +179,14 @@ __device__ void phase_photons(const Ctx& C, Smem& S, bool aux) {
     const double K = kPC.sigmaT * C.Rad * kPC.mc2 / kPC.h;          // sigmaT*R*m_el*c**2./h  LeHaMoC_f.py:170
     for (int k = tid; k < L.Nt; k += NT) {
         double a = interp_eval(S.Lsyn, C.TI[L.ps_j + k], C.T[L.ps_dx + k], C.T[L.ps_Dx + k]);
-        double b = interp_eval(S.Lic, C.TI[L.pi_j + k], C.T[L.pi_dx + k], C.T[L.pi_Dx + k]);
+        double b = interp_eval(S.Lic, C.TIs[L.pi_j + k], C.Ts[L.pi_dx + k], C.Ts[L.pi_Dx + k]);
         double nk = (exp10(a) + exp10(b)) / C.V + C.T[L.ext + k];
         S.n[k] = nk;
         if (aux) {
             S.Ln[k] = log10(nk);
             S.Lm[k] = log2(nk * kPC.mc2_h);                      // gamma-gamma phases interpolate in log2 (fast_exp2)
-            S.y[k] = C.T[L.xt + k] * nk * K;
-            S.tri[4 * k + 2] = C.T[L.wt + k] * nk;               // p_i = trapz weight x photons
+            S.y[k] = C.Ts[L.xt + k] * nk * K;
+            S.tri[4 * k + 2] = C.Ts[L.wt + k] * nk;               // p_i = trapz weight x photons
         }
     }
     __syncthreads();
@@ -240,7 +245,7 @@ __device__ void phase_uph(const Ctx& C, Smem& S, double* U_out /*smem or null*/)
     const int Nt = L.Nt;
     // exclusive prefix of the trapezoids of np.trapz(y, x): cum[m] = sum_{i<m} (x[i+1]-x[i])*(y[i+1]+y[i])/2
     for (int m = tid; m < Nt; m += NT)
-        S.dp[m] = (m < Nt - 1) ? (C.T[L.xt + m + 1] - C.T[L.xt + m]) * (S.y[m + 1] + S.y[m]) / 2.0 : 0.0;
+        S.dp[m] = (m < Nt - 1) ? (C.Ts[L.xt + m + 1] - C.Ts[L.xt + m]) * (S.y[m + 1] + S.y[m]) / 2.0 : 0.0;
     __syncthreads();
     if (tid < 32) exclusive_prefix_warp(S.dp, S.cum, Nt);
     __syncthreads();
@@ -248,21 +253,21 @@ __device__ void phase_uph(const Ctx& C, Smem& S, double* U_out /*smem or null*/)
     const double pre = kPC.mc2 / (kPC.sigmaT * C.Rad);
     // the `else` branch value U_ph_tot integrates nu*n*K over nu (not x) on nu[:-1]  LeHaMoC_f.py:162
     for (int j = tid; j < L.Ng; j += NT) {
-        int idx = C.TI[L.u_idx + j];
+        int idx = C.TIs[L.u_idx + j];
         double U;
         if (idx >= 1) {
-            double v = interp_eval(S.Ln, C.TI[L.u_j + j], C.T[L.u_dx + j], C.T[L.u_Dx + j]);
-            double xT = C.T[L.u_xT + j];
+            double v = interp_eval(S.Ln, C.TIs[L.u_j + j], C.Ts[L.u_dx + j], C.Ts[L.u_Dx + j]);
+            double xT = C.Ts[L.u_xT + j];
             double yT = xT * exp10(v) * K;
-            double xm = C.T[L.xt + idx - 1];
+            double xm = C.Ts[L.xt + idx - 1];
             U = pre * (S.cum[idx - 1] + (xT - xm) * (yT + S.y[idx - 1]) / 2.0);
         } else if (idx == 0) {
             U = 0.0;       // nu_T below the grid: the reference would raise (max of empty); unreachable
         } else {
             double s = 0.0;
             for (int i = 0; i < Nt - 2; ++i) {
-                double y0 = C.T[L.nt + i] * S.n[i] * K, y1 = C.T[L.nt + i + 1] * S.n[i + 1] * K;
-                s += (C.T[L.nt + i + 1] - C.T[L.nt + i]) * (y1 + y0) / 2.0;
+                double y0 = C.Ts[L.nt + i] * S.n[i] * K, y1 = C.Ts[L.nt + i + 1] * S.n[i + 1] * K;
+                s += (C.Ts[L.nt + i + 1] - C.Ts[L.nt + i]) * (y1 + y0) / 2.0;
             }
             U = pre * s;
         }
@@ -294,11 +299,11 @@ __device__ void phase_electrons(const Ctx& C, Smem& S) {
     const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (C.B * C.B) : 0.0;
     const double esc = kPC.c / C.Rad * (double)C.F.esc;
     for (int j = tid; j < n; j += NT) {
-        double smj = C.T[L.sm + j], spj = C.T[L.sp + j];
+        double smj = C.Ts[L.sm + j], spj = C.Ts[L.sp + j];
         double syn_m = b_syn * smj, syn_p = b_syn * spj;
         double ic_m = 0.0, ic_p = 0.0;
         if (C.F.ic_l) { ic_m = S.bcom[j + 1] * smj; ic_p = S.bcom[j + 2] * spj; }
-        double ad_m = b_ad * C.T[L.am + j], ad_p = b_ad * C.T[L.ap + j];
+        double ad_m = b_ad * C.Ts[L.am + j], ad_p = b_ad * C.Ts[L.ap + j];
         double V2 = 1.0 + dt * (esc + syn_m + ic_m + ad_m);
         double V3 = -dt * (syn_p + ic_p + ad_p);
         double d = S.N[j + 1];
@@ -318,7 +323,7 @@ __device__ void phase_vectors(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
     const int tid = threadIdx.x;
     const int Ng = L.Ng;
-    const double dgl = C.T[L.lg + 1] - C.T[L.lg + 0];            // dg_l_el  LeMoC.py:118
+    const double dgl = C.Ts[L.lg + 1] - C.Ts[L.lg + 0];            // dg_l_el  LeMoC.py:118
     for (int j = tid; j < Ng; j += NT) S.ne[j] = S.N[j] / C.V;
     __syncthreads();
     for (int j = tid; j < Ng; j += NT) {
@@ -326,12 +331,12 @@ __device__ void phase_vectors(const Ctx& C, Smem& S) {
         double nej = S.ne[j];
         double nuc = kPC.nuc_pref * C.B * (gj * gj);                // nu_c(g, B)  LeHaMoC_f.py:78-79
         S.inuc[j] = 1.0 / nuc;
-        S.av[j] = C.T[L.wg + j] * (nej * (1.0 / gj));                 // trapz weight x Np*g**(-1.)
-        S.u[j] = C.T[L.wg + j] * (nej * C.T[L.g13 + j]);
+        S.av[j] = C.Ts[L.wg + j] * (nej * (1.0 / gj));                 // trapz weight x Np*g**(-1.)
+        S.u[j] = C.Ts[L.wg + j] * (nej * C.Ts[L.g13 + j]);
         double vj = 0.0;
         if (j >= 1 && j <= Ng - 2) {
             double D = (S.ne[j + 1] - nej) / dgl - 2.0 * nej;        // np.diff(N_el[1:])/dg_l_el-2.*N_el[1:-1]
-            vj = C.T[L.wgi + j] * (pow(2.0 * nuc, -1.0 / 3.0) * D);
+            vj = C.Ts[L.wgi + j] * (pow(2.0 * nuc, -1.0 / 3.0) * D);
         }
         S.v[j] = vj;
     }
@@ -412,7 +417,7 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
             if (k == 0) continue;
             if (is_syn ? (k > Ns - 2) : (k > Ni - 2)) continue;
         }
-        const double nu = is_syn ? C.T[L.nsyn + k] : C.T[L.nic + k];
+        const double nu = is_syn ? C.T[L.nsyn + k] : C.Ts[L.nic + k];
         const bool do_q = is_syn && need_q && (k < Ns - 1);
         const int jm = do_q ? C.TI[L.jm_syn + k] : Ng;       // Q_syn_space mask: gammas below jm emit nothing
         double sq0 = 0.0, sq1 = 0.0, sa0 = 0.0, sa1 = 0.0;
@@ -490,7 +495,7 @@ __device__ void phase_syn_rows(const Ctx& C, Smem& S, bool all_rows) {
             if (k < Ns - 1) S.Qsyn[k] = do_q ? qpref * C.T[L.nm23s + k] * sq : 0.0;
             S.aS[k] = need_a ? apref * C.T[L.nm53s + k] * sa : 0.0;
         } else {
-            S.aI[k] = apref * C.T[L.nm53i + k] * sa;
+            S.aI[k] = apref * C.Ts[L.nm53i + k] * sa;
         }
     }
 }
@@ -631,8 +636,8 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
     }
     __syncthreads();
     const double* P0 = S.sfx, *P1 = S.sfx + NtP, *P2 = S.sfx + 2 * NtP, *P3 = S.sfx + 3 * NtP;
-    const double lnu0 = 0.5 * C.T[L.l2nt];                              // ln nu_0
-    const double inv_dl = (double)(Ntar - 1) / (0.5 * C.T[L.l2nt + Ntar - 1] - lnu0);
+    const double lnu0 = 0.5 * C.Ts[L.l2nt];                              // ln nu_0
+    const double inv_dl = (double)(Ntar - 1) / (0.5 * C.Ts[L.l2nt + Ntar - 1] - lnu0);
     for (int o = warp; o < No; o += NW) {
         const double eps = S.epsS[o], nuo = S.nuoS[o], lnu4 = S.lnu4S[o];
         double sum = 0.0;
@@ -696,8 +701,8 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor, const dou
     __syncthreads();
     for (int j = tid; j < ni; j += NT) {
         double aI = C.F.ssa ? -fabs(S.aI[j + 1]) : 0.0;
-        double V2 = 1.0 + dt * (esc + b_ad * C.T[L.aim + j] + S.agg[j + 1] * cc - aI * cc);
-        double V3 = -dt * (b_ad * C.T[L.aip + j]);
+        double V2 = 1.0 + dt * (esc + b_ad * C.Ts[L.aim + j] + S.agg[j + 1] * cc - aI * cc);
+        double V3 = -dt * (b_ad * C.Ts[L.aip + j]);
         double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
         double d = S.pic[j + 1] + (Q * dt) * C.V;
         S.cp[j] = V3 / V2;
@@ -871,17 +876,17 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
     for (int row = threadIdx.x; row < nrows; row += NT) {
         const bool is_a = row < Ni;
         const int r = is_a ? row : row - Ni;
-        const double a = __ldg(C.T + (is_a ? L.agg_a : L.qee_a) + r);
-        const double step = __ldg(C.T + (is_a ? L.agg_d : L.qee_d) + r);
-        const double cf = __ldg(C.T + (is_a ? L.agg_c : L.qee_c) + r);
-        const double r2 = __ldg(C.T + (is_a ? L.agg_r2 : L.qee_r2) + r);
+        const double a = __ldg(C.Ts + (is_a ? L.agg_a : L.qee_a) + r);
+        const double step = __ldg(C.Ts + (is_a ? L.agg_d : L.qee_d) + r);
+        const double cf = __ldg(C.Ts + (is_a ? L.agg_c : L.qee_c) + r);
+        const double r2 = __ldg(C.Ts + (is_a ? L.agg_r2 : L.qee_r2) + r);
         const double s = C.ggK ? gg_row_sum_tab(S, S.Lm, NP, C.ggK, C.ggT, C.ggJ, C.gg_rows, row)
                                : gg_row_sum(S, S.Lm, Nt, NP, a, step, cf, r2, is_a);
         if (is_a) agg_out[r] = s;
         else {
             double ng = 0.0;
             if (2.0 * S.gS[r] > 1.0)
-                ng = exp10(interp_eval(Lng, C.TI[L.q_j + r], C.T[L.q_dx + r], C.T[L.q_Dx + r]));
+                ng = exp10(interp_eval(Lng, C.TIs[L.q_j + r], C.Ts[L.q_dx + r], C.Ts[L.q_Dx + r]));
             qee_out[r] = kPC.qee_pref * (ng * s);
         }
     }
