@@ -1,6 +1,7 @@
 // lhm.cu -- liblhm.so: kernels + C ABI (include/lhm.h).  Build: see lehamoc_b200/build.py
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC lhm.cu -o liblhm.so
 #include <cuda_runtime.h>
+#include <algorithm>
 #include <atomic>
 #include <cmath>
 #include <cstdio>
@@ -1093,7 +1094,16 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
         h->F.ic_path = LHM_IC_PATH_R;                  // what the fused kernel runs when IC emission is switched off
         if (cfg->IC_emis_flag) {
             h->pathG = true;
-            const IcgDims D = h->GD = icg_dims(cfg->Ng, cfg->Ni, cfg->Nt);
+            h->GD = icg_dims(cfg->Ng, cfg->Ni, cfg->Nt);
+            {   // tiles of the contraction: whole grids while TWO CTAs fit an SM (113 KB each), else k- and gamma-sections.
+                // Measured with one 220 KB CTA per SM instead: grid 400 55.5 k against 57.9 k model-evals/s, grid 800 7.5 k
+                // against 8.6 k (profiles/r03_j_*).  LHM_ICG_SMEM_KB sets another budget per CTA (tests, experiments).
+                const char* e = std::getenv("LHM_ICG_SMEM_KB");
+                size_t limit = std::min((size_t)prop.sharedMemPerBlockOptin, (size_t)113 * 1024);
+                if (e && std::atoi(e) >= 32) limit = std::min((size_t)prop.sharedMemPerBlockOptin, (size_t)std::atoi(e) * 1024);
+                icg_choose_sections(h->GD, limit);
+            }
+            const IcgDims D = h->GD;
             if (icg_smem_bytes(D) > (size_t)prop.sharedMemPerBlockOptin) return LHM_ERR_CAPACITY;
             const size_t Wp = (W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
             h->Wpad_cap = (int)Wp;
@@ -1106,7 +1116,7 @@ static int init_handle(lhm_handle* h, const lhm_config* cfg, int device, void* c
             CUDA_TRY(cudaMalloc(&h->d_gav, Wp * D.NgP * sizeof(double)));
             CUDA_TRY(cudaMemset(h->d_gp, 0, Wp * D.Kp * sizeof(double)));       // padding walkers: p = av = 0
             CUDA_TRY(cudaMemset(h->d_gav, 0, Wp * D.NgP * sizeof(double)));
-            CUDA_TRY(cudaMalloc(&h->d_part, (size_t)D.NGC * Wp * D.NoPad * sizeof(double)));
+            CUDA_TRY(cudaMalloc(&h->d_part, (size_t)D.nks * D.NGC * Wp * D.NoPad * sizeof(double)));
             CUDA_TRY(cudaMalloc(&h->d_state, W * (size_t)gstate_layout(h->L).total * sizeof(double)));
             if (cfg->gg_flag) {
                 h->gg_rows = gg_table_rows(h->L, cfg->driver == 1);
@@ -1389,9 +1399,9 @@ int lhm_run_batch(lhm_handle* h, double* N_el_out, double* nuLnu_out, int snapsh
 static int icg_splits(int W, const IcgDims& D) {
     int dev = 0, sms = 148;
     if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int nwb = (W + ICG_NBW - 1) / ICG_NBW;
+    const int nwb = ((W + ICG_NBW - 1) / ICG_NBW) * D.nks * D.ngs;      // CTAs per split: walker blocks x sections
     const int slots = sms * (2 * (icg_smem_bytes(D) + 1024) <= (size_t)227 * 1024 ? 2 : 1);
-    int smax = D.ntasks / (2 * (ICG_NT / 32));
+    int smax = (D.ntasks / D.ngs) / (2 * (ICG_NT / 32));
     smax = smax < 1 ? 1 : (smax > 16 ? 16 : smax);
     int best = 1;
     double best_eff = 0.0;
@@ -1411,7 +1421,7 @@ static int launch_icg(lhm_handle* h, int ev_slot) {
     const size_t smem = icg_smem_bytes(h->GD);
     CUDA_TRY(ensure_dyn_smem(icg_kernel, smem, g_smem_icg[h->device % MAX_DEV]));
     if (ev_slot >= 0) CUDA_TRY(cudaEventRecord(h->evg[2 * ev_slot], h->stream));
-    icg_kernel<<<(I.Wpad / ICG_NBW) * I.S, ICG_NT, smem, h->stream>>>(I);
+    icg_kernel<<<(I.Wpad / ICG_NBW) * I.S * I.D.nks * I.D.ngs, ICG_NT, smem, h->stream>>>(I);
     g_launches++;
     CUDA_TRY(cudaGetLastError());
     if (ev_slot >= 0) CUDA_TRY(cudaEventRecord(h->evg[2 * ev_slot + 1], h->stream));
@@ -1564,7 +1574,7 @@ int lhm_last_icg_timing(lhm_handle* h, float* mean_ms, int* launches, int* ctas,
     }
     if (mean_ms) *mean_ms = (float)(tot / h->evg_n);
     if (launches) *launches = h->evg_n;
-    if (ctas) *ctas = ((h->W + ICG_NBW - 1) / ICG_NBW) * icg_splits(h->W, h->GD);
+    if (ctas) *ctas = ((h->W + ICG_NBW - 1) / ICG_NBW) * icg_splits(h->W, h->GD) * h->GD.nks * h->GD.ngs;
     if (smem_bytes) *smem_bytes = (int)icg_smem_bytes(h->GD);
     return LHM_OK;
 }

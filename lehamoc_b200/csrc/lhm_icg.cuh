@@ -35,6 +35,11 @@ struct IcgDims {
     int PST;            // row stride of the p tile in shared memory (PST % 16 == 4: conflict-free B fragments)
     int NGC;            // gamma chunks per group = NgP / ICG_GC
     int ntasks;         // NOG * NGC
+    // Large grids: a CTA stages only a SECTION of the target frequencies (nks sections of KSs k-steps) and of the gammas
+    // (ngs sections of GCs chunks), so that its tiles fit shared memory; every (task, k-section) has its own slot of
+    // the partial-sum buffer.  nks = ngs = 1 up to grid ~200.
+    int nks, KSs, ngs, GCs;
+    int PSTs;           // row stride of the sectioned p tile
 };
 
 __host__ __device__ inline IcgDims icg_dims(int Ng, int Ni, int Nt) {
@@ -45,10 +50,24 @@ __host__ __device__ inline IcgDims icg_dims(int Ng, int Ni, int Nt) {
     D.PST = D.Kp + ((4 - D.Kp % 16) + 16) % 16;
     D.NGC = D.NgP / ICG_GC;
     D.ntasks = D.NOG * D.NGC;
+    D.nks = 1; D.KSs = D.KS; D.ngs = 1; D.GCs = D.NGC; D.PSTs = D.PST;
     return D;
 }
 __host__ __device__ inline size_t icg_smem_bytes(const IcgDims& D) {
-    return ((size_t)ICG_NBW * D.PST + (size_t)D.NgP * ICG_AVS + (size_t)D.Kp * 4) * sizeof(double) + 16;
+    return ((size_t)ICG_NBW * D.PSTs + (size_t)D.GCs * ICG_GC * ICG_AVS + (size_t)D.KSs * 16) * sizeof(double) + 16;
+}
+// split the tiles until they fit `limit` bytes (k-sections first: they also shorten the p rows a warp strides over)
+__host__ inline void icg_choose_sections(IcgDims& D, size_t limit) {
+    for (int tries = 0; tries < 16 && icg_smem_bytes(D) > limit; ++tries) {
+        const size_t pbytes = (size_t)ICG_NBW * D.PSTs, abytes = (size_t)D.GCs * ICG_GC * ICG_AVS;
+        if (pbytes >= abytes && D.KSs > 8) D.nks *= 2; else if (D.GCs > 1) D.ngs *= 2; else D.nks *= 2;
+        D.KSs = (D.KS + D.nks - 1) / D.nks;
+        D.GCs = (D.NGC + D.ngs - 1) / D.ngs;
+        const int kp = 4 * D.KSs;
+        D.PSTs = kp + ((4 - kp % 16) + 16) % 16;
+    }
+    D.nks = (D.KS + D.KSs - 1) / D.KSs;                 // drop empty trailing sections
+    D.ngs = (D.NGC + D.GCs - 1) / D.GCs;
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -164,28 +183,35 @@ struct IcgArgs {
     const int* tasks;
     const double* gp;           // [Wpad][Kp]   p[w,i] = trapezoid weight x photon density (zero for i >= Ntar)
     const double* gav;          // [Wpad][NgP]  av[w,gamma] = trapezoid weight x N_e/gamma  (zero padding)
-    double* part;               // [NGC][Wpad][NoPad] partial sums over one gamma chunk
+    double* part;               // [nks][NGC][Wpad][NoPad] partial sums over one gamma chunk and one k-section
 };
 
 __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
     extern __shared__ __align__(16) double smg[];
     const IcgDims& D = A.D;
-    double* ps = smg;                                   // [ICG_NBW][PST]
-    double* avs = ps + (size_t)ICG_NBW * D.PST;         // [NgP][ICG_AVS]
-    double* xss = avs + (size_t)D.NgP * ICG_AVS;        // [Kp][4]
-    int* counter = reinterpret_cast<int*>(xss + (size_t)D.Kp * 4);
+    double* ps = smg;                                   // [ICG_NBW][PSTs]
+    double* avs = ps + (size_t)ICG_NBW * D.PSTs;        // [GCs * ICG_GC][ICG_AVS]
+    double* xss = avs + (size_t)D.GCs * ICG_GC * ICG_AVS;   // [4 KSs][4]
+    int* counter = reinterpret_cast<int*>(xss + (size_t)D.KSs * 16);
     const int tid = threadIdx.x, lane = tid & 31;
-    const int wb = blockIdx.x / A.S, split = blockIdx.x - wb * A.S;
+    // block -> (walker block, task split, gamma section, k-section)
+    int b = blockIdx.x;
+    const int ksec = b % D.nks; b /= D.nks;
+    const int gsec = b % D.ngs; b /= D.ngs;
+    const int wb = b / A.S, split = b - wb * A.S;
     const int w0 = wb * ICG_NBW;
-    for (int e = tid; e < ICG_NBW * D.Kp; e += ICG_NT) {
-        const int w = e / D.Kp, i = e - w * D.Kp;
-        ps[w * D.PST + i] = __ldg(A.gp + (size_t)(w0 + w) * D.Kp + i);
+    const int k0 = ksec * D.KSs, k1 = min(k0 + D.KSs, D.KS);            // k-steps of this section
+    const int gc0 = gsec * D.GCs, gc1 = min(gc0 + D.GCs, D.NGC);        // gamma chunks of this section
+    const int i0s = 4 * k0, ni = 4 * (k1 - k0), j0s = gc0 * ICG_GC, nj = (gc1 - gc0) * ICG_GC;
+    for (int e = tid; e < ICG_NBW * ni; e += ICG_NT) {
+        const int w = e / ni, i = e - w * ni;
+        ps[w * D.PSTs + i] = __ldg(A.gp + (size_t)(w0 + w) * D.Kp + i0s + i);
     }
-    for (int e = tid; e < ICG_NBW * D.NgP; e += ICG_NT) {
-        const int w = e / D.NgP, j = e - w * D.NgP;
-        avs[j * ICG_AVS + w] = __ldg(A.gav + (size_t)(w0 + w) * D.NgP + j);
+    for (int e = tid; e < ICG_NBW * nj; e += ICG_NT) {
+        const int w = e / nj, j = e - w * nj;
+        avs[j * ICG_AVS + w] = __ldg(A.gav + (size_t)(w0 + w) * D.NgP + j0s + j);
     }
-    for (int e = tid; e < D.Kp * 4; e += ICG_NT) xss[e] = __ldg(A.xs + e);
+    for (int e = tid; e < ni * 4; e += ICG_NT) xss[e] = __ldg(A.xs + (size_t)i0s * 4 + e);
     if (tid == 0) *counter = 0;
     __syncthreads();
     const int row = lane >> 2, kl = lane & 3;           // fragment coordinates: A[row][kl], B[kl][row], C[row][2 kl + {0,1}]
@@ -198,6 +224,7 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
         if (t >= D.ntasks) break;
         const int task = __ldg(A.tasks + t);
         const int og = task >> 16, gc = task & 0xffff;
+        if (gc < gc0 || gc >= gc1) continue;            // another gamma section's task
         double run[ICG_NB][2];
 #pragma unroll
         for (int nb = 0; nb < ICG_NB; ++nb) { run[nb][0] = 0.0; run[nb][1] = 0.0; }
@@ -205,18 +232,18 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
         const double2* pt = reinterpret_cast<const double2*>(A.ptg) + ((size_t)(og * D.NgP + gc * ICG_GC) * 8 + row) * 2;
         for (int pr = 0; pr < ICG_GC / 2; ++pr) {
             const ushort2 ki = __ldg(kin + pr);
-            const int ks0 = ki.x, ksc = ki.y;
-            if (ks0 >= D.KS) continue;                  // no active pair among the 8 x 2
-            const int j0 = gc * ICG_GC + 2 * pr;
+            const int ks0 = max((int)ki.x, k0), ksc = min(max((int)ki.y, k0), k1);
+            if (ks0 >= k1) continue;                    // no active pair among the 8 x 2 in this k-section
+            const int j0 = (gc - gc0) * ICG_GC + 2 * pr;                      // gamma index inside the staged section
             const double2 c0a = __ldg(pt + (size_t)(2 * pr) * 16), c0b = __ldg(pt + (size_t)(2 * pr) * 16 + 1);
             const double2 c1a = __ldg(pt + (size_t)(2 * pr + 1) * 16), c1b = __ldg(pt + (size_t)(2 * pr + 1) * 16 + 1);
             double C0[ICG_NB][2], C1[ICG_NB][2];
 #pragma unroll
             for (int nb = 0; nb < ICG_NB; ++nb) { C0[nb][0] = C0[nb][1] = C1[nb][0] = C1[nb][1] = 0.0; }
-            const double* pb = ps + row * D.PST + kl;
+            const double* pb = ps + row * D.PSTs + kl;
             int ks = ks0;
             for (; ks < ksc; ++ks) {                    // some pair may still have F <= 0 here: clamp
-                const int i = 4 * ks + kl;
+                const int i = 4 * (ks - k0) + kl;
                 const double2 xa = xs2[2 * i];          // {1/nu_i, (1/nu_i) 2 ln nu_i}
                 const double x2 = xss[4 * i + 2];
                 double F0 = fma(c0a.y, xa.x, c0a.x), F1 = fma(c1a.y, xa.x, c1a.x);
@@ -225,14 +252,14 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
                 F0 = clamp_neg_to_zero(F0); F1 = clamp_neg_to_zero(F1);      // function_IC[function_IC < 0.] = 0.
 #pragma unroll
                 for (int nb = 0; nb < ICG_NB; ++nb) {
-                    const double b = pb[(size_t)(8 * nb) * D.PST + 4 * ks];
-                    dmma884(C0[nb][0], C0[nb][1], F0, b);
-                    dmma884(C1[nb][0], C1[nb][1], F1, b);
+                    const double bv = pb[(size_t)(8 * nb) * D.PSTs + 4 * (ks - k0)];
+                    dmma884(C0[nb][0], C0[nb][1], F0, bv);
+                    dmma884(C1[nb][0], C1[nb][1], F1, bv);
                 }
             }
 #pragma unroll 2
-            for (; ks < D.KS; ++ks) {                   // q < 1 for every active pair: F > 0, the clamp is the identity
-                const int i = 4 * ks + kl;
+            for (; ks < k1; ++ks) {                     // q < 1 for every active pair: F > 0, the clamp is the identity
+                const int i = 4 * (ks - k0) + kl;
                 const double2 xa = xs2[2 * i];
                 const double x2 = xss[4 * i + 2];
                 double F0 = fma(c0a.y, xa.x, c0a.x), F1 = fma(c1a.y, xa.x, c1a.x);
@@ -240,9 +267,9 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
                 F0 = fma(c0b.y, x2, F0); F1 = fma(c1b.y, x2, F1);
 #pragma unroll
                 for (int nb = 0; nb < ICG_NB; ++nb) {
-                    const double b = pb[(size_t)(8 * nb) * D.PST + 4 * ks];
-                    dmma884(C0[nb][0], C0[nb][1], F0, b);
-                    dmma884(C1[nb][0], C1[nb][1], F1, b);
+                    const double bv = pb[(size_t)(8 * nb) * D.PSTs + 4 * (ks - k0)];
+                    dmma884(C0[nb][0], C0[nb][1], F0, bv);
+                    dmma884(C1[nb][0], C1[nb][1], F1, bv);
                 }
             }
             // weighted sum over gamma: run[o, w] += av[w, gamma] * C[o, w]
@@ -257,7 +284,7 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
                 run[nb][1] = fma(a1.y, C1[nb][1], run[nb][1]);
             }
         }
-        double* out = A.part + ((size_t)gc * A.Wpad + w0) * D.NoPad + og * 8 + row;
+        double* out = A.part + (((size_t)ksec * D.NGC + gc) * A.Wpad + w0) * D.NoPad + og * 8 + row;
 #pragma unroll
         for (int nb = 0; nb < ICG_NB; ++nb) {
             out[(size_t)(8 * nb + 2 * kl) * D.NoPad] = run[nb][0];
@@ -273,15 +300,16 @@ __device__ __forceinline__ void icg_finish(const double* __restrict__ part, cons
         double s = 0.0;
         const double* __restrict__ p = part + (size_t)w * D.NoPad + o;
         const size_t st = (size_t)Wpad * D.NoPad;
+        const int nslots = D.nks * D.NGC;                   // (k-section, gamma chunk) slots, k-section-major
         int gc = 0;
-        for (; gc + 8 <= D.NGC; gc += 8) {                  // eight loads in flight, added in the fixed chunk order
+        for (; gc + 8 <= nslots; gc += 8) {                 // eight loads in flight, added in the fixed slot order
             double v[8];
 #pragma unroll
             for (int u = 0; u < 8; ++u) v[u] = __ldg(p + (size_t)(gc + u) * st);
 #pragma unroll
             for (int u = 0; u < 8; ++u) s += v[u];
         }
-        for (; gc < D.NGC; ++gc) s += __ldg(p + (size_t)gc * st);
+        for (; gc < nslots; ++gc) s += __ldg(p + (size_t)gc * st);
         QIC[o] = kPC.ic_pref * s;
     }
 }

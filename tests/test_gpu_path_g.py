@@ -108,7 +108,8 @@ def test_path_G_full_size_batch_and_device_packing():
     assert_spectra_close(got[0][0], N[:, 0], "run_many path G n_e")
 
 
-@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user", "lh_bbpl200", "lh_bbpl400"])
+@pytest.mark.parametrize("name", ["lh_shipped", "lh_bbpl", "lh_expand", "lh_nogg", "lh_user", "lh_bbpl200", "lh_bbpl400",
+                                  "lh_bbpl800"])
 def test_lehamoc_driver_path_G(name):
     """Path G under the LeHaMoC.py driver (hadronic flags 0; BASELINE config 5 is such a fixed-grid sweep): walkers 0 and 2
     of a shared-grid batch are the fixture's parameter set (every step against the unmodified script), walker 1 is
@@ -131,15 +132,24 @@ def test_lehamoc_driver_path_G(name):
         log_close(Npr, np.log10(NprR), f"{name}: path G vs path R n_p", tol=1e-11)
 
 
-def test_lehamoc_driver_path_G_limits():
-    """Grid 800 does not fit the contraction's shared-memory tiles (32 walkers x 800 target frequencies + 800 gammas):
-    refused with LHM_ERR_CAPACITY, the caller falls back to path R; a hadronic flag is refused outright."""
+def test_lehamoc_driver_path_G_limits(monkeypatch):
+    """A hadronic flag is refused outright.  The contraction's tiles (32 walkers x target frequencies + gammas x 32) are cut
+    into k- and gamma-sections when they outgrow shared memory (grid 800 at the full budget, lh_bbpl800 above); a small
+    budget forces sections at every size and must not change a bit of the result (every (task, section) has its own
+    slot of the partial-sum buffer, added in a fixed order -- but the order differs from the unsectioned one: 1e-12)."""
     from lehamoc_b200 import LeHaMoC, _lib
-    _, P = load_golden("lh_bbpl")
-    with pytest.raises(_lib.LhmError):
-        LeHaMoC.run([dict(P, grid_g_el=800., grid_nu=800., time_end=1.)] * 2, ic_path="G")
+    from test_lehamoc_driver import log_close
+    z, P = load_golden("lh_bbpl200")
     with pytest.raises(_lib.LhmError):
         LeHaMoC.run([dict(P, pg_pi_l_flag=1.)] * 2, ic_path="G")
+    sets = [dict(P), dict(P, B0=P["B0"] * 1.3, p_el=P["p_el"] + 0.1)]
+    _, N0, sed0, _, _ = LeHaMoC.run(sets, ic_path="G")
+    monkeypatch.setenv("LHM_ICG_SMEM_KB", "48")
+    _, N1, sed1, _, _ = LeHaMoC.run(sets, ic_path="G")
+    log_close(sed1[0], z["nuLnu"], "sectioned contraction vs LeHaMoC.py")
+    with np.errstate(divide="ignore"):
+        log_close(sed1, np.log10(sed0), "sectioned vs whole-grid contraction nuLnu", tol=1e-12)
+        log_close(N1, np.log10(N0), "sectioned vs whole-grid contraction n_e", tol=1e-12)
 
 
 def test_path_G_refuses_what_it_cannot_do():

@@ -19,7 +19,7 @@ ap.add_argument("--walkers", type=int, default=296)
 ap.add_argument("--grids", type=int, nargs="+", default=[100, 200, 400, 800])
 ap.add_argument("--check", type=int, default=0, help="grid size at which walker 0 is compared with the CPU oracle")
 ap.add_argument("--phases", action="store_true", help="per-phase cycle breakdown of thread 0 (run_lh_kernel counters)")
-ap.add_argument("--ic-path", default="R", choices=["R", "S", "G"], help="G: dense contraction over walkers (grid <= 400)")
+ap.add_argument("--ic-path", default="R", choices=["R", "S", "G"], help="G: dense contraction over walkers")
 a = ap.parse_args()
 z = np.load(os.path.join(ROOT, "tests", "golden", "lh_bbpl.npz"))
 BASE = dict(zip([str(k) for k in z["param_keys"]], [float(v) for v in z["param_vals"]]))

@@ -203,8 +203,8 @@ def config4(walkers=1024, reps=10, ic_path="R"):
 # ------------------------------------------------------------------------------------------------------
 def config5(grid=400, W=4096, reps=3, ic_path="G", time_end=10.):
     """Grid-resolution sweep point: LeHaMoC.py driver, external black body + power-law photon fields, batch W.  A
-    fixed-grid sweep shares its grids, so the IC emissivity runs as the dense contraction over walkers (path G) whenever
-    the contraction's tiles fit (grid <= 400); the per-walker path R is timed next to it."""
+    fixed-grid sweep shares its grids, so the IC emissivity runs as the dense contraction over walkers (path G, its tiles
+    cut into k- and gamma-sections beyond grid ~200); the per-walker path R is timed next to it."""
     from lehamoc_b200 import LeHaMoC
     from lehamoc_b200._lib import LhmError
     from lehamoc_b200.engine import Engine
