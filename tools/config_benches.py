@@ -46,7 +46,7 @@ def _timed(fn, reps, stream=None):
 
 
 # ------------------------------------------------------------------------------------------------------
-def config2(W=1184, reps=3, ic_path="R"):
+def config2(W=1184, reps=5, ic_path="R"):
     """LeMoC Parameters_Test3.txt: adiabatic expansion, 600 timesteps (tests/golden/test3_adiabatic.npz)."""
     from lehamoc_b200.engine import Engine
     from lehamoc_b200.setup_host import pack_script
@@ -85,7 +85,7 @@ TEST4 = dict(time_init=0., time_end=10., step_alg=2., PL_inj=0., g_min_el=0., g_
              BB_flag=0., temperature=5., GB_ext=0., PL_flag=0., dE_dV_ph=0., nu_min_ph=0., nu_max_ph=0., s_ph=2.01, User_ph=0.)
 
 
-def config3(W=148, reps=2, host_fit=True):
+def config3(W=148, reps=5, host_fit=True):
     """LeHaMoC.py Test 4 at full size (Tests.ipynb:780-833: Ng=300, Np=160, Nt=100, 5 steps, photopion + Bethe-Heitler
     losses and emissivities + neutrinos).  The host set-up of the Bethe-Heitler spline surfaces (interp_cs_BH_int, once
     per nu_tot range) is timed and reported next to the device time."""
