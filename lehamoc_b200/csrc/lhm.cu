@@ -970,6 +970,7 @@ struct lhm_handle {
     double* d_Nout;
     double* d_sed;
     // lhm_fit_logl_host: pinned staging (in | out), device input row block, packed [W, n] arrays, SEDs, likelihoods
+    double* d_corscr;         // cor_kernel -> cor_loop_kernel hand-over
     double* d_ggK; double* d_ggT; int* d_ggJ; int gg_rows;      // path G: gamma-gamma sample table of the batch
     double* fit_pin; double* fit_din; double* fit_arr; double* fit_sed; double* fit_logl; size_t fit_cap;
     size_t Nout_cap, sed_cap;
@@ -1165,7 +1166,7 @@ void lhm_destroy(lhm_handle* h) {
     cudaFree(h->fit_din); cudaFree(h->fit_arr); cudaFree(h->fit_sed); cudaFree(h->fit_logl);
     cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
     cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
-    cudaFree(h->d_ggK); cudaFree(h->d_ggT); cudaFree(h->d_ggJ);
+    cudaFree(h->d_ggK); cudaFree(h->d_ggT); cudaFree(h->d_ggJ); cudaFree(h->d_corscr);
     free_had_tabs(h);
     for (int i = 0; i < 2; ++i) if (h->ev_tab[i]) cudaEventDestroy(h->ev_tab[i]);
     for (int i = 0; i < 2 * LHM_G_MAXEV; ++i) if (h->evg[i]) cudaEventDestroy(h->evg[i]);
@@ -1316,10 +1317,14 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
 
 static int launch_cor(lhm_handle* h, double* out, cudaStream_t st) {
     CorArgs A; A.W = h->W; A.Ng = h->cfg.Ng; A.consts = h->consts; A.g_el = h->g_el; A.out = out;
+    if (!h->d_corscr)
+        CUDA_TRY(cudaMalloc(&h->d_corscr, (size_t)h->cfg.max_walkers * cor_scratch_doubles(h->cfg.Ng) * sizeof(double)));
+    A.scratch = h->d_corscr;
     CUDA_TRY(cudaEventRecord(h->ev[2], st));
     CUDA_TRY(ensure_dyn_smem(cor_kernel, cor_smem_bytes(h->cfg.Ng), g_smem_cor[h->device % MAX_DEV]));
     cor_kernel<<<h->W, COR_NT, cor_smem_bytes(h->cfg.Ng), st>>>(A);
-    g_launches++;
+    cor_loop_kernel<<<(h->W + COR_LOOP_WARPS - 1) / COR_LOOP_WARPS, COR_LOOP_WARPS * 32, 0, st>>>(A);
+    g_launches += 2;
     CUDA_TRY(cudaGetLastError());
     CUDA_TRY(cudaEventRecord(h->ev[3], st));
     h->ev_set[1] = true;
@@ -1429,7 +1434,7 @@ static int launch_icg(lhm_handle* h, int ev_slot) {
 }
 
 // the lock-step time loop of path G: n + 1 launches of the per-walker half-steps around n contractions
-static int run_pathG(lhm_handle* h, const RunArgs& A) {
+static int run_pathG(lhm_handle* h, const RunArgs& A, bool join_cor_late) {
     const int n = h->lock_steps;
     if (n < 1) return LHM_ERR_STATE;                    // lhm_set_lockstep must precede the run
     GArgs G;
@@ -1448,6 +1453,8 @@ static int run_pathG(lhm_handle* h, const RunArgs& A) {
     h->evg_n = 0;
     for (int k = 0; k <= n; ++k) {
         G.step = k; G.do_B = k >= 1; G.do_A = k < n;
+        G.R.cor = (k == 0) ? nullptr : A.cor;           // launch 0 solves no photon equation
+        if (k == 1 && join_cor_late) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         kern<<<h->W, NT, h->smem, h->stream>>>(G);
         g_launches++;
         CUDA_TRY(cudaGetLastError());
@@ -1466,8 +1473,13 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     if (h->W < 1) return LHM_ERR_STATE;
     CUDA_TRY(cudaSetDevice(h->device));
     const double* cor = nullptr;
+    bool join_late = false;
     if (h->cfg.Syn_emis_flag) {
-        if (h->cor_valid) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // launched by lhm_setup_batch
+        // the cor-factor launched by lhm_setup_batch on the second stream.  The fused kernels need it in their first
+        // photon solve; the lock-step loop of path G only in its SECOND launch (the first runs the half of step 1 that
+        // precedes the IC emissivity), so there the join waits until the first half-step and contraction are queued
+        if (h->cor_valid && h->pathG) join_late = true;
+        else if (h->cor_valid) CUDA_TRY(cudaStreamWaitEvent(h->stream, h->ev_join, 0));
         else {
             int rc = launch_cor(h, h->d_cor, h->stream);
             if (rc != LHM_OK) return rc;
@@ -1491,7 +1503,7 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     A.HD = hadtab_dims(h->L);
     CUDA_TRY(cudaEventRecord(h->ev[4], h->stream));
     if (h->pathG) {
-        int rc = run_pathG(h, A);
+        int rc = run_pathG(h, A, join_late);
         if (rc != LHM_OK) return rc;
     } else if (lh && h->cfg.driver == 2) {
         CUDA_TRY(ensure_dyn_smem(run_code_lh_kernel, h->smem, g_smem_codelh[h->device % MAX_DEV]));

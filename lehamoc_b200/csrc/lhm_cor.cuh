@@ -1,4 +1,5 @@
-// lhm_cor.cuh -- A5: cor_factor_syn_el (LeMoC/LeHaMoC_f.py:175-237), one 128-thread CTA per walker.
+// lhm_cor.cuh -- A5: cor_factor_syn_el (LeMoC/LeHaMoC_f.py:175-237): cor_kernel (tables, one 128-thread CTA per walker)
+// + cor_loop_kernel (the 200 timesteps, one warp per walker).
 //
 // The reference runs a private synchrotron-only simulation (B = 1e4 G, 200 implicit steps of
 // 0.1001 R0/c) and returns L_ph/L_e,inj at the end; its arguments are constants of a model, so it is
@@ -28,6 +29,7 @@ struct CorArgs {
     const double* consts;   // [W, LHM_NCONST]
     const double* g_el;     // [W, Ng]
     double* out;            // [W]
+    double* scratch;        // [W, cor_scratch_doubles(Ng)]: what cor_kernel hands to cor_loop_kernel
 };
 
 constexpr int COR_NT = 128;             // threads per walker (set-up by all four warps, time loop by warp 0)
@@ -36,6 +38,9 @@ constexpr int COR_NNU = 100;            // private frequency grid, LeHaMoC_f.py:
 
 // chunk arrays: element i of lane l stored at [i*32 + l] (conflict-free)
 __host__ __device__ inline int cor_chunk(int Ng) { return (Ng - 2 + 31) / 32; }
+// per-walker hand-over: m, binv, injdt, z, N (chunk arrays, [i*32 + lane]) then lam0[32], El, ends, zb
+__host__ __device__ inline size_t cor_scratch_doubles(int Ng) { return (size_t)5 * cor_chunk(Ng) * 32 + 32 + 4; }
+constexpr int COR_LOOP_WARPS = 4;       // walkers per CTA of cor_loop_kernel
 __host__ __device__ inline size_t cor_smem_bytes(int Ng) {
     const size_t NgP = (size_t)((Ng + 1) & ~1);
     // m, binv, injdt, z, N: 5 chunk arrays; g, lg, inj, zfull: 4 x Ng; zq: NQ x Ng; nu, lnu, cnu, lam0c: 4 x 100; e2tab
@@ -239,6 +244,31 @@ __global__ void __launch_bounds__(COR_NT) cor_kernel(CorArgs A) {
     const double El = warp_sum(El_part);
     ends = warp_sum(ends);
     const double zb = zfull[0] * 1e-160 + zfull[Ng - 1] * 1e-160;   // N_el[0] = N_el[-1] = 1e-160 (:195)
+    // hand-over to cor_loop_kernel (the time loop needs one warp and 160 registers per walker: kept out of this kernel,
+    // whose other three warps would hold their registers for nothing while it runs)
+    double* sc = A.scratch + (size_t)w * cor_scratch_doubles(Ng);
+    for (int s = lane; s < CS; s += 32) {
+        sc[s] = m_[s]; sc[CS + s] = binv[s]; sc[2 * CS + s] = injdt[s]; sc[3 * CS + s] = z[s]; sc[4 * CS + s] = 0.0;
+    }
+    double* tail = sc + 5 * CS;
+    tail[lane] = lam0_part;
+    if (lane == 0) { tail[32] = El; tail[33] = ends; tail[34] = zb; }
+}
+
+// the 200 implicit timesteps (:204-236) as a time-skewed wavefront, one warp per walker
+__global__ void __launch_bounds__(COR_LOOP_WARPS * 32) cor_loop_kernel(CorArgs A) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int w = blockIdx.x * COR_LOOP_WARPS + warp;
+    if (w >= A.W) return;                                    // whole warp exits together
+    const int Ng = A.Ng, Cn = cor_chunk(Ng), CS = Cn * 32;
+    const PhysConst& pc = kPC;
+    const double R0 = A.consts[(size_t)w * LHM_NCONST + LHM_C_R0];
+    double* sc = A.scratch + (size_t)w * cor_scratch_doubles(Ng);
+    const double* m_ = sc; const double* binv = sc + CS; const double* injdt = sc + 2 * CS; const double* z = sc + 3 * CS;
+    double* Nn = sc + 4 * CS;
+    const double* tail = sc + 5 * CS;
+    const double lam0_part = tail[lane], El = tail[32], ends = tail[33], zb = tail[34];
+    const double dt = 0.1001 * R0 / pc.c;                    // LeHaMoC_f.py:205
     const double bph = 1.0 + dt * (pc.c / R0);               // photon equation is diagonal (:226)
     CorClock ck;
     ck.t = 0.0; ck.day = 0.0; ck.t_end = 20.0 * R0 / pc.c; ck.dt = dt; ck.period = 1.0 * R0 / pc.c;
