@@ -454,7 +454,7 @@ def main():
     #      kernel, D2H into pinned memory, results touched on the host.  At N > 1 the exchange step is inside as well:
     #      the SEDs of the batch are all-gathered over NCCL from the engine's device buffer and the gathered rows are what
     #      is copied to the host (every rank ends up with every walker's SED, like shard.evaluate_sharded).
-    E2E_DEPTH = 3                                   # batches in flight: one engine + CUDA stream + worker thread each
+    E2E_DEPTH = int(os.environ.get("LHM_E2E_DEPTH", "3"))   # batches in flight: one engine + worker thread each
     e2e_engines = [None] * E2E_DEPTH
     e2e_engines_h = [None] * E2E_DEPTH
     gathered_host = torch.empty((world * W, eng.Nt), dtype=torch.float64, pin_memory=True) if world > 1 else None

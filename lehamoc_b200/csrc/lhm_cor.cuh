@@ -209,6 +209,11 @@ __global__ void __launch_bounds__(COR_NT) cor_kernel(CorArgs A) {
                 double x[4], Ev[4];
 #pragma unroll
                 for (int u = 0; u < 4; ++u) x[u] = nu[min(k + u, k1 - 1)] * inv;
+                if (x[0] > 745.2) break;                    // x grows with k: exp(-x) == 0 from here on
+                if (x[3] < SYN_XSMALL) {                    // the whole batch in the range of the four-term series
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) Ev[u] = exp_neg_small(x[u]);
+                } else
                 fast_exp_neg<4>(x, Ev, e2tab);
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
