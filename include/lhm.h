@@ -125,6 +125,13 @@ int lhm_setup_batch(lhm_handle*, int W, const double* consts, const double* g_el
 /* ic_path G only: the number of timesteps every walker of the following batches runs (the lock-step loop is driven by
  * the host: nsteps + 1 launches of the per-walker half-steps around nsteps contractions; LeMoC.py:196 range(int(time_end))). */
 int lhm_set_lockstep(lhm_handle*, int nsteps);
+/* Ensembles smaller than the machine (the reference's fit: 24 walkers per emcee half-ensemble, Fit_emcee/fit_emcee.py:
+ * 225-242): evolve every walker on a thread-block CLUSTER of 2, 4 or 8 CTAs (1 restores the one-CTA kernel).  All CTAs keep
+ * the state and run the cheap phases redundantly; IC tiles, gamma-gamma rows and synchrotron / SSA rows are dealt to the
+ * CTAs and exchanged through distributed shared memory.  Leptonic drivers, IC path R.  Results equal the one-CTA kernel's up
+ * to the association of the IC partial sums (1e-15); the setting, not the batch size, decides the bits, so sharded and
+ * unsharded evaluations of the same walkers still agree bit for bit when they use the same setting. */
+int lhm_set_cluster(lhm_handle*, int ctas_per_walker);
 /* ic_path G only: mean device time of the contraction launches of the last run (CUDA events on the stream), how many
  * were timed, the grid size and the dynamic shared memory per CTA */
 int lhm_last_icg_timing(lhm_handle*, float* mean_ms, int* launches, int* ctas, int* smem_bytes);

@@ -72,6 +72,7 @@ SIGNATURES = {
     "lhm_last_timings": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float)]),
     "lhm_set_phase_profile": (C.c_int, [_P, _P]),
     "lhm_set_lockstep": (C.c_int, [_P, C.c_int]),
+    "lhm_set_cluster": (C.c_int, [_P, C.c_int]),
     "lhm_fit_logl_host": (C.c_int, [_P, C.POINTER(lhm_pack_args), _P, C.POINTER(lhm_fit_obs), _P]),
     "lhm_last_hadtab_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "lhm_last_icg_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),

@@ -1,6 +1,7 @@
 // lhm.cu -- liblhm.so: kernels + C ABI (include/lhm.h).  Build: see lehamoc_b200/build.py
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -shared -Xcompiler -fPIC lhm.cu -o liblhm.so
 #include <cuda_runtime.h>
+#include <cooperative_groups.h>
 #include <algorithm>
 #include <atomic>
 #include <cmath>
@@ -170,6 +171,121 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
             __syncthreads();
         }
     }
+}
+
+// =================================================================================================
+// run_kernel for ensembles smaller than the machine (the reference's own fit has 24 walkers per half-ensemble: 24 CTAs
+// on 148 SMs): one walker per thread-block CLUSTER.  Every CTA of the cluster keeps the whole state in its shared memory
+// and runs the cheap serial phases redundantly (identical arithmetic, identical results); the three phases that cost --
+// IC tiles, gamma-gamma rows, synchrotron / SSA rows -- are dealt to the CTAs, and what the others need is fetched from
+// the owner's shared memory (DSMEM) behind a cluster barrier: three barriers per timestep.  The IC partial sums of all
+// CTAs are added in a fixed (CTA, warp) order: deterministic, equal to run_kernel up to the association of that sum.
+// Path R, leptonic drivers; lhm_set_cluster(handle, 2 | 4 | 8).
+// =================================================================================================
+__global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_cluster_kernel(RunArgs A) {
+    namespace cg = cooperative_groups;
+    extern __shared__ __align__(16) double smem_raw[];
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CS = (int)cluster.num_blocks(), rank = (int)cluster.block_rank();
+    // lanes per row in the two row phases: as many (a power of two <= 8) as leave every row of this CTA a lane group
+    int tpr = 1;
+    {
+        const int rows_cta = (max(A.L.Ns + A.L.Ni, A.L.Ni + A.L.Ng - 1) + CS - 1) / CS;
+        while (tpr < 8 && rows_cta * (2 * tpr) <= NT) tpr *= 2;
+    }
+    const Part part{rank, CS, tpr};
+    const int w = blockIdx.x / CS;
+    const int tid = threadIdx.x;
+    Smem S;
+    carve(S, smem_raw, A.L, NW);
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, A.Ecache, A.ptab, A.ptab_shared, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    const double cor = A.cor ? A.cor[w] : 1.0;
+    if (nsteps < 1) { if (rank == 0) no_step_outputs<NT>(A, w, Ng, Nt, 0); return; }     // the whole cluster leaves together
+    for (int j = tid; j < Ng; j += NT) {
+        S.N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];
+        S.qee[j] = 0.0;
+    }
+    for (int k = tid; k < Ns; k += NT) { S.psyn[k] = LHM_SENT; S.Qsyn[k] = 0.0; S.aS[k] = 0.0; }
+    for (int k = tid; k < Ni; k += NT) { S.pic[k] = LHM_SENT; S.agg[k] = 0.0; S.QIC[k] = 0.0; S.aI[k] = 0.0; }
+    ic_prepare<NT>(C, S);
+    const int No = Ni - 1, NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
+    double t = C.tinit;
+    for (int step = 0; step < nsteps; ++step) {
+        t += C.dt;                                               // LeMoC.py:198-201
+        C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.V = volume_of(C.Rad);
+        if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
+        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        phase_electrons<NT>(C, S);
+        if (C.F.syn_e || C.F.ssa || C.F.ic_e) phase_vectors<NT>(C, S);
+        phase_syn_rows_split<NT>(C, S, part);
+        if (C.F.ic_e) phase_ic_R<NT>(C, S, part);
+        cluster.sync();                                          // [A] every CTA's rows and IC partial sums are in place
+        if (C.F.syn_e || C.F.ssa) {                              // rows from their owners (row % CS)
+            for (int k = tid; k < Ns; k += NT) {
+                const int owner = k % CS;
+                if (owner != rank) { S.Qsyn[k] = cluster.map_shared_rank(S.Qsyn, owner)[k]; S.aS[k] = cluster.map_shared_rank(S.aS, owner)[k]; }
+            }
+            for (int k = tid; k < Ni; k += NT) {
+                const int owner = (Ns + k) % CS;
+                if (owner != rank) S.aI[k] = cluster.map_shared_rank(S.aI, owner)[k];
+            }
+        }
+        if (C.F.ic_e) {                                          // Q_IC = 3/4 sigma_T c x the partial sums of all CTAs and warps
+            for (int o = tid; o < No; o += NT) {
+                double s = 0.0;
+                for (int c = 0; c < CS; ++c) {
+                    const double* P = cluster.map_shared_rank(S.partial, c);
+                    for (int wv = 0; wv < IC_NW; ++wv) s += P[wv * NiPad + o];
+                }
+                S.QIC[o] = kPC.ic_pref * s;
+            }
+        }
+        cluster.sync();                                          // [A2] the partial sums are consumed: their scratch is free again
+        phase_photon_solves<NT>(C, S, cor);
+        if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
+            const double* Lng = S.Ln;
+            if (C.F.qee_from_ic) {
+                for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
+                __syncthreads();
+                Lng = S.Lic;
+            }
+            phase_gg_split<NT>(C, S, Lng, S.agg, S.qee, part);
+            cluster.sync();                                      // [B]
+            const int nrows = Ni + (Ng - 1);
+            for (int row = tid; row < nrows; row += NT) {
+                const int owner = row % CS;
+                if (owner == rank) continue;
+                if (row < Ni) S.agg[row] = cluster.map_shared_rank(S.agg, owner)[row];
+                else S.qee[row - Ni] = cluster.map_shared_rank(S.qee, owner)[row - Ni];
+            }
+            __syncthreads();
+        }
+        const bool last = (step == nsteps - 1);
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && last)) {
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.sed_out) {
+                phase_photons<NT>(C, S, false);
+                if (rank == 0) {
+                    double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                    for (int k = tid; k < Nt; k += NT)
+                        o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+                }
+            }
+            if (A.N_out && rank == 0) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT) o[j] = S.N[j] / C.V;
+            }
+            __syncthreads();
+        }
+    }
+    cluster.sync();                                              // no CTA leaves while a neighbour may still read its shared memory
 }
 
 // =================================================================================================
@@ -933,7 +1049,7 @@ constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the regis
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
 static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
-    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV];
+    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -950,6 +1066,7 @@ struct lhm_handle {
     StepFlags F;
     int device;
     cudaStream_t stream;
+    int cluster;              // lhm_set_cluster: CTAs per walker of the fused leptonic kernel (1: run_kernel)
     int W;                    // walkers of the current batch (0 = none)
     size_t smem;
     double* d_tabd;
@@ -1518,6 +1635,16 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
             CUDA_TRY(ensure_dyn_smem(run_lh_kernel<NT, 2>, h->smem, g_smem_lh2[h->device % MAX_DEV]));
             run_lh_kernel<NT, 2><<<h->W, NT, h->smem, h->stream>>>(A);
         }
+    } else if (h->cluster > 1 && h->F.ic_path == LHM_IC_PATH_R) {
+        CUDA_TRY(ensure_dyn_smem(run_cluster_kernel, h->smem, g_smem_runc[h->device % MAX_DEV]));
+        cudaLaunchConfig_t lc = {};
+        lc.gridDim = dim3((unsigned)(h->W * h->cluster)); lc.blockDim = dim3(NT);
+        lc.dynamicSmemBytes = h->smem; lc.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)h->cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        lc.attrs = at; lc.numAttrs = 1;
+        CUDA_TRY(cudaLaunchKernelEx(&lc, run_cluster_kernel, A));
     } else {
         CUDA_TRY(ensure_dyn_smem(run_kernel, h->smem, g_smem_run[h->device % MAX_DEV]));
         run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
@@ -1561,6 +1688,13 @@ int lhm_last_hadtab_timing(lhm_handle* h, float* ms, int* table_sets, long long*
         *bytes = (long long)(h->htab_sets * ((F.bh_e ? h->HTab.bh_stride * 20 : 0) + (F.pg_e ? h->HTab.phi_stride * 8 : 0)
                                              + (F.pg_l ? h->HTab.loss_stride * 20 : 0)));
     }
+    return LHM_OK;
+}
+
+int lhm_set_cluster(lhm_handle* h, int ctas_per_walker) {
+    if (!h || (ctas_per_walker != 1 && ctas_per_walker != 2 && ctas_per_walker != 4 && ctas_per_walker != 8)) return LHM_ERR_ARG;
+    if (ctas_per_walker > 1 && (h->cfg.driver != 0 || h->pathG || h->F.ic_path != LHM_IC_PATH_R)) return LHM_ERR_STATE;
+    h->cluster = ctas_per_walker;
     return LHM_OK;
 }
 

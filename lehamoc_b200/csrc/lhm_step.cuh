@@ -27,6 +27,11 @@ __host__ __device__ inline bool any_hadronic(const StepFlags& F) {
     return F.pg_l || F.bh_l || F.pg_e || F.bh_e || F.pp_l || F.pp_ee || F.pp_g || F.pp_nu;
 }
 
+// A walker evolved by a thread-block CLUSTER (run_cluster_kernel): every CTA keeps the whole state and runs the cheap
+// serial phases redundantly; the three expensive phases deal their rows / tiles to the CTAs (rank of count) and the
+// results are exchanged through distributed shared memory.  {0, 1} is the single-CTA case.
+struct Part { int rank, count; int tpr = 1; };      // tpr: lanes that share one row in the *_split phases (power of two <= 8)
+
 // shared-memory carve-up; all pointers are into dynamic shared memory
 struct Smem {
     double *N, *psyn, *pic, *agg, *qee;          // state
@@ -529,7 +534,7 @@ __device__ __forceinline__ void ic_acc_if_nonneg(double& acc, double p, double F
 }
 
 template <int NT>
-__device__ void phase_ic_R(const Ctx& C, Smem& S) {
+__device__ void phase_ic_R(const Ctx& C, Smem& S, Part cta = Part{0, 1}) {
     const Layout& L = C.L;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int Ng = L.Ng, No = L.Ni - 1, Ntar = L.Nt - 1;
@@ -538,7 +543,12 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S) {
     double* part = S.partial + warp * NiPad;
     for (int o = lane; o < NiPad; o += 32) part[o] = 0.0;
     __syncwarp();
-    const int t0 = S.tbound[warp], t1 = S.tbound[warp + 1];
+    int t0 = S.tbound[warp], t1 = S.tbound[warp + 1];
+    if (cta.count > 1) {                            // this CTA's contiguous share of the warp's static tile range
+        const int n = t1 - t0;
+        t1 = t0 + (int)(((long long)n * (cta.rank + 1)) / cta.count);
+        t0 = t0 + (int)(((long long)n * cta.rank) / cta.count);
+    }
     const int osub = lane >> 2, gsub = lane & 3;
     int cur_og = -1;
     double run = 0.0;
@@ -753,9 +763,10 @@ __host__ __device__ inline int gg_batches(int NP) { return (NP + GG_U - 1) / GG_
 
 // The grid-only part of a row: for every batch of GG_U samples e0..e0+GG_U-1 the np.interp bracket j, the position t in
 // it and the static factor Kv = w_e * cf * (1 - s_e^-2) * ln s_e, handed to emit(e0, j, t, Kv).  y_e = a + e*step.
+// bstart / bstride: the batches bstart, bstart + bstride, ... only (several lanes sharing a row); 0 / 1 is the whole row.
 template <class Emit>
 __device__ __forceinline__ void gg_row_samples(const Smem& S, int Nt, int NP, double a, double step, double cf, double r2,
-                                               bool is_a, Emit&& emit) {
+                                               bool is_a, Emit&& emit, int bstart = 0, int bstride = 1) {
     const double* __restrict__ lxt = S.lxtS;
     const double* __restrict__ ilx = S.ilxS;
     const double lx0 = lxt[0], lxN = lxt[Nt - 1];
@@ -775,15 +786,22 @@ __device__ __forceinline__ void gg_row_samples(const Smem& S, int Nt, int NP, do
     double ed[GG_U];
 #pragma unroll
     for (int u = 0; u < GG_U; ++u) ed[u] = (double)u;
-    for (int e0 = 0; e0 < NP; e0 += GG_U) {
+    double rUs = rU;                                    // r2^(GG_U bstride): what a lane's s^-2 advances by per batch
+    for (int q = 1; q < bstride; ++q) rUs *= rU;
+    for (int q = 0; q < bstart; ++q) {
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) { inv[u] *= rU; ed[u] += (double)GG_U; }
+    }
+    const double edstep = (double)(GG_U * bstride);
+    for (int e0 = bstart * GG_U; e0 < NP; e0 += GG_U * bstride) {
         double y[GG_U], Kv[GG_U], t[GG_U];
         int j[GG_U];
 #pragma unroll
         for (int u = 0; u < GG_U; ++u) {
             y[u] = fma(ed[u], step, a);
             Kv[u] = dlcf * (1.0 - inv[u]) * fma(ed[u], dl, lns0);
-            inv[u] *= rU;
-            ed[u] += (double)GG_U;
+            inv[u] *= rUs;
+            ed[u] += edstep;
         }
         // trapezoid end weights and the exact last abscissa: only the first and the last batch (uniform branches)
         if (e0 == 0) Kv[0] *= 0.5;
@@ -888,6 +906,115 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
             if (2.0 * S.gS[r] > 1.0)
                 ng = exp10(interp_eval(Lng, C.TIs[L.q_j + r], C.Ts[L.q_dx + r], C.Ts[L.q_Dx + r]));
             qee_out[r] = kPC.qee_pref * (ng * s);
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The two row phases for a walker evolved by a CLUSTER (run_cluster_kernel): the rows are dealt round-robin to the CTAs,
+// which leaves a CTA with fewer rows than threads -- so `tpr` lanes share a row (interleaved gamma pairs / sample
+// batches, joined by an xor-shuffle tree): the phase shrinks with the cluster size instead of staying one row long.
+template <int NT>
+__device__ void phase_syn_rows_split(const Ctx& C, Smem& S, Part part) {
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni;
+    const bool need_q = C.F.syn_e, need_a = C.F.ssa;
+    if (!need_q && !need_a) return;
+    constexpr int NR = 32;
+    const int nrows = Ns + (need_a ? Ni : 0);
+    const double qpref = kPC.C_syn * pow(C.B, 2.0 / 3.0);
+    const double apref = kPC.ssa_pref * C.B;
+    const int tpr = part.tpr, grp = threadIdx.x / tpr, sub = threadIdx.x % tpr, ngrp = NT / tpr;
+    for (int base = 0; base < nrows; base += part.count * ngrp) {        // the same trip count for every lane of a warp
+        const int row = base + part.rank + part.count * grp;
+        const bool is_syn = row < Ns;
+        const int k = is_syn ? row : row - Ns;
+        bool act = row < nrows && k != 0 && !(is_syn ? (k > Ns - 2) : (k > Ni - 2));   // [1:] / [1:-1], LeMoC.py:268-276
+        const bool do_q = act && is_syn && need_q && (k < Ns - 1);
+        double sq0 = 0.0, sq1 = 0.0, sa0 = 0.0, sa1 = 0.0;
+        if (act) {
+            const double nu = is_syn ? C.T[L.nsyn + k] : C.Ts[L.nic + k];
+            const int jm = do_q ? C.TI[L.jm_syn + k] : Ng;
+            int jz, jx;
+            const double* __restrict__ Et = nullptr;
+            if (C.E) {
+                Et = C.E + ecache_index(row, 0, Ng);
+                jz = C.TI[L.jz + row] & ~1; jx = C.TI[L.jx + row];
+            } else {
+                int lo = 0, hi = Ng;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (nu * S.inuc[mid] > 745.2) lo = mid + 1; else hi = mid; }
+                jz = lo & ~1;
+                hi = Ng;
+                while (lo < hi) { const int mid = (lo + hi) >> 1; if (!(nu * S.inuc[mid] < SYN_XSMALL)) lo = mid + 1; else hi = mid; }
+                jx = min((lo + 1) & ~1, Ng & ~1);
+            }
+            for (int j = jz + 2 * sub; j < Ng; j += 2 * tpr) {            // this lane's gamma pairs (j, j + 1)
+                const bool two = j + 1 < Ng;
+                double x[2], Ev[2];
+                x[0] = nu * S.inuc[j]; x[1] = nu * S.inuc[min(j + 1, Ng - 1)];
+                if (j >= jx && x[0] < SYN_XSMALL) { Ev[0] = exp_neg_small(x[0]); Ev[1] = exp_neg_small(x[1]); }
+                else if (Et) { Ev[0] = __ldg(Et + (size_t)j * NR); Ev[1] = two ? __ldg(Et + (size_t)(j + 1) * NR) : 0.0; }
+                else fast_exp_neg<2>(x, Ev, S.e2tab);
+                if (j >= jm) sq0 = fma(Ev[0], S.u[j], sq0);
+                sa0 = fma(Ev[0], S.v[j], sa0);
+                if (two) {
+                    if (j + 1 >= jm) sq1 = fma(Ev[1], S.u[j + 1], sq1);
+                    sa1 = fma(Ev[1], S.v[j + 1], sa1);
+                }
+            }
+        }
+        double sq = sq0 + sq1, sa = sa0 + sa1;
+        for (int d = tpr >> 1; d > 0; d >>= 1) {
+            sq += __shfl_xor_sync(0xffffffffu, sq, d);
+            sa += __shfl_xor_sync(0xffffffffu, sa, d);
+        }
+        if (act && sub == 0) {
+            if (is_syn) {
+                if (k < Ns - 1) S.Qsyn[k] = do_q ? qpref * C.T[L.nm23s + k] * sq : 0.0;
+                S.aS[k] = need_a ? apref * C.T[L.nm53s + k] * sa : 0.0;
+            } else {
+                S.aI[k] = apref * C.Ts[L.nm53i + k] * sa;
+            }
+        }
+    }
+}
+
+template <int NT>
+__device__ void phase_gg_split(const Ctx& C, Smem& S, const double* Lng, double* agg_out, double* qee_out, Part part) {
+    const Layout& L = C.L;
+    const int NP = L.NP, Ni = L.Ni, Ng = L.Ng, Nt = L.Nt;
+    const int nrows = Ni + (Ng - 1);
+    const int tpr = part.tpr, grp = threadIdx.x / tpr, sub = threadIdx.x % tpr, ngrp = NT / tpr;
+    for (int base = 0; base < nrows; base += part.count * ngrp) {
+        const int row = base + part.rank + part.count * grp;
+        const bool act = row < nrows;
+        const bool is_a = row < Ni;
+        const int r = act ? (is_a ? row : row - Ni) : 0;
+        double acc[GG_U];
+#pragma unroll
+        for (int u = 0; u < GG_U; ++u) acc[u] = 0.0;
+        if (act) {
+            const double a = __ldg(C.Ts + (is_a ? L.agg_a : L.qee_a) + r);
+            const double step = __ldg(C.Ts + (is_a ? L.agg_d : L.qee_d) + r);
+            const double cf = __ldg(C.Ts + (is_a ? L.agg_c : L.qee_c) + r);
+            const double r2 = __ldg(C.Ts + (is_a ? L.agg_r2 : L.qee_r2) + r);
+            gg_row_samples(S, Nt, NP, a, step, cf, r2, is_a,
+                           [&](int, const int (&j)[GG_U], const double (&t)[GG_U], const double (&Kv)[GG_U]) {
+                               gg_batch_acc(S.Lm, S.e2tab, j, t, Kv, acc);
+                           }, sub, tpr);
+        }
+        double s = acc[0];
+#pragma unroll
+        for (int u = 1; u < GG_U; ++u) s += acc[u];
+        for (int d = tpr >> 1; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+        if (act && sub == 0) {
+            if (is_a) agg_out[r] = s;
+            else {
+                double ng = 0.0;
+                if (2.0 * S.gS[r] > 1.0)
+                    ng = exp10(interp_eval(Lng, C.TIs[L.q_j + r], C.Ts[L.q_dx + r], C.Ts[L.q_Dx + r]));
+                qee_out[r] = kPC.qee_pref * (ng * s);
+            }
         }
     }
 }

@@ -60,6 +60,12 @@ class Engine:
         self.W = 0
         self._keep = None           # device inputs of the current batch (the library reads them again)
 
+    def set_cluster(self, ctas_per_walker: int):
+        """Evolve every walker on a thread-block cluster of 2, 4 or 8 CTAs (lhm_set_cluster): for ensembles smaller than
+        the GPU (148 SMs), where one CTA per walker leaves most of the machine idle.  Leptonic drivers, ic_path 'R'."""
+        check(self.lib.lhm_set_cluster(self.h, int(ctas_per_walker)), "lhm_set_cluster")
+        self.cluster = int(ctas_per_walker)
+
     def close(self):
         if getattr(self, "h", None):
             self.lib.lhm_destroy(self.h)

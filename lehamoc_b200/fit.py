@@ -94,9 +94,15 @@ class FitEvaluator:
     """Owns the engine, the frozen parameter file and the device copy of the observed SED."""
 
     def __init__(self, x, y, yerr, yerr1, flags, param_file="Parameters.txt", D=D_DEFAULT, z=Z_DEFAULT,
-                 ic_path="R", device=None, flag_c="LeMoC", device_pack=True):
+                 ic_path="R", device=None, flag_c="LeMoC", device_pack=True, cluster=1):
+        """cluster = 2 | 4 | 8 (flag_c 'LeMoC', ic_path 'R'): every walker on a thread-block cluster of that many CTAs
+        (Engine.set_cluster) -- for ensembles smaller than the GPU, like the reference's own 24 walkers per half-ensemble.
+        The setting decides the last bits of the result, not the ensemble size."""
         if flag_c not in ("LeMoC", "LeHaMoC"):
             raise ValueError("flag_c must be 'LeMoC' or 'LeHaMoC' (fit_emcee.py:23)")
+        if int(cluster) != 1 and (flag_c != "LeMoC" or ic_path != "R"):
+            raise ValueError("cluster > 1 needs flag_c 'LeMoC' and ic_path 'R'")
+        self.cluster = int(cluster)
         self.flag_c = flag_c
         self.device_pack = bool(device_pack)    # False: NumPy set-up on the host (bit-identical grids, 2-3x slower)
         self.nfree = 6 if flag_c == "LeMoC" else 10                 # free parameters of the numerical model
@@ -128,6 +134,8 @@ class FitEvaluator:
             if self.eng is not None:
                 self.eng.close()
             self.eng = Engine(batch.cfg, max(batch.W, 64), ic_path=self.ic_path, device=self.device)
+            if self.cluster > 1:
+                self.eng.set_cluster(self.cluster)
         return self.eng
 
     def model_and_loglike(self, thetas, want_model=False):
@@ -197,11 +205,11 @@ class FitEvaluator:
 _evaluators = {}
 
 
-def _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c="LeMoC"):
-    key = (param_file if isinstance(param_file, str) else id(param_file), D, z, ic_path, flag_c)
+def _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c="LeMoC", cluster=1):
+    key = (param_file if isinstance(param_file, str) else id(param_file), D, z, ic_path, flag_c, cluster)
     ev = _evaluators.get(key)
     if ev is None:
-        ev = FitEvaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c=flag_c)
+        ev = FitEvaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c=flag_c, cluster=cluster)
         _evaluators[key] = ev
     else:
         ev.set_data(x, y, yerr, yerr1, flags)
@@ -240,9 +248,10 @@ def log_likelihood_LeHaMoC(theta, x, y, yerr, yerr1, flags, param_file="Paramete
 
 
 def log_probability_batch(thetas, x, y, yerr, yerr1, flags, flag_c="LeMoC", param_file="Parameters.txt",
-                          D=D_DEFAULT, z=Z_DEFAULT, ic_path="R"):
-    """fit_emcee.py:190-199 for thetas [W, 8] (LeMoC) or [W, 12] (LeHaMoC) at once -> [W]."""
-    return _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c).log_probability_sharded(thetas)
+                          D=D_DEFAULT, z=Z_DEFAULT, ic_path="R", cluster=1):
+    """fit_emcee.py:190-199 for thetas [W, 8] (LeMoC) or [W, 12] (LeHaMoC) at once -> [W].  cluster: CTAs per walker
+    (FitEvaluator), worth 2-8 for ensembles of a few dozen walkers."""
+    return _evaluator(x, y, yerr, yerr1, flags, param_file, D, z, ic_path, flag_c, cluster).log_probability_sharded(thetas)
 
 
 def log_probability(theta, x, y, yerr, yerr1, flags, flag_c):
@@ -367,7 +376,9 @@ def main(argv=None):
     init = [*params, -2]
     pos = init + 1e-2 * np.random.default_rng(0).standard_normal((48, len(init)))   # fit_emcee.py:224-225
     start = time.perf_counter()
-    fn = lambda th: log_probability_batch(th, xd, yd, yderr_hi, yderr_lo, flags, flag_c)
+    # 24 walkers per half-ensemble on a 148-SM GPU: four CTAs per walker (thread-block clusters) for the SSC model
+    cl = 4 if flag_c == 'LeMoC' else 1
+    fn = lambda th: log_probability_batch(th, xd, yd, yderr_hi, yderr_lo, flags, flag_c, cluster=cl)
     res = run_mcmc(fn, pos, steps, progress=True, chain_file=os.path.join(directory, "out.npz"),
                    checkpoint_every=max(1, min(100, steps // 10)))
     if rank == 0:

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import lehamoc_oracle as orc
-from util import GOLD, load_golden
+from util import GOLD, assert_spectra_close, load_golden
 
 
 @pytest.fixture(scope="module")
@@ -162,6 +162,48 @@ def test_gpu_one_call_fit_evaluation_equals_the_staged_path(gold):
     lpb = ev.log_probability(bad)
     assert np.isneginf(lpb[[1, 6]]).all()
     np.testing.assert_array_equal(np.delete(lpb, [1, 6]), np.delete(ev.log_probability(gold["theta8"]), [1, 6]))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("cluster", [2, 4, 8])
+def test_gpu_cluster_per_walker_matches_one_cta(gold, cluster):
+    """One walker per thread-block cluster (run_cluster_kernel: IC tiles, gamma-gamma rows and synchrotron rows dealt to
+    the CTAs, exchanged through distributed shared memory) against the one-CTA kernel: same log-probabilities up to the
+    association of the IC partial sums, the reference's numbers at the usual tolerance, spectra at 1e-12, and the result
+    of a walker does not depend on the ensemble it is evaluated in (bit for bit)."""
+    from lehamoc_b200 import Code, fit
+    from lehamoc_b200.engine import Engine
+    from lehamoc_b200.presets import fit_walkers
+    from lehamoc_b200.setup_host import pack_code
+    _, P = load_golden("code_fit")
+    kw = dict(param_file=P, D=float(gold["D_Mpc"]), z=float(gold["z"]))
+    data = (gold["xd"], gold["yd"], gold["yerr_hi"], gold["yerr_lo"], gold["flags"])
+    ev1 = fit.FitEvaluator(*data, **kw)
+    evc = fit.FitEvaluator(*data, cluster=cluster, **kw)
+    rng = np.random.default_rng(cluster)
+    th = np.column_stack([fit_walkers(37, seed=5), rng.uniform(0.8, 2.2, 37), rng.uniform(-4., -1., 37)])
+    lp1, lpc = ev1.log_probability(th), evc.log_probability(th)
+    ok = np.isfinite(lp1)
+    assert np.array_equal(ok, np.isfinite(lpc)) and ok.sum() > 20
+    np.testing.assert_allclose(lpc[ok], lp1[ok], rtol=1e-9)
+    np.testing.assert_allclose(evc.log_probability(gold["theta8"]), gold["logprob"], rtol=1e-6)
+    np.testing.assert_array_equal(evc.log_probability(th[5:19]), lpc[5:19])          # batch independence, bitwise
+    # spectra and electron distributions, every snapshot
+    b = pack_code(th[:9, :6], P)
+    outs = []
+    for n in (1, cluster):
+        eng = Engine(b.cfg, b.W)
+        if n > 1:
+            eng.set_cluster(n)
+        eng.setup(b)
+        S = int(b.nsteps.max())
+        N, sed = eng.run(snapshots=S)
+        outs.append((N.cpu().numpy(), sed.cpu().numpy(), S))
+        eng.close()
+    for w in range(b.W):
+        ns = int(b.nsteps[w])
+        assert_spectra_close(outs[1][1][w, :ns], outs[0][1][w, :ns], f"cluster {cluster} nuLnu walker {w}", tol=1e-12)
+        assert_spectra_close(outs[1][0][w, :ns], outs[0][0][w, :ns], f"cluster {cluster} n_e walker {w}", tol=1e-12)
 
 
 @pytest.mark.gpu

@@ -31,6 +31,7 @@ def main():
     ap.add_argument("--ic-path", default="R")
     ap.add_argument("--host-pack", action="store_true", help="NumPy set-up on the host instead of lhm_pack_batch")
     ap.add_argument("--mcmc", type=int, default=0, help="also run this many ensemble iterations of fit.run_mcmc")
+    ap.add_argument("--cluster", type=int, default=1, help="CTAs per walker (thread-block cluster): 2, 4 or 8 for small ensembles")
     ap.add_argument("--flag-c", default="LeMoC", choices=["LeMoC", "LeHaMoC"],
                     help="numerical model of the fit (fit_emcee.py:23): SSC or SSC + proton synchrotron")
     a = ap.parse_args()
@@ -44,7 +45,7 @@ def main():
     frozen = {str(k): float(v) for k, v in zip(cf["param_keys"], cf["param_vals"])}
     ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
                           D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=a.ic_path, device_pack=not a.host_pack,
-                          flag_c=a.flag_c)
+                          flag_c=a.flag_c, cluster=a.cluster)
     logp = ev.log_probability_sharded if world > 1 else ev.log_probability
     init = np.array([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2.])          # fit_emcee.py:207
     if a.flag_c == "LeHaMoC":
@@ -71,7 +72,7 @@ def main():
             b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
         pack = (time.perf_counter() - t1) / a.reps
         su, co, ru = ev.eng.last_timings()
-        print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up: "
+        print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up, {a.cluster} CTA(s) per walker: "
               f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
               f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
               f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
