@@ -214,17 +214,27 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_cluster_kernel(RunArgs A
     ic_prepare<NT>(C, S);
     const int No = Ni - 1, NiPad = ((Ni + IC_OG - 1) / IC_OG) * IC_OG;
     double t = C.tinit;
+    long long tprev = clock64();            // LHM_TICK: per-phase cycles of thread 0 of rank 0 (lhm_set_phase_profile)
+    const bool prof_on = A.prof && rank == 0;
+#define LHM_CTICK(i) do { if (prof_on && tid == 0) { long long now_ = clock64(); atomicAdd(A.prof + (i), (unsigned long long)(now_ - tprev)); tprev = now_; } } while (0)
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeMoC.py:198-201
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
         C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
         C.V = volume_of(C.Rad);
+        LHM_CTICK(0);
         if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
+        LHM_CTICK(1);
         if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        LHM_CTICK(2);
         phase_electrons<NT>(C, S);
+        LHM_CTICK(3);
         if (C.F.syn_e || C.F.ssa || C.F.ic_e) phase_vectors<NT>(C, S);
+        LHM_CTICK(4);
         phase_syn_rows_split<NT>(C, S, part);
+        LHM_CTICK(5);
         if (C.F.ic_e) phase_ic_R<NT>(C, S, part);
+        LHM_CTICK(6);
         cluster.sync();                                          // [A] every CTA's rows and IC partial sums are in place
         if (C.F.syn_e || C.F.ssa) {                              // rows from their owners (row % CS)
             for (int k = tid; k < Ns; k += NT) {
@@ -247,7 +257,9 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_cluster_kernel(RunArgs A
             }
         }
         cluster.sync();                                          // [A2] the partial sums are consumed: their scratch is free again
+        LHM_CTICK(7);
         phase_photon_solves<NT>(C, S, cor);
+        LHM_CTICK(8);
         if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
             const double* Lng = S.Ln;
             if (C.F.qee_from_ic) {
@@ -266,6 +278,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_cluster_kernel(RunArgs A
             }
             __syncthreads();
         }
+        LHM_CTICK(9);
         const bool last = (step == nsteps - 1);
         const int slot = A.snapshots > 0 ? step : 0;
         if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && last)) {

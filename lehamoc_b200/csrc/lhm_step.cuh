@@ -948,19 +948,57 @@ __device__ void phase_syn_rows_split(const Ctx& C, Smem& S, Part part) {
                 while (lo < hi) { const int mid = (lo + hi) >> 1; if (!(nu * S.inuc[mid] < SYN_XSMALL)) lo = mid + 1; else hi = mid; }
                 jx = min((lo + 1) & ~1, Ng & ~1);
             }
-            for (int j = jz + 2 * sub; j < Ng; j += 2 * tpr) {            // this lane's gamma pairs (j, j + 1)
-                const bool two = j + 1 < Ng;
-                double x[2], Ev[2];
-                x[0] = nu * S.inuc[j]; x[1] = nu * S.inuc[min(j + 1, Ng - 1)];
-                if (j >= jx && x[0] < SYN_XSMALL) { Ev[0] = exp_neg_small(x[0]); Ev[1] = exp_neg_small(x[1]); }
-                else if (Et) { Ev[0] = __ldg(Et + (size_t)j * NR); Ev[1] = two ? __ldg(Et + (size_t)(j + 1) * NR) : 0.0; }
-                else fast_exp_neg<2>(x, Ev, S.e2tab);
-                if (j >= jm) sq0 = fma(Ev[0], S.u[j], sq0);
-                sa0 = fma(Ev[0], S.v[j], sa0);
-                if (two) {
-                    if (j + 1 >= jm) sq1 = fma(Ev[1], S.u[j + 1], sq1);
-                    sa1 = fma(Ev[1], S.v[j + 1], sa1);
+            // this lane's gamma pairs (j, j + 1): j = jz + 2 sub, + 2 tpr, ...; first the part that needs the exponential
+            // (table or staged evaluation, loads batched), then the part where the four-term series does
+            const int st = 2 * tpr;
+            int j = jz + 2 * sub;
+            if (Et) {
+#pragma unroll 4
+                for (; j < jx; j += st) {
+                    const double E0 = __ldg(Et + (size_t)j * NR), E1 = __ldg(Et + (size_t)(j + 1) * NR);
+                    if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                    if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                    sa0 = fma(E0, S.v[j], sa0);
+                    sa1 = fma(E1, S.v[j + 1], sa1);
                 }
+            } else {
+                for (; j < jx; j += 2 * st) {                             // two pairs = four staged exponentials at once
+                    const bool more = j + st < jx;
+                    double x[4], Ev[4];
+                    x[0] = nu * S.inuc[j]; x[1] = nu * S.inuc[j + 1];
+                    x[2] = nu * S.inuc[more ? j + st : j]; x[3] = nu * S.inuc[more ? j + st + 1 : j + 1];
+                    fast_exp_neg<4>(x, Ev, S.e2tab);
+                    if (j >= jm) sq0 = fma(Ev[0], S.u[j], sq0);
+                    if (j + 1 >= jm) sq1 = fma(Ev[1], S.u[j + 1], sq1);
+                    sa0 = fma(Ev[0], S.v[j], sa0);
+                    sa1 = fma(Ev[1], S.v[j + 1], sa1);
+                    if (more) {
+                        const int j2 = j + st;
+                        if (j2 >= jm) sq0 = fma(Ev[2], S.u[j2], sq0);
+                        if (j2 + 1 >= jm) sq1 = fma(Ev[3], S.u[j2 + 1], sq1);
+                        sa0 = fma(Ev[2], S.v[j2], sa0);
+                        sa1 = fma(Ev[3], S.v[j2 + 1], sa1);
+                    }
+                }
+                if (j >= jx + st) j -= st;                                // the last round took one pair only
+            }
+            // j is now this lane's first pair at or beyond jx (jx - jz is even, the lane's pairs keep their residue)
+#pragma unroll 2
+            for (; j + 1 < Ng; j += st) {
+                const double E0 = exp_neg_small(nu * S.inuc[j]), E1 = exp_neg_small(nu * S.inuc[j + 1]);
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                if (j + 1 >= jm) sq1 = fma(E1, S.u[j + 1], sq1);
+                sa0 = fma(E0, S.v[j], sa0);
+                sa1 = fma(E1, S.v[j + 1], sa1);
+            }
+            if (j == Ng - 1) {                                           // odd Ng: the last gamma, whatever its x
+                const double x = nu * S.inuc[j];
+                double E0;
+                if (x < SYN_XSMALL) E0 = exp_neg_small(x);
+                else if (Et) E0 = __ldg(Et + (size_t)j * NR);
+                else { double xx[1] = {x}, ee[1]; fast_exp_neg<1>(xx, ee, S.e2tab); E0 = ee[0]; }
+                if (j >= jm) sq0 = fma(E0, S.u[j], sq0);
+                sa0 = fma(E0, S.v[j], sa0);
             }
         }
         double sq = sq0 + sq1, sa = sa0 + sa1;

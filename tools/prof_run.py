@@ -15,9 +15,12 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--walkers", type=int, default=296)
 ap.add_argument("--ic-path", default="R")
 ap.add_argument("--reps", type=int, default=2)
+ap.add_argument("--cluster", type=int, default=1, help="CTAs per walker (run_cluster_kernel, ic path R)")
 a = ap.parse_args()
 b = pack_script(test1_walkers(a.walkers))
 eng = Engine(b.cfg, a.walkers, ic_path=a.ic_path)
+if a.cluster > 1:
+    eng.set_cluster(a.cluster)
 eng.setup(b)
 for _ in range(a.reps):
     N, sed = eng.run()
@@ -33,6 +36,8 @@ torch.cuda.synchronize()
 eng.lib.lhm_set_phase_profile(eng.h, None)
 p = prof.cpu().numpy().astype(float)
 names = ["loop/out", "photons", "uph", "electrons", "vectors", "syn_rows(w0)", "ic(w0)", "wait_ic", "ic_fin+ph_solves", "gg"]
+if a.cluster > 1:
+    names = ["loop/out", "photons", "uph", "electrons", "vectors", "syn_rows", "ic tiles", "exchange (2 cluster barriers)", "photon solves", "gg + exchange"]
 if a.ic_path == "G":
     names = ["load+Q_IC / time", "photons", "uph", "electrons", "vectors", "syn_rows", "store", "-", "photon solves", "gg"]
     print("contraction (mean ms, launches, CTAs, smem):", eng.last_icg_timing())
