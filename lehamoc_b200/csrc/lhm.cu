@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeMoC.py:198-201
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
-        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);      // pow(x, 0) == 1 exactly: B0 * 1.0
         C.V = volume_of(C.Rad);
 
         LHM_TICK(0);
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_cluster_kernel(RunArgs A
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeMoC.py:198-201
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
-        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);      // pow(x, 0) == 1 exactly: B0 * 1.0
         C.V = volume_of(C.Rad);
         LHM_CTICK(0);
         if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
@@ -336,7 +336,7 @@ struct GArgs {
 
 __device__ __forceinline__ void set_time(Ctx& C, double t) {                 // LeMoC.py:198-201
     C.Rad = C.R0 + C.Vexp * (t - C.tinit);
-    C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+    C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);      // pow(x, 0) == 1 exactly: B0 * 1.0
     C.V = volume_of(C.Rad);
 }
 
@@ -714,7 +714,7 @@ __global__ void __launch_bounds__(NTL, MINB) run_lh_kernel(RunArgs A) {
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;                                               // LeHaMoC.py:268-272
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
-        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);      // pow(x, 0) == 1 exactly: B0 * 1.0
         C.V = volume_of(C.Rad);
         LHM_TICK(0);
         phase_photons<NTL>(C, S, true);
@@ -813,7 +813,7 @@ __global__ void __launch_bounds__(NT, 2) run_code_lh_kernel(RunArgs A) {
     for (int step = 0; step < nsteps; ++step) {
         t += C.dt;
         C.Rad = C.R0 + C.Vexp * (t - C.tinit);
-        C.B = C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);      // pow(x, 0) == 1 exactly: B0 * 1.0
         C.V = volume_of(C.Rad);
         phase_photons<NT>(C, S, true);
         if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);

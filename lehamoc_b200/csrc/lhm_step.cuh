@@ -694,8 +694,12 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor, const dou
     const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
     const double esc = cc / C.Rad;
     const int ns = L.Ns - 2, ni = L.Ni - 2;
-    // synchrotron photons -> cp/dp[0..ns)
-    for (int j = tid; j < ns; j += NT) {
+    // The two photon equations are independent: both coefficient sets are formed in one pass (the IC set in bcom / Lic,
+    // which are dead between the electron solve and the next photon field) and, when the adiabatic term makes the
+    // systems bidiagonal, warps 0 and 1 back-substitute side by side.  Same arithmetic per element as one after the other.
+    double* cp2 = S.bcom;
+    double* dp2 = S.Lic;
+    for (int j = tid; j < ns; j += NT) {                                 // synchrotron photons -> cp/dp[0..ns)
         double aS = C.F.ssa ? -fabs(S.aS[j + 1]) : 0.0;                  // -np.absolute(aSSA)  LeMoC.py:261
         double V2 = 1.0 + dt * (esc + b_ad * C.T[L.asm_ + j] - aS * cc);
         double V3 = -dt * (b_ad * C.T[L.asp_ + j]);
@@ -705,22 +709,23 @@ __device__ void phase_photon_solves(const Ctx& C, Smem& S, double cor, const dou
         S.cp[j] = V3 / V2;
         S.dp[j] = d / V2;
     }
-    __syncthreads();
-    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.psyn + 1, ns); }
-    else { for (int j = tid; j < ns; j += NT) S.psyn[j + 1] = S.dp[j]; }   // V3 == 0: diagonal system
-    __syncthreads();
-    for (int j = tid; j < ni; j += NT) {
+    for (int j = tid; j < ni; j += NT) {                                 // IC photons -> cp2/dp2[0..ni)
         double aI = C.F.ssa ? -fabs(S.aI[j + 1]) : 0.0;
         double V2 = 1.0 + dt * (esc + b_ad * C.Ts[L.aim + j] + S.agg[j + 1] * cc - aI * cc);
         double V3 = -dt * (b_ad * C.Ts[L.aip + j]);
         double Q = C.F.ic_e ? S.QIC[j + 1] : 0.0;
         double d = S.pic[j + 1] + (Q * dt) * C.V;
-        S.cp[j] = V3 / V2;
-        S.dp[j] = d / V2;
+        cp2[j] = V3 / V2;
+        dp2[j] = d / V2;
     }
     __syncthreads();
-    if (C.F.ad) { if (tid < 32) backsub_warp(S.cp, S.dp, S.pic + 1, ni); }
-    else { for (int j = tid; j < ni; j += NT) S.pic[j + 1] = S.dp[j]; }
+    if (C.F.ad) {
+        if (tid < 32) backsub_warp(S.cp, S.dp, S.psyn + 1, ns);
+        else if (tid < 64) backsub_warp(cp2, dp2, S.pic + 1, ni);
+    } else {                                                             // V3 == 0: diagonal systems
+        for (int j = tid; j < ns; j += NT) S.psyn[j + 1] = S.dp[j];
+        for (int j = tid; j < ni; j += NT) S.pic[j + 1] = dp2[j];
+    }
     __syncthreads();
 }
 
