@@ -298,6 +298,16 @@ typedef struct lhm_pack_args {
 } lhm_pack_args;
 int lhm_pack_batch(const lhm_pack_args* args, void* cuda_stream);
 
+/* Host-side helper for the two integer entries of a walker_params row: index_PL_min and index_PL_max of
+ * LeMoC.py:120-128 / Code.py:82-90 (`g_el[g_el > 10**g_PL_max][0]`, `g_el[g_el < 10**g_PL_min][-1]` on the np.logspace
+ * grid of n points between 10**g_lo and 10**g_hi), for W walkers, without building the grids.  No device work.
+ * idx_min / idx_max [W] receive the integers as doubles (the layout of walker_params; -1 = g_PL_max == g_max_el);
+ * status [W]: 0 decided; 1 a grid value lies within a few ulp of a threshold, where NumPy's array pow (the reference's
+ * grid) and libm's may disagree -- the caller decides that walker with the reference's own NumPy expressions
+ * (lehamoc_b200/setup_host.py does); 2 the window lies outside the grid (the reference raises IndexError there). */
+int lhm_window_indices_host(int W, int n, const double* g_lo, const double* g_hi, const double* pl_min, const double* pl_max,
+                            double* idx_min, double* idx_max, int* status);
+
 /* ---- one call per fit evaluation (replaces `pool.map(log_probability, thetas)` of Fit_emcee/fit_emcee.py:190-199,239-242
  * for flag_c = 'LeMoC', without the prior, which stays on the host): host in, host out.
  * obs: the observation table of fit_emcee.py:61-93 as DEVICE pointers [nd] (flags as the reference's floats) and the two

@@ -89,6 +89,7 @@ SIGNATURES = {
     "lhm_photopion_batch": (C.c_int, [C.c_int] * 7 + [_P] * 9 + [_P]),
     "lhm_bh_emis_batch": (C.c_int, [C.c_int] * 4 + [_P] * 5 + [_P, _P, _P, _P]),
     "lhm_pack_batch": (C.c_int, [_P, _P]),
+    "lhm_window_indices_host": (C.c_int, [C.c_int, C.c_int] + [_P] * 7),
     "lhm_pp_batch": (C.c_int, [C.c_int] * 4 + [_P] * 6 + [_P]),
     "lhm_fp64_peak_probe": (C.c_int, [C.c_int, _P, C.POINTER(C.c_double)]),
 }

@@ -1967,6 +1967,63 @@ int lhm_photopion_batch(int W, int species, int Ng, int Ni, int Np, int Nt, int 
     return LHM_OK;
 }
 
+// ---- host part of the device-side set-up: index_PL_min / index_PL_max of LeMoC.py:120-128 / Code.py:82-90 ----------------
+// First grid index whose value satisfies the (monotone) predicate `g > thr` (greater) or `not g < thr`, n if none, -1 if
+// this routine cannot vouch for the answer.  The reference compares np.logspace values (NumPy's array pow) with a Python
+// float 10**x (libm pow); here every grid value comes from libm, which may differ from NumPy's by an ulp, so a candidate
+// within a few ulp of the threshold -- or candidates that do not bracket the switch -- hand the walker back to the caller's
+// NumPy evaluation (lehamoc_b200/setup_host.py::_window_indices); everywhere else the comparison has one possible outcome.
+static int window_first_index(double lo, double hi, int n, double target, double thr, bool greater) {
+    const double step = (hi - lo) / (n - 1);
+    const double guess = std::floor((target - lo) / step);
+    if (!std::isfinite(guess) || !std::isfinite(thr) || !(thr > 0.0)) return -1;
+    const double gc = std::fmin(std::fmax(guess, -4.0), (double)n + 4.0);
+    const long g0 = (long)gc;
+    auto value = [&](long idx) { return std::pow(10.0, (idx == n - 1) ? hi : (double)idx * step + lo); };
+    if (g0 >= 0 && g0 + 1 <= n - 1) {
+        // the usual case: the switch sits between the arithmetic position of the threshold and the next point
+        const double ga = value(g0), gb = value(g0 + 1);
+        if (std::fabs(ga - thr) <= 1.0e-14 * thr || std::fabs(gb - thr) <= 1.0e-14 * thr) return -1;
+        const bool oka = greater ? (ga > thr) : !(ga < thr), okb = greater ? (gb > thr) : !(gb < thr);
+        if (!oka && okb) return (int)(g0 + 1);
+    }
+    int first = n;
+    bool ok_first = false, ok_last = false;
+    long c_first = 0, c_last = 0;
+    for (int d = -2; d < 4; ++d) {
+        long idx = g0 + d;
+        idx = idx < 0 ? 0 : (idx > n - 1 ? n - 1 : idx);
+        const double g = value(idx);
+        if (std::fabs(g - thr) <= 1.0e-14 * thr) return -1;
+        const bool ok = greater ? (g > thr) : !(g < thr);
+        if (ok && first == n) first = (int)idx;
+        if (d == -2) { ok_first = ok; c_first = idx; }
+        ok_last = ok; c_last = idx;
+    }
+    const bool bracket = (!ok_first || c_first == 0) && (ok_last || c_last == n - 1);
+    return bracket ? first : -1;
+}
+
+int lhm_window_indices_host(int W, int n, const double* g_lo, const double* g_hi, const double* pl_min, const double* pl_max,
+                            double* idx_min, double* idx_max, int* status) {
+    if (W < 1 || n < 4 || !g_lo || !g_hi || !pl_min || !pl_max || !idx_min || !idx_max || !status) return LHM_ERR_ARG;
+    for (int w = 0; w < W; ++w) {
+        const double lo = g_lo[w], hi = g_hi[w], a = pl_min[w], b = pl_max[w];
+        status[w] = 0; idx_min[w] = 1.0; idx_max[w] = -1.0;
+        // the window must lie inside the grid (LeMoC.py:120-128 index into empty arrays otherwise)
+        if ((b != hi && !(b < hi)) || (a != 0.0 && !(a > lo))) { status[w] = 2; continue; }
+        const bool same = (b == hi);
+        int first_gt = n, first_ge = n;
+        if (!same) first_gt = window_first_index(lo, hi, n, b, std::pow(10.0, b), true);
+        if (a != 0.0) first_ge = window_first_index(lo, hi, n, a, std::pow(10.0, a), false);
+        if (first_gt < 0 || first_ge < 0) { status[w] = 1; continue; }
+        if ((!same && first_gt >= n) || (a != 0.0 && first_ge < 1)) { status[w] = 2; continue; }
+        idx_min[w] = (a == 0.0) ? 1.0 : (double)(first_ge - 1);
+        idx_max[w] = same ? -1.0 : (double)first_gt;
+    }
+    return LHM_OK;
+}
+
 int lhm_pack_batch(const lhm_pack_args* a, void* stream) {
     if (!a || a->W < 1 || a->Ng < 4 || a->Nh < 3 || a->Nt < 4 || a->variant < 0 || a->variant > 1) return LHM_ERR_ARG;
     if (!a->walker_params || !a->nu_ic_row || !a->nu_tot_row || !a->ext_row || !a->consts || !a->g_el || !a->nu_syn

@@ -164,6 +164,9 @@ def test_window_indices_are_the_references():
             else:
                 pl_min[w] = np.log10(g[j])
         imin, imax = sh._window_indices(lo, hi, n, pl_min, pl_max)
+        # liblhm's host routine (the same candidates with libm's pow; near-ties handed back to the NumPy evaluation)
+        lmin, lmax = sh._window_indices_lib(lo, hi, n, pl_min, pl_max)
+        assert np.array_equal(lmin, imin) and np.array_equal(lmax, imax), n
         for w in range(W):
             g = np.logspace(lo[w], hi[w], n)
             rmax = -1 if pl_max[w] == hi[w] else int(np.min(np.where(g > 10 ** pl_max[w])[0]))
@@ -171,3 +174,5 @@ def test_window_indices_are_the_references():
             assert (rmin, rmax) == (imin[w], imax[w]), (n, w)
     with pytest.raises(ValueError):                 # window above the grid: the reference raises (min of empty)
         sh._window_indices(np.array([0.]), np.array([4.]), 50, np.array([1.]), np.array([5.]))
+    with pytest.raises(ValueError):
+        sh._window_indices_lib(np.array([0.]), np.array([4.]), 50, np.array([1.]), np.array([5.]))

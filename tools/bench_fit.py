@@ -21,7 +21,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch  # noqa: E402
 
-from lehamoc_b200 import fit  # noqa: E402
+from lehamoc_b200 import fit, setup_host  # noqa: E402
 
 
 def main():
@@ -69,13 +69,20 @@ def main():
         # where the time goes: host packing alone, and the GPU kernels alone
         t1 = time.perf_counter()
         for th in calls[2:]:
-            b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
+            if a.host_pack:
+                b = fit.pack_code(th[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(th[:, :10], frozen)
+            elif a.flag_c == "LeMoC":                # what the call itself does on the host: one row of scalars per walker
+                b = setup_host.pack_code_request(th[:, :6], frozen)
+            else:
+                b = setup_host.pack_code_lehamoc_request(th[:, :10], frozen)
         pack = (time.perf_counter() - t1) / a.reps
+        one = calls[2][:1]
+        steps = int((fit.pack_code(one[:, :6], frozen) if a.flag_c == "LeMoC" else fit.pack_code_lehamoc(one[:, :10], frozen)).nsteps[0])
         su, co, ru = ev.eng.last_timings()
         print(f"{world} GPU(s), {'host' if a.host_pack else 'device'}-side set-up, {a.cluster} CTA(s) per walker: "
               f"half-ensemble of {half} walkers: {dt * 1e3:.2f} ms per call = {half / dt:.0f} log-prob evaluations/s "
               f"(host packing {pack * 1e3:.2f} ms; kernels set-up {su:.2f} + cor {co:.2f} + run {ru:.2f} ms; "
-              f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={int(b.nsteps[0])})")
+              f"finite {np.isfinite(lp).mean():.2f}; Ng={ev.eng.Ng} Nt={ev.eng.Nt} steps={steps})")
     if a.mcmc:
         # the whole sampler loop (stretch move on the host, two half-ensemble evaluations per iteration on the GPU)
         pos = init + 1e-2 * rng.standard_normal((a.walkers, len(init)))

@@ -163,40 +163,53 @@ def config4(walkers=1024, reps=10, ic_path="R"):
     g = np.load(os.path.join(GOLD, "fit_loglike.npz"))
     cf, frozen = _golden("code_fit")
     world = dist.get_world_size() if dist.is_initialized() else 1
-    ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
-                          D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=ic_path)
-    logp = ev.log_probability_sharded if world > 1 else ev.log_probability
     init = np.array([15.25808, 0.038818, 3., 6.081445, -4., 2., 1.3, -2.])          # fit_emcee.py:207,224
     rng = np.random.default_rng(1)
     half = walkers // 2
     calls = [init + 1e-2 * rng.standard_normal((half, len(init))) for _ in range(reps + 2)]
-    for th in calls[:2]:
-        lp = logp(th)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    for th in calls[2:]:
-        lp = logp(th)
-    torch.cuda.synchronize()
-    dt = (time.perf_counter() - t0) / reps
-    if world > 1:
-        tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
-        dt = float(tmax.item())
-    su, co, ru = ev.eng.last_timings()
-    # parity: the reference's own log_probability on its own Code.LeMoC spectra (oracle/make_golden_fit.py)
-    lp_gold = logp(g["theta8"])
-    rel = float(np.max(np.abs(lp_gold - g["logprob"]) / np.abs(g["logprob"])))
-    res = {"what": f"config 4: Fit_emcee SSC fit, one half-ensemble call ({half} of {walkers} walkers; Code.LeMoC Ng={ev.eng.Ng} "
-                   f"Nt={ev.eng.Nt}, 4 timesteps + observation transform + log-likelihood + prior), host thetas in, host "
+
+    def timed(path):
+        ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
+                              D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=path)
+        logp = ev.log_probability_sharded if world > 1 else ev.log_probability
+        for th in calls[:2]:
+            lp = logp(th)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        for th in calls[2:]:
+            lp = logp(th)
+        torch.cuda.synchronize()
+        dt = (time.perf_counter() - t0) / reps
+        if world > 1:
+            tmax = torch.tensor([dt], dtype=torch.float64, device="cuda")
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dt = float(tmax.item())
+        timings = ev.eng.last_timings()
+        # parity: the reference's own log_probability on its own Code.LeMoC spectra (oracle/make_golden_fit.py)
+        lp_gold = logp(g["theta8"])
+        rel = float(np.max(np.abs(lp_gold - g["logprob"]) / np.abs(g["logprob"])))
+        dims = (ev.eng.Ng, ev.eng.Nt)
+        ev.eng.close()
+        return dt, timings, rel, lp, dims
+
+    dt, (su, co, ru), rel, lp, (Ng, Nt) = timed(ic_path)
+    # the exact suffix-sum form of the IC sum (path S) beside it: same spectra to 1e-14, 100x fewer flops
+    other = None
+    if ic_path == "R":
+        dtS, (suS, coS, ruS), relS, _, _ = timed("S")
+        other = {"ic_path": "S", "ms_per_call": dtS * 1e3, "value": half / dtS,
+                 "kernel_ms_last_call": {"setup": suS, "cor": coS, "run": ruS}, "max_rel_logprob": relS}
+    res = {"what": f"config 4: Fit_emcee SSC fit, one half-ensemble call ({half} of {walkers} walkers; Code.LeMoC Ng={Ng} "
+                   f"Nt={Nt}, 4 timesteps + observation transform + log-likelihood + prior), host thetas in, host "
                    f"log-probabilities out, walkers sharded over {world} rank(s) + one all-gather",
            "walkers": walkers, "ranks": world, "ms_per_call": dt * 1e3, "value": half / dt,
            "unit": "log-prob evaluations/s", "scaling": "strong",
            "kernel_ms_last_call": {"setup": su, "cor": co, "run": ru}, "finite_fraction": float(np.isfinite(lp).mean()),
            "parity": {"vs": "tests/golden/fit_loglike.npz (the reference's log_probability on its Code.LeMoC spectra), 8 walkers",
-                      "max_rel_logprob": rel}}
-    ev.eng.close()
+                      "max_rel_logprob": rel},
+           "ic_path": ic_path, "other_ic_path": other}
     return res
 
 
