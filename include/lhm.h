@@ -326,6 +326,12 @@ typedef struct lhm_fit_obs {
 } lhm_fit_obs;
 int lhm_fit_logl_host(lhm_handle*, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
                       double* logl_host);
+/* Same evaluation, result left on the device: logl_dev [W] (device memory) is written on the handle's stream and the call
+ * returns without waiting -- for a caller that goes on with device work on that stream, e.g. the all-gather of the
+ * per-rank blocks of a sharded ensemble (lehamoc_b200/fit.py::log_probability_sharded, fit_emcee.py:239-242).  stage_host may
+ * be reused as soon as the call returns (it is copied into the handle's pinned buffer first). */
+int lhm_fit_logl_device(lhm_handle*, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                        double* logl_dev);
 
 /* A14 pp channels (LeHaMoC_f.py:860-1014): product 0 Q_e_pp (grid = g_el), 1 Q_g_pp (grid = nu_ic), 2 Q_nu_mu_pp,
  * 3 Q_nu_e_pp (grid = nu_nu = E_nu/h).  grid [W,Nout]; g_pr, N_pr_TeV [W,Np] (dN_pr/dV dgamma divided by

@@ -74,6 +74,7 @@ SIGNATURES = {
     "lhm_set_lockstep": (C.c_int, [_P, C.c_int]),
     "lhm_set_cluster": (C.c_int, [_P, C.c_int]),
     "lhm_fit_logl_host": (C.c_int, [_P, C.POINTER(lhm_pack_args), _P, C.POINTER(lhm_fit_obs), _P]),
+    "lhm_fit_logl_device": (C.c_int, [_P, C.POINTER(lhm_pack_args), _P, C.POINTER(lhm_fit_obs), _P]),
     "lhm_last_hadtab_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_longlong)]),
     "lhm_last_icg_timing": (C.c_int, [_P, C.POINTER(C.c_float), C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "lhm_run_batch_host": (C.c_int, [_P, C.c_int] + [_P] * 9 + [C.c_int]),

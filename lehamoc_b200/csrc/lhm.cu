@@ -1103,6 +1103,7 @@ struct lhm_handle {
     double* d_corscr;         // cor_kernel -> cor_loop_kernel hand-over
     double* d_ggK; double* d_ggT; int* d_ggJ; int gg_rows;      // path G: gamma-gamma sample table of the batch
     double* fit_pin; double* fit_din; double* fit_arr; double* fit_sed; double* fit_logl; size_t fit_cap;
+    cudaEvent_t fit_up;       // the staging copy of the last lhm_fit_logl_* call has left the pinned buffer
     size_t Nout_cap, sed_cap;
     unsigned long long* d_prof;   // optional per-phase cycle counters (lhm_set_phase_profile)
     // device-side timing of the last setup / cor / run launches (lhm_last_timings)
@@ -1293,6 +1294,7 @@ void lhm_destroy(lhm_handle* h) {
     cudaFree(h->d_tabd); cudaFree(h->d_tabi); cudaFree(h->d_cor); cudaFree(h->d_E); cudaFree(h->d_ptab);
     cudaFree(h->d_in); cudaFree(h->d_Nout); cudaFree(h->d_sed);
     if (h->fit_pin) cudaFreeHost(h->fit_pin);
+    if (h->fit_up) cudaEventDestroy(h->fit_up);
     cudaFree(h->fit_din); cudaFree(h->fit_arr); cudaFree(h->fit_sed); cudaFree(h->fit_logl);
     cudaFree(h->d_ptg); cudaFree(h->d_kinfo); cudaFree(h->d_xs); cudaFree(h->d_tasks); cudaFree(h->d_cost);
     cudaFree(h->d_gp); cudaFree(h->d_gav); cudaFree(h->d_part); cudaFree(h->d_state);
@@ -2044,9 +2046,10 @@ int lhm_pack_batch(const lhm_pack_args* a, void* stream) {
     return LHM_OK;
 }
 
-int lhm_fit_logl_host(lhm_handle* h, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
-                      double* logl_host) {
-    if (!h || !pack || !stage_host || !obs || !logl_host) return LHM_ERR_ARG;
+// logl_dev != null: the likelihoods are left there (device memory), nothing is copied back and the call does not wait
+static int fit_logl_impl(lhm_handle* h, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                         double* logl_host, double* logl_dev) {
+    if (!h || !pack || !stage_host || !obs || (!logl_host && !logl_dev)) return LHM_ERR_ARG;
     const lhm_config& c = h->cfg;
     const int W = pack->W, Ng = c.Ng, Nh = c.Ni, Nt = c.Nt;
     if (c.driver != 0 || h->pathG) return LHM_ERR_STATE;
@@ -2062,12 +2065,16 @@ int lhm_fit_logl_host(lhm_handle* h, const lhm_pack_args* pack, const double* st
         CUDA_TRY(cudaMalloc(&h->fit_arr, Wm * per_w * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->fit_sed, Wm * Nt * sizeof(double)));
         CUDA_TRY(cudaMalloc(&h->fit_logl, Wm * sizeof(double)));
+        CUDA_TRY(cudaEventCreateWithFlags(&h->fit_up, cudaEventDisableTiming));
+    } else {
+        CUDA_TRY(cudaEventSynchronize(h->fit_up));        // an asynchronous predecessor may still be reading the staging buffer
     }
     cudaStream_t s = h->stream;
     const size_t o_par = 0, o_ic = (size_t)W * LHM_PACK_NPAR, o_tot = o_ic + Nh, o_ext = o_tot + Nt, o_dop = o_ext + Nt,
                  o_lf = o_dop + W, n_in = o_lf + W;
     std::memcpy(h->fit_pin, stage_host, n_in * sizeof(double));
     CUDA_TRY(cudaMemcpyAsync(h->fit_din, h->fit_pin, n_in * sizeof(double), cudaMemcpyHostToDevice, s));
+    CUDA_TRY(cudaEventRecord(h->fit_up, s));
     lhm_pack_args a = *pack;
     double* p = h->fit_arr;
     auto take = [&](size_t n) { double* r = p; p += Wm * n; return r; };
@@ -2083,14 +2090,25 @@ int lhm_fit_logl_host(lhm_handle* h, const lhm_pack_args* pack, const double* st
     rc = lhm_run_batch(h, nullptr, h->fit_sed, 0);
     if (rc != LHM_OK) return rc;
     rc = lhm_loglike_batch(W, Nt, a.nu_tot, h->fit_sed, h->fit_din + o_dop, h->fit_din + o_lf, obs->log10_1pz,
-                           obs->distance_norm, obs->nd, obs->x, obs->y, obs->yerr_hi, obs->yerr_lo, obs->flags, h->fit_logl,
-                           nullptr, s);
+                           obs->distance_norm, obs->nd, obs->x, obs->y, obs->yerr_hi, obs->yerr_lo, obs->flags,
+                           logl_dev ? logl_dev : h->fit_logl, nullptr, s);
     if (rc != LHM_OK) return rc;
+    if (logl_dev) return LHM_OK;
     double* pin_out = h->fit_pin + n_in_max;
     CUDA_TRY(cudaMemcpyAsync(pin_out, h->fit_logl, (size_t)W * sizeof(double), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
     std::memcpy(logl_host, pin_out, (size_t)W * sizeof(double));
     return LHM_OK;
+}
+
+int lhm_fit_logl_host(lhm_handle* h, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                      double* logl_host) {
+    return logl_host ? fit_logl_impl(h, pack, stage_host, obs, logl_host, nullptr) : LHM_ERR_ARG;
+}
+
+int lhm_fit_logl_device(lhm_handle* h, const lhm_pack_args* pack, const double* stage_host, const lhm_fit_obs* obs,
+                        double* logl_dev) {
+    return logl_dev ? fit_logl_impl(h, pack, stage_host, obs, nullptr, logl_dev) : LHM_ERR_ARG;
 }
 
 int lhm_pp_batch(int W, int product, int Nout, int Np, const double* grid, const double* g_pr, const double* N_pr_TeV,

@@ -204,11 +204,13 @@ class Engine:
         check(self.lib.lhm_pack_batch(C.byref(a), C.c_void_p(self.stream.cuda_stream)), "lhm_pack_batch")
         self.setup_device(W, *[t[:W] for t in outs])
 
-    def fit_logl_host(self, req, doppler, log_f, obs):
+    def fit_logl_host(self, req, doppler, log_f, obs, out_dev=None):
         """One fit evaluation in ONE library call (lhm_fit_logl_host): PackRequest of the Code.py variant + per-walker
         log10 Doppler factor and log_f + the observation table (a _lib.lhm_fit_obs of device pointers) -> log-likelihoods
         [W] as a NumPy array.  Packing, set-up, cor-factor, time loop, observation transform, likelihood and both copies
-        run inside the call."""
+        run inside the call.
+        out_dev (a float64 CUDA tensor with >= W elements): lhm_fit_logl_device instead -- the likelihoods are written there
+        on the engine's stream, nothing is copied back and the call does not wait (returns None)."""
         from .constants import c, m_el, sigmaT, q
         cfg = req.cfg
         for k in ("Ng", "Ns", "Ni", "Nt"):
@@ -229,10 +231,16 @@ class Engine:
         stage[o + Nh + 2 * Nt + W:] = log_f
         a = _lib.lhm_pack_args(W=W, Ng=cfg["Ng"], Nh=Nh, Nt=Nt, variant=1, c=c, c3=c ** 3., m_el=m_el, mc2=m_el * c ** 2.,
                                sigmaT=sigmaT, four_pi=4. * np.pi, nuc_pref=3. / (4. * np.pi) * q, **req.scalars)
+        self.W = W
+        if out_dev is not None:
+            if out_dev.dtype != torch.float64 or not out_dev.is_cuda or out_dev.numel() < W or not out_dev.is_contiguous():
+                raise LhmError("out_dev must be a contiguous float64 CUDA tensor with at least W elements")
+            check(self.lib.lhm_fit_logl_device(self.h, C.byref(a), stage.ctypes.data_as(C.c_void_p), C.byref(obs),
+                                               C.c_void_p(out_dev.data_ptr())), "lhm_fit_logl_device")
+            return None
         out = np.empty(W)
         check(self.lib.lhm_fit_logl_host(self.h, C.byref(a), stage.ctypes.data_as(C.c_void_p), C.byref(obs),
                                          out.ctypes.data_as(C.c_void_p)), "lhm_fit_logl_host")
-        self.W = W
         return out
 
     # -- the whole time integration ---------------------------------------------------------------

@@ -195,11 +195,66 @@ class FitEvaluator:
 
     def log_probability_sharded(self, thetas):
         """Same, with the walkers cut into per-rank blocks and the result all-gathered (shard.py)."""
+        if (shard.world()[1] > 1 and self.flag_c == "LeMoC" and self.device_pack and self.ic_path != "G"
+                and torch.distributed.get_backend() == "nccl"):
+            return self._log_probability_nccl(thetas)
+
         def local(block):
             if len(block) == 0:
                 return np.empty(0)
             return self.log_probability(block)
         return shard.evaluate_sharded(local, thetas)
+
+    def _log_probability_nccl(self, thetas):
+        """The sharded evaluation without a host round trip per rank: this rank's block goes through
+        lhm_fit_logl_device (likelihoods stay on the GPU, no synchronisation), ONE all-gather on the same stream carries
+        the blocks and a per-rank status word, one copy brings the ensemble's likelihoods to the host.  The prior is a
+        function of theta alone, so every rank evaluates it for the whole ensemble on the host.  A rank whose block fails
+        (a packer ValueError, say) still takes part in the gather and all ranks raise together."""
+        import torch.distributed as dist
+        thetas = np.atleast_2d(np.asarray(thetas, dtype=np.float64))
+        W, nf = thetas.shape[0], self.nfree
+        rank, ws = shard.world()
+        lp = log_prior_batch(thetas, self.flag_c)
+        a, b = shard.block_range(W, ws, rank)
+        m = -(-W // ws)                                     # the largest block; slot m of a rank's row is its status word
+        bufs = getattr(self, "_nccl_bufs", None)
+        if bufs is None or bufs[0].numel() != m + 1 or bufs[1].numel() != ws * (m + 1):
+            dev = torch.device("cuda", self.device)
+            bufs = (torch.zeros(m + 1, dtype=torch.float64, device=dev), torch.empty(ws * (m + 1), dtype=torch.float64, device=dev),
+                    torch.empty(m + 1, dtype=torch.float64, device=dev), torch.empty(ws * (m + 1), dtype=torch.float64).pin_memory())
+            self._nccl_bufs = bufs
+        loc, full, tmp, pin = bufs
+        err = None
+        try:
+            inside = np.isfinite(lp[a:b])
+            n_in = int(inside.sum())
+            if n_in:
+                th = thetas[a:b] if n_in == b - a else thetas[a:b][inside]
+                req = pack_code_request(th[:, :nf], self.frozen)
+                self._engine(req).fit_logl_host(req, th[:, nf], th[:, nf + 1], self._obs,
+                                                out_dev=loc if n_in == b - a else tmp)
+                if n_in != b - a:                           # walkers outside the prior box are not evolved: scatter the rest
+                    idx = torch.from_numpy(np.flatnonzero(inside)).to(loc.device)
+                    loc[:b - a].index_copy_(0, idx, tmp[:n_in])
+        except Exception as e:                              # noqa: BLE001 -- raised below, on every rank
+            err = e
+            loc[m:].fill_(1.0)
+        dist.all_gather_into_tensor(full, loc)
+        pin.copy_(full, non_blocking=True)
+        torch.cuda.current_stream(self.device).synchronize()
+        host = pin.numpy().reshape(ws, m + 1)
+        if err is not None:
+            loc[m:].zero_()
+            raise err
+        if host[:, m].any():
+            raise RuntimeError("log_probability_sharded: another rank failed to evaluate its block of walkers")
+        sizes = shard.block_sizes(W, ws)
+        logl = host[0, :W].copy() if ws == 1 else np.concatenate([host[r, :sizes[r]] for r in range(ws)])
+        out = np.full(W, -np.inf)
+        ins = np.isfinite(lp)
+        out[ins] = lp[ins] + logl[ins]
+        return out
 
 
 _evaluators = {}

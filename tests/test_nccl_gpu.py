@@ -69,6 +69,23 @@ def _worker(rank, ws, port, W, out_dir):
         rows = shard.evaluate_sharded(lambda blk: _rows(ev, blk), th[inside])
         np.save(os.path.join(out_dir, f"lp_{W}_{rank}.npy"), lp)
         np.save(os.path.join(out_dir, f"rows_{W}_{rank}.npy"), rows)
+        # a rank whose block cannot be packed: every rank raises (nobody is left waiting in the gather), and the
+        # evaluator is usable afterwards
+        real = fit.pack_code_request
+        if rank == 1:
+            def broken(*a, **k):
+                raise ValueError("this rank's block cannot be packed")
+            fit.pack_code_request = broken
+        try:
+            ev.log_probability_sharded(th)
+            raised = "nothing"
+        except Exception as e:                                                  # noqa: BLE001
+            raised = type(e).__name__
+        fit.pack_code_request = real
+        lp2 = ev.log_probability_sharded(th)
+        with open(os.path.join(out_dir, f"raised_{W}_{rank}.txt"), "w") as f:
+            f.write(raised)
+        np.save(os.path.join(out_dir, f"lp2_{W}_{rank}.npy"), lp2)
     finally:
         dist.destroy_process_group()
 
@@ -95,3 +112,5 @@ def test_nccl_gathered_rows_equal_single_gpu(tmp_path, W):
     for r in range(ws):
         np.testing.assert_array_equal(np.load(tmp_path / f"lp_{W}_{r}.npy"), lp)
         np.testing.assert_array_equal(np.load(tmp_path / f"rows_{W}_{r}.npy"), rows)
+        np.testing.assert_array_equal(np.load(tmp_path / f"lp2_{W}_{r}.npy"), lp)
+        assert (tmp_path / f"raised_{W}_{r}.txt").read_text() == ("ValueError" if r == 1 else "RuntimeError")

@@ -168,9 +168,13 @@ def config4(walkers=1024, reps=10, ic_path="R"):
     half = walkers // 2
     calls = [init + 1e-2 * rng.standard_normal((half, len(init))) for _ in range(reps + 2)]
 
+    # CTAs per walker: a thread-block cluster per walker when a rank's block is smaller than the GPU (148 SMs)
+    per_rank = -(-half // world)
+    cluster = 4 if per_rank <= 37 else 2 if per_rank <= 74 else 1
+
     def timed(path):
         ev = fit.FitEvaluator(g["xd"], g["yd"], g["yerr_hi"], g["yerr_lo"], g["flags"], param_file=frozen,
-                              D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=path)
+                              D=float(g["D_Mpc"]), z=float(g["z"]), ic_path=path, cluster=cluster if path == "R" else 1)
         logp = ev.log_probability_sharded if world > 1 else ev.log_probability
         for th in calls[:2]:
             lp = logp(th)
@@ -209,7 +213,7 @@ def config4(walkers=1024, reps=10, ic_path="R"):
            "kernel_ms_last_call": {"setup": su, "cor": co, "run": ru}, "finite_fraction": float(np.isfinite(lp).mean()),
            "parity": {"vs": "tests/golden/fit_loglike.npz (the reference's log_probability on its Code.LeMoC spectra), 8 walkers",
                       "max_rel_logprob": rel},
-           "ic_path": ic_path, "other_ic_path": other}
+           "ic_path": ic_path, "ctas_per_walker": cluster if ic_path == "R" else 1, "other_ic_path": other}
     return res
 
 
