@@ -87,7 +87,13 @@ __device__ void no_step_outputs(const RunArgs& A, int w, int Ng, int Nt, int Np)
 #ifndef LHM_MIN_CTAS
 #define LHM_MIN_CTAS 2
 #endif
-__global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
+// ICP: the handle's IC path as a compile-time constant -- the path-S instantiation carries neither path R's 126-register
+// pair loop nor its tile schedule, and reads its pair table (phase_ic_S_tab).
+#ifndef LHM_MIN_CTAS_S
+#define LHM_MIN_CTAS_S 2
+#endif
+template <int ICP>
+__global__ void __launch_bounds__(NT, ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LHM_MIN_CTAS) run_kernel(RunArgs A) {
     extern __shared__ __align__(16) double smem_raw[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x;
@@ -134,12 +140,12 @@ __global__ void __launch_bounds__(NT, LHM_MIN_CTAS) run_kernel(RunArgs A) {
         phase_syn_rows<NT>(C, S, false);
         LHM_TICK(5);
         if (C.F.ic_e) {
-            if (C.F.ic_path == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT>(C, S);
+            if (ICP == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT, true>(C, S);
         }
         LHM_TICK(6);
         __syncthreads();
         LHM_TICK(7);
-        if (C.F.ic_e && C.F.ic_path == LHM_IC_PATH_R) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        if (ICP == LHM_IC_PATH_R && C.F.ic_e) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
         phase_photon_solves<NT>(C, S, cor);
         LHM_TICK(8);
         if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
@@ -1062,7 +1068,7 @@ constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the regis
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
 static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
-    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV];
+    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV], g_smem_runS[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -1401,6 +1407,7 @@ int lhm_setup_batch(lhm_handle* h, int W, const double* consts, const double* g_
     A.consts = consts; A.g_el = g_el; A.nu_syn = nu_syn; A.nu_ic = nu_ic; A.nu_tot = nu_tot;
     A.el_inj = el_inj; A.ext = ext; A.tabd = h->d_tabd; A.tabi = h->d_tabi; A.Ecache = h->d_E;
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
+    A.ptab_path_S = (h->F.ic_path == LHM_IC_PATH_S) ? 1 : 0;
     A.skip_ic_schedule = h->pathG ? 1 : 0;
     A.g_pr = nullptr; A.pr_inj = nullptr;
     if (h->cfg.driver >= 1) {
@@ -1661,8 +1668,13 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
         lc.attrs = at; lc.numAttrs = 1;
         CUDA_TRY(cudaLaunchKernelEx(&lc, run_cluster_kernel, A));
     } else {
-        CUDA_TRY(ensure_dyn_smem(run_kernel, h->smem, g_smem_run[h->device % MAX_DEV]));
-        run_kernel<<<h->W, NT, h->smem, h->stream>>>(A);
+        if (h->F.ic_path == LHM_IC_PATH_S) {
+            CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_S>, h->smem, g_smem_runS[h->device % MAX_DEV]));
+            run_kernel<LHM_IC_PATH_S><<<h->W, NT, h->smem, h->stream>>>(A);
+        } else {
+            CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_R>, h->smem, g_smem_run[h->device % MAX_DEV]));
+            run_kernel<LHM_IC_PATH_R><<<h->W, NT, h->smem, h->stream>>>(A);
+        }
     }
     if (!h->pathG) g_launches++;
     CUDA_TRY(cudaGetLastError());
@@ -1799,6 +1811,7 @@ static int launch_unit(lhm_handle* h, int mode, const double* in0, const double*
     A.Ecache = nullptr;   // function-level calls take B as an argument: always recompute
     A.ptab = h->d_ptab; A.ptab_shared = h->cfg.shared_ic_grids;
     if (ic_path >= 0) A.F.ic_path = ic_path;
+    if (A.F.ic_path != h->F.ic_path) A.ptab = nullptr;      // the table holds the pair constants of the HANDLE's IC path
     A.in0 = in0; A.in1 = in1; A.in2 = in2; A.out0 = out0; A.out1 = out1; A.out2 = out2; A.mode = mode;
     CUDA_TRY(ensure_dyn_smem(unit_kernel, h->smem, g_smem_unit[h->device % MAX_DEV]));
     unit_kernel<<<h->W, NT, h->smem, h->stream>>>(A);

@@ -25,6 +25,8 @@ struct SetupArgs {
     int* tabi;              // [W, L.n_ints]
     double2* ptab;          // IC pair table [W or 1, ic_maxT*IC_PT*2*32] or null
     int ptab_shared;        // 1: every walker has the same g_el / nu_ic / nu_tot, one table (walker 0 builds it)
+    int ptab_path_S;        // 1: the handle runs IC path S -- the same memory holds ITS pair table (ln(gamma - eps) [No, Ng]
+                            //    doubles, then the cut index i* [No, Ng] as unsigned short; phase_ic_S_tab)
     int skip_ic_schedule;   // 1: the handle runs IC path G, nothing reads the per-walker tile schedule of paths R / S
     const double* g_pr;     // [W, Np] or null: proton grid / injection of the LeHaMoC.py driver
     const double* pr_inj;   // [W, Np]
@@ -336,7 +338,30 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
         }
         __syncthreads();
         // per-pair constants {G1, a1}, {a2, a3} in tile order: [tile][pair r][half][lane]
-        if (A.ptab && (!A.ptab_shared || w == 0)) {
+        if (A.ptab && A.ptab_path_S) {
+            if (!A.ptab_shared || w == 0) {
+                double* lndT = reinterpret_cast<double*>(A.ptab + (A.ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)));
+                unsigned short* isT = reinterpret_cast<unsigned short*>(lndT + (size_t)No * Ng);
+                const double lnu0 = 0.5 * T[L.l2nt];
+                const double inv_dl = (double)(Ntar - 1) / (0.5 * T[L.l2nt + Ntar - 1] - lnu0);
+                for (int e = tid; e < No * Ng; e += NT) {
+                    const int o = e / Ng, j = e - o * Ng;
+                    const double eps = T[L.eps + o], nuo = T[L.nic + o], lnu4 = T[L.lnu4 + o];
+                    const double gj = T[L.g + j];
+                    double lnd = 0.0;
+                    int is = 0;
+                    if (gj > eps) {                                     // the expressions of phase_ic_S, to the letter
+                        const double d = gj - eps, rr = 1.0 / d, i4 = T[L.inv4g + j];
+                        const double Av = nuo * rr * i4;
+                        lnd = log(d);
+                        const double lnA = lnu4 - T[L.lg + j] - lnd;
+                        is = ic_s_cut_index(lnA, Av, lnu0, inv_dl, xi, 1, Ntar);
+                    }
+                    lndT[e] = lnd;
+                    isT[e] = (unsigned short)is;
+                }
+            }
+        } else if (A.ptab && (!A.ptab_shared || w == 0)) {
             double2* P = A.ptab + (A.ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32));
             const int nt = TI[L.ic_nt];
             for (int e = tid; e < nt * IC_PT * 32; e += NT) {

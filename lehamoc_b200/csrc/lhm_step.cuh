@@ -624,9 +624,86 @@ __device__ void phase_ic_R(const Ctx& C, Smem& S, Part cta = Part{0, 1}) {
     }
 }
 
+// path S: first target index with nu_i > A (q < 1) -- arithmetic guess on the log-uniform nu_tot grid, then the exact
+// fix-up with the comparison the clamp makes.  x[i * stride] = 1/nu_i.  Used by the time loop and by the set-up table.
+__device__ __forceinline__ int ic_s_cut_index(double lnA, double Av, double lnu0, double inv_dl, const double* x, int stride,
+                                              int Ntar) {
+    int is = (int)floor((lnA - lnu0) * inv_dl) + 1;
+    is = max(0, min(is, Ntar));
+    while (is > 0 && !(Av * x[stride * (is - 1)] >= 1.0)) --is;          // nu_{is-1} > A  -> move left
+    while (is < Ntar && (Av * x[stride * is] >= 1.0)) ++is;              // nu_is <= A      -> move right
+    return is;
+}
+
+// The pair loop of path S from the set-up table.  What a pair needs beyond a reciprocal and a dozen multiply-adds depends
+// on the grids only: ln(gamma - eps) and the cut index i* were tabulated at set-up by the expressions of phase_ic_S's own
+// loop (setup_kernel; a path-S handle keeps them where path R keeps its pair constants), so the pairs of a row carry no
+// logarithm, no search and no data-dependent branch.  U blocks of 32 gammas side by side -- all their table loads are
+// issued before the first is used, nothing between them is conditional -- with the arithmetic and the summation order of
+// the loop it replaces.
+template <int U>
+__device__ __forceinline__ double ic_s_group(const Smem& S, const double* __restrict__ lnd_o,
+                                             const unsigned short* __restrict__ is_o, const double* P0, const double* P1,
+                                             const double* P2, const double* P3, double eps, double nuo, double lnu4,
+                                             int j0, int Ng, double sum) {
+    double lnd[U]; int is[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = min(j0 + 32 * u, Ng - 1);
+        lnd[u] = __ldg(lnd_o + j);
+        is[u] = __ldg(is_o + j);
+    }
+    double inner[U]; bool act[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+        const int j = min(j0 + 32 * u, Ng - 1);
+        const double gj = S.gS[j];
+        act[u] = (j0 + 32 * u < Ng) && (gj > eps);
+        const double d = gj - eps, rr = 1.0 / d, i4 = S.inv4gS[j];
+        const double Gv = 2.0 * eps * eps * rr * i4;
+        const double Av = nuo * rr * i4;
+        const double lnA = lnu4 - S.lgS[j] - lnd[u];
+        const double G1 = 1.0 + Gv, c1 = (1.0 - Gv) + 2.0 * lnA;
+        inner[u] = G1 * P0[is[u]] + Av * (c1 * P1[is[u]] - P2[is[u]] - 2.0 * Av * P3[is[u]]);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u)
+        if (act[u]) sum = fma(S.av[min(j0 + 32 * u, Ng - 1)], inner[u], sum);
+    return sum;
+}
+
+template <int NT>
+__device__ __forceinline__ void phase_ic_S_tab(const Ctx& C, Smem& S) {
+    const Layout& L = C.L;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT / 32;
+    const int Ng = L.Ng, No = L.Ni - 1;
+    const int NtP = pad2(L.Nt);
+    const double* P0 = S.sfx, *P1 = S.sfx + NtP, *P2 = S.sfx + 2 * NtP, *P3 = S.sfx + 3 * NtP;
+    const double* __restrict__ lndT = reinterpret_cast<const double*>(C.P);
+    const unsigned short* __restrict__ isT = reinterpret_cast<const unsigned short*>(lndT + (size_t)No * Ng);
+    constexpr int SU = 8;
+    const int nb = (Ng + 31) >> 5;                               // blocks of 32 gammas in a row
+    const int nfull = (nb / SU) * SU * 32;                       // gammas covered by whole groups of SU blocks
+    const int tail = nb - (nb / SU) * SU;                        // the rest in groups of 4, 2 and 1 blocks
+    for (int o = warp; o < No; o += NW) {
+        const double eps = S.epsS[o], nuo = S.nuoS[o], lnu4 = S.lnu4S[o];
+        const double* __restrict__ lnd_o = lndT + (size_t)o * Ng;
+        const unsigned short* __restrict__ is_o = isT + (size_t)o * Ng;
+        double sum = 0.0;
+        int j0 = lane;
+        for (; j0 < nfull; j0 += 32 * SU)
+            sum = ic_s_group<SU>(S, lnd_o, is_o, P0, P1, P2, P3, eps, nuo, lnu4, j0, Ng, sum);
+        if (tail & 4) { sum = ic_s_group<4>(S, lnd_o, is_o, P0, P1, P2, P3, eps, nuo, lnu4, j0, Ng, sum); j0 += 128; }
+        if (tail & 2) { sum = ic_s_group<2>(S, lnd_o, is_o, P0, P1, P2, P3, eps, nuo, lnu4, j0, Ng, sum); j0 += 64; }
+        if (tail & 1) sum = ic_s_group<1>(S, lnd_o, is_o, P0, P1, P2, P3, eps, nuo, lnu4, j0, Ng, sum);
+        sum = warp_sum(sum);
+        if (lane == 0) S.QIC[o] = kPC.ic_pref * sum;
+    }
+}
+
 // Phase F2, path S: the nu_i sum collapses to four suffix sums because max(F,0) only cuts the sum at the
 // first nu_i > A (F > 0 <=> q < 1) and F is rank-4 separable in (o,gamma) x (i)  (SURVEY.md 7.1b-1).
-template <int NT>
+template <int NT, bool TAB = false>
 __device__ void phase_ic_S(const Ctx& C, Smem& S) {
     const Layout& L = C.L;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, NW = NT / 32;
@@ -637,6 +714,7 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
         double s = 0.0;
         double* P = S.sfx + tid * NtP;
         P[Ntar] = 0.0;
+#pragma unroll 4
         for (int i = Ntar - 1; i >= 0; --i) {
             const double p = S.tri[4 * i + 2];
             const double f = (tid == 0) ? 1.0 : (tid == 1) ? S.tri[4 * i] : (tid == 2) ? S.tri[4 * i + 1] : S.tri[4 * i + 3];
@@ -646,6 +724,7 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
     }
     __syncthreads();
     const double* P0 = S.sfx, *P1 = S.sfx + NtP, *P2 = S.sfx + 2 * NtP, *P3 = S.sfx + 3 * NtP;
+    if (TAB && C.P) { phase_ic_S_tab<NT>(C, S); return; }      // only the kernel compiled for path-S handles (run_kernel<S>)
     const double lnu0 = 0.5 * C.Ts[L.l2nt];                              // ln nu_0
     const double inv_dl = (double)(Ntar - 1) / (0.5 * C.Ts[L.l2nt + Ntar - 1] - lnu0);
     for (int o = warp; o < No; o += NW) {
@@ -658,11 +737,7 @@ __device__ void phase_ic_S(const Ctx& C, Smem& S) {
             const double Gv = 2.0 * eps * eps * rr * i4;
             const double Av = nuo * rr * i4;
             const double lnA = lnu4 - S.lgS[j] - log(d);
-            // first i with nu_i > A (q < 1): arithmetic guess on the log-uniform grid, then exact fix-up
-            int is = (int)floor((lnA - lnu0) * inv_dl) + 1;
-            is = max(0, min(is, Ntar));
-            while (is > 0 && !(Av * S.tri[4 * (is - 1)] >= 1.0)) --is;       // nu_{is-1} > A  -> move left
-            while (is < Ntar && (Av * S.tri[4 * is] >= 1.0)) ++is;           // nu_is <= A      -> move right
+            const int is = ic_s_cut_index(lnA, Av, lnu0, inv_dl, S.tri, 4, Ntar);
             const double G1 = 1.0 + Gv, c1 = (1.0 - Gv) + 2.0 * lnA;
             // sum_i p_i [G1 + q(c1 - 2 ln nu_i - 2 q)],  q = A/nu_i
             double inner = G1 * P0[is] + Av * (c1 * P1[is] - P2[is] - 2.0 * Av * P3[is]);
