@@ -92,8 +92,11 @@ __device__ void no_step_outputs(const RunArgs& A, int w, int Ng, int Nt, int Np)
 #ifndef LHM_MIN_CTAS_S
 #define LHM_MIN_CTAS_S 2
 #endif
-template <int ICP>
-__global__ void __launch_bounds__(NT, ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LHM_MIN_CTAS) run_kernel(RunArgs A) {
+// LIGHT: a run without synchrotron / SSA rows, IC emission, Compton losses and gamma-gamma (Parameters_Test3.txt: adiabatic
+// losses only, 600 steps) is three bidiagonal solves per step -- pure latency.  Compiled without those phases the kernel
+// needs a third of the registers, so three walkers share an SM (shared memory allows no more) instead of two.
+template <int ICP, bool LIGHT = false>
+__global__ void __launch_bounds__(NT, LIGHT ? 3 : (ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LHM_MIN_CTAS)) run_kernel(RunArgs A) {
     extern __shared__ __align__(16) double smem_raw[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x;
@@ -129,26 +132,26 @@ __global__ void __launch_bounds__(NT, ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LH
         // the photon field of the top of the step feeds the Compton losses, the IC emissivity and the gamma-gamma block;
         // the per-gamma vectors feed the synchrotron / SSA rows and the IC pairs: runs with all of those switched off
         // (Parameters_Test3.txt: adiabatic losses only, 600 steps) skip both
-        if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
+        if (!LIGHT && (C.F.ic_l || C.F.ic_e || C.F.gg)) phase_photons<NT>(C, S, true);
         LHM_TICK(1);
-        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        if (!LIGHT && C.F.ic_l) phase_uph<NT>(C, S, nullptr);
         LHM_TICK(2);
         phase_electrons<NT>(C, S);
         LHM_TICK(3);
-        if (C.F.syn_e || C.F.ssa || C.F.ic_e) phase_vectors<NT>(C, S);
+        if (!LIGHT && (C.F.syn_e || C.F.ssa || C.F.ic_e)) phase_vectors<NT>(C, S);
         LHM_TICK(4);
-        phase_syn_rows<NT>(C, S, false);
+        if (!LIGHT) phase_syn_rows<NT>(C, S, false);
         LHM_TICK(5);
-        if (C.F.ic_e) {
+        if (!LIGHT && C.F.ic_e) {
             if (ICP == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT, true>(C, S);
         }
         LHM_TICK(6);
         __syncthreads();
         LHM_TICK(7);
-        if (ICP == LHM_IC_PATH_R && C.F.ic_e) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        if (!LIGHT && ICP == LHM_IC_PATH_R && C.F.ic_e) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
         phase_photon_solves<NT>(C, S, cor);
         LHM_TICK(8);
-        if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
+        if (!LIGHT && C.F.gg) {                                  // LeMoC.py:279-283 / Code.py:265-269
             const double* Lng = S.Ln;
             if (C.F.qee_from_ic) {
                 for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
@@ -1068,7 +1071,7 @@ constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the regis
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
 static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
-    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV], g_smem_runS[MAX_DEV];
+    g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV], g_smem_runS[MAX_DEV], g_smem_runL[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
     do {                                                                               \
@@ -1668,7 +1671,11 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
         lc.attrs = at; lc.numAttrs = 1;
         CUDA_TRY(cudaLaunchKernelEx(&lc, run_cluster_kernel, A));
     } else {
-        if (h->F.ic_path == LHM_IC_PATH_S) {
+        const StepFlags& F = h->F;
+        if (!F.syn_e && !F.ssa && !F.ic_e && !F.ic_l && !F.gg) {
+            CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_R, true>, h->smem, g_smem_runL[h->device % MAX_DEV]));
+            run_kernel<LHM_IC_PATH_R, true><<<h->W, NT, h->smem, h->stream>>>(A);
+        } else if (h->F.ic_path == LHM_IC_PATH_S) {
             CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_S>, h->smem, g_smem_runS[h->device % MAX_DEV]));
             run_kernel<LHM_IC_PATH_S><<<h->W, NT, h->smem, h->stream>>>(A);
         } else {
