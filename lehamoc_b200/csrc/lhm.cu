@@ -84,6 +84,12 @@ __device__ void no_step_outputs(const RunArgs& A, int w, int Ng, int Nt, int Np)
     if (A.Nnu_out) for (int k = threadIdx.x; k < S_ * 50; k += NTH) A.Nnu_out[(size_t)w * S_ * 50 + k] = nan;
 }
 
+#ifndef LHM_G_SYN_TPR
+#define LHM_G_SYN_TPR 2       // lanes per synchrotron / SSA row in stepG_kernel (1: one thread per row, phase_syn_rows)
+#endif
+#ifndef LHM_RUN_SYN_TPR
+#define LHM_RUN_SYN_TPR 2     // the same in run_kernel (per-walker grids: paths R and S)
+#endif
 #ifndef LHM_MIN_CTAS
 #define LHM_MIN_CTAS 2
 #endif
@@ -140,7 +146,11 @@ __global__ void __launch_bounds__(NT, LIGHT ? 3 : (ICP == LHM_IC_PATH_S ? LHM_MI
         LHM_TICK(3);
         if (!LIGHT && (C.F.syn_e || C.F.ssa || C.F.ic_e)) phase_vectors<NT>(C, S);
         LHM_TICK(4);
+#if LHM_RUN_SYN_TPR > 1
+        if (!LIGHT) phase_syn_rows_split<NT>(C, S, Part{0, 1, LHM_RUN_SYN_TPR}, true);
+#else
         if (!LIGHT) phase_syn_rows<NT>(C, S, false);
+#endif
         LHM_TICK(5);
         if (!LIGHT && C.F.ic_e) {
             if (ICP == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT, true>(C, S);
@@ -494,7 +504,11 @@ __global__ void __launch_bounds__(NT, MINB) stepG_kernel(GArgs G) {
         LHM_TICK(3);
         phase_vectors<NT>(C, S);
         LHM_TICK(4);
+#if LHM_G_SYN_TPR > 1
+        phase_syn_rows_split<NT>(C, S, Part{0, 1, LHM_G_SYN_TPR}, true);
+#else
         phase_syn_rows<NT>(C, S, false);
+#endif
         __syncthreads();
         LHM_TICK(5);
         for (int j = tid; j < Ng; j += NT) st[O.N + j] = S.N[j];
@@ -644,7 +658,11 @@ __global__ void __launch_bounds__(NT, MINB) stepG_lh_kernel(GArgs G) {
         LHM_TICK(3);
         phase_vectors<NT>(C, S);
         LHM_TICK(4);
+#if LHM_G_SYN_TPR > 1
+        phase_syn_rows_split<NT>(C, S, Part{0, 1, LHM_G_SYN_TPR}, true);
+#else
         phase_syn_rows<NT>(C, S, false);
+#endif
         phase_syn_protons<NT>(C, S, H);
         __syncthreads();
         LHM_TICK(5);

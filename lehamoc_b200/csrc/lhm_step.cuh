@@ -994,8 +994,12 @@ __device__ void phase_gg(const Ctx& C, Smem& S, const double* Lng, double* agg_o
 // The two row phases for a walker evolved by a CLUSTER (run_cluster_kernel): the rows are dealt round-robin to the CTAs,
 // which leaves a CTA with fewer rows than threads -- so `tpr` lanes share a row (interleaved gamma pairs / sample
 // batches, joined by an xor-shuffle tree): the phase shrinks with the cluster size instead of staying one row long.
+// serp: odd passes deal the rows to the lane groups in reverse order.  Within either family (nu_syn rows, nu_ic rows) the
+// non-zero length of a row falls with its frequency, so a warp that holds the longest rows of one pass holds the shortest of
+// the next -- the warps of a CTA reach the barrier behind the phase together (stepG_kernel: two lanes per row, two passes).
+// Which warp evaluates a row does not enter its arithmetic.
 template <int NT>
-__device__ void phase_syn_rows_split(const Ctx& C, Smem& S, Part part) {
+__device__ void phase_syn_rows_split(const Ctx& C, Smem& S, Part part, bool serp = false) {
     const Layout& L = C.L;
     const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni;
     const bool need_q = C.F.syn_e, need_a = C.F.ssa;
@@ -1006,7 +1010,8 @@ __device__ void phase_syn_rows_split(const Ctx& C, Smem& S, Part part) {
     const double apref = kPC.ssa_pref * C.B;
     const int tpr = part.tpr, grp = threadIdx.x / tpr, sub = threadIdx.x % tpr, ngrp = NT / tpr;
     for (int base = 0; base < nrows; base += part.count * ngrp) {        // the same trip count for every lane of a warp
-        const int row = base + part.rank + part.count * grp;
+        const bool rev = serp && (((base / (part.count * ngrp)) & 1) != 0);
+        const int row = base + part.rank + part.count * (rev ? ngrp - 1 - grp : grp);
         const bool is_syn = row < Ns;
         const int k = is_syn ? row : row - Ns;
         bool act = row < nrows && k != 0 && !(is_syn ? (k > Ns - 2) : (k > Ni - 2));   // [1:] / [1:-1], LeMoC.py:268-276
