@@ -1085,10 +1085,10 @@ static cudaError_t ensure_dyn_smem(K kernel, size_t bytes, std::atomic<size_t>& 
     if (e == cudaSuccess) { while (bytes > cur && !mark.compare_exchange_weak(cur, bytes)) {} }
     return e;
 }
-constexpr int LHM_G_DEFAULT_CTAS = 3;    // resident stepG CTAs per SM the registers are budgeted for (LHM_G_CTAS overrides)
+constexpr int LHM_G_MAX_CTAS = 4;        // most resident stepG CTAs per SM the registers are budgeted for (LHM_G_CTAS overrides)
 constexpr int LHM_G_MAXEV = 16;         // contraction launches timed per run (lhm_last_icg_timing)
 constexpr int MAX_DEV = 64;             // the attribute lives in the function's per-device state
-static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[MAX_DEV], g_smem_icg[MAX_DEV],
+static std::atomic<size_t> g_smem_run[MAX_DEV], g_smem_lh[MAX_DEV], g_smem_lh2[MAX_DEV], g_smem_codelh[MAX_DEV], g_smem_unit[MAX_DEV], g_smem_cor[MAX_DEV], g_smem_stepg[3][MAX_DEV], g_smem_icg[MAX_DEV],
     g_smem_icgu[MAX_DEV], g_smem_stepglh[MAX_DEV], g_smem_stepglh1[MAX_DEV], g_smem_runc[MAX_DEV], g_smem_runS[MAX_DEV], g_smem_runL[MAX_DEV];
 
 #define CUDA_TRY(expr)                                                                 \
@@ -1601,9 +1601,13 @@ static int run_pathG(lhm_handle* h, const RunArgs& A, bool join_cor_late) {
     G.R = A; G.D = h->GD; G.Wpad = (h->W + ICG_NBW - 1) / ICG_NBW * ICG_NBW;
     G.state = h->d_state; G.gp = h->d_gp; G.gav = h->d_gav; G.part = h->d_part;
     G.ggK = h->d_ggK; G.ggT = h->d_ggT; G.ggJ = h->d_ggJ; G.gg_rows = h->gg_rows;
-    static const int minb = [] { const char* e = std::getenv("LHM_G_CTAS"); const int v = e ? std::atoi(e) : 0; return (v >= 2 && v <= 4) ? v : LHM_G_DEFAULT_CTAS; }();
+    // registers budgeted for as many resident half-step CTAs as the shared memory of this grid size admits (2..4); measured
+    // at Test-1 size with the split row phase: 3.95 / 3.69 / 3.62 ms per 1184 walkers for 2 / 3 / 4.  LHM_G_CTAS overrides.
+    static const int minb_env = [] { const char* e = std::getenv("LHM_G_CTAS"); const int v = e ? std::atoi(e) : 0; return (v >= 2 && v <= 4) ? v : 0; }();
+    const int fit = (int)(((size_t)227 * 1024) / (h->smem + 1024));
+    const int minb = minb_env ? minb_env : std::min(LHM_G_MAX_CTAS, std::max(2, fit));
     void (*kern)(GArgs) = minb == 4 ? stepG_kernel<4> : minb == 3 ? stepG_kernel<3> : stepG_kernel<2>;
-    std::atomic<size_t>* smem_slot = &g_smem_stepg[h->device % MAX_DEV];
+    std::atomic<size_t>* smem_slot = &g_smem_stepg[minb - 2][h->device % MAX_DEV];     // one mark per instantiation
     if (h->cfg.driver == 1) {                            // two walkers per SM while their state fits, else one
         const bool two = h->smem * 2 + 2048 <= (size_t)227 * 1024;
         kern = two ? stepG_lh_kernel<2> : stepG_lh_kernel<1>;
