@@ -89,6 +89,26 @@ def test_path_G_batch_sizes_and_determinism(W):
         np.testing.assert_array_equal(N3, N[1:W // 2 + 1])
 
 
+@pytest.mark.parametrize("grid", [61, 87, 101, 122])
+def test_odd_gamma_grids_all_paths(grid):
+    """Grid sizes that are not multiples of two / four (the shipped LeHaMoC Parameters.txt has 183 gammas): the row phases
+    deal gamma pairs to two lanes per row and end on a partial pair.  Every step against the CPU oracle, all three IC paths,
+    walker 0 of a shared-grid batch; the other walkers path G against path R."""
+    import lehamoc_oracle
+    from lehamoc_b200 import LeMoC
+    from lehamoc_b200.presets import test1_walkers
+    sets = [dict(P, grid_g_el=float(grid), grid_nu=57., time_end=3.) for P in test1_walkers(5, seed=11)]
+    ge, ne_ref, sed_ref = lehamoc_oracle.run_script(sets[0])
+    out = {path: LeMoC.run(sets, ic_path=path) for path in ("G", "R", "S")}
+    for path, (_, N, sed) in out.items():
+        assert N.shape[2] == grid == len(ne_ref[0]) and N.shape[1] == len(ne_ref)
+        for s in range(len(ne_ref)):
+            assert_spectra_close(N[0, s], ne_ref[s], f"grid {grid} path {path} n_e step {s + 1}")
+            assert_spectra_close(sed[0, s], sed_ref[s], f"grid {grid} path {path} nuLnu step {s + 1}")
+    assert_spectra_close(out["G"][2], out["R"][2], f"grid {grid}: path G vs path R nuLnu", tol=1e-11)
+    assert_spectra_close(out["G"][1], out["R"][1], f"grid {grid}: path G vs path R n_e", tol=1e-11)
+
+
 def test_path_G_full_size_batch_and_device_packing():
     """The bench's workload: 1184 perturbed Test-1 walkers; walker 0 is Parameters_Test1.txt (live-reference fixture),
     all walkers against path R; the pipelined device-packed API (LeMoC.run_many) gives the same spectra within the
