@@ -331,12 +331,21 @@ class Engine:
         self.run_into(Nd, sd, 0)
         kN, kS = f"N{out_slot}", f"sed{out_slot}"
         Nh_, sh_ = self._pinned(kN, (W, self.Ng)), self._pinned(kS, (W, self.Nt))
-        with torch.cuda.stream(self.stream):
+        # The copies back run on a stream of their own behind an event: other engines may have queued later batches on
+        # the compute stream (LeMoC.run_many: one FIFO stream for all worker threads), and their kernels need not wait
+        # for this batch's 3.4 MB to cross PCIe.  The device buffers are this engine's; it is not launched again before
+        # `done` has been waited for.
+        if getattr(self, "_copy_stream", None) is None:
+            self._copy_stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(self.stream)
+        self._copy_stream.wait_event(ready)
+        with torch.cuda.stream(self._copy_stream):
             self._pin[kN][:W * self.Ng].copy_(Nd.view(-1)[:W * self.Ng], non_blocking=True)
             self._pin[kS][:W * self.Nt].copy_(sd.view(-1)[:W * self.Nt], non_blocking=True)
             done = torch.cuda.Event()
-            done.record(self.stream)
-        done.synchronize()          # this batch only: other engines may have queued later batches on the same stream
+            done.record(self._copy_stream)
+        done.synchronize()          # this batch only
         return Nh_, sh_
 
     def last_icg_timing(self):
