@@ -2109,7 +2109,7 @@ static int fit_logl_impl(lhm_handle* h, const lhm_pack_args* pack, const double*
         CUDA_TRY(cudaMalloc(&h->fit_logl, Wm * sizeof(double)));
         CUDA_TRY(cudaEventCreateWithFlags(&h->fit_up, cudaEventDisableTiming));
     } else {
-        CUDA_TRY(cudaEventSynchronize(h->fit_up));        // an asynchronous predecessor may still be reading the staging buffer
+        if (h->fit_up) CUDA_TRY(cudaEventSynchronize(h->fit_up));   // an asynchronous predecessor may still be reading the staging buffer
     }
     cudaStream_t s = h->stream;
     const size_t o_par = 0, o_ic = (size_t)W * LHM_PACK_NPAR, o_tot = o_ic + Nh, o_ext = o_tot + Nt, o_dop = o_ext + Nt,

@@ -339,6 +339,8 @@ __global__ void __launch_bounds__(NT) setup_kernel(SetupArgs A) {
         __syncthreads();
         // per-pair constants {G1, a1}, {a2, a3} in tile order: [tile][pair r][half][lane]
         if (A.ptab && A.ptab_path_S) {
+            // 10 bytes per pair in the room of path R's 32 (a tile of IC_OG x IC_GB pairs holds IC_PT*2*32 double2)
+            static_assert(IC_PT * 2 * 32 * sizeof(double2) >= (size_t)IC_OG * IC_GB * 10, "path-S pair table must fit path R's");
             if (!A.ptab_shared || w == 0) {
                 double* lndT = reinterpret_cast<double*>(A.ptab + (A.ptab_shared ? 0 : (size_t)w * L.ic_maxT * (IC_PT * 2 * 32)));
                 unsigned short* isT = reinterpret_cast<unsigned short*>(lndT + (size_t)No * Ng);
