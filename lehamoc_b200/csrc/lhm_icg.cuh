@@ -26,6 +26,7 @@ constexpr int ICG_NB = 4;                 // 8-walker blocks per A fragment
 constexpr int ICG_NBW = 8 * ICG_NB;       // walkers per CTA
 constexpr int ICG_GC = 16;                // gammas per task
 constexpr int ICG_NT = 256;               // threads per CTA
+constexpr int ICG_STAGE_BYTES = (ICG_NT / 32) * 2 * 32 * 16;   // per warp: two stages of the 2 x 8 x 2 double2 pair constants of a gamma pair
 constexpr int ICG_AVS = ICG_NBW + 2;      // row stride of the transposed av tile (16-byte aligned rows, spread banks)
 
 struct IcgDims {
@@ -54,7 +55,8 @@ __host__ __device__ inline IcgDims icg_dims(int Ng, int Ni, int Nt) {
     return D;
 }
 __host__ __device__ inline size_t icg_smem_bytes(const IcgDims& D) {
-    return ((size_t)ICG_NBW * D.PSTs + (size_t)D.GCs * ICG_GC * ICG_AVS + (size_t)D.KSs * 16) * sizeof(double) + 16;
+    return ((size_t)ICG_NBW * D.PSTs + (size_t)D.GCs * ICG_GC * ICG_AVS + (size_t)D.KSs * 16) * sizeof(double) + 16
+           + ICG_STAGE_BYTES;
 }
 // split the tiles until they fit `limit` bytes (k-sections first: they also shorten the p rows a warp strides over)
 __host__ inline void icg_choose_sections(IcgDims& D, size_t limit) {
@@ -194,6 +196,10 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
     double* xss = avs + (size_t)D.GCs * ICG_GC * ICG_AVS;   // [4 KSs][4]
     int* counter = reinterpret_cast<int*>(xss + (size_t)D.KSs * 16);
     const int tid = threadIdx.x, lane = tid & 31;
+    // per-warp staging of the pair constants: the 512 bytes of the NEXT gamma pair travel from L2 by cp.async while the
+    // current pair is contracted (a warp used to wait out an L2 round trip at the top of every pair)
+    double2* stg = reinterpret_cast<double2*>(reinterpret_cast<char*>(counter) + 16) + (tid >> 5) * 64;
+    const unsigned stg_s = (unsigned)__cvta_generic_to_shared(stg);
     // block -> (walker block, task split, gamma section, k-section)
     int b = blockIdx.x;
     const int ksec = b % D.nks; b /= D.nks;
@@ -229,14 +235,27 @@ __global__ void __launch_bounds__(ICG_NT, 2) icg_kernel(IcgArgs A) {
 #pragma unroll
         for (int nb = 0; nb < ICG_NB; ++nb) { run[nb][0] = 0.0; run[nb][1] = 0.0; }
         const ushort2* kin = A.kinfo + (size_t)og * (D.NgP / 2) + gc * (ICG_GC / 2);
-        const double2* pt = reinterpret_cast<const double2*>(A.ptg) + ((size_t)(og * D.NgP + gc * ICG_GC) * 8 + row) * 2;
+        const double2* ptl = reinterpret_cast<const double2*>(A.ptg) + (size_t)(og * D.NgP + gc * ICG_GC) * 16 + lane;
+        auto fetch = [&](int pr) {                      // lane l moves double2 l of the pair's 32
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(stg_s + (unsigned)(((pr & 1) * 32 + lane) * 16)),
+                         "l"(ptl + (size_t)pr * 32));
+        };
+        __syncwarp();                                   // the last pair of the previous task has been read by every lane
+        fetch(0);
+        asm volatile("cp.async.commit_group;");
+        ushort2 ki_next = __ldg(kin);
         for (int pr = 0; pr < ICG_GC / 2; ++pr) {
-            const ushort2 ki = __ldg(kin + pr);
+            const ushort2 ki = ki_next;
+            __syncwarp();                               // every lane is done with the stage the next copy overwrites
+            if (pr + 1 < ICG_GC / 2) { fetch(pr + 1); ki_next = __ldg(kin + pr + 1); }
+            asm volatile("cp.async.commit_group;");
+            asm volatile("cp.async.wait_group 1;");
+            __syncwarp();
             const int ks0 = max((int)ki.x, k0), ksc = min(max((int)ki.y, k0), k1);
             if (ks0 >= k1) continue;                    // no active pair among the 8 x 2 in this k-section
             const int j0 = (gc - gc0) * ICG_GC + 2 * pr;                      // gamma index inside the staged section
-            const double2 c0a = __ldg(pt + (size_t)(2 * pr) * 16), c0b = __ldg(pt + (size_t)(2 * pr) * 16 + 1);
-            const double2 c1a = __ldg(pt + (size_t)(2 * pr + 1) * 16), c1b = __ldg(pt + (size_t)(2 * pr + 1) * 16 + 1);
+            const double2* cs = stg + (pr & 1) * 32 + row * 2;
+            const double2 c0a = cs[0], c0b = cs[1], c1a = cs[16], c1b = cs[17];
             double C0[ICG_NB][2], C1[ICG_NB][2];
 #pragma unroll
             for (int nb = 0; nb < ICG_NB; ++nb) { C0[nb][0] = C0[nb][1] = C1[nb][0] = C1[nb][1] = 0.0; }
