@@ -235,14 +235,19 @@ class FitEvaluator:
                 self._engine(req).fit_logl_host(req, th[:, nf], th[:, nf + 1], self._obs,
                                                 out_dev=loc if n_in == b - a else tmp)
                 if n_in != b - a:                           # walkers outside the prior box are not evolved: scatter the rest
-                    idx = torch.from_numpy(np.flatnonzero(inside)).to(loc.device)
-                    loc[:b - a].index_copy_(0, idx, tmp[:n_in])
+                    with torch.cuda.stream(self.eng.stream):
+                        idx = torch.from_numpy(np.flatnonzero(inside)).to(loc.device)
+                        loc[:b - a].index_copy_(0, idx, tmp[:n_in])
         except Exception as e:                              # noqa: BLE001 -- raised below, on every rank
             err = e
-            loc[m:].fill_(1.0)
-        dist.all_gather_into_tensor(full, loc)
-        pin.copy_(full, non_blocking=True)
-        torch.cuda.current_stream(self.device).synchronize()
+            with torch.cuda.stream(self.eng.stream if self.eng is not None else torch.cuda.current_stream(self.device)):
+                loc[m:].fill_(1.0)
+        # gather and copy on the stream the evaluation was queued on (the engine's), whatever stream is current now
+        stream = self.eng.stream if self.eng is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(stream):
+            dist.all_gather_into_tensor(full, loc)
+            pin.copy_(full, non_blocking=True)
+        stream.synchronize()
         host = pin.numpy().reshape(ws, m + 1)
         if err is not None:
             loc[m:].zero_()
