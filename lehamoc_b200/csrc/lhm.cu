@@ -98,11 +98,8 @@ __device__ void no_step_outputs(const RunArgs& A, int w, int Ng, int Nt, int Np)
 #ifndef LHM_MIN_CTAS_S
 #define LHM_MIN_CTAS_S 2
 #endif
-// LIGHT: a run without synchrotron / SSA rows, IC emission, Compton losses and gamma-gamma (Parameters_Test3.txt: adiabatic
-// losses only, 600 steps) is three bidiagonal solves per step -- pure latency.  Compiled without those phases the kernel
-// needs a third of the registers, so three walkers share an SM (shared memory allows no more) instead of two.
-template <int ICP, bool LIGHT = false>
-__global__ void __launch_bounds__(NT, LIGHT ? 3 : (ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LHM_MIN_CTAS)) run_kernel(RunArgs A) {
+template <int ICP>
+__global__ void __launch_bounds__(NT, ICP == LHM_IC_PATH_S ? LHM_MIN_CTAS_S : LHM_MIN_CTAS) run_kernel(RunArgs A) {
     extern __shared__ __align__(16) double smem_raw[];
     const int w = blockIdx.x;
     const int tid = threadIdx.x;
@@ -138,30 +135,30 @@ __global__ void __launch_bounds__(NT, LIGHT ? 3 : (ICP == LHM_IC_PATH_S ? LHM_MI
         // the photon field of the top of the step feeds the Compton losses, the IC emissivity and the gamma-gamma block;
         // the per-gamma vectors feed the synchrotron / SSA rows and the IC pairs: runs with all of those switched off
         // (Parameters_Test3.txt: adiabatic losses only, 600 steps) skip both
-        if (!LIGHT && (C.F.ic_l || C.F.ic_e || C.F.gg)) phase_photons<NT>(C, S, true);
+        if (C.F.ic_l || C.F.ic_e || C.F.gg) phase_photons<NT>(C, S, true);
         LHM_TICK(1);
-        if (!LIGHT && C.F.ic_l) phase_uph<NT>(C, S, nullptr);
+        if (C.F.ic_l) phase_uph<NT>(C, S, nullptr);
         LHM_TICK(2);
         phase_electrons<NT>(C, S);
         LHM_TICK(3);
-        if (!LIGHT && (C.F.syn_e || C.F.ssa || C.F.ic_e)) phase_vectors<NT>(C, S);
+        if (C.F.syn_e || C.F.ssa || C.F.ic_e) phase_vectors<NT>(C, S);
         LHM_TICK(4);
 #if LHM_RUN_SYN_TPR > 1
-        if (!LIGHT) phase_syn_rows_split<NT>(C, S, Part{0, 1, LHM_RUN_SYN_TPR}, true);
+        phase_syn_rows_split<NT>(C, S, Part{0, 1, LHM_RUN_SYN_TPR}, true);
 #else
-        if (!LIGHT) phase_syn_rows<NT>(C, S, false);
+        phase_syn_rows<NT>(C, S, false);
 #endif
         LHM_TICK(5);
-        if (!LIGHT && C.F.ic_e) {
+        if (C.F.ic_e) {
             if (ICP == LHM_IC_PATH_R) phase_ic_R<NT>(C, S); else phase_ic_S<NT, true>(C, S);
         }
         LHM_TICK(6);
         __syncthreads();
         LHM_TICK(7);
-        if (!LIGHT && ICP == LHM_IC_PATH_R && C.F.ic_e) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
+        if (ICP == LHM_IC_PATH_R && C.F.ic_e) { phase_ic_finish_R<NT>(C, S); __syncthreads(); }
         phase_photon_solves<NT>(C, S, cor);
         LHM_TICK(8);
-        if (!LIGHT && C.F.gg) {                                  // LeMoC.py:279-283 / Code.py:265-269
+        if (C.F.gg) {                                            // LeMoC.py:279-283 / Code.py:265-269
             const double* Lng = S.Ln;
             if (C.F.qee_from_ic) {
                 for (int k = tid; k < Ni; k += NT) S.Lic[k] = log10(S.pic[k] / C.V);
@@ -189,6 +186,109 @@ __global__ void __launch_bounds__(NT, LIGHT ? 3 : (ICP == LHM_IC_PATH_S ? LHM_MI
             }
             __syncthreads();
         }
+    }
+}
+
+// Runs without synchrotron / SSA rows, IC emission, Compton losses and gamma-gamma (Parameters_Test3.txt: adiabatic losses
+// only, 600 steps): nothing couples the electron equation and the two photon equations any more, so each is a chain of
+// (coefficient pass, warp back-substitution) per step that ONE WARP advances on its own -- three warps per walker, no CTA
+// barrier inside the time loop, 19 KB of shared memory and 85 registers, eight walkers per SM (1184 walkers: one wave).
+// The coefficient expressions are those of phase_electrons / phase_photon_solves with the switched-off terms left out
+// (they add +0.0 to positive numbers); the output goes through phase_photons like everywhere else.
+constexpr int NT_LIGHT = 96;
+__global__ void __launch_bounds__(NT_LIGHT, 8) run_light_kernel(RunArgs A) {
+    extern __shared__ __align__(16) double smem_raw[];
+    const int w = blockIdx.x;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    Ctx C;
+    load_ctx(C, A.L, A.F, A.consts, A.tabd, A.tabi, nullptr, nullptr, 0, w);
+    const Layout& L = C.L;
+    const int Ng = L.Ng, Ns = L.Ns, Ni = L.Ni, Nt = L.Nt;
+    double* p = smem_raw;
+    auto take = [&](int n) { double* r = p; p += n; return r; };
+    double* N = take(pad2(Ng)); double* cpE = take(pad2(Ng)); double* dpE = take(pad2(Ng));
+    double* psyn = take(pad2(Ns)); double* cpS = take(pad2(Ns)); double* dpS = take(pad2(Ns));
+    double* pic = take(pad2(Ni)); double* cpI = take(pad2(Ni)); double* dpI = take(pad2(Ni));
+    Smem S = {};                                            // what phase_photons reads and writes at output time
+    S.psyn = psyn; S.pic = pic; S.Lsyn = cpS; S.Lic = cpI; S.n = cpE;
+    const int nsteps = (int)A.consts[(size_t)w * LHM_NCONST + LHM_C_NSTEPS];
+    if (nsteps < 1) { no_step_outputs<NT_LIGHT>(A, w, Ng, Nt, 0); return; }
+    for (int j = tid; j < Ng; j += NT_LIGHT) N[j] = (j == 0 || j == Ng - 1) ? LHM_SENT : C.T[L.elinj + j];   // LeMoC.py:172-183
+    for (int k = tid; k < Ns; k += NT_LIGHT) psyn[k] = LHM_SENT;
+    for (int k = tid; k < Ni; k += NT_LIGHT) pic[k] = LHM_SENT;
+    __syncthreads();
+    long long tprev = clock64();
+    auto tick = [&](int i) {
+        if (A.prof && tid == 0) { const long long now = clock64(); atomicAdd(A.prof + i, (unsigned long long)(now - tprev)); tprev = now; }
+    };
+    const double cc = kPC.c;
+    double t = C.tinit;
+    for (int step = 0; step < nsteps; ++step) {
+        t += C.dt;                                               // LeMoC.py:198-201
+        C.Rad = C.R0 + C.Vexp * (t - C.tinit);
+        C.B = (C.m == 0.0) ? C.B0 : C.B0 * pow(C.R0 / C.Rad, C.m);
+        C.V = volume_of(C.Rad);
+        const double dt = C.dt;
+        const double b_ad = C.F.ad ? C.Vexp / C.Rad : 0.0;
+        tick(0);
+        if (warp == 0) {                                         // electrons: phase_electrons (LeMoC.py:206-247)
+            const int n = Ng - 2;
+            const double b_syn = C.F.syn_l ? kPC.bsyn_pref * (C.B * C.B) : 0.0;
+            const double esc = cc / C.Rad * (double)C.F.esc;
+            for (int j = lane; j < n; j += 32) {
+                const double smj = C.Ts[L.sm + j], spj = C.Ts[L.sp + j];
+                const double syn_m = b_syn * smj, syn_p = b_syn * spj;
+                const double ic_m = 0.0, ic_p = 0.0;
+                const double ad_m = b_ad * C.Ts[L.am + j], ad_p = b_ad * C.Ts[L.ap + j];
+                const double V2 = 1.0 + dt * (esc + syn_m + ic_m + ad_m);
+                const double V3 = -dt * (syn_p + ic_p + ad_p);
+                double d = N[j + 1];
+                if (C.F.inj) d += C.T[L.elinj + j + 1] * dt;
+                cpE[j] = V3 / V2;
+                dpE[j] = d / V2;
+            }
+            __syncwarp();
+            backsub_warp(cpE, dpE, N + 1, n);
+            __syncwarp();
+        } else {                                                 // photons: phase_photon_solves (LeMoC.py:267-277)
+            const bool syn = (warp == 1);
+            const int n = (syn ? Ns : Ni) - 2;
+            double* ph = syn ? psyn : pic;
+            double* cp = syn ? cpS : cpI;
+            double* dp = syn ? dpS : dpI;
+            const double* am = C.T + (syn ? L.asm_ : 0);
+            const double esc = cc / C.Rad;
+            for (int j = lane; j < n; j += 32) {
+                const double a_m = syn ? am[j] : C.Ts[L.aim + j], a_p = syn ? C.T[L.asp_ + j] : C.Ts[L.aip + j];
+                const double V2 = 1.0 + dt * (esc + b_ad * a_m);
+                const double V3 = -dt * (b_ad * a_p);
+                const double d = ph[j + 1];
+                cp[j] = V3 / V2;
+                dp[j] = d / V2;
+            }
+            __syncwarp();
+            if (C.F.ad) backsub_warp(cp, dp, ph + 1, n);
+            else for (int j = lane; j < n; j += 32) ph[j + 1] = dp[j];   // V3 == 0: diagonal systems
+            __syncwarp();
+        }
+        const bool last = (step == nsteps - 1);
+        const int slot = A.snapshots > 0 ? step : 0;
+        if ((A.snapshots > 0 && step < A.snapshots) || (A.snapshots == 0 && last)) {
+            __syncthreads();                                     // the three populations of this step are complete
+            const int S_ = A.snapshots > 0 ? A.snapshots : 1;
+            if (A.N_out) {
+                double* o = A.N_out + ((size_t)w * S_ + slot) * Ng;
+                for (int j = tid; j < Ng; j += NT_LIGHT) o[j] = N[j] / C.V;
+            }
+            if (A.sed_out) {
+                phase_photons<NT_LIGHT>(C, S, false);            // overwrites solver scratch, rebuilt by the next step
+                double* o = A.sed_out + ((size_t)w * S_ + slot) * Nt;
+                for (int k = tid; k < Nt; k += NT_LIGHT)
+                    o[k] = S.n[k] * C.Ts[L.hnu2 + k] * 4.0 * M_PI / 3.0 * (C.Rad * C.Rad) * kPC.c;
+            }
+            __syncthreads();
+        }
+        tick(3);                                                 // thread 0: the electron chain (the longest of the three)
     }
 }
 
@@ -1695,8 +1795,9 @@ static int run_common(lhm_handle* h, double* N_el_out, double* nuLnu_out, double
     } else {
         const StepFlags& F = h->F;
         if (!F.syn_e && !F.ssa && !F.ic_e && !F.ic_l && !F.gg) {
-            CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_R, true>, h->smem, g_smem_runL[h->device % MAX_DEV]));
-            run_kernel<LHM_IC_PATH_R, true><<<h->W, NT, h->smem, h->stream>>>(A);
+            const size_t sl = smem_light_bytes(h->L);
+            CUDA_TRY(ensure_dyn_smem(run_light_kernel, sl, g_smem_runL[h->device % MAX_DEV]));
+            run_light_kernel<<<h->W, NT_LIGHT, sl, h->stream>>>(A);
         } else if (h->F.ic_path == LHM_IC_PATH_S) {
             CUDA_TRY(ensure_dyn_smem(run_kernel<LHM_IC_PATH_S>, h->smem, g_smem_runS[h->device % MAX_DEV]));
             run_kernel<LHM_IC_PATH_S><<<h->W, NT, h->smem, h->stream>>>(A);

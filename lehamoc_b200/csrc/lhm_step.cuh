@@ -117,6 +117,12 @@ __device__ inline void carve(Smem& S, double* base, const Layout& L, int NW) {
     S.ti1 = S.ti0 + mt;
 }
 
+// Shared memory of run_light_kernel (runs without row, IC and gamma-gamma phases): the three populations and the scratch of
+// their three solves; the output's scratch (Lsyn, Lic, n) lives on solver scratch that is dead by then.
+__host__ __device__ inline size_t smem_light_bytes(const Layout& L) {
+    return (size_t)(pad2(L.Ng) + pad2(L.Ns) + pad2(L.Ni)) * 3 * sizeof(double);
+}
+
 // Per-walker context: table pointers + scalars of the current step
 struct Ctx {
     Layout L;
